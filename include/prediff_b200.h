@@ -1,0 +1,144 @@
+/* prediff_b200 - C ABI of the B200-native PreDiff sampling path.
+ *
+ * Drop-in boundary for the one hot path of gaozhihan/PreDiff:
+ *   LatentDiffusion.p_sample_loop -> CuboidTransformerUNet.forward -> AutoencoderKL.encode / decode.
+ * Every entry point takes plain pointers and sizes (no torch types), returns 0 on success and a negative
+ * PD_ERR_* code on failure (never throws; message via pd_last_error()), and enqueues its work on the CUDA
+ * stream passed as `stream` (a cudaStream_t; NULL = legacy default stream). Device pointers must be 16-byte
+ * aligned. There is no CPU fallback: on a non-sm_100 device every call fails with PD_ERR_ARCH.
+ *
+ * Tensor layouts are channels-last, fp32 unless stated:
+ *   latent   z, cond : [B][T][H][W][C]      (the reference's "NTHWC", latent_diffusion.py:394-402)
+ *   VAE pixel frames : [N][H][W]            (== the reference's (N,1,H,W))
+ *   VAE latents      : [N][H/8][W/8][C]     (the reference's (N,C,h,w) permuted; the Python shim permutes views)
+ */
+#ifndef PREDIFF_B200_H
+#define PREDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_OK 0
+#define PD_ERR_CUDA (-1)
+#define PD_ERR_SHAPE (-2)
+#define PD_ERR_ARCH (-3)
+#define PD_ERR_WEIGHT (-4)
+#define PD_ERR_ARG (-5)
+#define PD_ERR_STATE (-6)
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+/* Checks the current device is sm_100, resolves driver entry points, raises kernel smem limits. Idempotent. */
+int pd_init(void);
+/* Message of the last failure on the calling thread ("" if none). */
+const char* pd_last_error(void);
+const char* pd_version(void);
+
+/* ---- CuboidTransformerUNet (reference: src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py) -- */
+typedef struct pd_unet pd_unet;
+typedef struct pd_unet_config {
+    int32_t t_in, t_out;   /* input_shape[0], target_shape[0]                       (cfg.yaml:158-159: 7, 6)   */
+    int32_t h, w, c;       /* latent H, W, C                                         (16, 16, 64)               */
+    int32_t base_units;    /* cfg.yaml:160 (256); level-1 width is 2*base_units                                 */
+    int32_t depth[2];      /* cfg.yaml:171 ([4, 4]); exactly two levels                                          */
+    int32_t num_heads;     /* cfg.yaml:163 (4)                                                                   */
+    int32_t max_batch;     /* largest batch a forward will be asked for (sizes the activation arena)             */
+} pd_unet_config;
+
+int pd_unet_create(const pd_unet_config* cfg, pd_unet** out);
+void pd_unet_destroy(pd_unet* m);
+/* Number of state_dict entries the model expects; name/shape of entry i (reference key names, e.g.
+ * "down_self_blocks.0.1.attn_l.2.qkv.weight"). shape has up to 5 dims; returns ndim. */
+int pd_unet_num_weights(const pd_unet* m);
+int pd_unet_weight_info(const pd_unet* m, int i, const char** name, int64_t shape[5]);
+/* Copies one fp32 tensor (host or device pointer, contiguous, reference layout) into the model. */
+int pd_unet_load_weight(pd_unet* m, const char* name, const float* data, const int64_t* shape, int ndim);
+/* Repacks all weights into kernel layouts (bf16, K-major, tap-major convs). Fails if any weight is missing. */
+int pd_unet_finalize(pd_unet* m);
+/* forward(x, t, cond) -> eps   (cuboid_transformer_unet.py:406-493)
+ *   x [B][t_out][h][w][c], t [B] int64, cond [B][t_in][h][w][c]  ->  out [B][t_out][h][w][c]; all device ptrs. */
+int pd_unet_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
+                    void* stream);
+
+/* ---- AutoencoderKL (reference: src/prediff/taming/autoencoder_kl.py:80-113, vae.py:70-86,150-166) --------- */
+typedef struct pd_vae pd_vae;
+typedef struct pd_vae_config {
+    int32_t in_channels;          /* 1 */
+    int32_t out_channels;         /* 1 */
+    int32_t latent_channels;      /* 64 */
+    int32_t block_out_channels[4];/* 128, 256, 512, 512 */
+    int32_t layers_per_block;     /* 2 */
+    int32_t norm_num_groups;      /* 32 */
+    int32_t h, w;                 /* pixel frame size (128, 128) */
+    int32_t max_frames;           /* largest N per encode/decode call */
+} pd_vae_config;
+
+int pd_vae_create(const pd_vae_config* cfg, pd_vae** out);
+void pd_vae_destroy(pd_vae* m);
+int pd_vae_num_weights(const pd_vae* m);
+int pd_vae_weight_info(const pd_vae* m, int i, const char** name, int64_t shape[5]);
+int pd_vae_load_weight(pd_vae* m, const char* name, const float* data, const int64_t* shape, int ndim);
+int pd_vae_finalize(pd_vae* m);
+/* encode: x [N][H][W] -> moments [N][H/8][W/8][2*latent] (mean | logvar), i.e. quant_conv(Encoder(x)). */
+int pd_vae_encode(pd_vae* m, const float* x, float* moments, int n, void* stream);
+/* decode: z [N][H/8][W/8][latent] -> [N][H][W], i.e. Decoder(post_quant_conv(z)). */
+int pd_vae_decode(pd_vae* m, const float* z, float* out, int n, void* stream);
+
+/* ---- sampler (reference: latent_diffusion.py:228-278,553-684; diffusion/utils.py:17-70) -------------------- */
+typedef struct pd_sampler pd_sampler;
+#define PD_MODE_DDPM 0  /* the reference's ancestral p_sample_loop, t = timesteps-1 .. 0                        */
+#define PD_MODE_DDIM 1  /* DDIM on make_ddim_timesteps('uniform', n, T) with eta        */
+
+/* Builds the beta schedule ("linear": linspace(sqrt(start), sqrt(end), T)^2 in float64) and keeps the per-step
+ * coefficient table resident on the device. */
+int pd_sampler_create(int num_timesteps, double linear_start, double linear_end, pd_sampler** out);
+void pd_sampler_destroy(pd_sampler* s);
+/* Copies one of the reference's registered schedule buffers (by its buffer name, e.g. "alphas_cumprod",
+ * "posterior_mean_coef1") to host memory `out[num_timesteps]` - for parity tests against register_schedule. */
+int pd_sampler_get_buffer(const pd_sampler* s, const char* name, float* out);
+/* Runs the whole denoising loop on the device:
+ *   z     [B][t_out][h][w][c]  in: z_T, out: z_0 (updated in place)
+ *   cond  [B][t_in][h][w][c]
+ *   noise NULL (DDIM eta=0) or [n_steps][B*t_out*h*w*c] pre-generated N(0,1) (step k uses slice k)
+ *   mode PD_MODE_*; n_steps: DDPM = number of ancestral steps (t = n_steps-1..0), DDIM = number of DDIM steps.
+ * The loop is captured into a CUDA graph on first use for a given (unet, batch) and replayed. */
+int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int mode,
+                   int n_steps, float eta, void* stream);
+/* One reference p_sample step at integer timestep t (all batch rows share t): z <- p_sample(z, cond, t). */
+int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
+                        void* stream);
+
+/* ---- kernel-level entry points (used by the parity tests; same kernels the models launch) ------------------ */
+/* out = epilogue(conv/linear(A, Wt)): A bf16 [samples][D][H][W][C], Wt bf16 [N][kt*kh*kw*C], zero padding k/2.
+ * bias[N], rowvec[samples][N], residual/out_f32 fp32 [M][N], out_bf16 bf16 [M][N]; any of them may be NULL.
+ * act: 0 none, 1 GELU(erf), 2 SiLU. block_n: 0 = heuristic, else 32/64/128/256. */
+int pd_op_conv_gemm(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt, int kh,
+                    int kw, int N, const float* bias, const float* rowvec, const float* residual, float* out_f32,
+                    void* out_bf16, int act, int block_n, void* stream);
+int pd_op_group_norm(const float* x, const float* gamma, const float* beta, void* y_bf16, int S, int R, int C, int G,
+                     float eps, int silu, void* stream);
+int pd_op_layer_norm(const float* x, const float* gamma, const float* beta, void* y_bf16, int P, int C, float eps,
+                     void* stream);
+int pd_op_patch_merge_ln(const float* x, const float* gamma, const float* beta, void* y_bf16, int BT, int H, int W,
+                         int C, float eps, void* stream);
+int pd_op_axial_attention(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W,
+                          int C, int heads, int axis, void* stream);
+int pd_op_sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef8,
+                         int64_t n, void* stream);
+int pd_op_timestep_embedding(const int64_t* t, float* out, int B, int dim, void* stream);
+int pd_op_small_linear(const float* in, const float* W, const float* bias, float* out, int B, int K, int N, int in_silu,
+                       int out_silu, void* stream);
+int pd_op_pack_conv(const float* w, void* out_bf16, int Co, int Ci, int taps, int Cipad, void* stream);
+int pd_op_pack_linear(const float* w, void* out_bf16, int N, int K, int Kpad, void* stream);
+int pd_op_upsample2x_cast(const float* x, void* y_bf16, int F, int H, int W, int C, void* stream);
+int pd_op_parity_split_cast(const float* x, void* y_bf16, int F, int H, int W, int C, void* stream);
+/* stride-2 3x3 conv with the reference's (0,1,0,1) zero pad (taming/resnet.py:183-188) on the parity-split input */
+int pd_op_conv_s2_gemm(const void* planes_bf16, const void* Wt_bf16, int F, int Ho, int Wo, int C, int N,
+                       const float* bias, float* out_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PREDIFF_B200_H */

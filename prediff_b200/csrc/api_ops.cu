@@ -1,0 +1,113 @@
+// extern "C" kernel-level entry points (include/prediff_b200.h): the same launchers the model programs use,
+// exposed so the parity tests can drive every kernel in isolation through the C ABI.
+#include "../../include/prediff_b200.h"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+using namespace pd;
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+}  // namespace
+
+extern "C" {
+
+int pd_init(void) { return gemm_init(); }
+const char* pd_last_error(void) { return last_error(); }
+const char* pd_version(void) { return "prediff_b200 0.1 (sm_100a)"; }
+
+int pd_op_conv_gemm(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw, int N,
+                    const float* bias, const float* rowvec, const float* residual, float* out_f32, void* out_bf16,
+                    int act, int block_n, void* stream) {
+    PD_TRY(gemm_init());
+    PD_CHECK(kt * kh * kw <= kMaxTaps, PD_ERR_SHAPE, "pd_op_conv_gemm: window too large");
+    GemmGeom g = GemmGeom::conv(samples, D, H, W, C, kt, kh, kw);
+    GemmEpilogue e;
+    e.bias = bias; e.rowvec = rowvec; e.residual = residual; e.out_f32 = out_f32;
+    e.out_bf16 = static_cast<bf16*>(out_bf16); e.act = act;
+    GemmOp op;
+    PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e, block_n));
+    return gemm_launch(op, S(stream));
+}
+
+int pd_op_conv_s2_gemm(const void* planes, const void* Wt, int F, int Ho, int Wo, int C, int N, const float* bias,
+                       float* out_f32, void* stream) {
+    PD_TRY(gemm_init());
+    GemmGeom g = GemmGeom::conv_s2_planes(F, Ho, Wo, C);
+    GemmEpilogue e;
+    e.bias = bias; e.out_f32 = out_f32;
+    GemmOp op;
+    PD_TRY(gemm_make(&op, static_cast<const bf16*>(planes), g, static_cast<const bf16*>(Wt), N, e));
+    return gemm_launch(op, S(stream));
+}
+
+int pd_op_group_norm(const float* x, const float* gamma, const float* beta, void* y, int Sn, int R, int C, int G,
+                     float eps, int silu, void* stream) {
+    PD_TRY(gemm_init());
+    double* sums = nullptr;
+    const size_t bytes = (size_t)Sn * G * 2 * sizeof(double);
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sums), bytes, S(stream)));
+    PD_CUDA(cudaMemsetAsync(sums, 0, bytes, S(stream)));
+    int rc = gn_stats(x, sums, Sn, R, C, G, S(stream));
+    if (rc == PD_OK) rc = gn_apply(x, sums, gamma, beta, static_cast<bf16*>(y), Sn, R, C, G, eps, silu, S(stream));
+    cudaFreeAsync(sums, S(stream));
+    return rc;
+}
+
+int pd_op_layer_norm(const float* x, const float* gamma, const float* beta, void* y, int P, int C, float eps,
+                     void* stream) {
+    PD_TRY(gemm_init());
+    return layer_norm(x, gamma, beta, static_cast<bf16*>(y), P, C, eps, S(stream));
+}
+
+int pd_op_patch_merge_ln(const float* x, const float* gamma, const float* beta, void* y, int BT, int H, int W, int C,
+                         float eps, void* stream) {
+    PD_TRY(gemm_init());
+    return patch_merge_ln(x, gamma, beta, static_cast<bf16*>(y), BT, H, W, C, eps, S(stream));
+}
+
+int pd_op_axial_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C,
+                          int heads, int axis, void* stream) {
+    PD_TRY(gemm_init());
+    return axial_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T, H, W, C, heads, axis,
+                           S(stream));
+}
+
+int pd_op_sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef8,
+                         int64_t n, void* stream) {
+    PD_TRY(gemm_init());
+    return sampler_update(z, eps, noise, guide, coef8, n, S(stream));
+}
+
+int pd_op_timestep_embedding(const int64_t* t, float* out, int B, int dim, void* stream) {
+    PD_TRY(gemm_init());
+    return timestep_embedding(t, out, B, dim, S(stream));
+}
+
+int pd_op_small_linear(const float* in, const float* W, const float* bias, float* out, int B, int K, int N, int in_silu,
+                       int out_silu, void* stream) {
+    PD_TRY(gemm_init());
+    return small_linear(in, W, bias, out, B, K, N, in_silu, out_silu, S(stream));
+}
+
+int pd_op_pack_conv(const float* w, void* out, int Co, int Ci, int taps, int Cipad, void* stream) {
+    PD_TRY(gemm_init());
+    return pack_conv(w, static_cast<bf16*>(out), Co, Ci, taps, Cipad, S(stream));
+}
+
+int pd_op_pack_linear(const float* w, void* out, int N, int K, int Kpad, void* stream) {
+    PD_TRY(gemm_init());
+    return pack_linear(w, static_cast<bf16*>(out), N, K, Kpad, S(stream));
+}
+
+int pd_op_upsample2x_cast(const float* x, void* y, int F, int H, int W, int C, void* stream) {
+    PD_TRY(gemm_init());
+    return upsample2x_cast(x, static_cast<bf16*>(y), F, H, W, C, S(stream));
+}
+
+int pd_op_parity_split_cast(const float* x, void* y, int F, int H, int W, int C, void* stream) {
+    PD_TRY(gemm_init());
+    return parity_split_cast(x, static_cast<bf16*>(y), F, H, W, C, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Common host/device helpers for the prediff_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/prediff_b200.h"
+
+namespace pd {
+
+// ---- error plumbing -------------------------------------------------------------------------
+// Every extern "C" entry returns int (0 = ok, negative = failure) and never throws; the message of
+// the last failure on this thread is kept for pd_last_error().
+// error codes: PD_OK / PD_ERR_* from the public header
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define PD_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::pd::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return PD_ERR_CUDA;                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define PD_CHECK(cond, code, ...)                  \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::pd::set_error(__VA_ARGS__);          \
+            return (code);                         \
+        }                                          \
+    } while (0)
+
+#define PD_TRY(expr)                  \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != 0) return _rc;     \
+    } while (0)
+
+#define PD_LAUNCH_CHECK() PD_CUDA(cudaGetLastError())
+
+typedef __nv_bfloat16 bf16;
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(t);
+}
+
+}  // namespace pd

@@ -1,0 +1,330 @@
+// tcgen05 + TMA implicit-GEMM kernel (see gemm.cuh). One 128 x BN output tile per CTA, warp-specialised:
+//   warp 0    : TMA producer (one elected lane) - A tile through a rank-5 tensor map with per-tap shifts,
+//               B (weights) through a rank-2 map; STAGES-deep mbarrier ring
+//   warp 1    : allocates TMEM, one lane issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM)
+//   warps 2-5 : epilogue - tcgen05.ld 32x32 chunks, transpose through smem, fused bias / time-embedding /
+//               GELU / residual, coalesced 128-bit stores of fp32 and/or bf16
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include <cudaTypedefs.h>
+#include <cstdlib>
+
+namespace pd {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBBytes = BN * kGemmBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    // BN=256: 4 x 48 KB (1 CTA/SM); BN=128: 3 x 32 KB (2 CTAs/SM); BN<=64: 4 stages (2+ CTAs/SM)
+    static constexpr int kStages = (BN == 128) ? 3 : 4;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ GemmKernelParams p) {
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tile = blockIdx.x;
+    const int n0 = blockIdx.y * BN;
+    const int sample = tile / p.tiles_per_sample;
+    const int p0 = (tile - sample * p.tiles_per_sample) * kGemmBlockM;
+    const int num_k = p.ntaps * p.cblks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(tmem_full_bar, 1);
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int z0 = p0 / p.HW;
+            const int rem = p0 - z0 * p.HW;
+            const int y0 = rem / p.W;
+            const int x0 = rem - y0 * p.W;
+            int tap = 0, cb = 0;
+            for (int it = 0; it < num_k; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + s * C::kStageBytes;
+                ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
+                ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
+                                 z0 + p.dz[tap], sample);
+                ptx::tma_load_2d(sa + kABytes, &tmap_b, &full_bar[s], it * kGemmBlockK, n0);
+                if (++cb == p.cblks) { cb = 0; ++tap; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kGemmBlockM, BN);
+            for (int it = 0; it < num_k; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(smem + s * C::kStageBytes);
+                const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                    const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
+                    const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
+                    ptx::umma_f16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+            }
+            ptx::umma_commit(tmem_full_bar);      // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
+        const int q = warp & 3;
+        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);  // aliases pipeline stage 0
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after();
+        const int ldo = p.ldo;
+        const int sub_row = lane >> 3;
+        const int c4 = (lane & 7) * 4;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+            ptx::tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(stage + lane * 36);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            __syncwarp();
+            const int col = n0 + c * 32 + c4;
+            float4 addv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) addv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            if (p.rowvec) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)sample * p.N + col));
+                addv.x += r.x; addv.y += r.y; addv.z += r.z; addv.w += r.w;
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = it * 4 + sub_row;
+                const int prow = p0 + q * 32 + row;
+                if (prow < p.rows_per_sample) {
+                    float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
+                    a.x += addv.x; a.y += addv.y; a.z += addv.z; a.w += addv.w;
+                    if (p.act == ACT_GELU) {
+                        a.x = gelu_erf_f(a.x); a.y = gelu_erf_f(a.y); a.z = gelu_erf_f(a.z); a.w = gelu_erf_f(a.w);
+                    } else if (p.act == ACT_SILU) {
+                        a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
+                    }
+                    const size_t off = ((size_t)sample * p.rows_per_sample + prow) * ldo + col;
+                    if (p.residual) {
+                        const float4 r = *reinterpret_cast<const float4*>(p.residual + off);
+                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                    }
+                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
+                    if (p.out_bf16) {
+                        uint2 o;
+                        o.x = pack_bf16x2(a.x, a.y);
+                        o.y = pack_bf16x2(a.z, a.w);
+                        *reinterpret_cast<uint2*>(p.out_bf16 + off) = o;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+bool g_inited = false;
+
+template <int BN>
+int set_smem_attr() {
+    PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    return PD_OK;
+}
+
+template <int BN>
+int launch_bn(const GemmOp& op, cudaStream_t stream) {
+    gemm_tc_kernel<BN><<<dim3(op.grid_x, op.grid_y), kThreads, Cfg<BN>::kSmem, stream>>>(op.tmap_a, op.tmap_b, op.p);
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
+
+}  // namespace
+
+int gemm_init() {
+    if (g_inited) return PD_OK;
+    int dev = 0;
+    PD_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    PD_CHECK(prop.major == 10, PD_ERR_ARCH,
+             "prediff_b200 requires an sm_100 (Blackwell B200) device; found sm_%d%d (%s). There is no fallback path.",
+             prop.major, prop.minor, prop.name);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PD_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, PD_ERR_CUDA,
+             "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    PD_TRY(set_smem_attr<32>());
+    PD_TRY(set_smem_attr<64>());
+    PD_TRY(set_smem_attr<128>());
+    PD_TRY(set_smem_attr<256>());
+    g_inited = true;
+    return PD_OK;
+}
+
+int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int N, const GemmEpilogue& e,
+              int force_block_n) {
+    PD_TRY(gemm_init());
+    PD_CHECK(A && Wt, PD_ERR_ARG, "gemm_make: null operand");
+    PD_CHECK(g.C > 0 && g.C % kGemmBlockK == 0, PD_ERR_SHAPE, "gemm: channels per tap (%d) must be a multiple of 64",
+             g.C);
+    PD_CHECK(N > 0 && N % 32 == 0, PD_ERR_SHAPE, "gemm: N (%d) must be a multiple of 32", N);
+    PD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, PD_ERR_SHAPE, "gemm: ntaps %d out of range", g.ntaps);
+    PD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0, PD_ERR_ARG,
+             "gemm: operands must be 16-byte aligned");
+    const int ldo = e.ldo ? e.ldo : N;
+    PD_CHECK(ldo % 4 == 0, PD_ERR_SHAPE, "gemm: output row stride must be a multiple of 4");
+    PD_CHECK(e.out_f32 || e.out_bf16, PD_ERR_ARG, "gemm: no output pointer");
+
+    // ---- A box: 128 rows = bw x bh x bd positions -------------------------------------------------------------
+    const int bw = g.W < kGemmBlockM ? g.W : kGemmBlockM;
+    PD_CHECK(kGemmBlockM % bw == 0, PD_ERR_SHAPE, "gemm: W=%d must divide 128 (or exceed it for a plain linear)", g.W);
+    PD_CHECK(g.W <= kGemmBlockM || (g.H == 1 && g.D == 1), PD_ERR_SHAPE, "gemm: W=%d > 128 only for plain linears", g.W);
+    int rows_left = kGemmBlockM / bw;
+    const int bh = g.H < rows_left ? g.H : rows_left;
+    PD_CHECK(rows_left % bh == 0 && g.H % bh == 0, PD_ERR_SHAPE, "gemm: H=%d incompatible with the 128-row tile", g.H);
+    const int bd = rows_left / bh;
+    PD_CHECK(bd == 1 || bh == g.H, PD_ERR_SHAPE, "gemm: tile geometry");
+    const int out_D = g.out_D ? g.out_D : g.D;
+    PD_CHECK(out_D == g.D || bd == 1, PD_ERR_SHAPE, "gemm: plane-indexed A needs H*W >= 128");
+
+    const int64_t sW = g.sW ? g.sW : g.C;
+    const int64_t sH = g.sH ? g.sH : sW * g.W;
+    const int64_t sD = g.sD ? g.sD : sH * g.H;
+    const int64_t sN = g.sN ? g.sN : sD * g.D;
+    {
+        cuuint64_t dims[5] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)g.samples};
+        cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sD * 2, (cuuint64_t)sN * 2};
+        cuuint32_t box[5] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        CUresult r = g_encode(&op->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(A), dims, strides, box,
+                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA,
+                 "cuTensorMapEncodeTiled(A) failed: %d (dims %d,%d,%d,%d,%d box %d,%d,%d,%d)", (int)r, g.C, g.W, g.H, g.D,
+                 g.samples, kGemmBlockK, bw, bh, bd);
+    }
+
+    // ---- tile shape -------------------------------------------------------------------------------------------
+    const int rows_per_sample = out_D * g.H * g.W;
+    const int tiles_per_sample = ceil_div(rows_per_sample, kGemmBlockM);
+    const int m_tiles = tiles_per_sample * g.samples;
+    int bn = force_block_n;
+    if (!bn) {
+        if (const char* s = getenv("PD_GEMM_BN")) bn = atoi(s);
+        if (bn && N % bn != 0) bn = 0;
+    }
+    if (!bn) {
+        // largest BLOCK_N whose grid still covers the SMs; otherwise the smallest one >= 64 (32 only if N forces it)
+        const int cands[4] = {256, 128, 64, 32};
+        int smallest = 0;
+        for (int c : cands) {
+            if (N % c != 0) continue;
+            if (c >= 64 || !smallest) smallest = c;
+            if ((int64_t)m_tiles * (N / c) >= kNumSMs) { bn = c; break; }
+        }
+        if (!bn) bn = smallest;
+    }
+    PD_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, PD_ERR_SHAPE, "gemm: bad BLOCK_N %d", bn);
+    PD_CHECK(N % bn == 0, PD_ERR_SHAPE, "gemm: N %d not a multiple of BLOCK_N %d", N, bn);
+    {
+        const int64_t ktot = (int64_t)g.ntaps * g.C;
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)bn};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = g_encode(&op->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(Wt), dims, strides, box,
+                              es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    }
+
+    GemmKernelParams& p = op->p;
+    memset(&p, 0, sizeof(p));
+    p.rows_per_sample = rows_per_sample;
+    p.tiles_per_sample = tiles_per_sample;
+    p.samples = g.samples;
+    p.N = N;
+    p.H = g.H;
+    p.W = g.W;
+    p.HW = g.H * g.W;
+    p.ntaps = g.ntaps;
+    p.cblks = g.C / kGemmBlockK;
+    memcpy(p.dz, g.dz, sizeof(p.dz));
+    memcpy(p.dy, g.dy, sizeof(p.dy));
+    memcpy(p.dx, g.dx, sizeof(p.dx));
+    p.bias = e.bias;
+    p.rowvec = e.rowvec;
+    p.residual = e.residual;
+    p.out_f32 = e.out_f32;
+    p.out_bf16 = e.out_bf16;
+    p.ldo = ldo;
+    p.act = e.act;
+    op->block_n = bn;
+    op->grid_x = (unsigned)m_tiles;
+    op->grid_y = (unsigned)(N / bn);
+    op->flops = 2.0 * (double)rows_per_sample * g.samples * (double)N * (double)g.ntaps * g.C;
+    return PD_OK;
+}
+
+int gemm_launch(const GemmOp& op, cudaStream_t stream) {
+    switch (op.block_n) {
+        case 32: return launch_bn<32>(op, stream);
+        case 64: return launch_bn<64>(op, stream);
+        case 128: return launch_bn<128>(op, stream);
+        case 256: return launch_bn<256>(op, stream);
+    }
+    set_error("gemm_launch: op not initialised");
+    return PD_ERR_STATE;
+}
+
+}  // namespace pd

@@ -1,0 +1,107 @@
+// tcgen05 / TMA implicit-GEMM: the one dense-contraction kernel of the sampling path.
+//
+//   out[row, n] = epilogue( sum_{tap, c} A[row shifted by tap, c] * Wt[n, tap, c] )
+//
+// A is a channels-last bf16 activation tensor viewed as [samples][D][H][W][C]; a "tap" is a (dz, dy, dx) shift
+// (one tap with zero shift = a plain Linear; 27 taps = Conv3d 3x3x3; 9 taps = Conv2d 3x3). Shifted tiles are
+// fetched with *tiled* TMA whose out-of-bounds zero fill implements the zero padding, so no im2col buffer exists.
+// Replaces the cuDNN / cuBLAS call sites listed in SURVEY.md section 2.1 (reference:
+// src/prediff/models/time_embed.py:93,120; cuboid_transformer.py:735,767,157,164; taming/resnet.py:405,421).
+#pragma once
+#include "common.cuh"
+
+namespace pd {
+
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int kMaxTaps = 27;
+
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
+
+struct GemmGeom {
+    int samples = 1;  // independent samples (tiles never straddle a sample)
+    int D = 1, H = 1, W = 1;
+    int out_D = 0;    // D extent of the OUTPUT grid (0 -> D); differs from D only for the parity-plane stride-2 conv
+    int C = 0;        // channels of A per tap (multiple of 64)
+    int ntaps = 1;
+    int8_t dz[kMaxTaps] = {0}, dy[kMaxTaps] = {0}, dx[kMaxTaps] = {0};
+    // strides of A in elements, in case the activation buffer is a view (default: dense channels-last)
+    int64_t sW = 0, sH = 0, sD = 0, sN = 0;
+
+    static GemmGeom linear(int M, int K) {
+        GemmGeom g;
+        g.W = M;
+        g.C = K;
+        return g;
+    }
+    // Conv with a (kt, kh, kw) window, stride 1, zero padding k/2 on every axis.
+    static GemmGeom conv(int samples, int D, int H, int W, int C, int kt, int kh, int kw) {
+        GemmGeom g;
+        g.samples = samples; g.D = D; g.H = H; g.W = W; g.C = C;
+        g.ntaps = kt * kh * kw;
+        int i = 0;
+        for (int a = 0; a < kt; ++a)
+            for (int b = 0; b < kh; ++b)
+                for (int c = 0; c < kw; ++c, ++i) {
+                    g.dz[i] = (int8_t)(a - kt / 2);
+                    g.dy[i] = (int8_t)(b - kh / 2);
+                    g.dx[i] = (int8_t)(c - kw / 2);
+                }
+        return g;
+    }
+    // Stride-2 3x3 conv with right/bottom zero pad (taming/resnet.py:183-188) over parity planes
+    // [F][4][Ho][Wo][C] (plane = (y%2)*2 + x%2): tap (kh, kw) reads plane (kh%2, kw%2) shifted by (kh/2, kw/2).
+    static GemmGeom conv_s2_planes(int F, int Ho, int Wo, int C) {
+        GemmGeom g;
+        g.samples = F; g.D = 4; g.out_D = 1; g.H = Ho; g.W = Wo; g.C = C;
+        g.ntaps = 9;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                const int i = kh * 3 + kw;
+                g.dz[i] = (int8_t)((kh & 1) * 2 + (kw & 1));
+                g.dy[i] = (int8_t)(kh >> 1);
+                g.dx[i] = (int8_t)(kw >> 1);
+            }
+        return g;
+    }
+};
+
+struct GemmEpilogue {
+    const float* bias = nullptr;      // [N]
+    const float* rowvec = nullptr;    // [samples][N], added to every row of the sample (time embedding)
+    const float* residual = nullptr;  // [M][ldo] fp32, may alias out_f32
+    float* out_f32 = nullptr;         // [M][ldo]
+    bf16* out_bf16 = nullptr;         // [M][ldo]
+    int ldo = 0;                      // row stride of residual/out in elements (0 -> N)
+    int act = ACT_NONE;               // applied after bias/rowvec, before the residual add
+};
+
+struct GemmKernelParams {
+    int rows_per_sample, tiles_per_sample, samples;
+    int N, H, W, HW;
+    int ntaps, cblks;
+    int8_t dz[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps];
+    const float* bias;
+    const float* rowvec;
+    const float* residual;
+    float* out_f32;
+    bf16* out_bf16;
+    int ldo, act;
+};
+
+struct GemmOp {
+    CUtensorMap tmap_a, tmap_b;
+    GemmKernelParams p;
+    int block_n = 0, stages = 0;
+    unsigned grid_x = 0, grid_y = 0;
+    size_t smem = 0;
+    double flops = 0;
+};
+
+// Builds tensor maps + launch geometry. `A` is bf16 [samples][D][H][W][C]; `Wt` is bf16 [N][ntaps*C] (K-major).
+int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int N, const GemmEpilogue& e,
+              int force_block_n = 0);
+int gemm_launch(const GemmOp& op, cudaStream_t stream);
+int gemm_init();  // resolves the driver entry point + raises the dynamic smem limits (idempotent)
+
+}  // namespace pd

@@ -1,0 +1,206 @@
+// GroupNorm (+SiLU) and LayerNorm kernels: fp32 channels-last in, bf16 out (the GEMM A operand).
+// HBM-bound elementwise/reduction work: 128-bit loads, 64-bit bf16x4 stores, one pass for statistics and one
+// pass for normalise+activate.
+#include "ops.cuh"
+
+namespace pd {
+namespace {
+
+constexpr int kGnThreads = 256;
+constexpr int kGnRowsPerBlock = 64;
+
+// x [S][R][C] -> partial (sum, sumsq) per (sample, group), accumulated in double.
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
+                                                              int R, int C, int G) {
+    __shared__ float red[kGnThreads][8];
+    const int s = blockIdx.y;
+    const int r0 = blockIdx.x * kGnRowsPerBlock;
+    const int r1 = min(r0 + kGnRowsPerBlock, R);
+    const int c4n = C >> 2;                     // float4 columns
+    const int lanes_r = kGnThreads / c4n;       // rows processed per iteration
+    const int tc = threadIdx.x % c4n;
+    const int tr = threadIdx.x / c4n;
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    if (tr < lanes_r) {
+        const float4* base = reinterpret_cast<const float4*>(x + ((size_t)s * R) * C) + tc;
+        for (int r = r0 + tr; r < r1; r += lanes_r) {
+            const float4 v = __ldg(base + (size_t)r * c4n);
+            a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+            q0 += v.x * v.x; q1 += v.y * v.y; q2 += v.z * v.z; q3 += v.w * v.w;
+        }
+    }
+    float* my = red[threadIdx.x];
+    my[0] = a0; my[1] = a1; my[2] = a2; my[3] = a3; my[4] = q0; my[5] = q1; my[6] = q2; my[7] = q3;
+    __syncthreads();
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += kGnThreads) {
+        float sm = 0.f, sq = 0.f;
+        for (int rr = 0; rr < lanes_r; ++rr)
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const float* e = red[rr * c4n + (c >> 2)];
+                sm += e[c & 3];
+                sq += e[4 + (c & 3)];
+            }
+        atomicAdd(&sums[((size_t)s * G + g) * 2 + 0], (double)sm);
+        atomicAdd(&sums[((size_t)s * G + g) * 2 + 1], (double)sq);
+    }
+}
+
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __restrict__ x,
+                                                              const double* __restrict__ sums,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, bf16* __restrict__ y,
+                                                              int R, int C, int G, float eps, int silu) {
+    __shared__ float s_mean[128], s_rstd[128];
+    const int s = blockIdx.y;
+    const int cpg = C / G;
+    for (int g = threadIdx.x; g < G; g += kGnThreads) {
+        const double n = (double)R * cpg;
+        const double m = sums[((size_t)s * G + g) * 2] / n;
+        double var = sums[((size_t)s * G + g) * 2 + 1] / n - m * m;
+        if (var < 0) var = 0;
+        s_mean[g] = (float)m;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int c4n = C >> 2;
+    const int r0 = blockIdx.x * kGnRowsPerBlock;
+    const int r1 = min(r0 + kGnRowsPerBlock, R);
+    const int n4 = (r1 - r0) * c4n;
+    const float4* xin = reinterpret_cast<const float4*>(x + ((size_t)s * R + r0) * C);
+    uint2* yout = reinterpret_cast<uint2*>(y + ((size_t)s * R + r0) * C);
+    for (int i = threadIdx.x; i < n4; i += kGnThreads) {
+        const int c = (i % c4n) * 4;
+        const float4 v = __ldg(xin + i);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float o[4] = {v.x, v.y, v.z, v.w};
+        const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
+        const float btv[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int g = (c + k) / cpg;
+            float t = (o[k] - s_mean[g]) * s_rstd[g] * gmv[k] + btv[k];
+            o[k] = silu ? silu_f(t) : t;
+        }
+        uint2 pk;
+        pk.x = pack_bf16x2(o[0], o[1]);
+        pk.y = pack_bf16x2(o[2], o[3]);
+        yout[i] = pk;
+    }
+}
+
+// One warp per output row. NV float4 per lane. GATHER: PatchMerging3D 2x2 space-to-depth on the fly.
+template <int NV, bool GATHER>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, bf16* __restrict__ y, int P,
+                                                         int C, float eps, int H, int W, int Cs) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= P) return;
+    const int c4n = C >> 2;
+    float4 v[NV];
+    if constexpr (!GATHER) {
+        const float4* row = reinterpret_cast<const float4*>(x + (size_t)warp * C);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c4 = lane + i * 32;
+            v[i] = c4 < c4n ? __ldg(row + c4) : make_float4(0, 0, 0, 0);
+        }
+    } else {
+        // output row = (f, h2, w2) over [F][H/2][W/2]; merged channel = (dh*2 + dw) * Cs + c
+        const int W2 = W >> 1, H2 = H >> 1;
+        const int w2 = warp % W2;
+        const int h2 = (warp / W2) % H2;
+        const int f = warp / (W2 * H2);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c4 = lane + i * 32;
+            if (c4 < c4n) {
+                const int c = c4 * 4;
+                const int seg = c / Cs;
+                const int cc = c - seg * Cs;
+                const int hh = 2 * h2 + (seg >> 1), ww = 2 * w2 + (seg & 1);
+                v[i] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)f * H + hh) * W + ww) * Cs + cc));
+            } else {
+                v[i] = make_float4(0, 0, 0, 0);
+            }
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + i * 32;
+        if (c4 < c4n) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            sq += a * a + b * b + c * c + d * d;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    uint2* out = reinterpret_cast<uint2*>(y + (size_t)warp * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c4 = lane + i * 32;
+        if (c4 < c4n) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+            uint2 pk;
+            pk.x = pack_bf16x2((v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y);
+            pk.y = pack_bf16x2((v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w);
+            out[c4] = pk;
+        }
+    }
+}
+
+template <bool GATHER>
+int launch_ln(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, float eps, int H, int W,
+              int Cs, cudaStream_t st) {
+    PD_CHECK(C % 4 == 0 && C >= 4 && C <= 2048, PD_ERR_SHAPE, "layer_norm: unsupported C=%d", C);
+    const int nv = ceil_div(C, 128);
+    const int blocks = ceil_div(P, 8);
+    if (nv <= 1) layer_norm_kernel<1, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 2) layer_norm_kernel<2, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 4) layer_norm_kernel<4, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 8) layer_norm_kernel<8, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else layer_norm_kernel<16, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
+
+}  // namespace
+
+int gn_stats(const float* x, double* sums, int S, int R, int C, int G, cudaStream_t st) {
+    PD_CHECK(C % 4 == 0 && (kGnThreads % (C / 4) == 0) && C / 4 <= kGnThreads, PD_ERR_SHAPE, "gn_stats: unsupported C=%d",
+             C);
+    PD_CHECK(G > 0 && C % G == 0 && G <= 128, PD_ERR_SHAPE, "gn_stats: unsupported groups=%d for C=%d", G, C);
+    dim3 grid(ceil_div(R, kGnRowsPerBlock), S);
+    gn_stats_kernel<<<grid, kGnThreads, 0, st>>>(x, sums, R, C, G);
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
+
+int gn_apply(const float* x, const double* sums, const float* gamma, const float* beta, bf16* y, int S, int R, int C,
+             int G, float eps, int silu, cudaStream_t st) {
+    PD_CHECK(C % 4 == 0 && G > 0 && C % G == 0 && G <= 128, PD_ERR_SHAPE, "gn_apply: unsupported C=%d G=%d", C, G);
+    dim3 grid(ceil_div(R, kGnRowsPerBlock), S);
+    gn_apply_kernel<<<grid, kGnThreads, 0, st>>>(x, sums, gamma, beta, y, R, C, G, eps, silu);
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
+
+int layer_norm(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, float eps,
+               cudaStream_t st) {
+    return launch_ln<false>(x, gamma, beta, y, P, C, eps, 0, 0, 0, st);
+}
+
+int patch_merge_ln(const float* x, const float* gamma, const float* beta, bf16* y, int BT, int H, int W, int C,
+                   float eps, cudaStream_t st) {
+    PD_CHECK(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, PD_ERR_SHAPE, "patch_merge_ln: H, W must be even (got %d, %d)", H, W);
+    return launch_ln<true>(x, gamma, beta, y, BT * (H / 2) * (W / 2), 4 * C, eps, H, W, C, st);
+}
+
+}  // namespace pd

@@ -1,0 +1,76 @@
+// Launchers for the non-GEMM kernels of the sampling path. All tensors are channels-last; fp32 is the residual
+// stream, bf16 is what feeds the tensor-core GEMM. Every launcher returns a pd error code.
+#pragma once
+#include "common.cuh"
+
+namespace pd {
+
+// ---- normalisation (norm.cu) -------------------------------------------------------------------------------
+// GroupNorm statistics: x fp32 [S][R][C], groups of cpg contiguous channels. Accumulates (sum, sumsq) as doubles
+// into sums[S][G][2]; the caller zeroes `sums` beforehand (one memset per forward covers every GN of the model).
+// Reference: torch.nn.GroupNorm in time_embed.py:90-92,116-118 and taming/resnet.py:403,419.
+int gn_stats(const float* x, double* sums, int S, int R, int C, int G, cudaStream_t st);
+// y = act((x - mean) * rstd * gamma + beta) -> bf16 [S][R][C]; mean/rstd derived from sums (biased variance).
+int gn_apply(const float* x, const double* sums, const float* gamma, const float* beta, bf16* y, int S, int R, int C,
+             int G, float eps, int silu, cudaStream_t st);
+// LayerNorm over the last dim (eps 1e-5): fp32 [P][C] -> bf16 [P][C]. C in {64,128,256,512,1024,2048}.
+// Reference: models/utils.py:218 (nn.LayerNorm) as used by cuboid_transformer.py:813,195.
+int layer_norm(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, float eps,
+               cudaStream_t st);
+// PatchMerging3D gather + LayerNorm(4C): x fp32 [B*T][H][W][C] -> bf16 [B*T][H/2][W/2][4C], merged channel order
+// (dh, dw, c). Reference: cuboid_transformer.py:286-294.
+int patch_merge_ln(const float* x, const float* gamma, const float* beta, bf16* y, int BT, int H, int W, int C,
+                   float eps, cudaStream_t st);
+
+// ---- attention (attention.cu) ------------------------------------------------------------------------------
+// Axial cuboid self-attention core: qkv bf16 [B][T][H][W][3C] (q|k|v, head-major), one softmax per line along
+// `axis` (0=T, 1=H, 2=W) and head, relative-position bias table fp32 [2L-1][heads]; out bf16 [B][T][H][W][C].
+// Reference: cuboid_transformer.py:849-861,949 with cuboids (T,1,1)/(1,H,1)/(1,1,W) (patterns.py:34-36).
+int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int T, int H, int W, int C, int heads,
+                    int axis, cudaStream_t st);
+// Row softmax for the VAE AttentionBlock: s fp32 [rows][L] -> p bf16 [rows][L], p = softmax(scale * s).
+int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st);
+// Batched transpose bf16: in [S][R][ld_in] (first C columns used) -> out [S][C][R].
+int transpose_bf16(const bf16* in, bf16* out, int S, int R, int C, int ld_in, cudaStream_t st);
+
+// ---- elementwise / data movement (elementwise.cu) ----------------------------------------------------------
+// UNet input assembly (cuboid_transformer_unet.py:425-428): cat(cond, x) on T, append the observed-indicator
+// channel, zero-pad channels to Cpad. Writes fp32 and bf16 copies [B][Tc+Tx][HW][Cpad].
+int unet_assemble(const float* x, const float* cond, float* out_f32, bf16* out_bf16, int B, int Tx, int Tc, int HW,
+                  int C, int Cpad, cudaStream_t st);
+// x[b,t,h,w,:] += Temb[t] + Hemb[h] + Wemb[w]   (cuboid_transformer.py:78-85)
+int pos_embed_add(float* x, const float* Te, const float* He, const float* We, int B, int T, int H, int W, int C,
+                  cudaStream_t st);
+// nearest 2x spatial upsample + cast: fp32 [F][H][W][C] -> bf16 [F][2H][2W][C]  (cuboid_transformer.py:340,373;
+// taming/resnet.py:128)
+int upsample2x_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st);
+// fp32 -> bf16 cast of a [S][R][C] slice taken from x with sample stride `in_sample_stride` elements.
+int cast_bf16(const float* x, bf16* y, int S, int64_t RC, int64_t in_sample_stride, cudaStream_t st);
+// Downsample2D prep (taming/resnet.py:183-188): fp32 [F][H][W][C] -> bf16 parity planes [F][4][H/2][W/2][C],
+// plane = (y%2)*2 + (x%2), so the stride-2 3x3 conv becomes 9 unit-stride shifted loads.
+int parity_split_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st);
+// sinusoidal timestep embedding (models/utils.py:77-83): out[b] = [cos(t f_i) | sin(t f_i)], dim even.
+int timestep_embedding(const int64_t* t, float* out, int B, int dim, cudaStream_t st);
+// out[b][n] = out_act( sum_k in_act(in[b][k]) * W[n][k] + bias[n] ), fp32, tiny-M linear (time-embedding MLP).
+int small_linear(const float* in, const float* W, const float* bias, float* out, int B, int K, int N, int in_silu,
+                 int out_silu, cudaStream_t st);
+// VAE conv_in (1 -> Cout, 3x3, pad 1): x fp32 [F][H][W] -> fp32 [F][H][W][Cout]. w fp32 [Cout][9].
+int conv3x3_c1_in(const float* x, const float* w, const float* bias, float* y, int F, int H, int W, int Cout,
+                  cudaStream_t st);
+// VAE decoder conv_out (Cin -> 1, 3x3, pad 1): x bf16 [F][H][W][Cin] -> fp32 [F][H][W]. w fp32 [9][Cin].
+int conv3x3_c1_out(const bf16* x, const float* w, float bias, float* y, int F, int H, int W, int Cin, cudaStream_t st);
+
+// ---- weight repacking (elementwise.cu) ---------------------------------------------------------------------
+// fp32 [N][K] -> bf16 [N][Kpad] (zero padded)
+int pack_linear(const float* w, bf16* out, int N, int K, int Kpad, cudaStream_t st);
+// fp32 [Co][Ci][taps] -> bf16 [Co][taps][Cipad]
+int pack_conv(const float* w, bf16* out, int Co, int Ci, int taps, int Cipad, cudaStream_t st);
+
+// ---- sampler (sampler.cu) ----------------------------------------------------------------------------------
+// One fused update of the latent (latent_diffusion.py:553-566,620-631 for DDPM; SURVEY section 8 S6 for DDIM):
+//   z0 = c[0] z - c[1] eps ;  z <- c[2] z0 + c[3] z + c[4] eps + c[5] noise - c[6] guide
+// coef points at 8 floats in device memory (the row of the resident schedule table for this step).
+int sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef, int64_t n,
+                   cudaStream_t st);
+
+}  // namespace pd

@@ -1,0 +1,254 @@
+"""Kernel-level parity tests (GPU): every CUDA kernel, called through the C ABI, against a plain PyTorch fp32
+reference of the same op evaluated on the same (bf16-rounded where the kernel consumes bf16) inputs."""
+import ctypes
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from prediff_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    L.init()
+
+
+def _sync_check(rc):
+    L.check(rc)
+    torch.cuda.synchronize()
+
+
+def rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def _randn(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,K,N,bn", [
+    (128, 64, 64, 0), (256, 256, 256, 0), (3328, 256, 768, 0), (832, 512, 1536, 0), (1000, 128, 96, 0),
+    (3328, 1024, 256, 64), (3328, 256, 256, 128), (3328, 256, 256, 256), (512, 2048, 512, 0), (384, 64, 32, 32),
+])
+def test_gemm_linear(M, K, N, bn):
+    a = _randn(M, K, seed=1).bfloat16()
+    w = _randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
+    bias = _randn(N, seed=3)
+    res = _randn(M, N, seed=4)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(a), L.ptr(w), 1, 1, 1, M, K, 1, 1, 1, N, L.ptr(bias), None, L.ptr(res),
+                                        L.ptr(out), L.ptr(outb), 1, bn, L.stream_ptr()))
+    ref = F.gelu(a.float() @ w.float().t() + bias) + res
+    e = rel_err(out, ref)
+    assert e < 2e-5, f"fp32 out rel err {e}"
+    assert rel_err(outb, ref) < 1e-2
+
+
+def test_gemm_plain_no_epilogue_and_rowvec():
+    M, K, N, samples = 512, 128, 128, 4
+    a = _randn(samples * M, K, seed=5).bfloat16()
+    w = _randn(N, K, seed=6, scale=K ** -0.5).bfloat16()
+    rv = _randn(samples, N, seed=7)
+    out = torch.empty(samples * M, N, device=DEV)
+    # 4 samples of a (D=1,H=4,W=128) grid -> rowvec indexed per sample
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(a), L.ptr(w), samples, 1, 4, 128, K, 1, 1, 1, N, None, L.ptr(rv), None,
+                                        L.ptr(out), None, 0, 0, L.stream_ptr()))
+    ref = (a.float() @ w.float().t()).view(samples, M, N) + rv[:, None, :]
+    assert rel_err(out.view(samples, M, N), ref) < 2e-5
+
+
+def _pack_conv(w, cipad):
+    co, ci = w.shape[:2]
+    taps = w[0, 0].numel()
+    out = torch.empty(co, taps, cipad, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_pack_conv(L.ptr(w.contiguous()), L.ptr(out), co, ci, taps, cipad, L.stream_ptr()))
+    return out
+
+
+@pytest.mark.parametrize("B,D,H,W,C,N,k", [
+    (2, 13, 16, 16, 64, 64, (3, 3, 3)),     # level-0 geometry: tile = 8 x 16 half plane
+    (2, 13, 8, 8, 128, 128, (3, 3, 3)),     # level-1 geometry: tile = 2 frames, ragged last tile (832 = 6.5 x 128)
+    (3, 1, 16, 16, 64, 64, (1, 3, 3)),      # VAE mid-block conv2d
+    (2, 1, 32, 32, 64, 32, (1, 3, 3)),
+    (1, 1, 128, 128, 64, 64, (1, 3, 3)),    # VAE full-resolution conv2d: tile = one image row
+    (2, 13, 16, 16, 128, 64, (1, 1, 1)),    # 1x1x1 skip conv
+    (1, 13, 16, 16, 256, 256, (3, 3, 3)),   # shipped level-0 conv
+])
+def test_conv_gemm(B, D, H, W, C, N, k):
+    kt, kh, kw = k
+    x = _randn(B, D, H, W, C, seed=11).bfloat16()
+    w = _randn(N, C, kt, kh, kw, seed=12, scale=(C * kt * kh * kw) ** -0.5)
+    wp = _pack_conv(w, C)
+    bias = _randn(N, seed=13)
+    temb = _randn(B, N, seed=14)
+    res = _randn(B, D, H, W, N, seed=15)
+    out = torch.full((B, D, H, W, N), float("nan"), device=DEV)
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(x), L.ptr(wp), B, D, H, W, C, kt, kh, kw, N, L.ptr(bias), L.ptr(temb),
+                                        L.ptr(res), L.ptr(out), None, 0, 0, L.stream_ptr()))
+    xr = x.float().permute(0, 4, 1, 2, 3)
+    wr = w.bfloat16().float()
+    ref = F.conv3d(xr, wr, bias, padding=(kt // 2, kh // 2, kw // 2)) + temb[:, :, None, None, None]
+    ref = ref.permute(0, 2, 3, 4, 1) + res
+    e = rel_err(out, ref)
+    assert e < 3e-5, f"conv rel err {e}"
+
+
+def test_conv_padded_input_channels():
+    # 65 real channels padded to 128 (first_proj): padded activations/weights are zero
+    B, D, H, W, Cr, Cp, N = 1, 13, 16, 16, 65, 128, 64
+    xr = _randn(B, D, H, W, Cr, seed=21).bfloat16()
+    x = torch.zeros(B, D, H, W, Cp, device=DEV, dtype=torch.bfloat16)
+    x[..., :Cr] = xr
+    w = _randn(N, Cr, 3, 3, 3, seed=22, scale=0.02)
+    wp = _pack_conv(w, Cp)
+    out = torch.empty(B, D, H, W, N, device=DEV)
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(x), L.ptr(wp), B, D, H, W, Cp, 3, 3, 3, N, None, None, None, L.ptr(out),
+                                        None, 0, 0, L.stream_ptr()))
+    ref = F.conv3d(xr.float().permute(0, 4, 1, 2, 3), w.bfloat16().float(), padding=1).permute(0, 2, 3, 4, 1)
+    assert rel_err(out, ref) < 3e-5
+
+
+@pytest.mark.parametrize("Fr,H,W,C,N", [(2, 32, 32, 64, 64), (1, 128, 128, 128, 128)])
+def test_conv_stride2(Fr, H, W, C, N):
+    x = _randn(Fr, H, W, C, seed=31)
+    w = _randn(N, C, 3, 3, seed=32, scale=(9 * C) ** -0.5)
+    bias = _randn(N, seed=33)
+    planes = torch.empty(Fr, 4, H // 2, W // 2, C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_parity_split_cast(L.ptr(x), L.ptr(planes), Fr, H, W, C, L.stream_ptr()))
+    wp = _pack_conv(w, C)
+    out = torch.empty(Fr, H // 2, W // 2, N, device=DEV)
+    _sync_check(L.lib().pd_op_conv_s2_gemm(L.ptr(planes), L.ptr(wp), Fr, H // 2, W // 2, C, N, L.ptr(bias), L.ptr(out),
+                                           L.stream_ptr()))
+    xr = F.pad(x.bfloat16().float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xr, w.bfloat16().float(), bias, stride=2).permute(0, 2, 3, 1)
+    assert rel_err(out, ref) < 3e-5
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("S,R,C,G,eps,silu", [(2, 3328, 256, 32, 1e-5, 1), (2, 832, 512, 32, 1e-5, 1),
+                                              (1, 3328, 128, 128, 1e-5, 1), (3, 16384, 128, 32, 1e-6, 1),
+                                              (2, 256, 512, 32, 1e-6, 0), (2, 3328, 64, 32, 1e-5, 1)])
+def test_group_norm(S, R, C, G, eps, silu):
+    x = _randn(S, R, C, seed=41) * 2 + 0.5
+    gamma = 1 + 0.1 * _randn(C, seed=42)
+    beta = 0.1 * _randn(C, seed=43)
+    y = torch.empty(S, R, C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_group_norm(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), S, R, C, G, ctypes.c_float(eps),
+                                         silu, L.stream_ptr()))
+    ref = F.group_norm(x.permute(0, 2, 1), G, gamma, beta, eps).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_err(y, ref) < 6e-3  # bf16 output rounding
+
+
+@pytest.mark.parametrize("P,C", [(3328, 256), (832, 512), (100, 1024), (64, 2048), (77, 64), (50, 128)])
+def test_layer_norm(P, C):
+    x = _randn(P, C, seed=51) * 3 - 1
+    gamma = 1 + 0.1 * _randn(C, seed=52)
+    beta = 0.1 * _randn(C, seed=53)
+    y = torch.empty(P, C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_layer_norm(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), P, C, ctypes.c_float(1e-5),
+                                         L.stream_ptr()))
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    assert rel_err(y, ref) < 6e-3
+
+
+def test_patch_merge_ln():
+    BT, H, W, C = 26, 16, 16, 256
+    x = _randn(BT, H, W, C, seed=61)
+    gamma = 1 + 0.1 * _randn(4 * C, seed=62)
+    beta = 0.1 * _randn(4 * C, seed=63)
+    y = torch.empty(BT, H // 2, W // 2, 4 * C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_patch_merge_ln(L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(y), BT, H, W, C,
+                                             ctypes.c_float(1e-5), L.stream_ptr()))
+    # reference cuboid_transformer.py:286-294
+    xr = x.reshape(BT, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(BT, H // 2, W // 2, 4 * C)
+    ref = F.layer_norm(xr, (4 * C,), gamma, beta, 1e-5)
+    assert rel_err(y, ref) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _axial_ref(qkv, table, B, T, H, W, C, heads, axis):
+    hd = C // heads
+    q, k, v = qkv.float().view(B, T, H, W, 3, heads, hd).unbind(4)  # (B,T,H,W,heads,hd)
+    dim = 1 + axis
+    Lx = (T, H, W)[axis]
+    q, k, v = (t.movedim(dim, 4) for t in (q, k, v))  # (B, o1, o2, heads, L, hd)
+    s = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    idx = torch.arange(Lx, device=qkv.device)
+    rel = idx[:, None] - idx[None, :] + Lx - 1
+    s = s + table[rel].permute(2, 0, 1)  # (heads, L, L)
+    o = torch.softmax(s, -1) @ v  # (B,o1,o2,heads,L,hd)
+    o = o.movedim(4, dim)  # back to (B,T,H,W,heads,hd)
+    return o.reshape(B, T, H, W, C)
+
+
+@pytest.mark.parametrize("T,H,W,C,heads", [(13, 16, 16, 256, 4), (13, 8, 8, 512, 4), (13, 16, 16, 64, 4),
+                                           (6, 16, 16, 128, 4)])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_axial_attention(T, H, W, C, heads, axis):
+    B = 2
+    qkv = _randn(B, T, H, W, 3 * C, seed=71).bfloat16()
+    Lx = (T, H, W)[axis]
+    table = _randn(2 * Lx - 1, heads, seed=72)
+    out = torch.empty(B, T, H, W, C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_axial_attention(L.ptr(qkv), L.ptr(table), L.ptr(out), B, T, H, W, C, heads, axis,
+                                              L.stream_ptr()))
+    ref = _axial_ref(qkv, table, B, T, H, W, C, heads, axis)
+    assert rel_err(out, ref) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+def test_sampler_update():
+    n = 4 * 6 * 16 * 16 * 64
+    z, eps, noise, guide = (_randn(n, seed=s) for s in (81, 82, 83, 84))
+    coef = torch.tensor([1.3, 0.7, 0.4, 0.55, 0.1, 0.2, 0.05, 0.0], device=DEV)
+    z0 = z.clone()
+    _sync_check(L.lib().pd_op_sampler_update(L.ptr(z), L.ptr(eps), L.ptr(noise), L.ptr(guide), L.ptr(coef),
+                                             ctypes.c_int64(n), L.stream_ptr()))
+    x0 = 1.3 * z0 - 0.7 * eps
+    ref = 0.4 * x0 + 0.55 * z0 + 0.1 * eps - 0.05 * guide + 0.2 * noise
+    assert (z - ref).abs().max().item() < 1e-5
+
+
+def test_timestep_embedding_and_small_linear():
+    B, dim = 4, 256
+    t = torch.tensor([0, 1, 500, 999], device=DEV, dtype=torch.int64)
+    out = torch.empty(B, dim, device=DEV)
+    _sync_check(L.lib().pd_op_timestep_embedding(L.ptr(t), L.ptr(out), B, dim, L.stream_ptr()))
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(DEV)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (out - ref).abs().max().item() < 2e-4
+    w = _randn(1024, dim, seed=91, scale=dim ** -0.5)
+    b = _randn(1024, seed=92)
+    y = torch.empty(B, 1024, device=DEV)
+    _sync_check(L.lib().pd_op_small_linear(L.ptr(ref), L.ptr(w), L.ptr(b), L.ptr(y), B, dim, 1024, 1, 1, L.stream_ptr()))
+    yr = F.silu(F.silu(ref) @ w.t() + b)
+    assert rel_err(y, yr) < 1e-5
+
+
+def test_upsample_and_pack_linear():
+    x = _randn(3, 8, 8, 64, seed=95)
+    y = torch.empty(3, 16, 16, 64, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_upsample2x_cast(L.ptr(x), L.ptr(y), 3, 8, 8, 64, L.stream_ptr()))
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(y, ref)
+    w = _randn(48, 65, seed=96)
+    p = torch.empty(48, 128, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_pack_linear(L.ptr(w), L.ptr(p), 48, 65, 128, L.stream_ptr()))
+    assert torch.equal(p[:, :65], w.bfloat16()) and p[:, 65:].float().abs().max().item() == 0.0
