@@ -1,0 +1,312 @@
+"""CPU oracle for the PreDiff sampling path - TEST INFRASTRUCTURE ONLY.
+
+A plain PyTorch fp32 (CPU) functional restatement of the reference algorithm for the hot path of
+gaozhihan/PreDiff. It is NOT part of the product: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import it, and only as the checker / reported CPU baseline.
+The product path (prediff_b200/) never imports this module and has no CPU fallback.
+
+Pinning: the reference has no tests or golden vectors of its own, so this restatement is pinned
+against outputs of the UNMODIFIED reference modules run in the build container - the fixtures under
+tests/golden/*.npz, produced by tests/golden/gen_golden.py (which imports /root/reference/src with a sys.modules
+stub for the absent `lightning`/`diffusers` packages) - plus the schedule known-answers of SURVEY.md section 4.
+tests/test_oracle.py checks every function here against those fixtures.
+
+Every function takes a `sd` dict (reference state_dict key -> torch fp32 tensor) and cites the reference lines
+it restates. Paths are relative to /root/reference/.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------- schedule
+
+
+def make_schedule(timesteps=1000, linear_start=1e-4, linear_end=2e-2):
+    """register_schedule (src/prediff/diffusion/latent_diffusion.py:228-278) with the "linear" beta schedule
+    (src/prediff/diffusion/utils.py:17-22): float64 math, fp32 buffers. v_posterior = 0."""
+    betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=np.float64) ** 2
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
+    buf = {
+        "betas": betas,
+        "alphas_cumprod": ac,
+        "alphas_cumprod_prev": ac_prev,
+        "sqrt_alphas_cumprod": np.sqrt(ac),
+        "sqrt_one_minus_alphas_cumprod": np.sqrt(1.0 - ac),
+        "log_one_minus_alphas_cumprod": np.log(1.0 - ac),
+        "sqrt_recip_alphas_cumprod": np.sqrt(1.0 / ac),
+        "sqrt_recipm1_alphas_cumprod": np.sqrt(1.0 / ac - 1),
+        "posterior_variance": post_var,
+        "posterior_log_variance_clipped": np.log(np.maximum(post_var, 1e-20)),
+        "posterior_mean_coef1": betas * np.sqrt(ac_prev) / (1.0 - ac),
+        "posterior_mean_coef2": (1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac),
+    }
+    return {k: torch.tensor(v, dtype=torch.float32) for k, v in buf.items()}
+
+
+def ddim_timesteps(num_ddim, num_ddpm=1000):
+    """make_ddim_timesteps('uniform', ...) (src/prediff/diffusion/utils.py:42-56): range(0, T, T//n) + 1."""
+    c = num_ddpm // num_ddim
+    return np.asarray(list(range(0, num_ddpm, c))) + 1
+
+
+def ddim_params(alphas_cumprod, ts, eta):
+    """make_ddim_sampling_parameters (src/prediff/diffusion/utils.py:59-70). alphas_cumprod: fp32 numpy."""
+    a = alphas_cumprod[ts]
+    a_prev = np.asarray([alphas_cumprod[0]] + alphas_cumprod[ts[:-1]].tolist())
+    sig = eta * np.sqrt((1 - a_prev) / (1 - a) * (1 - a / a_prev))
+    return sig, a, a_prev
+
+
+# ----------------------------------------------------------------------------------------------- UNet pieces
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    """src/prediff/models/utils.py:68-83 (cos first, then sin)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def _res_block3d(sd, p, x, t_emb, groups_in, groups_out):
+    """TimeEmbedResBlock.forward (src/prediff/models/time_embed.py:134-169), dims=3, no scale-shift, no up/down.
+    x: (B, C, T, H, W)."""
+    h = F.group_norm(x, groups_in, sd[f"{p}.in_layers.0.weight"], sd[f"{p}.in_layers.0.bias"], 1e-5)
+    h = F.conv3d(F.silu(h), sd[f"{p}.in_layers.2.weight"], sd[f"{p}.in_layers.2.bias"], padding=1)
+    if f"{p}.emb_layers.1.weight" in sd:
+        e = F.linear(F.silu(t_emb), sd[f"{p}.emb_layers.1.weight"], sd[f"{p}.emb_layers.1.bias"])
+        h = h + e[:, :, None, None, None]
+    h = F.group_norm(h, groups_out, sd[f"{p}.out_layers.0.weight"], sd[f"{p}.out_layers.0.bias"], 1e-5)
+    h = F.conv3d(F.silu(h), sd[f"{p}.out_layers.3.weight"], sd[f"{p}.out_layers.3.bias"], padding=1)
+    if f"{p}.skip_connection.weight" in sd:
+        x = F.conv3d(x, sd[f"{p}.skip_connection.weight"], sd[f"{p}.skip_connection.bias"])
+    return x + h
+
+
+def _gn_groups(c, g=32):
+    # time_embed.py:90,116: norm_groups if channels % norm_groups == 0 else channels
+    return g if c % g == 0 else c
+
+
+def axial_attention(sd, p, x, heads, axis):
+    """CuboidSelfAttentionLayer.forward (src/prediff/models/cuboid_transformer/cuboid_transformer.py:812-966)
+    for an axial cuboid ((T,1,1), (1,H,1) or (1,1,W); strategy 'l', no shift, no padding, no global vectors):
+    LN -> qkv -> per-line softmax(q k^T / sqrt(hd) + rel-pos bias) v -> proj. x: (B, T, H, W, C)."""
+    B, T, H, W, C = x.shape
+    hd = C // heads
+    y = F.layer_norm(x, (C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
+    qkv = F.linear(y, sd[f"{p}.qkv.weight"]).view(B, T, H, W, 3, heads, hd)
+    dim = 1 + axis
+    L = x.shape[dim]
+    q, k, v = (qkv[:, :, :, :, i].movedim(dim, 4) for i in range(3))  # (B, o1, o2, heads, L, hd)
+    s = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    idx = torch.arange(L)
+    rel = idx[:, None] - idx[None, :] + L - 1  # cuboid_transformer.py:719-734 reduced to one axis
+    s = s + sd[f"{p}.relative_position_bias_table"][rel].permute(2, 0, 1)
+    o = (torch.softmax(s, dim=-1) @ v).movedim(4, dim).reshape(B, T, H, W, C)
+    return F.linear(o, sd[f"{p}.proj.weight"], sd[f"{p}.proj.bias"])
+
+
+def ffn(sd, p, x):
+    """PositionwiseFFN.forward, pre-norm, GELU(erf) (cuboid_transformer.py:182-208)."""
+    C = x.shape[-1]
+    y = F.layer_norm(x, (C,), sd[f"{p}.layer_norm.weight"], sd[f"{p}.layer_norm.bias"], 1e-5)
+    y = F.gelu(F.linear(y, sd[f"{p}.ffn_1.weight"], sd[f"{p}.ffn_1.bias"]))
+    return F.linear(y, sd[f"{p}.ffn_2.weight"], sd[f"{p}.ffn_2.bias"]) + x
+
+
+def stack_block(sd, p, x, heads):
+    """StackCuboidSelfAttentionBlock.forward with use_inter_ffn (cuboid_transformer.py:1147-1156), axial."""
+    for i in range(3):
+        x = x + axial_attention(sd, f"{p}.attn_l.{i}", x, heads, i)
+        x = ffn(sd, f"{p}.ffn_l.{i}", x)
+    return x
+
+
+def patch_merge(sd, p, x):
+    """PatchMerging3D.forward, downsample (1,2,2) (cuboid_transformer.py:261-296)."""
+    B, T, H, W, C = x.shape
+    x = x.reshape(B, T, H // 2, 2, W // 2, 2, C).permute(0, 1, 2, 4, 3, 5, 6).reshape(B, T, H // 2, W // 2, 4 * C)
+    x = F.layer_norm(x, (4 * C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
+    return F.linear(x, sd[f"{p}.reduction.weight"])
+
+
+def upsample3d(sd, p, x):
+    """Upsample3DLayer.forward, no temporal upsample (cuboid_transformer.py:353-375)."""
+    B, T, H, W, C = x.shape
+    y = x.reshape(B * T, H, W, C).permute(0, 3, 1, 2)
+    y = F.interpolate(y, scale_factor=2, mode="nearest")
+    y = F.conv2d(y, sd[f"{p}.conv.weight"], sd[f"{p}.conv.bias"], padding=1)
+    return y.permute(0, 2, 3, 1).reshape(B, T, 2 * H, 2 * W, -1)
+
+
+def unet_forward(sd, cfg, x, t, cond):
+    """CuboidTransformerUNet.forward (src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py:406-493).
+    x (B,T_out,H,W,C), t (B,) int64, cond (B,T_in,H,W,C) -> (B,T_out,H,W,C)."""
+    heads = cfg.num_heads
+    x = torch.cat([cond, x], dim=1)
+    ind = torch.ones_like(x[..., :1])
+    ind[:, cfg.t_in:] = 0.0
+    x = torch.cat([x, ind], dim=-1).permute(0, 4, 1, 2, 3)
+    cin = cfg.c + 1
+    x = _res_block3d(sd, "first_proj", x, None, _gn_groups(cin), _gn_groups(cfg.units[0]))
+    x = x.permute(0, 2, 3, 4, 1)
+    B, T, H, W, C = x.shape
+    # PosEmbed 't+h+w' (cuboid_transformer.py:78-85)
+    x = x + sd["pos_embed.T_embed.weight"].reshape(T, 1, 1, C) + sd["pos_embed.H_embed.weight"].reshape(1, H, 1, C) \
+        + sd["pos_embed.W_embed.weight"].reshape(1, 1, W, C)
+    # TimeEmbedLayer (time_embed.py:16-24)
+    e = timestep_embedding(t, cfg.units[0])
+    e = F.linear(e, sd["time_embed.layer.0.weight"], sd["time_embed.layer.0.bias"])
+    t_emb = F.linear(F.silu(e), sd["time_embed.layer.2.weight"], sd["time_embed.layer.2.bias"])
+
+    def level(name_t, name_s, lvl, x):
+        g = _gn_groups(cfg.units[lvl])
+        for d in range(cfg.depth[lvl]):
+            x = _res_block3d(sd, f"{name_t}.{lvl}", x.permute(0, 4, 1, 2, 3), t_emb, g, g).permute(0, 2, 3, 4, 1)
+            x = stack_block(sd, f"{name_s}.{lvl}.{d}", x, heads)
+        return x
+
+    x = level("down_time_embed_blocks", "down_self_blocks", 0, x)
+    skip = x
+    x = patch_merge(sd, "downsample_layers.0", x)
+    x = level("down_time_embed_blocks", "down_self_blocks", 1, x)
+    x = level("up_time_embed_blocks", "up_self_blocks", 1, x)
+    x = upsample3d(sd, "upsample_layers.0", x)
+    x = x + skip
+    x = level("up_time_embed_blocks", "up_self_blocks", 0, x)
+    return F.linear(x[:, cfg.t_in:], sd["final_proj.weight"], sd["final_proj.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- VAE
+
+
+def _resnet2d(sd, p, x, groups):
+    """ResnetBlock2D.forward without temb (src/prediff/taming/resnet.py:454-495), eps 1e-6."""
+    h = F.silu(F.group_norm(x, groups, sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], 1e-6))
+    h = F.conv2d(h, sd[f"{p}.conv1.weight"], sd[f"{p}.conv1.bias"], padding=1)
+    h = F.silu(F.group_norm(h, groups, sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], 1e-6))
+    h = F.conv2d(h, sd[f"{p}.conv2.weight"], sd[f"{p}.conv2.bias"], padding=1)
+    if f"{p}.conv_shortcut.weight" in sd:
+        x = F.conv2d(x, sd[f"{p}.conv_shortcut.weight"], sd[f"{p}.conv_shortcut.bias"])
+    return x + h
+
+
+def _attn_block(sd, p, x, groups):
+    """AttentionBlock.forward, single head (src/prediff/taming/attention.py:136-189)."""
+    N, C, H, W = x.shape
+    h = F.group_norm(x, groups, sd[f"{p}.group_norm.weight"], sd[f"{p}.group_norm.bias"], 1e-6)
+    h = h.view(N, C, H * W).transpose(1, 2)
+    q = F.linear(h, sd[f"{p}.query.weight"], sd[f"{p}.query.bias"])
+    k = F.linear(h, sd[f"{p}.key.weight"], sd[f"{p}.key.bias"])
+    v = F.linear(h, sd[f"{p}.value.weight"], sd[f"{p}.value.bias"])
+    s = torch.softmax((q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(C)), dim=-1)
+    o = F.linear(s @ v, sd[f"{p}.proj_attn.weight"], sd[f"{p}.proj_attn.bias"])
+    return o.transpose(-1, -2).reshape(N, C, H, W) + x
+
+
+def _mid_block(sd, p, x, groups):
+    """UNetMidBlock2D.forward (src/prediff/taming/unet_2d_blocks.py:158-165)."""
+    x = _resnet2d(sd, f"{p}.resnets.0", x, groups)
+    x = _attn_block(sd, f"{p}.attentions.0", x, groups)
+    return _resnet2d(sd, f"{p}.resnets.1", x, groups)
+
+
+def vae_encode_moments(sd, cfg, x):
+    """AutoencoderKL.encode up to the moments tensor (autoencoder_kl.py:80-84; Encoder.forward vae.py:70-86;
+    DownEncoderBlock2D unet_2d_blocks.py:217-225; Downsample2D resnet.py:181-190). x (N,1,H,W) -> (N,2*latent,h,w)."""
+    g = cfg.norm_num_groups
+    boc = cfg.block_out_channels
+    h = F.conv2d(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    for i in range(len(boc)):
+        for j in range(cfg.layers_per_block):
+            h = _resnet2d(sd, f"encoder.down_blocks.{i}.resnets.{j}", h, g)
+        if i != len(boc) - 1:
+            p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"{p}.weight"], sd[f"{p}.bias"], stride=2)
+    h = _mid_block(sd, "encoder.mid_block", h, g)
+    h = F.silu(F.group_norm(h, g, sd["encoder.conv_norm_out.weight"], sd["encoder.conv_norm_out.bias"], 1e-6))
+    h = F.conv2d(h, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def vae_encode_mode(sd, cfg, x):
+    """DiagonalGaussianDistribution.mode() = mean = first half of the channels
+    (src/prediff/utils/distributions.py:26-33,70-71)."""
+    return vae_encode_moments(sd, cfg, x)[:, :cfg.latent_channels]
+
+
+def vae_decode(sd, cfg, z):
+    """AutoencoderKL.decode (autoencoder_kl.py:86-113; Decoder.forward vae.py:150-166; UpDecoderBlock2D
+    unet_2d_blocks.py:271-279; Upsample2D resnet.py:108-143). z (N,latent,h,w) -> (N,1,H,W)."""
+    g = cfg.norm_num_groups
+    boc = cfg.block_out_channels
+    h = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    h = F.conv2d(h, sd["decoder.conv_in.weight"], sd["decoder.conv_in.bias"], padding=1)
+    h = _mid_block(sd, "decoder.mid_block", h, g)
+    for i in range(len(boc)):
+        for j in range(cfg.layers_per_block + 1):
+            h = _resnet2d(sd, f"decoder.up_blocks.{i}.resnets.{j}", h, g)
+        if i != len(boc) - 1:
+            p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = F.conv2d(h, sd[f"{p}.weight"], sd[f"{p}.bias"], padding=1)
+    h = F.silu(F.group_norm(h, g, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], 1e-6))
+    return F.conv2d(h, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+
+
+# ----------------------------------------------------------------------------------------------- sampler
+
+
+def p_sample_ddpm(sched, eps, z, t, noise, guide=None):
+    """One ancestral step given the model output eps: predict_start_from_noise + q_posterior + p_sample
+    (latent_diffusion.py:553-566,598-631; clip_denoised False, temperature 1); optional knowledge-alignment shift
+    `guide` (aligned_mean, latent_diffusion.py:592-596). t: python int shared by the batch."""
+    z0 = sched["sqrt_recip_alphas_cumprod"][t] * z - sched["sqrt_recipm1_alphas_cumprod"][t] * eps
+    mean = sched["posterior_mean_coef1"][t] * z0 + sched["posterior_mean_coef2"][t] * z
+    logvar = sched["posterior_log_variance_clipped"][t]
+    if guide is not None:
+        mean = mean - (0.5 * logvar).exp() * guide
+    nonzero = 0.0 if t == 0 else 1.0
+    return mean + nonzero * (0.5 * logvar).exp() * noise
+
+
+def sample_loop_ddpm(sd, cfg, sched, z, cond, noise, n_steps):
+    """p_sample_loop (latent_diffusion.py:633-684) with `timesteps=n_steps`, x_T = z, and the per-step
+    torch.randn replaced by the pre-generated noise[k] (k-th executed step)."""
+    for k, i in enumerate(reversed(range(n_steps))):
+        t = torch.full((z.shape[0],), i, dtype=torch.long)
+        eps = unet_forward(sd, cfg, z, t, cond)
+        z = p_sample_ddpm(sched, eps, z, i, noise[k])
+    return z
+
+
+def ddim_coefficients(sched, n_steps, eta=0.0):
+    """Per-step (t, a_t, a_prev, sigma) for the S6 DDIM definition built from the
+    reference helpers diffusion/utils.py:42-70, iterated from the largest timestep down."""
+    ac = sched["alphas_cumprod"].numpy()
+    ts = ddim_timesteps(n_steps, ac.shape[0])
+    sig, a, a_prev = ddim_params(ac, ts, eta)
+    return [(int(ts[i]), float(a[i]), float(a_prev[i]), float(sig[i])) for i in reversed(range(len(ts)))]
+
+
+def sample_loop_ddim(sd, cfg, sched, z, cond, n_steps, eta=0.0, noise=None):
+    """50-step DDIM (eta=0 deterministic): z0 = (z - sqrt(1-a_t) eps)/sqrt(a_t);
+    z <- sqrt(a_prev) z0 + sqrt(1 - a_prev - sigma^2) eps + sigma noise."""
+    for k, (t, a_t, a_prev, sigma) in enumerate(ddim_coefficients(sched, n_steps, eta)):
+        tt = torch.full((z.shape[0],), t, dtype=torch.long)
+        eps = unet_forward(sd, cfg, z, tt, cond)
+        z0 = (z - math.sqrt(1.0 - a_t) * eps) / math.sqrt(a_t)
+        z = math.sqrt(a_prev) * z0 + math.sqrt(max(1.0 - a_prev - sigma ** 2, 0.0)) * eps
+        if noise is not None and sigma > 0:
+            z = z + sigma * noise[k]
+    return z
+
+
+def to_torch_sd(np_sd):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np_sd.items()}

@@ -1,0 +1,81 @@
+// extern "C" model-level entry points (include/prediff_b200.h): UNet, sampler. (VAE: api_vae.cu)
+#include "sampler_host.cuh"
+#include "unet.cuh"
+
+using namespace pd;
+
+struct pd_unet {
+    UNet impl;
+    explicit pd_unet(const pd_unet_config& c) : impl(c) {}
+};
+struct pd_sampler {
+    Sampler impl;
+    pd_sampler(int n, double a, double b) : impl(n, a, b) {}
+};
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+}
+
+extern "C" {
+
+int pd_unet_create(const pd_unet_config* cfg, pd_unet** out) {
+    PD_CHECK(cfg && out, PD_ERR_ARG, "pd_unet_create: null argument");
+    pd_unet* m = new (std::nothrow) pd_unet(*cfg);
+    PD_CHECK(m, PD_ERR_CUDA, "pd_unet_create: out of host memory");
+    const int rc = m->impl.validate();
+    if (rc != PD_OK) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return PD_OK;
+}
+void pd_unet_destroy(pd_unet* m) { delete m; }
+int pd_unet_num_weights(const pd_unet* m) { return m ? m->impl.ws.size() : 0; }
+int pd_unet_weight_info(const pd_unet* m, int i, const char** name, int64_t shape[5]) {
+    PD_CHECK(m && name && shape && i >= 0 && i < m->impl.ws.size(), PD_ERR_ARG, "pd_unet_weight_info: bad argument");
+    const WeightEntry& e = m->impl.ws.at(i);
+    *name = e.name.c_str();
+    for (size_t d = 0; d < 5; ++d) shape[d] = d < e.shape.size() ? e.shape[d] : 0;
+    return (int)e.shape.size();
+}
+int pd_unet_load_weight(pd_unet* m, const char* name, const float* data, const int64_t* shape, int ndim) {
+    PD_CHECK(m, PD_ERR_ARG, "pd_unet_load_weight: null model");
+    m->impl.finalized = false;
+    return m->impl.ws.load(name, data, shape, ndim);
+}
+int pd_unet_finalize(pd_unet* m) {
+    PD_CHECK(m, PD_ERR_ARG, "pd_unet_finalize: null model");
+    return m->impl.finalize();
+}
+int pd_unet_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
+                    void* stream) {
+    PD_CHECK(m, PD_ERR_ARG, "pd_unet_forward: null model");
+    return m->impl.forward(x, t, nullptr, cond, out, batch, S(stream));
+}
+
+int pd_sampler_create(int num_timesteps, double linear_start, double linear_end, pd_sampler** out) {
+    PD_CHECK(out && num_timesteps >= 2 && linear_start > 0 && linear_end > linear_start, PD_ERR_ARG,
+             "pd_sampler_create: bad argument");
+    *out = new (std::nothrow) pd_sampler(num_timesteps, linear_start, linear_end);
+    PD_CHECK(*out, PD_ERR_CUDA, "pd_sampler_create: out of host memory");
+    return PD_OK;
+}
+void pd_sampler_destroy(pd_sampler* s) { delete s; }
+int pd_sampler_get_buffer(const pd_sampler* s, const char* name, float* out) {
+    PD_CHECK(s, PD_ERR_ARG, "pd_sampler_get_buffer: null sampler");
+    return s->impl.get_buffer(name, out);
+}
+int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int mode,
+                   int n_steps, float eta, void* stream) {
+    PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_loop: null handle");
+    return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, S(stream));
+}
+int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
+                        void* stream) {
+    PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_step_ddpm: null handle");
+    return s->impl.step_ddpm(&unet->impl, z, cond, noise, batch, t, S(stream));
+}
+
+}  // extern "C"

@@ -85,7 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
                 ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
                                  z0 + p.dz[tap], sample);
-                ptx::tma_load_2d(sa + kABytes, &tmap_b, &full_bar[s], it * kGemmBlockK, n0);
+                ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], it * kGemmBlockK, n0, p.b_batched ? sample : 0);
                 if (++cb == p.cblks) { cb = 0; ++tap; }
             }
         }
@@ -133,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float4 addv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) addv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             if (p.rowvec) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)sample * p.N + col));
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)sample * p.rowvec_ld + col));
                 addv.x += r.x; addv.y += r.y; addv.z += r.z; addv.w += r.w;
             }
 #pragma unroll
@@ -278,11 +278,14 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     PD_CHECK(N % bn == 0, PD_ERR_SHAPE, "gemm: N %d not a multiple of BLOCK_N %d", N, bn);
     {
         const int64_t ktot = (int64_t)g.ntaps * g.C;
-        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)N};
-        cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)bn};
-        cuuint32_t es[2] = {1, 1};
-        CUresult r = g_encode(&op->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(Wt), dims, strides, box,
+        const int64_t ldb = g.ldb ? g.ldb : ktot;
+        const int nb = g.b_sample_stride ? g.samples : 1;
+        const int64_t bs = g.b_sample_stride ? g.b_sample_stride : ldb * N;
+        cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)N, (cuuint64_t)nb};
+        cuuint64_t strides[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)bs * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)bn, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = g_encode(&op->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(Wt), dims, strides, box,
                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
@@ -299,6 +302,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.HW = g.H * g.W;
     p.ntaps = g.ntaps;
     p.cblks = g.C / kGemmBlockK;
+    p.b_batched = g.b_sample_stride ? 1 : 0;
     memcpy(p.dz, g.dz, sizeof(p.dz));
     memcpy(p.dy, g.dy, sizeof(p.dy));
     memcpy(p.dx, g.dx, sizeof(p.dx));
@@ -309,6 +313,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.out_bf16 = e.out_bf16;
     p.ldo = ldo;
     p.act = e.act;
+    p.rowvec_ld = e.rowvec_ld ? e.rowvec_ld : N;
     op->block_n = bn;
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);

@@ -27,6 +27,9 @@ struct GemmGeom {
     int8_t dz[kMaxTaps] = {0}, dy[kMaxTaps] = {0}, dx[kMaxTaps] = {0};
     // strides of A in elements, in case the activation buffer is a view (default: dense channels-last)
     int64_t sW = 0, sH = 0, sD = 0, sN = 0;
+    // B operand: row stride in elements (0 -> ntaps*C) and, for a per-sample B (attention: K or V^T of that
+    // sample instead of shared weights), the element stride between samples (0 -> shared)
+    int64_t ldb = 0, b_sample_stride = 0;
 
     static GemmGeom linear(int M, int K) {
         GemmGeom g;
@@ -68,7 +71,8 @@ struct GemmGeom {
 
 struct GemmEpilogue {
     const float* bias = nullptr;      // [N]
-    const float* rowvec = nullptr;    // [samples][N], added to every row of the sample (time embedding)
+    const float* rowvec = nullptr;    // [samples][rowvec_ld], added to every row of the sample (time embedding)
+    int rowvec_ld = 0;                // row stride of rowvec in elements (0 -> N)
     const float* residual = nullptr;  // [M][ldo] fp32, may alias out_f32
     float* out_f32 = nullptr;         // [M][ldo]
     bf16* out_bf16 = nullptr;         // [M][ldo]
@@ -79,14 +83,14 @@ struct GemmEpilogue {
 struct GemmKernelParams {
     int rows_per_sample, tiles_per_sample, samples;
     int N, H, W, HW;
-    int ntaps, cblks;
+    int ntaps, cblks, b_batched;
     int8_t dz[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps];
     const float* bias;
     const float* rowvec;
     const float* residual;
     float* out_f32;
     bf16* out_bf16;
-    int ldo, act;
+    int ldo, act, rowvec_ld;
 };
 
 struct GemmOp {

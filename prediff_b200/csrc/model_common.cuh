@@ -1,0 +1,155 @@
+// Host-side plumbing shared by the UNet / VAE programs: named fp32 weight store (reference state_dict keys),
+// device buffers, a bump arena for activations, and the "plan" - the list of kernel launches one forward is.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+#include <cstdarg>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pd {
+
+struct DevMem {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevMem() = default;
+    DevMem(const DevMem&) = delete;
+    DevMem& operator=(const DevMem&) = delete;
+    ~DevMem() { release(); }
+    int alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        PD_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+        return PD_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+// Bump allocator over one device block; every allocation is 1 KiB aligned (TMA needs 16 B, keep tiles apart).
+class Arena {
+public:
+    int reserve(size_t bytes) { used_ = 0; return mem_.alloc(bytes); }
+    template <class T>
+    T* take(size_t count) {
+        const size_t b = (size_t)round_up64((int64_t)(count * sizeof(T)), 1024);
+        if (used_ + b > mem_.bytes) { overflow_ = true; return nullptr; }
+        T* r = reinterpret_cast<T*>(static_cast<uint8_t*>(mem_.p) + used_);
+        used_ += b;
+        return r;
+    }
+    bool overflowed() const { return overflow_; }
+    size_t used() const { return used_; }
+    size_t capacity() const { return mem_.bytes; }
+private:
+    DevMem mem_;
+    size_t used_ = 0;
+    bool overflow_ = false;
+};
+
+// Sizing pass: same take() calls against a null arena to learn the byte count.
+class ArenaSizer {
+public:
+    template <class T>
+    T* take(size_t count) {
+        used_ += (size_t)round_up64((int64_t)(count * sizeof(T)), 1024);
+        return nullptr;
+    }
+    size_t used() const { return used_; }
+private:
+    size_t used_ = 0;
+};
+
+struct WeightEntry {
+    std::string name;
+    std::vector<int64_t> shape;
+    int64_t numel = 0;
+    std::unique_ptr<DevMem> data;  // fp32, reference layout; null until loaded
+};
+
+class WeightStore {
+public:
+    void declare(const std::string& name, std::vector<int64_t> shape) {
+        WeightEntry e;
+        e.name = name;
+        e.numel = 1;
+        for (auto d : shape) e.numel *= d;
+        e.shape = std::move(shape);
+        index_[name] = (int)entries_.size();
+        entries_.push_back(std::move(e));
+    }
+    int size() const { return (int)entries_.size(); }
+    const WeightEntry& at(int i) const { return entries_[i]; }
+    int load(const char* name, const float* src, const int64_t* shape, int ndim) {
+        PD_CHECK(name && src && shape, PD_ERR_ARG, "load_weight: null argument");
+        auto it = index_.find(name);
+        PD_CHECK(it != index_.end(), PD_ERR_WEIGHT, "load_weight: unknown key '%s'", name);
+        WeightEntry& e = entries_[it->second];
+        bool same = ndim == (int)e.shape.size();
+        for (int i = 0; same && i < ndim; ++i) same = shape[i] == e.shape[i];
+        PD_CHECK(same, PD_ERR_WEIGHT, "load_weight: shape mismatch for '%s'", name);
+        if (!e.data) {
+            e.data.reset(new DevMem());
+            PD_TRY(e.data->alloc((size_t)e.numel * sizeof(float)));
+        }
+        PD_CUDA(cudaMemcpy(e.data->p, src, (size_t)e.numel * sizeof(float), cudaMemcpyDefault));
+        return PD_OK;
+    }
+    // nullptr + error if missing
+    const float* get(const std::string& name) const {
+        auto it = index_.find(name);
+        if (it == index_.end() || !entries_[it->second].data) {
+            set_error("weight '%s' was not loaded", name.c_str());
+            return nullptr;
+        }
+        return entries_[it->second].data->as<float>();
+    }
+    int check_complete() const {
+        for (const auto& e : entries_)
+            PD_CHECK(e.data != nullptr, PD_ERR_WEIGHT, "finalize: weight '%s' was never loaded", e.name.c_str());
+        return PD_OK;
+    }
+private:
+    std::vector<WeightEntry> entries_;
+    std::map<std::string, int> index_;
+};
+
+using Step = std::function<int(cudaStream_t)>;
+
+struct Plan {
+    std::vector<Step> steps;
+    double gemm_flops = 0;
+    int n_gemm = 0;
+    int run(cudaStream_t st) const {
+        for (const auto& s : steps) PD_TRY(s(st));
+        return PD_OK;
+    }
+    void add(Step s) { steps.push_back(std::move(s)); }
+    void add_gemm(const GemmOp& op) {
+        gemm_flops += op.flops;
+        ++n_gemm;
+        steps.push_back([op](cudaStream_t st) { return gemm_launch(op, st); });
+    }
+};
+
+inline std::string strf(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+inline std::string strf(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return buf;
+}
+
+}  // namespace pd

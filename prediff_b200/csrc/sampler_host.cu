@@ -1,0 +1,196 @@
+#include "sampler_host.cuh"
+#include <cmath>
+#include <cstdlib>
+
+namespace pd {
+
+Sampler::Sampler(int num_timesteps, double linear_start, double linear_end) : T(num_timesteps) {
+    // "linear" beta schedule: linspace(sqrt(start), sqrt(end), T)^2 in float64 (diffusion/utils.py:17-22)
+    std::vector<double> betas(T), ac(T), ac_prev(T);
+    const double s0 = std::sqrt(linear_start), s1 = std::sqrt(linear_end);
+    double cp = 1.0;
+    for (int i = 0; i < T; ++i) {
+        // torch.linspace(float64): start + i*step for the first half, end - (T-1-i)*step for the second half
+        const double step = (s1 - s0) / (double)(T - 1);
+        const double v = (i < T / 2) ? s0 + step * i : s1 - step * (T - 1 - i);
+        betas[i] = v * v;
+        ac_prev[i] = cp;
+        cp *= (1.0 - betas[i]);
+        ac[i] = cp;
+    }
+    auto put = [&](const char* name, auto fn) {
+        std::vector<float> v(T);
+        for (int i = 0; i < T; ++i) v[i] = (float)fn(i);
+        buf_[name] = std::move(v);
+    };
+    auto pv = [&](int i) { return betas[i] * (1.0 - ac_prev[i]) / (1.0 - ac[i]); };
+    put("betas", [&](int i) { return betas[i]; });
+    put("alphas_cumprod", [&](int i) { return ac[i]; });
+    put("alphas_cumprod_prev", [&](int i) { return ac_prev[i]; });
+    put("sqrt_alphas_cumprod", [&](int i) { return std::sqrt(ac[i]); });
+    put("sqrt_one_minus_alphas_cumprod", [&](int i) { return std::sqrt(1.0 - ac[i]); });
+    put("log_one_minus_alphas_cumprod", [&](int i) { return std::log(1.0 - ac[i]); });
+    put("sqrt_recip_alphas_cumprod", [&](int i) { return std::sqrt(1.0 / ac[i]); });
+    put("sqrt_recipm1_alphas_cumprod", [&](int i) { return std::sqrt(1.0 / ac[i] - 1.0); });
+    put("posterior_variance", pv);
+    put("posterior_log_variance_clipped", [&](int i) { return std::log(std::max(pv(i), 1e-20)); });
+    put("posterior_mean_coef1", [&](int i) { return betas[i] * std::sqrt(ac_prev[i]) / (1.0 - ac[i]); });
+    put("posterior_mean_coef2", [&](int i) { return (1.0 - ac_prev[i]) * std::sqrt(1.0 - betas[i]) / (1.0 - ac[i]); });
+}
+
+Sampler::~Sampler() { drop_graph(); }
+
+void Sampler::drop_graph() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    graph_exec_ = nullptr;
+}
+
+int Sampler::get_buffer(const char* name, float* out) const {
+    PD_CHECK(name && out, PD_ERR_ARG, "sampler_get_buffer: null argument");
+    auto it = buf_.find(name);
+    PD_CHECK(it != buf_.end(), PD_ERR_ARG, "sampler_get_buffer: unknown buffer '%s'", name);
+    memcpy(out, it->second.data(), (size_t)T * sizeof(float));
+    return PD_OK;
+}
+
+int Sampler::coefficients(int mode, int n_steps, float eta, std::vector<float>* rows, std::vector<int64_t>* ts) const {
+    PD_CHECK(n_steps >= 1 && n_steps <= T, PD_ERR_ARG, "sampler: n_steps %d outside [1, %d]", n_steps, T);
+    rows->assign((size_t)n_steps * 8, 0.f);
+    ts->assign(n_steps, 0);
+    if (mode == PD_MODE_DDPM) {
+        // p_sample_loop: for i in reversed(range(timesteps)) (latent_diffusion.py:663)
+        const auto& r = buf_.at("sqrt_recip_alphas_cumprod");
+        const auto& rm1 = buf_.at("sqrt_recipm1_alphas_cumprod");
+        const auto& c1 = buf_.at("posterior_mean_coef1");
+        const auto& c2 = buf_.at("posterior_mean_coef2");
+        const auto& lv = buf_.at("posterior_log_variance_clipped");
+        for (int k = 0; k < n_steps; ++k) {
+            const int t = n_steps - 1 - k;
+            float* c = rows->data() + (size_t)k * 8;
+            const float sigma = std::exp(0.5f * lv[t]);
+            c[0] = r[t]; c[1] = rm1[t]; c[2] = c1[t]; c[3] = c2[t]; c[4] = 0.f;
+            c[5] = t == 0 ? 0.f : sigma;   // no noise when t == 0 (latent_diffusion.py:624-626)
+            c[6] = sigma;                  // aligned_mean: mean - exp(0.5 logvar) * grad (:594-595)
+            (*ts)[k] = t;
+        }
+    } else if (mode == PD_MODE_DDIM) {
+        PD_CHECK(T % n_steps == 0 || T / n_steps >= 1, PD_ERR_ARG, "sampler: bad DDIM step count");
+        const auto& ac = buf_.at("alphas_cumprod");
+        const int c = T / n_steps;
+        std::vector<int> steps;
+        for (int i = 0; i < T; i += c) steps.push_back(i + 1);  // make_ddim_timesteps('uniform') (+1)
+        PD_CHECK((int)steps.size() == n_steps && steps.back() < T, PD_ERR_ARG,
+                 "sampler: DDIM with %d steps is not a uniform sub-sequence of %d", n_steps, T);
+        for (int k = 0; k < n_steps; ++k) {
+            const int i = n_steps - 1 - k;
+            const double a = ac[steps[i]];
+            const double a_prev = i == 0 ? ac[0] : ac[steps[i - 1]];
+            const double sigma = (double)eta * std::sqrt((1 - a_prev) / (1 - a) * (1 - a / a_prev));
+            float* cf = rows->data() + (size_t)k * 8;
+            const double c0 = 1.0 / std::sqrt(a), c1 = std::sqrt(1 - a) / std::sqrt(a), c2 = std::sqrt(a_prev);
+            const double c4 = std::sqrt(std::max(1 - a_prev - sigma * sigma, 0.0));
+            cf[0] = (float)c0; cf[1] = (float)c1; cf[2] = (float)c2; cf[3] = 0.f; cf[4] = (float)c4;
+            cf[5] = (float)sigma;
+            cf[6] = (float)((c2 * c1 - c4) * std::sqrt(1 - a));  // eps_hat = eps + sqrt(1-a_t) * guide (S6)
+            (*ts)[k] = steps[i];
+        }
+    } else {
+        set_error("sampler: unknown mode %d", mode);
+        return PD_ERR_ARG;
+    }
+    return PD_OK;
+}
+
+int Sampler::upload_tables(const std::vector<float>& rows, const std::vector<int64_t>& ts, int B, cudaStream_t st) {
+    const int n = (int)ts.size();
+    std::vector<int64_t> tt((size_t)n * B);
+    for (int k = 0; k < n; ++k)
+        for (int b = 0; b < B; ++b) tt[(size_t)k * B + b] = ts[k];
+    if (coef_dev_.bytes < rows.size() * sizeof(float)) PD_TRY(coef_dev_.alloc(rows.size() * sizeof(float)));
+    if (t_dev_.bytes < tt.size() * sizeof(int64_t)) {
+        PD_TRY(t_dev_.alloc(tt.size() * sizeof(int64_t)));
+        drop_graph();
+    }
+    if (!step_dev_.p) PD_TRY(step_dev_.alloc(sizeof(int)));
+    // synchronous small copies: the host vectors die at return
+    PD_CUDA(cudaStreamSynchronize(st));
+    PD_CUDA(cudaMemcpy(coef_dev_.p, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+    PD_CUDA(cudaMemcpy(t_dev_.p, tt.data(), tt.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    PD_CUDA(cudaMemset(step_dev_.p, 0, sizeof(int)));
+    return PD_OK;
+}
+
+int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st) {
+    const int64_t n = (int64_t)B * unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    const int* step = step_dev_.as<int>();
+    PD_TRY(unet->forward(z, t_dev_.as<int64_t>(), step, cond, eps_dev_.as<float>(), B, st));
+    PD_TRY(sampler_update(z, eps_dev_.as<float>(), noise, nullptr, coef_dev_.as<float>(), step, n, st));
+    return advance_step(step_dev_.as<int>(), st);
+}
+
+int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_steps, float eta,
+                  cudaStream_t st) {
+    PD_CHECK(unet && z && cond, PD_ERR_ARG, "sample_loop: null pointer");
+    std::vector<float> rows;
+    std::vector<int64_t> ts;
+    PD_TRY(coefficients(mode, n_steps, eta, &rows, &ts));
+    bool needs_noise = false;
+    for (int k = 0; k < n_steps; ++k) needs_noise |= rows[(size_t)k * 8 + 5] != 0.f;
+    PD_CHECK(!needs_noise || noise, PD_ERR_ARG, "sample_loop: this sampler is stochastic; pass the noise stack");
+    const size_t n = (size_t)B * unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    if (eps_dev_.bytes < n * sizeof(float)) {
+        PD_TRY(eps_dev_.alloc(n * sizeof(float)));
+        drop_graph();
+    }
+    PD_TRY(upload_tables(rows, ts, B, st));
+
+    const bool use_graph = getenv("PD_NO_GRAPH") == nullptr && n_steps > 2;
+    int k = 0;
+    if (use_graph) {
+        const Key key{unet, z, cond, noise, B};
+        if (!graph_exec_ || !(key == graph_key_)) {
+            drop_graph();
+            // first iteration runs eagerly (also performs any lazy one-time kernel attribute setup) ...
+            PD_TRY(one_iteration(unet, z, cond, noise, B, st));
+            k = 1;
+            // ... then one iteration is captured and replayed; the step index lives on the device
+            cudaGraph_t graph = nullptr;
+            PD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = one_iteration(unet, z, cond, noise, B, st);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != PD_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            PD_CUDA(ce);
+            const cudaError_t ie = cudaGraphInstantiate(&graph_exec_, graph, 0);
+            cudaGraphDestroy(graph);
+            PD_CUDA(ie);
+            graph_key_ = key;
+        }
+        for (; k < n_steps; ++k) PD_CUDA(cudaGraphLaunch(graph_exec_, st));
+    } else {
+        for (; k < n_steps; ++k) PD_TRY(one_iteration(unet, z, cond, noise, B, st));
+    }
+    return PD_OK;
+}
+
+int Sampler::step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st) {
+    PD_CHECK(unet && z && cond, PD_ERR_ARG, "sample_step: null pointer");
+    PD_CHECK(t >= 0 && t < T, PD_ERR_ARG, "sample_step: t=%d outside the schedule", t);
+    std::vector<float> rows;
+    std::vector<int64_t> ts;
+    PD_TRY(coefficients(PD_MODE_DDPM, t + 1, 0.f, &rows, &ts));  // row 0 is timestep t
+    rows.resize(8);
+    ts.resize(1);
+    PD_CHECK(rows[5] == 0.f || noise, PD_ERR_ARG, "sample_step: noise required for t > 0");
+    const size_t n = (size_t)B * unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    if (eps_dev_.bytes < n * sizeof(float)) {
+        PD_TRY(eps_dev_.alloc(n * sizeof(float)));
+        drop_graph();
+    }
+    PD_TRY(upload_tables(rows, ts, B, st));
+    return one_iteration(unet, z, cond, noise, B, st);
+}
+
+}  // namespace pd

@@ -1,0 +1,41 @@
+// Noise schedule + device-resident sampling loop.
+// Reference: LatentDiffusion.register_schedule (latent_diffusion.py:228-278), p_sample / p_sample_loop
+// (:598-684), make_ddim_timesteps / make_ddim_sampling_parameters (diffusion/utils.py:42-70).
+#pragma once
+#include "model_common.cuh"
+#include "unet.cuh"
+
+namespace pd {
+
+class Sampler {
+public:
+    Sampler(int num_timesteps, double linear_start, double linear_end);
+    ~Sampler();
+    int get_buffer(const char* name, float* out) const;
+    // Fills rows[k][8] + timesteps[k] for the k-th executed step.
+    int coefficients(int mode, int n_steps, float eta, std::vector<float>* rows, std::vector<int64_t>* ts) const;
+    int loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_steps, float eta,
+             cudaStream_t st);
+    int step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st);
+
+    int T;
+
+private:
+    int upload_tables(const std::vector<float>& rows, const std::vector<int64_t>& ts, int B, cudaStream_t st);
+    int one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st);
+    void drop_graph();
+
+    std::map<std::string, std::vector<float>> buf_;  // the reference's registered fp32 buffers
+    DevMem coef_dev_, t_dev_, step_dev_, eps_dev_;
+    // cached one-iteration graph
+    cudaGraphExec_t graph_exec_ = nullptr;
+    struct Key {
+        const void *unet, *z, *cond, *noise;
+        int B;
+        bool operator==(const Key& o) const {
+            return unet == o.unet && z == o.z && cond == o.cond && noise == o.noise && B == o.B;
+        }
+    } graph_key_{};
+};
+
+}  // namespace pd

@@ -1,0 +1,543 @@
+// CuboidTransformerUNet forward as a static launch plan over the kernels in gemm.cu / norm.cu / attention.cu /
+// elementwise.cu. Reference: src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py:406-493 (forward),
+// time_embed.py:134-169 (TimeEmbedResBlock), cuboid_transformer.py:812-966 (CuboidSelfAttentionLayer),
+// :182-208 (PositionwiseFFN), :261-296 (PatchMerging3D), :353-375 (Upsample3DLayer).
+//
+// Layout: activations stay channels-last [B][T][H][W][C] for the whole network (the reference's 32
+// "b t h w c <-> b c t h w" rearranges and 96 cuboid reorders per step do not exist). The fp32 residual stream x
+// lives in one buffer per level; every tensor a GEMM consumes is written as bf16 by its producer.
+#include "unet.cuh"
+#include <cstdarg>
+
+namespace pd {
+
+namespace {
+constexpr int kCinPad = 128;  // 65 input channels (64 latent + indicator) padded to two 64-wide K blocks
+}
+
+struct UNet::Bufs {
+    float *xin_f32, *x[2], *h[2];
+    bf16 *xin_bf16, *a[2], *ln[2], *qkv[2], *att[2], *mid[2], *pm, *up, *fin;
+    float *e0, *e1, *temb, *embs;
+    double* gn_sums;
+};
+
+struct UNet::BatchPlan {
+    Arena arena;
+    Bufs bufs;
+    Plan plan;
+    GemmOp final_op;
+    size_t t_slot = 0, in_slot = 0, out_slot = 0;
+    Bufs& bufs_storage() { return bufs; }
+};
+
+UNet::~UNet() = default;
+
+UNet::UNet(const pd_unet_config& c) : cfg(c) {
+    C0 = cfg.base_units;
+    C1 = 2 * cfg.base_units;
+    T = cfg.t_in + cfg.t_out;
+    TE = 4 * cfg.base_units;
+    declare_weights();
+}
+
+void UNet::declare_resblock(const std::string& p, int cin, int cout, bool emb) {
+    ws.declare(p + ".in_layers.0.weight", {cin});
+    ws.declare(p + ".in_layers.0.bias", {cin});
+    ws.declare(p + ".in_layers.2.weight", {cout, cin, 3, 3, 3});
+    ws.declare(p + ".in_layers.2.bias", {cout});
+    if (emb) {
+        ws.declare(p + ".emb_layers.1.weight", {cout, TE});
+        ws.declare(p + ".emb_layers.1.bias", {cout});
+    }
+    ws.declare(p + ".out_layers.0.weight", {cout});
+    ws.declare(p + ".out_layers.0.bias", {cout});
+    ws.declare(p + ".out_layers.3.weight", {cout, cout, 3, 3, 3});
+    ws.declare(p + ".out_layers.3.bias", {cout});
+    if (cin != cout) {
+        ws.declare(p + ".skip_connection.weight", {cout, cin, 1, 1, 1});
+        ws.declare(p + ".skip_connection.bias", {cout});
+    }
+}
+
+void UNet::declare_stack(const std::string& p, int dim, int lvl) {
+    const int L[3] = {T, cfg.h >> lvl, cfg.w >> lvl};
+    for (int i = 0; i < 3; ++i) {
+        const std::string f = p + strf(".ffn_l.%d", i);
+        ws.declare(f + ".ffn_1.weight", {4 * dim, dim});
+        ws.declare(f + ".ffn_1.bias", {4 * dim});
+        ws.declare(f + ".ffn_2.weight", {dim, 4 * dim});
+        ws.declare(f + ".ffn_2.bias", {dim});
+        ws.declare(f + ".layer_norm.weight", {dim});
+        ws.declare(f + ".layer_norm.bias", {dim});
+    }
+    for (int i = 0; i < 3; ++i) {
+        const std::string a = p + strf(".attn_l.%d", i);
+        ws.declare(a + ".relative_position_bias_table", {2 * L[i] - 1, cfg.num_heads});
+        ws.declare(a + ".qkv.weight", {3 * dim, dim});
+        ws.declare(a + ".proj.weight", {dim, dim});
+        ws.declare(a + ".proj.bias", {dim});
+        ws.declare(a + ".norm.weight", {dim});
+        ws.declare(a + ".norm.bias", {dim});
+    }
+}
+
+// Same names, shapes and order as the reference's state_dict() (minus derived int64 buffers).
+void UNet::declare_weights() {
+    declare_resblock("first_proj", cfg.c + 1, C0, false);
+    ws.declare("pos_embed.T_embed.weight", {T, C0});
+    ws.declare("pos_embed.H_embed.weight", {cfg.h, C0});
+    ws.declare("pos_embed.W_embed.weight", {cfg.w, C0});
+    ws.declare("time_embed.layer.0.weight", {TE, C0});
+    ws.declare("time_embed.layer.0.bias", {TE});
+    ws.declare("time_embed.layer.2.weight", {TE, TE});
+    ws.declare("time_embed.layer.2.bias", {TE});
+    ws.declare("downsample_layers.0.reduction.weight", {C1, 4 * C0});
+    ws.declare("downsample_layers.0.norm.weight", {4 * C0});
+    ws.declare("downsample_layers.0.norm.bias", {4 * C0});
+    ws.declare("upsample_layers.0.conv.weight", {C0, C1, 3, 3});
+    ws.declare("upsample_layers.0.conv.bias", {C0});
+    const char* sb[2] = {"down_self_blocks", "up_self_blocks"};
+    for (const char* n : sb)
+        for (int lvl = 0; lvl < 2; ++lvl)
+            for (int d = 0; d < cfg.depth[lvl]; ++d) declare_stack(strf("%s.%d.%d", n, lvl, d), lvl ? C1 : C0, lvl);
+    const char* tb[2] = {"down_time_embed_blocks", "up_time_embed_blocks"};
+    for (const char* n : tb)
+        for (int lvl = 0; lvl < 2; ++lvl) declare_resblock(strf("%s.%d", n, lvl), lvl ? C1 : C0, lvl ? C1 : C0, true);
+    ws.declare("final_proj.weight", {cfg.c, C0});
+    ws.declare("final_proj.bias", {cfg.c});
+}
+
+int UNet::validate() const {
+    PD_CHECK(cfg.t_in > 0 && cfg.t_out > 0 && T <= 16, PD_ERR_SHAPE, "unet: t_in + t_out = %d must be <= 16", T);
+    PD_CHECK(cfg.h <= 16 && cfg.w <= 16 && cfg.h % 2 == 0 && cfg.w % 2 == 0, PD_ERR_SHAPE,
+             "unet: latent H, W must be even and <= 16 (axial lines of <= 16 tokens)");
+    for (int lvl = 0; lvl < 2; ++lvl) {
+        const int hh = cfg.h >> lvl, ww = cfg.w >> lvl;
+        PD_CHECK(128 % ww == 0 && ((hh * ww) % 128 == 0 || 128 % (hh * ww) == 0), PD_ERR_SHAPE,
+                 "unet: H x W = %d x %d incompatible with 128-row tiles", hh, ww);
+    }
+    PD_CHECK(cfg.c % 4 == 0 && cfg.c + 1 <= kCinPad && cfg.c % 32 == 0, PD_ERR_SHAPE, "unet: latent channels %d", cfg.c);
+    PD_CHECK(C0 % 64 == 0 && C0 <= 512, PD_ERR_SHAPE, "unet: base_units %d must be a multiple of 64, <= 512", C0);
+    PD_CHECK(C0 % cfg.num_heads == 0, PD_ERR_SHAPE, "unet: heads");
+    const int hd0 = C0 / cfg.num_heads;
+    PD_CHECK(hd0 == 16 || hd0 == 32 || hd0 == 64, PD_ERR_SHAPE, "unet: head dim %d unsupported", hd0);
+    PD_CHECK(cfg.depth[0] >= 1 && cfg.depth[1] >= 1, PD_ERR_SHAPE, "unet: depth");
+    PD_CHECK(cfg.max_batch >= 1, PD_ERR_SHAPE, "unet: max_batch");
+    return PD_OK;
+}
+
+// ---- weight repacking ---------------------------------------------------------------------------------------
+int UNet::pack_conv_w(const std::string& name, int co, int ci, int taps, int cipad, bf16** out) {
+    const float* w = ws.get(name);
+    if (!w) return PD_ERR_WEIGHT;
+    packed.emplace_back(new DevMem());
+    PD_TRY(packed.back()->alloc((size_t)co * taps * cipad * sizeof(bf16)));
+    *out = packed.back()->as<bf16>();
+    return pack_conv(w, *out, co, ci, taps, cipad, 0);
+}
+int UNet::pack_linear_w(const std::string& name, int n, int k, bf16** out) {
+    const float* w = ws.get(name);
+    if (!w) return PD_ERR_WEIGHT;
+    packed.emplace_back(new DevMem());
+    PD_TRY(packed.back()->alloc((size_t)n * k * sizeof(bf16)));
+    *out = packed.back()->as<bf16>();
+    return pack_linear(w, *out, n, k, k, 0);
+}
+
+#define PD_GETW(dst, name)                      \
+    do {                                        \
+        (dst) = ws.get(name);                   \
+        if (!(dst)) return PD_ERR_WEIGHT;       \
+    } while (0)
+
+int UNet::finalize_resblock(const std::string& p, int cin, int cinpad, int cout, ResW* r) {
+    PD_GETW(r->gn1_w, p + ".in_layers.0.weight");
+    PD_GETW(r->gn1_b, p + ".in_layers.0.bias");
+    PD_GETW(r->conv1_b, p + ".in_layers.2.bias");
+    PD_GETW(r->gn2_w, p + ".out_layers.0.weight");
+    PD_GETW(r->gn2_b, p + ".out_layers.0.bias");
+    PD_GETW(r->conv2_b, p + ".out_layers.3.bias");
+    PD_TRY(pack_conv_w(p + ".in_layers.2.weight", cout, cin, 27, cinpad, &r->conv1_w));
+    PD_TRY(pack_conv_w(p + ".out_layers.3.weight", cout, cout, 27, cout, &r->conv2_w));
+    return PD_OK;
+}
+
+int UNet::finalize_stack(const std::string& p, int dim, StackW* s) {
+    for (int i = 0; i < 3; ++i) {
+        const std::string a = p + strf(".attn_l.%d", i), f = p + strf(".ffn_l.%d", i);
+        PD_GETW(s->a[i].ln_w, a + ".norm.weight");
+        PD_GETW(s->a[i].ln_b, a + ".norm.bias");
+        PD_GETW(s->a[i].table, a + ".relative_position_bias_table");
+        PD_GETW(s->a[i].proj_b, a + ".proj.bias");
+        PD_TRY(pack_linear_w(a + ".qkv.weight", 3 * dim, dim, &s->a[i].qkv_w));
+        PD_TRY(pack_linear_w(a + ".proj.weight", dim, dim, &s->a[i].proj_w));
+        PD_GETW(s->f[i].ln_w, f + ".layer_norm.weight");
+        PD_GETW(s->f[i].ln_b, f + ".layer_norm.bias");
+        PD_GETW(s->f[i].b1, f + ".ffn_1.bias");
+        PD_GETW(s->f[i].b2, f + ".ffn_2.bias");
+        PD_TRY(pack_linear_w(f + ".ffn_1.weight", 4 * dim, dim, &s->f[i].w1));
+        PD_TRY(pack_linear_w(f + ".ffn_2.weight", dim, 4 * dim, &s->f[i].w2));
+    }
+    return PD_OK;
+}
+
+int UNet::finalize() {
+    PD_TRY(gemm_init());
+    PD_TRY(validate());
+    PD_TRY(ws.check_complete());
+    packed.clear();
+    plans.clear();
+    const int cin = cfg.c + 1;
+    // first_proj: GroupNorm over 65 channels = 65 groups (time_embed.py:90); padded to 128 one-channel groups with
+    // zero gamma/beta so the padded lanes stay exactly zero.
+    PD_TRY(finalize_resblock("first_proj", cin, kCinPad, C0, &first));
+    PD_TRY(pack_conv_w("first_proj.skip_connection.weight", C0, cin, 1, kCinPad, &first_skip_w));
+    PD_GETW(first_skip_b, "first_proj.skip_connection.bias");
+    PD_TRY(first_gn_pad.alloc(2 * kCinPad * sizeof(float)));
+    PD_CUDA(cudaMemset(first_gn_pad.p, 0, 2 * kCinPad * sizeof(float)));
+    PD_CUDA(cudaMemcpy(first_gn_pad.as<float>(), first.gn1_w, cin * sizeof(float), cudaMemcpyDeviceToDevice));
+    PD_CUDA(cudaMemcpy(first_gn_pad.as<float>() + kCinPad, first.gn1_b, cin * sizeof(float), cudaMemcpyDeviceToDevice));
+    first.gn1_w = first_gn_pad.as<float>();
+    first.gn1_b = first_gn_pad.as<float>() + kCinPad;
+
+    PD_GETW(pos_T, "pos_embed.T_embed.weight");
+    PD_GETW(pos_H, "pos_embed.H_embed.weight");
+    PD_GETW(pos_W, "pos_embed.W_embed.weight");
+    PD_GETW(te_w0, "time_embed.layer.0.weight");
+    PD_GETW(te_b0, "time_embed.layer.0.bias");
+    PD_GETW(te_w2, "time_embed.layer.2.weight");
+    PD_GETW(te_b2, "time_embed.layer.2.bias");
+
+    // the four per-block embedding Linears share their input SiLU(t_emb): concatenate into one small linear
+    emb_total = 2 * (C0 + C1);
+    PD_TRY(emb_cat.alloc(((size_t)emb_total * TE + emb_total) * sizeof(float)));
+    {
+        const char* names[4] = {"down_time_embed_blocks.0", "down_time_embed_blocks.1", "up_time_embed_blocks.0",
+                                "up_time_embed_blocks.1"};
+        const int dims[4] = {C0, C1, C0, C1};
+        int off = 0;
+        float* wcat = emb_cat.as<float>();
+        float* bcat = wcat + (size_t)emb_total * TE;
+        for (int i = 0; i < 4; ++i) {
+            const float *w, *b;
+            PD_GETW(w, std::string(names[i]) + ".emb_layers.1.weight");
+            PD_GETW(b, std::string(names[i]) + ".emb_layers.1.bias");
+            PD_CUDA(cudaMemcpy(wcat + (size_t)off * TE, w, (size_t)dims[i] * TE * sizeof(float), cudaMemcpyDeviceToDevice));
+            PD_CUDA(cudaMemcpy(bcat + off, b, dims[i] * sizeof(float), cudaMemcpyDeviceToDevice));
+            emb_off[i] = off;
+            off += dims[i];
+        }
+    }
+    for (int lvl = 0; lvl < 2; ++lvl) {
+        const int dim = lvl ? C1 : C0;
+        PD_TRY(finalize_resblock(strf("down_time_embed_blocks.%d", lvl), dim, dim, dim, &down_res[lvl]));
+        PD_TRY(finalize_resblock(strf("up_time_embed_blocks.%d", lvl), dim, dim, dim, &up_res[lvl]));
+        down_stack[lvl].resize(cfg.depth[lvl]);
+        up_stack[lvl].resize(cfg.depth[lvl]);
+        for (int d = 0; d < cfg.depth[lvl]; ++d) {
+            PD_TRY(finalize_stack(strf("down_self_blocks.%d.%d", lvl, d), dim, &down_stack[lvl][d]));
+            PD_TRY(finalize_stack(strf("up_self_blocks.%d.%d", lvl, d), dim, &up_stack[lvl][d]));
+        }
+    }
+    PD_GETW(pm_ln_w, "downsample_layers.0.norm.weight");
+    PD_GETW(pm_ln_b, "downsample_layers.0.norm.bias");
+    PD_TRY(pack_linear_w("downsample_layers.0.reduction.weight", C1, 4 * C0, &pm_w));
+    PD_TRY(pack_conv_w("upsample_layers.0.conv.weight", C0, C1, 9, C1, &up_w));
+    PD_GETW(up_b, "upsample_layers.0.conv.bias");
+    PD_TRY(pack_linear_w("final_proj.weight", cfg.c, C0, &final_w));
+    PD_GETW(final_b, "final_proj.bias");
+    PD_CUDA(cudaDeviceSynchronize());
+    finalized = true;
+    return PD_OK;
+}
+
+// ---- plan construction --------------------------------------------------------------------------------------
+template <class A>
+void UNet::carve(A& ar, int B, Bufs* b) const {
+    const size_t P0 = (size_t)B * T * cfg.h * cfg.w, P1 = P0 / 4;
+    const size_t P[2] = {P0, P1};
+    const int C[2] = {C0, C1};
+    b->xin_f32 = ar.template take<float>(P0 * kCinPad);
+    b->xin_bf16 = ar.template take<bf16>(P0 * kCinPad);
+    for (int l = 0; l < 2; ++l) {
+        b->x[l] = ar.template take<float>(P[l] * C[l]);
+        b->h[l] = ar.template take<float>(P[l] * C[l]);
+        b->a[l] = ar.template take<bf16>(P[l] * (size_t)(l == 0 && C0 < kCinPad ? kCinPad : C[l]));
+        b->ln[l] = ar.template take<bf16>(P[l] * C[l]);
+        b->qkv[l] = ar.template take<bf16>(P[l] * 3 * C[l]);
+        b->att[l] = ar.template take<bf16>(P[l] * C[l]);
+        b->mid[l] = ar.template take<bf16>(P[l] * 4 * C[l]);
+    }
+    b->pm = ar.template take<bf16>(P1 * 4 * C0);
+    b->up = ar.template take<bf16>(P0 * C1);
+    b->fin = ar.template take<bf16>((size_t)B * cfg.t_out * cfg.h * cfg.w * C0);
+    b->e0 = ar.template take<float>((size_t)B * C0);
+    b->e1 = ar.template take<float>((size_t)B * TE);
+    b->temb = ar.template take<float>((size_t)B * TE);
+    b->embs = ar.template take<float>((size_t)B * emb_total);
+    b->gn_sums = ar.template take<double>((size_t)num_gn_slots() * B * 128 * 2);
+}
+
+int UNet::num_gn_slots() const { return 2 + 4 * (cfg.depth[0] + cfg.depth[1]); }
+
+int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot) {
+    const int H = cfg.h >> lvl, W = cfg.w >> lvl, C = lvl ? C1 : C0;
+    const int R = T * H * W;
+    float* x = b.x[lvl];
+    float* h = b.h[lvl];
+    bf16* a = b.a[lvl];
+    double* s1 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
+    double* s2 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
+    const float *g1w = r.gn1_w, *g1b = r.gn1_b, *g2w = r.gn2_w, *g2b = r.gn2_b;
+    pl.add([=](cudaStream_t st) { return gn_stats(x, s1, B, R, C, 32, st); });
+    pl.add([=](cudaStream_t st) { return gn_apply(x, s1, g1w, g1b, a, B, R, C, 32, 1e-5f, 1, st); });
+    {
+        GemmEpilogue e;
+        e.bias = r.conv1_b;
+        e.rowvec = b.embs + emb_off[emb_index];  // h + emb_out (time_embed.py:165)
+        e.rowvec_ld = emb_total;
+        e.out_f32 = h;
+        GemmOp op;
+        PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C, 3, 3, 3), r.conv1_w, C, e));
+        pl.add_gemm(op);
+    }
+    pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); });
+    pl.add([=](cudaStream_t st) { return gn_apply(h, s2, g2w, g2b, a, B, R, C, 32, 1e-5f, 1, st); });
+    {
+        GemmEpilogue e;
+        e.bias = r.conv2_b;
+        e.residual = x;  // skip_connection = Identity (time_embed.py:169)
+        e.out_f32 = x;
+        GemmOp op;
+        PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C, 3, 3, 3), r.conv2_w, C, e));
+        pl.add_gemm(op);
+    }
+    return PD_OK;
+}
+
+int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
+    const int H = cfg.h >> lvl, W = cfg.w >> lvl, C = lvl ? C1 : C0;
+    const int P = B * T * H * W;
+    float* x = b.x[lvl];
+    bf16 *ln = b.ln[lvl], *qkv = b.qkv[lvl], *att = b.att[lvl], *mid = b.mid[lvl];
+    const int heads = cfg.num_heads, Tn = T;
+    for (int i = 0; i < 3; ++i) {
+        const AttnW& aw = s.a[i];
+        const FfnW& fw = s.f[i];
+        // x = x + proj(attn(LN(x)))   (cuboid_transformer.py:1151, 813-952)
+        pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); });
+        {
+            GemmEpilogue e;
+            e.out_bf16 = qkv;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), aw.qkv_w, 3 * C, e));
+            pl.add_gemm(op);
+        }
+        pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, i, st); });
+        {
+            GemmEpilogue e;
+            e.bias = aw.proj_b;
+            e.residual = x;
+            e.out_f32 = x;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, att, GemmGeom::linear(P, C), aw.proj_w, C, e));
+            pl.add_gemm(op);
+        }
+        // x = x + W2 gelu(W1 LN(x) + b1) + b2   (cuboid_transformer.py:195-205)
+        pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); });
+        {
+            GemmEpilogue e;
+            e.bias = fw.b1;
+            e.act = ACT_GELU;
+            e.out_bf16 = mid;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), fw.w1, 4 * C, e));
+            pl.add_gemm(op);
+        }
+        {
+            GemmEpilogue e;
+            e.bias = fw.b2;
+            e.residual = x;
+            e.out_f32 = x;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, mid, GemmGeom::linear(P, 4 * C), fw.w2, C, e));
+            pl.add_gemm(op);
+        }
+    }
+    return PD_OK;
+}
+
+int UNet::build_plan(int B, BatchPlan* bp) {
+    ArenaSizer sz;
+    Bufs tmp;
+    carve(sz, B, &tmp);
+    PD_TRY(bp->arena.reserve(sz.used() + 4096));
+    Bufs& b = bp->bufs_storage();
+    carve(bp->arena, B, &b);
+    PD_CHECK(!bp->arena.overflowed(), PD_ERR_STATE, "unet: arena overflow");
+    Plan& pl = bp->plan;
+    const int H = cfg.h, W = cfg.w, HW = H * W;
+    const int R0 = T * HW;
+    int gn_slot = 0;
+    const size_t gn_bytes = (size_t)num_gn_slots() * B * 128 * 2 * sizeof(double);
+    double* gn_all = b.gn_sums;
+    pl.add([=](cudaStream_t st) {
+        PD_CUDA(cudaMemsetAsync(gn_all, 0, gn_bytes, st));
+        return PD_OK;
+    });
+    // ---- time embedding (models/utils.py:68-83, time_embed.py:16-24, :108-114) ----
+    {
+        const float *w0 = te_w0, *b0 = te_b0, *w2 = te_w2, *b2 = te_b2;
+        const float* wc = emb_cat.as<float>();
+        const float* bc = wc + (size_t)emb_total * TE;
+        const int c0 = C0, te = TE, et = emb_total;
+        float *e0 = b.e0, *e1 = b.e1, *temb = b.temb, *embs = b.embs;
+        bp->t_slot = pl.steps.size();
+        pl.add([](cudaStream_t) { return PD_OK; });  // placeholder: timestep_embedding, bound per call
+        (void)e0;
+        pl.add([=](cudaStream_t st) { return small_linear(e0, w0, b0, e1, B, c0, te, 0, 1, st); });
+        pl.add([=](cudaStream_t st) { return small_linear(e1, w2, b2, temb, B, te, te, 0, 0, st); });
+        pl.add([=](cudaStream_t st) { return small_linear(temb, wc, bc, embs, B, te, et, 1, 0, st); });
+    }
+    // ---- input assembly + first_proj (cuboid_transformer_unet.py:425-431) ----
+    bp->in_slot = pl.steps.size();
+    pl.add([](cudaStream_t) { return PD_OK; });  // placeholder: unet_assemble, bound per call (user pointers)
+    {
+        double* s1 = b.gn_sums + (size_t)gn_slot++ * B * 128 * 2;
+        double* s2 = b.gn_sums + (size_t)gn_slot++ * B * 128 * 2;
+        const float* xin = b.xin_f32;
+        bf16* a = b.a[0];
+        float *h = b.h[0], *x = b.x[0];
+        const ResW r = first;
+        const int c0 = C0;
+        pl.add([=](cudaStream_t st) { return gn_stats(xin, s1, B, R0, kCinPad, kCinPad, st); });
+        pl.add([=](cudaStream_t st) { return gn_apply(xin, s1, r.gn1_w, r.gn1_b, a, B, R0, kCinPad, kCinPad, 1e-5f, 1, st); });
+        {
+            GemmEpilogue e;
+            e.bias = r.conv1_b;
+            e.out_f32 = h;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, kCinPad, 3, 3, 3), r.conv1_w, C0, e));
+            pl.add_gemm(op);
+        }
+        {   // 1x1x1 skip conv on the raw (un-normalised) input
+            GemmEpilogue e;
+            e.bias = first_skip_b;
+            e.out_f32 = x;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, b.xin_bf16, GemmGeom::conv(B, T, H, W, kCinPad, 1, 1, 1), first_skip_w, C0, e));
+            pl.add_gemm(op);
+        }
+        pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R0, c0, 32, st); });
+        pl.add([=](cudaStream_t st) { return gn_apply(h, s2, r.gn2_w, r.gn2_b, a, B, R0, c0, 32, 1e-5f, 1, st); });
+        {
+            GemmEpilogue e;
+            e.bias = r.conv2_b;
+            e.residual = x;
+            e.out_f32 = x;
+            GemmOp op;
+            PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C0, 3, 3, 3), r.conv2_w, C0, e));
+            pl.add_gemm(op);
+        }
+        const float *pt = pos_T, *ph = pos_H, *pw = pos_W;
+        const int Tn = T;
+        pl.add([=](cudaStream_t st) { return pos_embed_add(x, pt, ph, pw, B, Tn, H, W, c0, st); });
+    }
+    // ---- down path ----
+    for (int d = 0; d < cfg.depth[0]; ++d) {
+        PD_TRY(add_resblock(pl, b, B, 0, down_res[0], 0, &gn_slot));
+        PD_TRY(add_stack(pl, b, B, 0, down_stack[0][d]));
+    }
+    {   // PatchMerging3D: x0 stays intact and doubles as the U-Net skip tensor
+        const float *x0 = b.x[0], *lw = pm_ln_w, *lb = pm_ln_b;
+        bf16* pm = b.pm;
+        const int BT = B * T, c0 = C0;
+        pl.add([=](cudaStream_t st) { return patch_merge_ln(x0, lw, lb, pm, BT, H, W, c0, 1e-5f, st); });
+        GemmEpilogue e;
+        e.out_f32 = b.x[1];
+        GemmOp op;
+        PD_TRY(gemm_make(&op, pm, GemmGeom::linear(B * T * HW / 4, 4 * C0), pm_w, C1, e));
+        pl.add_gemm(op);
+    }
+    for (int d = 0; d < cfg.depth[1]; ++d) {
+        PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot));
+        PD_TRY(add_stack(pl, b, B, 1, down_stack[1][d]));
+    }
+    // ---- up path ----
+    for (int d = 0; d < cfg.depth[1]; ++d) {
+        PD_TRY(add_resblock(pl, b, B, 1, up_res[1], 3, &gn_slot));
+        PD_TRY(add_stack(pl, b, B, 1, up_stack[1][d]));
+    }
+    {   // Upsample3DLayer (nearest 2x + Conv2d 3x3 per frame) with the U-Net skip add fused as the residual
+        const float* x1 = b.x[1];
+        bf16* up = b.up;
+        const int BT = B * T, c1 = C1;
+        pl.add([=](cudaStream_t st) { return upsample2x_cast(x1, up, BT, H / 2, W / 2, c1, st); });
+        GemmEpilogue e;
+        e.bias = up_b;
+        e.residual = b.x[0];
+        e.out_f32 = b.x[0];
+        GemmOp op;
+        PD_TRY(gemm_make(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e));
+        pl.add_gemm(op);
+    }
+    for (int d = 0; d < cfg.depth[0]; ++d) {
+        PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot));
+        PD_TRY(add_stack(pl, b, B, 0, up_stack[0][d]));
+    }
+    PD_CHECK(gn_slot == num_gn_slots(), PD_ERR_STATE, "unet: gn slot accounting");
+    // ---- final_proj on the target frames only (cuboid_transformer_unet.py:492) ----
+    {
+        const float* x0 = b.x[0];
+        bf16* fin = b.fin;
+        const int64_t rc = (int64_t)cfg.t_out * HW * C0, stride = (int64_t)T * HW * C0, off = (int64_t)cfg.t_in * HW * C0;
+        pl.add([=](cudaStream_t st) { return cast_bf16(x0 + off, fin, B, rc, stride, st); });
+        GemmEpilogue e;
+        e.bias = final_b;
+        e.out_f32 = reinterpret_cast<float*>(16);  // bound per call
+        PD_TRY(gemm_make(&bp->final_op, fin, GemmGeom::linear(B * cfg.t_out * HW, C0), final_w, cfg.c, e));
+        pl.gemm_flops += bp->final_op.flops;
+        ++pl.n_gemm;
+        bp->out_slot = pl.steps.size();
+        pl.add([](cudaStream_t) { return PD_OK; });  // placeholder: final GEMM, bound per call
+    }
+    return PD_OK;
+}
+
+int UNet::get_plan(int B, BatchPlan** out) {
+    PD_CHECK(finalized, PD_ERR_STATE, "unet: call pd_unet_finalize() after loading all weights");
+    PD_CHECK(B >= 1 && B <= cfg.max_batch, PD_ERR_SHAPE, "unet: batch %d outside [1, max_batch=%d]", B, cfg.max_batch);
+    auto it = plans.find(B);
+    if (it == plans.end()) {
+        std::unique_ptr<BatchPlan> bp(new BatchPlan());
+        PD_TRY(build_plan(B, bp.get()));
+        it = plans.emplace(B, std::move(bp)).first;
+    }
+    *out = it->second.get();
+    return PD_OK;
+}
+
+// t may point at a table indexed by a device-side step counter (sampler loop): t_table[*step * B + b].
+int UNet::forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B,
+                  cudaStream_t st) {
+    PD_CHECK(x && t && cond && out, PD_ERR_ARG, "unet forward: null pointer");
+    BatchPlan* bp = nullptr;
+    PD_TRY(get_plan(B, &bp));
+    const Bufs& b = bp->bufs_storage();
+    {
+        float* e0 = b.e0;
+        const int c0 = C0;
+        bp->plan.steps[bp->t_slot] = [=](cudaStream_t s) { return timestep_embedding(t, step, e0, B, c0, s); };
+    }
+    const int Tx = cfg.t_out, Tc = cfg.t_in, HW = cfg.h * cfg.w, C = cfg.c;
+    float* xf = b.xin_f32;
+    bf16* xb = b.xin_bf16;
+    bp->plan.steps[bp->in_slot] = [=](cudaStream_t s) { return unet_assemble(x, cond, xf, xb, B, Tx, Tc, HW, C, kCinPad, s); };
+    GemmOp fop = bp->final_op;
+    fop.p.out_f32 = out;
+    bp->plan.steps[bp->out_slot] = [fop](cudaStream_t s) { return gemm_launch(fop, s); };
+    return bp->plan.run(st);
+}
+
+}  // namespace pd

@@ -1,0 +1,69 @@
+// CuboidTransformerUNet on the GPU: weights (reference key names), repacked bf16 operands and per-batch plans.
+#pragma once
+#include "model_common.cuh"
+
+namespace pd {
+
+struct ResW {   // TimeEmbedResBlock
+    const float *gn1_w, *gn1_b, *conv1_b, *gn2_w, *gn2_b, *conv2_b;
+    bf16 *conv1_w, *conv2_w;
+};
+struct AttnW {  // CuboidSelfAttentionLayer
+    const float *ln_w, *ln_b, *table, *proj_b;
+    bf16 *qkv_w, *proj_w;
+};
+struct FfnW {   // PositionwiseFFN
+    const float *ln_w, *ln_b, *b1, *b2;
+    bf16 *w1, *w2;
+};
+struct StackW {  // StackCuboidSelfAttentionBlock: 3 x (attn, ffn)
+    AttnW a[3];
+    FfnW f[3];
+};
+
+class UNet {
+public:
+    struct Bufs;
+    struct BatchPlan;
+
+    explicit UNet(const pd_unet_config& c);
+    ~UNet();
+    int validate() const;
+    int finalize();
+    // t: device int64; if `step` (device int) is given, t is a table and row *step is used (sampler loop)
+    int forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B, cudaStream_t st);
+    int get_plan(int B, BatchPlan** out);
+
+    pd_unet_config cfg;
+    int C0, C1, T, TE;
+    WeightStore ws;
+    bool finalized = false;
+
+private:
+    void declare_weights();
+    void declare_resblock(const std::string& p, int cin, int cout, bool emb);
+    void declare_stack(const std::string& p, int dim, int lvl);
+    int pack_conv_w(const std::string& name, int co, int ci, int taps, int cipad, bf16** out);
+    int pack_linear_w(const std::string& name, int n, int k, bf16** out);
+    int finalize_resblock(const std::string& p, int cin, int cinpad, int cout, ResW* r);
+    int finalize_stack(const std::string& p, int dim, StackW* s);
+    int build_plan(int B, BatchPlan* bp);
+    int add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot);
+    int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s);
+    int num_gn_slots() const;
+    template <class A>
+    void carve(A& ar, int B, Bufs* b) const;
+
+    std::vector<std::unique_ptr<DevMem>> packed;
+    std::map<int, std::unique_ptr<BatchPlan>> plans;
+    ResW first{}, down_res[2]{}, up_res[2]{};
+    std::vector<StackW> down_stack[2], up_stack[2];
+    bf16 *first_skip_w = nullptr, *pm_w = nullptr, *up_w = nullptr, *final_w = nullptr;
+    const float *first_skip_b = nullptr, *pos_T = nullptr, *pos_H = nullptr, *pos_W = nullptr;
+    const float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
+    const float *pm_ln_w = nullptr, *pm_ln_b = nullptr, *up_b = nullptr, *final_b = nullptr;
+    DevMem first_gn_pad, emb_cat;
+    int emb_total = 0, emb_off[4] = {0, 0, 0, 0};
+};
+
+}  // namespace pd

@@ -1,0 +1,155 @@
+"""CuboidTransformerUNet - host-side mirror of the reference denoiser
+(src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py:23-493) over the CUDA implementation.
+
+Same constructor argument names, `forward(x, t, cond, verbose=False)` contract, `state_dict()` key names and
+shapes. Only the configuration family the shipped SEVIR-LR config uses is built (axial self-attention pattern,
+two levels, patch-merge / upsample, GELU FFN, relative position bias, no global vectors); anything else raises
+NotImplementedError at construction - there is no fallback path.
+"""
+import ctypes
+from typing import Sequence
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .module_tree import build_param_tree
+from .weights import UNetConfig, relative_position_index, unet_param_spec
+
+
+class _CUnetConfig(ctypes.Structure):
+    _fields_ = [("t_in", ctypes.c_int32), ("t_out", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("c", ctypes.c_int32), ("base_units", ctypes.c_int32), ("depth", ctypes.c_int32 * 2),
+                ("num_heads", ctypes.c_int32), ("max_batch", ctypes.c_int32)]
+
+
+def _unsupported(what):
+    raise NotImplementedError(f"prediff_b200.CuboidTransformerUNet: {what} is not built (only the shipped SEVIR-LR "
+                              "configuration family: axial pattern, 2 levels, no global vectors)")
+
+
+class CuboidTransformerUNet(nn.Module):
+
+    def __init__(self, input_shape, target_shape, base_units=128, block_units=None, scale_alpha=1.0,
+                 depth=(4, 4), downsample=2, downsample_type="patch_merge", upsample_type="upsample",
+                 upsample_kernel_size=3, block_attn_patterns="axial", num_heads=4, attn_drop=0.0, proj_drop=0.0,
+                 ffn_drop=0.0, ffn_activation="gelu", gated_ffn=False, norm_layer="layer_norm", use_inter_ffn=True,
+                 hierarchical_pos_embed=False, pos_embed_type="t+h+w", padding_type="zeros", checkpoint_level=0,
+                 use_relative_pos=True, self_attn_use_final_proj=True, num_global_vectors=0,
+                 time_embed_channels_mult=4, time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0,
+                 unet_res_connect=True, max_batch=32, **ignored_init_modes):
+        super().__init__()
+        T_in, H, W, C = input_shape
+        T_out, H2, W2, C2 = target_shape
+        assert (H, W, C) == (H2, W2, C2)
+        patterns = block_attn_patterns if isinstance(block_attn_patterns, (list, tuple)) else [block_attn_patterns] * len(depth)
+        if len(depth) != 2:
+            _unsupported(f"depth={list(depth)} (needs exactly two levels)")
+        if any(p != "axial" for p in patterns):
+            _unsupported(f"block_attn_patterns={patterns}")
+        if block_units is not None and list(block_units) != [base_units, 2 * base_units]:
+            _unsupported(f"block_units={block_units}")
+        checks = [(scale_alpha == 1.0, "scale_alpha != 1"), (downsample in (2, (1, 2, 2), [1, 2, 2]), "downsample != 2"),
+                  (downsample_type == "patch_merge", "downsample_type"), (upsample_type == "upsample", "upsample_type"),
+                  (upsample_kernel_size == 3, "upsample_kernel_size"), (ffn_activation == "gelu", "ffn_activation"),
+                  (not gated_ffn, "gated_ffn"), (norm_layer == "layer_norm", "norm_layer"), (use_inter_ffn, "use_inter_ffn"),
+                  (not hierarchical_pos_embed, "hierarchical_pos_embed"), (pos_embed_type == "t+h+w", "pos_embed_type"),
+                  (use_relative_pos, "use_relative_pos=False"), (self_attn_use_final_proj, "self_attn_use_final_proj"),
+                  (not num_global_vectors, "global vectors"), (time_embed_channels_mult == 4, "time_embed_channels_mult"),
+                  (not time_embed_use_scale_shift_norm, "scale-shift norm"), (unet_res_connect, "unet_res_connect=False")]
+        for ok, what in checks:
+            if not ok:
+                _unsupported(what)
+        self.cfg = UNetConfig(t_in=T_in, t_out=T_out, h=H, w=W, c=C, base_units=base_units, depth=tuple(depth),
+                              num_heads=num_heads)
+        self.input_shape, self.target_shape = list(input_shape), list(target_shape)
+        self.in_len, self.out_len = T_in, T_out
+        self.max_batch = max_batch
+        bufs = {}
+        for name in ("down_self_blocks", "up_self_blocks"):
+            for lvl in range(2):
+                for d in range(self.cfg.depth[lvl]):
+                    for i, cub in enumerate(self.cfg.cuboids(lvl)):
+                        bufs[f"{name}.{lvl}.{d}.attn_l.{i}.relative_position_index"] = \
+                            torch.from_numpy(relative_position_index(cub))
+        build_param_tree(self, unet_param_spec(self.cfg), bufs)
+        self._handle = None
+        self._dirty = True
+
+    # ---- C++ handle management -----------------------------------------------------------------------------
+    def _ensure_handle(self):
+        if self._handle is None:
+            c = self.cfg
+            cc = _CUnetConfig(c.t_in, c.t_out, c.h, c.w, c.c, c.base_units, (ctypes.c_int32 * 2)(*c.depth), c.num_heads,
+                              self.max_batch)
+            h = ctypes.c_void_p()
+            L.check(L.lib().pd_unet_create(ctypes.byref(cc), ctypes.byref(h)))
+            self._handle = h
+            self._dirty = True
+        return self._handle
+
+    def refresh(self):
+        """Pushes the current parameter values to the CUDA side and repacks them (bf16, K-major, tap-major)."""
+        h = self._ensure_handle()
+        lib = L.lib()
+        for name, p in self.named_parameters():
+            t = p.detach().contiguous().float()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            L.check(lib.pd_unet_load_weight(h, name.encode(), L.ptr(t), shape, t.dim()))
+        L.check(lib.pd_unet_finalize(h))
+        self._dirty = False
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._dirty = True
+        return r
+
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        self._dirty = True
+        return r
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                L.lib().pd_unet_destroy(self._handle)
+        except Exception:
+            pass
+
+    def weight_spec_from_library(self):
+        """(name, shape) list as declared by the C++ model - must equal weights.unet_param_spec."""
+        h = self._ensure_handle()
+        lib = L.lib()
+        out = []
+        for i in range(lib.pd_unet_num_weights(h)):
+            name = ctypes.c_char_p()
+            shape = (ctypes.c_int64 * 5)()
+            nd = lib.pd_unet_weight_info(h, i, ctypes.byref(name), shape)
+            out.append((name.value.decode(), tuple(shape[:nd])))
+        return out
+
+    @property
+    def handle(self):
+        if self._dirty:
+            self.refresh()
+        return self._handle
+
+    # ---- reference call surface -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, t, cond, verbose=False):
+        """x (B, T_out, H, W, C) fp32, t (B,) int64, cond (B, T_in, H, W, C) fp32 -> (B, T_out, H, W, C).
+        Reference: cuboid_transformer_unet.py:406-493."""
+        c = self.cfg
+        B = x.shape[0]
+        if not x.is_cuda:
+            raise L.PDError("prediff_b200.CuboidTransformerUNet runs on a CUDA (sm_100) device only; got a CPU tensor")
+        assert tuple(x.shape[1:]) == (c.t_out, c.h, c.w, c.c), f"x shape {tuple(x.shape)}"
+        assert tuple(cond.shape) == (B, c.t_in, c.h, c.w, c.c), f"cond shape {tuple(cond.shape)}"
+        assert t.shape == (B,)
+        x = x.contiguous().float()
+        cond = cond.contiguous().float()
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().pd_unet_forward(self.handle, L.ptr(x), L.ptr(t), L.ptr(cond), L.ptr(out), B, L.stream_ptr()))
+        return out

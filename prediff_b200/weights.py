@@ -1,0 +1,216 @@
+"""Configs, state_dict key/shape specs (the reference's key names) and a portable seeded weight generator.
+
+The reference ships no weights offline and its default init zeroes most projections, so parity
+tests and the benchmark use weights drawn by `seeded_state_dict`: numpy PCG64 streams, identical on every
+machine, every tensor non-degenerate (norm weights 1 + 0.1 N, biases 0.02 N, matrices N(0, gain^2/fan_in)).
+The same dict is loaded into the reference modules (golden generation), the oracle and the CUDA path.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+
+@dataclass
+class UNetConfig:
+    """Subset of cfg.yaml `model.latent_model` the CUDA path is built for (axial pattern, 2 levels)."""
+    t_in: int = 7
+    t_out: int = 6
+    h: int = 16
+    w: int = 16
+    c: int = 64
+    base_units: int = 256
+    depth: Tuple[int, int] = (4, 4)
+    num_heads: int = 4
+
+    @property
+    def T(self):
+        return self.t_in + self.t_out
+
+    @property
+    def units(self):
+        return (self.base_units, 2 * self.base_units)
+
+    @property
+    def temb_channels(self):
+        return 4 * self.base_units
+
+    def cuboids(self, level):
+        """self_axial pattern (cuboid_transformer_patterns.py:19-37) at a level's resolution."""
+        h, w = self.h >> level, self.w >> level
+        return [(self.T, 1, 1), (1, h, 1), (1, 1, w)]
+
+
+@dataclass
+class VAEConfig:
+    """cfg.yaml `model.vae` (diffusers-style AutoencoderKL vendored in src/prediff/taming)."""
+    in_channels: int = 1
+    out_channels: int = 1
+    latent_channels: int = 64
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    norm_num_groups: int = 32
+    h: int = 128
+    w: int = 128
+
+
+TINY_UNET = UNetConfig(base_units=64, depth=(1, 1))
+TINY_VAE = VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=64, w=64)
+
+Spec = List[Tuple[str, Tuple[int, ...]]]
+
+
+def _resblock3d(prefix, cin, cout, temb) -> Spec:
+    s = [(f"{prefix}.in_layers.0.weight", (cin,)), (f"{prefix}.in_layers.0.bias", (cin,)),
+         (f"{prefix}.in_layers.2.weight", (cout, cin, 3, 3, 3)), (f"{prefix}.in_layers.2.bias", (cout,))]
+    if temb:
+        s += [(f"{prefix}.emb_layers.1.weight", (cout, temb)), (f"{prefix}.emb_layers.1.bias", (cout,))]
+    s += [(f"{prefix}.out_layers.0.weight", (cout,)), (f"{prefix}.out_layers.0.bias", (cout,)),
+          (f"{prefix}.out_layers.3.weight", (cout, cout, 3, 3, 3)), (f"{prefix}.out_layers.3.bias", (cout,))]
+    if cin != cout:
+        s += [(f"{prefix}.skip_connection.weight", (cout, cin, 1, 1, 1)), (f"{prefix}.skip_connection.bias", (cout,))]
+    return s
+
+
+def _stack_block(prefix, dim, heads, cuboids) -> Spec:
+    s: Spec = []
+    for i in range(len(cuboids)):
+        p = f"{prefix}.ffn_l.{i}"
+        s += [(f"{p}.ffn_1.weight", (4 * dim, dim)), (f"{p}.ffn_1.bias", (4 * dim,)),
+              (f"{p}.ffn_2.weight", (dim, 4 * dim)), (f"{p}.ffn_2.bias", (dim,)),
+              (f"{p}.layer_norm.weight", (dim,)), (f"{p}.layer_norm.bias", (dim,))]
+    for i, (bt, bh, bw) in enumerate(cuboids):
+        p = f"{prefix}.attn_l.{i}"
+        s += [(f"{p}.relative_position_bias_table", ((2 * bt - 1) * (2 * bh - 1) * (2 * bw - 1), heads)),
+              (f"{p}.qkv.weight", (3 * dim, dim)),
+              (f"{p}.proj.weight", (dim, dim)), (f"{p}.proj.bias", (dim,)),
+              (f"{p}.norm.weight", (dim,)), (f"{p}.norm.bias", (dim,))]
+    return s
+
+
+def unet_param_spec(cfg: UNetConfig) -> Spec:
+    """Parameter names/shapes of the reference CuboidTransformerUNet.state_dict() (minus the int64
+    `relative_position_index` buffers, which are derived), in the reference's registration order."""
+    u0, u1 = cfg.units
+    te = cfg.temb_channels
+    s: Spec = []
+    s += _resblock3d("first_proj", cfg.c + 1, u0, 0)
+    s += [("pos_embed.T_embed.weight", (cfg.T, u0)), ("pos_embed.H_embed.weight", (cfg.h, u0)),
+          ("pos_embed.W_embed.weight", (cfg.w, u0))]
+    s += [("time_embed.layer.0.weight", (te, u0)), ("time_embed.layer.0.bias", (te,)),
+          ("time_embed.layer.2.weight", (te, te)), ("time_embed.layer.2.bias", (te,))]
+    s += [("downsample_layers.0.reduction.weight", (u1, 4 * u0)), ("downsample_layers.0.norm.weight", (4 * u0,)),
+          ("downsample_layers.0.norm.bias", (4 * u0,))]
+    s += [("upsample_layers.0.conv.weight", (u0, u1, 3, 3)), ("upsample_layers.0.conv.bias", (u0,))]
+    for name in ("down_self_blocks", "up_self_blocks"):
+        for lvl, dim in enumerate((u0, u1)):
+            for d in range(cfg.depth[lvl]):
+                s += _stack_block(f"{name}.{lvl}.{d}", dim, cfg.num_heads, cfg.cuboids(lvl))
+    for name in ("down_time_embed_blocks", "up_time_embed_blocks"):
+        for lvl, dim in enumerate((u0, u1)):
+            s += _resblock3d(f"{name}.{lvl}", dim, dim, te)
+    s += [("final_proj.weight", (cfg.c, u0)), ("final_proj.bias", (cfg.c,))]
+    return s
+
+
+def _resnet2d(prefix, cin, cout) -> Spec:
+    s = [(f"{prefix}.norm1.weight", (cin,)), (f"{prefix}.norm1.bias", (cin,)),
+         (f"{prefix}.conv1.weight", (cout, cin, 3, 3)), (f"{prefix}.conv1.bias", (cout,)),
+         (f"{prefix}.norm2.weight", (cout,)), (f"{prefix}.norm2.bias", (cout,)),
+         (f"{prefix}.conv2.weight", (cout, cout, 3, 3)), (f"{prefix}.conv2.bias", (cout,))]
+    if cin != cout:
+        s += [(f"{prefix}.conv_shortcut.weight", (cout, cin, 1, 1)), (f"{prefix}.conv_shortcut.bias", (cout,))]
+    return s
+
+
+def _mid_block(prefix, c) -> Spec:
+    a = f"{prefix}.attentions.0"
+    s = [(f"{a}.group_norm.weight", (c,)), (f"{a}.group_norm.bias", (c,))]
+    for n in ("query", "key", "value", "proj_attn"):
+        s += [(f"{a}.{n}.weight", (c, c)), (f"{a}.{n}.bias", (c,))]
+    s += _resnet2d(f"{prefix}.resnets.0", c, c)
+    s += _resnet2d(f"{prefix}.resnets.1", c, c)
+    return s
+
+
+def vae_param_spec(cfg: VAEConfig) -> Spec:
+    """Parameter names/shapes of the reference AutoencoderKL.state_dict() (taming/autoencoder_kl.py)."""
+    boc = cfg.block_out_channels
+    s: Spec = [("encoder.conv_in.weight", (boc[0], cfg.in_channels, 3, 3)), ("encoder.conv_in.bias", (boc[0],))]
+    cin = boc[0]
+    for i, cout in enumerate(boc):
+        for j in range(cfg.layers_per_block):
+            s += _resnet2d(f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i != len(boc) - 1:
+            s += [(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight", (cout, cout, 3, 3)),
+                  (f"encoder.down_blocks.{i}.downsamplers.0.conv.bias", (cout,))]
+        cin = cout
+    s += _mid_block("encoder.mid_block", boc[-1])
+    s += [("encoder.conv_norm_out.weight", (boc[-1],)), ("encoder.conv_norm_out.bias", (boc[-1],)),
+          ("encoder.conv_out.weight", (2 * cfg.latent_channels, boc[-1], 3, 3)),
+          ("encoder.conv_out.bias", (2 * cfg.latent_channels,))]
+    s += [("decoder.conv_in.weight", (boc[-1], cfg.latent_channels, 3, 3)), ("decoder.conv_in.bias", (boc[-1],))]
+    rev = list(reversed(boc))
+    cin = rev[0]
+    for i, cout in enumerate(rev):
+        for j in range(cfg.layers_per_block + 1):
+            s += _resnet2d(f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i != len(boc) - 1:
+            s += [(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight", (cout, cout, 3, 3)),
+                  (f"decoder.up_blocks.{i}.upsamplers.0.conv.bias", (cout,))]
+        cin = cout
+    s += _mid_block("decoder.mid_block", boc[-1])
+    s += [("decoder.conv_norm_out.weight", (boc[0],)), ("decoder.conv_norm_out.bias", (boc[0],)),
+          ("decoder.conv_out.weight", (cfg.out_channels, boc[0], 3, 3)), ("decoder.conv_out.bias", (cfg.out_channels,))]
+    s += [("quant_conv.weight", (2 * cfg.latent_channels, 2 * cfg.latent_channels, 1, 1)),
+          ("quant_conv.bias", (2 * cfg.latent_channels,)),
+          ("post_quant_conv.weight", (cfg.latent_channels, cfg.latent_channels, 1, 1)),
+          ("post_quant_conv.bias", (cfg.latent_channels,))]
+    return s
+
+
+def _is_norm_weight(name: str) -> bool:
+    parts = name.split(".")
+    if parts[-1] != "weight":
+        return False
+    owner = parts[-2]
+    if owner in ("norm", "layer_norm", "norm1", "norm2", "group_norm", "conv_norm_out"):
+        return True
+    # GroupNorm inside the nn.Sequential of TimeEmbedResBlock: in_layers.0 / out_layers.0
+    return len(parts) >= 3 and parts[-3] in ("in_layers", "out_layers") and owner == "0"
+
+
+def seeded_state_dict(spec: Spec, seed: int, gain: float = 1.0) -> Dict[str, np.ndarray]:
+    """Deterministic, platform-independent fp32 weights for a spec (one PCG64 stream per tensor)."""
+    out: Dict[str, np.ndarray] = {}
+    for idx, (name, shape) in enumerate(spec):
+        rng = np.random.Generator(np.random.PCG64([seed, idx]))
+        x = rng.standard_normal(shape, dtype=np.float32)
+        if _is_norm_weight(name):
+            x = 1.0 + 0.1 * x
+        elif name.endswith(".bias"):
+            x = 0.02 * x
+        elif name.endswith("relative_position_bias_table"):
+            x = 0.3 * x
+        elif "embed.weight" in name and name.startswith("pos_embed"):
+            x = 0.1 * x
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            x = x * np.float32(gain / np.sqrt(fan_in))
+        out[name] = np.ascontiguousarray(x, dtype=np.float32)
+    return out
+
+
+def relative_position_index(cuboid) -> np.ndarray:
+    """The derived int64 buffer of CuboidSelfAttentionLayer (cuboid_transformer.py:719-734)."""
+    bt, bh, bw = cuboid
+    t, h, w = np.meshgrid(np.arange(bt), np.arange(bh), np.arange(bw), indexing="ij")
+    c = np.stack([t.ravel(), h.ravel(), w.ravel()])  # (3, vol)
+    rel = c[:, :, None] - c[:, None, :]
+    rel = rel.transpose(1, 2, 0).copy()
+    rel[..., 0] += bt - 1
+    rel[..., 1] += bh - 1
+    rel[..., 2] += bw - 1
+    rel[..., 0] *= (2 * bh - 1) * (2 * bw - 1)
+    rel[..., 1] *= (2 * bw - 1)
+    return rel.sum(-1).astype(np.int64)

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 GPU (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: takes tens of seconds on CPU")
 
 
 def _has_gpu():

@@ -1,0 +1,253 @@
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference modules on CPU.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+    python tests/golden/gen_golden.py [--only schedule,unet_tiny,...] [--ddim-full]
+
+`lightning` and `diffusers` are absent from the image; they contribute no arithmetic to the sampling path
+(SURVEY.md section 8c), so they are replaced by inert sys.modules stubs before importing the reference.
+Weights come from prediff_b200.weights.seeded_state_dict (portable numpy PCG64 streams) and are loaded into the
+reference modules with load_state_dict; inputs come from the same kind of streams (`inp()` below), so tests can
+regenerate them bit-exactly anywhere. Only outputs (and small inputs) are stored.
+"""
+import argparse
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("PREDIFF_REFERENCE", "/root/reference")
+
+from prediff_b200 import weights as Wt  # noqa: E402
+
+UNET_SEED, VAE_SEED = 1001, 2002
+
+
+def inp(seed, *shape, uniform=False):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.random(shape, dtype=np.float32) if uniform else rng.standard_normal(shape, dtype=np.float32)
+    return torch.from_numpy(a)
+
+
+def install_stubs():
+    import torch.nn as nn
+
+    class _LM(nn.Module):
+        @property
+        def device(self):
+            return next(self.parameters()).device if any(True for _ in self.parameters()) else torch.device("cpu")
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("lightning")
+    mod("lightning.pytorch", LightningModule=_LM)
+    mod("lightning.pytorch.utilities")
+    mod("lightning.pytorch.utilities.rank_zero", rank_zero_only=lambda f: f)
+    sys.modules["lightning"].pytorch = sys.modules["lightning.pytorch"]
+    mod("diffusers")
+    mod("diffusers.models")
+    mod("diffusers.models.autoencoder_kl", AutoencoderKLOutput=type("AutoencoderKLOutput", (), {}),
+        DecoderOutput=type("DecoderOutput", (), {}))
+    sys.path.insert(0, os.path.join(REF, "src"))
+
+
+def ref_unet(cfg):
+    from prediff.models.cuboid_transformer import CuboidTransformerUNet
+    # arguments as in scripts/prediff/sevirlr/train_sevirlr_prediff.py:91-137 with cfg.yaml:157-206
+    m = CuboidTransformerUNet(
+        input_shape=[cfg.t_in, cfg.h, cfg.w, cfg.c], target_shape=[cfg.t_out, cfg.h, cfg.w, cfg.c],
+        base_units=cfg.base_units, scale_alpha=1.0, num_heads=cfg.num_heads, attn_drop=0.1, proj_drop=0.1, ffn_drop=0.1,
+        downsample=2, downsample_type="patch_merge", upsample_type="upsample", upsample_kernel_size=3,
+        depth=list(cfg.depth), block_attn_patterns=["axial"] * 2, num_global_vectors=0, use_global_vector_ffn=False,
+        use_global_self_attn=True, separate_global_qkv=True, global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
+        norm_layer="layer_norm", padding_type="zeros", checkpoint_level=0, pos_embed_type="t+h+w",
+        use_relative_pos=True, self_attn_use_final_proj=True, time_embed_channels_mult=4,
+        time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0, unet_res_connect=True)
+    sd = Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED)
+    res = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.endswith("relative_position_index") for k in res.missing_keys), res.missing_keys
+    ref_keys = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("relative_position_index")}
+    assert ref_keys == {k: tuple(v.shape) for k, v in sd.items()}, "spec != reference state_dict"
+    assert list(ref_keys) == [k for k, _ in Wt.unet_param_spec(cfg)], "spec order != reference registration order"
+    # the derived buffer must equal the reference's
+    for k, v in m.state_dict().items():
+        if k.endswith("relative_position_index"):
+            lvl = int(k.split(".")[1])
+            i = int(k.split(".")[4])
+            assert np.array_equal(v.numpy(), Wt.relative_position_index(cfg.cuboids(lvl)[i])), k
+    return m.eval()
+
+
+def ref_vae(cfg):
+    from prediff.taming import AutoencoderKL
+    m = AutoencoderKL(down_block_types=["DownEncoderBlock2D"] * 4, in_channels=cfg.in_channels,
+                      block_out_channels=list(cfg.block_out_channels), act_fn="silu",
+                      latent_channels=cfg.latent_channels, up_block_types=["UpDecoderBlock2D"] * 4,
+                      norm_num_groups=cfg.norm_num_groups, layers_per_block=cfg.layers_per_block,
+                      out_channels=cfg.out_channels)
+    sd = Wt.seeded_state_dict(Wt.vae_param_spec(cfg), VAE_SEED)
+    ref_keys = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ref_keys == {k: tuple(v.shape) for k, v in sd.items()}, \
+        (set(ref_keys) ^ set(sd), [k for k in ref_keys if k in sd and ref_keys[k] != sd[k].shape])
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return m.eval()
+
+
+def ref_ldm(unet, vae, ucfg, vcfg):
+    from prediff.diffusion.latent_diffusion import LatentDiffusion
+    return LatentDiffusion(
+        torch_nn_module=unet, layout="NTHWC", data_shape=(ucfg.t_out, vcfg.h, vcfg.w, 1), timesteps=1000,
+        beta_schedule="linear", use_ema=False, log_every_t=100, clip_denoised=False, linear_start=1e-4,
+        linear_end=2e-2, parameterization="eps", learn_logvar=False,
+        latent_shape=(ucfg.t_out, ucfg.h, ucfg.w, ucfg.c), first_stage_model=vae,
+        cond_stage_model="__is_first_stage__", scale_factor=1.0).eval()
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
+@torch.no_grad()
+def gen_schedule():
+    import prediff.diffusion.utils as U
+    ldm = ref_ldm(ref_unet(Wt.TINY_UNET), ref_vae(Wt.TINY_VAE), Wt.TINY_UNET, Wt.TINY_VAE)
+    names = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+             "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+             "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]
+    out = {n: getattr(ldm, n) for n in names}
+    ts = U.make_ddim_timesteps("uniform", 50, 1000, verbose=False)
+    for eta in (0.0, 1.0):
+        sig, a, ap = U.make_ddim_sampling_parameters(ldm.alphas_cumprod.numpy(), ts, eta, verbose=False)
+        out[f"ddim50_sigmas_eta{int(eta)}"] = sig
+    out.update(ddim50_timesteps=ts, ddim50_alphas=a, ddim50_alphas_prev=ap)
+    from prediff.models.utils import timestep_embedding
+    out["timestep_embedding_256"] = timestep_embedding(torch.tensor([0, 1, 500, 981, 999]), 256)
+    save("schedule", **out)
+
+
+@torch.no_grad()
+def gen_unet(tag, cfg, B, ts):
+    m = ref_unet(cfg)
+    x = inp(1234, B, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(1235, B, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    t = torch.tensor(ts, dtype=torch.long)
+    t0 = time.time()
+    out = m(x, t, cond)
+    print(f"unet_{tag}: forward {time.time() - t0:.1f}s, out std {out.std():.3f} absmax {out.abs().max():.3f}")
+    save(f"unet_{tag}", t=t, out=out)
+
+
+@torch.no_grad()
+def gen_vae(tag, cfg, N):
+    m = ref_vae(cfg)
+    x = inp(4321, N, 1, cfg.h, cfg.w, uniform=True)
+    post = m.encode(x)
+    moments = post.parameters
+    z = post.mode()
+    dec = m.decode(z)
+    print(f"vae_{tag}: moments std {moments.std():.3f}, dec std {dec.std():.3f}")
+    save(f"vae_{tag}", moments=moments, dec=dec)
+
+
+@torch.no_grad()
+def gen_loop_tiny():
+    """Reference p_sample_loop (DDPM ancestral) and sample() on the tiny config, RNG injected."""
+    import prediff.diffusion.latent_diffusion as LD
+    ucfg, vcfg = Wt.TINY_UNET, Wt.TINY_VAE
+    # the tiny VAE downsamples 64 -> 8, the tiny UNet runs at 16x16: use a 128x128 tiny VAE for sample()
+    vcfg = Wt.VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=128, w=128)
+    unet, vae = ref_unet(ucfg), ref_vae(vcfg)
+    ldm = ref_ldm(unet, vae, ucfg, vcfg)
+    B, n_steps = 2, 4
+    zT = inp(777, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    cond = inp(778, B, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    noise = inp(779, n_steps, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    calls = {"k": 0}
+
+    def fake_noise_like(shape, device):
+        k = calls["k"]
+        calls["k"] += 1
+        assert tuple(shape) == tuple(noise[k].shape)
+        return noise[k].clone()
+
+    orig = LD.noise_like
+    LD.noise_like = fake_noise_like
+    try:
+        z0, inter = ldm.p_sample_loop(cond=cond, shape=tuple(zT.shape), x_T=zT.clone(), timesteps=n_steps,
+                                      return_intermediates=True, log_every_t=1)
+        assert calls["k"] == n_steps
+        # one step at a large timestep (p_sample directly)
+        calls["k"] = 0
+        t = torch.full((B,), 900, dtype=torch.long)
+        z_step = ldm.p_sample(zt=zT.clone(), zc=cond, t=t)
+        # full sample(): encode context -> loop -> decode
+        calls["k"] = 0
+        y = inp(780, B, ucfg.t_in, vcfg.h, vcfg.w, 1, uniform=True)
+        dec = ldm.sample(cond={"y": y}, batch_size=B, x_T=zT.clone(), timesteps=n_steps)
+        zc = ldm.cond_stage_forward({"y": y})
+    finally:
+        LD.noise_like = orig
+    save("loop_tiny", z0=z0, inter=torch.stack(inter), z_step900=z_step, sample_dec=dec, sample_zc=zc)
+
+
+@torch.no_grad()
+def gen_ddim(tag, cfg, B, n_steps):
+    """S6 DDIM (eta = 0) with the reference UNet module and the reference's DDIM helper functions."""
+    import prediff.diffusion.utils as U
+    m = ref_unet(cfg)
+    betas = U.make_beta_schedule("linear", 1000, linear_start=1e-4, linear_end=2e-2)
+    ac = np.cumprod(1.0 - betas, axis=0).astype(np.float32)  # the registered fp32 buffer
+    ts = U.make_ddim_timesteps("uniform", n_steps, 1000, verbose=False)
+    sig, a, ap = U.make_ddim_sampling_parameters(ac, ts, 0.0, verbose=False)
+    z = inp(4242, B, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(4243, B, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    t0 = time.time()
+    snaps = {}
+    for k, i in enumerate(reversed(range(len(ts)))):
+        t = torch.full((B,), int(ts[i]), dtype=torch.long)
+        eps = m(z, t, cond)
+        z0 = (z - float(np.sqrt(1.0 - a[i])) * eps) / float(np.sqrt(a[i]))
+        z = float(np.sqrt(ap[i])) * z0 + float(np.sqrt(1.0 - ap[i] - sig[i] ** 2)) * eps
+        if k + 1 in (1, 10, 25):
+            snaps[f"z_after_{k + 1}"] = z.clone()
+        if k % 10 == 0:
+            print(f"ddim_{tag}: step {k + 1}/{len(ts)} ({time.time() - t0:.0f}s)", flush=True)
+    save(f"ddim_{tag}", z0=z, **snaps)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="schedule,unet_tiny,unet_full,vae_tiny,vae_full,loop_tiny,ddim_tiny")
+    args = ap.parse_args()
+    install_stubs()
+    torch.manual_seed(0)
+    todo = set(args.only.split(","))
+    FULL_U, FULL_V = Wt.UNetConfig(), Wt.VAEConfig()
+    if "schedule" in todo:
+        gen_schedule()
+    if "unet_tiny" in todo:
+        gen_unet("tiny", Wt.TINY_UNET, 2, [500, 37])
+    if "vae_tiny" in todo:
+        gen_vae("tiny", Wt.TINY_VAE, 2)
+    if "loop_tiny" in todo:
+        gen_loop_tiny()
+    if "ddim_tiny" in todo:
+        gen_ddim("tiny", Wt.TINY_UNET, 2, 50)
+    if "unet_full" in todo:
+        gen_unet("full", FULL_U, 1, [500])
+    if "vae_full" in todo:
+        gen_vae("full", FULL_V, 1)
+    if "ddim_full" in todo:
+        gen_ddim("full", FULL_U, 4, 50)
