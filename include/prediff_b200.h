@@ -106,6 +106,11 @@ int pd_sampler_get_buffer(const pd_sampler* s, const char* name, float* out);
  * The loop is captured into a CUDA graph on first use for a given (unet, batch) and replayed. */
 int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int mode,
                    int n_steps, float eta, void* stream);
+/* Same, restricted to the executed steps [k_begin, k_end) of the n_steps-step schedule (k = 0 is the noisiest step);
+ * noise[0] belongs to step k_begin. Lets the host interleave callbacks / intermediates / inpainting
+ * (latent_diffusion.py:659-680) between device-resident stretches. */
+int pd_sample_loop_range(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch,
+                         int mode, int n_steps, float eta, int k_begin, int k_end, void* stream);
 /* One reference p_sample step at integer timestep t (all batch rows share t): z <- p_sample(z, cond, t). */
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream);

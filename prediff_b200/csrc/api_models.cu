@@ -70,7 +70,12 @@ int pd_sampler_get_buffer(const pd_sampler* s, const char* name, float* out) {
 int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int mode,
                    int n_steps, float eta, void* stream) {
     PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_loop: null handle");
-    return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, S(stream));
+    return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, 0, n_steps, S(stream));
+}
+int pd_sample_loop_range(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch,
+                         int mode, int n_steps, float eta, int k_begin, int k_end, void* stream) {
+    PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_loop_range: null handle");
+    return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, k_begin, k_end, S(stream));
 }
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream) {

@@ -106,7 +106,10 @@ int Sampler::upload_tables(const std::vector<float>& rows, const std::vector<int
     std::vector<int64_t> tt((size_t)n * B);
     for (int k = 0; k < n; ++k)
         for (int b = 0; b < B; ++b) tt[(size_t)k * B + b] = ts[k];
-    if (coef_dev_.bytes < rows.size() * sizeof(float)) PD_TRY(coef_dev_.alloc(rows.size() * sizeof(float)));
+    if (coef_dev_.bytes < rows.size() * sizeof(float)) {
+        PD_TRY(coef_dev_.alloc(rows.size() * sizeof(float)));
+        drop_graph();  // the captured iteration holds the old table address
+    }
     if (t_dev_.bytes < tt.size() * sizeof(int64_t)) {
         PD_TRY(t_dev_.alloc(tt.size() * sizeof(int64_t)));
         drop_graph();
@@ -128,12 +131,18 @@ int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float*
     return advance_step(step_dev_.as<int>(), st);
 }
 
-int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_steps, float eta,
-                  cudaStream_t st) {
+int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_total, float eta,
+                  int k_begin, int k_end, cudaStream_t st) {
     PD_CHECK(unet && z && cond, PD_ERR_ARG, "sample_loop: null pointer");
     std::vector<float> rows;
     std::vector<int64_t> ts;
-    PD_TRY(coefficients(mode, n_steps, eta, &rows, &ts));
+    PD_TRY(coefficients(mode, n_total, eta, &rows, &ts));
+    PD_CHECK(0 <= k_begin && k_begin <= k_end && k_end <= n_total, PD_ERR_ARG, "sample_loop: bad step range [%d, %d)",
+             k_begin, k_end);
+    if (k_begin == k_end) return PD_OK;
+    rows = std::vector<float>(rows.begin() + (size_t)k_begin * 8, rows.begin() + (size_t)k_end * 8);
+    ts = std::vector<int64_t>(ts.begin() + k_begin, ts.begin() + k_end);
+    const int n_steps = k_end - k_begin;
     bool needs_noise = false;
     for (int k = 0; k < n_steps; ++k) needs_noise |= rows[(size_t)k * 8 + 5] != 0.f;
     PD_CHECK(!needs_noise || noise, PD_ERR_ARG, "sample_loop: this sampler is stochastic; pass the noise stack");

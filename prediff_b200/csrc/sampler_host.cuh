@@ -14,8 +14,9 @@ public:
     int get_buffer(const char* name, float* out) const;
     // Fills rows[k][8] + timesteps[k] for the k-th executed step.
     int coefficients(int mode, int n_steps, float eta, std::vector<float>* rows, std::vector<int64_t>* ts) const;
-    int loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_steps, float eta,
-             cudaStream_t st);
+    // Runs executed steps [k_begin, k_end) of the n_total-step schedule; noise[0] belongs to step k_begin.
+    int loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_total, float eta,
+             int k_begin, int k_end, cudaStream_t st);
     int step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st);
 
     int T;

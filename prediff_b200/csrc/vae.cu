@@ -4,8 +4,35 @@
 // (Upsample2D), :181-190 (Downsample2D), attention.py:136-189 (AttentionBlock).
 // Activations are channels-last [N][H][W][C]; fp32 residual stream, bf16 GEMM operands.
 #include "vae.cuh"
+#include <algorithm>
+#include <cmath>
 
 namespace pd {
+
+// ---- plan building ------------------------------------------------------------------------------------------
+struct VAE::Ctx {
+    Plan* pl;
+    int N;
+    float* f[3];      // fp32 pool: cur / conv1-out / spare
+    bf16 *a, *cast;   // GN output; casts, upsampled / parity-split tensors, V^T
+    bf16* qkv;        // attention q|k|v, later the attention output
+    double* gn_sums;
+    int gn_slot = 0, G = 32;
+    int cur = 0;      // index of the stream buffer in f[]
+    float* stream() const { return f[cur]; }
+    float* other(int k) const { return f[(cur + k) % 3]; }
+    double* next_sums() { return gn_sums + (size_t)(gn_slot++) * N * 128 * 2; }
+};
+
+struct VAE::DirPlan {
+    Arena arena;
+    Ctx ctx;
+    Plan plan;
+    GemmOp last_op;
+    float* first_buf = nullptr;
+    size_t in_slot = 0, out_slot = 0;
+    Ctx& ctx_storage() { return ctx; }
+};
 
 VAE::VAE(const pd_vae_config& c) : cfg(c) { declare_weights(); }
 VAE::~VAE() = default;
@@ -234,21 +261,6 @@ int VAE::finalize() {
     finalized = true;
     return PD_OK;
 }
-
-// ---- plan building ------------------------------------------------------------------------------------------
-struct VAE::Ctx {
-    Plan* pl;
-    int N;
-    float* f[3];      // fp32 pool: cur / conv1-out / spare
-    bf16 *a, *cast;   // GN output; casts, upsampled / parity-split tensors, V^T
-    bf16* qkv;        // attention q|k|v, later the attention output
-    double* gn_sums;
-    int gn_slot = 0, G = 32;
-    int cur = 0;      // index of the stream buffer in f[]
-    float* stream() const { return f[cur]; }
-    float* other(int k) const { return f[(cur + k) % 3]; }
-    double* next_sums() { return gn_sums + (size_t)(gn_slot++) * N * 128 * 2; }
-};
 
 int VAE::add_gn(Ctx& c, const float* x, const float* w, const float* b, bf16* y, int R, int C, int silu) {
     double* s = c.next_sums();

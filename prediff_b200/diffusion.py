@@ -1,0 +1,308 @@
+"""LatentDiffusion - host-side mirror of the reference sampling runtime
+(src/prediff/diffusion/latent_diffusion.py:25-724) over the device-resident CUDA loop.
+
+Keeps the reference call surface used by the Lightning script: constructor injection of
+`torch_nn_module` / `first_stage_model`, `sample`, `p_sample_loop`, `p_sample`, `apply_model`,
+`encode_first_stage` / `decode_first_stage`, `cond_stage_forward`, `set_alignment`, the registered schedule
+buffers - plus `ddim_sample_loop`, the 50-step DDIM the benchmark is quoted on (the reference has no DDIM
+sampler; SURVEY.md D1 / section 8 row S6 define it from the reference's own helper functions).
+
+Training-side members (losses, EMA, optimizers, Lightning hooks) are out of scope.
+"""
+import ctypes
+from typing import Any, Callable, Dict, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from .distributions import DiagonalGaussianDistribution
+
+PD_MODE_DDPM, PD_MODE_DDIM = 0, 1
+_SCHEDULE_BUFFERS = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+                     "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                     "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                     "posterior_mean_coef1", "posterior_mean_coef2"]
+
+
+def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=False):
+    """diffusion/utils.py:42-56, 'uniform' only."""
+    if ddim_discr_method != "uniform":
+        raise NotImplementedError(ddim_discr_method)
+    c = num_ddpm_timesteps // num_ddim_timesteps
+    return np.asarray(list(range(0, num_ddpm_timesteps, c))) + 1
+
+
+class LatentDiffusion(nn.Module):
+
+    def __init__(self, torch_nn_module: nn.Module, layout: str = "NTHWC", data_shape: Sequence[int] = (6, 128, 128, 1),
+                 timesteps=1000, beta_schedule="linear", loss_type="l2", monitor="val/loss", use_ema=False,
+                 log_every_t=100, clip_denoised=False, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3,
+                 given_betas=None, original_elbo_weight=0., v_posterior=0., l_simple_weight=1., parameterization="eps",
+                 learn_logvar=False, logvar_init=0., latent_shape: Sequence[int] = (6, 16, 16, 64),
+                 first_stage_model: nn.Module = None, cond_stage_model=None, num_timesteps_cond=None,
+                 cond_stage_trainable=False, cond_stage_forward=None, scale_by_std=False, scale_factor=1.0):
+        super().__init__()
+        if parameterization != "eps":
+            raise NotImplementedError("prediff_b200.LatentDiffusion: only eps-parameterization is built")
+        if beta_schedule != "linear" or given_betas is not None or v_posterior != 0.:
+            raise NotImplementedError("prediff_b200.LatentDiffusion: only the 'linear' beta schedule with v_posterior=0")
+        if layout != "NTHWC":
+            raise NotImplementedError("prediff_b200.LatentDiffusion: layout must be 'NTHWC'")
+        if clip_denoised:
+            raise NotImplementedError("prediff_b200.LatentDiffusion: clip_denoised=True is not built")
+        if num_timesteps_cond not in (None, 1):
+            raise NotImplementedError("prediff_b200.LatentDiffusion: shorten_cond_schedule is not built")
+        self.parameterization = parameterization
+        self.clip_denoised = clip_denoised
+        self.log_every_t = log_every_t
+        self.torch_nn_module = torch_nn_module
+        self.layout = layout
+        self.data_shape = tuple(data_shape)
+        self.latent_shape = tuple(latent_shape)
+        self.batch_axis, self.t_axis, self.h_axis, self.w_axis, self.c_axis = 0, 1, 2, 3, 4
+        self.use_ema = False  # EMA shadow weights are a training feature (utils/ema.py); out of scope
+        self.scale_factor = scale_factor
+        self.alignment_fn = None
+        self.shorten_cond_schedule = False
+        self.register_schedule(timesteps=timesteps, linear_start=linear_start, linear_end=linear_end)
+        self.first_stage_model = first_stage_model
+        if first_stage_model is not None:
+            first_stage_model.eval()
+        if cond_stage_model == "__is_first_stage__":
+            self.cond_stage_model = first_stage_model
+            self._cond_is_first_stage = True
+        elif cond_stage_model is None:
+            self.cond_stage_model = None
+            self._cond_is_first_stage = False
+        else:
+            raise NotImplementedError("prediff_b200.LatentDiffusion: cond_stage_model must be '__is_first_stage__' or None")
+
+    # ---- schedule -------------------------------------------------------------------------------------------
+    def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
+                          linear_end=2e-2, cosine_s=8e-3):
+        """latent_diffusion.py:228-278; the table is computed (float64) and owned by the C++ sampler."""
+        h = ctypes.c_void_p()
+        L.check(L.lib().pd_sampler_create(int(timesteps), ctypes.c_double(linear_start), ctypes.c_double(linear_end),
+                                          ctypes.byref(h)))
+        self._sampler = h
+        self.num_timesteps = int(timesteps)
+        self.linear_start, self.linear_end = linear_start, linear_end
+        for name in _SCHEDULE_BUFFERS:
+            buf = torch.empty(self.num_timesteps, dtype=torch.float32)
+            L.check(L.lib().pd_sampler_get_buffer(self._sampler, name.encode(), L.ptr(buf)))
+            self.register_buffer(name, buf)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_sampler", None) is not None:
+                L.lib().pd_sampler_destroy(self._sampler)
+        except Exception:
+            pass
+
+    def set_alignment(self, alignment_fn: Callable = None):
+        """latent_diffusion.py:169-180. Signature `alignment_fn(zt, t, zc=None, y=None, **kwargs)`."""
+        self.alignment_fn = alignment_fn
+
+    @property
+    def einops_layout(self):
+        return " ".join(self.layout)
+
+    def extract_into_tensor(self, a, t, x_shape):
+        out = a.gather(-1, t)
+        return out.reshape([t.shape[0]] + [1] * (len(x_shape) - 1))
+
+    def get_batch_latent_shape(self, batch_size=1):
+        return (batch_size,) + tuple(self.latent_shape)
+
+    # ---- first stage glue (latent_diffusion.py:361-432) ------------------------------------------------------
+    @torch.no_grad()
+    def cond_stage_forward(self, c: Dict[str, Any]):
+        """{"y": (N,T,H,W,C)} -> context latents (N,T,h,w,c): per-frame encode, posterior mode."""
+        if self._cond_is_first_stage:
+            c = c.get("y")
+            N, T = c.shape[0], c.shape[1]
+            frames = c.permute(0, 1, 4, 2, 3).reshape(N * T, c.shape[4], c.shape[2], c.shape[3])
+            post = self.cond_stage_model.encode(frames)
+            z = post.mode() if hasattr(post, "mode") else post
+            return z.reshape(N, T, *z.shape[1:]).permute(0, 1, 3, 4, 2).contiguous()
+        return c
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        post = self.first_stage_model.encode(x)
+        z = post.sample() if hasattr(post, "sample") else post
+        return (self.scale_factor * z).detach()
+
+    @torch.no_grad()
+    def decode_first_stage(self, z):
+        """(N,T,h,w,c) latents -> (N,T,H,W,C) pixels (latent_diffusion.py:423-432)."""
+        z = 1. / self.scale_factor * z
+        N, T = z.shape[0], z.shape[1]
+        frames = z.permute(0, 1, 4, 2, 3).reshape(N * T, z.shape[4], z.shape[2], z.shape[3])
+        out = self.first_stage_model.decode(frames)
+        return out.reshape(N, T, *out.shape[1:]).permute(0, 1, 3, 4, 2).contiguous()
+
+    # ---- denoiser --------------------------------------------------------------------------------------------
+    def apply_model(self, x_noisy, t, cond):
+        out = self.torch_nn_module(x_noisy, t, cond)
+        return out[0] if isinstance(out, tuple) else out
+
+    def _native(self):
+        """True when the denoiser is the CUDA UNet, i.e. the loop can stay resident on the device."""
+        from .unet import CuboidTransformerUNet
+        return isinstance(self.torch_nn_module, CuboidTransformerUNet)
+
+    def q_sample(self, x_start, t, noise=None):
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return (self.extract_into_tensor(self.sqrt_alphas_cumprod.to(x_start.device), t, x_start.shape) * x_start +
+                self.extract_into_tensor(self.sqrt_one_minus_alphas_cumprod.to(x_start.device), t, x_start.shape) * noise)
+
+    def _run_range(self, z, cond, noise, mode, n_total, eta, k0, k1):
+        B = z.shape[0]
+        with torch.cuda.device(z.device):
+            L.check(L.lib().pd_sample_loop_range(self._sampler, self.torch_nn_module.handle, L.ptr(z), L.ptr(cond),
+                                                 L.ptr(noise), B, mode, n_total, ctypes.c_float(eta), k0, k1,
+                                                 L.stream_ptr()))
+
+    @torch.no_grad()
+    def p_sample(self, zt, zc, t, y=None, use_alignment=False, alignment_kwargs=None, clip_denoised=False,
+                 return_x0=False, temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                 noise=None):
+        """One ancestral step (latent_diffusion.py:598-631). `noise` may be injected for parity tests; otherwise it
+        is drawn with torch.randn exactly where the reference draws it."""
+        assert not clip_denoised and score_corrector is None and noise_dropout == 0.
+        B = zt.shape[0]
+        eps = self.apply_model(zt, t, zc)
+        dev = zt.device
+        ex = lambda name: self.extract_into_tensor(getattr(self, name).to(dev), t, zt.shape)  # noqa: E731
+        z0 = ex("sqrt_recip_alphas_cumprod") * zt - ex("sqrt_recipm1_alphas_cumprod") * eps
+        mean = ex("posterior_mean_coef1") * z0 + ex("posterior_mean_coef2") * zt
+        logvar = ex("posterior_log_variance_clipped")
+        if use_alignment:
+            g = self.alignment_fn(zt, t, zc=zc, y=y, **(alignment_kwargs or {}))
+            mean = mean - (0.5 * logvar).exp() * g
+        if noise is None:
+            noise = torch.randn(zt.shape, device=dev)
+        noise = noise * temperature
+        nonzero = (1 - (t == 0).float()).reshape(B, *((1,) * (zt.dim() - 1)))
+        out = mean + nonzero * (0.5 * logvar).exp() * noise
+        return (out, z0) if return_x0 else out
+
+    @torch.no_grad()
+    def p_sample_loop(self, cond, shape, y=None, use_alignment=False, alignment_kwargs=None,
+                      return_intermediates=False, x_T=None, verbose=False, callback=None, timesteps=None, mask=None,
+                      x0=None, img_callback=None, start_T=None, log_every_t=None, noise=None):
+        """DDPM ancestral loop, t = timesteps-1 .. 0 (latent_diffusion.py:633-684).
+
+        With the CUDA UNet and no alignment / inpainting the stretches between logging points run as one
+        device-resident loop; the per-step noise is pre-drawn with the same torch.randn calls, in the same order,
+        that the reference makes (or taken from `noise` [steps, *shape])."""
+        log_every_t = log_every_t or self.log_every_t
+        device = cond.device
+        B = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T.clone()
+        img = img.contiguous().float()
+        intermediates = [img.clone()]
+        timesteps = self.num_timesteps if timesteps is None else timesteps
+        if start_T is not None:
+            timesteps = min(timesteps, start_T)
+        if mask is not None:
+            assert x0 is not None and x0.shape[2:3] == mask.shape[2:3]
+        cond = cond.contiguous().float()
+        host_driven = use_alignment or mask is not None or not self._native()
+        if host_driven:
+            for k, i in enumerate(reversed(range(timesteps))):
+                ts = torch.full((B,), i, device=device, dtype=torch.long)
+                img = self.p_sample(zt=img, zc=cond, t=ts, y=y, use_alignment=use_alignment,
+                                    alignment_kwargs=alignment_kwargs, noise=None if noise is None else noise[k])
+                if mask is not None:
+                    img = self.q_sample(x0, ts) * mask + (1. - mask) * img
+                if i % log_every_t == 0 or i == timesteps - 1:
+                    intermediates.append(img.clone())
+                if callback:
+                    callback(i)
+                if img_callback:
+                    img_callback(img, i)
+        else:
+            # stop points: after every step the reference would log / call back on
+            per_step_host = bool(callback or img_callback)
+            stops = [k + 1 for k, i in enumerate(reversed(range(timesteps)))
+                     if per_step_host or (return_intermediates and (i % log_every_t == 0 or i == timesteps - 1))]
+            if not stops or stops[-1] != timesteps:
+                stops.append(timesteps)
+            chunk = max(1, (256 << 20) // max(1, img.numel() * 4))  # <= 256 MiB of noise resident at a time
+            k = 0
+            for stop in stops:
+                while k < stop:
+                    k1 = min(stop, k + chunk)
+                    if noise is not None:
+                        nz = noise[k:k1].contiguous().float()
+                    else:  # the reference's per-step torch.randn(shape) calls, drawn up front in order
+                        nz = torch.stack([torch.randn(shape, device=device) for _ in range(k1 - k)])
+                    self._run_range(img, cond, nz, PD_MODE_DDPM, timesteps, 0.0, k, k1)
+                    k = k1
+                i = timesteps - stop  # timestep just executed
+                if return_intermediates and (i % log_every_t == 0 or i == timesteps - 1):
+                    intermediates.append(img.clone())
+                if per_step_host:
+                    if callback:
+                        callback(i)
+                    if img_callback:
+                        img_callback(img, i)
+        if return_intermediates:
+            return img, intermediates
+        return img
+
+    @torch.no_grad()
+    def ddim_sample_loop(self, cond, shape, x_T=None, ddim_steps=50, eta=0.0, noise=None):
+        """DDIM over make_ddim_timesteps('uniform', ddim_steps, T); eta = 0 is
+        deterministic. Runs entirely on the device (one CUDA-graph replay per step)."""
+        if not self._native():
+            raise L.PDError("ddim_sample_loop needs the prediff_b200 CuboidTransformerUNet as torch_nn_module")
+        device = cond.device
+        img = torch.randn(shape, device=device) if x_T is None else x_T.clone()
+        img = img.contiguous().float()
+        cond = cond.contiguous().float()
+        if eta != 0.0 and noise is None:
+            noise = torch.stack([torch.randn(shape, device=device) for _ in range(ddim_steps)])
+        nz = None if noise is None else noise.contiguous().float()
+        self._run_range(img, cond, nz, PD_MODE_DDIM, ddim_steps, float(eta), 0, ddim_steps)
+        return img
+
+    @torch.no_grad()
+    def sample(self, cond, batch_size=16, use_alignment=False, alignment_kwargs=None, return_intermediates=False,
+               x_T=None, verbose=False, timesteps=None, mask=None, x0=None, shape=None, return_decoded=True,
+               sampler="ddpm", ddim_steps=50, ddim_eta=0.0, **kwargs):
+        """latent_diffusion.py:686-724: encode the context, run the loop, decode. `sampler="ddim"` selects the
+        DDIM loop (not in the reference; default stays the reference's ancestral sampler)."""
+        if use_alignment:
+            assert self.alignment_fn is not None, "Alignment function not set."
+        if shape is None:
+            shape = self.get_batch_latent_shape(batch_size=batch_size)
+        if self.cond_stage_model is not None:
+            assert cond is not None
+            if isinstance(cond, dict):
+                zc = {k: (v[:batch_size] if not isinstance(v, list) else [e[:batch_size] for e in v])
+                      for k, v in cond.items()}
+            else:
+                zc = cond[:batch_size]
+            zc = self.cond_stage_forward(zc if isinstance(zc, dict) else {"y": zc})
+        else:
+            zc = cond if isinstance(cond, torch.Tensor) else cond.get("y", None)
+        y = cond if isinstance(cond, torch.Tensor) else cond.get("y", None)
+        if sampler == "ddim":
+            assert not use_alignment and mask is None and not return_intermediates
+            output = self.ddim_sample_loop(cond=zc, shape=shape, x_T=x_T, ddim_steps=ddim_steps, eta=ddim_eta)
+        else:
+            output = self.p_sample_loop(cond=zc, shape=shape, y=y, use_alignment=use_alignment,
+                                        alignment_kwargs=alignment_kwargs, return_intermediates=return_intermediates,
+                                        x_T=x_T, verbose=verbose, timesteps=timesteps, mask=mask, x0=x0, **kwargs)
+        if return_decoded:
+            if return_intermediates:
+                samples, inter = output
+                output = [self.decode_first_stage(samples), [self.decode_first_stage(e) for e in inter]]
+            else:
+                output = self.decode_first_stage(output)
+        return output

@@ -55,7 +55,7 @@ class VAEConfig:
 
 
 TINY_UNET = UNetConfig(base_units=64, depth=(1, 1))
-TINY_VAE = VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=64, w=64)
+TINY_VAE = VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=128, w=128)
 
 Spec = List[Tuple[str, Tuple[int, ...]]]
 

@@ -166,8 +166,6 @@ def gen_loop_tiny():
     """Reference p_sample_loop (DDPM ancestral) and sample() on the tiny config, RNG injected."""
     import prediff.diffusion.latent_diffusion as LD
     ucfg, vcfg = Wt.TINY_UNET, Wt.TINY_VAE
-    # the tiny VAE downsamples 64 -> 8, the tiny UNet runs at 16x16: use a 128x128 tiny VAE for sample()
-    vcfg = Wt.VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=128, w=128)
     unet, vae = ref_unet(ucfg), ref_vae(vcfg)
     ldm = ref_ldm(unet, vae, ucfg, vcfg)
     B, n_steps = 2, 4
@@ -199,7 +197,8 @@ def gen_loop_tiny():
         zc = ldm.cond_stage_forward({"y": y})
     finally:
         LD.noise_like = orig
-    save("loop_tiny", z0=z0, inter=torch.stack(inter), z_step900=z_step, sample_dec=dec, sample_zc=zc)
+    assert len(inter) == n_steps + 1 and torch.equal(inter[-1], z0) and torch.equal(inter[0], zT)
+    save("loop_tiny", z0=z0, inter1=inter[1], z_step900=z_step, sample_dec=dec, sample_zc=zc)
 
 
 @torch.no_grad()
@@ -220,7 +219,7 @@ def gen_ddim(tag, cfg, B, n_steps):
         eps = m(z, t, cond)
         z0 = (z - float(np.sqrt(1.0 - a[i])) * eps) / float(np.sqrt(a[i]))
         z = float(np.sqrt(ap[i])) * z0 + float(np.sqrt(1.0 - ap[i] - sig[i] ** 2)) * eps
-        if k + 1 in (1, 10, 25):
+        if k + 1 in (1, 25) and tag == "full":
             snaps[f"z_after_{k + 1}"] = z.clone()
         if k % 10 == 0:
             print(f"ddim_{tag}: step {k + 1}/{len(ts)} ({time.time() - t0:.0f}s)", flush=True)

@@ -1,0 +1,97 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/prediff_b200.h declares, declares the reference's state_dict keys, reproduces the reference schedule
+buffers bit-exactly, and refuses to compute without an sm_100 device (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from prediff_b200 import _lib as L
+from prediff_b200 import weights as Wt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "prediff_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.pd_version()
+
+
+def test_unet_and_vae_weight_specs_match_reference_keys():
+    from prediff_b200.unet import CuboidTransformerUNet
+    from prediff_b200.vae import AutoencoderKL
+    for cfg in (Wt.TINY_UNET, Wt.UNetConfig()):
+        m = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c],
+                                  base_units=cfg.base_units, depth=list(cfg.depth), num_heads=cfg.num_heads)
+        spec = [(n, tuple(s)) for n, s in Wt.unet_param_spec(cfg)]
+        assert m.weight_spec_from_library() == spec
+        assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == spec
+    full = Wt.UNetConfig()
+    assert sum(int(np.prod(s)) for _, s in Wt.unet_param_spec(full)) == 136817538
+    for cfg in (Wt.TINY_VAE, Wt.VAEConfig()):
+        m = AutoencoderKL(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block,
+                          latent_channels=cfg.latent_channels, sample_size=(cfg.h, cfg.w))
+        spec = [(n, tuple(s)) for n, s in Wt.vae_param_spec(cfg)]
+        assert m.weight_spec_from_library() == spec
+    assert sum(int(np.prod(s)) for _, s in Wt.vae_param_spec(Wt.VAEConfig())) == 84499393
+
+
+def test_state_dict_has_reference_keys_including_derived_buffers():
+    from prediff_b200.unet import CuboidTransformerUNet
+    cfg = Wt.TINY_UNET
+    m = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=64, depth=[1, 1])
+    sd = m.state_dict()
+    assert "down_self_blocks.0.0.attn_l.2.qkv.weight" in sd and tuple(sd["down_self_blocks.0.0.attn_l.2.qkv.weight"].shape) == (192, 64)
+    idx = sd["down_self_blocks.1.0.attn_l.1.relative_position_index"]
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (8, 8) and idx[0, 0] == 7 and idx[7, 0] == 14
+    # loading a dict that carries the buffers (as a real pretrained .pt does) works with strict=True
+    m.load_state_dict(sd, strict=True)
+
+
+def test_schedule_through_c_abi_is_bit_exact_vs_reference():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "schedule.npz"))
+    h = ctypes.c_void_p()
+    L.check(L.lib().pd_sampler_create(1000, ctypes.c_double(1e-4), ctypes.c_double(2e-2), ctypes.byref(h)))
+    for name in ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                 "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]:
+        buf = np.empty(1000, dtype=np.float32)
+        L.check(L.lib().pd_sampler_get_buffer(h, name.encode(), buf.ctypes.data_as(ctypes.c_void_p)))
+        assert np.array_equal(buf, g[name]), name
+    with pytest.raises(L.PDError):
+        L.check(L.lib().pd_sampler_get_buffer(h, b"no_such_buffer", buf.ctypes.data_as(ctypes.c_void_p)))
+    L.lib().pd_sampler_destroy(h)
+
+
+def test_unsupported_configs_fail_loudly():
+    from prediff_b200.unet import CuboidTransformerUNet
+    with pytest.raises(NotImplementedError):
+        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], block_attn_patterns="video_swin_2x4")
+    with pytest.raises(NotImplementedError):
+        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], depth=[2, 2, 2])
+    with pytest.raises(L.PDError):  # rejected by the C++ validate(): 24x24 latents do not tile
+        CuboidTransformerUNet([7, 24, 24, 64], [6, 24, 24, 64], base_units=64, depth=[1, 1]).weight_spec_from_library()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_error_not_fallback():
+    from prediff_b200.unet import CuboidTransformerUNet
+    cfg = Wt.TINY_UNET
+    m = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=64, depth=[1, 1])
+    with pytest.raises(L.PDError):
+        m(torch.zeros(1, 6, 16, 16, 64), torch.zeros(1, dtype=torch.long), torch.zeros(1, 7, 16, 16, 64))
+    with pytest.raises(L.PDError):
+        L.init()

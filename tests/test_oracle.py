@@ -97,7 +97,7 @@ def test_ddpm_loop_and_step_tiny_vs_reference(tiny_unet_sd):
 def test_sample_end_to_end_tiny_vs_reference(tiny_unet_sd):
     """LatentDiffusion.sample(): encode context (mode) -> DDPM loop -> decode (latent_diffusion.py:686-724)."""
     cfg = Wt.TINY_UNET
-    vcfg = Wt.VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=128, w=128)
+    vcfg = Wt.TINY_VAE
     vsd = O.to_torch_sd(Wt.seeded_state_dict(Wt.vae_param_spec(vcfg), VAE_SEED))
     g = gold("loop_tiny")
     sched = O.make_schedule()

@@ -1,0 +1,121 @@
+"""GPU parity of the sampling loop (LatentDiffusion mirror -> pd_sample_loop) against goldens of the reference's
+own p_sample / p_sample_loop / sample (RNG injected) and the S6 DDIM definition run with the reference UNet."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prediff_oracle as O
+from prediff_b200 import weights as Wt
+from prediff_b200.diffusion import LatentDiffusion
+from tests.golden.gen_golden import inp
+from tests.test_unet_gpu import errs, make_unet
+from tests.test_vae_gpu import make_vae
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+# loop tolerances: per-step bf16 error saturates over the chain (5.5e-3 after 50 DDIM steps)
+LOOP_RMS_TOL, LOOP_MAX_TOL = 2.5e-2, 8e-2
+
+
+@pytest.fixture(scope="module")
+def tiny_ldm():
+    unet, usd = make_unet(Wt.TINY_UNET)
+    vae, vsd = make_vae(Wt.TINY_VAE)
+    ldm = LatentDiffusion(torch_nn_module=unet, data_shape=(6, 128, 128, 1), latent_shape=(6, 16, 16, 64),
+                          first_stage_model=vae, cond_stage_model="__is_first_stage__")
+    return ldm, usd, vsd
+
+
+def test_schedule_buffers_match_reference(tiny_ldm):
+    ldm, _, _ = tiny_ldm
+    g = np.load(os.path.join(G, "schedule.npz"))
+    for name in ["betas", "alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped", "posterior_variance"]:
+        assert np.array_equal(getattr(ldm, name).numpy(), g[name]), name  # bit-exact fp32 buffers
+
+
+def test_p_sample_step_t900(tiny_ldm):
+    ldm, _, _ = tiny_ldm
+    cfg = Wt.TINY_UNET
+    g = np.load(os.path.join(G, "loop_tiny.npz"))
+    zT = inp(777, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    cond = inp(778, 2, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()
+    noise = inp(779, 4, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    out = ldm.p_sample(zt=zT, zc=cond, t=torch.full((2,), 900, device="cuda"), noise=noise[0])
+    r, m = errs(out, g["z_step900"])
+    print(f"p_sample t=900: rel_rms={r:.3e} max={m:.3e}")
+    assert r < LOOP_RMS_TOL and m < LOOP_MAX_TOL
+
+
+def test_ddpm_loop_vs_reference_p_sample_loop(tiny_ldm):
+    ldm, _, _ = tiny_ldm
+    cfg = Wt.TINY_UNET
+    g = np.load(os.path.join(G, "loop_tiny.npz"))
+    zT = inp(777, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    cond = inp(778, 2, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()
+    noise = inp(779, 4, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    z0, inter = ldm.p_sample_loop(cond=cond, shape=tuple(zT.shape), x_T=zT, timesteps=4, return_intermediates=True,
+                                  log_every_t=1, noise=noise)
+    assert len(inter) == 5 and torch.equal(inter[0], zT) and torch.equal(inter[-1], z0)
+    r, m = errs(z0, g["z0"])
+    r1, m1 = errs(inter[1], g["inter1"])
+    print(f"ddpm 4 steps: z0 rel_rms={r:.3e} max={m:.3e}; after step 1 rel_rms={r1:.3e}")
+    assert r < LOOP_RMS_TOL and m < LOOP_MAX_TOL and r1 < LOOP_RMS_TOL
+    # device-resident loop (graph) == stepping one call at a time through the range API (bit-exact)
+    z_b = zT.clone()
+    for k in range(4):
+        ldm._run_range(z_b, cond, noise[k:k + 1].contiguous(), 0, 4, 0.0, k, k + 1)
+    assert torch.equal(z_b, z0)
+    # x_T must not be mutated (ownership contract)
+    assert torch.equal(zT, inp(777, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda())
+
+
+def test_sample_end_to_end_vs_reference(tiny_ldm):
+    """LatentDiffusion.sample(cond={"y": frames}) : encode -> loop -> decode, vs the reference's own sample()."""
+    ldm, _, _ = tiny_ldm
+    cfg = Wt.TINY_UNET
+    g = np.load(os.path.join(G, "loop_tiny.npz"))
+    zT = inp(777, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    noise = inp(779, 4, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    y = inp(780, 2, cfg.t_in, 128, 128, 1, uniform=True).cuda()
+    zc = ldm.cond_stage_forward({"y": y})
+    rz, mz = errs(zc, g["sample_zc"])
+    dec = ldm.sample(cond={"y": y}, batch_size=2, x_T=zT, timesteps=4, noise=noise)
+    assert tuple(dec.shape) == (2, 6, 128, 128, 1)
+    r, m = errs(dec, g["sample_dec"])
+    print(f"sample(): context latents rel_rms={rz:.3e}; decoded frames rel_rms={r:.3e} max={m:.3e}")
+    assert rz < 1.5e-2 and r < LOOP_RMS_TOL and m < LOOP_MAX_TOL
+
+
+def test_ddim50_tiny_vs_reference_unet(tiny_ldm):
+    ldm, _, _ = tiny_ldm
+    cfg = Wt.TINY_UNET
+    g = np.load(os.path.join(G, "ddim_tiny.npz"))
+    z = inp(4242, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    cond = inp(4243, 2, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()
+    z0 = ldm.ddim_sample_loop(cond=cond, shape=tuple(z.shape), x_T=z, ddim_steps=50, eta=0.0)
+    r, m = errs(z0, g["z0"])
+    print(f"ddim50 tiny: rel_rms={r:.3e} max={m:.3e}")
+    assert r < LOOP_RMS_TOL and m < LOOP_MAX_TOL
+    # idempotent / deterministic: a second run (graph replay path) is bit-identical
+    z0b = ldm.ddim_sample_loop(cond=cond, shape=tuple(z.shape), x_T=z, ddim_steps=50, eta=0.0)
+    assert torch.equal(z0, z0b)
+
+
+def test_ddim50_full_config_b4_vs_reference_unet():
+    """BASELINE config 3: 50-step DDIM, batch 4, shipped UNet sizes; golden = reference UNet on CPU (fp32)."""
+    cfg = Wt.UNetConfig()
+    unet, _ = make_unet(cfg, max_batch=4)
+    ldm = LatentDiffusion(torch_nn_module=unet)
+    g = np.load(os.path.join(G, "ddim_full.npz"))
+    z = inp(4242, 4, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    cond = inp(4243, 4, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()
+    z0 = ldm.ddim_sample_loop(cond=cond, shape=tuple(z.shape), x_T=z, ddim_steps=50, eta=0.0)
+    r, m = errs(z0, g["z0"])
+    print(f"ddim50 full B=4: final z0 rel_rms={r:.3e} max={m:.3e}")
+    assert r < LOOP_RMS_TOL and m < LOOP_MAX_TOL
+    # shard invariance: rows [2,4) run alone give the same bits as inside the batch of 4
+    z0_half = ldm.ddim_sample_loop(cond=cond[2:], shape=(2,) + tuple(z.shape[1:]), x_T=z[2:], ddim_steps=50, eta=0.0)
+    assert torch.equal(z0_half, z0[2:])
