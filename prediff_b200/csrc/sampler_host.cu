@@ -38,7 +38,30 @@ Sampler::Sampler(int num_timesteps, double linear_start, double linear_end) : T(
     put("posterior_mean_coef2", [&](int i) { return (1.0 - ac_prev[i]) * std::sqrt(1.0 - betas[i]) / (1.0 - ac[i]); });
 }
 
-Sampler::~Sampler() { drop_graph(); }
+Sampler::~Sampler() {
+    drop_graph();
+    if (ev_in_) cudaEventDestroy(ev_in_);
+    if (ev_out_) cudaEventDestroy(ev_out_);
+    if (loop_stream_) cudaStreamDestroy(loop_stream_);
+}
+
+// The loop runs on a private non-blocking stream (stream capture is not allowed on the legacy default stream,
+// which is what torch hands us by default); events order it after / before the caller's stream.
+int Sampler::enter(cudaStream_t user) {
+    if (!loop_stream_) {
+        PD_CUDA(cudaStreamCreateWithFlags(&loop_stream_, cudaStreamNonBlocking));
+        PD_CUDA(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
+        PD_CUDA(cudaEventCreateWithFlags(&ev_out_, cudaEventDisableTiming));
+    }
+    PD_CUDA(cudaEventRecord(ev_in_, user));
+    PD_CUDA(cudaStreamWaitEvent(loop_stream_, ev_in_, 0));
+    return PD_OK;
+}
+int Sampler::leave(cudaStream_t user) {
+    PD_CUDA(cudaEventRecord(ev_out_, loop_stream_));
+    PD_CUDA(cudaStreamWaitEvent(user, ev_out_, 0));
+    return PD_OK;
+}
 
 void Sampler::drop_graph() {
     if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
@@ -132,8 +155,16 @@ int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float*
 }
 
 int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_total, float eta,
-                  int k_begin, int k_end, cudaStream_t st) {
+                  int k_begin, int k_end, cudaStream_t user) {
     PD_CHECK(unet && z && cond, PD_ERR_ARG, "sample_loop: null pointer");
+    PD_TRY(enter(user));
+    const int rc = loop_on(loop_stream_, unet, z, cond, noise, B, mode, n_total, eta, k_begin, k_end);
+    const int rl = leave(user);
+    return rc != PD_OK ? rc : rl;
+}
+
+int Sampler::loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int mode,
+                     int n_total, float eta, int k_begin, int k_end) {
     std::vector<float> rows;
     std::vector<int64_t> ts;
     PD_TRY(coefficients(mode, n_total, eta, &rows, &ts));
@@ -184,8 +215,15 @@ int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, i
     return PD_OK;
 }
 
-int Sampler::step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st) {
+int Sampler::step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t user) {
     PD_CHECK(unet && z && cond, PD_ERR_ARG, "sample_step: null pointer");
+    PD_TRY(enter(user));
+    const int rc = step_on(loop_stream_, unet, z, cond, noise, B, t);
+    const int rl = leave(user);
+    return rc != PD_OK ? rc : rl;
+}
+
+int Sampler::step_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int t) {
     PD_CHECK(t >= 0 && t < T, PD_ERR_ARG, "sample_step: t=%d outside the schedule", t);
     std::vector<float> rows;
     std::vector<int64_t> ts;

@@ -22,6 +22,11 @@ public:
     int T;
 
 private:
+    int enter(cudaStream_t user);
+    int leave(cudaStream_t user);
+    int loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int mode,
+                int n_total, float eta, int k_begin, int k_end);
+    int step_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int t);
     int upload_tables(const std::vector<float>& rows, const std::vector<int64_t>& ts, int B, cudaStream_t st);
     int one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st);
     void drop_graph();
@@ -30,6 +35,8 @@ private:
     DevMem coef_dev_, t_dev_, step_dev_, eps_dev_;
     // cached one-iteration graph
     cudaGraphExec_t graph_exec_ = nullptr;
+    cudaStream_t loop_stream_ = nullptr;
+    cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
     struct Key {
         const void *unet, *z, *cond, *noise;
         int B;
