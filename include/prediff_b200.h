@@ -62,6 +62,13 @@ int pd_unet_finalize(pd_unet* m);
 int pd_unet_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
                     void* stream);
 
+/* Measurement helpers. profile: one eager forward with every launch bracketed by CUDA events on `stream`;
+ * stats = {tensor-core GEMM/conv ms, #GEMM launches, other-kernel ms, #other launches, GEMM FLOPs}.
+ * kernels_per_forward: number of kernel launches one forward of this batch size issues. */
+int pd_unet_profile_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
+                            void* stream, double stats[5]);
+int pd_unet_kernels_per_forward(pd_unet* m, int batch, int* n);
+
 /* ---- AutoencoderKL (reference: src/prediff/taming/autoencoder_kl.py:80-113, vae.py:70-86,150-166) --------- */
 typedef struct pd_vae pd_vae;
 typedef struct pd_vae_config {

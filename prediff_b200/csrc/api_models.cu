@@ -55,6 +55,19 @@ int pd_unet_forward(pd_unet* m, const float* x, const int64_t* t, const float* c
     return m->impl.forward(x, t, nullptr, cond, out, batch, S(stream));
 }
 
+int pd_unet_profile_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
+                            void* stream, double stats[5]) {
+    PD_CHECK(m && stats, PD_ERR_ARG, "pd_unet_profile_forward: null argument");
+    PlanProfile p;
+    PD_TRY(m->impl.forward(x, t, nullptr, cond, out, batch, S(stream), &p));
+    stats[0] = p.gemm_ms; stats[1] = p.n_gemm; stats[2] = p.other_ms; stats[3] = p.n_other; stats[4] = p.gemm_flops;
+    return PD_OK;
+}
+int pd_unet_kernels_per_forward(pd_unet* m, int batch, int* n) {
+    PD_CHECK(m && n, PD_ERR_ARG, "pd_unet_kernels_per_forward: null argument");
+    return m->impl.kernels_per_forward(batch, n);
+}
+
 int pd_sampler_create(int num_timesteps, double linear_start, double linear_end, pd_sampler** out) {
     PD_CHECK(out && num_timesteps >= 2 && linear_start > 0 && linear_end > linear_start, PD_ERR_ARG,
              "pd_sampler_create: bad argument");

@@ -126,19 +126,60 @@ private:
 
 using Step = std::function<int(cudaStream_t)>;
 
+enum StepKind : uint8_t { STEP_KERNEL = 0, STEP_GEMM = 1, STEP_NONE = 2 /* memset / placeholder without a kernel */ };
+
+struct PlanProfile {
+    double gemm_ms = 0, other_ms = 0, gemm_flops = 0;
+    int n_gemm = 0, n_other = 0;
+};
+
 struct Plan {
     std::vector<Step> steps;
+    std::vector<uint8_t> kinds;
     double gemm_flops = 0;
     int n_gemm = 0;
     int run(cudaStream_t st) const {
         for (const auto& s : steps) PD_TRY(s(st));
         return PD_OK;
     }
-    void add(Step s) { steps.push_back(std::move(s)); }
+    void add(Step s, StepKind k = STEP_KERNEL) {
+        steps.push_back(std::move(s));
+        kinds.push_back(k);
+    }
     void add_gemm(const GemmOp& op) {
         gemm_flops += op.flops;
         ++n_gemm;
-        steps.push_back([op](cudaStream_t st) { return gemm_launch(op, st); });
+        add([op](cudaStream_t st) { return gemm_launch(op, st); }, STEP_GEMM);
+    }
+    int num_kernels() const {
+        int n = 0;
+        for (auto k : kinds) n += k != STEP_NONE;
+        return n;
+    }
+    // One eager pass with every launch bracketed by CUDA events on the launching stream; per-class device time.
+    int run_profiled(cudaStream_t st, PlanProfile* out) const {
+        const size_t n = steps.size();
+        std::vector<cudaEvent_t> ev(n + 1);
+        for (auto& e : ev) PD_CUDA(cudaEventCreate(&e));
+        int rc = PD_OK;
+        PD_CUDA(cudaEventRecord(ev[0], st));
+        for (size_t i = 0; i < n && rc == PD_OK; ++i) {
+            rc = steps[i](st);
+            cudaEventRecord(ev[i + 1], st);
+        }
+        cudaStreamSynchronize(st);
+        if (rc == PD_OK) {
+            *out = PlanProfile();
+            out->gemm_flops = gemm_flops;
+            for (size_t i = 0; i < n; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                if (kinds[i] == STEP_GEMM) { out->gemm_ms += ms; ++out->n_gemm; }
+                else if (kinds[i] == STEP_KERNEL) { out->other_ms += ms; ++out->n_other; }
+            }
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        return rc;
     }
 };
 

@@ -385,7 +385,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     pl.add([=](cudaStream_t st) {
         PD_CUDA(cudaMemsetAsync(gn_all, 0, gn_bytes, st));
         return PD_OK;
-    });
+    }, STEP_NONE);
     // ---- time embedding (models/utils.py:68-83, time_embed.py:16-24, :108-114) ----
     {
         const float *w0 = te_w0, *b0 = te_b0, *w2 = te_w2, *b2 = te_b2;
@@ -500,7 +500,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.gemm_flops += bp->final_op.flops;
         ++pl.n_gemm;
         bp->out_slot = pl.steps.size();
-        pl.add([](cudaStream_t) { return PD_OK; });  // placeholder: final GEMM, bound per call
+        pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM);  // placeholder: final GEMM, bound per call
     }
     return PD_OK;
 }
@@ -520,7 +520,7 @@ int UNet::get_plan(int B, BatchPlan** out) {
 
 // t may point at a table indexed by a device-side step counter (sampler loop): t_table[*step * B + b].
 int UNet::forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B,
-                  cudaStream_t st) {
+                  cudaStream_t st, PlanProfile* prof) {
     PD_CHECK(x && t && cond && out, PD_ERR_ARG, "unet forward: null pointer");
     BatchPlan* bp = nullptr;
     PD_TRY(get_plan(B, &bp));
@@ -537,7 +537,15 @@ int UNet::forward(const float* x, const int64_t* t, const int* step, const float
     GemmOp fop = bp->final_op;
     fop.p.out_f32 = out;
     bp->plan.steps[bp->out_slot] = [fop](cudaStream_t s) { return gemm_launch(fop, s); };
+    if (prof) return bp->plan.run_profiled(st, prof);
     return bp->plan.run(st);
+}
+
+int UNet::kernels_per_forward(int B, int* n) {
+    BatchPlan* bp = nullptr;
+    PD_TRY(get_plan(B, &bp));
+    *n = bp->plan.num_kernels();
+    return PD_OK;
 }
 
 }  // namespace pd

@@ -31,7 +31,9 @@ public:
     int validate() const;
     int finalize();
     // t: device int64; if `step` (device int) is given, t is a table and row *step is used (sampler loop)
-    int forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B, cudaStream_t st);
+    int forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B, cudaStream_t st,
+                PlanProfile* prof = nullptr);
+    int kernels_per_forward(int B, int* n);
     int get_plan(int B, BatchPlan** out);
 
     pd_unet_config cfg;

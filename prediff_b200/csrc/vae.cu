@@ -412,7 +412,7 @@ int VAE::build(int N, bool encode, DirPlan* dp) {
         pl.add([=](cudaStream_t st) {
             PD_CUDA(cudaMemsetAsync(gs, 0, bytes, st));
             return PD_OK;
-        });
+        }, STEP_NONE);
     }
     int h = cfg.h, w = cfg.w;
     if (encode) {
