@@ -8,16 +8,40 @@ namespace {
 
 constexpr int kMaxLine = 16;
 
-// One block per line (all heads): stage the line's L rows of [3C] bf16 in smem, then warp h handles head h.
-// Two lanes per query row, each owning half of the head dim.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gsrc) : "memory");
+}
+
+// One block per line (<= 16 tokens along the attended axis), one warp per head. The line's q|k|v rows are staged
+// in smem with cp.async (rows padded by 16 B so ldmatrix is bank-conflict free); per head the 16x16 score tile and
+// the 16xHD output come from warp-level mma.sync (the sequence is far too short to fill a 128-row tcgen05 tile:
+// this op is 0.25 % of the step's FLOPs), softmax stays in the accumulator registers.
 template <int HD>
-__global__ void __launch_bounds__(256) axial_attention_kernel(const bf16* __restrict__ qkv,
+__global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __restrict__ qkv,
                                                               const float* __restrict__ bias_table,
                                                               bf16* __restrict__ out, int T, int H, int W, int C,
                                                               int heads, int axis) {
     extern __shared__ __align__(16) uint8_t smem_att[];
-    bf16* s_qkv = reinterpret_cast<bf16*>(smem_att);  // [L][3C]
+    bf16* s_qkv = reinterpret_cast<bf16*>(smem_att);  // [16][3C + 8]
     const int C3 = 3 * C;
+    const int ld = C3 + 8;
     int L, stride, base;
     {
         const int line = blockIdx.x;
@@ -34,96 +58,88 @@ __global__ void __launch_bounds__(256) axial_attention_kernel(const bf16* __rest
             base = line * W;
         }
     }
-    // cooperative, coalesced copy of the L token rows
     {
         const int vec_per_row = C3 / 8;  // 16-byte vectors
-        const int total = L * vec_per_row;
+        const int total = kMaxLine * vec_per_row;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int r = i / vec_per_row, v = i - r * vec_per_row;
-            const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(base + r * stride) * C3) + v;
-            reinterpret_cast<uint4*>(s_qkv + (size_t)r * C3)[v] = __ldg(src);
+            bf16* dst = s_qkv + (size_t)r * ld + v * 8;
+            if (r < L) cp_async16(dst, qkv + (size_t)(base + r * stride) * C3 + v * 8);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);  // padded tokens: finite (zero) rows
         }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
-    constexpr int DPL = HD / 2;  // dims per lane
     const int lane = threadIdx.x & 31;
-    const int i = lane >> 1;     // query slot
-    const int part = lane & 1;
+    const int g = lane >> 2, tq = lane & 3;
     const float scale = rsqrtf((float)HD);
     for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
-        const bool active = i < L;
-        const int qi = active ? i : 0;
-        float q[DPL];
-        {
-            const bf16* qp = s_qkv + (size_t)qi * C3 + h * HD + part * DPL;
+        const bf16* sq = s_qkv + h * HD;
+        const bf16* sk = s_qkv + C + h * HD;
+        const bf16* sv = s_qkv + 2 * C + h * HD;
+        // ---- S = Q K^T : 16 x 16, two 8-wide key tiles ----
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int d = 0; d < DPL; d += 2) {
-                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + d));
-                q[d] = f.x * scale;
-                q[d + 1] = f.y * scale;
-            }
+        for (int kk = 0; kk < HD / 16; ++kk) {
+            uint32_t a[4], b[4];
+            ldmatrix_x4(a, sq + (size_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * ld + kk * 16 + 8 * (lane >> 4));
+            ldmatrix_x4(b, sk + (size_t)((lane & 7) + 8 * (lane >> 4)) * ld + kk * 16 + 8 * ((lane >> 3) & 1));
+            mma_bf16_16816(s0, a, b[0], b[1]);
+            mma_bf16_16816(s1, a, b[2], b[3]);
         }
-        float sc[kMaxLine];
-        float mx = -INFINITY;
+        // thread holds rows g, g+8; keys {2tq, 2tq+1} (s0) and {8+2tq, 9+2tq} (s1)
+        float p[2][4];  // [row half][key slot]
 #pragma unroll
-        for (int j = 0; j < kMaxLine; ++j) {
-            float acc = 0.f;
-            if (j < L) {
-                const bf16* kp = s_qkv + (size_t)j * C3 + C + h * HD + part * DPL;
+        for (int rh = 0; rh < 2; ++rh) {
+            const int i = g + 8 * rh;
+            float v[4] = {s0[2 * rh], s0[2 * rh + 1], s1[2 * rh], s1[2 * rh + 1]};
+            const int j[4] = {2 * tq, 2 * tq + 1, 8 + 2 * tq, 9 + 2 * tq};
+            float mx = -INFINITY;
 #pragma unroll
-                for (int d = 0; d < DPL; d += 2) {
-                    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kp + d));
-                    acc = fmaf(q[d], f.x, acc);
-                    acc = fmaf(q[d + 1], f.y, acc);
-                }
+            for (int k = 0; k < 4; ++k) {
+                if (j[k] < L && i < L) v[k] = v[k] * scale + __ldg(bias_table + (i - j[k] + L - 1) * heads + h);
+                else v[k] = -INFINITY;
+                mx = fmaxf(mx, v[k]);
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            if (j < L) {
-                acc += __ldg(bias_table + (qi - j + L - 1) * heads + h);
-                mx = fmaxf(mx, acc);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            if (mx == -INFINITY) mx = 0.f;  // padded query row
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = __expf(v[k] - mx);
+                sum += v[k];
             }
-            sc[j] = acc;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = sum > 0.f ? 1.f / sum : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[rh][k] = v[k] * inv;
         }
-        float den = 0.f;
+        // P (C-fragment layout) is already the A fragment of the next mma: a0=(g, k lo), a1=(g+8, k lo), a2/a3 = k hi
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(p[0][0], p[0][1]);
+        pa[1] = pack_bf16x2(p[1][0], p[1][1]);
+        pa[2] = pack_bf16x2(p[0][2], p[0][3]);
+        pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+        // ---- O = P V : 16 x HD ----
+        bf16* o_lo = out + (size_t)(base + g * stride) * C + h * HD + 2 * tq;
+        bf16* o_hi = out + (size_t)(base + (g + 8) * stride) * C + h * HD + 2 * tq;
 #pragma unroll
-        for (int j = 0; j < kMaxLine; ++j) {
-            const float e = (j < L) ? __expf(sc[j] - mx) : 0.f;
-            sc[j] = e;
-            den += e;
-        }
-        const float inv = 1.f / den;
-        float o[DPL];
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) o[d] = 0.f;
-#pragma unroll
-        for (int j = 0; j < kMaxLine; ++j) {
-            if (j < L) {
-                const float pj = sc[j] * inv;
-                const bf16* vp = s_qkv + (size_t)j * C3 + 2 * C + h * HD + part * DPL;
-#pragma unroll
-                for (int d = 0; d < DPL; d += 2) {
-                    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vp + d));
-                    o[d] = fmaf(pj, f.x, o[d]);
-                    o[d + 1] = fmaf(pj, f.y, o[d + 1]);
-                }
+        for (int jn = 0; jn < HD / 8; jn += 2) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, sv + (size_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * ld + 8 * (jn + (lane >> 4)));
+            float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(o0, pa, b[0], b[1]);
+            mma_bf16_16816(o1, pa, b[2], b[3]);
+            if (g < L) {
+                *reinterpret_cast<uint32_t*>(o_lo + 8 * jn) = pack_bf16x2(o0[0], o0[1]);
+                *reinterpret_cast<uint32_t*>(o_lo + 8 * jn + 8) = pack_bf16x2(o1[0], o1[1]);
             }
-        }
-        if (active) {
-            bf16* op = out + (size_t)(base + i * stride) * C + h * HD + part * DPL;
-            if constexpr (DPL % 8 == 0) {
-#pragma unroll
-                for (int d = 0; d < DPL; d += 8) {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(o[d], o[d + 1]);
-                    pk.y = pack_bf16x2(o[d + 2], o[d + 3]);
-                    pk.z = pack_bf16x2(o[d + 4], o[d + 5]);
-                    pk.w = pack_bf16x2(o[d + 6], o[d + 7]);
-                    *reinterpret_cast<uint4*>(op + d) = pk;
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < DPL; d += 2) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(o[d], o[d + 1]);
+            if (g + 8 < L) {
+                *reinterpret_cast<uint32_t*>(o_hi + 8 * jn) = pack_bf16x2(o0[2], o0[3]);
+                *reinterpret_cast<uint32_t*>(o_hi + 8 * jn + 8) = pack_bf16x2(o1[2], o1[3]);
             }
         }
     }
@@ -190,8 +206,8 @@ int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, 
     PD_CHECK(C % heads == 0 && C % 8 == 0, PD_ERR_SHAPE, "axial_attention: C=%d heads=%d", C, heads);
     const int hd = C / heads;
     const int lines = B * T * H * W / L;
-    const size_t smem = (size_t)L * 3 * C * sizeof(bf16);
-    const int threads = heads * 32 > 256 ? 256 : heads * 32;
+    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16);
+    const int threads = heads * 32 > 128 ? 128 : heads * 32;
 #define PD_LAUNCH_AX(HDV)                                                                                            \
     do {                                                                                                             \
         static bool attr_set = false;                                                                                \

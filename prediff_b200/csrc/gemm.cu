@@ -13,31 +13,47 @@ namespace pd {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
 
-template <int BN>
+template <int BN, int STAGES>
 struct Cfg {
     static constexpr int kBBytes = BN * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // BN=256: 4 x 48 KB (1 CTA/SM); BN=128: 3 x 32 KB (2 CTAs/SM); BN<=64: 4 stages (2+ CTAs/SM)
-    static constexpr int kStages = (BN == 128) ? 3 : 4;
-    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kPipeBytes = STAGES * kStageBytes;
+    // barriers + tmem slot (256 B) then the per-CTA epilogue vector (bias + time-embedding row), BN floats
+    static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + 256 + BN * 4;
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    // <= ~110 KB of smem lets two CTAs share an SM, so one CTA's epilogue overlaps the other's mainloop
+    static constexpr int kMinBlocks = (kSmem <= 112 * 1024) ? 2 : 1;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): one MUFU.RCP,
+// one MUFU.EX2 and 7 FMAs instead of erff()'s ~25-instruction branchy path - the FFN-1 epilogue is issue-bound.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-z * z);   // erf(|x|/sqrt2)
+    return 0.5f * x + 0.5f * fabsf(x) * e;           // x * 0.5 * (1 + sign(x) erf(|x|/sqrt2))
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, Cfg<BN, STAGES>::kMinBlocks)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ GemmKernelParams p) {
-    using C = Cfg<BN>;
-    constexpr int STAGES = C::kStages;
+    using C = Cfg<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kPipeBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* vec_s = reinterpret_cast<float*>(smem + C::kPipeBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,6 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int rem = p0 - z0 * p.HW;
             const int y0 = rem / p.W;
             const int x0 = rem - y0 * p.W;
+            const int bz = p.b_batched ? sample : 0;
             int tap = 0, cb = 0;
             for (int it = 0; it < num_k; ++it) {
                 const int s = it % STAGES;
@@ -85,7 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
                 ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
                                  z0 + p.dz[tap], sample);
-                ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], it * kGemmBlockK, n0, p.b_batched ? sample : 0);
+                ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], it * kGemmBlockK, n0, bz);
                 if (++cb == p.cblks) { cb = 0; ++tap; }
             }
         }
@@ -110,59 +127,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::umma_commit(tmem_full_bar);      // accumulator complete
         }
     } else {
-        // ---- epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
+        // ---- epilogue: warps 2..9. Warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a lane
+        // quarter and split the BN columns. Each thread owns one output row and 32 consecutive columns per chunk,
+        // so everything stays in registers: bias/time-embedding from smem (broadcast), residual prefetched with
+        // independent 128-bit loads, 128-bit stores.
+        const int e = warp - 2;
         const int q = warp & 3;
-        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);  // aliases pipeline stage 0
+        const int half = e >> 2;
+        const int et = threadIdx.x - 64;
+        for (int i = et; i < BN; i += 32 * kEpiWarps) {
+            float v = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+            if (p.rowvec) v += __ldg(p.rowvec + (size_t)sample * p.rowvec_ld + n0 + i);
+            vec_s[i] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        constexpr int kChunks = BN / 32;
+        constexpr int kPerHalf = (kChunks + 1) / 2;
+        const int c_begin = half * kPerHalf;
+        const int c_end = (c_begin + kPerHalf) < kChunks ? (c_begin + kPerHalf) : kChunks;
+        const int prow = p0 + q * 32 + lane;
+        const bool valid = prow < p.rows_per_sample;
+        const size_t row_off = ((size_t)sample * p.rows_per_sample + prow) * p.ldo + n0;
+        const float* res_row = p.residual ? p.residual + row_off : nullptr;
+        float* of_row = p.out_f32 ? p.out_f32 + row_off : nullptr;
+        bf16* ob_row = p.out_bf16 ? p.out_bf16 + row_off : nullptr;
+        const int act = p.act;
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
-        const int ldo = p.ldo;
-        const int sub_row = lane >> 3;
-        const int c4 = (lane & 7) * 4;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-            ptx::tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(stage + lane * 36);
+        for (int c = c_begin; c < c_end; ++c) {
+            const int col = c * 32;
+            float4 res[8];
+            if (res_row && valid) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            __syncwarp();
-            const int col = n0 + c * 32 + c4;
-            float4 addv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) addv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            if (p.rowvec) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.rowvec + (size_t)sample * p.rowvec_ld + col));
-                addv.x += r.x; addv.y += r.y; addv.z += r.z; addv.w += r.w;
+                for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(res_row + col + 4 * i);
             }
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
+            ptx::tmem_ld_wait();
+            if (valid) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int row = it * 4 + sub_row;
-                const int prow = p0 + q * 32 + row;
-                if (prow < p.rows_per_sample) {
-                    float4 a = *reinterpret_cast<const float4*>(stage + row * 36 + c4);
-                    a.x += addv.x; a.y += addv.y; a.z += addv.z; a.w += addv.w;
-                    if (p.act == ACT_GELU) {
-                        a.x = gelu_erf_f(a.x); a.y = gelu_erf_f(a.y); a.z = gelu_erf_f(a.z); a.w = gelu_erf_f(a.w);
-                    } else if (p.act == ACT_SILU) {
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = *reinterpret_cast<const float4*>(vec_s + col + 4 * i);
+                    float4 a = make_float4(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y,
+                                           __uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w);
+                    if (act == ACT_GELU) {
+                        a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
+                    } else if (act == ACT_SILU) {
                         a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
                     }
-                    const size_t off = ((size_t)sample * p.rows_per_sample + prow) * ldo + col;
-                    if (p.residual) {
-                        const float4 r = *reinterpret_cast<const float4*>(p.residual + off);
-                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-                    }
-                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
-                    if (p.out_bf16) {
-                        uint2 o;
-                        o.x = pack_bf16x2(a.x, a.y);
-                        o.y = pack_bf16x2(a.z, a.w);
-                        *reinterpret_cast<uint2*>(p.out_bf16 + off) = o;
-                    }
+                    if (res_row) { a.x += res[i].x; a.y += res[i].y; a.z += res[i].z; a.w += res[i].w; }
+                    if (of_row) *reinterpret_cast<float4*>(of_row + col + 4 * i) = a;
+                    v[4 * i] = pack_bf16x2(a.x, a.y);       // reuse v[] as the packed bf16 row segment
+                    v[4 * i + 1] = pack_bf16x2(a.z, a.w);
+                }
+                if (ob_row) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(ob_row + col + 8 * i) =
+                            make_uint4(v[8 * i], v[8 * i + 1], v[8 * i + 4], v[8 * i + 5]);
                 }
             }
-            __syncwarp();
         }
     }
     ptx::tc_fence_before();
@@ -173,15 +198,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 bool g_inited = false;
 
-template <int BN>
+template <int BN, int STAGES>
 int set_smem_attr() {
-    PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg<BN, STAGES>::kSmem));
     return PD_OK;
 }
 
-template <int BN>
-int launch_bn(const GemmOp& op, cudaStream_t stream) {
-    gemm_tc_kernel<BN><<<dim3(op.grid_x, op.grid_y), kThreads, Cfg<BN>::kSmem, stream>>>(op.tmap_a, op.tmap_b, op.p);
+template <int BN, int STAGES>
+int launch_cfg(const GemmOp& op, cudaStream_t stream) {
+    gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
+        op.tmap_a, op.tmap_b, op.p);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -203,10 +230,11 @@ int gemm_init() {
     PD_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, PD_ERR_CUDA,
              "cuTensorMapEncodeTiled not available from the driver");
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
-    PD_TRY(set_smem_attr<32>());
-    PD_TRY(set_smem_attr<64>());
-    PD_TRY(set_smem_attr<128>());
-    PD_TRY(set_smem_attr<256>());
+    PD_TRY((set_smem_attr<32, 4>()));
+    PD_TRY((set_smem_attr<64, 4>()));
+    PD_TRY((set_smem_attr<128, 3>()));
+    PD_TRY((set_smem_attr<256, 2>()));
+    PD_TRY((set_smem_attr<256, 4>()));
     g_inited = true;
     return PD_OK;
 }
@@ -263,14 +291,16 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         if (const char* s = getenv("PD_GEMM_BN")) bn = atoi(s);
         if (bn && N % bn != 0) bn = 0;
     }
+    const int num_k = g.ntaps * (g.C / kGemmBlockK);
     if (!bn) {
-        // largest BLOCK_N whose grid still covers the SMs; otherwise the smallest one >= 64 (32 only if N forces it)
+        // Wide tiles cut L2->SM operand traffic (the binding resource of the implicit GEMM); shrink only when the
+        // grid would leave more than half of the SMs idle.
         const int cands[4] = {256, 128, 64, 32};
         int smallest = 0;
         for (int c : cands) {
             if (N % c != 0) continue;
             if (c >= 64 || !smallest) smallest = c;
-            if ((int64_t)m_tiles * (N / c) >= kNumSMs) { bn = c; break; }
+            if ((int64_t)m_tiles * (N / c) >= kNumSMs / 2) { bn = c; break; }
         }
         if (!bn) bn = smallest;
     }
@@ -315,6 +345,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.act = e.act;
     p.rowvec_ld = e.rowvec_ld ? e.rowvec_ld : N;
     op->block_n = bn;
+    // short K: the kernel is epilogue/memory-bound -> 2 stages so that two CTAs fit on an SM
+    op->stages = bn == 256 ? (num_k <= 8 ? 2 : 4) : (bn == 128 ? 3 : 4);
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);
     op->flops = 2.0 * (double)rows_per_sample * g.samples * (double)N * (double)g.ntaps * g.C;
@@ -323,10 +355,10 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
     switch (op.block_n) {
-        case 32: return launch_bn<32>(op, stream);
-        case 64: return launch_bn<64>(op, stream);
-        case 128: return launch_bn<128>(op, stream);
-        case 256: return launch_bn<256>(op, stream);
+        case 32: return launch_cfg<32, 4>(op, stream);
+        case 64: return launch_cfg<64, 4>(op, stream);
+        case 128: return launch_cfg<128, 3>(op, stream);
+        case 256: return op.stages == 2 ? launch_cfg<256, 2>(op, stream) : launch_cfg<256, 4>(op, stream);
     }
     set_error("gemm_launch: op not initialised");
     return PD_ERR_STATE;

@@ -7,7 +7,7 @@ namespace pd {
 namespace {
 
 constexpr int kGnThreads = 256;
-constexpr int kGnRowsPerBlock = 64;
+constexpr int kGnRowsPerBlock = 32;
 
 // x [S][R][C] -> partial (sum, sumsq) per (sample, group), accumulated in double.
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
