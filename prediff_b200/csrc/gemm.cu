@@ -22,8 +22,10 @@ struct Cfg {
     static constexpr int kBBytes = BN * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kPipeBytes = STAGES * kStageBytes;
-    // barriers + tmem slot (256 B) then the per-CTA epilogue vector (bias + time-embedding row), BN floats
-    static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + 256 + BN * 4;
+    static constexpr int kBarBytes = 512;
+    static_assert(kPipeBytes >= kEpiWarps * 2 * 4096, "epilogue slabs alias the pipeline stages");
+    // barriers + tmem slot (512 B) then the per-CTA epilogue vector (bias + time-embedding row), BN floats
+    static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + kBarBytes + BN * 4;
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
     // <= ~110 KB of smem lets two CTAs share an SM, so one CTA's epilogue overlaps the other's mainloop
     static constexpr int kMinBlocks = (kSmem <= 112 * 1024) ? 2 : 1;
@@ -45,6 +47,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, Cfg<BN, STAGES>::kMinBlocks)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                const __grid_constant__ GemmKernelParams p) {
     using C = Cfg<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -53,7 +56,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    float* vec_s = reinterpret_cast<float*>(smem + C::kPipeBytes + 256);
+    uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + C::kPipeBytes + 256);  // [kEpiWarps][2]
+    float* vec_s = reinterpret_cast<float*>(smem + C::kPipeBytes + C::kBarBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -70,12 +74,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_init(&empty_bar[s], 1);
         }
         ptx::mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 2 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_out);
+        if (p.has_res) ptx::prefetch_tmap(&tmap_res);
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, C::kTmemCols);
@@ -128,9 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else {
         // ---- epilogue: warps 2..9. Warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a lane
-        // quarter and split the BN columns. Each thread owns one output row and 32 consecutive columns per chunk,
-        // so everything stays in registers: bias/time-embedding from smem (broadcast), residual prefetched with
-        // independent 128-bit loads, 128-bit stores.
+        // quarter and split the BN columns. Each thread owns one output row. All global traffic of the epilogue is
+        // TMA: the residual sub-tile (32 rows x 128 B) is bulk-loaded into a swizzled smem slab, combined in place
+        // with the accumulator (+ bias / time-embedding from smem, activation) and bulk-stored, so the L1/LSU path
+        // never sees the row-per-thread (uncoalesced) pattern and ragged rows are clipped by the tensor map.
         const int e = warp - 2;
         const int q = warp & 3;
         const int half = e >> 2;
@@ -141,34 +149,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             vec_s[i] = v;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        constexpr int kChunks = BN / 32;
-        constexpr int kPerHalf = (kChunks + 1) / 2;
-        const int c_begin = half * kPerHalf;
-        const int c_end = (c_begin + kPerHalf) < kChunks ? (c_begin + kPerHalf) : kChunks;
-        const int prow = p0 + q * 32 + lane;
-        const bool valid = prow < p.rows_per_sample;
-        const size_t row_off = ((size_t)sample * p.rows_per_sample + prow) * p.ldo + n0;
-        const float* res_row = p.residual ? p.residual + row_off : nullptr;
-        float* of_row = p.out_f32 ? p.out_f32 + row_off : nullptr;
-        bf16* ob_row = p.out_bf16 ? p.out_bf16 + row_off : nullptr;
+        uint8_t* slab0 = smem + e * 8192;               // two 4 KB slabs per warp, aliasing the (finished) pipeline
+        uint64_t* my_bar = res_bar + 2 * e;
+        const int row0 = p0 + q * 32;                   // first row of this warp inside the sample
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
         const int act = p.act;
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-            const int col = c * 32;
-            float4 res[8];
-            if (res_row && valid) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(res_row + col + 4 * i);
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        if (!p.out_is_bf16) {
+            constexpr int kChunks = BN / 32;
+            constexpr int kPerHalf = (kChunks + 1) / 2;
+            const int c_begin = half * kPerHalf;
+            const int c_end = (c_begin + kPerHalf) < kChunks ? (c_begin + kPerHalf) : kChunks;
+            const bool has_res = p.has_res != 0;
+            if (has_res && lane == 0 && c_begin < c_end) {
+                ptx::mbar_arrive_expect_tx(&my_bar[0], 4096);
+                ptx::tma_load_3d(slab0, &tmap_res, &my_bar[0], n0 + c_begin * 32, row0, sample);
             }
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
-            ptx::tmem_ld_wait();
-            if (valid) {
+#pragma unroll 1
+            for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
+                const int s = idx & 1;
+                uint8_t* slab = slab0 + s * 4096;
+                if (lane == 0) {
+                    if (has_res) {
+                        ptx::bulk_wait_read<0>();       // store idx-1 has finished reading slab s^1
+                        if (c + 1 < c_end) {
+                            ptx::mbar_arrive_expect_tx(&my_bar[s ^ 1], 4096);
+                            ptx::tma_load_3d(slab0 + (s ^ 1) * 4096, &tmap_res, &my_bar[s ^ 1], n0 + (c + 1) * 32, row0,
+                                             sample);
+                        }
+                    } else {
+                        ptx::bulk_wait_read<1>();       // store idx-2 has finished reading slab s
+                    }
+                }
+                __syncwarp();
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(t_lane + c * 32, v);
+                if (has_res) ptx::mbar_wait(&my_bar[s], (idx >> 1) & 1);
+                ptx::tmem_ld_wait();
+                uint8_t* my_row = slab + lane * 128;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 b = *reinterpret_cast<const float4*>(vec_s + col + 4 * i);
+                    const float4 b = *reinterpret_cast<const float4*>(vec_s + c * 32 + 4 * i);
                     float4 a = make_float4(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y,
                                            __uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w);
                     if (act == ACT_GELU) {
@@ -176,19 +199,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     } else if (act == ACT_SILU) {
                         a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
                     }
-                    if (res_row) { a.x += res[i].x; a.y += res[i].y; a.z += res[i].z; a.w += res[i].w; }
-                    if (of_row) *reinterpret_cast<float4*>(of_row + col + 4 * i) = a;
-                    v[4 * i] = pack_bf16x2(a.x, a.y);       // reuse v[] as the packed bf16 row segment
-                    v[4 * i + 1] = pack_bf16x2(a.z, a.w);
+                    float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                    if (has_res) {
+                        const float4 r = *cell;
+                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                    }
+                    *cell = a;
                 }
-                if (ob_row) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
+                    ptx::bulk_commit();
+                }
+            }
+        } else {
+            constexpr int kChunks = BN / 64;  // 64 bf16 columns = one 128-byte slab row
+            constexpr int kPerHalf = (kChunks + 1) / 2;
+            const int c_begin = half * kPerHalf;
+            const int c_end = (c_begin + kPerHalf) < kChunks ? (c_begin + kPerHalf) : kChunks;
+#pragma unroll 1
+            for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
+                uint8_t* slab = slab0 + (idx & 1) * 4096;
+                if (lane == 0) ptx::bulk_wait_read<1>();
+                __syncwarp();
+                uint8_t* my_row = slab + lane * 128;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4*>(ob_row + col + 8 * i) =
-                            make_uint4(v[8 * i], v[8 * i + 1], v[8 * i + 4], v[8 * i + 5]);
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_lane + c * 64 + hh * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {   // 8 columns -> one 16-byte cell
+                        float a[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            a[k] = __uint_as_float(v[8 * i + k]) + vec_s[c * 64 + hh * 32 + 8 * i + k];
+                            if (act == ACT_GELU) a[k] = gelu_fast(a[k]);
+                            else if (act == ACT_SILU) a[k] = silu_f(a[k]);
+                        }
+                        const uint32_t cellidx = static_cast<uint32_t>(hh * 4 + i) ^ sw;
+                        *reinterpret_cast<uint4*>(my_row + (cellidx << 4)) =
+                            make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
+                                       pack_bf16x2(a[6], a[7]));
+                    }
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_3d(&tmap_out, slab, n0 + c * 64, row0, sample);
+                    ptx::bulk_commit();
                 }
             }
         }
+        if (lane == 0) ptx::bulk_wait_read<0>();   // smem must stay valid until the last bulk store has read it
+        __syncwarp();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -208,7 +273,7 @@ int set_smem_attr() {
 template <int BN, int STAGES>
 int launch_cfg(const GemmOp& op, cudaStream_t stream) {
     gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
-        op.tmap_a, op.tmap_b, op.p);
+        op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.p);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -251,7 +316,9 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
              "gemm: operands must be 16-byte aligned");
     const int ldo = e.ldo ? e.ldo : N;
     PD_CHECK(ldo % 4 == 0, PD_ERR_SHAPE, "gemm: output row stride must be a multiple of 4");
-    PD_CHECK(e.out_f32 || e.out_bf16, PD_ERR_ARG, "gemm: no output pointer");
+    PD_CHECK((e.out_f32 != nullptr) != (e.out_bf16 != nullptr), PD_ERR_ARG,
+             "gemm: exactly one of out_f32 / out_bf16 must be given");
+    PD_CHECK(!e.residual || e.out_f32, PD_ERR_ARG, "gemm: a residual needs the fp32 output");
 
     // ---- A box: 128 rows = bw x bh x bd positions -------------------------------------------------------------
     const int bw = g.W < kGemmBlockM ? g.W : kGemmBlockM;
@@ -298,7 +365,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         const int cands[4] = {256, 128, 64, 32};
         int smallest = 0;
         for (int c : cands) {
-            if (N % c != 0) continue;
+            if (N % c != 0 || (e.out_bf16 && c < 64)) continue;
             if (c >= 64 || !smallest) smallest = c;
             if ((int64_t)m_tiles * (N / c) >= kNumSMs / 2) { bn = c; break; }
         }
@@ -321,6 +388,13 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
 
+    PD_CHECK(!e.out_bf16 || bn >= 64, PD_ERR_SHAPE, "gemm: bf16 output needs N to be a multiple of 64 (got %d)", N);
+    op->ldo = ldo;
+    op->out_rows = rows_per_sample;
+    op->out_samples = g.samples;
+    op->out_N = N;
+    PD_TRY(gemm_bind_output(op, e.out_f32, e.out_bf16, e.residual));
+
     GemmKernelParams& p = op->p;
     memset(&p, 0, sizeof(p));
     p.rows_per_sample = rows_per_sample;
@@ -338,10 +412,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     memcpy(p.dx, g.dx, sizeof(p.dx));
     p.bias = e.bias;
     p.rowvec = e.rowvec;
-    p.residual = e.residual;
-    p.out_f32 = e.out_f32;
-    p.out_bf16 = e.out_bf16;
-    p.ldo = ldo;
+    p.has_res = e.residual ? 1 : 0;
+    p.out_is_bf16 = e.out_bf16 ? 1 : 0;
     p.act = e.act;
     p.rowvec_ld = e.rowvec_ld ? e.rowvec_ld : N;
     op->block_n = bn;
@@ -350,6 +422,29 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);
     op->flops = 2.0 * (double)rows_per_sample * g.samples * (double)N * (double)g.ntaps * g.C;
+    return PD_OK;
+}
+
+// (Re)encodes the output / residual tensor maps: [samples][rows][N] with row stride ldo, 32-row x 128-byte boxes.
+int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual) {
+    PD_TRY(gemm_init());
+    auto enc = [&](CUtensorMap* m, void* ptr, bool is_bf16) -> int {
+        const int es_bytes = is_bf16 ? 2 : 4;
+        PD_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, PD_ERR_ARG, "gemm: output must be 16-byte aligned");
+        cuuint64_t dims[3] = {(cuuint64_t)op->out_N, (cuuint64_t)op->out_rows, (cuuint64_t)op->out_samples};
+        cuuint64_t strides[2] = {(cuuint64_t)op->ldo * es_bytes, (cuuint64_t)op->ldo * es_bytes * op->out_rows};
+        cuuint32_t box[3] = {(cuuint32_t)(128 / es_bytes), 32, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = g_encode(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr,
+                              dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+        return PD_OK;
+    };
+    if (out_bf16) PD_TRY(enc(&op->tmap_out, out_bf16, true));
+    else PD_TRY(enc(&op->tmap_out, out_f32, false));
+    if (residual) PD_TRY(enc(&op->tmap_res, const_cast<float*>(residual), false));
+    else op->tmap_res = op->tmap_out;
     return PD_OK;
 }
 

@@ -74,8 +74,8 @@ struct GemmEpilogue {
     const float* rowvec = nullptr;    // [samples][rowvec_ld], added to every row of the sample (time embedding)
     int rowvec_ld = 0;                // row stride of rowvec in elements (0 -> N)
     const float* residual = nullptr;  // [M][ldo] fp32, may alias out_f32
-    float* out_f32 = nullptr;         // [M][ldo]
-    bf16* out_bf16 = nullptr;         // [M][ldo]
+    float* out_f32 = nullptr;         // [M][ldo]   (exactly one of out_f32 / out_bf16)
+    bf16* out_bf16 = nullptr;         // [M][ldo]   (needs N % 64 == 0, no residual)
     int ldo = 0;                      // row stride of residual/out in elements (0 -> N)
     int act = ACT_NONE;               // applied after bias/rowvec, before the residual add
 };
@@ -87,15 +87,14 @@ struct GemmKernelParams {
     int8_t dz[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps];
     const float* bias;
     const float* rowvec;
-    const float* residual;
-    float* out_f32;
-    bf16* out_bf16;
-    int ldo, act, rowvec_ld;
+    int act, rowvec_ld;
+    int has_res, out_is_bf16;  // residual / output live in the tmap_res / tmap_out tensor maps
 };
 
 struct GemmOp {
-    CUtensorMap tmap_a, tmap_b;
+    CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res;
     GemmKernelParams p;
+    int ldo = 0, out_rows = 0, out_samples = 0, out_N = 0;
     int block_n = 0, stages = 0;
     unsigned grid_x = 0, grid_y = 0;
     size_t smem = 0;
@@ -106,6 +105,8 @@ struct GemmOp {
 int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int N, const GemmEpilogue& e,
               int force_block_n = 0);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
+// Points an already-built op at new output / residual buffers of the same shape (per-call user pointers).
+int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
 int gemm_init();  // resolves the driver entry point + raises the dynamic smem limits (idempotent)
 
 }  // namespace pd

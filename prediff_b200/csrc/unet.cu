@@ -495,7 +495,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.add([=](cudaStream_t st) { return cast_bf16(x0 + off, fin, B, rc, stride, st); });
         GemmEpilogue e;
         e.bias = final_b;
-        e.out_f32 = reinterpret_cast<float*>(16);  // bound per call
+        e.out_f32 = b.h[0];  // placeholder; re-bound to the caller's tensor per call
         PD_TRY(gemm_make(&bp->final_op, fin, GemmGeom::linear(B * cfg.t_out * HW, C0), final_w, cfg.c, e));
         pl.gemm_flops += bp->final_op.flops;
         ++pl.n_gemm;
@@ -535,7 +535,7 @@ int UNet::forward(const float* x, const int64_t* t, const int* step, const float
     bf16* xb = b.xin_bf16;
     bp->plan.steps[bp->in_slot] = [=](cudaStream_t s) { return unet_assemble(x, cond, xf, xb, B, Tx, Tc, HW, C, kCinPad, s); };
     GemmOp fop = bp->final_op;
-    fop.p.out_f32 = out;
+    PD_TRY(gemm_bind_output(&fop, out, nullptr, nullptr));
     bp->plan.steps[bp->out_slot] = [fop](cudaStream_t s) { return gemm_launch(fop, s); };
     if (prof) return bp->plan.run_profiled(st, prof);
     return bp->plan.run(st);

@@ -450,7 +450,7 @@ int VAE::build(int N, bool encode, DirPlan* dp) {
         {
             GemmEpilogue e;
             e.bias = quant_b;
-            e.out_f32 = reinterpret_cast<float*>(16);  // bound per call
+            e.out_f32 = c.stream();  // placeholder; re-bound to the caller's tensor per call
             PD_TRY(gemm_make(&dp->last_op, c.cast, GemmGeom::conv(N, 1, h, w, 2 * L, 1, 1, 1), quant_w, 2 * L, e));
             pl.gemm_flops += dp->last_op.flops;
             dp->out_slot = pl.steps.size();
@@ -527,7 +527,7 @@ int VAE::encode(const float* x, float* moments, int N, cudaStream_t st) {
     float* first = dp->first_buf;
     dp->plan.steps[dp->in_slot] = [=](cudaStream_t s) { return conv3x3_c1_in(x, w, b, first, N, H, W, c0, s); };
     GemmOp op = dp->last_op;
-    op.p.out_f32 = moments;
+    PD_TRY(gemm_bind_output(&op, moments, nullptr, nullptr));
     dp->plan.steps[dp->out_slot] = [op](cudaStream_t s) { return gemm_launch(op, s); };
     return dp->plan.run(st);
 }

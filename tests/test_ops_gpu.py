@@ -47,14 +47,23 @@ def test_gemm_linear(M, K, N, bn):
     w = _randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
     bias = _randn(N, seed=3)
     res = _randn(M, N, seed=4)
+    # fp32 output with fused bias + GELU + residual (TMA-loaded residual tile, TMA-stored result)
     out = torch.full((M, N), float("nan"), device=DEV)
-    outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
     _sync_check(L.lib().pd_op_conv_gemm(L.ptr(a), L.ptr(w), 1, 1, 1, M, K, 1, 1, 1, N, L.ptr(bias), None, L.ptr(res),
-                                        L.ptr(out), L.ptr(outb), 1, bn, L.stream_ptr()))
+                                        L.ptr(out), None, 1, bn, L.stream_ptr()))
     ref = F.gelu(a.float() @ w.float().t() + bias) + res
     e = rel_err(out, ref)
     assert e < 2e-5, f"fp32 out rel err {e}"
-    assert rel_err(outb, ref) < 1e-2
+    # in-place residual (out aliases residual), as the UNet uses it
+    out2 = res.clone()
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(a), L.ptr(w), 1, 1, 1, M, K, 1, 1, 1, N, L.ptr(bias), None, L.ptr(out2),
+                                        L.ptr(out2), None, 1, bn, L.stream_ptr()))
+    assert torch.equal(out2, out)
+    if N % 64 == 0:  # bf16 output path
+        outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        _sync_check(L.lib().pd_op_conv_gemm(L.ptr(a), L.ptr(w), 1, 1, 1, M, K, 1, 1, 1, N, L.ptr(bias), None, None,
+                                            None, L.ptr(outb), 1, bn, L.stream_ptr()))
+        assert rel_err(outb, F.gelu(a.float() @ w.float().t() + bias)) < 1e-2
 
 
 def test_gemm_plain_no_epilogue_and_rowvec():
