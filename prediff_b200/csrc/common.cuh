@@ -53,8 +53,35 @@ static inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b)
 constexpr int kNumSMs = 148;  // B200
 
 // ---- device helpers -------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// x * sigmoid(x): 1 FMUL + MUFU.EX2 + FADD + MUFU.RCP + FMUL
+__device__ __forceinline__ float silu_f(float x) {
+    return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + MUFU rounding):
+// 13 instructions incl. one MUFU.RCP and one MUFU.EX2 (erff() / __frcp_rn / __expf cost ~85) - the FFN-1 GEMM
+// epilogue is issue-bound on this function.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p = p * t;
+    const float ex = ex2_approx(ax * ax * (-0.5f * 1.4426950408889634f));  // exp(-x^2 / 2)
+    const float h = 0.5f * ax;
+    return fmaf(-h * p, ex, fmaf(0.5f, x, h));  // 0.5 x + 0.5 |x| erf(|x| / sqrt 2)
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

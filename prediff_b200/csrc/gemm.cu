@@ -31,19 +31,6 @@ struct Cfg {
     static constexpr int kMinBlocks = (kSmem <= 112 * 1024) ? 2 : 1;
 };
 
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): one MUFU.RCP,
-// one MUFU.EX2 and 7 FMAs instead of erff()'s ~25-instruction branchy path - the FFN-1 epilogue is issue-bound.
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * __expf(-z * z);   // erf(|x|/sqrt2)
-    return 0.5f * x + 0.5f * fabsf(x) * e;           // x * 0.5 * (1 + sign(x) erf(|x|/sqrt2))
-}
-
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, Cfg<BN, STAGES>::kMinBlocks)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -418,7 +405,9 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.rowvec_ld = e.rowvec_ld ? e.rowvec_ld : N;
     op->block_n = bn;
     // short K: the kernel is epilogue/memory-bound -> 2 stages so that two CTAs fit on an SM
-    op->stages = bn == 256 ? (num_k <= 8 ? 2 : 4) : (bn == 128 ? 3 : 4);
+    // ... unless the whole grid is a single wave anyway, where deeper prefetch wins
+    const bool multi_wave = (int64_t)m_tiles * (N / bn) > kNumSMs;
+    op->stages = bn == 256 ? ((num_k <= 8 && multi_wave) ? 2 : 4) : (bn == 128 ? 3 : 4);
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);
     op->flops = 2.0 * (double)rows_per_sample * g.samples * (double)N * (double)g.ntaps * g.C;
