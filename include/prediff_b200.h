@@ -129,6 +129,13 @@ int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* con
 int pd_op_conv_gemm(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt, int kh,
                     int kw, int N, const float* bias, const float* rowvec, const float* residual, float* out_f32,
                     void* out_bf16, int act, int block_n, void* stream);
+/* Same launch with clock64() phase stamps of CTA (dbg_block, 0) written to stamps9[9] (device u64):
+ * entry, setup done, first operand tile landed, last MMA issued, accumulator ready, first epilogue chunk ready,
+ * epilogue done, last bulk store drained, exit. Profiling aid (tools/gemm_phases.py). */
+int pd_op_conv_gemm_phases(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt,
+                           int kh, int kw, int N, const float* bias, const float* residual, float* out_f32,
+                           void* out_bf16, int act, int block_n, int dbg_block, unsigned long long* stamps9,
+                           void* stream);
 int pd_op_group_norm(const float* x, const float* gamma, const float* beta, void* y_bf16, int S, int R, int C, int G,
                      float eps, int silu, void* stream);
 int pd_op_layer_norm(const float* x, const float* gamma, const float* beta, void* y_bf16, int P, int C, float eps,

@@ -25,6 +25,30 @@ int pd_op_conv_gemm(const void* A, const void* Wt, int samples, int D, int H, in
     GemmEpilogue e;
     e.bias = bias; e.rowvec = rowvec; e.residual = residual; e.out_f32 = out_f32;
     e.out_bf16 = static_cast<bf16*>(out_bf16); e.act = act;
+    // long reductions exercise the split-K path: give it its (zeroed) per-tile handshake flags
+    int* flags = nullptr;
+    const int nflags = block_n == 0 || block_n == 256 ? gemm_split_flags_needed(g, N) : 0;
+    if (nflags > 0) {
+        PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&flags), nflags * sizeof(int), S(stream)));
+        PD_CUDA(cudaMemsetAsync(flags, 0, nflags * sizeof(int), S(stream)));
+        e.split_flags = flags;
+    }
+    GemmOp op;
+    int rc = gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e, block_n);
+    if (rc == PD_OK) rc = gemm_launch(op, S(stream));
+    if (flags) cudaFreeAsync(flags, S(stream));
+    return rc;
+}
+
+int pd_op_conv_gemm_phases(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
+                           int N, const float* bias, const float* residual, float* out_f32, void* out_bf16, int act,
+                           int block_n, int dbg_block, unsigned long long* stamps9, void* stream) {
+    PD_TRY(gemm_init());
+    GemmGeom g = GemmGeom::conv(samples, D, H, W, C, kt, kh, kw);
+    GemmEpilogue e;
+    e.bias = bias; e.residual = residual; e.out_f32 = out_f32;
+    e.out_bf16 = static_cast<bf16*>(out_bf16); e.act = act;
+    e.dbg = stamps9; e.dbg_block = dbg_block;
     GemmOp op;
     PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e, block_n));
     return gemm_launch(op, S(stream));

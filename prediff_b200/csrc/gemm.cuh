@@ -78,6 +78,9 @@ struct GemmEpilogue {
     bf16* out_bf16 = nullptr;         // [M][ldo]   (needs N % 64 == 0, no residual)
     int ldo = 0;                      // row stride of residual/out in elements (0 -> N)
     int act = ACT_NONE;               // applied after bias/rowvec, before the residual add
+    int* split_flags = nullptr;       // optional zeroed [m_tiles * n_tiles] ints: enables split-K (see gemm_make)
+    unsigned long long* dbg = nullptr;  // optional phase-timestamp buffer (9 x u64), see GemmKernelParams::dbg
+    int dbg_block = 0;
 };
 
 struct GemmKernelParams {
@@ -89,13 +92,16 @@ struct GemmKernelParams {
     const float* rowvec;
     int act, rowvec_ld;
     int has_res, out_is_bf16;  // residual / output live in the tmap_res / tmap_out tensor maps
+    int* split_flags;          // per-tile handshake between the two split-K CTAs (self re-arming)
+    unsigned long long* dbg;   // optional: 9 clock64() phase stamps of CTA (dbg_block, 0) - tools/gemm_phases.py
+    int dbg_block;
 };
 
 struct GemmOp {
     CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res;
     GemmKernelParams p;
     int ldo = 0, out_rows = 0, out_samples = 0, out_N = 0;
-    int block_n = 0, stages = 0;
+    int block_n = 0, stages = 0, split_k = 1;
     unsigned grid_x = 0, grid_y = 0;
     size_t smem = 0;
     double flops = 0;
@@ -107,6 +113,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
 // Points an already-built op at new output / residual buffers of the same shape (per-call user pointers).
 int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
+// Number of ints gemm_make may need in GemmEpilogue::split_flags for this geometry (0 if it will not split).
+int gemm_split_flags_needed(const GemmGeom& g, int N);
 int gemm_init();  // resolves the driver entry point + raises the dynamic smem limits (idempotent)
 
 }  // namespace pd

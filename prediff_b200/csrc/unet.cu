@@ -20,7 +20,9 @@ struct UNet::Bufs {
     bf16 *xin_bf16, *a[2], *ln[2], *qkv[2], *att[2], *mid[2], *pm, *up, *fin;
     float *e0, *e1, *temb, *embs;
     double* gn_sums;
+    int* split_flags;  // split-K tile handshake flags, shared by all convs of the plan (kernels run one at a time)
 };
+constexpr int kSplitFlagInts = 8192;
 
 struct UNet::BatchPlan {
     Arena arena;
@@ -277,6 +279,7 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
     b->temb = ar.template take<float>((size_t)B * TE);
     b->embs = ar.template take<float>((size_t)B * emb_total);
     b->gn_sums = ar.template take<double>((size_t)num_gn_slots() * B * 128 * 2);
+    b->split_flags = ar.template take<int>(kSplitFlagInts);
 }
 
 int UNet::num_gn_slots() const { return 2 + 4 * (cfg.depth[0] + cfg.depth[1]); }
@@ -298,8 +301,10 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         e.rowvec = b.embs + emb_off[emb_index];  // h + emb_out (time_embed.py:165)
         e.rowvec_ld = emb_total;
         e.out_f32 = h;
+        const GemmGeom g = GemmGeom::conv(B, T, H, W, C, 3, 3, 3);
+        if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
-        PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C, 3, 3, 3), r.conv1_w, C, e));
+        PD_TRY(gemm_make(&op, a, g, r.conv1_w, C, e));
         pl.add_gemm(op);
     }
     pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); });
@@ -309,8 +314,10 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         e.bias = r.conv2_b;
         e.residual = x;  // skip_connection = Identity (time_embed.py:169)
         e.out_f32 = x;
+        const GemmGeom g = GemmGeom::conv(B, T, H, W, C, 3, 3, 3);
+        if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
-        PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C, 3, 3, 3), r.conv2_w, C, e));
+        PD_TRY(gemm_make(&op, a, g, r.conv2_w, C, e));
         pl.add_gemm(op);
     }
     return PD_OK;
@@ -376,6 +383,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     Bufs& b = bp->bufs_storage();
     carve(bp->arena, B, &b);
     PD_CHECK(!bp->arena.overflowed(), PD_ERR_STATE, "unet: arena overflow");
+    PD_CUDA(cudaMemset(b.split_flags, 0, kSplitFlagInts * sizeof(int)));
     Plan& pl = bp->plan;
     const int H = cfg.h, W = cfg.w, HW = H * W;
     const int R0 = T * HW;

@@ -95,6 +95,7 @@ def _pack_conv(w, cipad):
     (1, 1, 128, 128, 64, 64, (1, 3, 3)),    # VAE full-resolution conv2d: tile = one image row
     (2, 13, 16, 16, 128, 64, (1, 1, 1)),    # 1x1x1 skip conv
     (1, 13, 16, 16, 256, 256, (3, 3, 3)),   # shipped level-0 conv
+    (2, 13, 8, 8, 512, 512, (3, 3, 3)),     # shipped level-1 conv: 216 k-blocks -> deterministic split-K = 2
 ])
 def test_conv_gemm(B, D, H, W, C, N, k):
     kt, kh, kw = k

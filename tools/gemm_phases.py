@@ -1,0 +1,59 @@
+"""Per-phase cycle stamps of one CTA of the tcgen05 GEMM for the UNet's shapes (B=4) + CUDA-event kernel times."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from prediff_b200 import _lib as L  # noqa: E402
+
+L.init()
+dev = "cuda"
+names = ["setup", "first_tile", "mainloop", "acc_ready", "first_chunk", "epilogue", "drain", "exit"]
+
+
+def run(tag, samples, D, H, W, C, k, N, res, bf16_out, act, bn=0):
+    kt, kh, kw = k
+    M = samples * D * H * W
+    a = torch.randn(M, C, device=dev).bfloat16()
+    w = (torch.randn(N, kt * kh * kw * C, device=dev) * 0.02).bfloat16()
+    bias = torch.randn(N, device=dev)
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    stamps = torch.zeros(9, device=dev, dtype=torch.int64)
+    args = lambda blk: (L.ptr(a), L.ptr(w), samples, D, H, W, C, kt, kh, kw, N, L.ptr(bias), L.ptr(out) if res else None,
+                        None if bf16_out else L.ptr(out), L.ptr(out) if bf16_out else None, act, bn, blk, L.ptr(stamps),
+                        L.stream_ptr())
+    for _ in range(3):
+        L.check(L.lib().pd_op_conv_gemm_phases(*args(0)))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        L.check(L.lib().pd_op_conv_gemm_phases(*args(0)))
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1000 / 20
+    flops = 2.0 * M * N * C * kt * kh * kw
+    line = f"{tag:28s} {us:7.1f} us/launch (back-to-back) {flops / us * 1e-6:7.1f} TF/s |"
+    for blk in (0, 50):
+        L.check(L.lib().pd_op_conv_gemm_phases(*args(blk)))
+        torch.cuda.synchronize()
+        s = stamps.cpu().tolist()
+        d = [s[i + 1] - s[i] for i in range(8)]
+        line += f" cta{blk}: " + " ".join(f"{n}={v}" for n, v in zip(names, d)) + f" total={s[8] - s[0]} |"
+    print(line)
+
+
+# level 0 (B=4): P = 13312 tokens, C=256
+run("L0 qkv   256->768 bf16", 1, 1, 1, 13312, 256, (1, 1, 1), 768, False, True, 0)
+run("L0 proj  256->256 f32+res", 1, 1, 1, 13312, 256, (1, 1, 1), 256, True, False, 0)
+run("L0 ffn1  256->1024 gelu", 1, 1, 1, 13312, 256, (1, 1, 1), 1024, False, True, 1)
+run("L0 ffn2  1024->256 f32+res", 1, 1, 1, 13312, 1024, (1, 1, 1), 256, True, False, 0)
+run("L0 conv3d 256->256", 4, 13, 16, 16, 256, (3, 3, 3), 256, True, False, 0)
+# level 1: P = 3328 tokens, C=512
+run("L1 qkv   512->1536 bf16", 1, 1, 1, 3328, 512, (1, 1, 1), 1536, False, True, 0)
+run("L1 proj  512->512 f32+res", 1, 1, 1, 3328, 512, (1, 1, 1), 512, True, False, 0)
+run("L1 ffn1  512->2048 gelu", 1, 1, 1, 3328, 512, (1, 1, 1), 2048, False, True, 1)
+run("L1 ffn2  2048->512 f32+res", 1, 1, 1, 3328, 2048, (1, 1, 1), 512, True, False, 0)
+run("L1 conv3d 512->512", 4, 13, 8, 8, 512, (3, 3, 3), 512, True, False, 0)
+run("L1 conv3d 512->512 bn256", 4, 13, 8, 8, 512, (3, 3, 3), 512, True, False, 0, 256)
