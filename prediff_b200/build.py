@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, f[:-3] + ".o") for f in _sources()]
     if jobs or not os.path.exists(LIB):
-        run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"])
+        run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+             "-Xlinker", "--no-undefined"])  # a stale object must fail the link, not the first call on the GPU box
     return LIB
 
 

@@ -43,17 +43,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + C::kPipeBytes + 256);  // [kEpiWarps][2]
+    uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + C::kPipeBytes + 128);  // [kEpiWarps][4]
     float* vec_s = reinterpret_cast<float*>(smem + C::kPipeBytes + C::kBarBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    unsigned long long* dbg = (p.dbg && blockIdx.x == p.dbg_block && blockIdx.y == 0) ? p.dbg : nullptr;
+#define PD_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) PD_STAMP(0);
 
     const int tile = blockIdx.x;
     const int n0 = blockIdx.y * BN;
     const int sample = tile / p.tiles_per_sample;
     const int p0 = (tile - sample * p.tiles_per_sample) * kGemmBlockM;
-    const int num_k = p.ntaps * p.cblks;
+    const int num_k_total = p.ntaps * p.cblks;
+    // split-K: CTA z handles k-blocks [k_begin, k_end); z = 0 owns bias / residual / plain store, z = 1 adds its
+    // partial with a TMA reduce-add once z = 0 has published the tile (fixed order -> deterministic sums)
+    const int split = blockIdx.z;
+    const int k_begin = (int)(((long long)num_k_total * split) / gridDim.z);
+    const int k_end = (int)(((long long)num_k_total * (split + 1)) / gridDim.z);
+    const int num_k = k_end - k_begin;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -61,7 +70,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_init(&empty_bar[s], 1);
         }
         ptx::mbar_init(tmem_full_bar, 1);
-        for (int i = 0; i < 2 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -79,6 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) PD_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -87,7 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int y0 = rem / p.W;
             const int x0 = rem - y0 * p.W;
             const int bz = p.b_batched ? sample : 0;
-            int tap = 0, cb = 0;
+            int tap = k_begin / p.cblks, cb = k_begin - tap * p.cblks;
             for (int it = 0; it < num_k; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -96,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
                 ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
                                  z0 + p.dz[tap], sample);
-                ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], it * kGemmBlockK, n0, bz);
+                ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], (k_begin + it) * kGemmBlockK, n0, bz);
                 if (++cb == p.cblks) { cb = 0; ++tap; }
             }
         }
@@ -108,6 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint32_t ph = (it / STAGES) & 1;
                 ptx::mbar_wait(&full_bar[s], ph);
                 ptx::tc_fence_after();
+                if (it == 0) PD_STAMP(2);
                 const uint32_t a_addr = ptx::smem_u32(smem + s * C::kStageBytes);
                 const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -119,6 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
             }
             ptx::umma_commit(tmem_full_bar);      // accumulator complete
+            PD_STAMP(3);
         }
     } else {
         // ---- epilogue: warps 2..9. Warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a lane
@@ -137,67 +149,128 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         uint8_t* slab0 = smem + e * 8192;               // two 4 KB slabs per warp, aliasing the (finished) pipeline
-        uint64_t* my_bar = res_bar + 2 * e;
+        uint64_t* my_bar = res_bar + 4 * e;
         const int row0 = p0 + q * 32;                   // first row of this warp inside the sample
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
         const int act = p.act;
         ptx::mbar_wait(tmem_full_bar, 0);
         ptx::tc_fence_after();
+        if (e == 0 && lane == 0) PD_STAMP(4);
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (!p.out_is_bf16) {
             constexpr int kChunks = BN / 32;
             constexpr int kPerHalf = (kChunks + 1) / 2;
+            constexpr int kMaxSlabs = C::kPipeBytes / (kEpiWarps * 4096);
+            constexpr int kSlabs = kPerHalf < kMaxSlabs ? kPerHalf : kMaxSlabs;   // 4 KB slabs per warp
+            constexpr bool kOwnSlab = kSlabs >= kPerHalf;                         // one slab per chunk: no reuse waits
+            uint8_t* slabs = smem + e * (kSlabs * 4096);   // aliases the (finished) pipeline stages
             const int c_begin = half * kPerHalf;
             const int c_end = (c_begin + kPerHalf) < kChunks ? (c_begin + kPerHalf) : kChunks;
-            const bool has_res = p.has_res != 0;
-            if (has_res && lane == 0 && c_begin < c_end) {
-                ptx::mbar_arrive_expect_tx(&my_bar[0], 4096);
-                ptx::tma_load_3d(slab0, &tmap_res, &my_bar[0], n0 + c_begin * 32, row0, sample);
-            }
+            const bool has_res = p.has_res != 0 && split == 0;
+            if (split != 0) {
+                // wait until split 0 has stored this tile, then add the partial sums on top (TMA reduce-add)
+                if (et == 0) {
+                    const int* flag = p.split_flags + blockIdx.y * gridDim.x + blockIdx.x;
+                    while (ptx::ld_acquire_gpu(flag) == 0) {}
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                ptx::fence_proxy_async_all();
 #pragma unroll 1
-            for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
-                const int s = idx & 1;
-                uint8_t* slab = slab0 + s * 4096;
-                if (lane == 0) {
-                    if (has_res) {
-                        ptx::bulk_wait_read<0>();       // store idx-1 has finished reading slab s^1
-                        if (c + 1 < c_end) {
-                            ptx::mbar_arrive_expect_tx(&my_bar[s ^ 1], 4096);
-                            ptx::tma_load_3d(slab0 + (s ^ 1) * 4096, &tmap_res, &my_bar[s ^ 1], n0 + (c + 1) * 32, row0,
-                                             sample);
-                        }
-                    } else {
-                        ptx::bulk_wait_read<1>();       // store idx-2 has finished reading slab s
+                for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
+                    uint8_t* slab = slabs + (kOwnSlab ? idx : (idx % kSlabs)) * 4096;
+                    if (!kOwnSlab) {
+                        if (lane == 0) ptx::bulk_wait_read<kSlabs - 1>();
+                        __syncwarp();
                     }
-                }
-                __syncwarp();
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(t_lane + c * 32, v);
-                if (has_res) ptx::mbar_wait(&my_bar[s], (idx >> 1) & 1);
-                ptx::tmem_ld_wait();
-                uint8_t* my_row = slab + lane * 128;
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_lane + c * 32, v);
+                    ptx::tmem_ld_wait();
+                    uint8_t* my_row = slab + lane * 128;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 b = *reinterpret_cast<const float4*>(vec_s + c * 32 + 4 * i);
-                    float4 a = make_float4(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y,
-                                           __uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w);
-                    if (act == ACT_GELU) {
-                        a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
-                    } else if (act == ACT_SILU) {
-                        a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<uint4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4)) =
+                            make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_reduce_add_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
+                        ptx::bulk_commit();
                     }
-                    float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
-                    if (has_res) {
-                        const float4 r = *cell;
-                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-                    }
-                    *cell = a;
                 }
-                ptx::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    ptx::tma_store_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
-                    ptx::bulk_commit();
+                if (lane == 0) ptx::bulk_wait_all<0>();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                if (et == 0) p.split_flags[blockIdx.y * gridDim.x + blockIdx.x] = 0;   // re-arm for the next launch
+            } else {
+                if (has_res && lane == 0) {
+                    if (kOwnSlab) {
+                        for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
+                            ptx::mbar_arrive_expect_tx(&my_bar[idx], 4096);
+                            ptx::tma_load_3d(slabs + idx * 4096, &tmap_res, &my_bar[idx], n0 + c * 32, row0, sample);
+                        }
+                    } else if (c_begin < c_end) {
+                        ptx::mbar_arrive_expect_tx(&my_bar[0], 4096);
+                        ptx::tma_load_3d(slabs, &tmap_res, &my_bar[0], n0 + c_begin * 32, row0, sample);
+                    }
+                }
+#pragma unroll 1
+                for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
+                    const int s = kOwnSlab ? idx : (idx % kSlabs);
+                    uint8_t* slab = slabs + s * 4096;
+                    if (!kOwnSlab) {
+                        if (lane == 0) {
+                            if (has_res) {
+                                ptx::bulk_wait_read<0>();   // the store that used the next slab has drained
+                                if (c + 1 < c_end) {
+                                    const int s1 = (idx + 1) % kSlabs;
+                                    ptx::mbar_arrive_expect_tx(&my_bar[s1], 4096);
+                                    ptx::tma_load_3d(slabs + s1 * 4096, &tmap_res, &my_bar[s1], n0 + (c + 1) * 32, row0,
+                                                     sample);
+                                }
+                            } else {
+                                ptx::bulk_wait_read<kSlabs - 1>();
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_lane + c * 32, v);
+                    if (has_res) ptx::mbar_wait(&my_bar[s], kOwnSlab ? 0u : static_cast<uint32_t>((idx / kSlabs) & 1));
+                    ptx::tmem_ld_wait();
+                    if (e == 0 && lane == 0 && idx == 0) PD_STAMP(5);
+                    uint8_t* my_row = slab + lane * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = *reinterpret_cast<const float4*>(vec_s + c * 32 + 4 * i);
+                        float4 a = make_float4(__uint_as_float(v[4 * i]) + b.x, __uint_as_float(v[4 * i + 1]) + b.y,
+                                               __uint_as_float(v[4 * i + 2]) + b.z, __uint_as_float(v[4 * i + 3]) + b.w);
+                        if (act == ACT_GELU) {
+                            a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
+                        } else if (act == ACT_SILU) {
+                            a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
+                        }
+                        float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                        if (has_res) {
+                            const float4 r = *cell;
+                            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                        }
+                        *cell = a;
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
+                        ptx::bulk_commit();
+                    }
+                }
+                if (gridDim.z > 1) {
+                    // publish the tile for the split-1 CTA: all bulk stores complete -> fence -> flag
+                    if (lane == 0) ptx::bulk_wait_all<0>();
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                    if (et == 0) {
+                        ptx::fence_proxy_async_all();
+                        __threadfence();
+                        ptx::st_release_gpu(p.split_flags + blockIdx.y * gridDim.x + blockIdx.x, 1);
+                    }
                 }
             }
         } else {
@@ -206,10 +279,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int c_begin = half * kPerHalf;
             const int c_end = (c_begin + kPerHalf) < kChunks ? (c_begin + kPerHalf) : kChunks;
 #pragma unroll 1
+            static_assert(kPerHalf <= 2, "bf16 epilogue: one slab per chunk");
             for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
-                uint8_t* slab = slab0 + (idx & 1) * 4096;
-                if (lane == 0) ptx::bulk_wait_read<1>();
-                __syncwarp();
+                uint8_t* slab = slab0 + idx * 4096;
                 uint8_t* my_row = slab + lane * 128;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -239,12 +311,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
         }
+        if (e == 0 && lane == 0) PD_STAMP(6);
         if (lane == 0) ptx::bulk_wait_read<0>();   // smem must stay valid until the last bulk store has read it
         __syncwarp();
+        if (e == 0 && lane == 0) PD_STAMP(7);
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (threadIdx.x == 0) PD_STAMP(8);
+#undef PD_STAMP
 }
 
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
@@ -259,7 +335,7 @@ int set_smem_attr() {
 
 template <int BN, int STAGES>
 int launch_cfg(const GemmOp& op, cudaStream_t stream) {
-    gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
+    gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y, op.split_k), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
         op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.p);
     PD_LAUNCH_CHECK();
     return PD_OK;
@@ -289,6 +365,13 @@ int gemm_init() {
     PD_TRY((set_smem_attr<256, 4>()));
     g_inited = true;
     return PD_OK;
+}
+
+int gemm_split_flags_needed(const GemmGeom& g, int N) {
+    const int out_D = g.out_D ? g.out_D : g.D;
+    const int num_k = g.ntaps * (g.C / kGemmBlockK);
+    if (num_k < 128 || N % 256 != 0) return 0;
+    return ceil_div(out_D * g.H * g.W, kGemmBlockM) * g.samples * (N / 256);
 }
 
 int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int N, const GemmEpilogue& e,
@@ -346,6 +429,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         if (bn && N % bn != 0) bn = 0;
     }
     const int num_k = g.ntaps * (g.C / kGemmBlockK);
+    if (!bn && e.split_flags && gemm_split_flags_needed(g, N) > 0 && e.out_f32 && e.act == ACT_NONE) bn = 256;
     if (!bn) {
         // Wide tiles cut L2->SM operand traffic (the binding resource of the implicit GEMM); shrink only when the
         // grid would leave more than half of the SMs idle.
@@ -402,12 +486,18 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.has_res = e.residual ? 1 : 0;
     p.out_is_bf16 = e.out_bf16 ? 1 : 0;
     p.act = e.act;
+    p.dbg = e.dbg;
+    p.dbg_block = e.dbg_block;
     p.rowvec_ld = e.rowvec_ld ? e.rowvec_ld : N;
     op->block_n = bn;
     // short K: the kernel is epilogue/memory-bound -> 2 stages so that two CTAs fit on an SM
     // ... unless the whole grid is a single wave anyway, where deeper prefetch wins
     const bool multi_wave = (int64_t)m_tiles * (N / bn) > kNumSMs;
     op->stages = bn == 256 ? ((num_k <= 8 && multi_wave) ? 2 : 4) : (bn == 128 ? 3 : 4);
+    // split-K = 2 for very long reductions (the level-1 Conv3d, 216 k-blocks): depends on the layer shape only, never
+    // on the batch, so results stay batch-invariant; the two partial sums are combined in a fixed order.
+    op->split_k = (e.split_flags && num_k >= 128 && bn == 256 && e.out_f32 && e.act == ACT_NONE) ? 2 : 1;
+    p.split_flags = e.split_flags;
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);
     op->flops = 2.0 * (double)rows_per_sample * g.samples * (double)N * (double)g.ntaps * g.C;
