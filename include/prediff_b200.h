@@ -129,6 +129,10 @@ int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* con
 int pd_op_conv_gemm(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt, int kh,
                     int kw, int N, const float* bias, const float* rowvec, const float* residual, float* out_f32,
                     void* out_bf16, int act, int block_n, void* stream);
+/* x[M][256] += A[M][K] Wt[256][K]^T + bias, and ln_out[M][256] (bf16) = LayerNorm(x row, eps 1e-5) * gamma + beta
+ * from the same epilogue (the fusion the UNet uses for proj / ffn_2 / conv2 -> next pre-norm at width 256). */
+int pd_op_linear_residual_ln(const void* A_bf16, const void* Wt_bf16, int M, int K, const float* bias, float* x_inout,
+                             const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream);
 /* Same launch with clock64() phase stamps of CTA (dbg_block, 0) written to stamps9[9] (device u64):
  * entry, setup done, first operand tile landed, last MMA issued, accumulator ready, first epilogue chunk ready,
  * epilogue done, last bulk store drained, exit. Profiling aid (tools/gemm_phases.py). */

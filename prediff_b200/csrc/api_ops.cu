@@ -40,6 +40,18 @@ int pd_op_conv_gemm(const void* A, const void* Wt, int samples, int D, int H, in
     return rc;
 }
 
+int pd_op_linear_residual_ln(const void* A, const void* Wt, int M, int K, const float* bias, float* x_inout,
+                             const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream) {
+    PD_TRY(gemm_init());
+    GemmGeom g = GemmGeom::linear(M, K);
+    GemmEpilogue e;
+    e.bias = bias; e.residual = x_inout; e.out_f32 = x_inout;
+    e.ln_gamma = ln_gamma; e.ln_beta = ln_beta; e.ln_out = static_cast<bf16*>(ln_out_bf16);
+    GemmOp op;
+    PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), 256, e));
+    return gemm_launch(op, S(stream));
+}
+
 int pd_op_conv_gemm_phases(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
                            int N, const float* bias, const float* residual, float* out_f32, void* out_bf16, int act,
                            int block_n, int dbg_block, unsigned long long* stamps9, void* stream) {

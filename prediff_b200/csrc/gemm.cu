@@ -23,9 +23,10 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kPipeBytes = STAGES * kStageBytes;
     static constexpr int kBarBytes = 512;
+    static constexpr int kLnBytes = 2 * BN * 4 + kEpiWarps * 32 * 8;  // fused-LN gamma/beta + row-sum exchange
     static_assert(kPipeBytes >= kEpiWarps * 2 * 4096, "epilogue slabs alias the pipeline stages");
     // barriers + tmem slot (512 B) then the per-CTA epilogue vector (bias + time-embedding row), BN floats
-    static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + kBarBytes + BN * 4;
+    static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + kBarBytes + BN * 4 + kLnBytes;
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
     // <= ~110 KB of smem lets two CTAs share an SM, so one CTA's epilogue overlaps the other's mainloop
     static constexpr int kMinBlocks = (kSmem <= 112 * 1024) ? 2 : 1;
@@ -35,7 +36,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, Cfg<BN, STAGES>::kMinBlocks)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-               const __grid_constant__ GemmKernelParams p) {
+               const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ GemmKernelParams p) {
     using C = Cfg<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -45,6 +46,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + C::kPipeBytes + 128);  // [kEpiWarps][4]
     float* vec_s = reinterpret_cast<float*>(smem + C::kPipeBytes + C::kBarBytes);
+    float* ln_g = vec_s + BN;                                   // fused LayerNorm: gamma, beta, per-row partial sums
+    float* ln_b = ln_g + BN;
+    float2* ln_x = reinterpret_cast<float2*>(ln_b + BN);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -79,6 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ptx::prefetch_tmap(&tmap_b);
         ptx::prefetch_tmap(&tmap_out);
         if (p.has_res) ptx::prefetch_tmap(&tmap_res);
+        if (p.ln_gamma) ptx::prefetch_tmap(&tmap_ln);
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, C::kTmemCols);
@@ -146,6 +151,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float v = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
             if (p.rowvec) v += __ldg(p.rowvec + (size_t)sample * p.rowvec_ld + n0 + i);
             vec_s[i] = v;
+            if (p.ln_gamma) {
+                ln_g[i] = __ldg(p.ln_gamma + n0 + i);
+                ln_b[i] = __ldg(p.ln_beta + n0 + i);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         uint8_t* slab0 = smem + e * 8192;               // two 4 KB slabs per warp, aliasing the (finished) pipeline
@@ -212,6 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         ptx::tma_load_3d(slabs, &tmap_res, &my_bar[0], n0 + c_begin * 32, row0, sample);
                     }
                 }
+                float ln_s1 = 0.f, ln_s2 = 0.f;
 #pragma unroll 1
                 for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
                     const int s = kOwnSlab ? idx : (idx % kSlabs);
@@ -254,12 +264,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
                         }
                         *cell = a;
+                        ln_s1 += (a.x + a.y) + (a.z + a.w);
+                        ln_s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         ptx::tma_store_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
                         ptx::bulk_commit();
+                    }
+                }
+                if constexpr (kOwnSlab && BN == 256 && kPerHalf == 4) {
+                    if (p.ln_gamma) {
+                        // ---- fused LayerNorm of the finished rows (this CTA owns all N = 256 columns) ----
+                        // each row lives in two warps (column halves): exchange partial sums through smem
+                        ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
+                        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+                        const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
+                        const float mean = (ln_s1 + o.x) * (1.0f / BN);
+                        const float var = fmaxf((ln_s2 + o.y) * (1.0f / BN) - mean * mean, 0.f);
+                        const float rstd = rsqrtf(var + p.ln_eps);
+                        uint8_t* bslabs = smem + kEpiWarps * 4 * 4096 + e * (2 * 4096);   // 2 bf16 slabs per warp
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {          // bf16 slab j = my fp32 chunks 2j, 2j+1 (64 columns)
+                            uint8_t* brow = bslabs + j * 4096 + lane * 128;
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc) {
+                                const uint8_t* frow = slabs + (2 * j + cc) * 4096 + lane * 128;
+                                const int colbase = (c_begin + 2 * j + cc) * 32;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {  // two fp32 cells -> one 16-byte bf16 cell
+                                    const float4 a0 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k) ^ sw) << 4));
+                                    const float4 a1 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k + 1) ^ sw) << 4));
+                                    const float4 g0 = *reinterpret_cast<const float4*>(ln_g + colbase + 8 * k);
+                                    const float4 g1 = *reinterpret_cast<const float4*>(ln_g + colbase + 8 * k + 4);
+                                    const float4 b0 = *reinterpret_cast<const float4*>(ln_b + colbase + 8 * k);
+                                    const float4 b1 = *reinterpret_cast<const float4*>(ln_b + colbase + 8 * k + 4);
+                                    uint4 pk;
+                                    pk.x = pack_bf16x2(fmaf((a0.x - mean) * rstd, g0.x, b0.x), fmaf((a0.y - mean) * rstd, g0.y, b0.y));
+                                    pk.y = pack_bf16x2(fmaf((a0.z - mean) * rstd, g0.z, b0.z), fmaf((a0.w - mean) * rstd, g0.w, b0.w));
+                                    pk.z = pack_bf16x2(fmaf((a1.x - mean) * rstd, g1.x, b1.x), fmaf((a1.y - mean) * rstd, g1.y, b1.y));
+                                    pk.w = pack_bf16x2(fmaf((a1.z - mean) * rstd, g1.z, b1.z), fmaf((a1.w - mean) * rstd, g1.w, b1.w));
+                                    *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(cc * 4 + k) ^ sw) << 4)) = pk;
+                                }
+                            }
+                        }
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_3d(&tmap_ln, bslabs, n0 + (c_begin + 0) * 32, row0, sample);
+                            ptx::tma_store_3d(&tmap_ln, bslabs + 4096, n0 + (c_begin + 2) * 32, row0, sample);
+                            ptx::bulk_commit();
+                        }
                     }
                 }
                 if (gridDim.z > 1) {
@@ -336,7 +392,7 @@ int set_smem_attr() {
 template <int BN, int STAGES>
 int launch_cfg(const GemmOp& op, cudaStream_t stream) {
     gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y, op.split_k), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
-        op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.p);
+        op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.tmap_ln, op.p);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -424,12 +480,21 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     const int tiles_per_sample = ceil_div(rows_per_sample, kGemmBlockM);
     const int m_tiles = tiles_per_sample * g.samples;
     int bn = force_block_n;
+    const bool want_ln = e.ln_out != nullptr;
+    if (want_ln) {
+        PD_CHECK(N == 256 && e.out_f32 && e.ln_gamma && e.ln_beta, PD_ERR_SHAPE,
+                 "gemm: the fused output LayerNorm needs N == 256 and an fp32 output (got N=%d)", N);
+        bn = 256;
+    }
     if (!bn) {
         if (const char* s = getenv("PD_GEMM_BN")) bn = atoi(s);
         if (bn && N % bn != 0) bn = 0;
     }
     const int num_k = g.ntaps * (g.C / kGemmBlockK);
     if (!bn && e.split_flags && gemm_split_flags_needed(g, N) > 0 && e.out_f32 && e.act == ACT_NONE) bn = 256;
+    // A 128 x 128 tcgen05.mma takes the same ~128 cycles as 128 x 256 (measured, tools/gemm_phases.py), so once the
+    // mainloop matters (>= 16 k-blocks) BN = 256 halves it even if fewer CTAs run.
+    if (!bn && N % 256 == 0 && num_k >= 16 && (int64_t)m_tiles * (N / 256) >= kNumSMs / 4) bn = 256;
     if (!bn) {
         // Wide tiles cut L2->SM operand traffic (the binding resource of the implicit GEMM); shrink only when the
         // grid would leave more than half of the SMs idle.
@@ -496,7 +561,22 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     op->stages = bn == 256 ? ((num_k <= 8 && multi_wave) ? 2 : 4) : (bn == 128 ? 3 : 4);
     // split-K = 2 for very long reductions (the level-1 Conv3d, 216 k-blocks): depends on the layer shape only, never
     // on the batch, so results stay batch-invariant; the two partial sums are combined in a fixed order.
-    op->split_k = (e.split_flags && num_k >= 128 && bn == 256 && e.out_f32 && e.act == ACT_NONE) ? 2 : 1;
+    op->split_k = (e.split_flags && num_k >= 128 && bn == 256 && e.out_f32 && e.act == ACT_NONE && !want_ln) ? 2 : 1;
+    if (want_ln) op->stages = 4;   // the LN pass needs every chunk resident in its own slab (192 KB of stages)
+    p.ln_gamma = want_ln ? e.ln_gamma : nullptr;
+    p.ln_beta = e.ln_beta;
+    p.ln_eps = e.ln_eps;
+    op->tmap_ln = op->tmap_out;
+    if (want_ln) {
+        cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows_per_sample, (cuuint64_t)g.samples};
+        cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * 2 * rows_per_sample};
+        cuuint32_t box[3] = {64, 32, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = g_encode(&op->tmap_ln, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, e.ln_out, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(ln) failed: %d", (int)r);
+    }
     p.split_flags = e.split_flags;
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);

@@ -78,6 +78,12 @@ struct GemmEpilogue {
     bf16* out_bf16 = nullptr;         // [M][ldo]   (needs N % 64 == 0, no residual)
     int ldo = 0;                      // row stride of residual/out in elements (0 -> N)
     int act = ACT_NONE;               // applied after bias/rowvec, before the residual add
+    // Optional fused LayerNorm of the OUTPUT rows (needs out_f32, N == 256 so one CTA owns whole rows):
+    // ln_out[M][N] bf16 = LN(out row) * ln_gamma + ln_beta - the next layer's pre-norm, saving its kernel + a pass.
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    bf16* ln_out = nullptr;
+    float ln_eps = 1e-5f;
     int* split_flags = nullptr;       // optional zeroed [m_tiles * n_tiles] ints: enables split-K (see gemm_make)
     unsigned long long* dbg = nullptr;  // optional phase-timestamp buffer (9 x u64), see GemmKernelParams::dbg
     int dbg_block = 0;
@@ -92,13 +98,16 @@ struct GemmKernelParams {
     const float* rowvec;
     int act, rowvec_ld;
     int has_res, out_is_bf16;  // residual / output live in the tmap_res / tmap_out tensor maps
+    const float* ln_gamma;     // fused output LayerNorm (null = off); result goes through tmap_ln
+    const float* ln_beta;
+    float ln_eps;
     int* split_flags;          // per-tile handshake between the two split-K CTAs (self re-arming)
     unsigned long long* dbg;   // optional: 9 clock64() phase stamps of CTA (dbg_block, 0) - tools/gemm_phases.py
     int dbg_block;
 };
 
 struct GemmOp {
-    CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res;
+    CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_ln;
     GemmKernelParams p;
     int ldo = 0, out_rows = 0, out_samples = 0, out_N = 0;
     int block_n = 0, stages = 0, split_k = 1;

@@ -284,7 +284,8 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
 
 int UNet::num_gn_slots() const { return 2 + 4 * (cfg.depth[0] + cfg.depth[1]); }
 
-int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot) {
+int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
+                       const StackW* next) {
     const int H = cfg.h >> lvl, W = cfg.w >> lvl, C = lvl ? C1 : C0;
     const int R = T * H * W;
     float* x = b.x[lvl];
@@ -314,6 +315,11 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         e.bias = r.conv2_b;
         e.residual = x;  // skip_connection = Identity (time_embed.py:169)
         e.out_f32 = x;
+        if (next && ln_fusable(lvl)) {  // LayerNorm of the first attention layer, computed on the finished rows
+            e.ln_gamma = next->a[0].ln_w;
+            e.ln_beta = next->a[0].ln_b;
+            e.ln_out = b.ln[lvl];
+        }
         const GemmGeom g = GemmGeom::conv(B, T, H, W, C, 3, 3, 3);
         if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
@@ -332,8 +338,10 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
     for (int i = 0; i < 3; ++i) {
         const AttnW& aw = s.a[i];
         const FfnW& fw = s.f[i];
-        // x = x + proj(attn(LN(x)))   (cuboid_transformer.py:1151, 813-952)
-        pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); });
+        const bool fuse = ln_fusable(lvl);
+        // x = x + proj(attn(LN(x)))   (cuboid_transformer.py:1151, 813-952). With C == 256 the LayerNorm was
+        // produced by the epilogue of the GEMM that last wrote x (conv2 / previous ffn_2).
+        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); });
         {
             GemmEpilogue e;
             e.out_bf16 = qkv;
@@ -347,12 +355,17 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             e.bias = aw.proj_b;
             e.residual = x;
             e.out_f32 = x;
+            if (fuse) {  // pre-norm of the FFN that follows
+                e.ln_gamma = fw.ln_w;
+                e.ln_beta = fw.ln_b;
+                e.ln_out = ln;
+            }
             GemmOp op;
             PD_TRY(gemm_make(&op, att, GemmGeom::linear(P, C), aw.proj_w, C, e));
             pl.add_gemm(op);
         }
         // x = x + W2 gelu(W1 LN(x) + b1) + b2   (cuboid_transformer.py:195-205)
-        pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); });
+        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); });
         {
             GemmEpilogue e;
             e.bias = fw.b1;
@@ -367,6 +380,11 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             e.bias = fw.b2;
             e.residual = x;
             e.out_f32 = x;
+            if (fuse && i < 2) {  // pre-norm of the next attention layer of this stack
+                e.ln_gamma = s.a[i + 1].ln_w;
+                e.ln_beta = s.a[i + 1].ln_b;
+                e.ln_out = ln;
+            }
             GemmOp op;
             PD_TRY(gemm_make(&op, mid, GemmGeom::linear(P, 4 * C), fw.w2, C, e));
             pl.add_gemm(op);
@@ -454,7 +472,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     }
     // ---- down path ----
     for (int d = 0; d < cfg.depth[0]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 0, down_res[0], 0, &gn_slot));
+        PD_TRY(add_resblock(pl, b, B, 0, down_res[0], 0, &gn_slot, &down_stack[0][d]));
         PD_TRY(add_stack(pl, b, B, 0, down_stack[0][d]));
     }
     {   // PatchMerging3D: x0 stays intact and doubles as the U-Net skip tensor
@@ -469,12 +487,12 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.add_gemm(op);
     }
     for (int d = 0; d < cfg.depth[1]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot));
+        PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot, &down_stack[1][d]));
         PD_TRY(add_stack(pl, b, B, 1, down_stack[1][d]));
     }
     // ---- up path ----
     for (int d = 0; d < cfg.depth[1]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 1, up_res[1], 3, &gn_slot));
+        PD_TRY(add_resblock(pl, b, B, 1, up_res[1], 3, &gn_slot, &up_stack[1][d]));
         PD_TRY(add_stack(pl, b, B, 1, up_stack[1][d]));
     }
     {   // Upsample3DLayer (nearest 2x + Conv2d 3x3 per frame) with the U-Net skip add fused as the residual
@@ -491,7 +509,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.add_gemm(op);
     }
     for (int d = 0; d < cfg.depth[0]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot));
+        PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot, &up_stack[0][d]));
         PD_TRY(add_stack(pl, b, B, 0, up_stack[0][d]));
     }
     PD_CHECK(gn_slot == num_gn_slots(), PD_ERR_STATE, "unet: gn slot accounting");

@@ -50,8 +50,12 @@ private:
     int finalize_resblock(const std::string& p, int cin, int cinpad, int cout, ResW* r);
     int finalize_stack(const std::string& p, int dim, StackW* s);
     int build_plan(int B, BatchPlan* bp);
-    int add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot);
+    // `next`: the stack block that follows - when the level width is 256 its first LayerNorm is fused into the
+    // resblock's conv2 epilogue (and add_stack skips that LayerNorm launch)
+    int add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
+                     const StackW* next);
     int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s);
+    bool ln_fusable(int lvl) const { return (lvl ? C1 : C0) == 256; }
     int num_gn_slots() const;
     template <class A>
     void carve(A& ar, int B, Bufs* b) const;

@@ -66,6 +66,24 @@ def test_gemm_linear(M, K, N, bn):
         assert rel_err(outb, F.gelu(a.float() @ w.float().t() + bias)) < 1e-2
 
 
+@pytest.mark.parametrize("M,K", [(3328, 256), (1000, 1024), (13312, 256)])
+def test_gemm_residual_fused_layernorm(M, K):
+    N = 256
+    a = _randn(M, K, seed=1).bfloat16()
+    w = _randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
+    bias = _randn(N, seed=3)
+    x = _randn(M, N, seed=4) * 2 + 0.3
+    gamma = 1 + 0.1 * _randn(N, seed=5)
+    beta = 0.1 * _randn(N, seed=6)
+    ref_x = a.float() @ w.float().t() + bias + x
+    ref_ln = F.layer_norm(ref_x, (N,), gamma, beta, 1e-5)
+    ln = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_linear_residual_ln(L.ptr(a), L.ptr(w), M, K, L.ptr(bias), L.ptr(x), L.ptr(gamma),
+                                                 L.ptr(beta), L.ptr(ln), L.stream_ptr()))
+    assert rel_err(x, ref_x) < 2e-5
+    assert rel_err(ln, ref_ln) < 6e-3
+
+
 def test_gemm_plain_no_epilogue_and_rowvec():
     M, K, N, samples = 512, 128, 128, 4
     a = _randn(samples * M, K, seed=5).bfloat16()
