@@ -266,8 +266,9 @@ def main():
                                                 L.stream_ptr(), stats))
     gemm_ms, n_gemm, other_ms, n_other, gemm_flops = list(stats)
     nk = ctypes.c_int()
-    L.check(L.lib().pd_unet_kernels_per_forward(unet.handle, B, ctypes.byref(nk)))
-    launches_per_loop_step = nk.value + 2   # + sampler_update + advance_step
+    n_sub = L.lib().pd_sampler_sub_batches(ldm._sampler, B)   # concurrent sub-batches inside the loop
+    L.check(L.lib().pd_unet_kernels_per_forward(unet.handle, B // n_sub, ctypes.byref(nk)))
+    launches_per_loop_step = n_sub * (nk.value + 1) + 1   # per sub-batch: UNet + sampler_update; + advance_step
     gpu_launches = launches_per_loop_step * S * K
 
     if rank != 0:
@@ -288,7 +289,8 @@ def main():
                    "step": f"one {S}-step DDIM loop over a batch of {B} forecasts per GPU = {B * S} UNet evaluations",
                    "ensemble": f"{G} members, {B} per rank, no data-path collective; one all-gather of decoded frames in e2e",
                    "l2": "inputs exceed L2: 274 MB of bf16 UNet weights are re-streamed every denoise step (L2 = 126 MB)",
-                   "numerics": "bf16 tensor-core operands, fp32 accumulate, fp32 residual stream", "cuda_graph": True},
+                   "numerics": "bf16 tensor-core operands, fp32 accumulate, fp32 residual stream", "cuda_graph": True,
+                   "sub_batches": n_sub},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K, "api": "LatentDiffusion.sample(cond={'y': frames}, sampler='ddim')"},
         "gpu_launches": gpu_launches,

@@ -118,6 +118,8 @@ int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, co
  * (latent_diffusion.py:659-680) between device-resident stretches. */
 int pd_sample_loop_range(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch,
                          int mode, int n_steps, float eta, int k_begin, int k_end, void* stream);
+/* Number of independent sub-batches (parallel streams) the loop cuts a batch into (env PD_SUB_BATCHES, default 2). */
+int pd_sampler_sub_batches(const pd_sampler* s, int batch);
 /* One reference p_sample step at integer timestep t (all batch rows share t): z <- p_sample(z, cond, t). */
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream);

@@ -90,6 +90,7 @@ int pd_sample_loop_range(pd_sampler* s, pd_unet* unet, float* z, const float* co
     PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_loop_range: null handle");
     return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, k_begin, k_end, S(stream));
 }
+int pd_sampler_sub_batches(const pd_sampler* s, int batch) { return s ? s->impl.n_sub_for(batch) : 0; }
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream) {
     PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_step_ddpm: null handle");

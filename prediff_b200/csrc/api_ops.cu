@@ -112,12 +112,12 @@ int pd_op_axial_attention(const void* qkv, const float* bias_table, void* out, i
 int pd_op_sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef8,
                          int64_t n, void* stream) {
     PD_TRY(gemm_init());
-    return sampler_update(z, eps, noise, guide, coef8, nullptr, n, S(stream));
+    return sampler_update(z, eps, noise, guide, coef8, nullptr, n, 0, S(stream));
 }
 
 int pd_op_timestep_embedding(const int64_t* t, float* out, int B, int dim, void* stream) {
     PD_TRY(gemm_init());
-    return timestep_embedding(t, nullptr, out, B, dim, S(stream));
+    return timestep_embedding(t, nullptr, 0, out, B, dim, S(stream));
 }
 
 int pd_op_small_linear(const float* in, const float* W, const float* bias, float* out, int B, int K, int N, int in_silu,

@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(kEwThreads) parity_split_kernel(const float* _
     }
 }
 
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const int* __restrict__ step,
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const int* __restrict__ step, int t_stride,
                                           float* __restrict__ out, int B, int dim) {
-    if (step) t += (size_t)(*step) * B;
+    if (step) t += (size_t)(*step) * t_stride;
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -279,10 +279,11 @@ int parity_split_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaS
     return PD_OK;
 }
 
-int timestep_embedding(const int64_t* t, const int* step, float* out, int B, int dim, cudaStream_t st) {
+int timestep_embedding(const int64_t* t, const int* step, int t_stride, float* out, int B, int dim,
+                       cudaStream_t st) {
     PD_CHECK(dim % 2 == 0, PD_ERR_SHAPE, "timestep_embedding: dim must be even");
     const int total = B * (dim / 2);
-    timestep_embedding_kernel<<<ceil_div(total, 128), 128, 0, st>>>(t, step, out, B, dim);
+    timestep_embedding_kernel<<<ceil_div(total, 128), 128, 0, st>>>(t, step, t_stride ? t_stride : B, out, B, dim);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -51,7 +51,7 @@ int cast_bf16(const float* x, bf16* y, int S, int64_t RC, int64_t in_sample_stri
 int parity_split_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st);
 // sinusoidal timestep embedding (models/utils.py:77-83): out[b] = [cos(t f_i) | sin(t f_i)], dim even.
 // If `step` (device int) is non-null, t is a table [n_steps][B] and row *step is used (device-resident loop).
-int timestep_embedding(const int64_t* t, const int* step, float* out, int B, int dim, cudaStream_t st);
+int timestep_embedding(const int64_t* t, const int* step, int t_stride, float* out, int B, int dim, cudaStream_t st);
 // out[b][n] = out_act( sum_k in_act(in[b][k]) * W[n][k] + bias[n] ), fp32, tiny-M linear (time-embedding MLP).
 int small_linear(const float* in, const float* W, const float* bias, float* out, int B, int K, int N, int in_silu,
                  int out_silu, cudaStream_t st);
@@ -72,8 +72,9 @@ int pack_conv(const float* w, bf16* out, int Co, int Ci, int taps, int Cipad, cu
 //   z0 = c[0] z - c[1] eps ;  z <- c[2] z0 + c[3] z + c[4] eps + c[5] noise - c[6] guide
 // coef points at 8 floats in device memory (the row of the resident schedule table for this step).
 // If `step` (device int) is non-null, coef is a table [n_steps][8] and noise a stack [n_steps][n]; row *step is used.
+// noise_step_stride: elements between consecutive steps of the noise stack (0 -> n; larger when z is a sub-batch).
 int sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef,
-                   const int* step, int64_t n, cudaStream_t st);
+                   const int* step, int64_t n, int64_t noise_step_stride, cudaStream_t st);
 // *step += 1 (one thread): closes one iteration of the device-resident sampling loop.
 int advance_step(int* step, cudaStream_t st);
 

@@ -10,11 +10,12 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
                                                              const float* __restrict__ noise,
                                                              const float* __restrict__ guide,
                                                              const float* __restrict__ coef,
-                                                             const int* __restrict__ step, int64_t n4) {
+                                                             const int* __restrict__ step, int64_t n4,
+                                                             int64_t noise_step_stride) {
     if (step) {
         const int k = *step;
         coef += (size_t)k * 8;
-        if (noise) noise += (size_t)k * n4 * 4;
+        if (noise) noise += (size_t)k * noise_step_stride;
     }
     const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], c4 = coef[4], c5 = coef[5], c6 = coef[6];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -49,13 +50,14 @@ int advance_step(int* step, cudaStream_t st) {
 }
 
 int sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef,
-                   const int* step, int64_t n, cudaStream_t st) {
+                   const int* step, int64_t n, int64_t noise_step_stride, cudaStream_t st) {
     PD_CHECK(n % 4 == 0, PD_ERR_SHAPE, "sampler_update: n must be a multiple of 4");
     const int64_t n4 = n / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
-    sampler_update_kernel<<<blocks, 256, 0, st>>>(z, eps, noise, guide, coef, step, n4);
+    sampler_update_kernel<<<blocks, 256, 0, st>>>(z, eps, noise, guide, coef, step, n4,
+                                                  noise_step_stride ? noise_step_stride : n);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -40,6 +40,11 @@ Sampler::Sampler(int num_timesteps, double linear_start, double linear_end) : T(
 
 Sampler::~Sampler() {
     drop_graph();
+    for (int i = 0; i < kMaxSub; ++i) {
+        if (sub_stream_[i]) cudaStreamDestroy(sub_stream_[i]);
+        if (ev_sub_[i]) cudaEventDestroy(ev_sub_[i]);
+    }
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_in_) cudaEventDestroy(ev_in_);
     if (ev_out_) cudaEventDestroy(ev_out_);
     if (loop_stream_) cudaStreamDestroy(loop_stream_);
@@ -146,11 +151,44 @@ int Sampler::upload_tables(const std::vector<float>& rows, const std::vector<int
     return PD_OK;
 }
 
+int Sampler::n_sub_for(int B) const {
+    int n = 2;
+    if (const char* e = getenv("PD_SUB_BATCHES")) n = atoi(e);
+    if (n < 1) n = 1;
+    if (n > kMaxSub) n = kMaxSub;
+    while (n > 1 && B % n != 0) --n;
+    return n;
+}
+
 int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st) {
-    const int64_t n = (int64_t)B * unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    const int64_t per = (int64_t)unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    const int64_t per_c = (int64_t)unet->cfg.t_in * unet->cfg.h * unet->cfg.w * unet->cfg.c;
     const int* step = step_dev_.as<int>();
-    PD_TRY(unet->forward(z, t_dev_.as<int64_t>(), step, cond, eps_dev_.as<float>(), B, st));
-    PD_TRY(sampler_update(z, eps_dev_.as<float>(), noise, nullptr, coef_dev_.as<float>(), step, n, st));
+    const int ns = n_sub_for(B);
+    if (ns == 1) {
+        PD_TRY(unet->forward(z, t_dev_.as<int64_t>(), step, cond, eps_dev_.as<float>(), B, st));
+        PD_TRY(sampler_update(z, eps_dev_.as<float>(), noise, nullptr, coef_dev_.as<float>(), step, B * per, 0, st));
+        return advance_step(step_dev_.as<int>(), st);
+    }
+    const int Bs = B / ns;
+    if (!ev_fork_) PD_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    PD_CUDA(cudaEventRecord(ev_fork_, st));
+    for (int i = 0; i < ns; ++i) {
+        if (!sub_stream_[i]) {
+            PD_CUDA(cudaStreamCreateWithFlags(&sub_stream_[i], cudaStreamNonBlocking));
+            PD_CUDA(cudaEventCreateWithFlags(&ev_sub_[i], cudaEventDisableTiming));
+        }
+        cudaStream_t ss = sub_stream_[i];
+        PD_CUDA(cudaStreamWaitEvent(ss, ev_fork_, 0));
+        float* zi = z + (int64_t)i * Bs * per;
+        float* ei = eps_dev_.as<float>() + (int64_t)i * Bs * per;
+        PD_TRY(unet->forward(zi, t_dev_.as<int64_t>() + (int64_t)i * Bs, step, cond + (int64_t)i * Bs * per_c, ei, Bs, ss,
+                             nullptr, i, B));
+        PD_TRY(sampler_update(zi, ei, noise ? noise + (int64_t)i * Bs * per : nullptr, nullptr, coef_dev_.as<float>(),
+                              step, Bs * per, B * per, ss));
+        PD_CUDA(cudaEventRecord(ev_sub_[i], ss));
+        PD_CUDA(cudaStreamWaitEvent(st, ev_sub_[i], 0));
+    }
     return advance_step(step_dev_.as<int>(), st);
 }
 

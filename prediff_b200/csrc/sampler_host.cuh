@@ -20,6 +20,8 @@ public:
     int step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st);
 
     int T;
+    // number of concurrent sub-batches a batch of B is cut into (env PD_SUB_BATCHES, default 2, must divide B)
+    int n_sub_for(int B) const;
 
 private:
     int enter(cudaStream_t user);
@@ -35,6 +37,11 @@ private:
     DevMem coef_dev_, t_dev_, step_dev_, eps_dev_;
     // cached one-iteration graph
     cudaGraphExec_t graph_exec_ = nullptr;
+    // sub-batch concurrency: the batch is cut into n_sub independent slices (samples never interact) that run the
+    // same launch sequence on parallel streams, so one slice's prologue / epilogue bubbles are filled by another's work
+    static constexpr int kMaxSub = 4;
+    cudaStream_t sub_stream_[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork_ = nullptr, ev_sub_[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t loop_stream_ = nullptr;
     cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
     struct Key {

@@ -531,14 +531,14 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     return PD_OK;
 }
 
-int UNet::get_plan(int B, BatchPlan** out) {
+int UNet::get_plan(int B, BatchPlan** out, int replica) {
     PD_CHECK(finalized, PD_ERR_STATE, "unet: call pd_unet_finalize() after loading all weights");
     PD_CHECK(B >= 1 && B <= cfg.max_batch, PD_ERR_SHAPE, "unet: batch %d outside [1, max_batch=%d]", B, cfg.max_batch);
-    auto it = plans.find(B);
+    auto it = plans.find({B, replica});
     if (it == plans.end()) {
         std::unique_ptr<BatchPlan> bp(new BatchPlan());
         PD_TRY(build_plan(B, bp.get()));
-        it = plans.emplace(B, std::move(bp)).first;
+        it = plans.emplace(std::make_pair(B, replica), std::move(bp)).first;
     }
     *out = it->second.get();
     return PD_OK;
@@ -546,15 +546,15 @@ int UNet::get_plan(int B, BatchPlan** out) {
 
 // t may point at a table indexed by a device-side step counter (sampler loop): t_table[*step * B + b].
 int UNet::forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B,
-                  cudaStream_t st, PlanProfile* prof) {
+                  cudaStream_t st, PlanProfile* prof, int replica, int t_stride) {
     PD_CHECK(x && t && cond && out, PD_ERR_ARG, "unet forward: null pointer");
     BatchPlan* bp = nullptr;
-    PD_TRY(get_plan(B, &bp));
+    PD_TRY(get_plan(B, &bp, replica));
     const Bufs& b = bp->bufs_storage();
     {
         float* e0 = b.e0;
         const int c0 = C0;
-        bp->plan.steps[bp->t_slot] = [=](cudaStream_t s) { return timestep_embedding(t, step, e0, B, c0, s); };
+        bp->plan.steps[bp->t_slot] = [=](cudaStream_t s) { return timestep_embedding(t, step, t_stride, e0, B, c0, s); };
     }
     const int Tx = cfg.t_out, Tc = cfg.t_in, HW = cfg.h * cfg.w, C = cfg.c;
     float* xf = b.xin_f32;

@@ -31,10 +31,12 @@ public:
     int validate() const;
     int finalize();
     // t: device int64; if `step` (device int) is given, t is a table and row *step is used (sampler loop)
+    // replica: independent workspace index (sub-batches of one call running concurrently on different streams);
+    // t_stride: row length of the t table when `step` is given (0 -> B)
     int forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B, cudaStream_t st,
-                PlanProfile* prof = nullptr);
+                PlanProfile* prof = nullptr, int replica = 0, int t_stride = 0);
     int kernels_per_forward(int B, int* n);
-    int get_plan(int B, BatchPlan** out);
+    int get_plan(int B, BatchPlan** out, int replica = 0);
 
     pd_unet_config cfg;
     int C0, C1, T, TE;
@@ -61,7 +63,7 @@ private:
     void carve(A& ar, int B, Bufs* b) const;
 
     std::vector<std::unique_ptr<DevMem>> packed;
-    std::map<int, std::unique_ptr<BatchPlan>> plans;
+    std::map<std::pair<int, int>, std::unique_ptr<BatchPlan>> plans;  // (batch, replica)
     ResW first{}, down_res[2]{}, up_res[2]{};
     std::vector<StackW> down_stack[2], up_stack[2];
     bf16 *first_skip_w = nullptr, *pm_w = nullptr, *up_w = nullptr, *final_w = nullptr;
