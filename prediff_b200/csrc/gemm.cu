@@ -379,6 +379,194 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #undef PD_STAMP
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for the multi-wave, bf16-output GEMMs (QKV, FFN-1: K <= 512, several tiles per SM): one CTA per
+// SM walks tiles m-major; the accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
+// (8 warps: TMEM -> +bias -> GELU -> bf16 -> swizzled slab -> TMA store) runs under the TMA loads + MMAs of tile i+1,
+// and barrier setup / TMEM allocation / first-tile latency are paid once per SM instead of once per tile.
+constexpr int kPersBN = 256;
+constexpr int kPersStages = 3;
+struct PersCfg {
+    static constexpr int kStageBytes = kABytes + kPersBN * kGemmBlockK * 2;   // 48 KB
+    static constexpr int kPipeBytes = kPersStages * kStageBytes;              // 144 KB
+    static constexpr int kSlabBytes = kEpiWarps * 2 * 4096;                   // 64 KB, NOT aliased (pipeline stays live)
+    static constexpr int kBarBytes = 256;
+    static constexpr int kSmem = kPipeBytes + kSlabBytes + 1024 + kBarBytes + 2 * kPersBN * 4;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ GemmKernelParams p,
+                          int n_tiles_n, int total_tiles) {
+    constexpr int BN = kPersBN, STAGES = kPersStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* slab_base = smem + PersCfg::kPipeBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(slab_base + PersCfg::kSlabBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* vec_s = reinterpret_cast<float*>(slab_base + PersCfg::kSlabBytes + PersCfg::kBarBytes);  // [2][BN]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k = p.ntaps * p.cblks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&acc_full[a], 1);
+            ptx::mbar_init(&acc_empty[a], kEpiWarps);
+        }
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_out);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;  // running k-block counter across tiles: stage = it % STAGES
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / n_tiles_n;
+                const int n0 = (tile - m_tile * n_tiles_n) * BN;
+                const int sample = m_tile / p.tiles_per_sample;
+                const int p0 = (m_tile - sample * p.tiles_per_sample) * kGemmBlockM;
+                const int z0 = p0 / p.HW;
+                const int rem = p0 - z0 * p.HW;
+                const int y0 = rem / p.W;
+                const int x0 = rem - y0 * p.W;
+                const int bz = p.b_batched ? sample : 0;
+                int tap = 0, cb = 0;
+                for (int k = 0; k < num_k; ++k, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * PersCfg::kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], PersCfg::kStageBytes);
+                    ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
+                                     z0 + p.dz[tap], sample);
+                    ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * kGemmBlockK, n0, bz);
+                    if (++cb == p.cblks) { cb = 0; ++tap; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kGemmBlockM, BN);
+            int it = 0, li = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+                const int acc = li & 1;
+                ptx::mbar_wait(&acc_empty[acc], ((li >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int k = 0; k < num_k; ++k, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + s * PersCfg::kStageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int kk = 0; kk < kGemmBlockK / 16; ++kk) {
+                        const uint64_t da = ptx::make_smem_desc_sw128(a_addr + kk * 32);
+                        const uint64_t db = ptx::make_smem_desc_sw128(b_addr + kk * 32);
+                        ptx::umma_f16(tmem_d, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);
+                }
+                ptx::umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        const int e = warp - 2;
+        const int q = warp & 3;
+        const int half = e >> 2;
+        const int et = threadIdx.x - 64;
+        uint8_t* slab0 = slab_base + e * 8192;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        const int act = p.act;
+        constexpr int kChunks = BN / 64, kPerHalf = kChunks / 2;   // 2 chunks of 64 bf16 columns per warp
+        int li = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+            const int acc = li & 1;
+            const int m_tile = tile / n_tiles_n;
+            const int n0 = (tile - m_tile * n_tiles_n) * BN;
+            const int sample = m_tile / p.tiles_per_sample;
+            const int p0 = (m_tile - sample * p.tiles_per_sample) * kGemmBlockM;
+            const int row0 = p0 + q * 32;
+            float* vs = vec_s + acc * BN;
+            // bias (+ per-sample row vector) for this tile's columns; the other buffer may still be in use by slower warps
+            {
+                float v = p.bias ? __ldg(p.bias + n0 + et) : 0.f;
+                if (p.rowvec) v += __ldg(p.rowvec + (size_t)sample * p.rowvec_ld + n0 + et);
+                vs[et] = v;   // 256 epilogue threads == BN columns
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            if (lane == 0) ptx::bulk_wait_read<0>();   // my slabs: the previous tile's stores have been read out
+            __syncwarp();
+            ptx::mbar_wait(&acc_full[acc], (li >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t t_lane = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c = half * kPerHalf, idx = 0; c < (half + 1) * kPerHalf; ++c, ++idx) {
+                uint8_t* my_row = slab0 + idx * 4096 + lane * 128;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_lane + c * 64 + hh * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float a[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            a[k] = __uint_as_float(v[8 * i + k]) + vs[c * 64 + hh * 32 + 8 * i + k];
+                            if (act == ACT_GELU) a[k] = gelu_fast(a[k]);
+                            else if (act == ACT_SILU) a[k] = silu_f(a[k]);
+                        }
+                        const uint32_t cellidx = static_cast<uint32_t>(hh * 4 + i) ^ sw;
+                        *reinterpret_cast<uint4*>(my_row + (cellidx << 4)) =
+                            make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
+                                       pack_bf16x2(a[6], a[7]));
+                    }
+                }
+                if (idx == kPerHalf - 1) {   // all TMEM reads of this tile are done: hand the accumulator back
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_3d(&tmap_out, slab0 + idx * 4096, n0 + c * 64, row0, sample);
+                    ptx::bulk_commit();
+                }
+            }
+        }
+        if (lane == 0) ptx::bulk_wait_read<0>();
+        __syncwarp();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 bool g_inited = false;
 
@@ -386,6 +574,15 @@ template <int BN, int STAGES>
 int set_smem_attr() {
     PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg<BN, STAGES>::kSmem));
+    return PD_OK;
+}
+
+int launch_persistent(const GemmOp& op, cudaStream_t stream) {
+    const int total = (int)(op.grid_x * op.grid_y);
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    gemm_tc_persistent_kernel<<<grid, kThreads, PersCfg::kSmem, stream>>>(op.tmap_a, op.tmap_b, op.tmap_out, op.p,
+                                                                         (int)op.grid_y, total);
+    PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
@@ -419,6 +616,7 @@ int gemm_init() {
     PD_TRY((set_smem_attr<128, 3>()));
     PD_TRY((set_smem_attr<256, 2>()));
     PD_TRY((set_smem_attr<256, 4>()));
+    PD_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PersCfg::kSmem));
     g_inited = true;
     return PD_OK;
 }
@@ -578,6 +776,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(ln) failed: %d", (int)r);
     }
     p.split_flags = e.split_flags;
+    // multi-wave bf16-output GEMMs (QKV, FFN-1) take the persistent kernel: epilogue under the next tile's mainloop
+    op->persistent = (e.out_bf16 && bn == 256 && (int64_t)m_tiles * (N / bn) > kNumSMs && getenv("PD_NO_PERSISTENT") == nullptr) ? 1 : 0;
     op->grid_x = (unsigned)m_tiles;
     op->grid_y = (unsigned)(N / bn);
     op->flops = 2.0 * (double)rows_per_sample * g.samples * (double)N * (double)g.ntaps * g.C;
@@ -608,6 +808,7 @@ int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* re
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
+    if (op.persistent) return launch_persistent(op, stream);
     switch (op.block_n) {
         case 32: return launch_cfg<32, 4>(op, stream);
         case 64: return launch_cfg<64, 4>(op, stream);

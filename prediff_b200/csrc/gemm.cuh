@@ -110,7 +110,7 @@ struct GemmOp {
     CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_ln;
     GemmKernelParams p;
     int ldo = 0, out_rows = 0, out_samples = 0, out_N = 0;
-    int block_n = 0, stages = 0, split_k = 1;
+    int block_n = 0, stages = 0, split_k = 1, persistent = 0;
     unsigned grid_x = 0, grid_y = 0;
     size_t smem = 0;
     double flops = 0;

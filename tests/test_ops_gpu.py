@@ -66,6 +66,24 @@ def test_gemm_linear(M, K, N, bn):
         assert rel_err(outb, F.gelu(a.float() @ w.float().t() + bias)) < 1e-2
 
 
+@pytest.mark.parametrize("M,K,N,act", [(13312, 256, 768, 0), (13312, 256, 1024, 1), (6656, 512, 2048, 1),
+                                         (6600, 256, 1024, 1)])
+def test_gemm_persistent_bf16(M, K, N, act):
+    """Multi-wave bf16-output GEMMs (> 148 tiles of 128 x 256) run the persistent double-buffered-TMEM kernel."""
+    a = _randn(M, K, seed=1).bfloat16()
+    w = _randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
+    bias = _randn(N, seed=3)
+    outb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(a), L.ptr(w), 1, 1, 1, M, K, 1, 1, 1, N, L.ptr(bias), None, None, None,
+                                        L.ptr(outb), act, 0, L.stream_ptr()))
+    ref = a.float() @ w.float().t() + bias
+    if act:
+        ref = F.gelu(ref)
+    assert rel_err(outb, ref) < 1e-2
+    # exactness of the accumulation itself: compare against the bf16 rounding of the fp32 reference
+    assert (outb.float() - ref.bfloat16().float()).abs().max().item() <= 2 * ref.abs().max().item() * 2 ** -8
+
+
 @pytest.mark.parametrize("M,K", [(3328, 256), (1000, 1024), (13312, 256)])
 def test_gemm_residual_fused_layernorm(M, K):
     N = 256
