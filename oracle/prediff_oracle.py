@@ -308,5 +308,60 @@ def sample_loop_ddim(sd, cfg, sched, z, cond, n_steps, eta=0.0, noise=None):
     return z
 
 
+# ----------------------------------------------------------------------------------------------- knowledge alignment
+
+
+def ka_forward(sd, cfg, x, t):
+    """NoisyCuboidTransformerEncoder.forward (src/prediff/diffusion/knowledge_alignment/models.py:459-528) with
+    pool="attention", readout_seq=True, out_len=T: x (B,T,H,W,C), t (B,) -> (B,T,1)."""
+    heads = cfg.num_heads
+    u0, u1 = cfg.units
+    B, T = x.shape[0], x.shape[1]
+    h = _res_block3d(sd, "first_proj", x.permute(0, 4, 1, 2, 3), None, _gn_groups(cfg.c), _gn_groups(u0)).permute(0, 2, 3, 4, 1)
+    _, _, H, W, C = h.shape
+    h = h + sd["pos_embed.T_embed.weight"].reshape(T, 1, 1, C) + sd["pos_embed.H_embed.weight"].reshape(1, H, 1, C) \
+        + sd["pos_embed.W_embed.weight"].reshape(1, 1, W, C)
+    e = timestep_embedding(t, u0)
+    e = F.linear(e, sd["time_embed.layer.0.weight"], sd["time_embed.layer.0.bias"])
+    t_emb = F.linear(F.silu(e), sd["time_embed.layer.2.weight"], sd["time_embed.layer.2.bias"])
+    for lvl in range(2):
+        if lvl > 0:
+            h = patch_merge(sd, "downsample_layers.0", h)
+        g = _gn_groups(cfg.units[lvl])
+        for d in range(cfg.depth[lvl]):
+            h = _res_block3d(sd, f"down_time_embed_blocks.{lvl}", h.permute(0, 4, 1, 2, 3), t_emb, g, g).permute(0, 2, 3, 4, 1)
+            h = stack_block(sd, f"down_self_blocks.{lvl}.{d}", h, heads)
+    # read-out per frame: GroupNorm(32) + SiLU + AttentionPool3d (models.py:49-104), token 0 of the pooled sequence
+    o = h.permute(0, 1, 4, 2, 3).reshape(B * T, u1, -1)                       # (b t) c (h w)
+    o = F.silu(F.group_norm(o, min(u1, 32), sd["out.0.weight"], sd["out.0.bias"], 1e-5))
+    o = torch.cat([o.mean(dim=-1, keepdim=True), o], dim=-1) + sd["out.2.positional_embedding"][None]
+    qkv = F.conv1d(o, sd["out.2.qkv_proj.weight"], sd["out.2.qkv_proj.bias"])  # (bt, 3c, L)
+    bs, width, L = qkv.shape
+    ch = width // (3 * heads)
+    q, k, v = qkv.chunk(3, dim=1)
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    wgt = torch.einsum("bct,bcs->bts", (q * scale).reshape(bs * heads, ch, L), (k * scale).reshape(bs * heads, ch, L))
+    wgt = torch.softmax(wgt, dim=-1)
+    a = torch.einsum("bts,bcs->bct", wgt, v.reshape(bs * heads, ch, L)).reshape(bs, -1, L)
+    out = F.conv1d(a, sd["out.2.c_proj.weight"], sd["out.2.c_proj.bias"])[:, :, 0]
+    return out.reshape(B, T, -1)
+
+
+def ka_alignment_value(sd, cfg, zt, t, avg_x_gt):
+    """SEVIRAvgIntensityAlignment.alignment_fn (knowledge_alignment/sevir.py:55-83): || mean_T U(zt,t) - target ||_2
+    with the norm taken over the whole (B,1) tensor."""
+    pred = ka_forward(sd, cfg, zt, t).mean(dim=1)
+    return torch.linalg.vector_norm(pred - avg_x_gt, ord=2)
+
+
+def ka_mean_shift(sd, cfg, zt, t, avg_x_gt, guide_scale=50.0):
+    """get_mean_shift (sevir.py:85-104) = guide_scale * d alignment_fn / d zt (alignment_pl.py:423-446)."""
+    with torch.enable_grad():
+        z = zt.detach().clone().requires_grad_(True)
+        val = ka_alignment_value(sd, cfg, z, t, avg_x_gt)
+        grad = torch.autograd.grad(val.sum(), z)[0]
+    return guide_scale * grad
+
+
 def to_torch_sd(np_sd):
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in np_sd.items()}

@@ -54,6 +54,31 @@ class VAEConfig:
     w: int = 128
 
 
+@dataclass
+class KAConfig:
+    """cfg.yaml `model.align.model_args`: NoisyCuboidTransformerEncoder (knowledge-alignment network U(z_t, t))."""
+    t: int = 6
+    h: int = 16
+    w: int = 16
+    c: int = 64
+    base_units: int = 128
+    depth: Tuple[int, int] = (1, 1)
+    num_heads: int = 4
+    guide_scale: float = 50.0
+
+    @property
+    def units(self):
+        return (self.base_units, 2 * self.base_units)
+
+    @property
+    def temb_channels(self):
+        return 4 * self.base_units
+
+    def cuboids(self, level):
+        h, w = self.h >> level, self.w >> level
+        return [(self.t, 1, 1), (1, h, 1), (1, 1, w)]
+
+
 TINY_UNET = UNetConfig(base_units=64, depth=(1, 1))
 TINY_VAE = VAEConfig(latent_channels=64, block_out_channels=(64, 64, 128, 128), layers_per_block=1, h=128, w=128)
 
@@ -169,12 +194,39 @@ def vae_param_spec(cfg: VAEConfig) -> Spec:
     return s
 
 
+def ka_param_spec(cfg: KAConfig) -> Spec:
+    """Parameter names/shapes of the reference NoisyCuboidTransformerEncoder.state_dict()
+    (src/prediff/diffusion/knowledge_alignment/models.py), minus the derived int64 buffers."""
+    u0, u1 = cfg.units
+    te = cfg.temb_channels
+    s: Spec = []
+    s += _resblock3d("first_proj", cfg.c, u0, 0)
+    s += [("pos_embed.T_embed.weight", (cfg.t, u0)), ("pos_embed.H_embed.weight", (cfg.h, u0)),
+          ("pos_embed.W_embed.weight", (cfg.w, u0))]
+    s += [("time_embed.layer.0.weight", (te, u0)), ("time_embed.layer.0.bias", (te,)),
+          ("time_embed.layer.2.weight", (te, te)), ("time_embed.layer.2.bias", (te,))]
+    s += [("downsample_layers.0.reduction.weight", (u1, 4 * u0)), ("downsample_layers.0.norm.weight", (4 * u0,)),
+          ("downsample_layers.0.norm.bias", (4 * u0,))]
+    for lvl, dim in enumerate((u0, u1)):
+        for d in range(cfg.depth[lvl]):
+            s += _stack_block(f"down_self_blocks.{lvl}.{d}", dim, cfg.num_heads, cfg.cuboids(lvl))
+    for lvl, dim in enumerate((u0, u1)):
+        s += _resblock3d(f"down_time_embed_blocks.{lvl}", dim, dim, te)
+    tokens = (cfg.h // 2) * (cfg.w // 2) + 1
+    s += [("out.0.weight", (u1,)), ("out.0.bias", (u1,)), ("out.2.positional_embedding", (u1, tokens)),
+          ("out.2.qkv_proj.weight", (3 * u1, u1, 1)), ("out.2.qkv_proj.bias", (3 * u1,)),
+          ("out.2.c_proj.weight", (1, u1, 1)), ("out.2.c_proj.bias", (1,))]
+    return s
+
+
 def _is_norm_weight(name: str) -> bool:
     parts = name.split(".")
     if parts[-1] != "weight":
         return False
     owner = parts[-2]
     if owner in ("norm", "layer_norm", "norm1", "norm2", "group_norm", "conv_norm_out"):
+        return True
+    if name == "out.0.weight":  # GroupNorm of the knowledge-alignment read-out head
         return True
     # GroupNorm inside the nn.Sequential of TimeEmbedResBlock: in_layers.0 / out_layers.0
     return len(parts) >= 3 and parts[-3] in ("in_layers", "out_layers") and owner == "0"
@@ -194,6 +246,8 @@ def seeded_state_dict(spec: Spec, seed: int, gain: float = 1.0) -> Dict[str, np.
             x = 0.3 * x
         elif "embed.weight" in name and name.startswith("pos_embed"):
             x = 0.1 * x
+        elif name.endswith("positional_embedding"):
+            x = x * np.float32(shape[0] ** -0.5)
         else:
             fan_in = int(np.prod(shape[1:]))
             x = x * np.float32(gain / np.sqrt(fan_in))

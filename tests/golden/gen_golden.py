@@ -25,7 +25,7 @@ REF = os.environ.get("PREDIFF_REFERENCE", "/root/reference")
 
 from prediff_b200 import weights as Wt  # noqa: E402
 
-UNET_SEED, VAE_SEED = 1001, 2002
+UNET_SEED, VAE_SEED, KA_SEED = 1001, 2002, 3003
 
 
 def inp(seed, *shape, uniform=False):
@@ -111,6 +111,62 @@ def ref_ldm(unet, vae, ucfg, vcfg):
         linear_end=2e-2, parameterization="eps", learn_logvar=False,
         latent_shape=(ucfg.t_out, ucfg.h, ucfg.w, ucfg.c), first_stage_model=vae,
         cond_stage_model="__is_first_stage__", scale_factor=1.0).eval()
+
+
+def ref_ka(cfg):
+    from prediff.diffusion.knowledge_alignment.sevir import SEVIRAvgIntensityAlignment
+    # model_args as in scripts/prediff/sevirlr/cfg.yaml:105-156
+    args = dict(input_shape=[cfg.t, cfg.h, cfg.w, cfg.c], out_channels=1, base_units=cfg.base_units, scale_alpha=1.0,
+                depth=list(cfg.depth), downsample=2, downsample_type="patch_merge", block_attn_patterns="axial",
+                num_heads=cfg.num_heads, attn_drop=0.1, proj_drop=0.1, ffn_drop=0.1, ffn_activation="gelu", gated_ffn=False,
+                norm_layer="layer_norm", use_inter_ffn=True, hierarchical_pos_embed=False, pos_embed_type="t+h+w",
+                padding_type="zeros", checkpoint_level=0, use_relative_pos=True, self_attn_use_final_proj=True,
+                num_global_vectors=0, use_global_vector_ffn=True, use_global_self_attn=False, separate_global_qkv=False,
+                global_dim_ratio=1, time_embed_channels_mult=4, time_embed_use_scale_shift_norm=False,
+                time_embed_dropout=0.0, pool="attention", readout_seq=True, out_len=cfg.t)
+    al = SEVIRAvgIntensityAlignment(alignment_type="avg_x", guide_scale=cfg.guide_scale, model_type="cuboid",
+                                    model_args=args, model_ckpt_path=None)
+    sd = Wt.seeded_state_dict(Wt.ka_param_spec(cfg), KA_SEED)
+    res = al.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.endswith("relative_position_index") for k in res.missing_keys), res.missing_keys
+    ref_keys = {k: tuple(v.shape) for k, v in al.model.state_dict().items() if not k.endswith("relative_position_index")}
+    assert ref_keys == {k: tuple(v.shape) for k, v in sd.items()}, set(ref_keys) ^ set(sd)
+    assert list(ref_keys) == [k for k, _ in Wt.ka_param_spec(cfg)]
+    al.model.eval()
+    return al
+
+
+def gen_ka():
+    """U(z_t, t) and the guidance g = guide_scale * grad || mean_T U - avg_x_gt ||_2 of the reference
+    (SEVIRAvgIntensityAlignment.get_mean_shift), plus one aligned DDPM step of the reference LatentDiffusion."""
+    import prediff.diffusion.latent_diffusion as LD
+    cfg = Wt.KAConfig()
+    al = ref_ka(cfg)
+    B = 4
+    zt = inp(5151, B, cfg.t, cfg.h, cfg.w, cfg.c)
+    t = torch.tensor([981, 500, 20, 0], dtype=torch.long)
+    target = torch.full((B, 1), 0.3)
+    with torch.no_grad():
+        pred = al.model(zt, t)
+    g = al.get_mean_shift(zt, t, avg_x_gt=target)
+    print(f"ka: pred std {pred.std():.4f}, grad absmax {g.abs().max():.4e}")
+    # aligned p_sample of the reference LatentDiffusion (tiny UNet) with the full KA network
+    ucfg = Wt.TINY_UNET
+    ldm = ref_ldm(ref_unet(ucfg), ref_vae(Wt.TINY_VAE), ucfg, Wt.TINY_VAE)
+    ldm.set_alignment(al.get_mean_shift)
+    zT = inp(777, 2, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    cond = inp(778, 2, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    noise = inp(779, 4, 2, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    orig = LD.noise_like
+    LD.noise_like = lambda shape, device: noise[0].clone()
+    try:
+        ts = torch.full((2,), 900, dtype=torch.long)
+        z_al = ldm.p_sample(zt=zT.clone(), zc=cond, t=ts, use_alignment=True,
+                            alignment_kwargs={"avg_x_gt": torch.full((2, 1), 0.3)})
+    finally:
+        LD.noise_like = orig
+    save("ka_full", t=t, pred=pred, grad=g, z_aligned_step900=z_al)
 
 
 def save(name, **arrs):
@@ -248,5 +304,7 @@ if __name__ == "__main__":
         gen_unet("full", FULL_U, 1, [500])
     if "vae_full" in todo:
         gen_vae("full", FULL_V, 1)
+    if "ka" in todo:
+        gen_ka()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

@@ -149,3 +149,31 @@ def test_vae_full_vs_reference():
         dec = O.vae_decode(sd, cfg, mom[:, :cfg.latent_channels])
     assert maxrel(mom, g["moments"]) < 5e-5
     assert maxrel(dec, g["dec"]) < 5e-5
+
+
+def test_knowledge_alignment_vs_reference(tiny_unet_sd):
+    """U(z_t, t), the guidance gradient (get_mean_shift) and one aligned DDPM step vs the reference's own."""
+    from tests.golden.gen_golden import KA_SEED
+    cfg = Wt.KAConfig()
+    sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.ka_param_spec(cfg), KA_SEED))
+    g = gold("ka_full")
+    zt = inp(5151, 4, cfg.t, cfg.h, cfg.w, cfg.c)
+    t = torch.as_tensor(g["t"])
+    target = torch.full((4, 1), 0.3)
+    with torch.no_grad():
+        pred = O.ka_forward(sd, cfg, zt, t)
+    assert maxrel(pred, g["pred"]) < 5e-5
+    grad = O.ka_mean_shift(sd, cfg, zt, t, target, cfg.guide_scale)
+    assert maxrel(grad, g["grad"]) < 2e-4
+    # aligned p_sample (latent_diffusion.py:592-631) with the tiny UNet
+    ucfg = Wt.TINY_UNET
+    sched = O.make_schedule()
+    zT = inp(777, 2, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    cond = inp(778, 2, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    noise = inp(779, 4, 2, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    ts = torch.full((2,), 900)
+    with torch.no_grad():
+        eps = O.unet_forward(tiny_unet_sd, ucfg, zT, ts, cond)
+    guide = O.ka_mean_shift(sd, cfg, zT, ts, torch.full((2, 1), 0.3), cfg.guide_scale)
+    z = O.p_sample_ddpm(sched, eps, zT, 900, noise[0], guide=guide)
+    assert maxrel(z, g["z_aligned_step900"]) < 5e-5
