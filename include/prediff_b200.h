@@ -93,6 +93,36 @@ int pd_vae_encode(pd_vae* m, const float* x, float* moments, int n, void* stream
 /* decode: z [N][H/8][W/8][latent] -> [N][H][W], i.e. Decoder(post_quant_conv(z)). */
 int pd_vae_decode(pd_vae* m, const float* z, float* out, int n, void* stream);
 
+/* ---- knowledge-alignment network (reference: src/prediff/diffusion/knowledge_alignment/models.py:459-528
+ *      NoisyCuboidTransformerEncoder; sevir.py:55-104 SEVIRAvgIntensityAlignment; alignment_pl.py:423-446) -------- */
+typedef struct pd_ka pd_ka;
+typedef struct pd_ka_config {
+    int32_t t;             /* input_shape[0] = number of target frames      (cfg.yaml:105-156: 6)                 */
+    int32_t h, w, c;       /* latent H, W, C                                 (16, 16, 64)                          */
+    int32_t base_units;    /* 128; level-1 width is 2*base_units                                                   */
+    int32_t depth[2];      /* [1, 1]                                                                               */
+    int32_t num_heads;     /* 4                                                                                    */
+    int32_t max_batch;
+} pd_ka_config;
+
+int pd_ka_create(const pd_ka_config* cfg, pd_ka** out);
+void pd_ka_destroy(pd_ka* m);
+int pd_ka_num_weights(const pd_ka* m);
+int pd_ka_weight_info(const pd_ka* m, int i, const char** name, int64_t shape[5]);
+int pd_ka_load_weight(pd_ka* m, const char* name, const float* data, const int64_t* shape, int ndim);
+int pd_ka_finalize(pd_ka* m);
+/* forward(zt, t) -> pred [B][t]  (models.py:459-528 with pool="attention", readout_seq=True; the reference returns
+ * (B, t, 1)). zt [B][t][h][w][c] fp32, t [B] int64; device pointers. */
+int pd_ka_forward(pd_ka* m, const float* zt, const int64_t* t, float* pred, int batch, void* stream);
+/* get_mean_shift (sevir.py:85-104): grad [B][t][h][w][c] = guide_scale * d || mean_T U(zt, t) - avg_x_gt ||_2 / d zt,
+ * the L2 norm taken over the whole batch (sevir.py:82). avg_x_gt: device fp32 [B]. Forward + hand-written
+ * input-gradient backward on the device (replaces torch.autograd.grad, alignment_pl.py:441-445).
+ * loss_out: optional device float receiving the alignment value. */
+int pd_ka_mean_shift(pd_ka* m, const float* zt, const int64_t* t, const float* avg_x_gt, float guide_scale, float* grad,
+                     float* loss_out, int batch, void* stream);
+/* kernel launches of one forward / one backward at this batch size */
+int pd_ka_kernels(pd_ka* m, int batch, int* n_forward, int* n_backward);
+
 /* ---- sampler (reference: latent_diffusion.py:228-278,553-684; diffusion/utils.py:17-70) -------------------- */
 typedef struct pd_sampler pd_sampler;
 #define PD_MODE_DDPM 0  /* the reference's ancestral p_sample_loop, t = timesteps-1 .. 0                        */
@@ -118,6 +148,13 @@ int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, co
  * (latent_diffusion.py:659-680) between device-resident stretches. */
 int pd_sample_loop_range(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch,
                          int mode, int n_steps, float eta, int k_begin, int k_end, void* stream);
+/* pd_sample_loop_range with knowledge-alignment guidance (latent_diffusion.py:592-596 aligned_mean for DDPM;
+ * SURVEY.md section 8 S6 for DDIM: eps_hat = eps + sqrt(1 - a_t) * g): every step also evaluates
+ * g = pd_ka_mean_shift(z_t, t, avg_x_gt, guide_scale) - concurrently with the UNet on a second stream - and the fused
+ * update subtracts coef * g. The whole iteration (UNet + KA forward/backward + update) is one CUDA-graph replay. */
+int pd_sample_loop_aligned(pd_sampler* s, pd_unet* unet, pd_ka* ka, float* z, const float* cond, const float* noise,
+                           const float* avg_x_gt, float guide_scale, int batch, int mode, int n_steps, float eta,
+                           int k_begin, int k_end, void* stream);
 /* Number of independent sub-batches (parallel streams) the loop cuts a batch into (env PD_SUB_BATCHES, default 2). */
 int pd_sampler_sub_batches(const pd_sampler* s, int batch);
 /* One reference p_sample step at integer timestep t (all batch rows share t): z <- p_sample(z, cond, t). */
@@ -162,6 +199,22 @@ int pd_op_parity_split_cast(const float* x, void* y_bf16, int F, int H, int W, i
 /* stride-2 3x3 conv with the reference's (0,1,0,1) zero pad (taming/resnet.py:183-188) on the parity-split input */
 int pd_op_conv_s2_gemm(const void* planes_bf16, const void* Wt_bf16, int F, int Ho, int Wo, int C, int N,
                        const float* bias, float* out_f32, void* stream);
+
+/* ---- input-gradient kernels of the knowledge-alignment guidance (csrc/backward.cu); used by the parity tests --- */
+/* GroupNorm(+SiLU) backward: x, dy fp32 [S][R][C] -> dx_io fp32 (+= if accumulate) and/or dx_bf16 (either may be NULL) */
+int pd_op_group_norm_bwd(const float* x, const float* dy, const float* gamma, const float* beta, float* dx_io,
+                         void* dx_bf16, int S, int R, int C, int G, float eps, int silu, int accumulate, void* stream);
+int pd_op_layer_norm_bwd(const float* x, const float* gamma, const float* dy, float* dx_io, void* dx_bf16, int P, int C,
+                         float eps, int accumulate, void* stream);
+int pd_op_patch_merge_ln_bwd(const float* x, const float* gamma, const float* dy, float* dx, void* dx_bf16, int BT, int H,
+                             int W, int C, float eps, void* stream);
+int pd_op_gelu(const float* pre, void* y_bf16, int64_t n, void* stream);
+int pd_op_gelu_bwd(const float* pre, const void* dy_bf16, void* dpre_bf16, int64_t n, void* stream);
+int pd_op_axial_attention_bwd(const void* qkv_bf16, const float* bias_table, const void* dout_bf16, void* dqkv_bf16, int B,
+                              int T, int H, int W, int C, int heads, int axis, void* stream);
+/* dgrad operands: fp32 [N][K] -> bf16 [K][N];  fp32 [Co][Ci][taps] -> bf16 [Ci][taps reversed][Co] */
+int pd_op_pack_linear_t(const float* w, void* out_bf16, int N, int K, void* stream);
+int pd_op_pack_conv_dgrad(const float* w, void* out_bf16, int Co, int Ci, int taps, void* stream);
 
 #ifdef __cplusplus
 }

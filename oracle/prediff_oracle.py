@@ -295,12 +295,16 @@ def ddim_coefficients(sched, n_steps, eta=0.0):
     return [(int(ts[i]), float(a[i]), float(a_prev[i]), float(sig[i])) for i in reversed(range(len(ts)))]
 
 
-def sample_loop_ddim(sd, cfg, sched, z, cond, n_steps, eta=0.0, noise=None):
+def sample_loop_ddim(sd, cfg, sched, z, cond, n_steps, eta=0.0, noise=None, guide_fn=None):
     """50-step DDIM (eta=0 deterministic): z0 = (z - sqrt(1-a_t) eps)/sqrt(a_t);
-    z <- sqrt(a_prev) z0 + sqrt(1 - a_prev - sigma^2) eps + sigma noise."""
+    z <- sqrt(a_prev) z0 + sqrt(1 - a_prev - sigma^2) eps + sigma noise.
+    guide_fn(z, t) -> g (knowledge alignment): eps_hat = eps + sqrt(1 - a_t) * g, i.e.
+    guided-diffusion's condition_score with the sign of the reference's aligned_mean (latent_diffusion.py:594-595)."""
     for k, (t, a_t, a_prev, sigma) in enumerate(ddim_coefficients(sched, n_steps, eta)):
         tt = torch.full((z.shape[0],), t, dtype=torch.long)
         eps = unet_forward(sd, cfg, z, tt, cond)
+        if guide_fn is not None:
+            eps = eps + math.sqrt(1.0 - a_t) * guide_fn(z, tt)
         z0 = (z - math.sqrt(1.0 - a_t) * eps) / math.sqrt(a_t)
         z = math.sqrt(a_prev) * z0 + math.sqrt(max(1.0 - a_prev - sigma ** 2, 0.0)) * eps
         if noise is not None and sigma > 0:

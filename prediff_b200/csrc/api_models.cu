@@ -1,6 +1,7 @@
 // extern "C" model-level entry points (include/prediff_b200.h): UNet, sampler. (VAE: api_vae.cu)
 #include "sampler_host.cuh"
 #include "unet.cuh"
+#include "ka_api.cuh"
 
 using namespace pd;
 
@@ -89,6 +90,16 @@ int pd_sample_loop_range(pd_sampler* s, pd_unet* unet, float* z, const float* co
                          int mode, int n_steps, float eta, int k_begin, int k_end, void* stream) {
     PD_CHECK(s && unet, PD_ERR_ARG, "pd_sample_loop_range: null handle");
     return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, k_begin, k_end, S(stream));
+}
+int pd_sample_loop_aligned(pd_sampler* s, pd_unet* unet, pd_ka* ka, float* z, const float* cond, const float* noise,
+                           const float* avg_x_gt, float guide_scale, int batch, int mode, int n_steps, float eta,
+                           int k_begin, int k_end, void* stream) {
+    PD_CHECK(s && unet && ka && avg_x_gt, PD_ERR_ARG, "pd_sample_loop_aligned: null argument");
+    Sampler::Align al;
+    al.ka = &ka->impl;
+    al.avg_x_gt = avg_x_gt;
+    al.guide_scale = guide_scale;
+    return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, k_begin, k_end, S(stream), al);
 }
 int pd_sampler_sub_batches(const pd_sampler* s, int batch) { return s ? s->impl.n_sub_for(batch) : 0; }
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,

@@ -146,4 +146,60 @@ int pd_op_parity_split_cast(const float* x, void* y, int F, int H, int W, int C,
     return parity_split_cast(x, static_cast<bf16*>(y), F, H, W, C, S(stream));
 }
 
+// ---- input-gradient kernels (backward.cu) ------------------------------------------------------------------
+int pd_op_group_norm_bwd(const float* x, const float* dy, const float* gamma, const float* beta, float* dx_io,
+                         void* dx_bf16, int Sn, int R, int C, int G, float eps, int silu, int accumulate, void* stream) {
+    PD_TRY(gemm_init());
+    double* sums = nullptr;
+    const size_t bytes = (size_t)Sn * G * 2 * sizeof(double);
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sums), 2 * bytes, S(stream)));
+    PD_CUDA(cudaMemsetAsync(sums, 0, 2 * bytes, S(stream)));
+    double* bsums = sums + (size_t)Sn * G * 2;
+    int rc = gn_stats(x, sums, Sn, R, C, G, S(stream));
+    if (rc == PD_OK)
+        rc = gn_bwd(x, dy, sums, bsums, gamma, beta, dx_io, static_cast<bf16*>(dx_bf16), Sn, R, C, G, eps, silu,
+                    accumulate, S(stream));
+    cudaFreeAsync(sums, S(stream));
+    return rc;
+}
+
+int pd_op_layer_norm_bwd(const float* x, const float* gamma, const float* dy, float* dx_io, void* dx_bf16, int P, int C,
+                         float eps, int accumulate, void* stream) {
+    PD_TRY(gemm_init());
+    return layer_norm_bwd(x, gamma, dy, dx_io, static_cast<bf16*>(dx_bf16), P, C, eps, accumulate, S(stream));
+}
+
+int pd_op_patch_merge_ln_bwd(const float* x, const float* gamma, const float* dy, float* dx, void* dx_bf16, int BT, int H,
+                             int W, int C, float eps, void* stream) {
+    PD_TRY(gemm_init());
+    return patch_merge_ln_bwd(x, gamma, dy, dx, static_cast<bf16*>(dx_bf16), BT, H, W, C, eps, S(stream));
+}
+
+int pd_op_gelu(const float* pre, void* y_bf16, int64_t n, void* stream) {
+    PD_TRY(gemm_init());
+    return gelu_fwd(pre, static_cast<bf16*>(y_bf16), n, S(stream));
+}
+
+int pd_op_gelu_bwd(const float* pre, const void* dy_bf16, void* dpre_bf16, int64_t n, void* stream) {
+    PD_TRY(gemm_init());
+    return gelu_bwd(pre, static_cast<const bf16*>(dy_bf16), static_cast<bf16*>(dpre_bf16), n, S(stream));
+}
+
+int pd_op_axial_attention_bwd(const void* qkv, const float* bias_table, const void* dout, void* dqkv, int B, int T, int H,
+                              int W, int C, int heads, int axis, void* stream) {
+    PD_TRY(gemm_init());
+    return axial_attention_bwd(static_cast<const bf16*>(qkv), bias_table, static_cast<const bf16*>(dout),
+                               static_cast<bf16*>(dqkv), B, T, H, W, C, heads, axis, S(stream));
+}
+
+int pd_op_pack_linear_t(const float* w, void* out, int N, int K, void* stream) {
+    PD_TRY(gemm_init());
+    return pack_linear_t(w, static_cast<bf16*>(out), N, K, S(stream));
+}
+
+int pd_op_pack_conv_dgrad(const float* w, void* out, int Co, int Ci, int taps, void* stream) {
+    PD_TRY(gemm_init());
+    return pack_conv_dgrad(w, static_cast<bf16*>(out), Co, Ci, taps, S(stream));
+}
+
 }  // extern "C"

@@ -67,6 +67,39 @@ int pack_linear(const float* w, bf16* out, int N, int K, int Kpad, cudaStream_t 
 // fp32 [Co][Ci][taps] -> bf16 [Co][taps][Cipad]
 int pack_conv(const float* w, bf16* out, int Co, int Ci, int taps, int Cipad, cudaStream_t st);
 
+// ---- input-gradient kernels (backward.cu) - knowledge-alignment guidance only ---------------------------------
+// GroupNorm(+SiLU) backward: x, dy fp32 [S][R][C]; sums = forward (sum, sumsq); bsums = zeroed scratch [S][G][2].
+// dx_io (fp32, optional) = (accumulate ? dx_io : 0) + dx; dxb (bf16, optional) = the same value.
+int gn_bwd(const float* x, const float* dy, const double* sums, double* bsums, const float* gamma, const float* beta,
+           float* dx_io, bf16* dxb, int S, int R, int C, int G, float eps, int silu, int accumulate, cudaStream_t st);
+// LayerNorm backward: x (forward input), dy fp32 [P][C]; dx_io = (accumulate ? dx_io : 0) + dx; dxb = bf16(dx_io).
+int layer_norm_bwd(const float* x, const float* gamma, const float* dy, float* dx_io, bf16* dxb, int P, int C, float eps,
+                   int accumulate, cudaStream_t st);
+// Backward of patch_merge_ln: dy fp32 [BT*(H/2)*(W/2)][4C] -> dx fp32 / dxb bf16 [BT][H][W][C] (plain store).
+int patch_merge_ln_bwd(const float* x, const float* gamma, const float* dy, float* dx, bf16* dxb, int BT, int H, int W,
+                       int C, float eps, cudaStream_t st);
+// y = GELU_erf(pre) -> bf16; dpre = dmid * GELU'(pre).
+int gelu_fwd(const float* pre, bf16* y, int64_t n, cudaStream_t st);
+int gelu_bwd(const float* pre, const bf16* dmid, bf16* dpre, int64_t n, cudaStream_t st);
+// Backward of axial_attention: qkv (forward input), dout bf16 [B][T][H][W][C] -> dqkv bf16 [B][T][H][W][3C].
+int axial_attention_bwd(const bf16* qkv, const float* bias_table, const bf16* dout, bf16* dqkv, int B, int T, int H,
+                        int W, int C, int heads, int axis, cudaStream_t st);
+// dgrad operands: fp32 [N][K] -> bf16 [K][N];  fp32 [Co][Ci][taps] -> bf16 [Ci][taps reversed][Co].
+int pack_linear_t(const float* w, bf16* out, int N, int K, cudaStream_t st);
+int pack_conv_dgrad(const float* w, bf16* out, int Co, int Ci, int taps, cudaStream_t st);
+
+// ---- knowledge-alignment read-out head (ka_head.cu; reference knowledge_alignment/models.py:19-104,500-528) ----
+int ka_tokens(const float* x, const double* sums, const float* gamma, const float* beta, const float* pos_tc, bf16* tok,
+              int F, int R, int C, int G, float eps, cudaStream_t st);
+int ka_pool(const float* qkv, const float* cw, float cb, float* wsave, float* out, int F, int L, int C, int heads,
+            cudaStream_t st);
+int ka_loss_grad(const float* out, const float* target, float* dout, float* loss, int B, int T, float guide_scale,
+                 cudaStream_t st);
+int ka_pool_bwd(const float* qkv, const float* cw, const float* wsave, const float* dout, bf16* dqkv, int F, int L, int C,
+                int heads, cudaStream_t st);
+int ka_tokens_bwd(const float* dtok, float* dout, int F, int R, int C, cudaStream_t st);
+int transpose_f32(const float* in, float* out, int R, int C, cudaStream_t st);
+
 // ---- sampler (sampler.cu) ----------------------------------------------------------------------------------
 // One fused update of the latent (latent_diffusion.py:553-566,620-631 for DDPM; SURVEY section 8 S6 for DDIM):
 //   z0 = c[0] z - c[1] eps ;  z <- c[2] z0 + c[3] z + c[4] eps + c[5] noise - c[6] guide

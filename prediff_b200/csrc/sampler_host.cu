@@ -45,6 +45,8 @@ Sampler::~Sampler() {
         if (ev_sub_[i]) cudaEventDestroy(ev_sub_[i]);
     }
     if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_ka_) cudaEventDestroy(ev_ka_);
+    if (ka_stream_) cudaStreamDestroy(ka_stream_);
     if (ev_in_) cudaEventDestroy(ev_in_);
     if (ev_out_) cudaEventDestroy(ev_out_);
     if (loop_stream_) cudaStreamDestroy(loop_stream_);
@@ -160,19 +162,38 @@ int Sampler::n_sub_for(int B) const {
     return n;
 }
 
-int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st) {
+int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st,
+                           const Align& al) {
     const int64_t per = (int64_t)unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
     const int64_t per_c = (int64_t)unet->cfg.t_in * unet->cfg.h * unet->cfg.w * unet->cfg.c;
     const int* step = step_dev_.as<int>();
     const int ns = n_sub_for(B);
+    const bool fork = ns > 1 || al.ka != nullptr;
+    const float* guide = nullptr;
+    if (fork) {
+        if (!ev_fork_) PD_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+        PD_CUDA(cudaEventRecord(ev_fork_, st));
+    }
+    if (al.ka) {
+        // the guidance depends on z_t only, not on eps: it runs beside the UNet and fills its idle SMs
+        if (!ka_stream_) {
+            PD_CUDA(cudaStreamCreateWithFlags(&ka_stream_, cudaStreamNonBlocking));
+            PD_CUDA(cudaEventCreateWithFlags(&ev_ka_, cudaEventDisableTiming));
+        }
+        PD_CUDA(cudaStreamWaitEvent(ka_stream_, ev_fork_, 0));
+        PD_TRY(al.ka->mean_shift(z, t_dev_.as<int64_t>(), step, B, al.avg_x_gt, al.guide_scale, nullptr, B, ka_stream_));
+        PD_CUDA(cudaEventRecord(ev_ka_, ka_stream_));
+        float* g = nullptr;
+        PD_TRY(al.ka->guide_buffer(B, &g, nullptr));
+        guide = g;
+    }
     if (ns == 1) {
         PD_TRY(unet->forward(z, t_dev_.as<int64_t>(), step, cond, eps_dev_.as<float>(), B, st));
-        PD_TRY(sampler_update(z, eps_dev_.as<float>(), noise, nullptr, coef_dev_.as<float>(), step, B * per, 0, st));
+        if (al.ka) PD_CUDA(cudaStreamWaitEvent(st, ev_ka_, 0));
+        PD_TRY(sampler_update(z, eps_dev_.as<float>(), noise, guide, coef_dev_.as<float>(), step, B * per, 0, st));
         return advance_step(step_dev_.as<int>(), st);
     }
     const int Bs = B / ns;
-    if (!ev_fork_) PD_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-    PD_CUDA(cudaEventRecord(ev_fork_, st));
     for (int i = 0; i < ns; ++i) {
         if (!sub_stream_[i]) {
             PD_CUDA(cudaStreamCreateWithFlags(&sub_stream_[i], cudaStreamNonBlocking));
@@ -184,25 +205,35 @@ int Sampler::one_iteration(UNet* unet, float* z, const float* cond, const float*
         float* ei = eps_dev_.as<float>() + (int64_t)i * Bs * per;
         PD_TRY(unet->forward(zi, t_dev_.as<int64_t>() + (int64_t)i * Bs, step, cond + (int64_t)i * Bs * per_c, ei, Bs, ss,
                              nullptr, i, B));
-        PD_TRY(sampler_update(zi, ei, noise ? noise + (int64_t)i * Bs * per : nullptr, nullptr, coef_dev_.as<float>(),
-                              step, Bs * per, B * per, ss));
+        if (!al.ka)   // with guidance z_t must stay intact until the KA stream has read it: update after the join
+            PD_TRY(sampler_update(zi, ei, noise ? noise + (int64_t)i * Bs * per : nullptr, nullptr, coef_dev_.as<float>(),
+                                  step, Bs * per, B * per, ss));
         PD_CUDA(cudaEventRecord(ev_sub_[i], ss));
         PD_CUDA(cudaStreamWaitEvent(st, ev_sub_[i], 0));
+    }
+    if (al.ka) {
+        PD_CUDA(cudaStreamWaitEvent(st, ev_ka_, 0));
+        PD_TRY(sampler_update(z, eps_dev_.as<float>(), noise, guide, coef_dev_.as<float>(), step, B * per, 0, st));
     }
     return advance_step(step_dev_.as<int>(), st);
 }
 
 int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_total, float eta,
-                  int k_begin, int k_end, cudaStream_t user) {
+                  int k_begin, int k_end, cudaStream_t user, const Align& al) {
     PD_CHECK(unet && z && cond, PD_ERR_ARG, "sample_loop: null pointer");
+    PD_CHECK(!al.ka || al.avg_x_gt, PD_ERR_ARG, "sample_loop: alignment needs avg_x_gt");
+    if (al.ka)
+        PD_CHECK(al.ka->cfg.t == unet->cfg.t_out && al.ka->cfg.h == unet->cfg.h && al.ka->cfg.w == unet->cfg.w &&
+                     al.ka->cfg.c == unet->cfg.c,
+                 PD_ERR_SHAPE, "sample_loop: the alignment network's input shape differs from the UNet's target shape");
     PD_TRY(enter(user));
-    const int rc = loop_on(loop_stream_, unet, z, cond, noise, B, mode, n_total, eta, k_begin, k_end);
+    const int rc = loop_on(loop_stream_, unet, z, cond, noise, B, mode, n_total, eta, k_begin, k_end, al);
     const int rl = leave(user);
     return rc != PD_OK ? rc : rl;
 }
 
 int Sampler::loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int mode,
-                     int n_total, float eta, int k_begin, int k_end) {
+                     int n_total, float eta, int k_begin, int k_end, const Align& al) {
     std::vector<float> rows;
     std::vector<int64_t> ts;
     PD_TRY(coefficients(mode, n_total, eta, &rows, &ts));
@@ -225,16 +256,16 @@ int Sampler::loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, c
     const bool use_graph = getenv("PD_NO_GRAPH") == nullptr && n_steps > 2;
     int k = 0;
     if (use_graph) {
-        const Key key{unet, z, cond, noise, B};
+        const Key key{unet, z, cond, noise, al.ka, al.avg_x_gt, B, al.guide_scale};
         if (!graph_exec_ || !(key == graph_key_)) {
             drop_graph();
             // first iteration runs eagerly (also performs any lazy one-time kernel attribute setup) ...
-            PD_TRY(one_iteration(unet, z, cond, noise, B, st));
+            PD_TRY(one_iteration(unet, z, cond, noise, B, st, al));
             k = 1;
             // ... then one iteration is captured and replayed; the step index lives on the device
             cudaGraph_t graph = nullptr;
             PD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = one_iteration(unet, z, cond, noise, B, st);
+            const int rc = one_iteration(unet, z, cond, noise, B, st, al);
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != PD_OK) {
                 if (graph) cudaGraphDestroy(graph);
@@ -248,7 +279,7 @@ int Sampler::loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, c
         }
         for (; k < n_steps; ++k) PD_CUDA(cudaGraphLaunch(graph_exec_, st));
     } else {
-        for (; k < n_steps; ++k) PD_TRY(one_iteration(unet, z, cond, noise, B, st));
+        for (; k < n_steps; ++k) PD_TRY(one_iteration(unet, z, cond, noise, B, st, al));
     }
     return PD_OK;
 }

@@ -4,11 +4,21 @@
 #pragma once
 #include "model_common.cuh"
 #include "unet.cuh"
+#include "ka.cuh"
 
 namespace pd {
 
+// Optional knowledge alignment: ka != null adds g = ka->mean_shift(z_t, t, avg_x_gt, guide_scale) to every step
+// (computed on its own stream, concurrently with the UNet) and the update subtracts coef[6] * g.
+struct SamplerAlign {
+    KANet* ka = nullptr;
+    const float* avg_x_gt = nullptr;   // device fp32 [B]
+    float guide_scale = 0.f;
+};
+
 class Sampler {
 public:
+    using Align = SamplerAlign;
     Sampler(int num_timesteps, double linear_start, double linear_end);
     ~Sampler();
     int get_buffer(const char* name, float* out) const;
@@ -16,7 +26,7 @@ public:
     int coefficients(int mode, int n_steps, float eta, std::vector<float>* rows, std::vector<int64_t>* ts) const;
     // Runs executed steps [k_begin, k_end) of the n_total-step schedule; noise[0] belongs to step k_begin.
     int loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_total, float eta,
-             int k_begin, int k_end, cudaStream_t st);
+             int k_begin, int k_end, cudaStream_t st, const Align& al = Align());
     int step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st);
 
     int T;
@@ -27,10 +37,11 @@ private:
     int enter(cudaStream_t user);
     int leave(cudaStream_t user);
     int loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int mode,
-                int n_total, float eta, int k_begin, int k_end);
+                int n_total, float eta, int k_begin, int k_end, const Align& al);
     int step_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int t);
     int upload_tables(const std::vector<float>& rows, const std::vector<int64_t>& ts, int B, cudaStream_t st);
-    int one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st);
+    int one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st,
+                      const Align& al = Align());
     void drop_graph();
 
     std::map<std::string, std::vector<float>> buf_;  // the reference's registered fp32 buffers
@@ -42,13 +53,17 @@ private:
     static constexpr int kMaxSub = 4;
     cudaStream_t sub_stream_[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork_ = nullptr, ev_sub_[kMaxSub] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t ka_stream_ = nullptr;
+    cudaEvent_t ev_ka_ = nullptr;
     cudaStream_t loop_stream_ = nullptr;
     cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
     struct Key {
-        const void *unet, *z, *cond, *noise;
+        const void *unet, *z, *cond, *noise, *ka, *target;
         int B;
+        float gs;
         bool operator==(const Key& o) const {
-            return unet == o.unet && z == o.z && cond == o.cond && noise == o.noise && B == o.B;
+            return unet == o.unet && z == o.z && cond == o.cond && noise == o.noise && B == o.B && ka == o.ka &&
+                   target == o.target && gs == o.gs;
         }
     } graph_key_{};
 };

@@ -159,12 +159,38 @@ class LatentDiffusion(nn.Module):
         return (self.extract_into_tensor(self.sqrt_alphas_cumprod.to(x_start.device), t, x_start.shape) * x_start +
                 self.extract_into_tensor(self.sqrt_one_minus_alphas_cumprod.to(x_start.device), t, x_start.shape) * noise)
 
-    def _run_range(self, z, cond, noise, mode, n_total, eta, k0, k1):
+    def _native_alignment(self, use_alignment, alignment_kwargs):
+        """(alignment object, avg_x_gt [B] device tensor factory) when the registered alignment_fn is the
+        `get_mean_shift` of a prediff_b200 SEVIRAvgIntensityAlignment - then the guided loop stays on the device."""
+        if not use_alignment:
+            return None
+        from .alignment import SEVIRAvgIntensityAlignment
+        owner = getattr(self.alignment_fn, "__self__", None)
+        if isinstance(owner, SEVIRAvgIntensityAlignment) and alignment_kwargs and "avg_x_gt" in alignment_kwargs \
+                and getattr(self.alignment_fn, "__name__", "") == "get_mean_shift":
+            return owner
+        return None
+
+    def _run_range(self, z, cond, noise, mode, n_total, eta, k0, k1, align=None, avg_x_gt=None):
         B = z.shape[0]
         with torch.cuda.device(z.device):
-            L.check(L.lib().pd_sample_loop_range(self._sampler, self.torch_nn_module.handle, L.ptr(z), L.ptr(cond),
-                                                 L.ptr(noise), B, mode, n_total, ctypes.c_float(eta), k0, k1,
-                                                 L.stream_ptr()))
+            if align is None:
+                L.check(L.lib().pd_sample_loop_range(self._sampler, self.torch_nn_module.handle, L.ptr(z), L.ptr(cond),
+                                                     L.ptr(noise), B, mode, n_total, ctypes.c_float(eta), k0, k1,
+                                                     L.stream_ptr()))
+            else:
+                L.check(L.lib().pd_sample_loop_aligned(self._sampler, self.torch_nn_module.handle, align.model.handle,
+                                                       L.ptr(z), L.ptr(cond), L.ptr(noise), L.ptr(avg_x_gt),
+                                                       ctypes.c_float(align.guide_scale), B, mode, n_total,
+                                                       ctypes.c_float(eta), k0, k1, L.stream_ptr()))
+
+    @staticmethod
+    def _target_vector(alignment_kwargs, B, device):
+        t = torch.as_tensor(alignment_kwargs["avg_x_gt"], dtype=torch.float32, device=device).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(B)
+        assert t.numel() == B, "avg_x_gt must hold one value per sample"
+        return t.contiguous()
 
     @torch.no_grad()
     def p_sample(self, zt, zc, t, y=None, use_alignment=False, alignment_kwargs=None, clip_denoised=False,
@@ -211,7 +237,9 @@ class LatentDiffusion(nn.Module):
         if mask is not None:
             assert x0 is not None and x0.shape[2:3] == mask.shape[2:3]
         cond = cond.contiguous().float()
-        host_driven = use_alignment or mask is not None or not self._native()
+        align = self._native_alignment(use_alignment, alignment_kwargs) if self._native() else None
+        host_driven = (use_alignment and align is None) or mask is not None or not self._native()
+        target = self._target_vector(alignment_kwargs, B, device) if align is not None else None
         if host_driven:
             for k, i in enumerate(reversed(range(timesteps))):
                 ts = torch.full((B,), i, device=device, dtype=torch.long)
@@ -241,7 +269,7 @@ class LatentDiffusion(nn.Module):
                         nz = noise[k:k1].contiguous().float()
                     else:  # the reference's per-step torch.randn(shape) calls, drawn up front in order
                         nz = torch.stack([torch.randn(shape, device=device) for _ in range(k1 - k)])
-                    self._run_range(img, cond, nz, PD_MODE_DDPM, timesteps, 0.0, k, k1)
+                    self._run_range(img, cond, nz, PD_MODE_DDPM, timesteps, 0.0, k, k1, align, target)
                     k = k1
                 i = timesteps - stop  # timestep just executed
                 if return_intermediates and (i % log_every_t == 0 or i == timesteps - 1):
@@ -256,9 +284,11 @@ class LatentDiffusion(nn.Module):
         return img
 
     @torch.no_grad()
-    def ddim_sample_loop(self, cond, shape, x_T=None, ddim_steps=50, eta=0.0, noise=None):
+    def ddim_sample_loop(self, cond, shape, x_T=None, ddim_steps=50, eta=0.0, noise=None, use_alignment=False,
+                         alignment_kwargs=None):
         """DDIM over make_ddim_timesteps('uniform', ddim_steps, T); eta = 0 is
-        deterministic. Runs entirely on the device (one CUDA-graph replay per step)."""
+        deterministic. Runs entirely on the device (one CUDA-graph replay per step). With `use_alignment` the
+        knowledge-alignment guidance enters as eps_hat = eps + sqrt(1 - a_t) * g (S6), g from the CUDA KA network."""
         if not self._native():
             raise L.PDError("ddim_sample_loop needs the prediff_b200 CuboidTransformerUNet as torch_nn_module")
         device = cond.device
@@ -268,7 +298,12 @@ class LatentDiffusion(nn.Module):
         if eta != 0.0 and noise is None:
             noise = torch.stack([torch.randn(shape, device=device) for _ in range(ddim_steps)])
         nz = None if noise is None else noise.contiguous().float()
-        self._run_range(img, cond, nz, PD_MODE_DDIM, ddim_steps, float(eta), 0, ddim_steps)
+        align = self._native_alignment(use_alignment, alignment_kwargs)
+        if use_alignment and align is None:
+            raise L.PDError("ddim_sample_loop(use_alignment=True) needs set_alignment(<prediff_b200 "
+                            "SEVIRAvgIntensityAlignment>.get_mean_shift) and alignment_kwargs={'avg_x_gt': ...}")
+        target = self._target_vector(alignment_kwargs, img.shape[0], device) if align is not None else None
+        self._run_range(img, cond, nz, PD_MODE_DDIM, ddim_steps, float(eta), 0, ddim_steps, align, target)
         return img
 
     @torch.no_grad()
@@ -293,8 +328,9 @@ class LatentDiffusion(nn.Module):
             zc = cond if isinstance(cond, torch.Tensor) else cond.get("y", None)
         y = cond if isinstance(cond, torch.Tensor) else cond.get("y", None)
         if sampler == "ddim":
-            assert not use_alignment and mask is None and not return_intermediates
-            output = self.ddim_sample_loop(cond=zc, shape=shape, x_T=x_T, ddim_steps=ddim_steps, eta=ddim_eta)
+            assert mask is None and not return_intermediates
+            output = self.ddim_sample_loop(cond=zc, shape=shape, x_T=x_T, ddim_steps=ddim_steps, eta=ddim_eta,
+                                           use_alignment=use_alignment, alignment_kwargs=alignment_kwargs)
         else:
             output = self.p_sample_loop(cond=zc, shape=shape, y=y, use_alignment=use_alignment,
                                         alignment_kwargs=alignment_kwargs, return_intermediates=return_intermediates,

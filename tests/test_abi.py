@@ -49,6 +49,22 @@ def test_unet_and_vae_weight_specs_match_reference_keys():
     assert sum(int(np.prod(s)) for _, s in Wt.vae_param_spec(Wt.VAEConfig())) == 84499393
 
 
+def test_ka_weight_spec_matches_reference_keys():
+    from prediff_b200.alignment import NoisyCuboidTransformerEncoder, SEVIRAvgIntensityAlignment
+    cfg = Wt.KAConfig()
+    al = SEVIRAvgIntensityAlignment(guide_scale=50.0, model_args=dict(
+        input_shape=[cfg.t, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units, depth=list(cfg.depth), block_attn_patterns="axial",
+        num_heads=cfg.num_heads, pool="attention", readout_seq=True, out_len=cfg.t))
+    spec = [(n, tuple(s)) for n, s in Wt.ka_param_spec(cfg)]
+    assert al.model.weight_spec_from_library() == spec
+    assert [(n, tuple(p.shape)) for n, p in al.model.named_parameters()] == spec
+    assert sum(int(np.prod(s)) for _, s in spec) == 8937033
+    with pytest.raises(NotImplementedError):
+        NoisyCuboidTransformerEncoder([6, 16, 16, 64], pool="adaptive")
+    with pytest.raises(NotImplementedError):
+        NoisyCuboidTransformerEncoder([6, 16, 16, 64], block_attn_patterns="video_swin_2x4")
+
+
 def test_state_dict_has_reference_keys_including_derived_buffers():
     from prediff_b200.unet import CuboidTransformerUNet
     cfg = Wt.TINY_UNET
