@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 from prediff_b200 import weights as Wt  # noqa: E402
 
 GFLOP_PER_SAMPLE_STEP = 653.43   # algorithmic FLOPs of one UNet forward for one sample
-UNET_SEED, VAE_SEED = 1001, 2002
+UNET_SEED, VAE_SEED, KA_SEED = 1001, 2002, 3003
 METRIC = "SEVIR-LR denoise-steps/sec (50-step DDIM, 7->6x128x128)"
 UNIT = "sample-steps/s"
 
@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4, help="forecasts per GPU (BASELINE config 3: 4)")
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ka", action="store_true", help="skip the knowledge-alignment (configs[3]) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -257,6 +258,43 @@ def main():
     h2d = y_host.numel() * 4 + zT_host.numel() * 4
     d2h = out_host.numel() * 4
 
+    # ---- BASELINE.json configs[3]: the same loop with knowledge-alignment guidance (KA forward + backward each step) ----
+    ka_line = None
+    if not args.no_ka:
+        from prediff_b200.alignment import SEVIRAvgIntensityAlignment
+        kcfg = Wt.KAConfig()
+        al = SEVIRAvgIntensityAlignment(alignment_type="avg_x", guide_scale=kcfg.guide_scale, model_type="cuboid",
+                                        model_args=dict(input_shape=[kcfg.t, kcfg.h, kcfg.w, kcfg.c], base_units=kcfg.base_units,
+                                                        depth=list(kcfg.depth), block_attn_patterns="axial",
+                                                        num_heads=kcfg.num_heads, pool="attention", readout_seq=True,
+                                                        out_len=kcfg.t, max_batch=B))
+        al.model.load_state_dict({k: torch.from_numpy(v) for k, v in
+                                  Wt.seeded_state_dict(Wt.ka_param_spec(kcfg), KA_SEED).items()}, strict=False)
+        ldm.set_alignment(al.get_mean_shift)
+        kw = {"avg_x_gt": torch.full((B, 1), 0.3, device=dev)}
+        Kk = max(2, min(K, 5))
+        for _ in range(2):
+            ldm.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0, use_alignment=True, alignment_kwargs=kw)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Kk):
+            ldm.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0, use_alignment=True, alignment_kwargs=kw)
+        e1.record()
+        barrier()
+        ms_ka = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_ka, op=dist.ReduceOp.MAX)
+        nf, nb = ctypes.c_int(), ctypes.c_int()
+        L.check(L.lib().pd_ka_kernels(al.model.handle, B, ctypes.byref(nf), ctypes.byref(nb)))
+        ka_line = {"workload": f"PreDiff-KA: {S}-step DDIM with knowledge-alignment guidance, batch={B} per GPU "
+                               "(BASELINE.json configs[3]); KA forward + input-gradient backward every step, run on a "
+                               "second stream beside the UNet",
+                   "value": world * B * S * Kk / (ms_ka.item() * 1e-3), "unit": UNIT, "loops": Kk,
+                   "ms_per_step": ms_ka.item() / Kk, "ka_kernels_per_step": nf.value + nb.value,
+                   "gflop_per_sample_step": GFLOP_PER_SAMPLE_STEP + 22.95}
+        ldm.set_alignment(None)
+
     # ---- per-kernel-class device time of one UNet forward (events around every launch) -----------------------
     stats = (ctypes.c_double * 5)()
     t = torch.full((B,), 981, device=dev, dtype=torch.int64)
@@ -307,6 +345,9 @@ def main():
                                          "share_of_forward": gemm_ms / (gemm_ms + other_ms)},
                      "other_kernels": {"launches_per_forward": int(n_other), "ms_per_forward": other_ms}},
     }
+    if ka_line is not None:
+        ka_line["slowdown_vs_unguided"] = (ka_line["ms_per_step"]) / (ms / K)
+        line["knowledge_alignment"] = ka_line
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(args)
     print(json.dumps(line), flush=True)

@@ -68,6 +68,11 @@ int pd_unet_forward(pd_unet* m, const float* x, const int64_t* t, const float* c
 int pd_unet_profile_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
                             void* stream, double stats[5]);
 int pd_unet_kernels_per_forward(pd_unet* m, int batch, int* n);
+/* Per-launch trace: one eager forward with a %globaltimer stamp kernel after every plan step. ns_dev[i] (device u64,
+ * max_slots entries) = stamp after step i-1 (ns_dev[0] = start); labels (host, optional) receives one '\n'-terminated
+ * label per step ("L0.stack.ffn1", "L1.res.conv2", ...). Returns the number of steps (>= 0) or a PD_ERR_* code. */
+int pd_unet_trace_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
+                          void* stream, unsigned long long* ns_dev, int max_slots, char* labels, int labels_bytes);
 
 /* ---- AutoencoderKL (reference: src/prediff/taming/autoencoder_kl.py:80-113, vae.py:70-86,150-166) --------- */
 typedef struct pd_vae pd_vae;
@@ -172,7 +177,7 @@ int pd_op_conv_gemm(const void* A_bf16, const void* Wt_bf16, int samples, int D,
  * from the same epilogue (the fusion the UNet uses for proj / ffn_2 / conv2 -> next pre-norm at width 256). */
 int pd_op_linear_residual_ln(const void* A_bf16, const void* Wt_bf16, int M, int K, const float* bias, float* x_inout,
                              const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream);
-/* Same launch with clock64() phase stamps of CTA (dbg_block, 0) written to stamps9[9] (device u64):
+/* Same launch with clock64() phase stamps of CTA (dbg_block, 0) written to stamps9[0..8] (device u64[16]; [9], [10] = %globaltimer ns at entry / exit):
  * entry, setup done, first operand tile landed, last MMA issued, accumulator ready, first epilogue chunk ready,
  * epilogue done, last bulk store drained, exit. Profiling aid (tools/gemm_phases.py). */
 int pd_op_conv_gemm_phases(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt,

@@ -64,6 +64,21 @@ int pd_unet_profile_forward(pd_unet* m, const float* x, const int64_t* t, const 
     stats[0] = p.gemm_ms; stats[1] = p.n_gemm; stats[2] = p.other_ms; stats[3] = p.n_other; stats[4] = p.gemm_flops;
     return PD_OK;
 }
+int pd_unet_trace_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
+                          void* stream, unsigned long long* ns_dev, int max_slots, char* labels, int labels_bytes) {
+    PD_CHECK(m && ns_dev, PD_ERR_ARG, "pd_unet_trace_forward: null argument");
+    std::vector<std::string> lab;
+    PD_TRY(m->impl.plan_labels(batch, &lab));
+    PD_CHECK((int)lab.size() + 1 <= max_slots, PD_ERR_ARG, "pd_unet_trace_forward: need %d slots", (int)lab.size() + 1);
+    if (labels) {
+        std::string all;
+        for (const auto& l : lab) { all += l; all += '\n'; }
+        PD_CHECK((int)all.size() + 1 <= labels_bytes, PD_ERR_ARG, "pd_unet_trace_forward: label buffer too small");
+        memcpy(labels, all.c_str(), all.size() + 1);
+    }
+    PD_TRY(m->impl.forward(x, t, nullptr, cond, out, batch, S(stream), nullptr, 0, 0, ns_dev));
+    return (int)lab.size();
+}
 int pd_unet_kernels_per_forward(pd_unet* m, int batch, int* n) {
     PD_CHECK(m && n, PD_ERR_ARG, "pd_unet_kernels_per_forward: null argument");
     return m->impl.kernels_per_forward(batch, n);

@@ -54,7 +54,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int lane = threadIdx.x & 31;
     unsigned long long* dbg = (p.dbg && blockIdx.x == p.dbg_block && blockIdx.y == 0) ? p.dbg : nullptr;
 #define PD_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
-    if (threadIdx.x == 0) PD_STAMP(0);
+    if (threadIdx.x == 0) {
+        PD_STAMP(0);
+        if (dbg) {   // wall-clock (ns) stamps: effective SM frequency + launch skew between CTAs
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            dbg[9] = gt;
+        }
+    }
 
     const int tile = blockIdx.x;
     const int n0 = blockIdx.y * BN;
@@ -375,7 +382,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, C::kTmemCols);
-    if (threadIdx.x == 0) PD_STAMP(8);
+    if (threadIdx.x == 0) {
+        PD_STAMP(8);
+        if (dbg) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            dbg[10] = gt;
+        }
+    }
 #undef PD_STAMP
 }
 

@@ -133,23 +133,40 @@ struct PlanProfile {
     int n_gemm = 0, n_other = 0;
 };
 
+// Writes %globaltimer (ns) to *slot: the per-launch trace of Plan::run_traced (tools/trace_unet.py).
+int stamp_globaltimer(unsigned long long* slot, cudaStream_t st);
+
 struct Plan {
     std::vector<Step> steps;
     std::vector<uint8_t> kinds;
+    std::vector<std::string> labels;   // one per step: kernel class + site, for the per-launch trace
+    std::string scope;                 // prefix applied to labels added from now on (e.g. "L0.res")
     double gemm_flops = 0;
     int n_gemm = 0;
     int run(cudaStream_t st) const {
         for (const auto& s : steps) PD_TRY(s(st));
         return PD_OK;
     }
-    void add(Step s, StepKind k = STEP_KERNEL) {
+    void add(Step s, StepKind k = STEP_KERNEL, const char* label = "") {
         steps.push_back(std::move(s));
         kinds.push_back(k);
+        labels.push_back(scope.empty() ? std::string(label) : scope + "." + label);
     }
-    void add_gemm(const GemmOp& op) {
+    void add(Step s, const char* label) { add(std::move(s), STEP_KERNEL, label); }
+    void add_gemm(const GemmOp& op, const char* label = "gemm") {
         gemm_flops += op.flops;
         ++n_gemm;
-        add([op](cudaStream_t st) { return gemm_launch(op, st); }, STEP_GEMM);
+        add([op](cudaStream_t st) { return gemm_launch(op, st); }, STEP_GEMM, label);
+    }
+    // One eager pass with a %globaltimer stamp kernel after every step: ns[i] = stamp after step i (ns[0] = start),
+    // so ns[i+1] - ns[i] = duration of step i + one (constant) stamp-kernel slot. `ns` has steps.size() + 1 slots.
+    int run_traced(cudaStream_t st, unsigned long long* ns_dev) const {
+        PD_TRY(stamp_globaltimer(ns_dev, st));
+        for (size_t i = 0; i < steps.size(); ++i) {
+            PD_TRY(steps[i](st));
+            PD_TRY(stamp_globaltimer(ns_dev + i + 1, st));
+        }
+        return PD_OK;
     }
     int num_kernels() const {
         int n = 0;

@@ -2,6 +2,7 @@
 // (reference latent_diffusion.py:553-566,598-631) collapse into one kernel that reads its coefficients from
 // the device-resident schedule table, so the step loop never returns to the host.
 #include "ops.cuh"
+#include "model_common.cuh"
 
 namespace pd {
 namespace {
@@ -40,8 +41,19 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
 }
 
 __global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void stamp_globaltimer_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
 
 }  // namespace
+
+int stamp_globaltimer(unsigned long long* slot, cudaStream_t st) {
+    stamp_globaltimer_kernel<<<1, 1, 0, st>>>(slot);
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
 
 int advance_step(int* step, cudaStream_t st) {
     advance_step_kernel<<<1, 1, 0, st>>>(step);

@@ -294,8 +294,9 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
     double* s1 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
     double* s2 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
     const float *g1w = r.gn1_w, *g1b = r.gn1_b, *g2w = r.gn2_w, *g2b = r.gn2_b;
-    pl.add([=](cudaStream_t st) { return gn_stats(x, s1, B, R, C, 32, st); });
-    pl.add([=](cudaStream_t st) { return gn_apply(x, s1, g1w, g1b, a, B, R, C, 32, 1e-5f, 1, st); });
+    pl.scope = strf("L%d.res", lvl);
+    pl.add([=](cudaStream_t st) { return gn_stats(x, s1, B, R, C, 32, st); }, "gn_stats");
+    pl.add([=](cudaStream_t st) { return gn_apply(x, s1, g1w, g1b, a, B, R, C, 32, 1e-5f, 1, st); }, "gn_apply");
     {
         GemmEpilogue e;
         e.bias = r.conv1_b;
@@ -306,10 +307,10 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
         PD_TRY(gemm_make(&op, a, g, r.conv1_w, C, e));
-        pl.add_gemm(op);
+        pl.add_gemm(op, "conv1");
     }
-    pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); });
-    pl.add([=](cudaStream_t st) { return gn_apply(h, s2, g2w, g2b, a, B, R, C, 32, 1e-5f, 1, st); });
+    pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); }, "gn_stats");
+    pl.add([=](cudaStream_t st) { return gn_apply(h, s2, g2w, g2b, a, B, R, C, 32, 1e-5f, 1, st); }, "gn_apply");
     {
         GemmEpilogue e;
         e.bias = r.conv2_b;
@@ -324,8 +325,9 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
         PD_TRY(gemm_make(&op, a, g, r.conv2_w, C, e));
-        pl.add_gemm(op);
+        pl.add_gemm(op, "conv2");
     }
+    pl.scope.clear();
     return PD_OK;
 }
 
@@ -335,21 +337,23 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
     float* x = b.x[lvl];
     bf16 *ln = b.ln[lvl], *qkv = b.qkv[lvl], *att = b.att[lvl], *mid = b.mid[lvl];
     const int heads = cfg.num_heads, Tn = T;
+    pl.scope = strf("L%d.stack", lvl);
     for (int i = 0; i < 3; ++i) {
         const AttnW& aw = s.a[i];
         const FfnW& fw = s.f[i];
         const bool fuse = ln_fusable(lvl);
         // x = x + proj(attn(LN(x)))   (cuboid_transformer.py:1151, 813-952). With C == 256 the LayerNorm was
         // produced by the epilogue of the GEMM that last wrote x (conv2 / previous ffn_2).
-        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); });
+        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
         {
             GemmEpilogue e;
             e.out_bf16 = qkv;
             GemmOp op;
             PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), aw.qkv_w, 3 * C, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "qkv");
         }
-        pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, i, st); });
+        pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, i, st); },
+               i == 0 ? "attn_T" : (i == 1 ? "attn_H" : "attn_W"));
         {
             GemmEpilogue e;
             e.bias = aw.proj_b;
@@ -362,10 +366,10 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             }
             GemmOp op;
             PD_TRY(gemm_make(&op, att, GemmGeom::linear(P, C), aw.proj_w, C, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "proj");
         }
         // x = x + W2 gelu(W1 LN(x) + b1) + b2   (cuboid_transformer.py:195-205)
-        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); });
+        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
         {
             GemmEpilogue e;
             e.bias = fw.b1;
@@ -373,7 +377,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             e.out_bf16 = mid;
             GemmOp op;
             PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), fw.w1, 4 * C, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "ffn1");
         }
         {
             GemmEpilogue e;
@@ -387,9 +391,10 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             }
             GemmOp op;
             PD_TRY(gemm_make(&op, mid, GemmGeom::linear(P, 4 * C), fw.w2, C, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "ffn2");
         }
     }
+    pl.scope.clear();
     return PD_OK;
 }
 
@@ -411,7 +416,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     pl.add([=](cudaStream_t st) {
         PD_CUDA(cudaMemsetAsync(gn_all, 0, gn_bytes, st));
         return PD_OK;
-    }, STEP_NONE);
+    }, STEP_NONE, "memset");
     // ---- time embedding (models/utils.py:68-83, time_embed.py:16-24, :108-114) ----
     {
         const float *w0 = te_w0, *b0 = te_b0, *w2 = te_w2, *b2 = te_b2;
@@ -420,15 +425,15 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         const int c0 = C0, te = TE, et = emb_total;
         float *e0 = b.e0, *e1 = b.e1, *temb = b.temb, *embs = b.embs;
         bp->t_slot = pl.steps.size();
-        pl.add([](cudaStream_t) { return PD_OK; });  // placeholder: timestep_embedding, bound per call
+        pl.add([](cudaStream_t) { return PD_OK; }, "temb.sincos");  // placeholder: timestep_embedding, bound per call
         (void)e0;
-        pl.add([=](cudaStream_t st) { return small_linear(e0, w0, b0, e1, B, c0, te, 0, 1, st); });
-        pl.add([=](cudaStream_t st) { return small_linear(e1, w2, b2, temb, B, te, te, 0, 0, st); });
-        pl.add([=](cudaStream_t st) { return small_linear(temb, wc, bc, embs, B, te, et, 1, 0, st); });
+        pl.add([=](cudaStream_t st) { return small_linear(e0, w0, b0, e1, B, c0, te, 0, 1, st); }, "temb.linear");
+        pl.add([=](cudaStream_t st) { return small_linear(e1, w2, b2, temb, B, te, te, 0, 0, st); }, "temb.linear");
+        pl.add([=](cudaStream_t st) { return small_linear(temb, wc, bc, embs, B, te, et, 1, 0, st); }, "temb.linear");
     }
     // ---- input assembly + first_proj (cuboid_transformer_unet.py:425-431) ----
     bp->in_slot = pl.steps.size();
-    pl.add([](cudaStream_t) { return PD_OK; });  // placeholder: unet_assemble, bound per call (user pointers)
+    pl.add([](cudaStream_t) { return PD_OK; }, "assemble");  // placeholder: unet_assemble, bound per call (user pointers)
     {
         double* s1 = b.gn_sums + (size_t)gn_slot++ * B * 128 * 2;
         double* s2 = b.gn_sums + (size_t)gn_slot++ * B * 128 * 2;
@@ -437,15 +442,16 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         float *h = b.h[0], *x = b.x[0];
         const ResW r = first;
         const int c0 = C0;
-        pl.add([=](cudaStream_t st) { return gn_stats(xin, s1, B, R0, kCinPad, kCinPad, st); });
-        pl.add([=](cudaStream_t st) { return gn_apply(xin, s1, r.gn1_w, r.gn1_b, a, B, R0, kCinPad, kCinPad, 1e-5f, 1, st); });
+        pl.scope = "first";
+        pl.add([=](cudaStream_t st) { return gn_stats(xin, s1, B, R0, kCinPad, kCinPad, st); }, "gn_stats");
+        pl.add([=](cudaStream_t st) { return gn_apply(xin, s1, r.gn1_w, r.gn1_b, a, B, R0, kCinPad, kCinPad, 1e-5f, 1, st); }, "gn_apply");
         {
             GemmEpilogue e;
             e.bias = r.conv1_b;
             e.out_f32 = h;
             GemmOp op;
             PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, kCinPad, 3, 3, 3), r.conv1_w, C0, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "conv1");
         }
         {   // 1x1x1 skip conv on the raw (un-normalised) input
             GemmEpilogue e;
@@ -453,10 +459,10 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             e.out_f32 = x;
             GemmOp op;
             PD_TRY(gemm_make(&op, b.xin_bf16, GemmGeom::conv(B, T, H, W, kCinPad, 1, 1, 1), first_skip_w, C0, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "skip");
         }
-        pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R0, c0, 32, st); });
-        pl.add([=](cudaStream_t st) { return gn_apply(h, s2, r.gn2_w, r.gn2_b, a, B, R0, c0, 32, 1e-5f, 1, st); });
+        pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R0, c0, 32, st); }, "gn_stats");
+        pl.add([=](cudaStream_t st) { return gn_apply(h, s2, r.gn2_w, r.gn2_b, a, B, R0, c0, 32, 1e-5f, 1, st); }, "gn_apply");
         {
             GemmEpilogue e;
             e.bias = r.conv2_b;
@@ -464,11 +470,12 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             e.out_f32 = x;
             GemmOp op;
             PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C0, 3, 3, 3), r.conv2_w, C0, e));
-            pl.add_gemm(op);
+            pl.add_gemm(op, "conv2");
         }
         const float *pt = pos_T, *ph = pos_H, *pw = pos_W;
         const int Tn = T;
-        pl.add([=](cudaStream_t st) { return pos_embed_add(x, pt, ph, pw, B, Tn, H, W, c0, st); });
+        pl.add([=](cudaStream_t st) { return pos_embed_add(x, pt, ph, pw, B, Tn, H, W, c0, st); }, "pos_embed");
+        pl.scope.clear();
     }
     // ---- down path ----
     for (int d = 0; d < cfg.depth[0]; ++d) {
@@ -479,12 +486,12 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         const float *x0 = b.x[0], *lw = pm_ln_w, *lb = pm_ln_b;
         bf16* pm = b.pm;
         const int BT = B * T, c0 = C0;
-        pl.add([=](cudaStream_t st) { return patch_merge_ln(x0, lw, lb, pm, BT, H, W, c0, 1e-5f, st); });
+        pl.add([=](cudaStream_t st) { return patch_merge_ln(x0, lw, lb, pm, BT, H, W, c0, 1e-5f, st); }, "down.merge_ln");
         GemmEpilogue e;
         e.out_f32 = b.x[1];
         GemmOp op;
         PD_TRY(gemm_make(&op, pm, GemmGeom::linear(B * T * HW / 4, 4 * C0), pm_w, C1, e));
-        pl.add_gemm(op);
+        pl.add_gemm(op, "down.reduction");
     }
     for (int d = 0; d < cfg.depth[1]; ++d) {
         PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot, &down_stack[1][d]));
@@ -499,14 +506,14 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         const float* x1 = b.x[1];
         bf16* up = b.up;
         const int BT = B * T, c1 = C1;
-        pl.add([=](cudaStream_t st) { return upsample2x_cast(x1, up, BT, H / 2, W / 2, c1, st); });
+        pl.add([=](cudaStream_t st) { return upsample2x_cast(x1, up, BT, H / 2, W / 2, c1, st); }, "up.nearest");
         GemmEpilogue e;
         e.bias = up_b;
         e.residual = b.x[0];
         e.out_f32 = b.x[0];
         GemmOp op;
         PD_TRY(gemm_make(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e));
-        pl.add_gemm(op);
+        pl.add_gemm(op, "up.conv");
     }
     for (int d = 0; d < cfg.depth[0]; ++d) {
         PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot, &up_stack[0][d]));
@@ -518,7 +525,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         const float* x0 = b.x[0];
         bf16* fin = b.fin;
         const int64_t rc = (int64_t)cfg.t_out * HW * C0, stride = (int64_t)T * HW * C0, off = (int64_t)cfg.t_in * HW * C0;
-        pl.add([=](cudaStream_t st) { return cast_bf16(x0 + off, fin, B, rc, stride, st); });
+        pl.add([=](cudaStream_t st) { return cast_bf16(x0 + off, fin, B, rc, stride, st); }, "final.cast");
         GemmEpilogue e;
         e.bias = final_b;
         e.out_f32 = b.h[0];  // placeholder; re-bound to the caller's tensor per call
@@ -526,7 +533,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.gemm_flops += bp->final_op.flops;
         ++pl.n_gemm;
         bp->out_slot = pl.steps.size();
-        pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM);  // placeholder: final GEMM, bound per call
+        pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM, "final.proj");  // placeholder: final GEMM, bound per call
     }
     return PD_OK;
 }
@@ -546,7 +553,7 @@ int UNet::get_plan(int B, BatchPlan** out, int replica) {
 
 // t may point at a table indexed by a device-side step counter (sampler loop): t_table[*step * B + b].
 int UNet::forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B,
-                  cudaStream_t st, PlanProfile* prof, int replica, int t_stride) {
+                  cudaStream_t st, PlanProfile* prof, int replica, int t_stride, unsigned long long* trace_ns) {
     PD_CHECK(x && t && cond && out, PD_ERR_ARG, "unet forward: null pointer");
     BatchPlan* bp = nullptr;
     PD_TRY(get_plan(B, &bp, replica));
@@ -563,8 +570,16 @@ int UNet::forward(const float* x, const int64_t* t, const int* step, const float
     GemmOp fop = bp->final_op;
     PD_TRY(gemm_bind_output(&fop, out, nullptr, nullptr));
     bp->plan.steps[bp->out_slot] = [fop](cudaStream_t s) { return gemm_launch(fop, s); };
+    if (trace_ns) return bp->plan.run_traced(st, trace_ns);
     if (prof) return bp->plan.run_profiled(st, prof);
     return bp->plan.run(st);
+}
+
+int UNet::plan_labels(int B, std::vector<std::string>* out) {
+    BatchPlan* bp = nullptr;
+    PD_TRY(get_plan(B, &bp));
+    *out = bp->plan.labels;
+    return PD_OK;
 }
 
 int UNet::kernels_per_forward(int B, int* n) {

@@ -34,7 +34,8 @@ public:
     // replica: independent workspace index (sub-batches of one call running concurrently on different streams);
     // t_stride: row length of the t table when `step` is given (0 -> B)
     int forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B, cudaStream_t st,
-                PlanProfile* prof = nullptr, int replica = 0, int t_stride = 0);
+                PlanProfile* prof = nullptr, int replica = 0, int t_stride = 0, unsigned long long* trace_ns = nullptr);
+    int plan_labels(int B, std::vector<std::string>* out);   // one label per plan step (trace_ns has size + 1 slots)
     int kernels_per_forward(int B, int* n);
     int get_plan(int B, BatchPlan** out, int replica = 0);
 

@@ -19,7 +19,7 @@ def run(tag, samples, D, H, W, C, k, N, res, bf16_out, act, bn=0):
     w = (torch.randn(N, kt * kh * kw * C, device=dev) * 0.02).bfloat16()
     bias = torch.randn(N, device=dev)
     out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16 if bf16_out else torch.float32)
-    stamps = torch.zeros(9, device=dev, dtype=torch.int64)
+    stamps = torch.zeros(16, device=dev, dtype=torch.int64)
     args = lambda blk: (L.ptr(a), L.ptr(w), samples, D, H, W, C, kt, kh, kw, N, L.ptr(bias), L.ptr(out) if res else None,
                         None if bf16_out else L.ptr(out), L.ptr(out) if bf16_out else None, act, bn, blk, L.ptr(stamps),
                         L.stream_ptr())
@@ -35,12 +35,15 @@ def run(tag, samples, D, H, W, C, k, N, res, bf16_out, act, bn=0):
     us = e0.elapsed_time(e1) * 1000 / 20
     flops = 2.0 * M * N * C * kt * kh * kw
     line = f"{tag:28s} {us:7.1f} us/launch (back-to-back) {flops / us * 1e-6:7.1f} TF/s |"
-    for blk in (0, 50):
+    t_first = None
+    for blk in (0, 25, 50):
         L.check(L.lib().pd_op_conv_gemm_phases(*args(blk)))
         torch.cuda.synchronize()
         s = stamps.cpu().tolist()
         d = [s[i + 1] - s[i] for i in range(8)]
-        line += f" cta{blk}: " + " ".join(f"{n}={v}" for n, v in zip(names, d)) + f" total={s[8] - s[0]} |"
+        ns = s[10] - s[9]
+        line += f" cta{blk}: " + " ".join(f"{n}={v}" for n, v in zip(names, d)) + \
+            f" total={s[8] - s[0]} cyc = {ns} ns -> {(s[8] - s[0]) / max(ns, 1):.3f} GHz |"
     print(line)
 
 
