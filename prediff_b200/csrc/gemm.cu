@@ -426,6 +426,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_k = p.ntaps * p.cblks;
+    unsigned long long* dbg = (p.dbg && (int)blockIdx.x == p.dbg_block) ? p.dbg : nullptr;
+    if (dbg && threadIdx.x == 0) {
+        dbg[0] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[9] = gt;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -452,6 +459,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -536,6 +544,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             __syncwarp();
             ptx::mbar_wait(&acc_full[acc], (li >> 1) & 1);
             ptx::tc_fence_after();
+            if (dbg && et == 0 && li < 3) dbg[2 + 2 * li] = clock64();
             const uint32_t t_lane = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = half * kPerHalf, idx = 0; c < (half + 1) * kPerHalf; ++c, ++idx) {
@@ -572,6 +581,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                     ptx::bulk_commit();
                 }
             }
+            if (dbg && et == 0 && li < 3) dbg[3 + 2 * li] = clock64();
         }
         if (lane == 0) ptx::bulk_wait_read<0>();
         __syncwarp();
@@ -579,6 +589,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    if (dbg && threadIdx.x == 0) {
+        dbg[8] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[10] = gt;
+    }
 }
 
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
@@ -635,10 +651,10 @@ int gemm_init() {
     return PD_OK;
 }
 
-int gemm_split_flags_needed(const GemmGeom& g, int N) {
+int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split) {
     const int out_D = g.out_D ? g.out_D : g.D;
     const int num_k = g.ntaps * (g.C / kGemmBlockK);
-    if (num_k < 128 || N % 256 != 0) return 0;
+    if ((num_k < 128 && force_split != 2) || N % 256 != 0) return 0;
     return ceil_div(out_D * g.H * g.W, kGemmBlockM) * g.samples * (N / 256);
 }
 
@@ -703,7 +719,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         if (bn && N % bn != 0) bn = 0;
     }
     const int num_k = g.ntaps * (g.C / kGemmBlockK);
-    if (!bn && e.split_flags && gemm_split_flags_needed(g, N) > 0 && e.out_f32 && e.act == ACT_NONE) bn = 256;
+    if (!bn && e.split_flags && gemm_split_flags_needed(g, N, e.force_split) > 0 && e.out_f32 && e.act == ACT_NONE)
+        bn = 256;
     // A 128 x 128 tcgen05.mma takes the same ~128 cycles as 128 x 256 (measured, tools/gemm_phases.py), so once the
     // mainloop matters (>= 16 k-blocks) BN = 256 halves it even if fewer CTAs run.
     if (!bn && N % 256 == 0 && num_k >= 16 && (int64_t)m_tiles * (N / 256) >= kNumSMs / 4) bn = 256;
@@ -773,7 +790,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     op->stages = bn == 256 ? ((num_k <= 8 && multi_wave) ? 2 : 4) : (bn == 128 ? 3 : 4);
     // split-K = 2 for very long reductions (the level-1 Conv3d, 216 k-blocks): depends on the layer shape only, never
     // on the batch, so results stay batch-invariant; the two partial sums are combined in a fixed order.
-    op->split_k = (e.split_flags && num_k >= 128 && bn == 256 && e.out_f32 && e.act == ACT_NONE && !want_ln) ? 2 : 1;
+    op->split_k = (e.split_flags && (num_k >= 128 || (e.force_split == 2 && num_k >= 8)) && bn == 256 && e.out_f32 &&
+                   e.act == ACT_NONE && !want_ln) ? 2 : 1;
     if (want_ln) op->stages = 4;   // the LN pass needs every chunk resident in its own slab (192 KB of stages)
     p.ln_gamma = want_ln ? e.ln_gamma : nullptr;
     p.ln_beta = e.ln_beta;

@@ -85,6 +85,8 @@ struct GemmEpilogue {
     bf16* ln_out = nullptr;
     float ln_eps = 1e-5f;
     int* split_flags = nullptr;       // optional zeroed [m_tiles * n_tiles] ints: enables split-K (see gemm_make)
+    int force_split = 0;              // 2: split K in two even below the automatic threshold (few tiles, long K);
+                                      // must depend on the layer shape only so results stay batch-invariant
     unsigned long long* dbg = nullptr;  // optional phase-timestamp buffer (9 x u64), see GemmKernelParams::dbg
     int dbg_block = 0;
 };
@@ -123,7 +125,7 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream);
 // Points an already-built op at new output / residual buffers of the same shape (per-call user pointers).
 int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
 // Number of ints gemm_make may need in GemmEpilogue::split_flags for this geometry (0 if it will not split).
-int gemm_split_flags_needed(const GemmGeom& g, int N);
+int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split = 0);
 int gemm_init();  // resolves the driver entry point + raises the dynamic smem limits (idempotent)
 
 }  // namespace pd

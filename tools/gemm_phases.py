@@ -37,11 +37,18 @@ def run(tag, samples, D, H, W, C, k, N, res, bf16_out, act, bn=0):
     line = f"{tag:28s} {us:7.1f} us/launch (back-to-back) {flops / us * 1e-6:7.1f} TF/s |"
     t_first = None
     for blk in (0, 25, 50):
+        stamps.zero_()
         L.check(L.lib().pd_op_conv_gemm_phases(*args(blk)))
         torch.cuda.synchronize()
         s = stamps.cpu().tolist()
-        d = [s[i + 1] - s[i] for i in range(8)]
         ns = s[10] - s[9]
+        if bf16_out and s[2] and not s[7]:   # persistent kernel: entry, setup, (epilogue begin, end) x tiles, exit
+            line += f" cta{blk}(persistent): setup={s[1]-s[0]} " + " ".join(
+                f"t{i}:wait_acc@{s[2+2*i]-s[0]} epi={s[3+2*i]-s[2+2*i]}" for i in range(3) if s[2 + 2 * i]) + \
+                f" total={s[8]-s[0]} cyc = {ns} ns |"
+            stamps.zero_()
+            continue
+        d = [s[i + 1] - s[i] for i in range(8)]
         line += f" cta{blk}: " + " ".join(f"{n}={v}" for n, v in zip(names, d)) + \
             f" total={s[8] - s[0]} cyc = {ns} ns -> {(s[8] - s[0]) / max(ns, 1):.3f} GHz |"
     print(line)
