@@ -166,6 +166,17 @@ int pd_sampler_sub_batches(const pd_sampler* s, int batch);
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream);
 
+/* ---- on-device evaluation step (reference: src/prediff/datasets/sevir/evaluation.py:88-285 SEVIRSkillScore.update,
+ *      _threshold :12-37; sevir_dataloader.py:652-681 back-transform; torchmetrics MSE / MAE sums beside it in
+ *      train_sevirlr_prediff.py:960-962) ------------------------------------------------------------------------ */
+/* One pass over forecast and target frames, fp32 [N][T][H][W] in [0,1] (device): values are mapped back to VIL units
+ * (x / (1/255)), optionally max-pooled (`pool` x `pool`, 1 = none), compared with each threshold (NaN in either ->
+ * neither hit, miss nor false alarm) and ADDED to counts int64 [n_thresholds][T][3] = (hits, misses, false alarms)
+ * per threshold and lead time; sums double [2] += (sum (pred - target)^2, sum |pred - target|) over the raw pixels.
+ * thresholds_host: host pointer (e.g. 16, 74, 133, 160, 181, 219), at most 8. Integer results are exact. */
+int pd_sevir_eval_update(const float* pred, const float* target, int64_t* counts, double* sums, int N, int T, int H,
+                         int W, int pool, const float* thresholds_host, int n_thresholds, void* stream);
+
 /* ---- kernel-level entry points (used by the parity tests; same kernels the models launch) ------------------ */
 /* out = epilogue(conv/linear(A, Wt)): A bf16 [samples][D][H][W][C], Wt bf16 [N][kt*kh*kw*C], zero padding k/2.
  * bias[N], rowvec[samples][N], residual/out_f32 fp32 [M][N], out_bf16 bf16 [M][N]; any of them may be NULL.
@@ -177,6 +188,11 @@ int pd_op_conv_gemm(const void* A_bf16, const void* Wt_bf16, int samples, int D,
  * from the same epilogue (the fusion the UNet uses for proj / ffn_2 / conv2 -> next pre-norm at width 256). */
 int pd_op_linear_residual_ln(const void* A_bf16, const void* Wt_bf16, int M, int K, const float* bias, float* x_inout,
                              const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream);
+/* Same for a row width N of 256 or 512. N = 512: the two CTAs that share a row tile form a thread-block cluster and
+ * exchange their partial row sums through distributed shared memory (the level-1 width of the UNet). */
+int pd_op_linear_residual_ln_n(const void* A_bf16, const void* Wt_bf16, int M, int K, int N, const float* bias,
+                               float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
+                               void* stream);
 /* Same launch with clock64() phase stamps of CTA (dbg_block, 0) written to stamps9[0..8] (device u64[16]; [9], [10] = %globaltimer ns at entry / exit):
  * entry, setup done, first operand tile landed, last MMA issued, accumulator ready, first epilogue chunk ready,
  * epilogue done, last bulk store drained, exit. Profiling aid (tools/gemm_phases.py). */

@@ -40,16 +40,21 @@ int pd_op_conv_gemm(const void* A, const void* Wt, int samples, int D, int H, in
     return rc;
 }
 
-int pd_op_linear_residual_ln(const void* A, const void* Wt, int M, int K, const float* bias, float* x_inout,
-                             const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream) {
+int pd_op_linear_residual_ln_n(const void* A, const void* Wt, int M, int K, int N, const float* bias, float* x_inout,
+                               const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream) {
     PD_TRY(gemm_init());
     GemmGeom g = GemmGeom::linear(M, K);
     GemmEpilogue e;
     e.bias = bias; e.residual = x_inout; e.out_f32 = x_inout;
     e.ln_gamma = ln_gamma; e.ln_beta = ln_beta; e.ln_out = static_cast<bf16*>(ln_out_bf16);
     GemmOp op;
-    PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), 256, e));
+    PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e));
     return gemm_launch(op, S(stream));
+}
+
+int pd_op_linear_residual_ln(const void* A, const void* Wt, int M, int K, const float* bias, float* x_inout,
+                             const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream) {
+    return pd_op_linear_residual_ln_n(A, Wt, M, K, 256, bias, x_inout, ln_gamma, ln_beta, ln_out_bf16, stream);
 }
 
 int pd_op_conv_gemm_phases(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
@@ -200,6 +205,13 @@ int pd_op_pack_linear_t(const float* w, void* out, int N, int K, void* stream) {
 int pd_op_pack_conv_dgrad(const float* w, void* out, int Co, int Ci, int taps, void* stream) {
     PD_TRY(gemm_init());
     return pack_conv_dgrad(w, static_cast<bf16*>(out), Co, Ci, taps, S(stream));
+}
+
+int pd_sevir_eval_update(const float* pred, const float* target, int64_t* counts, double* sums, int N, int T, int H,
+                         int W, int pool, const float* thresholds_host, int n_thresholds, void* stream) {
+    PD_TRY(gemm_init());
+    return sevir_eval_update(pred, target, reinterpret_cast<long long*>(counts), sums, N, T, H, W, pool, thresholds_host,
+                             n_thresholds, S(stream));
 }
 
 }  // extern "C"

@@ -23,7 +23,8 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kPipeBytes = STAGES * kStageBytes;
     static constexpr int kBarBytes = 512;
-    static constexpr int kLnBytes = 2 * BN * 4 + kEpiWarps * 32 * 8;  // fused-LN gamma/beta + row-sum exchange
+    // fused-LN gamma/beta + row-sum exchange inside the CTA + [128] row sums and one mbarrier written by the peer CTA
+    static constexpr int kLnBytes = 2 * BN * 4 + kEpiWarps * 32 * 8 + kGemmBlockM * 8 + 16;
     static_assert(kPipeBytes >= kEpiWarps * 2 * 4096, "epilogue slabs alias the pipeline stages");
     // barriers + tmem slot (512 B) then the per-CTA epilogue vector (bias + time-embedding row), BN floats
     static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + kBarBytes + BN * 4 + kLnBytes;
@@ -49,6 +50,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* ln_g = vec_s + BN;                                   // fused LayerNorm: gamma, beta, per-row partial sums
     float* ln_b = ln_g + BN;
     float2* ln_x = reinterpret_cast<float2*>(ln_b + BN);
+    float2* ln_peer = ln_x + kEpiWarps * 32;                    // [128]: the peer CTA's (sum, sumsq) of my rows
+    uint64_t* ln_bar = reinterpret_cast<uint64_t*>(ln_peer + kGemmBlockM);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -82,6 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         ptx::mbar_init(tmem_full_bar, 1);
         for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
+        ptx::mbar_init(ln_bar, kGemmBlockM);   // one remote arrive per row (cluster LayerNorm only)
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -98,6 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     ptx::tc_fence_before();
     __syncthreads();
+    // cluster LayerNorm: the peer's mbarrier must be initialised before anything is sent to it
+    if (p.ln_gamma && p.ln_cluster > 1) ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) PD_STAMP(1);
@@ -288,8 +294,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
                         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
                         const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
-                        const float mean = (ln_s1 + o.x) * (1.0f / BN);
-                        const float var = fmaxf((ln_s2 + o.y) * (1.0f / BN) - mean * mean, 0.f);
+                        float tot1 = ln_s1 + o.x, tot2 = ln_s2 + o.y, inv_n = 1.0f / BN;
+                        if (p.ln_cluster > 1) {
+                            // N = 2 x BN: send this CTA's row sums to the peer (DSMEM store + remote mbarrier arrive),
+                            // wait for the peer's; both CTAs add the two partials in the same order (own n-tile index
+                            // decides) so the statistics are bit-identical on both sides
+                            const uint32_t peer = ptx::cluster_ctarank() ^ 1u;
+                            if (half == 0) {
+                                ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_u32(&ln_peer[q * 32 + lane]), peer), tot1, tot2);
+                                ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(ln_bar), peer));
+                            }
+                            ptx::mbar_wait_cluster(ln_bar, 0);
+                            const float2 pr = ln_peer[q * 32 + lane];
+                            const bool first = (blockIdx.y & 1) == 0;
+                            tot1 = first ? tot1 + pr.x : pr.x + tot1;
+                            tot2 = first ? tot2 + pr.y : pr.y + tot2;
+                            inv_n = 1.0f / (2 * BN);
+                        }
+                        const float mean = tot1 * inv_n;
+                        const float var = fmaxf(tot2 * inv_n - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + p.ln_eps);
                         uint8_t* bslabs = smem + kEpiWarps * 4 * 4096 + e * (2 * 4096);   // 2 bf16 slabs per warp
 #pragma unroll
@@ -618,6 +641,23 @@ int launch_persistent(const GemmOp& op, cudaStream_t stream) {
 
 template <int BN, int STAGES>
 int launch_cfg(const GemmOp& op, cudaStream_t stream) {
+    if (op.cluster_y > 1) {   // the CTAs of one row tile (along N) form a thread-block cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(op.grid_x, op.grid_y, op.split_k);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg<BN, STAGES>::kSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1;
+        at[0].val.clusterDim.y = (unsigned)op.cluster_y;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        PD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res,
+                                   op.tmap_ln, op.p));
+        return PD_OK;
+    }
     gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y, op.split_k), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
         op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.tmap_ln, op.p);
     PD_LAUNCH_CHECK();
@@ -710,8 +750,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     int bn = force_block_n;
     const bool want_ln = e.ln_out != nullptr;
     if (want_ln) {
-        PD_CHECK(N == 256 && e.out_f32 && e.ln_gamma && e.ln_beta, PD_ERR_SHAPE,
-                 "gemm: the fused output LayerNorm needs N == 256 and an fp32 output (got N=%d)", N);
+        PD_CHECK((N == 256 || N == 512) && e.out_f32 && e.ln_gamma && e.ln_beta, PD_ERR_SHAPE,
+                 "gemm: the fused output LayerNorm needs N == 256 or 512 and an fp32 output (got N=%d)", N);
         bn = 256;
     }
     if (!bn) {
@@ -794,6 +834,8 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
                    e.act == ACT_NONE && !want_ln) ? 2 : 1;
     if (want_ln) op->stages = 4;   // the LN pass needs every chunk resident in its own slab (192 KB of stages)
     p.ln_gamma = want_ln ? e.ln_gamma : nullptr;
+    p.ln_cluster = want_ln ? N / 256 : 1;
+    op->cluster_y = p.ln_cluster;
     p.ln_beta = e.ln_beta;
     p.ln_eps = e.ln_eps;
     op->tmap_ln = op->tmap_out;

@@ -78,7 +78,8 @@ struct GemmEpilogue {
     bf16* out_bf16 = nullptr;         // [M][ldo]   (needs N % 64 == 0, no residual)
     int ldo = 0;                      // row stride of residual/out in elements (0 -> N)
     int act = ACT_NONE;               // applied after bias/rowvec, before the residual add
-    // Optional fused LayerNorm of the OUTPUT rows (needs out_f32, N == 256 so one CTA owns whole rows):
+    // Optional fused LayerNorm of the OUTPUT rows (needs out_f32; N == 256: one CTA owns whole rows; N == 512: the two
+    // CTAs of a row form a thread-block cluster and exchange their row sums through distributed shared memory):
     // ln_out[M][N] bf16 = LN(out row) * ln_gamma + ln_beta - the next layer's pre-norm, saving its kernel + a pass.
     const float* ln_gamma = nullptr;
     const float* ln_beta = nullptr;
@@ -103,6 +104,7 @@ struct GemmKernelParams {
     const float* ln_gamma;     // fused output LayerNorm (null = off); result goes through tmap_ln
     const float* ln_beta;
     float ln_eps;
+    int ln_cluster;            // CTAs along N that share a row (cluster size): 1, or 2 when the fused LN spans N = 512
     int* split_flags;          // per-tile handshake between the two split-K CTAs (self re-arming)
     unsigned long long* dbg;   // optional: 9 clock64() phase stamps of CTA (dbg_block, 0) - tools/gemm_phases.py
     int dbg_block;
@@ -112,7 +114,7 @@ struct GemmOp {
     CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_ln;
     GemmKernelParams p;
     int ldo = 0, out_rows = 0, out_samples = 0, out_N = 0;
-    int block_n = 0, stages = 0, split_k = 1, persistent = 0;
+    int block_n = 0, stages = 0, split_k = 1, persistent = 0, cluster_y = 1;
     unsigned grid_x = 0, grid_y = 0;
     size_t smem = 0;
     double flops = 0;

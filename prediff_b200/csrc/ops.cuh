@@ -100,6 +100,13 @@ int ka_pool_bwd(const float* qkv, const float* cw, const float* wsave, const flo
 int ka_tokens_bwd(const float* dtok, float* dout, int F, int R, int C, cudaStream_t st);
 int transpose_f32(const float* in, float* out, int R, int C, cudaStream_t st);
 
+// ---- evaluation (eval.cu) ----------------------------------------------------------------------------------
+// SEVIR skill-score contingency counts + error sums, accumulated on the device (evaluation.py:197-245).
+// pred / target fp32 [N][T][H][W] in [0,1]; counts int64 [n_thr][T][3] (hits, misses, false alarms) and sums double [2]
+// (sum sq err, sum abs err) are ADDED to; thresholds: host pointer, VIL units 0..255.
+int sevir_eval_update(const float* pred, const float* target, long long* counts, double* sums, int N, int T, int H, int W,
+                      int pool, const float* thresholds, int n_thr, cudaStream_t st);
+
 // ---- sampler (sampler.cu) ----------------------------------------------------------------------------------
 // One fused update of the latent (latent_diffusion.py:553-566,620-631 for DDPM; SURVEY section 8 S6 for DDIM):
 //   z0 = c[0] z - c[1] eps ;  z <- c[2] z0 + c[3] z + c[4] eps + c[5] noise - c[6] guide

@@ -316,7 +316,7 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         e.bias = r.conv2_b;
         e.residual = x;  // skip_connection = Identity (time_embed.py:169)
         e.out_f32 = x;
-        if (next && ln_fusable(lvl)) {  // LayerNorm of the first attention layer, computed on the finished rows
+        if (next && ln_fusable_conv(lvl)) {  // LayerNorm of the first attention layer, computed on the finished rows
             e.ln_gamma = next->a[0].ln_w;
             e.ln_beta = next->a[0].ln_b;
             e.ln_out = b.ln[lvl];
@@ -344,7 +344,8 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
         const bool fuse = ln_fusable(lvl);
         // x = x + proj(attn(LN(x)))   (cuboid_transformer.py:1151, 813-952). With C == 256 the LayerNorm was
         // produced by the epilogue of the GEMM that last wrote x (conv2 / previous ffn_2).
-        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
+        const bool ln_ready = fuse && (i > 0 || ln_fusable_conv(lvl));
+        if (!ln_ready) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
         {
             GemmEpilogue e;
             e.out_bf16 = qkv;

@@ -58,7 +58,10 @@ private:
     int add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
                      const StackW* next);
     int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s);
-    bool ln_fusable(int lvl) const { return (lvl ? C1 : C0) == 256; }
+    // The LayerNorm that follows a GEMM is computed in that GEMM's epilogue when a CTA (width 256) or a 2-CTA cluster
+    // (width 512) owns whole rows; the resblock's conv2 only when it is not split-K (27 * C / 64 < 128 k-blocks).
+    bool ln_fusable(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 || c == 512; }
+    bool ln_fusable_conv(int lvl) const { const int c = lvl ? C1 : C0; return c == 256; }
     int num_gn_slots() const;
     template <class A>
     void carve(A& ar, int B, Bufs* b) const;

@@ -169,6 +169,68 @@ def gen_ka():
     save("ka_full", t=t, pred=pred, grad=g, z_aligned_step900=z_al)
 
 
+def skill_inputs(seed=6161, N=3, T=6, H=32, W=32):
+    """Smooth-ish synthetic forecast / target pairs in [0,1] with values on both sides of every threshold, a few
+    exact-threshold pixels (k/255) and a few NaNs."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    target = rng.random((N, T, H, W), dtype=np.float32) ** 2
+    pred = np.clip(target + 0.15 * rng.standard_normal((N, T, H, W), dtype=np.float32), 0.0, 1.0).astype(np.float32)
+    for i, th in enumerate((16, 74, 133, 160, 181, 219)):
+        target[0, i % T, i, :8] = np.float32(th) / np.float32(255.0)
+        pred[1, i % T, :8, i] = np.float32(th) / np.float32(255.0)
+    pred[2, 1, 3, 4] = np.nan
+    target[2, 2, 5, 6] = np.nan
+    target[0, 0, 30, 30] = np.nan
+    pred[0, 0, 30, 30] = np.nan
+    return torch.from_numpy(pred), torch.from_numpy(target)
+
+
+def gen_skill():
+    """SEVIRSkillScore of the unmodified reference (datasets/sevir/evaluation.py). `torchmetrics` and `h5py` are absent
+    from the image; the metric only uses torchmetrics.Metric as a state container (add_state / reset), so an inert
+    stand-in with exactly that is installed; all arithmetic (update / compute) is the reference's own."""
+    import torch.nn as nn
+
+    class Metric(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+            self._defaults = {}
+
+        def add_state(self, name, default, dist_reduce_fx=None):
+            self._defaults[name] = default.clone()
+            setattr(self, name, default.clone())
+
+        def reset(self):
+            for k, v in self._defaults.items():
+                setattr(self, k, v.clone())
+
+    for name, attrs in (("torchmetrics", {"Metric": Metric}), ("h5py", {})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+    from prediff.datasets.sevir.evaluation import SEVIRSkillScore
+    pred, target = skill_inputs()
+    out = {}
+    thr = (16, 74, 133, 160, 181, 219)
+    for tag, pre in (("p1", "sevir"), ("p4", "sevir_pool4")):
+        for mode in ("0", "1", "2"):
+            sc = SEVIRSkillScore(layout="NTHWC", mode=mode, seq_len=6, preprocess_type=pre, threshold_list=thr,
+                                 metrics_list=("csi", "bias", "sucr", "pod"), eps=1e-4)
+            sc.update(pred.unsqueeze(-1), target.unsqueeze(-1))
+            sc.update(pred.flip(0).unsqueeze(-1), target.unsqueeze(-1))   # a second batch accumulates
+            out[f"{tag}_m{mode}_hits"] = sc.hits
+            out[f"{tag}_m{mode}_misses"] = sc.misses
+            out[f"{tag}_m{mode}_fas"] = sc.fas
+            res = sc.compute()
+            for m in ("csi", "bias", "sucr", "pod"):
+                out[f"{tag}_m{mode}_{m}"] = np.stack([np.asarray(res[t][m], dtype=np.float64) for t in thr])
+                out[f"{tag}_m{mode}_avg_{m}"] = np.asarray(res["avg"][m], dtype=np.float64)
+    fin = torch.nan_to_num(pred) - torch.nan_to_num(target)
+    out["mse_nonan"] = (fin.double() ** 2).mean()
+    out["mae_nonan"] = fin.double().abs().mean()
+    save("skill", **out)
+
+
 def save(name, **arrs):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
@@ -306,5 +368,7 @@ if __name__ == "__main__":
         gen_vae("full", FULL_V, 1)
     if "ka" in todo:
         gen_ka()
+    if "skill" in todo:
+        gen_skill()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

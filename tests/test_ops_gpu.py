@@ -84,9 +84,10 @@ def test_gemm_persistent_bf16(M, K, N, act):
     assert (outb.float() - ref.bfloat16().float()).abs().max().item() <= 2 * ref.abs().max().item() * 2 ** -8
 
 
-@pytest.mark.parametrize("M,K", [(3328, 256), (1000, 1024), (13312, 256)])
-def test_gemm_residual_fused_layernorm(M, K):
-    N = 256
+@pytest.mark.parametrize("M,K,N", [(3328, 256, 256), (1000, 1024, 256), (13312, 256, 256), (3328, 512, 512),
+                                   (832, 2048, 512), (1000, 512, 512)])
+def test_gemm_residual_fused_layernorm(M, K, N):
+    """N = 512: LayerNorm statistics exchanged between the two CTAs of a cluster through DSMEM."""
     a = _randn(M, K, seed=1).bfloat16()
     w = _randn(N, K, seed=2, scale=K ** -0.5).bfloat16()
     bias = _randn(N, seed=3)
@@ -96,8 +97,8 @@ def test_gemm_residual_fused_layernorm(M, K):
     ref_x = a.float() @ w.float().t() + bias + x
     ref_ln = F.layer_norm(ref_x, (N,), gamma, beta, 1e-5)
     ln = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
-    _sync_check(L.lib().pd_op_linear_residual_ln(L.ptr(a), L.ptr(w), M, K, L.ptr(bias), L.ptr(x), L.ptr(gamma),
-                                                 L.ptr(beta), L.ptr(ln), L.stream_ptr()))
+    _sync_check(L.lib().pd_op_linear_residual_ln_n(L.ptr(a), L.ptr(w), M, K, N, L.ptr(bias), L.ptr(x), L.ptr(gamma),
+                                                   L.ptr(beta), L.ptr(ln), L.stream_ptr()))
     assert rel_err(x, ref_x) < 2e-5
     assert rel_err(ln, ref_ln) < 6e-3
 
