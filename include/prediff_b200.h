@@ -221,6 +221,18 @@ int pd_op_parity_split_cast(const float* x, void* y_bf16, int F, int H, int W, i
 int pd_op_conv_s2_gemm(const void* planes_bf16, const void* Wt_bf16, int F, int Ho, int Wo, int C, int N,
                        const float* bias, float* out_f32, void* stream);
 
+/* Fused PositionwiseFFN at width 256 / hidden 1024 (cuboid_transformer.py:182-208 after its pre-norm):
+ * x[M][256] += W2 GELU(W1 ln_in + b1) + b2 in one kernel (the hidden activation never leaves the SM), and, if ln_gamma
+ * is given, ln_out[M][256] (bf16) = LayerNorm(new x row) * ln_gamma + ln_beta. W1 bf16 [1024][256], W2 bf16 [256][1024]. */
+int pd_op_ffn_fused(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
+                    float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, int M, void* stream);
+/* Same launch with clock64() stamps of CTA 0 in stamps32 (device u64[32]): [0] entry, [1] MMA warp ready, [2] A tile
+ * landed, [3+c] GEMM-2 of chunk c issued, [12+2c] / [13+2c] GELU epilogue of chunk c begins / ends, [28] accumulator 2
+ * complete, [29] final epilogue done, [30] exit. Profiling aid (tools/ffn_phases.py). */
+int pd_op_ffn_fused_phases(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                           const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
+                           int M, unsigned long long* stamps32, void* stream);
+
 /* ---- input-gradient kernels of the knowledge-alignment guidance (csrc/backward.cu); used by the parity tests --- */
 /* GroupNorm(+SiLU) backward: x, dy fp32 [S][R][C] -> dx_io fp32 (+= if accumulate) and/or dx_bf16 (either may be NULL) */
 int pd_op_group_norm_bwd(const float* x, const float* dy, const float* gamma, const float* beta, float* dx_io,

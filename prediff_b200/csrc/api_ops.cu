@@ -214,4 +214,21 @@ int pd_sevir_eval_update(const float* pred, const float* target, int64_t* counts
                              n_thresholds, S(stream));
 }
 
+int pd_op_ffn_fused_phases(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                           const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
+                           int M, unsigned long long* stamps32, void* stream) {
+    PD_TRY(gemm_init());
+    FfnFusedOp op;
+    PD_TRY(ffn_fused_make(&op, static_cast<const bf16*>(ln_in_bf16), M, static_cast<const bf16*>(W1_bf16), b1,
+                          static_cast<const bf16*>(W2_bf16), b2, x_inout, ln_gamma, ln_beta,
+                          static_cast<bf16*>(ln_out_bf16), 1e-5f, stamps32));
+    return ffn_fused_launch(op, S(stream));
+}
+
+int pd_op_ffn_fused(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
+                    float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, int M, void* stream) {
+    return pd_op_ffn_fused_phases(ln_in_bf16, W1_bf16, b1, W2_bf16, b2, x_inout, ln_gamma, ln_beta, ln_out_bf16, M,
+                                  nullptr, stream);
+}
+
 }  // extern "C"

@@ -1,0 +1,407 @@
+// Fused PositionwiseFFN for width-256 levels: x <- x + W2 GELU(W1 ln + b1) + b2 (and, optionally, the LayerNorm that
+// follows) in ONE kernel per 128-row tile - the 128 x 1024 hidden activation never leaves the SM.
+// Reference: PositionwiseFFN.forward (src/prediff/models/cuboid_transformer/cuboid_transformer.py:182-208), pre-norm
+// input `ln` produced by the preceding epilogue. Replaces the FFN-1 GEMM (bf16 `mid` round trip through HBM/L2:
+// 27 MB written + read per call at batch 4) and the FFN-2 GEMM.
+//
+//   warp 0    : TMA producer - 3-stage ring of 48 KB stages: GEMM-1 stages carry an A k-block (128 x 64) + a W1 tile
+//               (256 hidden rows x 64), GEMM-2 stages a W2 tile (256 output rows x 64)
+//   warp 1    : one lane issues tcgen05.mma 128 x 256 x 16 (an N = 128 MMA costs the same ~128 cycles, measured):
+//                 G1(c):  acc1  = ln . W1[c]^T                       c = 0..3, 256 hidden columns per chunk
+//                 G2h(c): acc2 += gelu_c[:, 128h : 128h+128] . W2[:, ...]^T   (two K halves, each as soon as it is ready)
+//               order G1(0) | G1(c+1) G2h0(c) G2h1(c) | ... : GEMM-1 of the next chunk and the first half of GEMM-2 run
+//               under the second half of this chunk's GELU epilogue
+//   warps 2-9 : E1(c), two phases of 128 hidden columns: acc1 (TMEM) -> + b1 -> GELU -> bf16 -> 128B-swizzled K-major
+//               smem tiles = the A operand of G2(c); acc1 is handed back right after the second phase's TMEM loads;
+//               final: acc2 -> + b2 + residual (TMA-loaded) -> x (TMA store) -> fused LayerNorm -> bf16 (TMA store)
+// TMEM: acc1 (256 columns) + acc2 (256 columns) = 512 columns.
+#include "gemm.cuh"
+#include "ops.cuh"
+#include "ptx.cuh"
+
+namespace pd {
+namespace {
+
+constexpr int kC = 256;            // model width (K of GEMM-1, N of GEMM-2)
+constexpr int kHid = 1024;         // hidden width
+constexpr int kChunk = 256;        // hidden columns per chunk
+constexpr int kNumChunks = kHid / kChunk;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kTileA = 128 * 64 * 2;         // 16 KB: 128 rows x 64 bf16
+constexpr int kTileW = 256 * 64 * 2;         // 32 KB: 256 rows x 64 bf16
+constexpr int kStage = kTileA + kTileW;      // 48 KB
+constexpr int kStages = 3;
+constexpr int kRingBytes = kStages * kStage; // 144 KB
+constexpr int kMidBytes = 4 * kTileA;        // 64 KB: four k-blocks of the GELU'd chunk
+constexpr int kPipeBytes = kRingBytes + kMidBytes;   // 208 KB
+constexpr int kBarBytes = 1024;
+constexpr int kSmem = kPipeBytes + 1024 + kBarBytes + kHid * 4 + kC * 4 + 2 * kC * 4 + kEpiWarps * 32 * 8;
+static_assert(kRingBytes >= kEpiWarps * 4 * 4096, "fp32 epilogue slabs alias the ring");
+static_assert(kMidBytes >= kEpiWarps * 2 * 4096, "bf16 LayerNorm slabs alias mid");
+
+struct FfnParams {
+    const float* b1;
+    const float* b2;
+    const float* ln_gamma;   // null: no fused LayerNorm output
+    const float* ln_beta;
+    float ln_eps;
+    int M;
+    unsigned long long* dbg;   // optional clock64() stamps of CTA 0 (tools/ffn_phases.py): see PD_FSTAMP sites
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
+                 const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x,
+                 const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ FfnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sRing = smem;
+    uint8_t* sMid = smem + kRingBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes);
+    uint64_t* w_full = bars;                 // [kStages]
+    uint64_t* w_empty = w_full + kStages;    // [kStages]
+    uint64_t* acc1_full = w_empty + kStages; // [1]
+    uint64_t* acc1_empty = acc1_full + 1;    // [1]
+    uint64_t* mid_full = acc1_empty + 1;     // [2] (K halves)
+    uint64_t* mid_empty = mid_full + 2;      // [2]
+    uint64_t* acc2_full = mid_empty + 2;     // [1]
+    uint64_t* res_bar = acc2_full + 1;       // [kEpiWarps][4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * kEpiWarps);
+    float* b1_s = reinterpret_cast<float*>(smem + kPipeBytes + kBarBytes);   // [1024]
+    float* b2_s = b1_s + kHid;                                               // [256]
+    float* ln_g = b2_s + kC;
+    float* ln_b = ln_g + kC;
+    float2* ln_x = reinterpret_cast<float2*>(ln_b + kC);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row_tile = blockIdx.x * 128;
+    unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+#define PD_FSTAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) PD_FSTAMP(0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(&w_full[s], 1);
+            ptx::mbar_init(&w_empty[s], 1);
+        }
+        ptx::mbar_init(acc1_full, 1);
+        ptx::mbar_init(acc1_empty, kEpiWarps);
+        for (int h = 0; h < 2; ++h) {
+            ptx::mbar_init(&mid_full[h], kEpiWarps);
+            ptx::mbar_init(&mid_empty[h], 1);
+        }
+        ptx::mbar_init(acc2_full, 1);
+        for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_w1);
+        ptx::prefetch_tmap(&tmap_w2);
+        ptx::prefetch_tmap(&tmap_x);
+        if (p.ln_gamma) ptx::prefetch_tmap(&tmap_ln);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            auto g1 = [&](int c) {   // 4 stages: A k-block + W1[c] tile
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % kStages;
+                    ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
+                    uint8_t* st = sRing + s * kStage;
+                    ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
+                    ptx::tma_load_3d(st, &tmap_a, &w_full[s], kb * 64, row_tile, 0);
+                    ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, c * kChunk);
+                }
+            };
+            auto g2h = [&](int c, int h) {   // 2 stages: W2 tiles for hidden columns c*256 + h*128 + {0, 64}
+                for (int kb = 0; kb < 2; ++kb, ++it) {
+                    const int s = it % kStages;
+                    ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
+                    uint8_t* st = sRing + s * kStage;
+                    ptx::mbar_arrive_expect_tx(&w_full[s], kTileW);
+                    ptx::tma_load_2d(st + kTileA, &tmap_w2, &w_full[s], c * kChunk + h * 128 + kb * 64, 0);
+                }
+            };
+            g1(0);
+            for (int c = 0; c < kNumChunks; ++c) {
+                if (c + 1 < kNumChunks) g1(c + 1);
+                g2h(c, 0);
+                g2h(c, 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256);
+            int it = 0;
+            auto g1 = [&](int c) {
+                ptx::mbar_wait(acc1_empty, (c & 1) ^ 1);              // E1(c - 1) has read the accumulator out
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % kStages;
+                    ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sRing + s * kStage);
+                    const uint32_t b_addr = a_addr + kTileA;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_addr + k * 32),
+                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&w_empty[s]);
+                }
+                ptx::umma_commit(acc1_full);
+            };
+            auto g2h = [&](int c, int h) {
+                ptx::mbar_wait(&mid_full[h], c & 1);                  // E1(c) phase h has written its two k-blocks
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < 2; ++kb, ++it) {
+                    const int s = it % kStages;
+                    ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sMid + (h * 2 + kb) * kTileA);
+                    const uint32_t b_addr = ptx::smem_u32(sRing + s * kStage + kTileA);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_base + 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
+                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (c | h | kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&w_empty[s]);
+                }
+                ptx::umma_commit(&mid_empty[h]);
+            };
+            PD_FSTAMP(1);
+            g1(0);
+            PD_FSTAMP(2);
+            for (int c = 0; c < kNumChunks; ++c) {
+                if (c + 1 < kNumChunks) g1(c + 1);   // its operands were prefetched while this warp waited for E1(c)
+                g2h(c, 0);
+                g2h(c, 1);
+                PD_FSTAMP(3 + c);          // G2(c) issued
+            }
+            ptx::umma_commit(acc2_full);
+        }
+    } else {
+        const int e = warp - 2;
+        const int q = warp & 3;          // TMEM lane quarter
+        const int half = e >> 2;         // column half
+        const int et = threadIdx.x - 64;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        for (int i = et; i < kHid; i += 32 * kEpiWarps) b1_s[i] = __ldg(p.b1 + i);
+        for (int i = et; i < kC; i += 32 * kEpiWarps) {
+            b2_s[i] = __ldg(p.b2 + i);
+            if (p.ln_gamma) {
+                ln_g[i] = __ldg(p.ln_gamma + i);
+                ln_b[i] = __ldg(p.ln_beta + i);
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        // ---- E1: GELU chunks -> swizzled A tiles of GEMM-2 ----
+#pragma unroll 1
+        for (int c = 0; c < kNumChunks; ++c) {
+            ptx::mbar_wait(acc1_full, c & 1);
+            ptx::tc_fence_after();
+            if (et == 0) PD_FSTAMP(12 + 2 * c);   // E1(c) begins
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {          // phase h: hidden columns [128 h, 128 h + 128) of the chunk
+                const int col = h * 128 + half * 64;   // this warp's 64 columns = k-block (2 h + half) of mid
+                uint32_t v0[32], v1[32];
+                ptx::tmem_ld_32x32(t_lane + col, v0);
+                ptx::tmem_ld_32x32(t_lane + col + 32, v1);
+                ptx::tmem_ld_wait();
+                if (h == 1) {                      // every TMEM read of this chunk is done: G1(c + 1) may overwrite acc1
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(acc1_empty);
+                }
+                ptx::mbar_wait(&mid_empty[h], (c & 1) ^ 1);           // G2h(c - 1) no longer reads these k-blocks
+                uint8_t* my_row = sMid + (h * 2 + half) * kTileA + (q * 32 + lane) * 128;
+                const float* bias = b1_s + c * kChunk + col;
+#pragma unroll
+                for (int cell = 0; cell < 8; ++cell) {
+                    float a[8];
+                    const float4 bv0 = *reinterpret_cast<const float4*>(bias + cell * 8);
+                    const float4 bv1 = *reinterpret_cast<const float4*>(bias + cell * 8 + 4);
+                    const float bb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t raw = cell < 4 ? v0[cell * 8 + k] : v1[(cell - 4) * 8 + k];
+                        a[k] = gelu_fast(__uint_as_float(raw) + bb[k]);
+                    }
+                    *reinterpret_cast<uint4*>(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4)) =
+                        make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
+                                   pack_bf16x2(a[6], a[7]));
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&mid_full[h]);
+            }
+            if (et == 0) PD_FSTAMP(13 + 2 * c);   // E1(c) done
+        }
+        // ---- final epilogue: acc2 + b2 + residual -> x (fp32, TMA store), fused LayerNorm -> bf16 ----
+        ptx::mbar_wait(acc2_full, 0);
+        ptx::tc_fence_after();
+        if (et == 0) PD_FSTAMP(28);               // accumulator 2 complete
+        uint8_t* slabs = smem + e * (4 * 4096);                    // aliases the ring (all MMAs have completed)
+        uint64_t* my_bar = res_bar + 4 * e;
+        const int row0 = row_tile + q * 32;
+        const int c_begin = half * 4;
+        if (lane == 0) {
+            for (int idx = 0; idx < 4; ++idx) {
+                ptx::mbar_arrive_expect_tx(&my_bar[idx], 4096);
+                ptx::tma_load_3d(slabs + idx * 4096, &tmap_x, &my_bar[idx], (c_begin + idx) * 32, row0, 0);
+            }
+        }
+        float ln_s1 = 0.f, ln_s2 = 0.f;
+#pragma unroll 1
+        for (int idx = 0; idx < 4; ++idx) {
+            const int c = c_begin + idx;
+            uint8_t* slab = slabs + idx * 4096;
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_lane + 256 + c * 32, v);
+            ptx::mbar_wait(&my_bar[idx], 0);
+            ptx::tmem_ld_wait();
+            uint8_t* my_row = slab + lane * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(b2_s + c * 32 + 4 * i);
+                float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                const float4 r = *cell;
+                float4 a = make_float4(__uint_as_float(v[4 * i]) + bb.x + r.x, __uint_as_float(v[4 * i + 1]) + bb.y + r.y,
+                                       __uint_as_float(v[4 * i + 2]) + bb.z + r.z, __uint_as_float(v[4 * i + 3]) + bb.w + r.w);
+                *cell = a;
+                ln_s1 += (a.x + a.y) + (a.z + a.w);
+                ln_s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_3d(&tmap_x, slab, c * 32, row0, 0);
+                ptx::bulk_commit();
+            }
+        }
+        if (p.ln_gamma) {
+            ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
+            const float mean = (ln_s1 + o.x) * (1.0f / kC);
+            const float var = fmaxf((ln_s2 + o.y) * (1.0f / kC) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + p.ln_eps);
+            uint8_t* bslabs = sMid + e * (2 * 4096);               // aliases mid
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint8_t* brow = bslabs + j * 4096 + lane * 128;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const uint8_t* frow = slabs + (2 * j + cc) * 4096 + lane * 128;
+                    const int colbase = (c_begin + 2 * j + cc) * 32;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 a0 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k) ^ sw) << 4));
+                        const float4 a1 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k + 1) ^ sw) << 4));
+                        const float4 g0 = *reinterpret_cast<const float4*>(ln_g + colbase + 8 * k);
+                        const float4 g1 = *reinterpret_cast<const float4*>(ln_g + colbase + 8 * k + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(ln_b + colbase + 8 * k);
+                        const float4 b1v = *reinterpret_cast<const float4*>(ln_b + colbase + 8 * k + 4);
+                        uint4 pk;
+                        pk.x = pack_bf16x2(fmaf((a0.x - mean) * rstd, g0.x, b0.x), fmaf((a0.y - mean) * rstd, g0.y, b0.y));
+                        pk.y = pack_bf16x2(fmaf((a0.z - mean) * rstd, g0.z, b0.z), fmaf((a0.w - mean) * rstd, g0.w, b0.w));
+                        pk.z = pack_bf16x2(fmaf((a1.x - mean) * rstd, g1.x, b1v.x), fmaf((a1.y - mean) * rstd, g1.y, b1v.y));
+                        pk.w = pack_bf16x2(fmaf((a1.z - mean) * rstd, g1.z, b1v.z), fmaf((a1.w - mean) * rstd, g1.w, b1v.w));
+                        *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(cc * 4 + k) ^ sw) << 4)) = pk;
+                    }
+                }
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_3d(&tmap_ln, bslabs, (c_begin + 0) * 32, row0, 0);
+                ptx::tma_store_3d(&tmap_ln, bslabs + 4096, (c_begin + 2) * 32, row0, 0);
+                ptx::bulk_commit();
+            }
+        }
+        if (lane == 0) ptx::bulk_wait_read<0>();   // smem must stay valid until the last bulk store has read it
+        __syncwarp();
+        if (et == 0) PD_FSTAMP(29);               // final epilogue done
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    if (threadIdx.x == 0) PD_FSTAMP(30);
+#undef PD_FSTAMP
+}
+
+}  // namespace
+
+struct FfnFusedOpImpl {
+    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln;
+    FfnParams p;
+    int tiles;
+};
+static_assert(sizeof(FfnFusedOpImpl) <= sizeof(FfnFusedOp), "FfnFusedOp storage too small");
+
+int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
+                   const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out,
+                   float ln_eps, unsigned long long* dbg) {
+    FfnFusedOpImpl* op = reinterpret_cast<FfnFusedOpImpl*>(op_);
+    PD_TRY(gemm_init());
+    PD_CHECK(ln_in && w1 && b1 && w2 && b2 && x_inout && M > 0, PD_ERR_ARG, "ffn_fused: null argument");
+    PD_CHECK((ln_gamma != nullptr) == (ln_out != nullptr), PD_ERR_ARG, "ffn_fused: ln_gamma and ln_out go together");
+    static bool attr_set = false;
+    if (!attr_set) {
+        PD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_set = true;
+    }
+    {   // A: ln [M][256] bf16, boxes of 128 rows x 64 columns
+        const uint64_t dims[3] = {kC, (uint64_t)M, 1}, st[2] = {kC * 2, (uint64_t)kC * 2 * M};
+        const uint32_t box[3] = {64, 128, 1};
+        PD_TRY(tmap_encode_sw128(&op->tmap_a, true, 3, ln_in, dims, st, box));
+    }
+    {   // W1 [1024][256] (K-major), W2 [256][1024]: boxes of 256 rows x 64 K
+        const uint64_t d1[2] = {kC, kHid}, s1[1] = {kC * 2};
+        const uint64_t d2[2] = {kHid, kC}, s2[1] = {kHid * 2};
+        const uint32_t box[2] = {64, 256};
+        PD_TRY(tmap_encode_sw128(&op->tmap_w1, true, 2, w1, d1, s1, box));
+        PD_TRY(tmap_encode_sw128(&op->tmap_w2, true, 2, w2, d2, s2, box));
+    }
+    {   // x [M][256] fp32 (residual in, result out): 32-row x 32-column boxes
+        const uint64_t dims[3] = {kC, (uint64_t)M, 1}, st[2] = {kC * 4, (uint64_t)kC * 4 * M};
+        const uint32_t box[3] = {32, 32, 1};
+        PD_TRY(tmap_encode_sw128(&op->tmap_x, false, 3, x_inout, dims, st, box));
+    }
+    op->tmap_ln = op->tmap_x;
+    if (ln_out) {
+        const uint64_t dims[3] = {kC, (uint64_t)M, 1}, st[2] = {kC * 2, (uint64_t)kC * 2 * M};
+        const uint32_t box[3] = {64, 32, 1};
+        PD_TRY(tmap_encode_sw128(&op->tmap_ln, true, 3, ln_out, dims, st, box));
+    }
+    op->p.b1 = b1;
+    op->p.b2 = b2;
+    op->p.ln_gamma = ln_gamma;
+    op->p.ln_beta = ln_beta;
+    op->p.ln_eps = ln_eps;
+    op->p.M = M;
+    op->p.dbg = dbg;
+    op->tiles = ceil_div(M, 128);
+    return PD_OK;
+}
+
+int ffn_fused_launch(const FfnFusedOp& op_, cudaStream_t st) {
+    const FfnFusedOpImpl& op = reinterpret_cast<const FfnFusedOpImpl&>(op_);
+    ffn_fused_kernel<<<op.tiles, kThreads, kSmem, st>>>(op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.p);
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
+
+}  // namespace pd

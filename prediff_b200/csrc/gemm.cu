@@ -691,6 +691,23 @@ int gemm_init() {
     return PD_OK;
 }
 
+// cuTensorMapEncodeTiled with the settings every kernel here uses (128-byte swizzle, no OOB fill); for other
+// translation units (ffn_fused.cu) that build their own tensor maps.
+int tmap_encode_sw128(CUtensorMap* m, bool is_bf16, int rank, const void* ptr, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
+    PD_TRY(gemm_init());
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+    PD_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, PD_ERR_ARG, "tensor map: pointer must be 16-byte aligned");
+    CUresult r = g_encode(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                          const_cast<void*>(ptr), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return PD_OK;
+}
+
 int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split) {
     const int out_D = g.out_D ? g.out_D : g.D;
     const int num_k = g.ntaps * (g.C / kGemmBlockK);

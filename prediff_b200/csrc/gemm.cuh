@@ -128,6 +128,8 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream);
 int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
 // Number of ints gemm_make may need in GemmEpilogue::split_flags for this geometry (0 if it will not split).
 int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split = 0);
+int tmap_encode_sw128(CUtensorMap* m, bool is_bf16, int rank, const void* ptr, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
 int gemm_init();  // resolves the driver entry point + raises the dynamic smem limits (idempotent)
 
 }  // namespace pd

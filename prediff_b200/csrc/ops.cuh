@@ -100,6 +100,18 @@ int ka_pool_bwd(const float* qkv, const float* cw, const float* wsave, const flo
 int ka_tokens_bwd(const float* dtok, float* dout, int F, int R, int C, cudaStream_t st);
 int transpose_f32(const float* in, float* out, int R, int C, cudaStream_t st);
 
+// ---- fused FFN (ffn_fused.cu) ---------------------------------------------------------------------------------
+// x[M][256] += W2 GELU(W1 ln + b1) + b2 in one kernel per 128-row tile (hidden width 1024 stays on the SM), optionally
+// followed by the fused LayerNorm of the new rows -> ln_out (bf16). ln_in bf16 [M][256]; W1 bf16 [1024][256]; W2 bf16
+// [256][1024]. Reference: PositionwiseFFN.forward, cuboid_transformer.py:182-208.
+struct FfnFusedOp {
+    alignas(64) unsigned char storage[1024];
+};
+int ffn_fused_make(FfnFusedOp* op, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
+                   const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out,
+                   float ln_eps, unsigned long long* dbg = nullptr);
+int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
+
 // ---- evaluation (eval.cu) ----------------------------------------------------------------------------------
 // SEVIR skill-score contingency counts + error sums, accumulated on the device (evaluation.py:197-245).
 // pred / target fp32 [N][T][H][W] in [0,1]; counts int64 [n_thr][T][3] (hits, misses, false alarms) and sums double [2]

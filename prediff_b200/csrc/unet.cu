@@ -8,6 +8,7 @@
 // lives in one buffer per level; every tensor a GEMM consumes is written as bf16 by its producer.
 #include "unet.cuh"
 #include <cstdarg>
+#include <cstdlib>
 
 namespace pd {
 
@@ -371,6 +372,17 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
         }
         // x = x + W2 gelu(W1 LN(x) + b1) + b2   (cuboid_transformer.py:195-205)
         if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
+        if (C == 256 && getenv("PD_NO_FFN_FUSION") == nullptr) {
+            // width 256: both GEMMs + GELU (+ the next layer's LayerNorm) in one kernel; `mid` never leaves the SM
+            FfnFusedOp op;
+            const bool next_ln = i < 2;   // pre-norm of the next attention layer of this stack
+            PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
+                                  next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f));
+            pl.gemm_flops += 2.0 * 2.0 * (double)P * C * 4 * C;
+            pl.n_gemm += 1;
+            pl.add([op](cudaStream_t st) { return ffn_fused_launch(op, st); }, STEP_GEMM, "ffn_fused");
+            continue;
+        }
         {
             GemmEpilogue e;
             e.bias = fw.b1;

@@ -103,6 +103,37 @@ def test_gemm_residual_fused_layernorm(M, K, N):
     assert rel_err(ln, ref_ln) < 6e-3
 
 
+@pytest.mark.parametrize("M,with_ln", [(13312, True), (3328, True), (1000, False), (128, True)])
+def test_ffn_fused(M, with_ln):
+    """One kernel: x += W2 gelu(W1 ln + b1) + b2 (+ LayerNorm of the result); hidden activation rounded to bf16
+    between the two GEMMs exactly like the two-kernel path."""
+    C, Hd = 256, 1024
+    ln_in = _randn(M, C, seed=1).bfloat16()
+    w1 = _randn(Hd, C, seed=2, scale=C ** -0.5).bfloat16()
+    w2 = _randn(C, Hd, seed=3, scale=Hd ** -0.5).bfloat16()
+    b1, b2 = 0.1 * _randn(Hd, seed=4), 0.1 * _randn(C, seed=5)
+    x = _randn(M, C, seed=6) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * _randn(C, seed=7), 0.1 * _randn(C, seed=8)
+    mid = F.gelu(ln_in.float() @ w1.float().t() + b1).bfloat16().float()
+    ref_x = x + mid @ w2.float().t() + b2
+    ref_ln = F.layer_norm(ref_x, (C,), gamma, beta, 1e-5)
+    xo = x.clone()
+    ln = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_ffn_fused(L.ptr(ln_in), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(xo),
+                                        L.ptr(gamma) if with_ln else None, L.ptr(beta) if with_ln else None,
+                                        L.ptr(ln) if with_ln else None, M, L.stream_ptr()))
+    # bf16 rounding of `mid` can flip at ties between the two implementations: tolerance of a few bf16 ulps of mid
+    assert rel_err(xo, ref_x) < 2e-3
+    if with_ln:
+        assert rel_err(ln, ref_ln) < 8e-3
+    # determinism
+    xo2 = x.clone()
+    _sync_check(L.lib().pd_op_ffn_fused(L.ptr(ln_in), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(xo2),
+                                        L.ptr(gamma) if with_ln else None, L.ptr(beta) if with_ln else None,
+                                        L.ptr(ln) if with_ln else None, M, L.stream_ptr()))
+    assert torch.equal(xo, xo2)
+
+
 def test_gemm_plain_no_epilogue_and_rowvec():
     M, K, N, samples = 512, 128, 128, 4
     a = _randn(samples * M, K, seed=5).bfloat16()
