@@ -1,5 +1,6 @@
 // extern "C" kernel-level entry points (include/prediff_b200.h): the same launchers the model programs use,
 // exposed so the parity tests can drive every kernel in isolation through the C ABI.
+#include <cstdlib>
 #include "../../include/prediff_b200.h"
 #include "gemm.cuh"
 #include "ops.cuh"
@@ -66,6 +67,14 @@ int pd_op_conv_gemm_phases(const void* A, const void* Wt, int samples, int D, in
     e.bias = bias; e.residual = residual; e.out_f32 = out_f32;
     e.out_bf16 = static_cast<bf16*>(out_bf16); e.act = act;
     e.dbg = stamps9; e.dbg_block = dbg_block;
+    if (getenv("PD_PHASE_SPLIT")) {   // profiling aid: let the long-K convs split like they do inside the UNet plan
+        static int* flags = nullptr;
+        if (!flags) {
+            PD_CUDA(cudaMalloc(reinterpret_cast<void**>(&flags), 8192 * sizeof(int)));
+            PD_CUDA(cudaMemset(flags, 0, 8192 * sizeof(int)));
+        }
+        if (gemm_split_flags_needed(g, N) <= 8192) e.split_flags = flags;
+    }
     GemmOp op;
     PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e, block_n));
     return gemm_launch(op, S(stream));

@@ -55,7 +55,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    unsigned long long* dbg = (p.dbg && blockIdx.x == p.dbg_block && blockIdx.y == 0) ? p.dbg : nullptr;
+    // dbg_block = x + 1000 * z selects the stamped CTA (y = 0)
+    unsigned long long* dbg = (p.dbg && (int)blockIdx.x == p.dbg_block % 1000 && blockIdx.y == 0 &&
+                               (int)blockIdx.z == p.dbg_block / 1000) ? p.dbg : nullptr;
 #define PD_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
     if (threadIdx.x == 0) {
         PD_STAMP(0);

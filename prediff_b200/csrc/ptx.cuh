@@ -76,6 +76,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t cta)
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
 }
+__device__ __forceinline__ void st_cluster_f64(uint32_t cluster_addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// contiguous global -> shared bulk copy (TMA, no tensor map); bytes % 16 == 0, 16-byte aligned addresses
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }

@@ -9,6 +9,7 @@ from prediff_b200 import _lib as L  # noqa: E402
 
 L.init()
 dev = "cuda"
+BLOCKS = (0, 25, 1000, 1025) if os.environ.get("PD_PHASE_SPLIT") else (0, 25, 50)   # x + 1000 * z
 names = ["setup", "first_tile", "mainloop", "acc_ready", "first_chunk", "epilogue", "drain", "exit"]
 
 
@@ -36,7 +37,7 @@ def run(tag, samples, D, H, W, C, k, N, res, bf16_out, act, bn=0):
     flops = 2.0 * M * N * C * kt * kh * kw
     line = f"{tag:28s} {us:7.1f} us/launch (back-to-back) {flops / us * 1e-6:7.1f} TF/s |"
     t_first = None
-    for blk in (0, 25, 50):
+    for blk in BLOCKS:
         stamps.zero_()
         L.check(L.lib().pd_op_conv_gemm_phases(*args(blk)))
         torch.cuda.synchronize()
@@ -67,3 +68,6 @@ run("L1 ffn1  512->2048 gelu", 1, 1, 1, 3328, 512, (1, 1, 1), 2048, False, True,
 run("L1 ffn2  2048->512 f32+res", 1, 1, 1, 3328, 2048, (1, 1, 1), 512, True, False, 0)
 run("L1 conv3d 512->512", 4, 13, 8, 8, 512, (3, 3, 3), 512, True, False, 0)
 run("L1 conv3d 512->512 bn256", 4, 13, 8, 8, 512, (3, 3, 3), 512, True, False, 0, 256)
+if os.environ.get("PD_PHASE_SPLIT"):
+    names_blocks = (0, 25, 1000, 1025)
+
