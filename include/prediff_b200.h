@@ -233,6 +233,16 @@ int pd_op_ffn_fused_phases(const void* ln_in_bf16, const void* W1_bf16, const fl
                            const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
                            int M, unsigned long long* stamps32, void* stream);
 
+/* The same kernel with the attention output projection fused in front (CuboidSelfAttentionLayer proj +
+ * StackCuboidSelfAttentionBlock residual, cuboid_transformer.py:952,1151, then PositionwiseFFN :182-208):
+ *   x1 = x + att Wp^T + bp;  x <- x1 + W2 GELU(W1 LayerNorm(x1; ln1) + b1) + b2;  ln_out = LayerNorm(x; ln) (optional).
+ * ln_scratch_bf16 [M][256]: scratch the normalised tile round-trips through (may be the ln_out buffer). stamps32 may be
+ * NULL. */
+int pd_op_proj_ffn_fused(const void* att_bf16, const void* Wp_bf16, const float* bp, const float* ln1_gamma,
+                         const float* ln1_beta, void* ln_scratch_bf16, const void* W1_bf16, const float* b1,
+                         const void* W2_bf16, const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta,
+                         void* ln_out_bf16, int M, unsigned long long* stamps32, void* stream);
+
 /* ---- input-gradient kernels of the knowledge-alignment guidance (csrc/backward.cu); used by the parity tests --- */
 /* GroupNorm(+SiLU) backward: x, dy fp32 [S][R][C] -> dx_io fp32 (+= if accumulate) and/or dx_bf16 (either may be NULL) */
 int pd_op_group_norm_bwd(const float* x, const float* dy, const float* gamma, const float* beta, float* dx_io,

@@ -240,4 +240,22 @@ int pd_op_ffn_fused(const void* ln_in_bf16, const void* W1_bf16, const float* b1
                                   nullptr, stream);
 }
 
+int pd_op_proj_ffn_fused(const void* att_bf16, const void* Wp_bf16, const float* bp, const float* ln1_gamma,
+                         const float* ln1_beta, void* ln_scratch_bf16, const void* W1_bf16, const float* b1,
+                         const void* W2_bf16, const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta,
+                         void* ln_out_bf16, int M, unsigned long long* stamps32, void* stream) {
+    PD_TRY(gemm_init());
+    FfnProjArgs pa;
+    pa.att = static_cast<const bf16*>(att_bf16);
+    pa.wp = static_cast<const bf16*>(Wp_bf16);
+    pa.bp = bp;
+    pa.ln1_gamma = ln1_gamma;
+    pa.ln1_beta = ln1_beta;
+    FfnFusedOp op;
+    PD_TRY(ffn_fused_make(&op, static_cast<const bf16*>(ln_scratch_bf16), M, static_cast<const bf16*>(W1_bf16), b1,
+                          static_cast<const bf16*>(W2_bf16), b2, x_inout, ln_gamma, ln_beta,
+                          static_cast<bf16*>(ln_out_bf16), 1e-5f, stamps32, &pa));
+    return ffn_fused_launch(op, S(stream));
+}
+
 }  // extern "C"

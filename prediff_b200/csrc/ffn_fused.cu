@@ -48,12 +48,25 @@ struct FfnParams {
     float ln_eps;
     int M;
     unsigned long long* dbg;   // optional clock64() stamps of CTA 0 (tools/ffn_phases.py): see PD_FSTAMP sites
+    // PROJ variant (attention output projection fused in front): x1 = x + att Wp^T + bp never leaves the SM
+    const float* bp;         // proj bias
+    const float* ln1_gamma;  // the FFN's own pre-norm, applied to x1 inside the kernel
+    const float* ln1_beta;
 };
 
+// PROJ = false: A operand of GEMM-1 is the (already normalised) tensor behind tmap_a; acc2 starts at zero and the
+//               residual is added in the final epilogue.
+// PROJ = true : the kernel first builds x1 = x + bp + att . Wp^T in the acc2 columns of TMEM (the epilogue warps preset
+//               acc2 with x + bp through tcgen05.st while the first operands are in flight, GEMM-0 accumulates on top),
+//               normalises it (the FFN's pre-norm) into the bf16 tensor behind tmap_a - an L2-resident round trip of the
+//               tile's own rows - and GEMM-2 keeps accumulating onto x1, so no residual is ever re-loaded.
+template <bool PROJ>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x,
-                 const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ FfnParams p) {
+                 const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ CUtensorMap tmap_att,
+                 const __grid_constant__ CUtensorMap tmap_wp, const __grid_constant__ CUtensorMap tmap_ln1st,
+                 const __grid_constant__ FfnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sRing = smem;
@@ -65,8 +78,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc1_empty = acc1_full + 1;    // [1]
     uint64_t* mid_full = acc1_empty + 1;     // [2] (K halves)
     uint64_t* mid_empty = mid_full + 2;      // [2]
-    uint64_t* acc2_full = mid_empty + 2;     // [1]
-    uint64_t* res_bar = acc2_full + 1;       // [kEpiWarps][4]
+    uint64_t* acc2_full = mid_empty + 2;     // [1] (PROJ: phase 0 = x1 complete, phase 1 = FFN complete)
+    uint64_t* acc2_init = acc2_full + 1;     // [1] PROJ: acc2 preset with x + bp
+    uint64_t* ln1_ready = acc2_init + 1;     // [1] PROJ: LayerNorm(x1) stored behind tmap_a
+    uint64_t* res_bar = ln1_ready + 1;       // [kEpiWarps][4]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * kEpiWarps);
     float* b1_s = reinterpret_cast<float*>(smem + kPipeBytes + kBarBytes);   // [1024]
     float* b2_s = b1_s + kHid;                                               // [256]
@@ -93,6 +108,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::mbar_init(&mid_empty[h], 1);
         }
         ptx::mbar_init(acc2_full, 1);
+        ptx::mbar_init(acc2_init, kEpiWarps);
+        ptx::mbar_init(ln1_ready, kEpiWarps);
         for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -103,6 +120,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::prefetch_tmap(&tmap_w2);
         ptx::prefetch_tmap(&tmap_x);
         if (p.ln_gamma) ptx::prefetch_tmap(&tmap_ln);
+        if (PROJ) {
+            ptx::prefetch_tmap(&tmap_att);
+            ptx::prefetch_tmap(&tmap_wp);
+            ptx::prefetch_tmap(&tmap_ln1st);
+        }
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, 512);
@@ -116,14 +138,29 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
+            if (PROJ) {   // GEMM-0: att k-block + Wp tile per stage
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % kStages;
+                    ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
+                    uint8_t* st = sRing + s * kStage;
+                    ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
+                    ptx::tma_load_3d(st, &tmap_att, &w_full[s], kb * 64, row_tile, 0);
+                    ptx::tma_load_2d(st + kTileA, &tmap_wp, &w_full[s], kb * 64, 0);
+                }
+            }
+            bool a_ready = !PROJ;
             auto g1 = [&](int c) {   // 4 stages: A k-block + W1[c] tile
                 for (int kb = 0; kb < 4; ++kb, ++it) {
                     const int s = it % kStages;
                     ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
                     uint8_t* st = sRing + s * kStage;
                     ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
-                    ptx::tma_load_3d(st, &tmap_a, &w_full[s], kb * 64, row_tile, 0);
                     ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, c * kChunk);
+                    if (!a_ready) {   // PROJ: the A operand is LayerNorm(x1), written by this CTA's epilogue warps
+                        ptx::mbar_wait(ln1_ready, 0);
+                        a_ready = true;
+                    }
+                    ptx::tma_load_3d(st, &tmap_a, &w_full[s], kb * 64, row_tile, 0);
                 }
             };
             auto g2h = [&](int c, int h) {   // 2 stages: W2 tiles for hidden columns c*256 + h*128 + {0, 64}
@@ -173,14 +210,32 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const uint32_t a_addr = ptx::smem_u32(sMid + (h * 2 + kb) * kTileA);
                     const uint32_t b_addr = ptx::smem_u32(sRing + s * kStage + kTileA);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 4; ++k)   // PROJ: acc2 already holds x1, always accumulate
                         ptx::umma_f16(tmem_base + 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
-                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (c | h | kb | k) != 0 ? 1u : 0u);
+                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc,
+                                      (PROJ || (c | h | kb | k) != 0) ? 1u : 0u);
                     ptx::umma_commit(&w_empty[s]);
                 }
                 ptx::umma_commit(&mid_empty[h]);
             };
             PD_FSTAMP(1);
+            if (PROJ) {   // GEMM-0: acc2 (preset with x + bp) += att . Wp^T
+                ptx::mbar_wait(acc2_init, 0);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % kStages;
+                    ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(sRing + s * kStage);
+                    const uint32_t b_addr = a_addr + kTileA;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_base + 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
+                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, 1u);
+                    ptx::umma_commit(&w_empty[s]);
+                }
+                ptx::umma_commit(acc2_full);   // phase 0: x1 complete
+            }
             g1(0);
             PD_FSTAMP(2);
             for (int c = 0; c < kNumChunks; ++c) {
@@ -207,6 +262,107 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int row0 = row_tile + q * 32;
+        const int c_begin = half * 4;              // this warp's four 32-column chunks of the 256-wide row
+        uint64_t* my_bar = res_bar + 4 * e;
+        if (PROJ) {
+            // ---- preset acc2 with x + bp (two rounds of two 4 KB slabs per warp through the idle mid region) ----
+            uint8_t* islab = sMid + e * (2 * 4096);
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+                if (lane == 0) {
+                    for (int j = 0; j < 2; ++j) {
+                        ptx::mbar_arrive_expect_tx(&my_bar[2 * r + j], 4096);
+                        ptx::tma_load_3d(islab + j * 4096, &tmap_x, &my_bar[2 * r + j], (c_begin + 2 * r + j) * 32, row0, 0);
+                    }
+                }
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    const int c = c_begin + 2 * r + j;
+                    ptx::mbar_wait(&my_bar[2 * r + j], 0);
+                    const uint8_t* my_row = islab + j * 4096 + lane * 128;
+                    uint32_t v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 xv = *reinterpret_cast<const float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bp + c * 32 + 4 * i));
+                        v[4 * i] = __float_as_uint(xv.x + bb.x);
+                        v[4 * i + 1] = __float_as_uint(xv.y + bb.y);
+                        v[4 * i + 2] = __float_as_uint(xv.z + bb.z);
+                        v[4 * i + 3] = __float_as_uint(xv.w + bb.w);
+                    }
+                    ptx::tmem_st_32x32(t_lane + 256 + c * 32, v);
+                }
+                __syncwarp();   // both slabs consumed before the next round overwrites them
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc2_init);
+            // ---- E0: x1 = acc2 after GEMM-0; LayerNorm(x1) -> bf16 -> global (the A operand of GEMM-1) ----
+            ptx::mbar_wait(acc2_full, 0);
+            ptx::tc_fence_after();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int idx = 0; idx < 4; ++idx) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(t_lane + 256 + (c_begin + idx) * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a = __uint_as_float(v[i]);
+                    s1 += a;
+                    s2 = fmaf(a, a, s2);
+                }
+            }
+            ln_x[(q * 2 + half) * 32 + lane] = make_float2(s1, s2);
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
+            const float mean = (s1 + o.x) * (1.0f / kC);
+            const float var = fmaxf((s2 + o.y) * (1.0f / kC) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + p.ln_eps);
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // ln_x is reused by the final epilogue
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {          // bf16 slab j = my chunks 2j, 2j+1 (64 columns)
+                uint8_t* brow = islab + j * 4096 + lane * 128;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int colbase = (c_begin + 2 * j + cc) * 32;
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(t_lane + 256 + colbase, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln1_gamma + colbase + 8 * k));
+                        const float4 g1v = __ldg(reinterpret_cast<const float4*>(p.ln1_gamma + colbase + 8 * k + 4));
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln1_beta + colbase + 8 * k));
+                        const float4 b1v = __ldg(reinterpret_cast<const float4*>(p.ln1_beta + colbase + 8 * k + 4));
+                        float a[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) a[t] = __uint_as_float(v[8 * k + t]);
+                        uint4 pk;
+                        pk.x = pack_bf16x2(fmaf((a[0] - mean) * rstd, g0.x, b0.x), fmaf((a[1] - mean) * rstd, g0.y, b0.y));
+                        pk.y = pack_bf16x2(fmaf((a[2] - mean) * rstd, g0.z, b0.z), fmaf((a[3] - mean) * rstd, g0.w, b0.w));
+                        pk.z = pack_bf16x2(fmaf((a[4] - mean) * rstd, g1v.x, b1v.x), fmaf((a[5] - mean) * rstd, g1v.y, b1v.y));
+                        pk.w = pack_bf16x2(fmaf((a[6] - mean) * rstd, g1v.z, b1v.z), fmaf((a[7] - mean) * rstd, g1v.w, b1v.w));
+                        *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(cc * 4 + k) ^ sw) << 4)) = pk;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                // tmap_ln1st: the tensor behind tmap_a, addressed with 64-column x 32-row store boxes
+                ptx::tma_store_3d(&tmap_ln1st, islab, (c_begin + 0) * 32, row0, 0);
+                ptx::tma_store_3d(&tmap_ln1st, islab + 4096, (c_begin + 2) * 32, row0, 0);
+                ptx::bulk_commit();
+                ptx::bulk_wait_all<0>();            // written (not just read): the producer will TMA-load it back
+                ptx::fence_proxy_async_all();
+                ptx::mbar_arrive(ln1_ready);
+            }
+            __syncwarp();
+        }
         // ---- E1: GELU chunks -> swizzled A tiles of GEMM-2 ----
 #pragma unroll 1
         for (int c = 0; c < kNumChunks; ++c) {
@@ -250,14 +406,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (et == 0) PD_FSTAMP(13 + 2 * c);   // E1(c) done
         }
         // ---- final epilogue: acc2 + b2 + residual -> x (fp32, TMA store), fused LayerNorm -> bf16 ----
-        ptx::mbar_wait(acc2_full, 0);
+        ptx::mbar_wait(acc2_full, PROJ ? 1 : 0);
         ptx::tc_fence_after();
         if (et == 0) PD_FSTAMP(28);               // accumulator 2 complete
         uint8_t* slabs = smem + e * (4 * 4096);                    // aliases the ring (all MMAs have completed)
-        uint64_t* my_bar = res_bar + 4 * e;
-        const int row0 = row_tile + q * 32;
-        const int c_begin = half * 4;
-        if (lane == 0) {
+        if (!PROJ && lane == 0) {                                  // PROJ: the residual is already inside acc2
             for (int idx = 0; idx < 4; ++idx) {
                 ptx::mbar_arrive_expect_tx(&my_bar[idx], 4096);
                 ptx::tma_load_3d(slabs + idx * 4096, &tmap_x, &my_bar[idx], (c_begin + idx) * 32, row0, 0);
@@ -270,14 +423,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint8_t* slab = slabs + idx * 4096;
             uint32_t v[32];
             ptx::tmem_ld_32x32(t_lane + 256 + c * 32, v);
-            ptx::mbar_wait(&my_bar[idx], 0);
+            if (!PROJ) ptx::mbar_wait(&my_bar[idx], 0);
             ptx::tmem_ld_wait();
             uint8_t* my_row = slab + lane * 128;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 bb = *reinterpret_cast<const float4*>(b2_s + c * 32 + 4 * i);
                 float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
-                const float4 r = *cell;
+                const float4 r = PROJ ? make_float4(0.f, 0.f, 0.f, 0.f) : *cell;
                 float4 a = make_float4(__uint_as_float(v[4 * i]) + bb.x + r.x, __uint_as_float(v[4 * i + 1]) + bb.y + r.y,
                                        __uint_as_float(v[4 * i + 2]) + bb.z + r.z, __uint_as_float(v[4 * i + 3]) + bb.w + r.w);
                 *cell = a;
@@ -345,47 +498,54 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }  // namespace
 
 struct FfnFusedOpImpl {
-    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln;
+    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln, tmap_att, tmap_wp, tmap_ln1st;
     FfnParams p;
     int tiles;
+    int proj;
 };
 static_assert(sizeof(FfnFusedOpImpl) <= sizeof(FfnFusedOp), "FfnFusedOp storage too small");
 
 int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
                    const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out,
-                   float ln_eps, unsigned long long* dbg) {
+                   float ln_eps, unsigned long long* dbg, const FfnProjArgs* proj) {
     FfnFusedOpImpl* op = reinterpret_cast<FfnFusedOpImpl*>(op_);
     PD_TRY(gemm_init());
     PD_CHECK(ln_in && w1 && b1 && w2 && b2 && x_inout && M > 0, PD_ERR_ARG, "ffn_fused: null argument");
     PD_CHECK((ln_gamma != nullptr) == (ln_out != nullptr), PD_ERR_ARG, "ffn_fused: ln_gamma and ln_out go together");
+    PD_CHECK(!proj || (proj->att && proj->wp && proj->bp && proj->ln1_gamma && proj->ln1_beta), PD_ERR_ARG,
+             "ffn_fused: incomplete projection arguments");
     static bool attr_set = false;
     if (!attr_set) {
-        PD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
-    {   // A: ln [M][256] bf16, boxes of 128 rows x 64 columns
-        const uint64_t dims[3] = {kC, (uint64_t)M, 1}, st[2] = {kC * 2, (uint64_t)kC * 2 * M};
-        const uint32_t box[3] = {64, 128, 1};
-        PD_TRY(tmap_encode_sw128(&op->tmap_a, true, 3, ln_in, dims, st, box));
-    }
-    {   // W1 [1024][256] (K-major), W2 [256][1024]: boxes of 256 rows x 64 K
+    const uint64_t dims_b[3] = {kC, (uint64_t)M, 1}, st_b[2] = {kC * 2, (uint64_t)kC * 2 * M};   // bf16 [M][256]
+    const uint32_t box_ld[3] = {64, 128, 1}, box_st[3] = {64, 32, 1};
+    // A of GEMM-1: ln [M][256] bf16, boxes of 128 rows x 64 columns (PROJ: written by the kernel itself first)
+    PD_TRY(tmap_encode_sw128(&op->tmap_a, true, 3, ln_in, dims_b, st_b, box_ld));
+    PD_TRY(tmap_encode_sw128(&op->tmap_ln1st, true, 3, ln_in, dims_b, st_b, box_st));
+    {   // W1 [1024][256] (K-major), W2 [256][1024], Wp [256][256]: boxes of 256 rows x 64 K
         const uint64_t d1[2] = {kC, kHid}, s1[1] = {kC * 2};
         const uint64_t d2[2] = {kHid, kC}, s2[1] = {kHid * 2};
+        const uint64_t dp[2] = {kC, kC};
         const uint32_t box[2] = {64, 256};
         PD_TRY(tmap_encode_sw128(&op->tmap_w1, true, 2, w1, d1, s1, box));
         PD_TRY(tmap_encode_sw128(&op->tmap_w2, true, 2, w2, d2, s2, box));
+        op->tmap_wp = op->tmap_w1;
+        op->tmap_att = op->tmap_a;
+        if (proj) {
+            PD_TRY(tmap_encode_sw128(&op->tmap_wp, true, 2, proj->wp, dp, s1, box));
+            PD_TRY(tmap_encode_sw128(&op->tmap_att, true, 3, proj->att, dims_b, st_b, box_ld));
+        }
     }
     {   // x [M][256] fp32 (residual in, result out): 32-row x 32-column boxes
         const uint64_t dims[3] = {kC, (uint64_t)M, 1}, st[2] = {kC * 4, (uint64_t)kC * 4 * M};
         const uint32_t box[3] = {32, 32, 1};
         PD_TRY(tmap_encode_sw128(&op->tmap_x, false, 3, x_inout, dims, st, box));
     }
-    op->tmap_ln = op->tmap_x;
-    if (ln_out) {
-        const uint64_t dims[3] = {kC, (uint64_t)M, 1}, st[2] = {kC * 2, (uint64_t)kC * 2 * M};
-        const uint32_t box[3] = {64, 32, 1};
-        PD_TRY(tmap_encode_sw128(&op->tmap_ln, true, 3, ln_out, dims, st, box));
-    }
+    op->tmap_ln = op->tmap_ln1st;
+    if (ln_out) PD_TRY(tmap_encode_sw128(&op->tmap_ln, true, 3, ln_out, dims_b, st_b, box_st));
     op->p.b1 = b1;
     op->p.b2 = b2;
     op->p.ln_gamma = ln_gamma;
@@ -393,13 +553,22 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
     op->p.ln_eps = ln_eps;
     op->p.M = M;
     op->p.dbg = dbg;
+    op->p.bp = proj ? proj->bp : nullptr;
+    op->p.ln1_gamma = proj ? proj->ln1_gamma : nullptr;
+    op->p.ln1_beta = proj ? proj->ln1_beta : nullptr;
+    op->proj = proj ? 1 : 0;
     op->tiles = ceil_div(M, 128);
     return PD_OK;
 }
 
 int ffn_fused_launch(const FfnFusedOp& op_, cudaStream_t st) {
     const FfnFusedOpImpl& op = reinterpret_cast<const FfnFusedOpImpl&>(op_);
-    ffn_fused_kernel<<<op.tiles, kThreads, kSmem, st>>>(op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.p);
+    if (op.proj)
+        ffn_fused_kernel<true><<<op.tiles, kThreads, kSmem, st>>>(op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln,
+                                                                  op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
+    else
+        ffn_fused_kernel<false><<<op.tiles, kThreads, kSmem, st>>>(op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln,
+                                                                   op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -105,11 +105,21 @@ int transpose_f32(const float* in, float* out, int R, int C, cudaStream_t st);
 // followed by the fused LayerNorm of the new rows -> ln_out (bf16). ln_in bf16 [M][256]; W1 bf16 [1024][256]; W2 bf16
 // [256][1024]. Reference: PositionwiseFFN.forward, cuboid_transformer.py:182-208.
 struct FfnFusedOp {
-    alignas(64) unsigned char storage[1024];
+    alignas(64) unsigned char storage[1536];
+};
+// Optional front-end: the attention output projection x1 = x + att Wp^T + bp and the FFN's pre-norm LayerNorm(x1)
+// (gamma / beta below) are computed inside the kernel as well; `ln_in` is then only the bf16 scratch tensor the
+// normalised tile makes its L2 round trip through, x1 itself never leaves the SM (it seeds the GEMM-2 accumulator).
+struct FfnProjArgs {
+    const bf16* att;        // [M][256] attention output (A operand of the projection)
+    const bf16* wp;         // [256][256]
+    const float* bp;        // [256]
+    const float* ln1_gamma; // [256]
+    const float* ln1_beta;
 };
 int ffn_fused_make(FfnFusedOp* op, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
                    const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out,
-                   float ln_eps, unsigned long long* dbg = nullptr);
+                   float ln_eps, unsigned long long* dbg = nullptr, const FfnProjArgs* proj = nullptr);
 int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 
 // ---- evaluation (eval.cu) ----------------------------------------------------------------------------------

@@ -356,6 +356,20 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
         }
         pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, i, st); },
                i == 0 ? "attn_T" : (i == 1 ? "attn_H" : "attn_W"));
+        if (C == 256 && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {
+            // width 256: projection + residual + pre-norm + FFN (+ the next layer's LayerNorm) in ONE kernel per row
+            // tile - x1 = x + proj(att) lives in TMEM and seeds the FFN-2 accumulator (ffn_fused.cu, PROJ variant)
+            FfnProjArgs pa;
+            pa.att = att; pa.wp = aw.proj_w; pa.bp = aw.proj_b; pa.ln1_gamma = fw.ln_w; pa.ln1_beta = fw.ln_b;
+            FfnFusedOp op;
+            const bool next_ln = i < 2;
+            PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
+                                  next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f, nullptr, &pa));
+            pl.gemm_flops += 2.0 * (double)P * C * C + 2.0 * 2.0 * (double)P * C * 4 * C;
+            pl.n_gemm += 1;
+            pl.add([op](cudaStream_t st) { return ffn_fused_launch(op, st); }, STEP_GEMM, "proj_ffn_fused");
+            continue;
+        }
         {
             GemmEpilogue e;
             e.bias = aw.proj_b;

@@ -134,6 +134,38 @@ def test_ffn_fused(M, with_ln):
     assert torch.equal(xo, xo2)
 
 
+@pytest.mark.parametrize("M,with_ln", [(13312, True), (3328, False), (1000, True)])
+def test_proj_ffn_fused(M, with_ln):
+    """Attention projection + residual + pre-norm + FFN (+ next LayerNorm) in one kernel."""
+    C, Hd = 256, 1024
+    att = _randn(M, C, seed=11).bfloat16()
+    wp = _randn(C, C, seed=12, scale=C ** -0.5).bfloat16()
+    bp = 0.1 * _randn(C, seed=13)
+    g1, be1 = 1 + 0.1 * _randn(C, seed=14), 0.1 * _randn(C, seed=15)
+    w1 = _randn(Hd, C, seed=2, scale=C ** -0.5).bfloat16()
+    w2 = _randn(C, Hd, seed=3, scale=Hd ** -0.5).bfloat16()
+    b1, b2 = 0.1 * _randn(Hd, seed=4), 0.1 * _randn(C, seed=5)
+    x = _randn(M, C, seed=6) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * _randn(C, seed=7), 0.1 * _randn(C, seed=8)
+    x1 = x + att.float() @ wp.float().t() + bp
+    ln1 = F.layer_norm(x1, (C,), g1, be1, 1e-5).bfloat16().float()
+    mid = F.gelu(ln1 @ w1.float().t() + b1).bfloat16().float()
+    ref_x = x1 + mid @ w2.float().t() + b2
+    ref_ln = F.layer_norm(ref_x, (C,), gamma, beta, 1e-5)
+    xo = x.clone()
+    ln = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    args = lambda xx: (L.ptr(att), L.ptr(wp), L.ptr(bp), L.ptr(g1), L.ptr(be1), L.ptr(ln), L.ptr(w1), L.ptr(b1), L.ptr(w2),  # noqa: E731
+                       L.ptr(b2), L.ptr(xx), L.ptr(gamma) if with_ln else None, L.ptr(beta) if with_ln else None,
+                       L.ptr(ln) if with_ln else None, M, None, L.stream_ptr())
+    _sync_check(L.lib().pd_op_proj_ffn_fused(*args(xo)))
+    assert rel_err(xo, ref_x) < 3e-3   # bf16 roundings of ln1 / mid may flip at ties between the implementations
+    if with_ln:
+        assert rel_err(ln, ref_ln) < 1e-2
+    xo2 = x.clone()
+    _sync_check(L.lib().pd_op_proj_ffn_fused(*args(xo2)))
+    assert torch.equal(xo, xo2)
+
+
 def test_gemm_plain_no_epilogue_and_rowvec():
     M, K, N, samples = 512, 128, 128, 4
     a = _randn(samples * M, K, seed=5).bfloat16()
