@@ -221,6 +221,23 @@ int pd_op_parity_split_cast(const float* x, void* y_bf16, int F, int H, int W, i
 int pd_op_conv_s2_gemm(const void* planes_bf16, const void* Wt_bf16, int F, int Ho, int Wo, int C, int N,
                        const float* bias, float* out_f32, void* stream);
 
+/* pd_op_conv_gemm (fp32 output, no activation) scheduled stream-K: the (tile, k-block) units of every sample are cut
+ * into ctas_per_sample equal contiguous ranges, one CTA each; partial tiles go through a global workspace and are summed
+ * in a fixed order by the CTA that owns the head of the tile (csrc/gemm_streamk.cu). N must be a multiple of 256; the
+ * optional fused LayerNorm needs N == 256. */
+int pd_op_conv_gemm_streamk(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt, int kh,
+                            int kw, int N, const float* bias, const float* rowvec, const float* residual, float* out_f32,
+                            const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, int ctas_per_sample,
+                            void* stream);
+/* Same launch with clock64() phase stamps of schedule CTA dbg_cta written to stamps13 (device u64[16]): [0] entry, [1] setup
+ * done, [2] first operand stage landed, [3]/[6] last MMA of segment 0/1 issued, [4]/[7] accumulator 0/1 complete, [5] partial
+ * dumped, [8] the tile's partials arrived, [9] epilogue done, [10] exit, [11]/[12] %globaltimer ns at entry/exit.
+ * Profiling aid (tools/streamk_phases.py). */
+int pd_op_conv_gemm_streamk_phases(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt,
+                                   int kh, int kw, int N, const float* bias, const float* rowvec, const float* residual,
+                                   float* out_f32, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
+                                   int ctas_per_sample, int dbg_cta, unsigned long long* stamps13, void* stream);
+
 /* Fused PositionwiseFFN at width 256 / hidden 1024 (cuboid_transformer.py:182-208 after its pre-norm):
  * x[M][256] += W2 GELU(W1 ln_in + b1) + b2 in one kernel (the hidden activation never leaves the SM), and, if ln_gamma
  * is given, ln_out[M][256] (bf16) = LayerNorm(new x row) * ln_gamma + ln_beta. W1 bf16 [1024][256], W2 bf16 [256][1024]. */

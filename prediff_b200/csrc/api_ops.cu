@@ -1,6 +1,7 @@
 // extern "C" kernel-level entry points (include/prediff_b200.h): the same launchers the model programs use,
 // exposed so the parity tests can drive every kernel in isolation through the C ABI.
 #include <cstdlib>
+#include <vector>
 #include "../../include/prediff_b200.h"
 #include "gemm.cuh"
 #include "ops.cuh"
@@ -256,6 +257,62 @@ int pd_op_proj_ffn_fused(const void* att_bf16, const void* Wp_bf16, const float*
                           static_cast<const bf16*>(W2_bf16), b2, x_inout, ln_gamma, ln_beta,
                           static_cast<bf16*>(ln_out_bf16), 1e-5f, stamps32, &pa));
     return ffn_fused_launch(op, S(stream));
+}
+
+int pd_op_conv_gemm_streamk(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
+                            int N, const float* bias, const float* rowvec, const float* residual, float* out_f32,
+                            const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, int ctas_per_sample,
+                            void* stream) {
+    return pd_op_conv_gemm_streamk_phases(A, Wt, samples, D, H, W, C, kt, kh, kw, N, bias, rowvec, residual, out_f32, ln_gamma,
+                                          ln_beta, ln_out_bf16, ctas_per_sample, -1, nullptr, stream);
+}
+
+int pd_op_conv_gemm_streamk_phases(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh,
+                                   int kw, int N, const float* bias, const float* rowvec, const float* residual,
+                                   float* out_f32, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
+                                   int ctas_per_sample, int dbg_cta, unsigned long long* stamps13, void* stream) {
+    PD_TRY(gemm_init());
+    GemmGeom g = GemmGeom::conv(samples, D, H, W, C, kt, kh, kw);
+    GemmEpilogue e;
+    e.bias = bias; e.rowvec = rowvec; e.residual = residual; e.out_f32 = out_f32;
+    e.ln_gamma = ln_gamma; e.ln_beta = ln_beta; e.ln_out = static_cast<bf16*>(ln_out_bf16);
+    e.dbg = stamps13; e.dbg_block = dbg_cta;
+    GemmOp op;
+    PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e, 256));
+    std::vector<SkSeg> segs;
+    int n_slots = 0, n_flags = 0;
+    PD_TRY(gemm_streamk_schedule(op, ctas_per_sample, &segs, &n_slots, &n_flags));
+    cudaStream_t st = S(stream);
+    SkSeg* segs_dev = nullptr;
+    float* partials = nullptr;
+    int* flags = nullptr;
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&segs_dev), segs.size() * sizeof(SkSeg), st));
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partials), (size_t)(n_slots + 1) * 128 * 256 * sizeof(float), st));
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&flags), (size_t)n_flags * sizeof(int), st));
+    PD_CUDA(cudaMemcpyAsync(segs_dev, segs.data(), segs.size() * sizeof(SkSeg), cudaMemcpyHostToDevice, st));
+    PD_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_flags * sizeof(int), st));
+    PD_CUDA(cudaStreamSynchronize(st));   // the host vector dies at return
+    PD_TRY(gemm_streamk_attach(&op, segs_dev, (int)segs.size() / 2, partials, flags));
+    int rc = gemm_launch(op, st);
+    if (rc == PD_OK && stamps13 && dbg_cta < -1) {   // back-to-back launches timed with events: ns per launch -> stamps13[15]
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < -dbg_cta && rc == PD_OK; ++i) rc = gemm_launch(op, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const unsigned long long ns = (unsigned long long)(ms * 1e6 / -dbg_cta);
+        cudaMemcpy(stamps13 + 15, &ns, sizeof(ns), cudaMemcpyHostToDevice);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    cudaFreeAsync(segs_dev, st);
+    cudaFreeAsync(partials, st);
+    cudaFreeAsync(flags, st);
+    return rc;
 }
 
 }  // extern "C"

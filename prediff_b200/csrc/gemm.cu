@@ -901,6 +901,7 @@ int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* re
 }
 
 int gemm_launch(const GemmOp& op, cudaStream_t stream) {
+    if (op.sk_segs) return gemm_streamk_launch(op, stream);
     if (op.persistent) return launch_persistent(op, stream);
     switch (op.block_n) {
         case 32: return launch_cfg<32, 4>(op, stream);

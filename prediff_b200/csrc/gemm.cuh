@@ -9,6 +9,7 @@
 // src/prediff/models/time_embed.py:93,120; cuboid_transformer.py:735,767,157,164; taming/resnet.py:405,421).
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace pd {
 
@@ -110,11 +111,26 @@ struct GemmKernelParams {
     int dbg_block;
 };
 
+// Stream-K schedule entry (gemm_streamk.cu): one contiguous k-block range of one output tile.
+enum SkRole : int { SK_NONE = 0, SK_DUMP = 1, SK_FINAL = 2 };
+struct SkSeg {
+    int m_tile, n_tile;   // output tile (m_tile counts over all samples)
+    int k_begin, k_end;   // k-block range
+    int role;             // SK_DUMP: write the raw partial to workspace slot `slot`, bump flag; SK_FINAL: epilogue
+    int slot;             // DUMP: slot written; FINAL: first of the n_part consecutive slots to add
+    int n_part;           // FINAL: number of partials of this tile
+    int flag;             // index of the tile's arrival counter
+};
+
 struct GemmOp {
     CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_ln;
     GemmKernelParams p;
     int ldo = 0, out_rows = 0, out_samples = 0, out_N = 0;
     int block_n = 0, stages = 0, split_k = 1, persistent = 0, cluster_y = 1;
+    const SkSeg* sk_segs = nullptr;   // non-null: launch through the stream-K kernel with sk_ctas CTAs
+    int sk_ctas = 0;
+    float* sk_partials = nullptr;
+    int* sk_flags = nullptr;
     unsigned grid_x = 0, grid_y = 0;
     size_t smem = 0;
     double flops = 0;
@@ -128,6 +144,12 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream);
 int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
 // Number of ints gemm_make may need in GemmEpilogue::split_flags for this geometry (0 if it will not split).
 int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split = 0);
+// Stream-K for long-K fp32-output convolutions (gemm_streamk.cu). schedule(): host-side cut of an op built by gemm_make
+// into 2 * ctas_per_sample * samples segments (+ the number of 128 KB partial slots / flags it needs); attach(): points
+// the op at the device copy of the schedule and at the workspace, after which gemm_launch uses the stream-K kernel.
+int gemm_streamk_schedule(const GemmOp& op, int ctas_per_sample, std::vector<SkSeg>* segs, int* n_slots, int* n_flags);
+int gemm_streamk_attach(GemmOp* op, const SkSeg* segs_dev, int n_ctas, float* partials, int* flags);
+int gemm_streamk_launch(const GemmOp& op, cudaStream_t stream);
 int tmap_encode_sw128(CUtensorMap* m, bool is_bf16, int rank, const void* ptr, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box);
 int gemm_init();  // resolves the driver entry point + raises the dynamic smem limits (idempotent)

@@ -24,11 +24,17 @@ struct UNet::Bufs {
     int* split_flags;  // split-K tile handshake flags, shared by all convs of the plan (kernels run one at a time)
 };
 constexpr int kSplitFlagInts = 8192;
+constexpr int kStreamKCtasPerSample = 36;
 
 struct UNet::BatchPlan {
     Arena arena;
     Bufs bufs;
     Plan plan;
+    // stream-K (gemm_streamk.cu): per-conv schedules + tile flags, and one partial-tile workspace shared by all convs
+    // of the plan (kernels of a plan run one at a time)
+    std::vector<std::unique_ptr<DevMem>> sk_mem;
+    DevMem sk_partials;
+    int sk_slots = 0;
     GemmOp final_op;
     size_t t_slot = 0, in_slot = 0, out_slot = 0;
     Bufs& bufs_storage() { return bufs; }
@@ -283,6 +289,44 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
     b->split_flags = ar.template take<int>(kSplitFlagInts);
 }
 
+// Long-K fp32-output convolutions are scheduled stream-K: 36 CTAs per sample whatever the batch (the cut - hence the
+// summation order - depends on the layer shape only, so results stay bit-identical between a batch and its shards).
+// Falls back to the plain / split-K kernel when the shape is not eligible.
+int UNet::make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b) {
+    BatchPlan* bp = building_;
+    const int num_k = g.ntaps * (g.C / kGemmBlockK);
+    static const bool enabled = getenv("PD_NO_STREAMK") == nullptr;
+    if (enabled && bp && g.ntaps > 1 && num_k >= 64 && N % 256 == 0 && e.out_f32 && e.act == ACT_NONE &&
+        (!e.ln_gamma || N == 256)) {
+        GemmOp sk;
+        PD_TRY(gemm_make(&sk, a, g, w, N, e, 256));
+        std::vector<SkSeg> segs;
+        int n_slots = 0, n_flags = 0;
+        if (gemm_streamk_schedule(sk, kStreamKCtasPerSample, &segs, &n_slots, &n_flags) == PD_OK) {
+            if (n_slots + 1 > bp->sk_slots) {
+                // grown only while the plan is being built; ops attached earlier keep a stale pointer, so size it once
+                PD_CHECK(bp->sk_slots == 0, PD_ERR_STATE, "unet: stream-K workspace sized twice");
+                bp->sk_slots = kStreamKCtasPerSample * g.samples + 1;
+                PD_CHECK(n_slots + 1 <= bp->sk_slots, PD_ERR_STATE, "unet: stream-K slot bound");
+                PD_TRY(bp->sk_partials.alloc((size_t)bp->sk_slots * kGemmBlockM * 256 * sizeof(float)));
+            }
+            std::unique_ptr<DevMem> sm(new DevMem()), fm(new DevMem());
+            PD_TRY(sm->alloc(segs.size() * sizeof(SkSeg)));
+            PD_TRY(fm->alloc((size_t)n_flags * sizeof(int)));
+            PD_CUDA(cudaMemcpy(sm->p, segs.data(), segs.size() * sizeof(SkSeg), cudaMemcpyHostToDevice));
+            PD_CUDA(cudaMemset(fm->p, 0, (size_t)n_flags * sizeof(int)));
+            PD_TRY(gemm_streamk_attach(&sk, sm->as<SkSeg>(), (int)segs.size() / 2, bp->sk_partials.as<float>(),
+                                       fm->as<int>()));
+            bp->sk_mem.push_back(std::move(sm));
+            bp->sk_mem.push_back(std::move(fm));
+            *op = sk;
+            return PD_OK;
+        }
+    }
+    if (gemm_split_flags_needed(g, N) <= kSplitFlagInts) e.split_flags = b.split_flags;
+    return gemm_make(op, a, g, w, N, e);
+}
+
 int UNet::num_gn_slots() const { return 2 + 4 * (cfg.depth[0] + cfg.depth[1]); }
 
 int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
@@ -305,9 +349,8 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         e.rowvec_ld = emb_total;
         e.out_f32 = h;
         const GemmGeom g = GemmGeom::conv(B, T, H, W, C, 3, 3, 3);
-        if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
-        PD_TRY(gemm_make(&op, a, g, r.conv1_w, C, e));
+        PD_TRY(make_conv(&op, a, g, r.conv1_w, C, e, b));
         pl.add_gemm(op, "conv1");
     }
     pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); }, "gn_stats");
@@ -323,9 +366,8 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
             e.ln_out = b.ln[lvl];
         }
         const GemmGeom g = GemmGeom::conv(B, T, H, W, C, 3, 3, 3);
-        if (gemm_split_flags_needed(g, C) <= kSplitFlagInts) e.split_flags = b.split_flags;
         GemmOp op;
-        PD_TRY(gemm_make(&op, a, g, r.conv2_w, C, e));
+        PD_TRY(make_conv(&op, a, g, r.conv2_w, C, e, b));
         pl.add_gemm(op, "conv2");
     }
     pl.scope.clear();
@@ -435,6 +477,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     PD_CHECK(!bp->arena.overflowed(), PD_ERR_STATE, "unet: arena overflow");
     PD_CUDA(cudaMemset(b.split_flags, 0, kSplitFlagInts * sizeof(int)));
     Plan& pl = bp->plan;
+    building_ = bp;
     const int H = cfg.h, W = cfg.w, HW = H * W;
     const int R0 = T * HW;
     int gn_slot = 0;
@@ -496,7 +539,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             e.residual = x;
             e.out_f32 = x;
             GemmOp op;
-            PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, C0, 3, 3, 3), r.conv2_w, C0, e));
+            PD_TRY(make_conv(&op, a, GemmGeom::conv(B, T, H, W, C0, 3, 3, 3), r.conv2_w, C0, e, b));
             pl.add_gemm(op, "conv2");
         }
         const float *pt = pos_T, *ph = pos_H, *pw = pos_W;
@@ -539,7 +582,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         e.residual = b.x[0];
         e.out_f32 = b.x[0];
         GemmOp op;
-        PD_TRY(gemm_make(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e));
+        PD_TRY(make_conv(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e, b));
         pl.add_gemm(op, "up.conv");
     }
     for (int d = 0; d < cfg.depth[0]; ++d) {

@@ -58,6 +58,7 @@ private:
     int add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
                      const StackW* next);
     int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s);
+    int make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b);
     // The LayerNorm that follows a GEMM is computed in that GEMM's epilogue when a CTA (width 256) or a 2-CTA cluster
     // (width 512) owns whole rows; the resblock's conv2 only when it is not split-K (27 * C / 64 < 128 k-blocks).
     bool ln_fusable(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 || c == 512; }
@@ -66,6 +67,7 @@ private:
     template <class A>
     void carve(A& ar, int B, Bufs* b) const;
 
+    BatchPlan* building_ = nullptr;   // plan under construction (make_conv attaches stream-K workspaces to it)
     std::vector<std::unique_ptr<DevMem>> packed;
     std::map<std::pair<int, int>, std::unique_ptr<BatchPlan>> plans;  // (batch, replica)
     ResW first{}, down_res[2]{}, up_res[2]{};

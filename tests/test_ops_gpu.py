@@ -166,6 +166,45 @@ def test_proj_ffn_fused(M, with_ln):
     assert torch.equal(xo, xo2)
 
 
+@pytest.mark.parametrize("B,D,H,W,C,N,P,with_ln", [
+    (4, 13, 16, 16, 256, 256, 36, True),    # shipped level-0 Conv3d: 26 tiles x 108 k-blocks per sample -> 36 ranges of 78
+    (2, 13, 8, 8, 512, 512, 36, False),     # shipped level-1 Conv3d: 14 tiles x 216 k-blocks -> 36 ranges of 84 (4 parts)
+    (1, 13, 16, 16, 128, 256, 30, False),   # ragged cut: 26 x 54 units in 30 ranges
+    (3, 6, 16, 16, 128, 256, 13, True),
+])
+def test_conv3d_streamk(B, D, H, W, C, N, P, with_ln):
+    """Stream-K schedule of the implicit-GEMM conv vs torch conv3d; bias + per-sample row vector + in-place residual
+    (+ fused LayerNorm); deterministic and identical for a sub-batch (batch invariance)."""
+    x = _randn(B, D, H, W, C, seed=21).bfloat16()
+    w = _randn(N, C, 3, 3, 3, seed=22, scale=(27 * C) ** -0.5)
+    wp = _pack_conv(w, C)
+    bias = _randn(N, seed=23)
+    rv = _randn(B, N, seed=24)
+    res = _randn(B, D, H, W, N, seed=25)
+    gamma, beta = 1 + 0.1 * _randn(N, seed=26), 0.1 * _randn(N, seed=27)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.bfloat16().float(), bias, padding=1).permute(0, 2, 3, 4, 1)
+    ref = ref + rv[:, None, None, None, :] + res
+
+    def run(xs, rvs, ress, b):
+        out = ress.clone()
+        ln = torch.zeros(b, D, H, W, N, device=DEV, dtype=torch.bfloat16)
+        _sync_check(L.lib().pd_op_conv_gemm_streamk(L.ptr(xs), L.ptr(wp), b, D, H, W, C, 3, 3, 3, N, L.ptr(bias), L.ptr(rvs),
+                                                    L.ptr(out), L.ptr(out), L.ptr(gamma) if with_ln else None,
+                                                    L.ptr(beta) if with_ln else None, L.ptr(ln) if with_ln else None, P,
+                                                    L.stream_ptr()))
+        return out, ln
+
+    out, ln = run(x, rv, res, B)
+    assert rel_err(out, ref) < 3e-5
+    if with_ln:
+        assert rel_err(ln, F.layer_norm(ref, (N,), gamma, beta, 1e-5)) < 6e-3
+    out2, _ = run(x, rv, res, B)
+    assert torch.equal(out, out2)
+    if B > 1:   # the last sample alone: same bits (the cut depends on the layer shape only)
+        o1, _ = run(x[-1:].contiguous(), rv[-1:].contiguous(), res[-1:].contiguous(), 1)
+        assert torch.equal(o1[0], out[-1])
+
+
 def test_gemm_plain_no_epilogue_and_rowvec():
     M, K, N, samples = 512, 128, 128, 4
     a = _randn(samples * M, K, seed=5).bfloat16()
