@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
                                                               const float* __restrict__ bias_table,
                                                               bf16* __restrict__ out, int T, int H, int W, int C,
                                                               int heads, int axis) {
+    grid_dep_launch();
+    grid_dep_wait();
     extern __shared__ __align__(16) uint8_t smem_att[];
     bf16* s_qkv = reinterpret_cast<bf16*>(smem_att);  // [16][3C + 8]
     const int C3 = 3 * C;
@@ -148,6 +150,8 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
 // p = softmax(scale * s) per row; one warp per row, L <= 1024, L % 32 == 0.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int rows,
                                                            int L, float scale) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -180,6 +184,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 // in [S][R][ld_in] -> out [S][C][R], 32x32 tiles through padded smem.
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R,
                                                              int C, int ld_in) {
+    grid_dep_launch();
+    grid_dep_wait();
     __shared__ bf16 tile[32][34];
     const int s = blockIdx.z;
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -216,7 +222,7 @@ int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, 
                                          160 * 1024));                                                               \
             attr_set = true;                                                                                         \
         }                                                                                                            \
-        axial_attention_kernel<HDV><<<lines, threads, smem, st>>>(qkv, bias_table, out, T, H, W, C, heads, axis);    \
+        PD_LAUNCH((axial_attention_kernel<HDV>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, axis);    \
     } while (0)
     PD_CHECK(smem <= 160 * 1024, PD_ERR_SHAPE, "axial_attention: line of %zu bytes does not fit in smem", smem);
     switch (hd) {
@@ -233,14 +239,14 @@ int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, 
 
 int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st) {
     PD_CHECK(L % 32 == 0 && L <= 1024, PD_ERR_SHAPE, "softmax_rows: L=%d", L);
-    softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(s, p, rows, L, scale);
+    PD_LAUNCH(softmax_rows_kernel, ceil_div(rows, 8), 256, 0, st, s, p, rows, L, scale);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
 int transpose_bf16(const bf16* in, bf16* out, int S, int R, int C, int ld_in, cudaStream_t st) {
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32), S);
-    transpose_bf16_kernel<<<grid, 256, 0, st>>>(in, out, R, C, ld_in);
+    PD_LAUNCH(transpose_bf16_kernel, grid, 256, 0, st, in, out, R, C, ld_in);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

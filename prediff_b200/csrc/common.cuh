@@ -52,6 +52,51 @@ static inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b)
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch -----------------------------------------------------------
+// The denoise step is a chain of ~300 dependent launches of single-wave kernels, so what the chain costs is the sum of
+// (launch latency + prologue + first-operand latency) per kernel. Every kernel on the sampling path therefore
+//   * calls grid_dep_launch() first: the next kernel of the stream may be dispatched as soon as all CTAs of this one
+//     are resident, and runs its own prologue (barrier init, TMEM allocation, tensor-map fetch, weight-tile TMA loads -
+//     nothing that depends on this kernel) under this kernel's execution;
+//   * calls grid_dep_wait() before its first access to memory another kernel writes or reads: it returns once the
+//     preceding kernel has completed and flushed (which, by induction, means every earlier kernel of the stream has).
+// Both are no-ops when the launch carries no programmatic attribute. PD_NO_PDL=1 disables the attribute.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute (and an optional cluster shape).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster.x;
+        at[n].val.clusterDim.y = cluster.y;
+        at[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define PD_LAUNCH(kernel, grid, block, smem, st, ...) \
+    PD_CUDA(::pd::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, dim3(1, 1, 1), __VA_ARGS__))
+#endif
+
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(kEwThreads) unet_assemble_kernel(const float* 
                                                                    const float* __restrict__ cond,
                                                                    float* __restrict__ of, bf16* __restrict__ ob,
                                                                    int B, int Tx, int Tc, int HW, int C, int Cpad) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int T = Tx + Tc;
     const int c4n = Cpad >> 2;
     const int64_t total = (int64_t)B * T * HW * c4n;
@@ -47,6 +49,8 @@ __global__ void __launch_bounds__(kEwThreads) pos_embed_kernel(float* __restrict
                                                                const float* __restrict__ He,
                                                                const float* __restrict__ We, int B, int T, int H, int W,
                                                                int C) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int c4n = C >> 2;
     const int64_t total = (int64_t)B * T * H * W * c4n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -68,6 +72,8 @@ __global__ void __launch_bounds__(kEwThreads) pos_embed_kernel(float* __restrict
 
 __global__ void __launch_bounds__(kEwThreads) upsample2x_kernel(const float* __restrict__ x, bf16* __restrict__ y, int F,
                                                                 int H, int W, int C) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int c4n = C >> 2;
     const int H2 = 2 * H, W2 = 2 * W;
     const int64_t total = (int64_t)F * H2 * W2 * c4n;
@@ -87,6 +93,8 @@ __global__ void __launch_bounds__(kEwThreads) upsample2x_kernel(const float* __r
 
 __global__ void __launch_bounds__(kEwThreads) cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int S,
                                                                int64_t RC4, int64_t in_stride) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int64_t total = (int64_t)S * RC4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = i / RC4, e = i - s * RC4;
@@ -100,6 +108,8 @@ __global__ void __launch_bounds__(kEwThreads) cast_bf16_kernel(const float* __re
 
 __global__ void __launch_bounds__(kEwThreads) parity_split_kernel(const float* __restrict__ x, bf16* __restrict__ y,
                                                                   int F, int H, int W, int C) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int c4n = C >> 2;
     const int H2 = H >> 1, W2 = W >> 1;
     const int64_t total = (int64_t)F * H * W * c4n;
@@ -121,6 +131,8 @@ __global__ void __launch_bounds__(kEwThreads) parity_split_kernel(const float* _
 
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const int* __restrict__ step, int t_stride,
                                           float* __restrict__ out, int B, int dim) {
+    grid_dep_launch();
+    grid_dep_wait();
     if (step) t += (size_t)(*step) * t_stride;
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,6 +149,8 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const i
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const float* __restrict__ Wt,
                                                            const float* __restrict__ bias, float* __restrict__ out, int B,
                                                            int K, int N, int in_silu, int out_silu) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -161,6 +175,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 __global__ void __launch_bounds__(kEwThreads) conv3x3_c1_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ y,
                                                                    int F, int H, int W, int Cout) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int c4n = Cout >> 2;
     const int64_t total = (int64_t)F * H * W * c4n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -189,6 +205,8 @@ __global__ void __launch_bounds__(kEwThreads) conv3x3_c1_in_kernel(const float* 
 __global__ void __launch_bounds__(256) conv3x3_c1_out_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                              float bias, float* __restrict__ y, int F, int H, int W,
                                                              int Cin) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int64_t total = (int64_t)F * H * W;
     const int lane = threadIdx.x & 31;
     for (int64_t pix = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; pix < total;
@@ -241,7 +259,7 @@ int unet_assemble(const float* x, const float* cond, float* out_f32, bf16* out_b
                   int C, int Cpad, cudaStream_t st) {
     PD_CHECK(C % 4 == 0 && Cpad % 4 == 0 && Cpad > C, PD_ERR_SHAPE, "unet_assemble: C=%d Cpad=%d", C, Cpad);
     const int64_t total = (int64_t)B * (Tx + Tc) * HW * (Cpad / 4);
-    unet_assemble_kernel<<<ew_blocks(total), kEwThreads, 0, st>>>(x, cond, out_f32, out_bf16, B, Tx, Tc, HW, C, Cpad);
+    PD_LAUNCH(unet_assemble_kernel, ew_blocks(total), kEwThreads, 0, st, x, cond, out_f32, out_bf16, B, Tx, Tc, HW, C, Cpad);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -250,7 +268,7 @@ int pos_embed_add(float* x, const float* Te, const float* He, const float* We, i
                   cudaStream_t st) {
     PD_CHECK(C % 4 == 0, PD_ERR_SHAPE, "pos_embed_add: C=%d", C);
     const int64_t total = (int64_t)B * T * H * W * (C / 4);
-    pos_embed_kernel<<<ew_blocks(total), kEwThreads, 0, st>>>(x, Te, He, We, B, T, H, W, C);
+    PD_LAUNCH(pos_embed_kernel, ew_blocks(total), kEwThreads, 0, st, x, Te, He, We, B, T, H, W, C);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -258,7 +276,7 @@ int pos_embed_add(float* x, const float* Te, const float* He, const float* We, i
 int upsample2x_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st) {
     PD_CHECK(C % 4 == 0, PD_ERR_SHAPE, "upsample2x_cast: C=%d", C);
     const int64_t total = (int64_t)F * 4 * H * W * (C / 4);
-    upsample2x_kernel<<<ew_blocks(total), kEwThreads, 0, st>>>(x, y, F, H, W, C);
+    PD_LAUNCH(upsample2x_kernel, ew_blocks(total), kEwThreads, 0, st, x, y, F, H, W, C);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -266,7 +284,7 @@ int upsample2x_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStr
 int cast_bf16(const float* x, bf16* y, int S, int64_t RC, int64_t in_sample_stride, cudaStream_t st) {
     PD_CHECK(RC % 4 == 0 && in_sample_stride % 4 == 0, PD_ERR_SHAPE, "cast_bf16: sizes must be multiples of 4");
     const int64_t total = (int64_t)S * (RC / 4);
-    cast_bf16_kernel<<<ew_blocks(total), kEwThreads, 0, st>>>(x, y, S, RC / 4, in_sample_stride);
+    PD_LAUNCH(cast_bf16_kernel, ew_blocks(total), kEwThreads, 0, st, x, y, S, RC / 4, in_sample_stride);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -274,7 +292,7 @@ int cast_bf16(const float* x, bf16* y, int S, int64_t RC, int64_t in_sample_stri
 int parity_split_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st) {
     PD_CHECK(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, PD_ERR_SHAPE, "parity_split_cast: shape");
     const int64_t total = (int64_t)F * H * W * (C / 4);
-    parity_split_kernel<<<ew_blocks(total), kEwThreads, 0, st>>>(x, y, F, H, W, C);
+    PD_LAUNCH(parity_split_kernel, ew_blocks(total), kEwThreads, 0, st, x, y, F, H, W, C);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -283,14 +301,14 @@ int timestep_embedding(const int64_t* t, const int* step, int t_stride, float* o
                        cudaStream_t st) {
     PD_CHECK(dim % 2 == 0, PD_ERR_SHAPE, "timestep_embedding: dim must be even");
     const int total = B * (dim / 2);
-    timestep_embedding_kernel<<<ceil_div(total, 128), 128, 0, st>>>(t, step, t_stride ? t_stride : B, out, B, dim);
+    PD_LAUNCH(timestep_embedding_kernel, ceil_div(total, 128), 128, 0, st, t, step, t_stride ? t_stride : B, out, B, dim);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
 int small_linear(const float* in, const float* W, const float* bias, float* out, int B, int K, int N, int in_silu,
                  int out_silu, cudaStream_t st) {
-    small_linear_kernel<<<ceil_div(N, 8), 256, 0, st>>>(in, W, bias, out, B, K, N, in_silu, out_silu);
+    PD_LAUNCH(small_linear_kernel, ceil_div(N, 8), 256, 0, st, in, W, bias, out, B, K, N, in_silu, out_silu);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -299,7 +317,7 @@ int conv3x3_c1_in(const float* x, const float* w, const float* bias, float* y, i
                   cudaStream_t st) {
     PD_CHECK(Cout % 4 == 0, PD_ERR_SHAPE, "conv3x3_c1_in: Cout=%d", Cout);
     const int64_t total = (int64_t)F * H * W * (Cout / 4);
-    conv3x3_c1_in_kernel<<<ew_blocks(total), kEwThreads, 0, st>>>(x, w, bias, y, F, H, W, Cout);
+    PD_LAUNCH(conv3x3_c1_in_kernel, ew_blocks(total), kEwThreads, 0, st, x, w, bias, y, F, H, W, Cout);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -307,7 +325,7 @@ int conv3x3_c1_in(const float* x, const float* w, const float* bias, float* y, i
 int conv3x3_c1_out(const bf16* x, const float* w, float bias, float* y, int F, int H, int W, int Cin, cudaStream_t st) {
     PD_CHECK(Cin % 4 == 0, PD_ERR_SHAPE, "conv3x3_c1_out: Cin=%d", Cin);
     const int64_t total = (int64_t)F * H * W * 32;
-    conv3x3_c1_out_kernel<<<ew_blocks(total), 256, 0, st>>>(x, w, bias, y, F, H, W, Cin);
+    PD_LAUNCH(conv3x3_c1_out_kernel, ew_blocks(total), 256, 0, st, x, w, bias, y, F, H, W, Cin);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

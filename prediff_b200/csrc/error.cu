@@ -1,5 +1,6 @@
 #include "common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 
 namespace pd {
 namespace {
@@ -12,4 +13,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+bool pdl_enabled() {
+    static const bool on = getenv("PD_NO_PDL") == nullptr;
+    return on;
+}
 }  // namespace pd

@@ -126,6 +126,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::prefetch_tmap(&tmap_ln1st);
         }
     }
+    // Weight tiles of the first kStages stages (Wp when PROJ, else W1 chunk 0) do not depend on the preceding kernel:
+    // requested before the dependency wait (common.cuh); the activation halves follow after it.
+    if (threadIdx.x == 0) {
+        for (int kb = 0; kb < kStages; ++kb) {
+            ptx::mbar_arrive_expect_tx(&w_full[kb], kStage);
+            if (PROJ) ptx::tma_load_2d(sRing + kb * kStage + kTileA, &tmap_wp, &w_full[kb], kb * 64, 0);
+            else ptx::tma_load_2d(sRing + kb * kStage + kTileA, &tmap_w1, &w_full[kb], kb * 64, 0);
+        }
+    }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
@@ -134,6 +143,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // dependents are released only now: a dependent CTA that became co-resident before this CTA owned its TMEM columns
+    // could take them and then sit in its own dependency wait forever
+    grid_dep_launch();
+    grid_dep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -141,21 +154,25 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (PROJ) {   // GEMM-0: att k-block + Wp tile per stage
                 for (int kb = 0; kb < 4; ++kb, ++it) {
                     const int s = it % kStages;
-                    ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
                     uint8_t* st = sRing + s * kStage;
-                    ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
+                    if (it >= kStages) {
+                        ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
+                        ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
+                        ptx::tma_load_2d(st + kTileA, &tmap_wp, &w_full[s], kb * 64, 0);
+                    }
                     ptx::tma_load_3d(st, &tmap_att, &w_full[s], kb * 64, row_tile, 0);
-                    ptx::tma_load_2d(st + kTileA, &tmap_wp, &w_full[s], kb * 64, 0);
                 }
             }
             bool a_ready = !PROJ;
             auto g1 = [&](int c) {   // 4 stages: A k-block + W1[c] tile
                 for (int kb = 0; kb < 4; ++kb, ++it) {
                     const int s = it % kStages;
-                    ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
                     uint8_t* st = sRing + s * kStage;
-                    ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
-                    ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, c * kChunk);
+                    if (PROJ || it >= kStages) {   // !PROJ: the first kStages W1 tiles were requested in the prologue
+                        ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
+                        ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
+                        ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, c * kChunk);
+                    }
                     if (!a_ready) {   // PROJ: the A operand is LayerNorm(x1), written by this CTA's epilogue warps
                         ptx::mbar_wait(ln1_ready, 0);
                         a_ready = true;
@@ -564,11 +581,11 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
 int ffn_fused_launch(const FfnFusedOp& op_, cudaStream_t st) {
     const FfnFusedOpImpl& op = reinterpret_cast<const FfnFusedOpImpl&>(op_);
     if (op.proj)
-        ffn_fused_kernel<true><<<op.tiles, kThreads, kSmem, st>>>(op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln,
-                                                                  op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
+        PD_LAUNCH(ffn_fused_kernel<true>, op.tiles, kThreads, kSmem, st, op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x,
+                  op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
     else
-        ffn_fused_kernel<false><<<op.tiles, kThreads, kSmem, st>>>(op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln,
-                                                                   op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
+        PD_LAUNCH(ffn_fused_kernel<false>, op.tiles, kThreads, kSmem, st, op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x,
+                  op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -98,6 +98,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.has_res) ptx::prefetch_tmap(&tmap_res);
         if (p.ln_gamma) ptx::prefetch_tmap(&tmap_ln);
     }
+    // Weight tiles of the first stages do not depend on the preceding kernel: request them before the dependency wait
+    // (thread 0 initialised the barriers above). The activation halves of those stages follow after the wait.
+    int b_pre = 0;
+    if (threadIdx.x == 0 && !p.b_batched) {
+        b_pre = num_k < STAGES ? num_k : STAGES;
+        for (int it = 0; it < b_pre; ++it) {
+            ptx::mbar_arrive_expect_tx(&full_bar[it], C::kStageBytes);
+            ptx::tma_load_3d(smem + it * C::kStageBytes + kABytes, &tmap_b, &full_bar[it], (k_begin + it) * kGemmBlockK,
+                             n0, 0);
+        }
+    }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, C::kTmemCols);
         ptx::tmem_relinquish();
@@ -108,6 +119,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (p.ln_gamma && p.ln_cluster > 1) ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // dependents are released only now: a dependent CTA that became co-resident before this CTA owned its TMEM columns
+    // could take them and then sit in its own dependency wait forever
+    grid_dep_launch();
+    grid_dep_wait();     // everything below reads or writes tensors other kernels of the stream touch
     if (threadIdx.x == 0) PD_STAMP(1);
 
     if (warp == 0) {
@@ -121,12 +136,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int it = 0; it < num_k; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* sa = smem + s * C::kStageBytes;
-                ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
+                if (it >= b_pre) {
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
+                }
                 ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
                                  z0 + p.dz[tap], sample);
-                ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], (k_begin + it) * kGemmBlockK, n0, bz);
+                if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], (k_begin + it) * kGemmBlockK, n0, bz);
                 if (++cb == p.cblks) { cb = 0; ++tap; }
             }
         }
@@ -476,6 +493,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         ptx::prefetch_tmap(&tmap_b);
         ptx::prefetch_tmap(&tmap_out);
     }
+    int b_pre = 0;   // weight tiles of the first tile's first stages, requested before the dependency wait
+    if (threadIdx.x == 0 && !p.b_batched) {
+        b_pre = num_k < STAGES ? num_k : STAGES;
+        const int n0 = ((int)blockIdx.x % n_tiles_n) * BN;
+        for (int it = 0; it < b_pre; ++it) {
+            ptx::mbar_arrive_expect_tx(&full_bar[it], PersCfg::kStageBytes);
+            ptx::tma_load_3d(smem + it * PersCfg::kStageBytes + kABytes, &tmap_b, &full_bar[it], it * kGemmBlockK, n0, 0);
+        }
+    }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
@@ -484,6 +510,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // dependents are released only now: a dependent CTA that became co-resident before this CTA owned its TMEM columns
+    // could take them and then sit in its own dependency wait forever
+    grid_dep_launch();
+    grid_dep_wait();
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
@@ -503,12 +533,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                 for (int k = 0; k < num_k; ++k, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * PersCfg::kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], PersCfg::kStageBytes);
+                    if (it >= b_pre) {
+                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], PersCfg::kStageBytes);
+                    }
                     ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
                                      z0 + p.dz[tap], sample);
-                    ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * kGemmBlockK, n0, bz);
+                    if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * kGemmBlockK, n0, bz);
                     if (++cb == p.cblks) { cb = 0; ++tap; }
                 }
             }
@@ -635,34 +667,17 @@ int set_smem_attr() {
 int launch_persistent(const GemmOp& op, cudaStream_t stream) {
     const int total = (int)(op.grid_x * op.grid_y);
     const int grid = total < kNumSMs ? total : kNumSMs;
-    gemm_tc_persistent_kernel<<<grid, kThreads, PersCfg::kSmem, stream>>>(op.tmap_a, op.tmap_b, op.tmap_out, op.p,
-                                                                         (int)op.grid_y, total);
-    PD_LAUNCH_CHECK();
+    PD_LAUNCH(gemm_tc_persistent_kernel, grid, kThreads, PersCfg::kSmem, stream, op.tmap_a, op.tmap_b, op.tmap_out, op.p,
+              (int)op.grid_y, total);
     return PD_OK;
 }
 
 template <int BN, int STAGES>
 int launch_cfg(const GemmOp& op, cudaStream_t stream) {
-    if (op.cluster_y > 1) {   // the CTAs of one row tile (along N) form a thread-block cluster
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(op.grid_x, op.grid_y, op.split_k);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = Cfg<BN, STAGES>::kSmem;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1;
-        at[0].val.clusterDim.y = (unsigned)op.cluster_y;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        PD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES>, op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res,
-                                   op.tmap_ln, op.p));
-        return PD_OK;
-    }
-    gemm_tc_kernel<BN, STAGES><<<dim3(op.grid_x, op.grid_y, op.split_k), kThreads, Cfg<BN, STAGES>::kSmem, stream>>>(
-        op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.tmap_ln, op.p);
-    PD_LAUNCH_CHECK();
+    // cluster_y > 1: the CTAs of one row tile (along N) form a thread-block cluster
+    PD_CUDA(launch_pdl(gemm_tc_kernel<BN, STAGES>, dim3(op.grid_x, op.grid_y, op.split_k), dim3(kThreads),
+                       (size_t)Cfg<BN, STAGES>::kSmem, stream, dim3(1, (unsigned)op.cluster_y, 1), op.tmap_a, op.tmap_b,
+                       op.tmap_out, op.tmap_res, op.tmap_ln, op.p));
     return PD_OK;
 }
 

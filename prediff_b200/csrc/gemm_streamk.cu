@@ -80,6 +80,15 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (p.has_res) ptx::prefetch_tmap(&tmap_res);
         if (p.ln_gamma) ptx::prefetch_tmap(&tmap_ln);
     }
+    int b_pre = 0;   // weight tiles of the first stages, requested before the dependency wait (common.cuh)
+    if (threadIdx.x == 0 && seg0.role != SK_NONE) {
+        b_pre = seg0.k_end - seg0.k_begin < STAGES ? seg0.k_end - seg0.k_begin : STAGES;
+        for (int it = 0; it < b_pre; ++it) {
+            ptx::mbar_arrive_expect_tx(&full_bar[it], kStageBytes);
+            ptx::tma_load_3d(smem + it * kStageBytes + kABytes, &tmap_b, &full_bar[it], (seg0.k_begin + it) * kGemmBlockK,
+                             seg0.n_tile * BN, 0);
+        }
+    }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
@@ -88,6 +97,10 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // dependents are released only now: a dependent CTA that became co-resident before this CTA owned its TMEM columns
+    // could take them and then sit in its own dependency wait forever
+    grid_dep_launch();
+    grid_dep_wait();
     if (threadIdx.x == 0) SK_STAMP(1);
 
     if (warp == 0) {
@@ -107,12 +120,14 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 int tap = sgm.k_begin / p.cblks, cb = sgm.k_begin - tap * p.cblks;
                 for (int k = sgm.k_begin; k < sgm.k_end; ++k, ++it) {
                     const int s = it % STAGES;
-                    ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t* sa = smem + s * kStageBytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    if (it >= b_pre) {
+                        ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    }
                     ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
                                      z0 + p.dz[tap], sample);
-                    ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * kGemmBlockK, n0, 0);
+                    if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * kGemmBlockK, n0, 0);
                     if (++cb == p.cblks) { cb = 0; ++tap; }
                 }
             }
@@ -398,9 +413,8 @@ int gemm_streamk_attach(GemmOp* op, const SkSeg* segs_dev, int n_ctas, float* pa
 }
 
 int gemm_streamk_launch(const GemmOp& op, cudaStream_t stream) {
-    conv_streamk_kernel<<<op.sk_ctas, kThreads, kSmem, stream>>>(op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res, op.tmap_ln,
-                                                                  op.p, op.sk_segs, op.sk_partials, op.sk_flags);
-    PD_LAUNCH_CHECK();
+    PD_LAUNCH(conv_streamk_kernel, op.sk_ctas, kThreads, kSmem, stream, op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res,
+              op.tmap_ln, op.p, op.sk_segs, op.sk_partials, op.sk_flags);
     return PD_OK;
 }
 

@@ -13,6 +13,8 @@ constexpr int kGnIters = 8;  // independent 128-bit loads in flight per thread (
 // rows; a thread keeps one channel quad, so its 8 row loads are independent and issued back to back.
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
                                                               int R, int C, int G) {
+    grid_dep_launch();
+    grid_dep_wait();
     __shared__ float red[kGnThreads][8];
     const int s = blockIdx.y;
     const int c4n = C >> 2;                     // float4 columns
@@ -58,6 +60,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __res
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, bf16* __restrict__ y,
                                                               int R, int C, int G, float eps, int silu) {
+    grid_dep_launch();
+    grid_dep_wait();
     const int s = blockIdx.y;
     const int c4n = C >> 2;
     const int lanes_r = kGnThreads / c4n;
@@ -123,6 +127,8 @@ template <int NV, bool GATHER>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, bf16* __restrict__ y, int P,
                                                          int C, float eps, int H, int W, int Cs) {
+    grid_dep_launch();
+    grid_dep_wait();
     constexpr int ROWS = NV <= 4 ? kLnRows : 1;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -203,11 +209,11 @@ int launch_ln(const float* x, const float* gamma, const float* beta, bf16* y, in
     const int nv = ceil_div(C, 128);
     const int rows_per_warp = nv <= 4 ? kLnRows : 1;
     const int blocks = ceil_div(ceil_div(P, rows_per_warp), 8);
-    if (nv <= 1) layer_norm_kernel<1, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else if (nv <= 2) layer_norm_kernel<2, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else if (nv <= 4) layer_norm_kernel<4, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else if (nv <= 8) layer_norm_kernel<8, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else layer_norm_kernel<16, GATHER><<<blocks, 256, 0, st>>>(x, gamma, beta, y, P, C, eps, H, W, Cs);
+    if (nv <= 1) PD_LAUNCH((layer_norm_kernel<1, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 2) PD_LAUNCH((layer_norm_kernel<2, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 4) PD_LAUNCH((layer_norm_kernel<4, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 8) PD_LAUNCH((layer_norm_kernel<8, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else PD_LAUNCH((layer_norm_kernel<16, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -219,7 +225,7 @@ int gn_stats(const float* x, double* sums, int S, int R, int C, int G, cudaStrea
              C);
     PD_CHECK(G > 0 && C % G == 0 && G <= 128, PD_ERR_SHAPE, "gn_stats: unsupported groups=%d for C=%d", G, C);
     dim3 grid(ceil_div(R, (kGnThreads / (C / 4)) * kGnIters), S);
-    gn_stats_kernel<<<grid, kGnThreads, 0, st>>>(x, sums, R, C, G);
+    PD_LAUNCH(gn_stats_kernel, grid, kGnThreads, 0, st, x, sums, R, C, G);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -229,7 +235,7 @@ int gn_apply(const float* x, const double* sums, const float* gamma, const float
     PD_CHECK(C % 4 == 0 && G > 0 && C % G == 0 && G <= 128, PD_ERR_SHAPE, "gn_apply: unsupported C=%d G=%d", C, G);
     PD_CHECK(kGnThreads % (C / 4) == 0 && C / 4 <= kGnThreads, PD_ERR_SHAPE, "gn_apply: unsupported C=%d", C);
     dim3 grid(ceil_div(R, (kGnThreads / (C / 4)) * kGnIters), S);
-    gn_apply_kernel<<<grid, kGnThreads, 0, st>>>(x, sums, gamma, beta, y, R, C, G, eps, silu);
+    PD_LAUNCH(gn_apply_kernel, grid, kGnThreads, 0, st, x, sums, gamma, beta, y, R, C, G, eps, silu);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
                                                              const float* __restrict__ coef,
                                                              const int* __restrict__ step, int64_t n4,
                                                              int64_t noise_step_stride) {
+    grid_dep_launch();
+    grid_dep_wait();
     if (step) {
         const int k = *step;
         coef += (size_t)k * 8;
@@ -40,7 +42,9 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
     }
 }
 
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) {
+    grid_dep_launch();
+    grid_dep_wait(); *step += 1; }
 __global__ void stamp_globaltimer_kernel(unsigned long long* slot) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -56,7 +60,7 @@ int stamp_globaltimer(unsigned long long* slot, cudaStream_t st) {
 }
 
 int advance_step(int* step, cudaStream_t st) {
-    advance_step_kernel<<<1, 1, 0, st>>>(step);
+    PD_LAUNCH(advance_step_kernel, 1, 1, 0, st, step);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -68,7 +72,7 @@ int sampler_update(float* z, const float* eps, const float* noise, const float* 
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
-    sampler_update_kernel<<<blocks, 256, 0, st>>>(z, eps, noise, guide, coef, step, n4,
+    PD_LAUNCH(sampler_update_kernel, blocks, 256, 0, st, z, eps, noise, guide, coef, step, n4,
                                                   noise_step_stride ? noise_step_stride : n);
     PD_LAUNCH_CHECK();
     return PD_OK;

@@ -21,6 +21,9 @@ from prediff_b200.unet import CuboidTransformerUNet  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--out", default=None)
+ap.add_argument("--graph", action="store_true",
+                help="capture the stamped forward into a CUDA graph and replay it: launches are then issued by the GPU "
+                     "front end, not by the host (an eager trace is host-launch-bound for kernels shorter than ~5 us)")
 args = ap.parse_args()
 cfg = Wt.UNetConfig()
 B = args.batch
@@ -37,12 +40,26 @@ SLOTS = 2048
 ns = torch.zeros(SLOTS, device="cuda", dtype=torch.int64)
 labels = ctypes.create_string_buffer(1 << 16)
 n = 0
-for _ in range(4):
+
+
+def traced():
+    global n
     n = L.lib().pd_unet_trace_forward(unet.handle, L.ptr(x), L.ptr(t), L.ptr(cond), L.ptr(out), B, L.stream_ptr(), L.ptr(ns),
                                       SLOTS, labels, len(labels))
     if n < 0:
         L.check(n)
+
+
+for _ in range(4):
+    traced()
     torch.cuda.synchronize()
+if args.graph:
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        traced()
+    for _ in range(4):
+        g.replay()
+        torch.cuda.synchronize()
 lab = labels.value.decode().split("\n")[:n]
 s = ns.cpu().numpy()[:n + 1]
 d = np.diff(s).astype(np.float64) * 1e-3   # us per step (incl. one stamp slot)
@@ -54,7 +71,7 @@ for name, us in zip(lab, d):
     a[0] += 1
     a[1] += us - slot
 total = sum(v[1] for v in agg.values())
-lines = [f"UNet forward, batch {B}: {n} plan steps, {(s[-1] - s[0]) * 1e-3:.1f} us wall with stamps, "
+lines = [f"UNet forward, batch {B}{' (CUDA-graph replay)' if args.graph else ''}: {n} plan steps, {(s[-1] - s[0]) * 1e-3:.1f} us wall with stamps, "
          f"{total:.1f} us after removing {n} stamp slots of {slot:.2f} us",
          f"{'site':28s} {'n':>4s} {'avg us':>8s} {'total us':>9s} {'share':>6s}"]
 for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
