@@ -143,6 +143,59 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// GroupNorm statistics accumulated by the epilogue that PRODUCES the tensor (the GroupNorm that follows then needs no
+// statistics pass of its own): the lane holds 32 consecutive channels of one output row as eight float4 cells whose sums
+// and sums of squares are s[8], q[8]; cpg = channels per group (8, 16 or 32). The 32 rows of the warp belong to one
+// sample; dst = &sums[(sample * G + first group of this chunk) * 2] in the [S][G][2] double table of gn_stats().
+__device__ __forceinline__ void gn_chunk_accumulate(const float (&s)[8], const float (&q)[8], bool valid, int cpg, double* dst,
+                                                    int lane) {
+    float v[8];
+    int nv;
+    if (cpg == 8) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { v[2 * g] = s[2 * g] + s[2 * g + 1]; v[2 * g + 1] = q[2 * g] + q[2 * g + 1]; }
+        nv = 8;
+    } else if (cpg == 16) {
+        v[0] = (s[0] + s[1]) + (s[2] + s[3]); v[1] = (q[0] + q[1]) + (q[2] + q[3]);
+        v[2] = (s[4] + s[5]) + (s[6] + s[7]); v[3] = (q[4] + q[5]) + (q[6] + q[7]);
+        v[4] = v[5] = v[6] = v[7] = 0.f;
+        nv = 4;
+    } else {
+        v[0] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+        v[1] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
+        nv = 2;
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < nv) {   // warp-uniform
+            float t = valid ? v[k] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == k) mine = t;
+        }
+    }
+    if (lane < nv) atomicAdd(dst + lane, (double)mine);
+}
+
+// For the GEMM epilogues: re-reads the lane's 128-byte row of the swizzled fp32 slab it has just written (cell i sits at
+// ((i ^ sw) << 4)) and accumulates its statistics. Only instantiated in the GN = true kernel variants: the shuffle tree
+// inside the chunk loop slowed every epilogue by ~5 % (measured) when it was compiled into the common kernels, used or not.
+__device__ __forceinline__ void gn_chunk_from_slab(const uint8_t* my_row, uint32_t sw, bool valid, double* sums, int cpg,
+                                                int groups, int gn_rows, int global_row0, int col0, int lane) {
+    float gs[8], gq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+        gs[i] = (a.x + a.y) + (a.z + a.w);
+        gq[i] = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+    }
+    // global_row0: first row of the warp counted over all samples; col0: first channel of the chunk
+    double* dst = sums + ((size_t)(global_row0 / gn_rows) * groups + col0 / cpg) * 2;
+    gn_chunk_accumulate(gs, gq, valid, cpg, dst, lane);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);

@@ -52,6 +52,9 @@ struct FfnParams {
     const float* bp;         // proj bias
     const float* ln1_gamma;  // the FFN's own pre-norm, applied to x1 inside the kernel
     const float* ln1_beta;
+    // fused GroupNorm statistics of the new x rows (gemm.cuh GemmEpilogue::gn_sums): the resblock that follows a stack
+    double* gn_sums;
+    int gn_cpg, gn_groups, gn_rows;
 };
 
 // PROJ = false: A operand of GEMM-1 is the (already normalised) tensor behind tmap_a; acc2 starts at zero and the
@@ -60,7 +63,7 @@ struct FfnParams {
 //               acc2 with x + bp through tcgen05.st while the first operands are in flight, GEMM-0 accumulates on top),
 //               normalises it (the FFN's pre-norm) into the bf16 tensor behind tmap_a - an L2-resident round trip of the
 //               tile's own rows - and GEMM-2 keeps accumulating onto x1, so no residual is ever re-loaded.
-template <bool PROJ>
+template <bool PROJ, bool GN>   // GN: also accumulate GroupNorm statistics of the new x rows (FfnParams::gn_sums)
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x,
@@ -460,6 +463,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::tma_store_3d(&tmap_x, slab, c * 32, row0, 0);
                 ptx::bulk_commit();
             }
+            if constexpr (GN) if (row0 < p.M) {
+                gn_chunk_from_slab(my_row, sw, row0 + lane < p.M, p.gn_sums, p.gn_cpg, p.gn_groups, p.gn_rows, row0, c * 32,
+                                   lane);
+            }
         }
         if (p.ln_gamma) {
             ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
@@ -533,8 +540,10 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
              "ffn_fused: incomplete projection arguments");
     static bool attr_set = false;
     if (!attr_set) {
-        PD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        PD_CUDA(cudaFuncSetAttribute(ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute((ffn_fused_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute((ffn_fused_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute((ffn_fused_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute((ffn_fused_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
     const uint64_t dims_b[3] = {kC, (uint64_t)M, 1}, st_b[2] = {kC * 2, (uint64_t)kC * 2 * M};   // bf16 [M][256]
@@ -573,19 +582,36 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
     op->p.bp = proj ? proj->bp : nullptr;
     op->p.ln1_gamma = proj ? proj->ln1_gamma : nullptr;
     op->p.ln1_beta = proj ? proj->ln1_beta : nullptr;
+    op->p.gn_sums = nullptr;
+    op->p.gn_cpg = op->p.gn_groups = op->p.gn_rows = 0;
     op->proj = proj ? 1 : 0;
     op->tiles = ceil_div(M, 128);
     return PD_OK;
 }
 
+int ffn_fused_set_gn(FfnFusedOp* op_, double* gn_sums, int groups, int rows) {
+    FfnFusedOpImpl* op = reinterpret_cast<FfnFusedOpImpl*>(op_);
+    PD_CHECK(gn_sums && gemm_gn_fusable(kC, groups, rows), PD_ERR_SHAPE, "ffn_fused: GroupNorm statistics not fusable");
+    op->p.gn_sums = gn_sums;
+    op->p.gn_groups = groups;
+    op->p.gn_rows = rows;
+    op->p.gn_cpg = kC / groups;
+    return PD_OK;
+}
+
 int ffn_fused_launch(const FfnFusedOp& op_, cudaStream_t st) {
     const FfnFusedOpImpl& op = reinterpret_cast<const FfnFusedOpImpl&>(op_);
-    if (op.proj)
-        PD_LAUNCH(ffn_fused_kernel<true>, op.tiles, kThreads, kSmem, st, op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x,
-                  op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
-    else
-        PD_LAUNCH(ffn_fused_kernel<false>, op.tiles, kThreads, kSmem, st, op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x,
-                  op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p);
+#define PD_FFN_LAUNCH(PROJ, GN)                                                                                          \
+    PD_LAUNCH((ffn_fused_kernel<PROJ, GN>), op.tiles, kThreads, kSmem, st, op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x,     \
+              op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p)
+    if (op.proj) {
+        if (op.p.gn_sums) PD_FFN_LAUNCH(true, true);
+        else PD_FFN_LAUNCH(true, false);
+    } else {
+        if (op.p.gn_sums) PD_FFN_LAUNCH(false, true);
+        else PD_FFN_LAUNCH(false, false);
+    }
+#undef PD_FFN_LAUNCH
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -33,7 +33,7 @@ struct Cfg {
     static constexpr int kMinBlocks = (kSmem <= 112 * 1024) ? 2 : 1;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool GN>   // GN: also accumulate GroupNorm statistics of the output (GemmEpilogue::gn_sums)
 __global__ void __launch_bounds__(kThreads, Cfg<BN, STAGES>::kMinBlocks)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -304,6 +304,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (lane == 0) {
                         ptx::tma_store_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
                         ptx::bulk_commit();
+                    }
+                    if constexpr (GN) if (row0 < p.rows_per_sample) {   // statistics for the GroupNorm that reads this output
+                        gn_chunk_from_slab(my_row, sw, row0 + lane < p.rows_per_sample, p.gn_sums, p.gn_cpg, p.gn_groups,
+                                           p.gn_rows, sample * p.rows_per_sample + row0, n0 + c * 32, lane);
                     }
                 }
                 if constexpr (kOwnSlab && BN == 256 && kPerHalf == 4) {
@@ -659,8 +663,11 @@ bool g_inited = false;
 
 template <int BN, int STAGES>
 int set_smem_attr() {
-    PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg<BN, STAGES>::kSmem));
+    if (BN == 256 && STAGES == 4)
+        PD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<256, 4>::kSmem));
     return PD_OK;
 }
 
@@ -675,7 +682,13 @@ int launch_persistent(const GemmOp& op, cudaStream_t stream) {
 template <int BN, int STAGES>
 int launch_cfg(const GemmOp& op, cudaStream_t stream) {
     // cluster_y > 1: the CTAs of one row tile (along N) form a thread-block cluster
-    PD_CUDA(launch_pdl(gemm_tc_kernel<BN, STAGES>, dim3(op.grid_x, op.grid_y, op.split_k), dim3(kThreads),
+    if (op.p.gn_sums) {   // fused GroupNorm statistics exist for the 256 x 4-stage configuration only (gemm_make checks)
+        PD_CUDA(launch_pdl(gemm_tc_kernel<256, 4, true>, dim3(op.grid_x, op.grid_y, op.split_k), dim3(kThreads),
+                           (size_t)Cfg<256, 4>::kSmem, stream, dim3(1, (unsigned)op.cluster_y, 1), op.tmap_a, op.tmap_b,
+                           op.tmap_out, op.tmap_res, op.tmap_ln, op.p));
+        return PD_OK;
+    }
+    PD_CUDA(launch_pdl(gemm_tc_kernel<BN, STAGES, false>, dim3(op.grid_x, op.grid_y, op.split_k), dim3(kThreads),
                        (size_t)Cfg<BN, STAGES>::kSmem, stream, dim3(1, (unsigned)op.cluster_y, 1), op.tmap_a, op.tmap_b,
                        op.tmap_out, op.tmap_res, op.tmap_ln, op.p));
     return PD_OK;
@@ -795,6 +808,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     const int num_k = g.ntaps * (g.C / kGemmBlockK);
     if (!bn && e.split_flags && gemm_split_flags_needed(g, N, e.force_split) > 0 && e.out_f32 && e.act == ACT_NONE)
         bn = 256;
+    if (!bn && e.gn_sums && N % 256 == 0) bn = 256;   // the statistics epilogue exists for the 256-wide, 4-stage kernel
     // A 128 x 128 tcgen05.mma takes the same ~128 cycles as 128 x 256 (measured, tools/gemm_phases.py), so once the
     // mainloop matters (>= 16 k-blocks) BN = 256 halves it even if fewer CTAs run.
     if (!bn && N % 256 == 0 && num_k >= 16 && (int64_t)m_tiles * (N / 256) >= kNumSMs / 4) bn = 256;
@@ -884,6 +898,17 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(ln) failed: %d", (int)r);
     }
     p.split_flags = e.split_flags;
+    p.gn_sums = e.gn_sums;
+    p.gn_groups = e.gn_groups;
+    p.gn_rows = e.gn_rows;
+    p.gn_cpg = e.gn_sums ? N / e.gn_groups : 0;
+    if (e.gn_sums) {
+        PD_CHECK(e.out_f32 && gemm_gn_fusable(N, e.gn_groups, e.gn_rows) && bn % 32 == 0, PD_ERR_SHAPE,
+                 "gemm: fused GroupNorm statistics need an fp32 output, 8/16/32 channels per group and rows %% 32 == 0");
+        PD_CHECK(op->split_k == 1, PD_ERR_SHAPE, "gemm: fused GroupNorm statistics are not available with split-K");
+        PD_CHECK(bn == 256, PD_ERR_SHAPE, "gemm: fused GroupNorm statistics need N %% 256 == 0 (BLOCK_N = 256)");
+        op->stages = 4;
+    }
     // multi-wave bf16-output GEMMs (QKV, FFN-1) take the persistent kernel: epilogue under the next tile's mainloop
     op->persistent = (e.out_bf16 && bn == 256 && (int64_t)m_tiles * (N / bn) > kNumSMs && getenv("PD_NO_PERSISTENT") == nullptr) ? 1 : 0;
     op->grid_x = (unsigned)m_tiles;

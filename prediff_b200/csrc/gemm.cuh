@@ -86,6 +86,11 @@ struct GemmEpilogue {
     const float* ln_beta = nullptr;
     bf16* ln_out = nullptr;
     float ln_eps = 1e-5f;
+    // Optional GroupNorm statistics of the OUTPUT (fp32 output, no split-K): (sum, sum of squares) per (sample, group)
+    // added to gn_sums[S][gn_groups][2] (double, zeroed by the caller) - the table gn_stats() would fill. gn_rows = rows
+    // per GroupNorm sample (multiple of 32); N / gn_groups must be 8, 16 or 32.
+    double* gn_sums = nullptr;
+    int gn_groups = 0, gn_rows = 0;
     int* split_flags = nullptr;       // optional zeroed [m_tiles * n_tiles] ints: enables split-K (see gemm_make)
     int force_split = 0;              // 2: split K in two even below the automatic threshold (few tiles, long K);
                                       // must depend on the layer shape only so results stay batch-invariant
@@ -106,6 +111,8 @@ struct GemmKernelParams {
     const float* ln_beta;
     float ln_eps;
     int ln_cluster;            // CTAs along N that share a row (cluster size): 1, or 2 when the fused LN spans N = 512
+    double* gn_sums;           // fused GroupNorm statistics of the output (null = off), see GemmEpilogue::gn_sums
+    int gn_cpg, gn_groups, gn_rows;
     int* split_flags;          // per-tile handshake between the two split-K CTAs (self re-arming)
     unsigned long long* dbg;   // optional: 9 clock64() phase stamps of CTA (dbg_block, 0) - tools/gemm_phases.py
     int dbg_block;
@@ -144,6 +151,12 @@ int gemm_launch(const GemmOp& op, cudaStream_t stream);
 int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
 // Number of ints gemm_make may need in GemmEpilogue::split_flags for this geometry (0 if it will not split).
 int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split = 0);
+// True if GemmEpilogue::gn_sums can be honoured for this shape (channels per group 8 / 16 / 32, rows per sample % 32 == 0).
+inline bool gemm_gn_fusable(int N, int groups, int rows) {
+    if (groups <= 0 || N % groups != 0 || rows % 32 != 0 || N % 256 != 0) return false;
+    const int cpg = N / groups;
+    return cpg == 8 || cpg == 16 || cpg == 32;
+}
 // Stream-K for long-K fp32-output convolutions (gemm_streamk.cu). schedule(): host-side cut of an op built by gemm_make
 // into 2 * ctas_per_sample * samples segments (+ the number of 128 KB partial slots / flags it needs); attach(): points
 // the op at the device copy of the schedule and at the workspace, after which gemm_launch uses the stream-K kernel.

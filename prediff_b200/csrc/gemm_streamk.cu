@@ -27,6 +27,7 @@ constexpr int kPipeBytes = STAGES * kStageBytes;        // 192 KB
 constexpr int kBarBytes = 512;
 constexpr int kSmem = kPipeBytes + 1024 + kBarBytes + BN * 4 + 2 * BN * 4 + kEpiWarps * 32 * 8;
 
+template <bool GN>   // GN: also accumulate GroupNorm statistics of the output (GemmEpilogue::gn_sums)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -275,6 +276,10 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::tma_store_3d(&tmap_out, slab, n0 + c * 32, row0, sample);
                     ptx::bulk_commit();
                 }
+                if constexpr (GN) if (row0 < p.rows_per_sample) {   // statistics for the GroupNorm that reads this output
+                    gn_chunk_from_slab(my_row, sw, row0 + lane < p.rows_per_sample, p.gn_sums, p.gn_cpg, p.gn_groups,
+                                       p.gn_rows, sample * p.rows_per_sample + row0, n0 + c * 32, lane);
+                }
             }
             if (p.ln_gamma) {   // fused LayerNorm of the finished rows (N == 256: this CTA owns whole rows)
                 ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
@@ -401,7 +406,8 @@ int gemm_streamk_schedule(const GemmOp& op, int ctas_per_sample, std::vector<SkS
 int gemm_streamk_attach(GemmOp* op, const SkSeg* segs_dev, int n_ctas, float* partials, int* flags) {
     static bool attr_set = false;
     if (!attr_set) {
-        PD_CUDA(cudaFuncSetAttribute(conv_streamk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(conv_streamk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(conv_streamk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
     op->sk_segs = segs_dev;
@@ -413,8 +419,12 @@ int gemm_streamk_attach(GemmOp* op, const SkSeg* segs_dev, int n_ctas, float* pa
 }
 
 int gemm_streamk_launch(const GemmOp& op, cudaStream_t stream) {
-    PD_LAUNCH(conv_streamk_kernel, op.sk_ctas, kThreads, kSmem, stream, op.tmap_a, op.tmap_b, op.tmap_out, op.tmap_res,
-              op.tmap_ln, op.p, op.sk_segs, op.sk_partials, op.sk_flags);
+    if (op.p.gn_sums)
+        PD_LAUNCH(conv_streamk_kernel<true>, op.sk_ctas, kThreads, kSmem, stream, op.tmap_a, op.tmap_b, op.tmap_out,
+                  op.tmap_res, op.tmap_ln, op.p, op.sk_segs, op.sk_partials, op.sk_flags);
+    else
+        PD_LAUNCH(conv_streamk_kernel<false>, op.sk_ctas, kThreads, kSmem, stream, op.tmap_a, op.tmap_b, op.tmap_out,
+                  op.tmap_res, op.tmap_ln, op.p, op.sk_segs, op.sk_partials, op.sk_flags);
     return PD_OK;
 }
 

@@ -120,6 +120,8 @@ struct FfnProjArgs {
 int ffn_fused_make(FfnFusedOp* op, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
                    const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out,
                    float ln_eps, unsigned long long* dbg = nullptr, const FfnProjArgs* proj = nullptr);
+// Also accumulate the GroupNorm statistics of the new x rows into gn_sums[S][groups][2] (see GemmEpilogue::gn_sums).
+int ffn_fused_set_gn(FfnFusedOp* op, double* gn_sums, int groups, int rows_per_sample);
 int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 
 // ---- evaluation (eval.cu) ----------------------------------------------------------------------------------

@@ -25,6 +25,10 @@ struct UNet::Bufs {
 };
 constexpr int kSplitFlagInts = 8192;
 constexpr int kStreamKCtasPerSample = 36;
+bool gn_fusion_on() {
+    static const bool on = getenv("PD_NO_GN_FUSION") == nullptr;
+    return on;
+}
 
 struct UNet::BatchPlan {
     Arena arena;
@@ -292,8 +296,10 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
 // Long-K fp32-output convolutions are scheduled stream-K: 36 CTAs per sample whatever the batch (the cut - hence the
 // summation order - depends on the layer shape only, so results stay bit-identical between a batch and its shards).
 // Falls back to the plain / split-K kernel when the shape is not eligible.
-int UNet::make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b) {
+int UNet::make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b,
+                    bool* gn_fused) {
     BatchPlan* bp = building_;
+    if (gn_fused) *gn_fused = e.gn_sums != nullptr;
     const int num_k = g.ntaps * (g.C / kGemmBlockK);
     static const bool enabled = getenv("PD_NO_STREAMK") == nullptr;
     if (enabled && bp && g.ntaps > 1 && num_k >= 64 && N % 256 == 0 && e.out_f32 && e.act == ACT_NONE &&
@@ -324,13 +330,17 @@ int UNet::make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w,
         }
     }
     if (gemm_split_flags_needed(g, N) <= kSplitFlagInts) e.split_flags = b.split_flags;
+    if (e.gn_sums && e.split_flags && gemm_split_flags_needed(g, N) > 0) {   // split-K cannot produce the statistics
+        e.gn_sums = nullptr;
+        if (gn_fused) *gn_fused = false;
+    }
     return gemm_make(op, a, g, w, N, e);
 }
 
 int UNet::num_gn_slots() const { return 2 + 4 * (cfg.depth[0] + cfg.depth[1]); }
 
 int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
-                       const StackW* next) {
+                       const StackW* next, bool x_stats_ready) {
     const int H = cfg.h >> lvl, W = cfg.w >> lvl, C = lvl ? C1 : C0;
     const int R = T * H * W;
     float* x = b.x[lvl];
@@ -340,20 +350,27 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
     double* s2 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
     const float *g1w = r.gn1_w, *g1b = r.gn1_b, *g2w = r.gn2_w, *g2b = r.gn2_b;
     pl.scope = strf("L%d.res", lvl);
-    pl.add([=](cudaStream_t st) { return gn_stats(x, s1, B, R, C, 32, st); }, "gn_stats");
+    // the statistics of x were accumulated by the epilogue that produced it (gn_slot_for_next / GemmEpilogue::gn_sums)
+    if (!x_stats_ready) pl.add([=](cudaStream_t st) { return gn_stats(x, s1, B, R, C, 32, st); }, "gn_stats");
     pl.add([=](cudaStream_t st) { return gn_apply(x, s1, g1w, g1b, a, B, R, C, 32, 1e-5f, 1, st); }, "gn_apply");
+    bool h_stats_ready = false;
     {
         GemmEpilogue e;
         e.bias = r.conv1_b;
         e.rowvec = b.embs + emb_off[emb_index];  // h + emb_out (time_embed.py:165)
         e.rowvec_ld = emb_total;
         e.out_f32 = h;
+        if (gn_fusion_on() && gemm_gn_fusable(C, 32, R)) {   // statistics of h for the second GroupNorm
+            e.gn_sums = s2;
+            e.gn_groups = 32;
+            e.gn_rows = R;
+        }
         const GemmGeom g = GemmGeom::conv(B, T, H, W, C, 3, 3, 3);
         GemmOp op;
-        PD_TRY(make_conv(&op, a, g, r.conv1_w, C, e, b));
+        PD_TRY(make_conv(&op, a, g, r.conv1_w, C, e, b, &h_stats_ready));
         pl.add_gemm(op, "conv1");
     }
-    pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); }, "gn_stats");
+    if (!h_stats_ready) pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); }, "gn_stats");
     pl.add([=](cudaStream_t st) { return gn_apply(h, s2, g2w, g2b, a, B, R, C, 32, 1e-5f, 1, st); }, "gn_apply");
     {
         GemmEpilogue e;
@@ -374,7 +391,7 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
     return PD_OK;
 }
 
-int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
+int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, double* gn_next) {
     const int H = cfg.h >> lvl, W = cfg.w >> lvl, C = lvl ? C1 : C0;
     const int P = B * T * H * W;
     float* x = b.x[lvl];
@@ -407,6 +424,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             const bool next_ln = i < 2;
             PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                   next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f, nullptr, &pa));
+            if (gn_next && i == 2) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
             pl.gemm_flops += 2.0 * (double)P * C * C + 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.n_gemm += 1;
             pl.add([op](cudaStream_t st) { return ffn_fused_launch(op, st); }, STEP_GEMM, "proj_ffn_fused");
@@ -434,6 +452,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
             const bool next_ln = i < 2;   // pre-norm of the next attention layer of this stack
             PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                   next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f));
+            if (gn_next && i == 2) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
             pl.gemm_flops += 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.n_gemm += 1;
             pl.add([op](cudaStream_t st) { return ffn_fused_launch(op, st); }, STEP_GEMM, "ffn_fused");
@@ -457,6 +476,11 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s) {
                 e.ln_gamma = s.a[i + 1].ln_w;
                 e.ln_beta = s.a[i + 1].ln_b;
                 e.ln_out = ln;
+            }
+            if (gn_next && i == 2) {   // statistics for the first GroupNorm of the resblock that follows
+                e.gn_sums = gn_next;
+                e.gn_groups = 32;
+                e.gn_rows = T * H * W;
             }
             GemmOp op;
             PD_TRY(gemm_make(&op, mid, GemmGeom::linear(P, 4 * C), fw.w2, C, e));
@@ -548,9 +572,19 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.scope.clear();
     }
     // ---- down path ----
+    // GroupNorm statistics travel with the producer: the kernel that writes a resblock's input also accumulates the
+    // (sum, sum of squares) table of that resblock's first GroupNorm (slot = the next gn_slot), so gn_stats launches only
+    // remain where the producer is an elementwise kernel.
+    const int R1 = T * HW / 4;
+    auto next_slot = [&](int C, int R) -> double* {
+        return gn_fusion_on() && gemm_gn_fusable(C, 32, R) ? b.gn_sums + (size_t)gn_slot * B * 128 * 2 : nullptr;
+    };
+    bool x_ready = false;   // first_proj ends with the elementwise pos-embed add
     for (int d = 0; d < cfg.depth[0]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 0, down_res[0], 0, &gn_slot, &down_stack[0][d]));
-        PD_TRY(add_stack(pl, b, B, 0, down_stack[0][d]));
+        PD_TRY(add_resblock(pl, b, B, 0, down_res[0], 0, &gn_slot, &down_stack[0][d], x_ready));
+        double* nx = d + 1 < cfg.depth[0] ? next_slot(C0, R0) : nullptr;
+        PD_TRY(add_stack(pl, b, B, 0, down_stack[0][d], nx));
+        x_ready = nx != nullptr;
     }
     {   // PatchMerging3D: x0 stays intact and doubles as the U-Net skip tensor
         const float *x0 = b.x[0], *lw = pm_ln_w, *lb = pm_ln_b;
@@ -559,18 +593,26 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.add([=](cudaStream_t st) { return patch_merge_ln(x0, lw, lb, pm, BT, H, W, c0, 1e-5f, st); }, "down.merge_ln");
         GemmEpilogue e;
         e.out_f32 = b.x[1];
+        e.gn_sums = cfg.depth[1] > 0 ? next_slot(C1, R1) : nullptr;
+        e.gn_groups = 32;
+        e.gn_rows = R1;
+        x_ready = e.gn_sums != nullptr;
         GemmOp op;
         PD_TRY(gemm_make(&op, pm, GemmGeom::linear(B * T * HW / 4, 4 * C0), pm_w, C1, e));
         pl.add_gemm(op, "down.reduction");
     }
     for (int d = 0; d < cfg.depth[1]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot, &down_stack[1][d]));
-        PD_TRY(add_stack(pl, b, B, 1, down_stack[1][d]));
+        PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot, &down_stack[1][d], x_ready));
+        double* nx = next_slot(C1, R1);   // the next down resblock, or the first up resblock (depth[1] >= 1)
+        PD_TRY(add_stack(pl, b, B, 1, down_stack[1][d], nx));
+        x_ready = nx != nullptr;
     }
     // ---- up path ----
     for (int d = 0; d < cfg.depth[1]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 1, up_res[1], 3, &gn_slot, &up_stack[1][d]));
-        PD_TRY(add_stack(pl, b, B, 1, up_stack[1][d]));
+        PD_TRY(add_resblock(pl, b, B, 1, up_res[1], 3, &gn_slot, &up_stack[1][d], x_ready));
+        double* nx = d + 1 < cfg.depth[1] ? next_slot(C1, R1) : nullptr;
+        PD_TRY(add_stack(pl, b, B, 1, up_stack[1][d], nx));
+        x_ready = nx != nullptr;
     }
     {   // Upsample3DLayer (nearest 2x + Conv2d 3x3 per frame) with the U-Net skip add fused as the residual
         const float* x1 = b.x[1];
@@ -581,13 +623,18 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         e.bias = up_b;
         e.residual = b.x[0];
         e.out_f32 = b.x[0];
+        e.gn_sums = cfg.depth[0] > 0 ? next_slot(C0, R0) : nullptr;
+        e.gn_groups = 32;
+        e.gn_rows = R0;
         GemmOp op;
-        PD_TRY(make_conv(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e, b));
+        PD_TRY(make_conv(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e, b, &x_ready));
         pl.add_gemm(op, "up.conv");
     }
     for (int d = 0; d < cfg.depth[0]; ++d) {
-        PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot, &up_stack[0][d]));
-        PD_TRY(add_stack(pl, b, B, 0, up_stack[0][d]));
+        PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot, &up_stack[0][d], x_ready));
+        double* nx = d + 1 < cfg.depth[0] ? next_slot(C0, R0) : nullptr;
+        PD_TRY(add_stack(pl, b, B, 0, up_stack[0][d], nx));
+        x_ready = nx != nullptr;
     }
     PD_CHECK(gn_slot == num_gn_slots(), PD_ERR_STATE, "unet: gn slot accounting");
     // ---- final_proj on the target frames only (cuboid_transformer_unet.py:492) ----

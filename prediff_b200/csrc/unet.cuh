@@ -55,10 +55,13 @@ private:
     int build_plan(int B, BatchPlan* bp);
     // `next`: the stack block that follows - when the level width is 256 its first LayerNorm is fused into the
     // resblock's conv2 epilogue (and add_stack skips that LayerNorm launch)
+    // x_stats_ready: the producer of x already accumulated the first GroupNorm's statistics (GemmEpilogue::gn_sums)
     int add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, int emb_index, int* gn_slot,
-                     const StackW* next);
-    int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s);
-    int make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b);
+                     const StackW* next, bool x_stats_ready);
+    // gn_next: statistics table of the resblock that follows the stack (filled by the stack's last kernel), or null
+    int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, double* gn_next);
+    int make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b,
+                  bool* gn_fused = nullptr);
     // The LayerNorm that follows a GEMM is computed in that GEMM's epilogue when a CTA (width 256) or a 2-CTA cluster
     // (width 512) owns whole rows; the resblock's conv2 only when it is not split-K (27 * C / 64 < 128 k-blocks).
     bool ln_fusable(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 || c == 512; }
