@@ -177,6 +177,18 @@ int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* con
 int pd_sevir_eval_update(const float* pred, const float* target, int64_t* counts, double* sums, int N, int T, int H,
                          int W, int pool, const float* thresholds_host, int n_thresholds, void* stream);
 
+/* ---- input side (reference: src/prediff/datasets/sevir/sevir_dataloader.py:834-877 SEVIRDataLoader._idx_sample in
+ *      'sequent' mode, :610-650 preprocess_data_dict, :71-84 change_layout, constants :25-44) ------------------------- */
+/* events_u8: raw VIL events as stored in the SEVIR-LR HDF5 files, uint8 [n_events][H][W][T_raw] ('NHWT') on the device,
+ * holding events event_base .. event_base + n_events - 1 of the split. Writes the sequent windows first_seq ..
+ * first_seq + batch - 1 (window s = event s / n, frames (s % n) * stride .. + seq_len, n = 1 + (T_raw - seq_len) / stride)
+ * as fp32 [batch][seq_len][H][W][1] = scale * (x + offset) - bit-identical to the reference batch in layout 'NTHWC'
+ * (scale, offset: 1/255, 0 for rescale '01'; 1/47.54, -33.44 for 'sevir'). PD_ERR_SHAPE if a window needs an event
+ * outside the buffer. */
+int pd_sevir_windows(const unsigned char* events_u8, int event_base, int n_events, int H, int W, int T_raw,
+                     long long first_seq, int batch, int seq_len, int stride, float scale, float offset, float* out,
+                     void* stream);
+
 /* ---- kernel-level entry points (used by the parity tests; same kernels the models launch) ------------------ */
 /* out = epilogue(conv/linear(A, Wt)): A bf16 [samples][D][H][W][C], Wt bf16 [N][kt*kh*kw*C], zero padding k/2.
  * bias[N], rowvec[samples][N], residual/out_f32 fp32 [M][N], out_bf16 bf16 [M][N]; any of them may be NULL.

@@ -315,4 +315,11 @@ int pd_op_conv_gemm_streamk_phases(const void* A, const void* Wt, int samples, i
     return rc;
 }
 
+int pd_sevir_windows(const unsigned char* events_u8, int event_base, int n_events, int H, int W, int T_raw,
+                     long long first_seq, int batch, int seq_len, int stride, float scale, float offset, float* out,
+                     void* stream) {
+    return sevir_windows(events_u8, event_base, n_events, H, W, T_raw, first_seq, batch, seq_len, stride, scale, offset, out,
+                         S(stream));
+}
+
 }  // extern "C"

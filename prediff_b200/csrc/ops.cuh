@@ -131,6 +131,13 @@ int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 int sevir_eval_update(const float* pred, const float* target, long long* counts, double* sums, int N, int T, int H, int W,
                       int pool, const float* thresholds, int n_thr, cudaStream_t st);
 
+// ---- input side (io.cu) ------------------------------------------------------------------------------------
+// Raw uint8 VIL events [n_events][H][W][T_raw] (events event_base .. event_base + n_events - 1) -> sequent windows
+// first_seq .. first_seq + batch - 1 as fp32 [batch][seq_len][H][W] = scale * (x + offset) (sevir_dataloader.py:834-877,
+// :610-650).
+int sevir_windows(const uint8_t* events, int event_base, int n_events, int H, int W, int T_raw, long long first_seq, int batch,
+                  int seq_len, int stride, float scale, float offset, float* out, cudaStream_t st);
+
 // ---- sampler (sampler.cu) ----------------------------------------------------------------------------------
 // One fused update of the latent (latent_diffusion.py:553-566,620-631 for DDPM; SURVEY section 8 S6 for DDIM):
 //   z0 = c[0] z - c[1] eps ;  z <- c[2] z0 + c[3] z + c[4] eps + c[5] noise - c[6] guide

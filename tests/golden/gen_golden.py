@@ -185,6 +185,40 @@ def skill_inputs(seed=6161, N=3, T=6, H=32, W=32):
     return torch.from_numpy(pred), torch.from_numpy(target)
 
 
+def loader_events(seed=7171, E=5, H=16, W=24, T_raw=25):
+    """Synthetic raw VIL events, uint8 'NHWT' like the SEVIR-LR HDF5 datasets (sevir_dataloader.py:22, :360-380)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.integers(0, 256, size=(E, H, W, T_raw), dtype=np.uint8)
+
+
+def gen_loader():
+    """Batches of the unmodified reference SEVIRDataLoader._idx_sample (sequent windows + preprocess + layout change,
+    sevir_dataloader.py:834-891, :610-650). The HDF5 read (_load_event_batch) is replaced by a slice of a synthetic
+    uint8 event array - h5py / the dataset are absent - everything after it is the reference's own code."""
+    for name in ("h5py",):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    from prediff.datasets.sevir.sevir_dataloader import SEVIRDataLoader
+    ev = loader_events()
+    out = {}
+    for tag, (bs, seq_len, stride, rescale, layout) in {
+        "lr": (4, 13, 6, "01", "NTHWC"),          # shipped SEVIR-LR config (cfg.yaml:5-12)
+        "b3": (3, 13, 6, "01", "NTHWC"),          # batches straddle events
+        "sevir": (2, 10, 5, "sevir", "NTHWC"),    # the original SEVIR offsets / scales
+        "nthw": (2, 13, 12, "01", "NTHW"),
+    }.items():
+        dl = object.__new__(SEVIRDataLoader)
+        dl.data_types = ["vil"]
+        dl.batch_size, dl.seq_len, dl.raw_seq_len, dl.stride = bs, seq_len, ev.shape[-1], stride
+        dl.preprocess, dl.rescale_method, dl.layout, dl.downsample_dict = True, rescale, layout, None
+        dl._load_event_batch = lambda event_idx, event_batch_size: [ev[event_idx:event_idx + event_batch_size]]
+        n_batches = (ev.shape[0] * dl.num_seq_per_event) // bs
+        out[f"{tag}_n"] = np.asarray(n_batches)
+        for i in range(n_batches):
+            out[f"{tag}_{i}"] = dl._idx_sample(i)["vil"]
+    save("loader", **out)
+
+
 def gen_skill():
     """SEVIRSkillScore of the unmodified reference (datasets/sevir/evaluation.py). `torchmetrics` and `h5py` are absent
     from the image; the metric only uses torchmetrics.Metric as a state container (add_state / reset), so an inert
@@ -370,5 +404,7 @@ if __name__ == "__main__":
         gen_ka()
     if "skill" in todo:
         gen_skill()
+    if "loader" in todo:
+        gen_loader()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)
