@@ -143,6 +143,35 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- L2 weight prefetch ----------------------------------------------------------------------------------------
+// The UNet's bf16 weights (274 MB) do not fit the 126 MB L2, so every GEMM of a denoise step finds its weights in HBM:
+// measured with cold weights a GEMM CTA runs 3-10 % longer (tools/gemm_phases.py, PD_PHASE_COLD=1), all of it on the
+// step's critical path. Each GEMM-family kernel therefore starts by asking the L2 for the weights of the NEXT GEMM of
+// the plan (up to three ranges; every CTA requests its 1/gridDim share with cp.async.bulk.prefetch.L2), which then
+// stream in from HBM underneath this kernel's own work. Plan::link_prefetch() chains the ranges.
+struct WRange {
+    const uint8_t* p[3];
+    uint32_t n[3];   // bytes, multiples of 16
+};
+__device__ __forceinline__ void prefetch_l2_share(const WRange& r, unsigned cta, unsigned nctas) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t total = r.n[i];
+        if (total == 0) continue;
+        const uint32_t share = ((total + nctas - 1) / nctas + 255u) & ~255u;
+        uint32_t off = cta * share;
+        if (off >= total) continue;
+        uint32_t len = total - off < share ? total - off : share;
+        const uint8_t* src = r.p[i] + off;
+        while (len > 0) {
+            const uint32_t piece = len < 16384u ? len : 16384u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(piece) : "memory");
+            src += piece;
+            len -= piece;
+        }
+    }
+}
+
 // GroupNorm statistics accumulated by the epilogue that PRODUCES the tensor (the GroupNorm that follows then needs no
 // statistics pass of its own): the lane holds 32 consecutive channels of one output row as eight float4 cells whose sums
 // and sums of squares are s[8], q[8]; cpg = channels per group (8, 16 or 32). The 32 rows of the warp belong to one

@@ -55,6 +55,7 @@ struct FfnParams {
     // fused GroupNorm statistics of the new x rows (gemm.cuh GemmEpilogue::gn_sums): the resblock that follows a stack
     double* gn_sums;
     int gn_cpg, gn_groups, gn_rows;
+    WRange pf;               // weights of the next GEMM of the plan, requested into L2 at kernel start (common.cuh)
 };
 
 // PROJ = false: A operand of GEMM-1 is the (already normalised) tensor behind tmap_a; acc2 starts at zero and the
@@ -98,6 +99,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
 #define PD_FSTAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
     if (threadIdx.x == 0) PD_FSTAMP(0);
+    if (threadIdx.x == 32) prefetch_l2_share(p.pf, blockIdx.x, gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -524,6 +526,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 struct FfnFusedOpImpl {
     CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln, tmap_att, tmap_wp, tmap_ln1st;
     FfnParams p;
+    WRange own_w;
     int tiles;
     int proj;
 };
@@ -582,12 +585,20 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
     op->p.bp = proj ? proj->bp : nullptr;
     op->p.ln1_gamma = proj ? proj->ln1_gamma : nullptr;
     op->p.ln1_beta = proj ? proj->ln1_beta : nullptr;
+    op->p.pf = WRange{};
+    op->own_w = WRange{};
+    op->own_w.p[0] = reinterpret_cast<const uint8_t*>(w1); op->own_w.n[0] = kHid * kC * 2;
+    op->own_w.p[1] = reinterpret_cast<const uint8_t*>(w2); op->own_w.n[1] = kHid * kC * 2;
+    if (proj) { op->own_w.p[2] = reinterpret_cast<const uint8_t*>(proj->wp); op->own_w.n[2] = kC * kC * 2; }
     op->p.gn_sums = nullptr;
     op->p.gn_cpg = op->p.gn_groups = op->p.gn_rows = 0;
     op->proj = proj ? 1 : 0;
     op->tiles = ceil_div(M, 128);
     return PD_OK;
 }
+
+void ffn_fused_set_prefetch(FfnFusedOp* op_, const WRange& next) { reinterpret_cast<FfnFusedOpImpl*>(op_)->p.pf = next; }
+WRange ffn_fused_weights(const FfnFusedOp& op_) { return reinterpret_cast<const FfnFusedOpImpl&>(op_).own_w; }
 
 int ffn_fused_set_gn(FfnFusedOp* op_, double* gn_sums, int groups, int rows) {
     FfnFusedOpImpl* op = reinterpret_cast<FfnFusedOpImpl*>(op_);

@@ -59,6 +59,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     unsigned long long* dbg = (p.dbg && (int)blockIdx.x == p.dbg_block % 1000 && blockIdx.y == 0 &&
                                (int)blockIdx.z == p.dbg_block / 1000) ? p.dbg : nullptr;
 #define PD_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+    if (threadIdx.x == 32)   // a lane of the MMA warp, idle during set-up
+        prefetch_l2_share(p.pf, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, gridDim.x * gridDim.y * gridDim.z);
     if (threadIdx.x == 0) {
         PD_STAMP(0);
         if (dbg) {   // wall-clock (ns) stamps: effective SM frequency + launch skew between CTAs
@@ -473,6 +475,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int lane = threadIdx.x & 31;
     const int num_k = p.ntaps * p.cblks;
     unsigned long long* dbg = (p.dbg && (int)blockIdx.x == p.dbg_block) ? p.dbg : nullptr;
+    if (threadIdx.x == 32) prefetch_l2_share(p.pf, blockIdx.x, gridDim.x);
     if (dbg && threadIdx.x == 0) {
         dbg[0] = clock64();
         unsigned long long gt;
@@ -898,6 +901,10 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(ln) failed: %d", (int)r);
     }
     p.split_flags = e.split_flags;
+    if (!g.b_sample_stride && (g.ldb == 0 || g.ldb == (int64_t)g.ntaps * g.C)) {   // a plain weight matrix [N][K]
+        op->own_w.p[0] = reinterpret_cast<const uint8_t*>(Wt);
+        op->own_w.n[0] = (uint32_t)((size_t)N * g.ntaps * g.C * 2);
+    }
     p.gn_sums = e.gn_sums;
     p.gn_groups = e.gn_groups;
     p.gn_rows = e.gn_rows;

@@ -116,6 +116,7 @@ struct GemmKernelParams {
     int* split_flags;          // per-tile handshake between the two split-K CTAs (self re-arming)
     unsigned long long* dbg;   // optional: 9 clock64() phase stamps of CTA (dbg_block, 0) - tools/gemm_phases.py
     int dbg_block;
+    WRange pf;                 // weights of the next GEMM of the plan, requested into L2 at kernel start (common.cuh)
 };
 
 // Stream-K schedule entry (gemm_streamk.cu): one contiguous k-block range of one output tile.
@@ -141,6 +142,7 @@ struct GemmOp {
     unsigned grid_x = 0, grid_y = 0;
     size_t smem = 0;
     double flops = 0;
+    WRange own_w = {};   // this op's weight bytes (what the preceding GEMM should prefetch)
 };
 
 // Builds tensor maps + launch geometry. `A` is bf16 [samples][D][H][W][C]; `Wt` is bf16 [N][ntaps*C] (K-major).

@@ -50,6 +50,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // A tile's finishing CTA waits for CTAs holding later k ranges (higher schedule index): give those the lower block
     // indices, which are dispatched first, so a launch larger than one wave cannot park its waiters on every SM.
     const int cta = gridDim.x - 1 - blockIdx.x;
+    if (threadIdx.x == 32) prefetch_l2_share(p.pf, blockIdx.x, gridDim.x);   // next GEMM's weights -> L2 (common.cuh)
     const SkSeg seg0 = segs[2 * cta], seg1 = segs[2 * cta + 1];
     // phase stamps of schedule CTA p.dbg_block (tools/streamk_phases.py): [0] entry, [1] setup done, [2] first operand
     // stage landed, [3]/[6] last MMA of segment 0 / 1 issued, [4]/[7] accumulator 0 / 1 complete, [5] partial dumped,

@@ -153,10 +153,29 @@ struct Plan {
         labels.push_back(scope.empty() ? std::string(label) : scope + "." + label);
     }
     void add(Step s, const char* label) { add(std::move(s), STEP_KERNEL, label); }
+    // GEMM-family steps in launch order, for the L2 weight prefetch chain (common.cuh): `own` = the step's weight ranges,
+    // `set_next` stores the ranges the step should request for its successor.
+    struct WeightUser {
+        std::function<void(const WRange&)> set_next;
+        WRange own;
+    };
+    std::vector<WeightUser> weight_users;
     void add_gemm(const GemmOp& op, const char* label = "gemm") {
         gemm_flops += op.flops;
         ++n_gemm;
-        add([op](cudaStream_t st) { return gemm_launch(op, st); }, STEP_GEMM, label);
+        auto sp = std::make_shared<GemmOp>(op);
+        add([sp](cudaStream_t st) { return gemm_launch(*sp, st); }, STEP_GEMM, label);
+        weight_users.push_back({[sp](const WRange& r) { sp->p.pf = r; }, op.own_w});
+    }
+    void add_ffn_fused(const FfnFusedOp& op, const char* label) {
+        auto sp = std::make_shared<FfnFusedOp>(op);
+        add([sp](cudaStream_t st) { return ffn_fused_launch(*sp, st); }, STEP_GEMM, label);
+        weight_users.push_back({[sp](const WRange& r) { ffn_fused_set_prefetch(sp.get(), r); }, ffn_fused_weights(op)});
+    }
+    // Every GEMM-family step requests the weights of the next one (the last wraps around to the first of the next pass).
+    void link_prefetch() {
+        const size_t n = weight_users.size();
+        for (size_t i = 0; i < n; ++i) weight_users[i].set_next(weight_users[(i + 1) % n].own);
     }
     // One eager pass with a %globaltimer stamp kernel after every step: ns[i] = stamp after step i (ns[0] = start),
     // so ns[i+1] - ns[i] = duration of step i + one (constant) stamp-kernel slot. `ns` has steps.size() + 1 slots.

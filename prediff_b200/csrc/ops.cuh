@@ -122,6 +122,9 @@ int ffn_fused_make(FfnFusedOp* op, const bf16* ln_in, int M, const bf16* w1, con
                    float ln_eps, unsigned long long* dbg = nullptr, const FfnProjArgs* proj = nullptr);
 // Also accumulate the GroupNorm statistics of the new x rows into gn_sums[S][groups][2] (see GemmEpilogue::gn_sums).
 int ffn_fused_set_gn(FfnFusedOp* op, double* gn_sums, int groups, int rows_per_sample);
+// L2 weight prefetch chain (common.cuh WRange): this op's weight ranges / the ranges it should request for its successor.
+void ffn_fused_set_prefetch(FfnFusedOp* op, const WRange& next);
+WRange ffn_fused_weights(const FfnFusedOp& op);
 int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 
 // ---- evaluation (eval.cu) ----------------------------------------------------------------------------------

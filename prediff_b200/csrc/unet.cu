@@ -427,7 +427,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             if (gn_next && i == 2) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
             pl.gemm_flops += 2.0 * (double)P * C * C + 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.n_gemm += 1;
-            pl.add([op](cudaStream_t st) { return ffn_fused_launch(op, st); }, STEP_GEMM, "proj_ffn_fused");
+            pl.add_ffn_fused(op, "proj_ffn_fused");
             continue;
         }
         {
@@ -455,7 +455,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             if (gn_next && i == 2) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
             pl.gemm_flops += 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.n_gemm += 1;
-            pl.add([op](cudaStream_t st) { return ffn_fused_launch(op, st); }, STEP_GEMM, "ffn_fused");
+            pl.add_ffn_fused(op, "ffn_fused");
             continue;
         }
         {
@@ -652,6 +652,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         bp->out_slot = pl.steps.size();
         pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM, "final.proj");  // placeholder: final GEMM, bound per call
     }
+    if (getenv("PD_NO_L2_PREFETCH") == nullptr) pl.link_prefetch();
     return PD_OK;
 }
 

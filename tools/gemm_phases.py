@@ -10,6 +10,8 @@ from prediff_b200 import _lib as L  # noqa: E402
 L.init()
 dev = "cuda"
 BLOCKS = (0, 25, 1000, 1025) if os.environ.get("PD_PHASE_SPLIT") else (0, 25, 50)   # x + 1000 * z
+COLD = bool(os.environ.get("PD_PHASE_COLD"))   # weights cold in L2 (as in the real step: 274 MB of weights > L2)
+FLUSH = torch.zeros(96 * 1024 * 1024, device=dev) if COLD else None
 names = ["setup", "first_tile", "mainloop", "acc_ready", "first_chunk", "epilogue", "drain", "exit"]
 
 
@@ -39,6 +41,10 @@ def run(tag, samples, D, H, W, C, k, N, res, bf16_out, act, bn=0):
     t_first = None
     for blk in BLOCKS:
         stamps.zero_()
+        if COLD:   # evict the weights (and everything else) from the 126 MB L2, then re-touch the activations only
+            FLUSH.add_(1.0)
+            a.add_(0)
+            out.add_(0)
         L.check(L.lib().pd_op_conv_gemm_phases(*args(blk)))
         torch.cuda.synchronize()
         s = stamps.cpu().tolist()
