@@ -337,7 +337,7 @@ def main():
                      "frac": achieved / peaks["tensor_tflops"], "traffic": traffic,
                      "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                      "definition": "sample-steps/s per GPU x 653.43 GFLOP (SURVEY.md 8d) / sustained bf16 peak",
-                     "dominant_kernel": {"name": "gemm_tc_kernel (tcgen05 implicit GEMM: conv3d/conv2d/linear)",
+                     "dominant_kernel": {"name": "tcgen05 implicit-GEMM family: gemm_tc_kernel, gemm_tc_persistent_kernel, conv_streamk_kernel, ffn_fused_kernel (conv3d/conv2d/linear)",
                                          "launches_per_forward": int(n_gemm), "ms_per_forward": gemm_ms,
                                          "avg_launch_us": 1e3 * gemm_ms / max(n_gemm, 1),
                                          "tflops": gemm_flops / (gemm_ms * 1e-3) * 1e-12,
