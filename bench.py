@@ -12,6 +12,7 @@ metric through LatentDiffusion.sample() from pinned host frames to pinned host f
 VAE decode + the final all-gather + both copies inside the timed region). Weights are seeded random (no
 checkpoints offline), data synthetic. Prints ONE JSON line on rank 0.
 """
+import ctypes
 import argparse
 import json
 import os
@@ -144,6 +145,45 @@ def cpu_baseline_leg(args, budget_s=25.0):
     return {"value": B * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} UNet denoise steps at batch {B} (of the {args.ddim_steps} x K in the GPU run), fp32, "
                       f"torch CPU with {cores} threads"}
+
+
+CUBOID_GFLOP_PER_SAMPLE_STEP = 252.9   # StackCuboidSelfAttentionBlock incl. FFN
+
+
+def graph_trace(unet, B, x, t, cond, out):
+    """{site label: (launches, us)} of one UNet forward replayed as a CUDA graph with a stamp kernel after every launch."""
+    import collections
+    import numpy as np
+    import torch
+    from prediff_b200 import _lib as L
+    slots = 2048
+    ns = torch.zeros(slots, device=x.device, dtype=torch.int64)
+    labels = ctypes.create_string_buffer(1 << 16)
+    n = [0]
+
+    def traced():
+        n[0] = L.lib().pd_unet_trace_forward(unet.handle, L.ptr(x), L.ptr(t), L.ptr(cond), L.ptr(out), B, L.stream_ptr(),
+                                             L.ptr(ns), slots, labels, len(labels))
+        if n[0] < 0:
+            L.check(n[0])
+
+    traced()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        traced()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    lab = labels.value.decode().split("\n")[:n[0]]
+    d = np.diff(ns.cpu().numpy()[:n[0] + 1]).astype(np.float64) * 1e-3
+    slot = float(d.min())
+    agg = collections.OrderedDict()
+    for name, us in zip(lab, d):
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += us - slot
+    return agg
 
 
 def main():
@@ -303,6 +343,18 @@ def main():
         L.check(L.lib().pd_unet_profile_forward(unet.handle, L.ptr(zT), L.ptr(t), L.ptr(zc), L.ptr(eps), B,
                                                 L.stream_ptr(), stats))
     gemm_ms, n_gemm, other_ms, n_other, gemm_flops = list(stats)
+    # the same forward as a CUDA-graph replay with a %globaltimer stamp after every launch (tools/trace_unet.py --graph):
+    # launches are issued by the GPU front end, so kernels shorter than the ~5 us host launch cost are timed correctly
+    trace = graph_trace(unet, B, zT, t, zc, eps)
+    gemm_sites = ("conv1", "conv2", "qkv", "proj", "ffn1", "ffn2", "proj_ffn_fused", "ffn_fused", "skip", "up.conv",
+                  "down.reduction", "final.proj")
+    tr_gemm = [v for k, v in trace.items() if k.split(".")[-1] in gemm_sites or k in gemm_sites]
+    tr_other = [v for k, v in trace.items() if not (k.split(".")[-1] in gemm_sites or k in gemm_sites)]
+    tr_stack = [v for k, v in trace.items() if ".stack." in k]
+    gemm_ms = sum(v[1] for v in tr_gemm) * 1e-3
+    other_ms = sum(v[1] for v in tr_other) * 1e-3
+    n_gemm, n_other = sum(v[0] for v in tr_gemm), sum(v[0] for v in tr_other if v[1] > 0)
+    stack_ms = sum(v[1] for v in tr_stack) * 1e-3
     nk = ctypes.c_int()
     n_sub = L.lib().pd_sampler_sub_batches(ldm._sampler, B)   # concurrent sub-batches inside the loop
     L.check(L.lib().pd_unet_kernels_per_forward(unet.handle, B // n_sub, ctypes.byref(nk)))
@@ -343,7 +395,17 @@ def main():
                                          "tflops": gemm_flops / (gemm_ms * 1e-3) * 1e-12,
                                          "frac_of_peak": gemm_flops / (gemm_ms * 1e-3) * 1e-12 / peaks["tensor_tflops"],
                                          "share_of_forward": gemm_ms / (gemm_ms + other_ms)},
-                     "other_kernels": {"launches_per_forward": int(n_other), "ms_per_forward": other_ms}},
+                     "other_kernels": {"launches_per_forward": int(n_other), "ms_per_forward": other_ms},
+                     "kernel_timing": f"per-launch globaltimer stamps inside a CUDA-graph replay of one batch-{B} forward "
+                                      "(one stamp-kernel slot subtracted per launch)",
+                     # north_star's "cuboid-attention roofline": the StackCuboidSelfAttentionBlock subset (LayerNorm, QKV,
+                     # axial attention, projection, FFN of all 24 + 24 layers = 252.9 of the 653.43 GFLOP),
+                     # timed in place inside the same replay
+                     "cuboid_attention_blocks": {
+                         "gflop_per_sample_step": CUBOID_GFLOP_PER_SAMPLE_STEP, "ms_per_forward": stack_ms,
+                         "tflops": CUBOID_GFLOP_PER_SAMPLE_STEP * B / stack_ms,   # GFLOP / ms = TFLOP/s
+                         "frac_of_peak": CUBOID_GFLOP_PER_SAMPLE_STEP * B / stack_ms / peaks["tensor_tflops"],
+                         "share_of_forward": stack_ms / (gemm_ms + other_ms)}},
     }
     if ka_line is not None:
         ka_line["slowdown_vs_unguided"] = (ka_line["ms_per_step"]) / (ms / K)

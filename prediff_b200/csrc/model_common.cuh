@@ -143,8 +143,39 @@ struct Plan {
     std::string scope;                 // prefix applied to labels added from now on (e.g. "L0.res")
     double gemm_flops = 0;
     int n_gemm = 0;
+    // Optional side branch: steps [fork_begin, fork_end) do not depend on the steps that follow them until step
+    // `join_before` (the time-embedding MLP at the head of the UNet plan: its output is first read by a conv epilogue
+    // ~10 launches later). They run on `aux` between two events, so inside a captured graph they become a parallel branch
+    // instead of 36 us at the head of the dependent chain.
+    size_t fork_begin = 0, fork_end = 0, join_before = 0;
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int enable_fork(size_t begin, size_t end, size_t join) {
+        if (end <= begin || join < end || join >= steps.size()) return PD_OK;
+        PD_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        PD_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        PD_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        fork_begin = begin; fork_end = end; join_before = join;
+        return PD_OK;
+    }
     int run(cudaStream_t st) const {
-        for (const auto& s : steps) PD_TRY(s(st));
+        if (!aux) {
+            for (const auto& s : steps) PD_TRY(s(st));
+            return PD_OK;
+        }
+        for (size_t i = 0; i < steps.size(); ++i) {
+            if (i == fork_begin) {
+                PD_CUDA(cudaEventRecord(ev_fork, st));
+                PD_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
+            }
+            if (i >= fork_begin && i < fork_end) {
+                PD_TRY(steps[i](aux));
+                if (i + 1 == fork_end) PD_CUDA(cudaEventRecord(ev_join, aux));
+                continue;
+            }
+            if (i == join_before) PD_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+            PD_TRY(steps[i](st));
+        }
         return PD_OK;
     }
     void add(Step s, StepKind k = STEP_KERNEL, const char* label = "") {

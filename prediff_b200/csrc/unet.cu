@@ -653,6 +653,12 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM, "final.proj");  // placeholder: final GEMM, bound per call
     }
     if (getenv("PD_NO_L2_PREFETCH") == nullptr) pl.link_prefetch();
+    if (getenv("PD_NO_TEMB_FORK") == nullptr) {   // time-embedding MLP beside first_proj; joined at the first conv that adds it
+        size_t join = 0;
+        for (size_t i = 0; i < pl.labels.size() && !join; ++i)
+            if (pl.labels[i] == "L0.res.conv1") join = i;
+        if (join) PD_TRY(pl.enable_fork(bp->t_slot, bp->t_slot + 4, join));
+    }
     return PD_OK;
 }
 
