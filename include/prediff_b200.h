@@ -250,6 +250,14 @@ int pd_op_conv_gemm_streamk_phases(const void* A_bf16, const void* Wt_bf16, int 
                                    float* out_f32, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
                                    int ctas_per_sample, int dbg_cta, unsigned long long* stamps13, void* stream);
 
+/* pd_op_conv_gemm with fp32 output (+ bias, + in-place residual) that also ADDS the GroupNorm statistics of the output to
+ * gn_sums[samples][groups][2] (double: sum, sum of squares per (sample, group of N / groups channels)) - the table the
+ * GroupNorm that follows would otherwise compute in a pass of its own (time_embed.py:116-117 after :93). N % 256 == 0,
+ * N / groups in {8, 16, 32}, D*H*W % 32 == 0. streamk_ctas_per_sample > 0 runs the stream-K schedule. */
+int pd_op_conv_gemm_gnstats(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt, int kh,
+                            int kw, int N, const float* bias, const float* residual, float* out_f32, double* gn_sums,
+                            int groups, int streamk_ctas_per_sample, void* stream);
+
 /* Fused PositionwiseFFN at width 256 / hidden 1024 (cuboid_transformer.py:182-208 after its pre-norm):
  * x[M][256] += W2 GELU(W1 ln_in + b1) + b2 in one kernel (the hidden activation never leaves the SM), and, if ln_gamma
  * is given, ln_out[M][256] (bf16) = LayerNorm(new x row) * ln_gamma + ln_beta. W1 bf16 [1024][256], W2 bf16 [256][1024]. */

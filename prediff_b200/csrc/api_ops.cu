@@ -315,6 +315,38 @@ int pd_op_conv_gemm_streamk_phases(const void* A, const void* Wt, int samples, i
     return rc;
 }
 
+int pd_op_conv_gemm_gnstats(const void* A, const void* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
+                            int N, const float* bias, const float* residual, float* out_f32, double* gn_sums, int groups,
+                            int streamk_ctas_per_sample, void* stream) {
+    PD_TRY(gemm_init());
+    GemmGeom g = GemmGeom::conv(samples, D, H, W, C, kt, kh, kw);
+    GemmEpilogue e;
+    e.bias = bias; e.residual = residual; e.out_f32 = out_f32;
+    e.gn_sums = gn_sums; e.gn_groups = groups; e.gn_rows = D * H * W;
+    GemmOp op;
+    PD_TRY(gemm_make(&op, static_cast<const bf16*>(A), g, static_cast<const bf16*>(Wt), N, e, 256));
+    cudaStream_t st = S(stream);
+    if (streamk_ctas_per_sample <= 0) return gemm_launch(op, st);
+    std::vector<SkSeg> segs;
+    int n_slots = 0, n_flags = 0;
+    PD_TRY(gemm_streamk_schedule(op, streamk_ctas_per_sample, &segs, &n_slots, &n_flags));
+    SkSeg* segs_dev = nullptr;
+    float* partials = nullptr;
+    int* flags = nullptr;
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&segs_dev), segs.size() * sizeof(SkSeg), st));
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partials), (size_t)(n_slots + 1) * 128 * 256 * sizeof(float), st));
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&flags), (size_t)n_flags * sizeof(int), st));
+    PD_CUDA(cudaMemcpyAsync(segs_dev, segs.data(), segs.size() * sizeof(SkSeg), cudaMemcpyHostToDevice, st));
+    PD_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_flags * sizeof(int), st));
+    PD_CUDA(cudaStreamSynchronize(st));   // the host vector dies at return
+    PD_TRY(gemm_streamk_attach(&op, segs_dev, (int)segs.size() / 2, partials, flags));
+    const int rc = gemm_launch(op, st);
+    cudaFreeAsync(segs_dev, st);
+    cudaFreeAsync(partials, st);
+    cudaFreeAsync(flags, st);
+    return rc;
+}
+
 int pd_sevir_windows(const unsigned char* events_u8, int event_base, int n_events, int H, int W, int T_raw,
                      long long first_seq, int batch, int seq_len, int stride, float scale, float offset, float* out,
                      void* stream) {

@@ -205,6 +205,36 @@ def test_conv3d_streamk(B, D, H, W, C, N, P, with_ln):
         assert torch.equal(o1[0], out[-1])
 
 
+@pytest.mark.parametrize("B,D,H,W,C,N,P", [
+    (2, 13, 16, 16, 256, 256, 36),    # level-0 resblock conv1 (stream-K): 8 channels per group
+    (2, 13, 8, 8, 512, 512, 36),      # level-1 (ragged last tile: 832 rows = 6.5 tiles): 16 channels per group
+    (3, 4, 8, 8, 128, 256, 0),        # plain kernel (gemm_tc_kernel<256, 4, GN>)
+    (2, 13, 8, 8, 64, 512, 0),        # plain kernel, two n-tiles, ragged rows
+])
+def test_conv_fused_groupnorm_statistics(B, D, H, W, C, N, P):
+    """GroupNorm (sum, sum of squares) tables accumulated by the conv epilogue == statistics of the tensor it wrote."""
+    x = _randn(B, D, H, W, C, seed=31).bfloat16()
+    w = _randn(N, C, 3, 3, 3, seed=32, scale=(27 * C) ** -0.5)
+    wp = _pack_conv(w, C)
+    bias = _randn(N, seed=33)
+    res = _randn(B, D, H, W, N, seed=34)
+    out = res.clone()
+    sums = torch.zeros(B, 32, 2, device=DEV, dtype=torch.float64)
+    _sync_check(L.lib().pd_op_conv_gemm_gnstats(L.ptr(x), L.ptr(wp), B, D, H, W, C, 3, 3, 3, N, L.ptr(bias), L.ptr(out),
+                                                L.ptr(out), L.ptr(sums), 32, P, L.stream_ptr()))
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.bfloat16().float(), bias, padding=1).permute(0, 2, 3, 4, 1) + res
+    assert rel_err(out, ref) < 3e-5
+    g = out.double().reshape(B, -1, 32, N // 32)           # statistics of exactly what was written
+    want = torch.stack([g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))], dim=-1)
+    assert torch.allclose(sums, want, rtol=2e-6, atol=1e-3)
+    # and they reproduce torch's group_norm through the same mean / variance formula gn_apply uses
+    n = g.shape[1] * g.shape[3]
+    mean, var = sums[..., 0] / n, sums[..., 1] / n - (sums[..., 0] / n) ** 2
+    gn = F.group_norm(ref.permute(0, 4, 1, 2, 3), 32, eps=1e-5).permute(0, 2, 3, 4, 1)
+    mine = (out.reshape(B, -1, 32, N // 32) - mean[:, None, :, None]) / torch.sqrt(var[:, None, :, None] + 1e-5)
+    assert rel_err(mine.reshape_as(gn).float(), gn) < 1e-4
+
+
 def test_gemm_plain_no_epilogue_and_rowvec():
     M, K, N, samples = 512, 128, 128, 4
     a = _randn(samples * M, K, seed=5).bfloat16()
