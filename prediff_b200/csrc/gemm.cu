@@ -24,7 +24,7 @@ struct Cfg {
     static constexpr int kPipeBytes = STAGES * kStageBytes;
     static constexpr int kBarBytes = 512;
     // fused-LN gamma/beta + row-sum exchange inside the CTA + [128] row sums and one mbarrier written by the peer CTA
-    static constexpr int kLnBytes = 2 * BN * 4 + kEpiWarps * 32 * 8 + kGemmBlockM * 8 + 16;
+    static constexpr int kLnBytes = 2 * BN * 4 + kEpiWarps * 32 * 8 + 4 * kGemmBlockM * 8 + 16;   // peers: up to 4 ranks
     static_assert(kPipeBytes >= kEpiWarps * 2 * 4096, "epilogue slabs alias the pipeline stages");
     // barriers + tmem slot (512 B) then the per-CTA epilogue vector (bias + time-embedding row), BN floats
     static constexpr int kSmem = kPipeBytes + 1024 /*align slack*/ + kBarBytes + BN * 4 + kLnBytes;
@@ -50,8 +50,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float* ln_g = vec_s + BN;                                   // fused LayerNorm: gamma, beta, per-row partial sums
     float* ln_b = ln_g + BN;
     float2* ln_x = reinterpret_cast<float2*>(ln_b + BN);
-    float2* ln_peer = ln_x + kEpiWarps * 32;                    // [128]: the peer CTA's (sum, sumsq) of my rows
-    uint64_t* ln_bar = reinterpret_cast<uint64_t*>(ln_peer + kGemmBlockM);
+    float2* ln_peer = ln_x + kEpiWarps * 32;                    // [4][128]: (sum, sumsq) of my rows, by sender rank
+    uint64_t* ln_bar = reinterpret_cast<uint64_t*>(ln_peer + 4 * kGemmBlockM);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -89,7 +89,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         ptx::mbar_init(tmem_full_bar, 1);
         for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
-        ptx::mbar_init(ln_bar, kGemmBlockM);   // one remote arrive per row (cluster LayerNorm only)
+        // one remote arrive per row and peer (cluster LayerNorm only)
+        ptx::mbar_init(ln_bar, kGemmBlockM * (p.ln_cluster > 1 ? p.ln_cluster - 1 : 1));
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -312,36 +313,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                            p.gn_rows, sample * p.rows_per_sample + row0, n0 + c * 32, lane);
                     }
                 }
-                if constexpr (kOwnSlab && BN == 256 && kPerHalf == 4) {
+                if constexpr (kOwnSlab && ((BN == 256 && kPerHalf == 4) || (BN == 128 && kPerHalf == 2))) {
+                    constexpr int kBf = kPerHalf / 2;   // bf16 slabs (64 columns each) per warp
                     if (p.ln_gamma) {
-                        // ---- fused LayerNorm of the finished rows (this CTA owns all N = 256 columns) ----
+                        // ---- fused LayerNorm of the finished rows (this CTA / cluster owns all N columns) ----
                         // each row lives in two warps (column halves): exchange partial sums through smem
                         ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
                         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
                         const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
                         float tot1 = ln_s1 + o.x, tot2 = ln_s2 + o.y, inv_n = 1.0f / BN;
                         if (p.ln_cluster > 1) {
-                            // N = 2 x BN: send this CTA's row sums to the peer (DSMEM store + remote mbarrier arrive),
-                            // wait for the peer's; both CTAs add the two partials in the same order (own n-tile index
-                            // decides) so the statistics are bit-identical on both sides
-                            const uint32_t peer = ptx::cluster_ctarank() ^ 1u;
+                            // N = nc x BN: send this CTA's row sums to every peer (DSMEM store + remote mbarrier
+                            // arrive), wait for theirs; all CTAs add the nc partials in rank order, so the statistics are
+                            // bit-identical on every side
+                            const uint32_t nc = (uint32_t)p.ln_cluster, me = ptx::cluster_ctarank();
                             if (half == 0) {
-                                ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_u32(&ln_peer[q * 32 + lane]), peer), tot1, tot2);
-                                ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(ln_bar), peer));
+                                for (uint32_t d = 1; d < nc; ++d) {
+                                    const uint32_t peer = (me + d) & (nc - 1);
+                                    ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_u32(&ln_peer[me * kGemmBlockM + q * 32 + lane]), peer),
+                                                          tot1, tot2);
+                                    ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(ln_bar), peer));
+                                }
                             }
                             ptx::mbar_wait_cluster(ln_bar, 0);
-                            const float2 pr = ln_peer[q * 32 + lane];
-                            const bool first = (blockIdx.y & 1) == 0;
-                            tot1 = first ? tot1 + pr.x : pr.x + tot1;
-                            tot2 = first ? tot2 + pr.y : pr.y + tot2;
-                            inv_n = 1.0f / (2 * BN);
+                            float s1 = 0.f, s2 = 0.f;
+                            for (uint32_t r = 0; r < nc; ++r) {
+                                const float2 v = r == me ? make_float2(tot1, tot2) : ln_peer[r * kGemmBlockM + q * 32 + lane];
+                                s1 = r == 0 ? v.x : s1 + v.x;
+                                s2 = r == 0 ? v.y : s2 + v.y;
+                            }
+                            tot1 = s1;
+                            tot2 = s2;
+                            inv_n = 1.0f / (float)(nc * BN);
                         }
                         const float mean = tot1 * inv_n;
                         const float var = fmaxf(tot2 * inv_n - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + p.ln_eps);
-                        uint8_t* bslabs = smem + kEpiWarps * 4 * 4096 + e * (2 * 4096);   // 2 bf16 slabs per warp
+                        uint8_t* bslabs = smem + kEpiWarps * kPerHalf * 4096 + e * (kBf * 4096);   // kBf bf16 slabs per warp
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {          // bf16 slab j = my fp32 chunks 2j, 2j+1 (64 columns)
+                        for (int j = 0; j < kBf; ++j) {        // bf16 slab j = my fp32 chunks 2j, 2j+1 (64 columns)
                             uint8_t* brow = bslabs + j * 4096 + lane * 128;
 #pragma unroll
                             for (int cc = 0; cc < 2; ++cc) {
@@ -367,8 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         ptx::fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            ptx::tma_store_3d(&tmap_ln, bslabs, n0 + (c_begin + 0) * 32, row0, sample);
-                            ptx::tma_store_3d(&tmap_ln, bslabs + 4096, n0 + (c_begin + 2) * 32, row0, sample);
+#pragma unroll
+                            for (int j = 0; j < kBf; ++j)
+                                ptx::tma_store_3d(&tmap_ln, bslabs + j * 4096, n0 + (c_begin + 2 * j) * 32, row0, sample);
                             ptx::bulk_commit();
                         }
                     }
@@ -802,7 +813,9 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     if (want_ln) {
         PD_CHECK((N == 256 || N == 512) && e.out_f32 && e.ln_gamma && e.ln_beta, PD_ERR_SHAPE,
                  "gemm: the fused output LayerNorm needs N == 256 or 512 and an fp32 output (got N=%d)", N);
-        bn = 256;
+        // N = 512: four 128-wide CTAs per row tile in a cluster (half the epilogue per CTA, twice the CTAs; a
+        // 128 x 128 MMA costs as much as 128 x 256, but these GEMMs are epilogue-bound) - PD_LN_BN256=1: two 256-wide
+        bn = (N == 512 && getenv("PD_LN_BN256") == nullptr) ? 128 : 256;
     }
     if (!bn) {
         if (const char* s = getenv("PD_GEMM_BN")) bn = atoi(s);
@@ -883,9 +896,9 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     // on the batch, so results stay batch-invariant; the two partial sums are combined in a fixed order.
     op->split_k = (e.split_flags && (num_k >= 128 || (e.force_split == 2 && num_k >= 8)) && bn == 256 && e.out_f32 &&
                    e.act == ACT_NONE && !want_ln) ? 2 : 1;
-    if (want_ln) op->stages = 4;   // the LN pass needs every chunk resident in its own slab (192 KB of stages)
+    if (want_ln && bn == 256) op->stages = 4;   // the LN pass needs every chunk resident in its own slab (192 KB of stages)
     p.ln_gamma = want_ln ? e.ln_gamma : nullptr;
-    p.ln_cluster = want_ln ? N / 256 : 1;
+    p.ln_cluster = want_ln ? N / bn : 1;
     op->cluster_y = p.ln_cluster;
     p.ln_beta = e.ln_beta;
     p.ln_eps = e.ln_eps;
