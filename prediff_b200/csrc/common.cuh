@@ -178,6 +178,7 @@ __device__ __forceinline__ void prefetch_l2_share(const WRange& r, unsigned cta,
 // sample; dst = &sums[(sample * G + first group of this chunk) * 2] in the [S][G][2] double table of gn_stats().
 __device__ __forceinline__ void gn_chunk_accumulate(const float (&s)[8], const float (&q)[8], bool valid, int cpg, double* dst,
                                                     int lane) {
+    // v[2 g + {0, 1}] = (sum, sum of squares) of group g of this chunk for the lane's row; unused entries are zero
     float v[8];
     int nv;
     if (cpg == 8) {
@@ -195,24 +196,38 @@ __device__ __forceinline__ void gn_chunk_accumulate(const float (&s)[8], const f
         v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
         nv = 2;
     }
-    float mine = 0.f;
+    if (!valid) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k < nv) {   // warp-uniform
-            float t = valid ? v[k] : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == k) mine = t;
-        }
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
     }
-    if (lane < nv) atomicAdd(dst + lane, (double)mine);
+    // Transposing reduction over the 32 rows: 4 + 2 + 1 + 1 + 1 = 9 shuffles in 5 dependent steps. (The first version ran
+    // eight 5-step butterflies one after the other - 40 dependent shuffle / add pairs per chunk with two warps per
+    // scheduler to hide them, seen as a serial chain in the ncu source view - and cost the epilogue 6-7 us.)
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    float a0 = b4 ? v[4] : v[0], a1 = b4 ? v[5] : v[1], a2 = b4 ? v[6] : v[2], a3 = b4 ? v[7] : v[3];
+    const float s0 = b4 ? v[0] : v[4], s1 = b4 ? v[1] : v[5], s2 = b4 ? v[2] : v[6], s3 = b4 ? v[3] : v[7];
+    a0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    a1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    a2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+    a3 += __shfl_xor_sync(0xffffffffu, s3, 16);
+    float c0 = b3 ? a2 : a0, c1 = b3 ? a3 : a1;
+    const float t0 = b3 ? a0 : a2, t1 = b3 ? a1 : a3;
+    c0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+    c1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+    float e = b2 ? c1 : c0;
+    const float u = b2 ? c0 : c1;
+    e += __shfl_xor_sync(0xffffffffu, u, 4);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    const int k = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);   // the entry this lane quad ended up with
+    if ((lane & 3) == 0 && k < nv) atomicAdd(dst + k, (double)e);
 }
 
 // For the GEMM epilogues: re-reads the lane's 128-byte row of the swizzled fp32 slab it has just written (cell i sits at
 // ((i ^ sw) << 4)) and accumulates its statistics. Only instantiated in the GN = true kernel variants: the shuffle tree
 // inside the chunk loop slowed every epilogue by ~5 % (measured) when it was compiled into the common kernels, used or not.
 __device__ __forceinline__ void gn_chunk_from_slab(const uint8_t* my_row, uint32_t sw, bool valid, double* sums, int cpg,
-                                                int groups, int gn_rows, int global_row0, int col0, int lane) {
+                                                   int groups, int gsample, int col0, int lane) {
     float gs[8], gq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -220,9 +235,10 @@ __device__ __forceinline__ void gn_chunk_from_slab(const uint8_t* my_row, uint32
         gs[i] = (a.x + a.y) + (a.z + a.w);
         gq[i] = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
     }
-    // global_row0: first row of the warp counted over all samples; col0: first channel of the chunk
-    double* dst = sums + ((size_t)(global_row0 / gn_rows) * groups + col0 / cpg) * 2;
-    gn_chunk_accumulate(gs, gq, valid, cpg, dst, lane);
+    // gsample: GroupNorm sample of the warp's rows (computed once per warp by the caller); col0: first channel of the chunk;
+    // cpg is 8, 16 or 32, so the group index is a shift
+    const int shift = cpg == 8 ? 3 : (cpg == 16 ? 4 : 5);
+    gn_chunk_accumulate(gs, gq, valid, cpg, sums + ((size_t)gsample * groups + (col0 >> shift)) * 2, lane);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

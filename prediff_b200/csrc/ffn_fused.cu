@@ -439,6 +439,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
         float ln_s1 = 0.f, ln_s2 = 0.f;
+        const int gsample = GN ? row0 / p.gn_rows : 0;   // GroupNorm sample of my rows
 #pragma unroll 1
         for (int idx = 0; idx < 4; ++idx) {
             const int c = c_begin + idx;
@@ -466,8 +467,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::bulk_commit();
             }
             if constexpr (GN) if (row0 < p.M) {
-                gn_chunk_from_slab(my_row, sw, row0 + lane < p.M, p.gn_sums, p.gn_cpg, p.gn_groups, p.gn_rows, row0, c * 32,
-                                   lane);
+                gn_chunk_from_slab(my_row, sw, row0 + lane < p.M, p.gn_sums, p.gn_cpg, p.gn_groups, gsample, c * 32, lane);
             }
         }
         if (p.ln_gamma) {

@@ -257,6 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                 }
                 float ln_s1 = 0.f, ln_s2 = 0.f;
+                const int gsample = GN ? (sample * p.rows_per_sample + row0) / p.gn_rows : 0;   // GroupNorm sample of my rows
 #pragma unroll 1
                 for (int c = c_begin, idx = 0; c < c_end; ++c, ++idx) {
                     const int s = kOwnSlab ? idx : (idx % kSlabs);
@@ -310,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     if constexpr (GN) if (row0 < p.rows_per_sample) {   // statistics for the GroupNorm that reads this output
                         gn_chunk_from_slab(my_row, sw, row0 + lane < p.rows_per_sample, p.gn_sums, p.gn_cpg, p.gn_groups,
-                                           p.gn_rows, sample * p.rows_per_sample + row0, n0 + c * 32, lane);
+                                           gsample, n0 + c * 32, lane);
                     }
                 }
                 if constexpr (kOwnSlab && ((BN == 256 && kPerHalf == 4) || (BN == 128 && kPerHalf == 2))) {

@@ -235,6 +235,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             if (et == 0) SK_STAMP(8);
             float ln_s1 = 0.f, ln_s2 = 0.f;
+            const int gsample = GN ? (sample * p.rows_per_sample + row0) / p.gn_rows : 0;   // GroupNorm sample of my rows
 #pragma unroll 1
             for (int idx = 0; idx < 4; ++idx) {
                 const int c = c_begin + idx;
@@ -279,7 +280,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 if constexpr (GN) if (row0 < p.rows_per_sample) {   // statistics for the GroupNorm that reads this output
                     gn_chunk_from_slab(my_row, sw, row0 + lane < p.rows_per_sample, p.gn_sums, p.gn_cpg, p.gn_groups,
-                                       p.gn_rows, sample * p.rows_per_sample + row0, n0 + c * 32, lane);
+                                       gsample, n0 + c * 32, lane);
                 }
             }
             if (p.ln_gamma) {   // fused LayerNorm of the finished rows (N == 256: this CTA owns whole rows)

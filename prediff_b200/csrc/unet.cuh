@@ -1,6 +1,7 @@
 // CuboidTransformerUNet on the GPU: weights (reference key names), repacked bf16 operands and per-batch plans.
 #pragma once
 #include "model_common.cuh"
+#include <cstdlib>
 
 namespace pd {
 
@@ -64,7 +65,11 @@ private:
                   bool* gn_fused = nullptr);
     // The LayerNorm that follows a GEMM is computed in that GEMM's epilogue when a CTA (width 256) or a 2-CTA cluster
     // (width 512) owns whole rows; the resblock's conv2 only when it is not split-K (27 * C / 64 < 128 k-blocks).
-    bool ln_fusable(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 || c == 512; }
+    bool ln_fusable(int lvl) const {
+        const int c = lvl ? C1 : C0;
+        static const bool no_cluster = getenv("PD_NO_LN_CLUSTER") != nullptr;   // A/B: separate LayerNorm launches at 512
+        return c == 256 || (c == 512 && !no_cluster);
+    }
     bool ln_fusable_conv(int lvl) const { const int c = lvl ? C1 : C0; return c == 256; }
     int num_gn_slots() const;
     template <class A>
