@@ -330,12 +330,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(t_lane + 256 + (c_begin + idx) * 32, v);
                 ptx::tmem_ld_wait();
+                float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains, not one of 32
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float a = __uint_as_float(v[i]);
-                    s1 += a;
-                    s2 = fmaf(a, a, s2);
+                    p1[i & 3] += a;
+                    p2[i & 3] = fmaf(a, a, p2[i & 3]);
                 }
+                s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
             }
             ln_x[(q * 2 + half) * 32 + lane] = make_float2(s1, s2);
             asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
