@@ -89,10 +89,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         ptx::mbar_init(tmem_full_bar, 1);
         for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
-        // one remote arrive per row and peer (cluster LayerNorm only)
-        ptx::mbar_init(ln_bar, kGemmBlockM * (p.ln_cluster > 1 ? p.ln_cluster - 1 : 1));
+        // cluster LayerNorm: the peers' row sums arrive as asynchronous DSMEM stores counted in bytes on this barrier
+        ptx::mbar_init(ln_bar, 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
+        if (p.ln_gamma && p.ln_cluster > 1)   // 8 bytes per row from each of the other CTAs of the cluster
+            ptx::mbar_arrive_expect_tx(ln_bar, (uint32_t)(p.ln_cluster - 1) * kGemmBlockM * 8u);
     }
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -119,7 +121,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();
     // cluster LayerNorm: the peer's mbarrier must be initialised before anything is sent to it
-    if (p.ln_gamma && p.ln_cluster > 1) ptx::cluster_sync_all();
+    // (split phase: arrive here, wait right before the first store into a peer - nobody stalls at start-up)
+    if (p.ln_gamma && p.ln_cluster > 1) ptx::cluster_arrive();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // dependents are released only now: a dependent CTA that became co-resident before this CTA owned its TMEM columns
@@ -328,12 +331,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             // arrive), wait for theirs; all CTAs add the nc partials in rank order, so the statistics are
                             // bit-identical on every side
                             const uint32_t nc = (uint32_t)p.ln_cluster, me = ptx::cluster_ctarank();
+                            ptx::cluster_wait();   // every peer has initialised and armed its ln_bar (arrive: kernel start)
                             if (half == 0) {
                                 for (uint32_t d = 1; d < nc; ++d) {
                                     const uint32_t peer = (me + d) & (nc - 1);
-                                    ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_u32(&ln_peer[me * kGemmBlockM + q * 32 + lane]), peer),
-                                                          tot1, tot2);
-                                    ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(ln_bar), peer));
+                                    ptx::st_async_cluster_f32x2(
+                                        ptx::mapa(ptx::smem_u32(&ln_peer[me * kGemmBlockM + q * 32 + lane]), peer), tot1, tot2,
+                                        ptx::mapa(ptx::smem_u32(ln_bar), peer));
                                 }
                             }
                             ptx::mbar_wait_cluster(ln_bar, 0);
@@ -439,6 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         __syncwarp();
         if (e == 0 && lane == 0) PD_STAMP(7);
     }
+    if (warp < 2 && p.ln_gamma && p.ln_cluster > 1) ptx::cluster_wait();   // pairs with the arrive of these two warps
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, C::kTmemCols);

@@ -91,6 +91,17 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// split-phase cluster barrier: arrive early (non-blocking), wait just before the first access to a peer's shared memory
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// Asynchronous DSMEM store of two floats whose completion is counted (8 bytes) on the DESTINATION CTA's mbarrier: the
+// consumer arms its barrier with expect_tx and simply waits - no release fence on the producer side (an
+// mbarrier.arrive.release.cluster per thread costs a MEMBAR + ERRBAR + CCTL.IVALL sequence, ~2 us per kernel here).
+__device__ __forceinline__ void st_async_cluster_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+                 "f"(a), "f"(b), "r"(cluster_bar_addr)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
