@@ -192,7 +192,8 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                 }
-                __threadfence();
+                // the CTA barrier orders every warp's stores before thread 0, whose gpu-scope fence then publishes them
+                // (cumulativity) ahead of the flag increment - one fence per CTA instead of one per thread
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
                 if (et == 0) {
                     __threadfence();

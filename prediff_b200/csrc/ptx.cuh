@@ -92,7 +92,9 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  : "memory");
 }
 // split-phase cluster barrier: arrive early (non-blocking), wait just before the first access to a peer's shared memory
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// (relaxed arrive: the only thing peers must see is the mbarrier initialisation, which fence.mbarrier_init.release.cluster
+// - fence_barrier_init() - already publishes; a releasing arrive costs a MEMBAR + ERRBAR sequence at kernel start)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // Asynchronous DSMEM store of two floats whose completion is counted (8 bytes) on the DESTINATION CTA's mbarrier: the
 // consumer arms its barrier with expect_tx and simply waits - no release fence on the producer side (an
