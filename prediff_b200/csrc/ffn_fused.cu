@@ -274,30 +274,37 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int half = e >> 2;         // column half
         const int et = threadIdx.x - 64;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        for (int i = et; i < kHid; i += 32 * kEpiWarps) b1_s[i] = __ldg(p.b1 + i);
-        for (int i = et; i < kC; i += 32 * kEpiWarps) {
-            b2_s[i] = __ldg(p.b2 + i);
-            if (p.ln_gamma) {
-                ln_g[i] = __ldg(p.ln_gamma + i);
-                ln_b[i] = __ldg(p.ln_beta + i);
-            }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int row0 = row_tile + q * 32;
         const int c_begin = half * 4;              // this warp's four 32-column chunks of the 256-wide row
         uint64_t* my_bar = res_bar + 4 * e;
+        uint8_t* islab = sMid + e * (2 * 4096);
+        auto load_x_round = [&](int r) {           // PROJ: two residual slabs of this warp's rows -> the idle mid region
+            for (int j = 0; j < 2; ++j) {
+                ptx::mbar_arrive_expect_tx(&my_bar[2 * r + j], 4096);
+                ptx::tma_load_3d(islab + j * 4096, &tmap_x, &my_bar[2 * r + j], (c_begin + 2 * r + j) * 32, row0, 0);
+            }
+        };
+        if (PROJ && lane == 0) load_x_round(0);    // in flight while the bias / LayerNorm vectors are staged below
+        {   // stage b1 / b2 / gamma / beta: all of a thread's loads are issued before the first store (one latency, not 4-7)
+            constexpr int kPer = kHid / (32 * kEpiWarps);   // 4
+            float t1[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) t1[k] = __ldg(p.b1 + et + k * 32 * kEpiWarps);
+            const float t2 = __ldg(p.b2 + et);
+            const float tg = p.ln_gamma ? __ldg(p.ln_gamma + et) : 0.f, tb = p.ln_gamma ? __ldg(p.ln_beta + et) : 0.f;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) b1_s[et + k * 32 * kEpiWarps] = t1[k];
+            b2_s[et] = t2;
+            if (p.ln_gamma) { ln_g[et] = tg; ln_b[et] = tb; }
+        }
+        static_assert(kC == 32 * kEpiWarps && kHid % (32 * kEpiWarps) == 0, "vector staging assumes 256 epilogue threads");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (PROJ) {
             // ---- preset acc2 with x + bp (two rounds of two 4 KB slabs per warp through the idle mid region) ----
-            uint8_t* islab = sMid + e * (2 * 4096);
 #pragma unroll 1
             for (int r = 0; r < 2; ++r) {
-                if (lane == 0) {
-                    for (int j = 0; j < 2; ++j) {
-                        ptx::mbar_arrive_expect_tx(&my_bar[2 * r + j], 4096);
-                        ptx::tma_load_3d(islab + j * 4096, &tmap_x, &my_bar[2 * r + j], (c_begin + 2 * r + j) * 32, row0, 0);
-                    }
-                }
+                if (lane == 0 && r > 0) load_x_round(r);
 #pragma unroll 1
                 for (int j = 0; j < 2; ++j) {
                     const int c = c_begin + 2 * r + j;
@@ -382,8 +389,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::tma_store_3d(&tmap_ln1st, islab, (c_begin + 0) * 32, row0, 0);
                 ptx::tma_store_3d(&tmap_ln1st, islab + 4096, (c_begin + 2) * 32, row0, 0);
                 ptx::bulk_commit();
-                ptx::bulk_wait_all<0>();            // written (not just read): the producer will TMA-load it back
-                ptx::fence_proxy_async_all();
+                // written (not just read): the producer will TMA-load it back. Both sides are async-proxy accesses to
+                // global memory ordered by the wait + the mbarrier hand-off; the full-proxy fence that used to sit here
+                // (MEMBAR.GPU + CCTL.IVALL, ~1.4 us per launch in the ncu source view) is not needed
+                ptx::bulk_wait_all<0>();
                 ptx::mbar_arrive(ln1_ready);
             }
             __syncwarp();
