@@ -24,7 +24,18 @@ struct UNet::Bufs {
     int* split_flags;  // split-K tile handshake flags, shared by all convs of the plan (kernels run one at a time)
 };
 constexpr int kSplitFlagInts = 8192;
-constexpr int kStreamKCtasPerSample = 36;
+constexpr int kStreamKCtasPerSampleDefault = 36;
+// CTAs per sample of the stream-K cut (PD_STREAMK_CPS overrides, for experiments; it must not depend on the batch, or
+// results stop being identical between a batch and its shards)
+int stream_k_ctas_per_sample() {
+    static const int v = [] {
+        const char* e = getenv("PD_STREAMK_CPS");
+        const int n = e ? atoi(e) : 0;
+        return n > 0 ? n : kStreamKCtasPerSampleDefault;
+    }();
+    return v;
+}
+#define kStreamKCtasPerSample stream_k_ctas_per_sample()
 bool gn_fusion_on() {
     static const bool on = getenv("PD_NO_GN_FUSION") == nullptr;
     return on;
