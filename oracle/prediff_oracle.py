@@ -120,10 +120,111 @@ def ffn(sd, p, x):
     return F.linear(y, sd[f"{p}.ffn_2.weight"], sd[f"{p}.ffn_2.bias"]) + x
 
 
-def stack_block(sd, p, x, heads):
-    """StackCuboidSelfAttentionBlock.forward with use_inter_ffn (cuboid_transformer.py:1147-1156), axial."""
-    for i in range(3):
-        x = x + axial_attention(sd, f"{p}.attn_l.{i}", x, heads, i)
+def _to_cuboids(x, size, strategy):
+    """cuboid_reorder (cuboid_transformer.py:388-429): (B, T, H, W, C) -> (B, num_cuboids, volume, C). Per axis the
+    padded length splits as (blocks, in-block) for 'l' and (in-block, blocks) for 'd'."""
+    B, C = x.shape[0], x.shape[-1]
+    shape, blk, inn = [B], [], []
+    for a in range(3):
+        n = x.shape[1 + a] // size[a]
+        shape += [n, size[a]] if strategy[a] == "l" else [size[a], n]
+        blk.append(1 + 2 * a + (0 if strategy[a] == "l" else 1))
+        inn.append(1 + 2 * a + (1 if strategy[a] == "l" else 0))
+    y = x.reshape(shape + [C]).permute([0] + blk + inn + [7])
+    return y.reshape(B, -1, size[0] * size[1] * size[2], C)
+
+
+def _from_cuboids(y, size, strategy, padded):
+    """cuboid_reorder_reverse (cuboid_transformer.py:432-467)."""
+    B, C = y.shape[0], y.shape[-1]
+    n = [padded[a] // size[a] for a in range(3)]
+    y = y.reshape([B] + n + list(size) + [C])
+    perm = [0]
+    for a in range(3):
+        perm += [1 + a, 4 + a] if strategy[a] == "l" else [4 + a, 1 + a]
+    return y.permute(perm + [7]).reshape(B, padded[0], padded[1], padded[2], C)
+
+
+def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_type="zeros"):
+    """The attention core of CuboidSelfAttentionLayer.forward (cuboid_transformer.py:812-966, no global vectors)
+    from the per-token q|k|v rows: qkv (B, T, H, W, 3C), taken BEFORE padding (qkv has no bias, so the zero rows the
+    reference pads after its LayerNorm map to zero q, k, v) -> (B, T, H, W, C) before the final projection.
+    Cuboid size / shift update :563-592; zero padding at the end of each axis; roll by -shift; reorder; mask =
+    same shifted-window region (and, for 'ignore', both tokens real) :470-528; bias = table[index[:vol, :vol]]
+    with the index built from the constructor's cuboid size :714-734, 855-861; masked_softmax :531-560."""
+    B, T, H, W, C3 = qkv.shape
+    C, hd = C3 // 3, C3 // 3 // heads
+    dims = (T, H, W)
+    size, shift = list(size0), list(shift0)
+    for a in range(3):
+        if strategy[a] == "d":
+            shift[a] = 0
+        if dims[a] <= size[a]:
+            size[a], shift[a] = dims[a], 0
+    pad = [(size[a] - dims[a] % size[a]) % size[a] for a in range(3)]
+    padded = [dims[a] + pad[a] for a in range(3)]
+    real = torch.ones(1, T, H, W, 1)
+    region = torch.zeros(1, *padded, 1)
+    for a in range(3):  # three slices per axis, last assignment wins (a zero shift leaves a single region)
+        idx = torch.arange(padded[a])
+        lab = torch.zeros(padded[a])
+        lab[idx >= padded[a] - size[a]] = 1
+        if shift[a] > 0:
+            lab[idx >= padded[a] - shift[a]] = 2
+        else:
+            lab[:] = 2
+        view = [1, 1, 1, 1, 1]
+        view[1 + a] = padded[a]
+        region = region * 3 + lab.view(view)
+    y = F.pad(qkv, (0, 0, 0, pad[2], 0, pad[1], 0, pad[0]))
+    real = F.pad(real, (0, 0, 0, pad[2], 0, pad[1], 0, pad[0]))
+    if any(s > 0 for s in shift):
+        y = torch.roll(y, shifts=[-s for s in shift], dims=(1, 2, 3))
+        real = torch.roll(real, shifts=[-s for s in shift], dims=(1, 2, 3))
+    y = _to_cuboids(y, size, strategy)                      # (B, nc, vol, 3C)
+    nc, vol = y.shape[1], y.shape[2]
+    region = _to_cuboids(region, size, strategy)[0, :, :, 0]  # (nc, vol)
+    mask = region[:, :, None] == region[:, None, :]
+    if padding_type == "ignore":
+        ok = _to_cuboids(real, size, strategy)[0, :, :, 0] > 0
+        mask = mask & ok[:, :, None] & ok[:, None, :]
+    q, k, v = y.reshape(B, nc, vol, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)
+    s = (q * hd ** -0.5) @ k.transpose(-1, -2)                # (B, heads, nc, vol, vol)
+    bt, bh, bw = size0
+    i = torch.arange(vol)
+    ct, ch, cw = i // (bh * bw), (i // bw) % bh, i % bw
+    rel = ((ct[:, None] - ct[None] + bt - 1) * (2 * bh - 1) + (ch[:, None] - ch[None] + bh - 1)) * (2 * bw - 1) \
+        + (cw[:, None] - cw[None] + bw - 1)
+    s = s + table[rel].permute(2, 0, 1)[:, None]
+    s = s.masked_fill(~mask, -1e18)
+    p = torch.softmax(s, dim=-1) * mask
+    o = (p @ v).permute(0, 2, 3, 1, 4).reshape(B, nc, vol, C)
+    o = _from_cuboids(o, size, strategy, padded)
+    if any(s_ > 0 for s_ in shift):
+        o = torch.roll(o, shifts=list(shift), dims=(1, 2, 3))
+    return o[:, :T, :H, :W].contiguous()
+
+
+def cuboid_attention(sd, p, x, heads, size0, strategy, shift0, padding_type="zeros"):
+    """CuboidSelfAttentionLayer.forward (cuboid_transformer.py:812-966) for any cuboid size / strategy / shift with
+    'zeros' or 'ignore' padding: LN -> qkv (no bias) -> cuboid_attention_core -> proj. x: (B, T, H, W, C)."""
+    C = x.shape[-1]
+    y = F.layer_norm(x, (C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
+    o = cuboid_attention_core(F.linear(y, sd[f"{p}.qkv.weight"]), sd[f"{p}.relative_position_bias_table"], heads,
+                              size0, strategy, shift0, padding_type)
+    return F.linear(o, sd[f"{p}.proj.weight"], sd[f"{p}.proj.bias"])
+
+
+def stack_block(sd, p, x, heads, layers=None, padding_type="zeros"):
+    """StackCuboidSelfAttentionBlock.forward with use_inter_ffn (cuboid_transformer.py:1147-1156). `layers`: list of
+    (cuboid_size, strategy, shift_size) (None = the axial pattern of the shipped config)."""
+    if layers is None:
+        for i in range(3):
+            x = x + axial_attention(sd, f"{p}.attn_l.{i}", x, heads, i)
+            x = ffn(sd, f"{p}.ffn_l.{i}", x)
+        return x
+    for i, (size, strategy, shift) in enumerate(layers):
+        x = x + cuboid_attention(sd, f"{p}.attn_l.{i}", x, heads, size, strategy, shift, padding_type)
         x = ffn(sd, f"{p}.ffn_l.{i}", x)
     return x
 
@@ -149,6 +250,8 @@ def unet_forward(sd, cfg, x, t, cond):
     """CuboidTransformerUNet.forward (src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py:406-493).
     x (B,T_out,H,W,C), t (B,) int64, cond (B,T_in,H,W,C) -> (B,T_out,H,W,C)."""
     heads = cfg.num_heads
+    pats = tuple(getattr(cfg, "patterns", ("axial", "axial")))
+    layers = [None if pats[lvl] == "axial" else cfg.layers(lvl) for lvl in range(2)]
     x = torch.cat([cond, x], dim=1)
     ind = torch.ones_like(x[..., :1])
     ind[:, cfg.t_in:] = 0.0
@@ -169,7 +272,7 @@ def unet_forward(sd, cfg, x, t, cond):
         g = _gn_groups(cfg.units[lvl])
         for d in range(cfg.depth[lvl]):
             x = _res_block3d(sd, f"{name_t}.{lvl}", x.permute(0, 4, 1, 2, 3), t_emb, g, g).permute(0, 2, 3, 4, 1)
-            x = stack_block(sd, f"{name_s}.{lvl}.{d}", x, heads)
+            x = stack_block(sd, f"{name_s}.{lvl}.{d}", x, heads, layers[lvl], getattr(cfg, "padding_type", "zeros"))
         return x
 
     x = level("down_time_embed_blocks", "down_self_blocks", 0, x)

@@ -22,6 +22,9 @@ class UNetConfig:
     base_units: int = 256
     depth: Tuple[int, int] = (4, 4)
     num_heads: int = 4
+    # block_attn_patterns per level (names of cuboid_transformer_patterns.py) and padding_type ('zeros' | 'ignore')
+    patterns: Tuple[str, str] = ("axial", "axial")
+    padding_type: str = "zeros"
 
     @property
     def T(self):
@@ -35,10 +38,15 @@ class UNetConfig:
     def temb_channels(self):
         return 4 * self.base_units
 
+    def layers(self, level):
+        """(cuboid_size, strategy, shift_size) of every attention layer of a level's StackCuboidSelfAttentionBlock:
+        the level's pattern evaluated on its mem_shape (cuboid_transformer_unet.py:201-214, 387-404)."""
+        from . import patterns as P
+        return P.resolve(self.patterns[level], (self.T, self.h >> level, self.w >> level, self.units[level]))
+
     def cuboids(self, level):
-        """self_axial pattern (cuboid_transformer_patterns.py:19-37) at a level's resolution."""
-        h, w = self.h >> level, self.w >> level
-        return [(self.T, 1, 1), (1, h, 1), (1, 1, w)]
+        """Constructor cuboid sizes of a level's attention layers (axial: (T,1,1), (1,H,1), (1,1,W))."""
+        return [size for size, _, _ in self.layers(level)]
 
 
 @dataclass

@@ -62,15 +62,16 @@ def install_stubs():
 
 def ref_unet(cfg):
     from prediff.models.cuboid_transformer import CuboidTransformerUNet
+    pats = list(getattr(cfg, "patterns", ("axial", "axial")))
     # arguments as in scripts/prediff/sevirlr/train_sevirlr_prediff.py:91-137 with cfg.yaml:157-206
     m = CuboidTransformerUNet(
         input_shape=[cfg.t_in, cfg.h, cfg.w, cfg.c], target_shape=[cfg.t_out, cfg.h, cfg.w, cfg.c],
         base_units=cfg.base_units, scale_alpha=1.0, num_heads=cfg.num_heads, attn_drop=0.1, proj_drop=0.1, ffn_drop=0.1,
         downsample=2, downsample_type="patch_merge", upsample_type="upsample", upsample_kernel_size=3,
-        depth=list(cfg.depth), block_attn_patterns=["axial"] * 2, num_global_vectors=0, use_global_vector_ffn=False,
+        depth=list(cfg.depth), block_attn_patterns=pats, num_global_vectors=0, use_global_vector_ffn=False,
         use_global_self_attn=True, separate_global_qkv=True, global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
-        norm_layer="layer_norm", padding_type="zeros", checkpoint_level=0, pos_embed_type="t+h+w",
-        use_relative_pos=True, self_attn_use_final_proj=True, time_embed_channels_mult=4,
+        norm_layer="layer_norm", padding_type=getattr(cfg, "padding_type", "zeros"), checkpoint_level=0,
+        pos_embed_type="t+h+w", use_relative_pos=True, self_attn_use_final_proj=True, time_embed_channels_mult=4,
         time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0, unet_res_connect=True)
     sd = Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED)
     res = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
@@ -302,6 +303,36 @@ def gen_unet(tag, cfg, B, ts):
 
 
 @torch.no_grad()
+def gen_patterns():
+    """Other cuboid patterns: single CuboidSelfAttentionLayer outputs of the unmodified reference
+    class for shifted / padded / dilated / clipped cuboids under 'zeros' and 'ignore' padding, and forwards of the
+    unmodified reference UNet built with non-axial block_attn_patterns."""
+    import dataclasses
+    from prediff.models.cuboid_transformer.cuboid_transformer import CuboidSelfAttentionLayer
+    import pattern_cases as PC
+    out = {}
+    for tag, dims, C, heads, size, strat, shift, pad in PC.LAYER_CASES:
+        m = CuboidSelfAttentionLayer(dim=C, num_heads=heads, cuboid_size=size, shift_size=shift, strategy=tuple(strat),
+                                     padding_type=pad, qkv_bias=False, attn_drop=0.0, proj_drop=0.0,
+                                     use_final_proj=True, norm_layer="layer_norm", use_global_vector=False,
+                                     checkpoint_level=0, use_relative_pos=True).eval()
+        sd = Wt.seeded_state_dict(PC.layer_spec(C, heads, size), PC.LAYER_SEED)
+        res = m.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not res.unexpected_keys and res.missing_keys == ["relative_position_index"], res
+        x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+        out[f"layer_{tag}"] = m(x)
+    for tag, pats, pad in PC.UNET_CASES:
+        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
+        m = ref_unet(cfg)
+        x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c)
+        cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c)
+        t0 = time.time()
+        out[f"unet_{tag}"] = m(x, torch.tensor([500], dtype=torch.long), cond)
+        print(f"patterns unet_{tag}: {time.time() - t0:.1f}s, out std {out[f'unet_{tag}'].std():.3f}")
+    save("patterns", **out)
+
+
+@torch.no_grad()
 def gen_vae(tag, cfg, N):
     m = ref_vae(cfg)
     x = inp(4321, N, 1, cfg.h, cfg.w, uniform=True)
@@ -406,5 +437,7 @@ if __name__ == "__main__":
         gen_skill()
     if "loader" in todo:
         gen_loader()
+    if "patterns" in todo:
+        gen_patterns()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

@@ -1,0 +1,27 @@
+"""Shared case lists for the cuboid-pattern goldens (gen_golden.py writes them, tests read them)."""
+
+# (tag, (T, H, W), C, heads, cuboid_size, strategy, shift_size, padding_type)
+LAYER_CASES = [
+    ("swin_pad_shift_z", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "zeros"),
+    ("swin_pad_shift_i", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "ignore"),
+    ("dilated_i", (13, 8, 8), 32, 2, (1, 4, 4), "ddd", (0, 0, 0), "ignore"),
+    ("mixed_ragged_z", (6, 7, 9), 32, 2, (4, 3, 4), "ldl", (2, 1, 2), "zeros"),
+    ("mixed_ragged_i", (6, 7, 9), 32, 2, (4, 3, 4), "ldl", (2, 1, 2), "ignore"),
+    ("clipped_i", (5, 6, 6), 32, 2, (8, 4, 8), "lll", (4, 2, 4), "ignore"),
+    ("full_z", (5, 8, 8), 32, 2, (5, 8, 8), "lll", (0, 0, 0), "zeros"),
+    ("plane_hd32", (3, 8, 8), 64, 2, (1, 8, 8), "lll", (0, 0, 0), "zeros"),
+]
+LAYER_SEED = 4004
+
+# (tag, block_attn_patterns, padding_type): tiny UNet (base_units 64, depth (1, 1)), B = 1, t = 500
+UNET_CASES = [
+    ("swin_lg", ("video_swin_4x4", "spatial_lg_4"), "zeros"),
+    ("dst_dilate", ("divided_st", "axial_space_dilate_2"), "ignore"),
+    ("full_swin", ("full", "video_swin_2x8"), "ignore"),
+]
+
+
+def layer_spec(C, heads, size):
+    n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
+    return [("a.relative_position_bias_table", (n_rel, heads)), ("a.qkv.weight", (3 * C, C)),
+            ("a.proj.weight", (C, C)), ("a.proj.bias", (C,)), ("a.norm.weight", (C,)), ("a.norm.bias", (C,))]

@@ -1,0 +1,107 @@
+"""CPU tests for the non-axial cuboid patterns: pins the oracle's general cuboid attention and
+the pattern-configured UNet against outputs of the unmodified reference (tests/golden/patterns.npz), and checks the
+host-side geometry tables the CUDA kernel consumes (prediff_b200/patterns.py) against the pinned oracle."""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prediff_oracle as O
+from prediff_b200 import patterns as P
+from prediff_b200 import weights as Wt
+from tests.golden import pattern_cases as PC
+from tests.golden.gen_golden import UNET_SEED, inp
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "patterns.npz"))
+
+
+def maxrel(a, b):
+    a, b = torch.as_tensor(np.asarray(a)).double(), torch.as_tensor(np.asarray(b)).double()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def test_pattern_registry_names():
+    # names registered by cuboid_transformer_patterns.py:60-118
+    for name in ("full", "axial", "video_swin", "divided_st", "spatial_lg_v1", "video_swin_2x8", "video_swin_10x32",
+                 "spatial_lg_4", "axial_space_dilate_4"):
+        assert P.resolve(name, (13, 16, 16, 256))
+    for bad in ("video_swin_3x4", "spatial_lg_5", "axial_space_dilate_3", "nope"):
+        with pytest.raises(KeyError):
+            P.get(bad)
+    assert P.resolve("video_swin_2x8", (13, 8, 8, 512)) == [((2, 8, 8), ("l", "l", "l"), (0, 0, 0)),
+                                                             ((2, 8, 8), ("l", "l", "l"), (1, 4, 4))]
+    assert P.resolve("spatial_lg_8", (13, 8, 8, 512)) == [((13, 1, 1), ("l",) * 3, (0, 0, 0)), ((1, 8, 8), ("l",) * 3, (0, 0, 0))]
+    assert [s for s, _, _ in P.resolve("axial_space_dilate_2", (13, 8, 8, 512))] == \
+        [(13, 1, 1), (1, 4, 1), (1, 4, 1), (1, 1, 4), (1, 1, 4)]
+
+
+@pytest.mark.parametrize("case", PC.LAYER_CASES, ids=[c[0] for c in PC.LAYER_CASES])
+def test_oracle_layer_vs_reference(case):
+    tag, dims, C, heads, size, strat, shift, pad = case
+    sd = O.to_torch_sd(Wt.seeded_state_dict(PC.layer_spec(C, heads, size), PC.LAYER_SEED))
+    x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+    out = O.cuboid_attention(sd, "a", x, heads, size, tuple(strat), shift, pad)
+    assert maxrel(out, G[f"layer_{tag}"]) < 2e-5
+
+
+@pytest.mark.parametrize("case", PC.UNET_CASES, ids=[c[0] for c in PC.UNET_CASES])
+def test_oracle_unet_patterns_vs_reference(case):
+    tag, pats, pad = case
+    cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
+    sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED))
+    x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    out = O.unet_forward(sd, cfg, x, torch.tensor([500]), cond)
+    assert maxrel(out, G[f"unet_{tag}"]) < 1e-4
+
+
+def attention_from_tables(qkv, table, heads, geo):
+    """What the CUDA kernel computes, in numpy: gather rows by `tok`, mask by `lab`, bias by `rel`."""
+    B, T, H, W, C3 = qkv.shape
+    C, hd = C3 // 3, C3 // 3 // heads
+    nc, vol = geo["num_cuboids"], geo["volume"]
+    tok, lab, rel = geo["tok"].reshape(nc, vol), geo["lab"].reshape(nc, vol), geo["rel"]
+    rows = np.concatenate([qkv.reshape(B, T * H * W, C3), np.zeros((B, 1, C3), qkv.dtype)], axis=1)
+    out = np.zeros((B, T * H * W + 1, C), np.float64)
+    bias = table[rel[:, None] - rel[None, :] + geo["rel_off"]]  # (vol, vol, heads)
+    for c in range(nc):
+        y = rows[:, tok[c]].astype(np.float64).reshape(B, vol, 3, heads, hd)   # tok == -1 picks the zero row
+        q, k, v = (y[:, :, i].transpose(0, 2, 1, 3) for i in range(3))
+        s = (q * hd ** -0.5) @ k.transpose(0, 1, 3, 2) + bias.transpose(2, 0, 1)[None]
+        m = (lab[c][:, None] == lab[c][None, :]) & (lab[c][:, None] >= 0) & (lab[c][None, :] >= 0)
+        s = np.where(m, s, -np.inf)
+        mx = np.where(np.isfinite(s.max(-1, keepdims=True)), s.max(-1, keepdims=True), 0.0)
+        p = np.exp(s - mx)
+        den = p.sum(-1, keepdims=True)
+        p = np.where(den > 0, p / np.where(den > 0, den, 1.0), 0.0)
+        o = (p @ v).transpose(0, 2, 1, 3).reshape(B, vol, C)
+        out[:, tok[c]] = o   # padded tokens land in the scratch row
+    return out[:, :-1].reshape(B, T, H, W, C)
+
+
+GEOM_CASES = [(c[1], c[3], c[4], c[5], c[6], c[7]) for c in PC.LAYER_CASES] + [
+    ((13, 16, 16), 4, (13, 1, 1), "lll", (0, 0, 0), "zeros"),
+    ((13, 16, 16), 4, (1, 16, 16), "lll", (0, 0, 0), "ignore"),
+    ((13, 8, 8), 4, (2, 8, 8), "lll", (1, 4, 4), "ignore"),
+    ((13, 8, 8), 4, (1, 4, 1), "ddd", (0, 0, 0), "zeros"),
+]
+
+
+@pytest.mark.parametrize("case", GEOM_CASES, ids=[f"{c[0]}-{c[2]}-{c[3]}-{c[4]}-{c[5]}" for c in GEOM_CASES])
+def test_geometry_tables_vs_oracle(case):
+    dims, heads, size, strat, shift, pad = case
+    hd = 8
+    C = heads * hd
+    rng = np.random.Generator(np.random.PCG64(11))
+    qkv = rng.standard_normal((2, *dims, 3 * C), dtype=np.float32)
+    n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
+    table = (0.3 * rng.standard_normal((n_rel, heads), dtype=np.float32))
+    want = O.cuboid_attention_core(torch.from_numpy(qkv), torch.from_numpy(table), heads, size, tuple(strat), shift, pad)
+    geo = P.layer_geometry(dims, size, tuple(strat), shift, pad)
+    got = attention_from_tables(qkv, table, heads, geo)
+    assert maxrel(got, want) < 1e-5
+    # every real token belongs to exactly one cuboid slot
+    t = geo["tok"][geo["tok"] >= 0]
+    assert np.array_equal(np.sort(t), np.arange(dims[0] * dims[1] * dims[2]))
