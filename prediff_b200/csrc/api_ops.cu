@@ -124,6 +124,54 @@ int pd_op_axial_attention(const void* qkv, const float* bias_table, void* out, i
                            S(stream));
 }
 
+int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                     int padding_type, int32_t meta[12], int32_t* tok, int32_t* lab, int32_t* rel, int64_t capacity) {
+    CuboidLayerSpec sp;
+    for (int a = 0; a < 3; ++a) {
+        sp.size[a] = size[a];
+        sp.strategy[a] = strategy[a];
+        sp.shift[a] = shift[a];
+    }
+    CuboidTables g;
+    PD_TRY(build_cuboid_tables(T, H, W, sp, padding_type, &g));
+    for (int a = 0; a < 3; ++a) {
+        meta[a] = g.size[a];
+        meta[3 + a] = g.shift[a];
+        meta[6 + a] = g.pad[a];
+    }
+    meta[9] = g.num_cuboids;
+    meta[10] = g.volume;
+    meta[11] = g.rel_off;
+    if (tok || lab || rel) {
+        PD_CHECK((int64_t)g.tok.size() <= capacity, PD_ERR_ARG, "pd_cuboid_tables: capacity %lld < %zu", (long long)capacity,
+                 g.tok.size());
+        if (tok) memcpy(tok, g.tok.data(), g.tok.size() * sizeof(int));
+        if (lab) memcpy(lab, g.lab.data(), g.lab.size() * sizeof(int));
+        if (rel) memcpy(rel, g.rel.data(), g.rel.size() * sizeof(int));
+    }
+    return g.axial_axis >= 0 ? 1 + g.axial_axis : 0;
+}
+
+int pd_op_cuboid_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
+                           const int32_t size[3], const int32_t strategy[3], const int32_t shift[3], int padding_type,
+                           void* stream) {
+    PD_TRY(gemm_init());
+    CuboidLayerSpec sp;
+    for (int a = 0; a < 3; ++a) {
+        sp.size[a] = size[a];
+        sp.strategy[a] = strategy[a];
+        sp.shift[a] = shift[a];
+    }
+    CuboidTables g;
+    PD_TRY(build_cuboid_tables(T, H, W, sp, padding_type, &g));
+    CuboidTablesDev d;
+    PD_TRY(d.upload(g));
+    PD_TRY(cuboid_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T * H * W, C, heads, d.dev,
+                            S(stream)));
+    PD_CUDA(cudaStreamSynchronize(S(stream)));   // the tables are freed on return
+    return PD_OK;
+}
+
 int pd_op_sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef8,
                          int64_t n, void* stream) {
     PD_TRY(gemm_init());

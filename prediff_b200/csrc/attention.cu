@@ -147,6 +147,186 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
     }
 }
 
+// ---- general cuboid attention ---------------------------------------------------------------------------------
+// Any cuboid size / strategy ('l' local, 'd' dilated) / shifted window / end padding of CuboidSelfAttentionLayer
+// (cuboid_transformer.py:812-966). The reference pads, rolls and reorders the activations into
+// (num_cuboids, volume, C) and builds a (num_cuboids, volume, volume) mask; here none of those tensors exist: a
+// per-layer table gives, for every (cuboid, slot), the token row it holds (-1 = padding) and its shifted-window region
+// label (-1 = masked out), and the kernel gathers q|k|v rows straight from the QKV GEMM output.
+//   score(i, j) = q_i k_j / sqrt(hd) + table[rel[i] - rel[j] + rel_off]   if lab[i] == lab[j] >= 0, else masked
+// Flash-style: one block per (64-query tile, cuboid, sample x head), 4 warps x 16 query rows, keys streamed through
+// shared memory in chunks of 64 with an online softmax; QK^T and PV on warp-level mma.sync m16n8k16 (bf16, fp32
+// accumulate). Padding slots contribute zero q/k/v rows (the reference pads after its LayerNorm and qkv has no bias).
+constexpr int kQTile = 64;
+
+template <int HD>
+__global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __restrict__ qkv,
+                                                               const float* __restrict__ bias_table,
+                                                               bf16* __restrict__ out, const int* __restrict__ tok,
+                                                               const int* __restrict__ lab, const int* __restrict__ rel,
+                                                               int N, int C, int heads, int vol, int rel_off) {
+    grid_dep_launch();
+    grid_dep_wait();
+    constexpr int LD = HD + 8;        // row pitch: +16 B keeps ldmatrix bank-conflict free
+    constexpr int VPR = HD / 8;       // 16-byte vectors per row
+    extern __shared__ __align__(16) uint8_t smem_cub[];
+    bf16* sQ = reinterpret_cast<bf16*>(smem_cub);
+    bf16* sK = sQ + kQTile * LD;
+    bf16* sV = sK + kQTile * LD;
+    int* s_qtok = reinterpret_cast<int*>(sV + kQTile * LD);
+    int* s_qlab = s_qtok + kQTile;
+    int* s_qrel = s_qlab + kQTile;
+    int* s_ktok = s_qrel + kQTile;
+    int* s_klab = s_ktok + kQTile;
+    int* s_krel = s_klab + kQTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int c = blockIdx.y, b = blockIdx.z / heads, h = blockIdx.z - b * heads;
+    const int q0 = blockIdx.x * kQTile;
+    const int C3 = 3 * C;
+    const int* ctok = tok + (size_t)c * vol;
+    const int* clab = lab + (size_t)c * vol;
+    const bf16* base = qkv + (size_t)b * N * C3 + h * HD;
+
+    if (tid < kQTile) {
+        const int i = q0 + tid;
+        const bool in = i < vol;
+        s_qtok[tid] = in ? ctok[i] : -1;
+        s_qlab[tid] = in ? clab[i] : -1;
+        s_qrel[tid] = in ? rel[i] : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < kQTile * VPR; i += 128) {
+        const int r = i / VPR, v = i - r * VPR;
+        bf16* dst = sQ + r * LD + v * 8;
+        const int t = s_qtok[r];
+        if (t >= 0) cp_async16(dst, base + (size_t)t * C3 + v * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const float scale = rsqrtf((float)HD);
+    const int r_lo = warp * 16 + g;
+    const int qlab[2] = {s_qlab[r_lo], s_qlab[r_lo + 8]};
+    const int qrel[2] = {s_qrel[r_lo] + rel_off, s_qrel[r_lo + 8] + rel_off};
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[HD / 8][4];
+#pragma unroll
+    for (int jn = 0; jn < HD / 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
+
+    for (int k0 = 0; k0 < vol; k0 += kQTile) {
+        __syncthreads();  // every warp is done with the previous chunk
+        if (tid < kQTile) {
+            const int j = k0 + tid;
+            const bool in = j < vol;
+            s_ktok[tid] = in ? ctok[j] : -1;
+            s_klab[tid] = in ? clab[j] : -1;   // slots past the cuboid's end are always masked
+            s_krel[tid] = in ? rel[j] : 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < kQTile * VPR; i += 128) {
+            const int r = i / VPR, v = i - r * VPR;
+            const int t = s_ktok[r];
+            bf16* dk = sK + r * LD + v * 8;
+            bf16* dv = sV + r * LD + v * 8;
+            if (t >= 0) {
+                const bf16* src = base + (size_t)t * C3 + v * 8;
+                cp_async16(dk, src + C);
+                cp_async16(dv, src + 2 * C);
+            } else {
+                *reinterpret_cast<uint4*>(dk) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(dv) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- S = Q K^T : 16 query rows x 64 keys per warp (8 key tiles of 8) ----
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+            uint32_t a[4];
+            ldmatrix_x4(a, sQ + (size_t)(warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + kk * 16 + 8 * (lane >> 4));
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+                uint32_t bb[4];
+                ldmatrix_x4(bb, sK + (size_t)(kb * 16 + (lane & 7) + 8 * (lane >> 4)) * LD + kk * 16 + 8 * ((lane >> 3) & 1));
+                mma_bf16_16816(s[2 * kb], a, bb[0], bb[1]);
+                mma_bf16_16816(s[2 * kb + 1], a, bb[2], bb[3]);
+            }
+        }
+        // ---- bias, mask, online softmax (thread: rows g / g+8, keys nt*8 + 2tq + {0,1}) ----
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int jl = nt * 8 + 2 * tq + e;
+                    const bool ok = qlab[rh] >= 0 && s_klab[jl] == qlab[rh];
+                    float v = -INFINITY;
+                    if (ok) v = s[nt][2 * rh + e] * scale + __ldg(bias_table + (size_t)(qrel[rh] - s_krel[jl]) * heads + h);
+                    s[nt][2 * rh + e] = v;
+                    mx = fmaxf(mx, v);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run[rh], mx);
+            const float alpha = (m_new == -INFINITY) ? 1.f : __expf(m_run[rh] - m_new);
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float v = s[nt][2 * rh + e];
+                    const float p = (v == -INFINITY) ? 0.f : __expf(v - m_new);
+                    s[nt][2 * rh + e] = p;
+                    sum += p;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            l_run[rh] = l_run[rh] * alpha + sum;
+            m_run[rh] = m_new;
+#pragma unroll
+            for (int jn = 0; jn < HD / 8; ++jn) {
+                o[jn][2 * rh] *= alpha;
+                o[jn][2 * rh + 1] *= alpha;
+            }
+        }
+        // ---- O += P V : the score fragments are already the A fragments of the next mma ----
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]);
+            pa[1] = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
+            pa[2] = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+#pragma unroll
+            for (int jn = 0; jn < HD / 8; jn += 2) {
+                uint32_t bb[4];
+                ldmatrix_x4_trans(bb, sV + (size_t)(kb * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + 8 * (jn + (lane >> 4)));
+                mma_bf16_16816(o[jn], pa, bb[0], bb[1]);
+                mma_bf16_16816(o[jn + 1], pa, bb[2], bb[3]);
+            }
+        }
+    }
+    // ---- normalise and scatter the rows of real tokens (padding slots are dropped = the reference's unpadding) ----
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+        const int t = s_qtok[r_lo + 8 * rh];
+        if (t < 0) continue;
+        const float inv = l_run[rh] > 0.f ? 1.f / l_run[rh] : 0.f;
+        bf16* dst = out + ((size_t)b * N + t) * C + h * HD + 2 * tq;
+#pragma unroll
+        for (int jn = 0; jn < HD / 8; ++jn)
+            *reinterpret_cast<uint32_t*>(dst + 8 * jn) = pack_bf16x2(o[jn][2 * rh] * inv, o[jn][2 * rh + 1] * inv);
+    }
+}
+
 // p = softmax(scale * s) per row; one warp per row, L <= 1024, L % 32 == 0.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int rows,
                                                            int L, float scale) {
@@ -235,6 +415,125 @@ int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, 
 #undef PD_LAUNCH_AX
     PD_LAUNCH_CHECK();
     return PD_OK;
+}
+
+// Host-side geometry of one CuboidSelfAttentionLayer (same tables as prediff_b200/patterns.py::layer_geometry; both are
+// tested against the unmodified reference's cuboid_reorder / compute_cuboid_self_attention_mask).
+int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int padding_type, CuboidTables* g) {
+    PD_CHECK(padding_type == 0 || padding_type == 1, PD_ERR_ARG,
+             "cuboid attention: padding_type %d (0 = zeros, 1 = ignore; 'nearest' is not built)", padding_type);
+    const int dims[3] = {T, H, W};
+    int n[3], padded[3];
+    for (int a = 0; a < 3; ++a) {
+        PD_CHECK(spec.size[a] >= 1 && spec.shift[a] >= 0 && (spec.strategy[a] == 0 || spec.strategy[a] == 1) && dims[a] >= 1,
+                 PD_ERR_ARG, "cuboid attention: bad layer spec on axis %d", a);
+        // update_cuboid_size_shift_size (cuboid_transformer.py:563-592)
+        g->size[a] = spec.size[a];
+        g->shift[a] = spec.strategy[a] == 1 ? 0 : spec.shift[a];
+        if (dims[a] <= spec.size[a]) {
+            g->size[a] = dims[a];
+            g->shift[a] = 0;
+        }
+        PD_CHECK(g->shift[a] < g->size[a], PD_ERR_ARG, "cuboid attention: shift %d >= cuboid size %d", g->shift[a], g->size[a]);
+        g->pad[a] = (g->size[a] - dims[a] % g->size[a]) % g->size[a];
+        padded[a] = dims[a] + g->pad[a];
+        n[a] = padded[a] / g->size[a];
+    }
+    const int nc = n[0] * n[1] * n[2], vol = g->size[0] * g->size[1] * g->size[2];
+    g->num_cuboids = nc;
+    g->volume = vol;
+    g->tok.assign((size_t)nc * vol, -1);
+    g->lab.assign((size_t)nc * vol, -1);
+    const bool any_shift = g->shift[0] > 0 || g->shift[1] > 0 || g->shift[2] > 0;
+    for (int c = 0; c < nc; ++c) {
+        const int cub[3] = {c / (n[1] * n[2]), (c / n[2]) % n[1], c % n[2]};
+        for (int i = 0; i < vol; ++i) {
+            const int inn[3] = {i / (g->size[1] * g->size[2]), (i / g->size[2]) % g->size[1], i % g->size[2]};
+            bool valid = true;
+            int label = 0, src[3];
+            for (int a = 0; a < 3; ++a) {
+                // cuboid_reorder (:388-429): 'l' splits the axis as (block, in-block), 'd' as (in-block, block)
+                const int p = spec.strategy[a] == 0 ? cub[a] * g->size[a] + inn[a] : inn[a] * n[a] + cub[a];
+                // shifted-window region of the rolled frame (:513-522): three slices per axis, one if the shift is 0
+                const int la = g->shift[a] == 0 ? 2 : (p < padded[a] - g->size[a] ? 0 : (p < padded[a] - g->shift[a] ? 1 : 2));
+                label = label * 3 + la;
+                src[a] = any_shift ? (p + g->shift[a]) % padded[a] : p;   // torch.roll(x, -shift)
+                valid = valid && src[a] < dims[a];
+            }
+            const size_t k = (size_t)c * vol + i;
+            g->tok[k] = valid ? (src[0] * H + src[1]) * W + src[2] : -1;
+            g->lab[k] = (!valid && padding_type == 1) ? -1 : label;
+        }
+    }
+    // relative_position_index[:vol, :vol] is built from the CONSTRUCTOR's cuboid size (:714-734, 855-857)
+    const int b1 = spec.size[1], b2 = spec.size[2];
+    const int s1 = (2 * b1 - 1) * (2 * b2 - 1), s2 = 2 * b2 - 1;
+    g->rel.resize(vol);
+    for (int i = 0; i < vol; ++i) g->rel[i] = (i / (b1 * b2)) * s1 + ((i / b2) % b1) * s2 + i % b2;
+    g->rel_off = (spec.size[0] - 1) * s1 + (b1 - 1) * s2 + (b2 - 1);
+    // the axial fast path: one non-unit axis spanning the whole dimension, no shift / padding / dilation effects
+    g->axial_axis = -1;
+    int non_unit = 0, ax = 0;
+    for (int a = 0; a < 3; ++a)
+        if (g->size[a] > 1) { ++non_unit; ax = a; }
+    bool same = true;
+    for (int a = 0; a < 3; ++a) same = same && g->size[a] == spec.size[a];
+    if (non_unit == 1 && same && g->size[ax] == dims[ax] && dims[ax] <= kMaxLine && !any_shift) g->axial_axis = ax;
+    return PD_OK;
+}
+
+int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
+                     const CuboidDev& g, cudaStream_t st) {
+    PD_CHECK(C % heads == 0, PD_ERR_SHAPE, "cuboid_attention: C=%d heads=%d", C, heads);
+    const int hd = C / heads;
+    PD_CHECK(g.num_cuboids >= 1 && g.num_cuboids <= 65535 && B * heads <= 65535, PD_ERR_SHAPE,
+             "cuboid_attention: %d cuboids, %d sample-heads exceed the grid limits", g.num_cuboids, B * heads);
+    dim3 grid(ceil_div(g.volume, kQTile), g.num_cuboids, B * heads);
+#define PD_LAUNCH_CUB(HDV)                                                                                          \
+    do {                                                                                                            \
+        const size_t smem = (size_t)3 * kQTile * (HDV + 8) * sizeof(bf16) + 6 * kQTile * sizeof(int);              \
+        static bool attr_set = false;                                                                               \
+        if (!attr_set) {                                                                                            \
+            PD_CUDA(cudaFuncSetAttribute(cuboid_attention_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                               \
+            attr_set = true;                                                                                        \
+        }                                                                                                           \
+        PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, N, C,    \
+                  heads, g.volume, g.rel_off);                                                                      \
+    } while (0)
+    switch (hd) {
+        case 16: PD_LAUNCH_CUB(16); break;
+        case 32: PD_LAUNCH_CUB(32); break;
+        case 64: PD_LAUNCH_CUB(64); break;
+        case 128: PD_LAUNCH_CUB(128); break;
+        default: set_error("cuboid_attention: unsupported head dim %d", hd); return PD_ERR_SHAPE;
+    }
+#undef PD_LAUNCH_CUB
+    PD_LAUNCH_CHECK();
+    return PD_OK;
+}
+
+int CuboidTablesDev::upload(const CuboidTables& t) {
+    const size_t nt = t.tok.size(), nr = t.rel.size();
+    if (cudaMalloc(&mem, (2 * nt + nr) * sizeof(int)) != cudaSuccess) {
+        mem = nullptr;
+        set_error("cuboid tables: cudaMalloc of %zu ints failed", 2 * nt + nr);
+        return PD_ERR_CUDA;
+    }
+    int* p = static_cast<int*>(mem);
+    PD_CUDA(cudaMemcpy(p, t.tok.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+    PD_CUDA(cudaMemcpy(p + nt, t.lab.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+    PD_CUDA(cudaMemcpy(p + 2 * nt, t.rel.data(), nr * sizeof(int), cudaMemcpyHostToDevice));
+    dev.tok = p;
+    dev.lab = p + nt;
+    dev.rel = p + 2 * nt;
+    dev.num_cuboids = t.num_cuboids;
+    dev.volume = t.volume;
+    dev.rel_off = t.rel_off;
+    return PD_OK;
+}
+CuboidTablesDev::~CuboidTablesDev() {
+    if (mem) cudaFree(mem);
 }
 
 int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st) {

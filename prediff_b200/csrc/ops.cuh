@@ -2,6 +2,7 @@
 // stream, bf16 is what feeds the tensor-core GEMM. Every launcher returns a pd error code.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace pd {
 
@@ -28,6 +29,38 @@ int patch_merge_ln(const float* x, const float* gamma, const float* beta, bf16* 
 // Reference: cuboid_transformer.py:849-861,949 with cuboids (T,1,1)/(1,H,1)/(1,1,W) (patterns.py:34-36).
 int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int T, int H, int W, int C, int heads,
                     int axis, cudaStream_t st);
+// General cuboid self-attention core (any cuboid size, 'l' / 'd' strategy, shifted windows, end padding with
+// padding_type 'zeros' (0) or 'ignore' (1)): cuboid_transformer.py:812-966 without global vectors.
+struct CuboidLayerSpec {   // constructor arguments of one CuboidSelfAttentionLayer
+    int size[3];           // cuboid_size (bT, bH, bW)
+    int strategy[3];       // 0 = 'l' (local), 1 = 'd' (dilated)
+    int shift[3];          // shift_size
+};
+struct CuboidTables {      // host tables of one layer on a (T, H, W) grid
+    int size[3], shift[3], pad[3];                 // effective size / shift (:563-592), end padding per axis
+    int num_cuboids = 0, volume = 0, rel_off = 0;
+    int axial_axis = -1;                           // >= 0: the layer is exactly axial_attention() along that axis
+    std::vector<int> tok;  // [num_cuboids * volume] token row inside a sample's [T*H*W] block, -1 = padding slot
+    std::vector<int> lab;  // [num_cuboids * volume] shifted-window region label, -1 = masked out ('ignore' padding)
+    std::vector<int> rel;  // [volume] relative_position_index[i][j] == rel[i] - rel[j] + rel_off
+};
+int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int padding_type, CuboidTables* out);
+struct CuboidDev {         // device copies
+    const int *tok = nullptr, *lab = nullptr, *rel = nullptr;
+    int num_cuboids = 0, volume = 0, rel_off = 0;
+};
+struct CuboidTablesDev {   // owner of the device copies
+    void* mem = nullptr;
+    CuboidDev dev;
+    CuboidTablesDev() = default;
+    CuboidTablesDev(const CuboidTablesDev&) = delete;
+    CuboidTablesDev& operator=(const CuboidTablesDev&) = delete;
+    ~CuboidTablesDev();
+    int upload(const CuboidTables& t);
+};
+// qkv bf16 [B][N][3C] (N = T*H*W tokens per sample, q|k|v head-major), bias_table fp32 [n_rel][heads] -> out bf16 [B][N][C]
+int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
+                     const CuboidDev& g, cudaStream_t st);
 // Row softmax for the VAE AttentionBlock: s fp32 [rows][L] -> p bf16 [rows][L], p = softmax(scale * s).
 int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st);
 // Batched transpose bf16: in [S][R][ld_in] (first C columns used) -> out [S][C][R].

@@ -105,3 +105,26 @@ def test_geometry_tables_vs_oracle(case):
     # every real token belongs to exactly one cuboid slot
     t = geo["tok"][geo["tok"] >= 0]
     assert np.array_equal(np.sort(t), np.arange(dims[0] * dims[1] * dims[2]))
+
+
+@pytest.mark.parametrize("case", GEOM_CASES, ids=[f"{c[0]}-{c[2]}-{c[3]}-{c[4]}-{c[5]}" for c in GEOM_CASES])
+def test_c_abi_tables_equal_python_tables(case):
+    """pd_cuboid_tables (host-only C++ builder the UNet plan uses) == prediff_b200.patterns.layer_geometry."""
+    import ctypes
+    from prediff_b200 import _lib as L
+    dims, heads, size, strat, shift, pad = case
+    geo = P.layer_geometry(dims, size, tuple(strat), shift, pad)
+    i3 = ctypes.c_int32 * 3
+    meta = (ctypes.c_int32 * 12)()
+    n = geo["num_cuboids"] * geo["volume"]
+    tok, lab, rel = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(geo["volume"], np.int32)
+    rc = L.lib().pd_cuboid_tables(*dims, i3(*size), i3(*[0 if s == "l" else 1 for s in strat]), i3(*shift),
+                                  0 if pad == "zeros" else 1, meta, tok.ctypes.data_as(ctypes.c_void_p),
+                                  lab.ctypes.data_as(ctypes.c_void_p), rel.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n))
+    assert rc >= 0
+    assert tuple(meta[0:3]) == geo["size"] and tuple(meta[3:6]) == geo["shift"] and tuple(meta[6:9]) == geo["pad"]
+    assert (meta[9], meta[10], meta[11]) == (geo["num_cuboids"], geo["volume"], geo["rel_off"])
+    assert np.array_equal(tok, geo["tok"]) and np.array_equal(lab, geo["lab"]) and np.array_equal(rel, geo["rel"])
+    is_axial = sum(s > 1 for s in geo["size"]) == 1 and geo["size"] == tuple(size) and max(geo["size"]) <= 16 \
+        and all(geo["size"][a] in (1, dims[a]) for a in range(3)) and not any(geo["shift"])
+    assert (rc > 0) == is_axial
