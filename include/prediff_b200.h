@@ -48,6 +48,20 @@ typedef struct pd_unet_config {
 } pd_unet_config;
 
 int pd_unet_create(const pd_unet_config* cfg, pd_unet** out);
+/* block_attn_patterns other than 'axial' (cuboid_transformer_unet.py:201-214 -> StackCuboidSelfAttentionBlock
+ * cuboid_transformer.py:1026-1110): per level, the (cuboid_size, strategy, shift_size) of every attention layer of the
+ * level's stack block, as the pattern functions of cuboid_transformer_patterns.py return them for the level's
+ * (T, H, W). strategy: 0 = 'l', 1 = 'd'. padding_type: 0 = 'zeros', 1 = 'ignore'. pd_unet_create == pd_unet_create_ex
+ * with the axial pattern at both levels and 'zeros' padding (the shipped SEVIR-LR config). */
+#define PD_MAX_ATTN_LAYERS 8
+typedef struct pd_unet_pattern {
+    int32_t n_layers[2];
+    int32_t cuboid_size[2][PD_MAX_ATTN_LAYERS][3];
+    int32_t strategy[2][PD_MAX_ATTN_LAYERS][3];
+    int32_t shift_size[2][PD_MAX_ATTN_LAYERS][3];
+    int32_t padding_type;
+} pd_unet_pattern;
+int pd_unet_create_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern, pd_unet** out);
 void pd_unet_destroy(pd_unet* m);
 /* Number of state_dict entries the model expects; name/shape of entry i (reference key names, e.g.
  * "down_self_blocks.0.1.attn_l.2.qkv.weight"). shape has up to 5 dims; returns ndim. */

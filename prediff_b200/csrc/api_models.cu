@@ -7,7 +7,7 @@ using namespace pd;
 
 struct pd_unet {
     UNet impl;
-    explicit pd_unet(const pd_unet_config& c) : impl(c) {}
+    pd_unet(const pd_unet_config& c, const pd_unet_pattern* p) : impl(c, p) {}
 };
 struct pd_sampler {
     Sampler impl;
@@ -20,9 +20,14 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 extern "C" {
 
-int pd_unet_create(const pd_unet_config* cfg, pd_unet** out) {
+int pd_unet_create(const pd_unet_config* cfg, pd_unet** out) { return pd_unet_create_ex(cfg, nullptr, out); }
+int pd_unet_create_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern, pd_unet** out) {
     PD_CHECK(cfg && out, PD_ERR_ARG, "pd_unet_create: null argument");
-    pd_unet* m = new (std::nothrow) pd_unet(*cfg);
+    if (pattern)
+        for (int l = 0; l < 2; ++l)
+            PD_CHECK(pattern->n_layers[l] >= 1 && pattern->n_layers[l] <= PD_MAX_ATTN_LAYERS, PD_ERR_ARG,
+                     "pd_unet_create_ex: level %d has %d attention layers (1..%d)", l, pattern->n_layers[l], PD_MAX_ATTN_LAYERS);
+    pd_unet* m = new (std::nothrow) pd_unet(*cfg, pattern);
     PD_CHECK(m, PD_ERR_CUDA, "pd_unet_create: out of host memory");
     const int rc = m->impl.validate();
     if (rc != PD_OK) {

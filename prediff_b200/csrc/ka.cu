@@ -174,6 +174,8 @@ int KANet::finalize_resblock(const std::string& p, int cin, int cout, ResW* r, R
 }
 
 int KANet::finalize_stack(const std::string& p, int dim, StackW* s, StackBwdW* sb) {
+    s->a.assign(3, AttnW{});   // the KA network is built for the axial pattern only (three layers per stack block)
+    s->f.assign(3, FfnW{});
     for (int i = 0; i < 3; ++i) {
         const std::string a = p + strf(".attn_l.%d", i), f = p + strf(".ffn_l.%d", i);
         PD_GETW(s->a[i].ln_w, a + ".norm.weight");

@@ -7,6 +7,7 @@
 // "b t h w c <-> b c t h w" rearranges and 96 cuboid reorders per step do not exist). The fp32 residual stream x
 // lives in one buffer per level; every tensor a GEMM consumes is written as bf16 by its producer.
 #include "unet.cuh"
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 
@@ -57,11 +58,28 @@ struct UNet::BatchPlan {
 
 UNet::~UNet() = default;
 
-UNet::UNet(const pd_unet_config& c) : cfg(c) {
+UNet::UNet(const pd_unet_config& c, const pd_unet_pattern* pattern) : cfg(c) {
     C0 = cfg.base_units;
     C1 = 2 * cfg.base_units;
     T = cfg.t_in + cfg.t_out;
     TE = 4 * cfg.base_units;
+    for (int lvl = 0; lvl < 2; ++lvl) {
+        if (!pattern) {  // self_axial (cuboid_transformer_patterns.py:19-37)
+            const int sz[3][3] = {{T, 1, 1}, {1, cfg.h >> lvl, 1}, {1, 1, cfg.w >> lvl}};
+            for (int i = 0; i < 3; ++i) layers[lvl].push_back(CuboidLayerSpec{{sz[i][0], sz[i][1], sz[i][2]}, {0, 0, 0}, {0, 0, 0}});
+            continue;
+        }
+        for (int i = 0; i < pattern->n_layers[lvl]; ++i) {
+            CuboidLayerSpec sp;
+            for (int a = 0; a < 3; ++a) {
+                sp.size[a] = pattern->cuboid_size[lvl][i][a];
+                sp.strategy[a] = pattern->strategy[lvl][i][a];
+                sp.shift[a] = pattern->shift_size[lvl][i][a];
+            }
+            layers[lvl].push_back(sp);
+        }
+    }
+    padding_type = pattern ? pattern->padding_type : 0;
     declare_weights();
 }
 
@@ -85,8 +103,8 @@ void UNet::declare_resblock(const std::string& p, int cin, int cout, bool emb) {
 }
 
 void UNet::declare_stack(const std::string& p, int dim, int lvl) {
-    const int L[3] = {T, cfg.h >> lvl, cfg.w >> lvl};
-    for (int i = 0; i < 3; ++i) {
+    const int n = (int)layers[lvl].size();
+    for (int i = 0; i < n; ++i) {
         const std::string f = p + strf(".ffn_l.%d", i);
         ws.declare(f + ".ffn_1.weight", {4 * dim, dim});
         ws.declare(f + ".ffn_1.bias", {4 * dim});
@@ -95,9 +113,11 @@ void UNet::declare_stack(const std::string& p, int dim, int lvl) {
         ws.declare(f + ".layer_norm.weight", {dim});
         ws.declare(f + ".layer_norm.bias", {dim});
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < n; ++i) {
         const std::string a = p + strf(".attn_l.%d", i);
-        ws.declare(a + ".relative_position_bias_table", {2 * L[i] - 1, cfg.num_heads});
+        const int* sz = layers[lvl][i].size;   // the table is sized by the constructor's cuboid (cuboid_transformer.py:714-716)
+        ws.declare(a + ".relative_position_bias_table",
+                   {(2 * std::max(sz[0], 1) - 1) * (2 * std::max(sz[1], 1) - 1) * (2 * std::max(sz[2], 1) - 1), cfg.num_heads});
         ws.declare(a + ".qkv.weight", {3 * dim, dim});
         ws.declare(a + ".proj.weight", {dim, dim});
         ws.declare(a + ".proj.bias", {dim});
@@ -148,6 +168,12 @@ int UNet::validate() const {
     PD_CHECK(hd0 == 16 || hd0 == 32 || hd0 == 64, PD_ERR_SHAPE, "unet: head dim %d unsupported", hd0);
     PD_CHECK(cfg.depth[0] >= 1 && cfg.depth[1] >= 1, PD_ERR_SHAPE, "unet: depth");
     PD_CHECK(cfg.max_batch >= 1, PD_ERR_SHAPE, "unet: max_batch");
+    PD_CHECK(padding_type == 0 || padding_type == 1, PD_ERR_ARG, "unet: padding_type %d (0 'zeros' | 1 'ignore')", padding_type);
+    for (int lvl = 0; lvl < 2; ++lvl)
+        for (const CuboidLayerSpec& sp : layers[lvl])
+            for (int a = 0; a < 3; ++a)
+                PD_CHECK(sp.size[a] >= 1 && sp.shift[a] >= 0 && (sp.strategy[a] == 0 || sp.strategy[a] == 1), PD_ERR_ARG,
+                         "unet: bad cuboid layer spec at level %d", lvl);
     return PD_OK;
 }
 
@@ -187,8 +213,11 @@ int UNet::finalize_resblock(const std::string& p, int cin, int cinpad, int cout,
     return PD_OK;
 }
 
-int UNet::finalize_stack(const std::string& p, int dim, StackW* s) {
-    for (int i = 0; i < 3; ++i) {
+int UNet::finalize_stack(const std::string& p, int dim, int lvl, StackW* s) {
+    const int n = (int)layers[lvl].size();
+    s->a.assign(n, AttnW{});
+    s->f.assign(n, FfnW{});
+    for (int i = 0; i < n; ++i) {
         const std::string a = p + strf(".attn_l.%d", i), f = p + strf(".ffn_l.%d", i);
         PD_GETW(s->a[i].ln_w, a + ".norm.weight");
         PD_GETW(s->a[i].ln_b, a + ".norm.bias");
@@ -260,8 +289,23 @@ int UNet::finalize() {
         down_stack[lvl].resize(cfg.depth[lvl]);
         up_stack[lvl].resize(cfg.depth[lvl]);
         for (int d = 0; d < cfg.depth[lvl]; ++d) {
-            PD_TRY(finalize_stack(strf("down_self_blocks.%d.%d", lvl, d), dim, &down_stack[lvl][d]));
-            PD_TRY(finalize_stack(strf("up_self_blocks.%d.%d", lvl, d), dim, &up_stack[lvl][d]));
+            PD_TRY(finalize_stack(strf("down_self_blocks.%d.%d", lvl, d), dim, lvl, &down_stack[lvl][d]));
+            PD_TRY(finalize_stack(strf("up_self_blocks.%d.%d", lvl, d), dim, lvl, &up_stack[lvl][d]));
+        }
+    }
+    // geometry tables of the attention layers (batch-independent; axial layers keep the strided fast path)
+    for (int lvl = 0; lvl < 2; ++lvl) {
+        cub_dev[lvl].clear();
+        cub_axis[lvl].clear();
+        for (const CuboidLayerSpec& sp : layers[lvl]) {
+            CuboidTables g;
+            PD_TRY(build_cuboid_tables(T, cfg.h >> lvl, cfg.w >> lvl, sp, padding_type, &g));
+            cub_axis[lvl].push_back(g.axial_axis);
+            cub_dev[lvl].emplace_back(nullptr);
+            if (g.axial_axis < 0) {
+                cub_dev[lvl].back().reset(new CuboidTablesDev());
+                PD_TRY(cub_dev[lvl].back()->upload(g));
+            }
         }
     }
     PD_GETW(pm_ln_w, "downsample_layers.0.norm.weight");
@@ -409,7 +453,9 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
     bf16 *ln = b.ln[lvl], *qkv = b.qkv[lvl], *att = b.att[lvl], *mid = b.mid[lvl];
     const int heads = cfg.num_heads, Tn = T;
     pl.scope = strf("L%d.stack", lvl);
-    for (int i = 0; i < 3; ++i) {
+    const int n_layers = (int)s.a.size(), last = n_layers - 1;
+    const int N_tok = T * H * W;
+    for (int i = 0; i < n_layers; ++i) {
         const AttnW& aw = s.a[i];
         const FfnW& fw = s.f[i];
         const bool fuse = ln_fusable(lvl);
@@ -424,18 +470,25 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), aw.qkv_w, 3 * C, e));
             pl.add_gemm(op, "qkv");
         }
-        pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, i, st); },
-               i == 0 ? "attn_T" : (i == 1 ? "attn_H" : "attn_W"));
+        if (cub_axis[lvl][i] >= 0) {
+            const int axis = cub_axis[lvl][i];
+            pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st); },
+                   axis == 0 ? "attn_T" : (axis == 1 ? "attn_H" : "attn_W"));
+        } else {   // any other cuboid (shifted / padded / dilated / multi-axis): gather tables + flash-style kernel
+            const CuboidDev cd = cub_dev[lvl][i]->dev;
+            pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
+                   "attn_cuboid");
+        }
         if (C == 256 && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {
             // width 256: projection + residual + pre-norm + FFN (+ the next layer's LayerNorm) in ONE kernel per row
             // tile - x1 = x + proj(att) lives in TMEM and seeds the FFN-2 accumulator (ffn_fused.cu, PROJ variant)
             FfnProjArgs pa;
             pa.att = att; pa.wp = aw.proj_w; pa.bp = aw.proj_b; pa.ln1_gamma = fw.ln_w; pa.ln1_beta = fw.ln_b;
             FfnFusedOp op;
-            const bool next_ln = i < 2;
+            const bool next_ln = i < last;
             PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                   next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f, nullptr, &pa));
-            if (gn_next && i == 2) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
+            if (gn_next && i == last) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
             pl.gemm_flops += 2.0 * (double)P * C * C + 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.n_gemm += 1;
             pl.add_ffn_fused(op, "proj_ffn_fused");
@@ -460,10 +513,10 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
         if (C == 256 && getenv("PD_NO_FFN_FUSION") == nullptr) {
             // width 256: both GEMMs + GELU (+ the next layer's LayerNorm) in one kernel; `mid` never leaves the SM
             FfnFusedOp op;
-            const bool next_ln = i < 2;   // pre-norm of the next attention layer of this stack
+            const bool next_ln = i < last;   // pre-norm of the next attention layer of this stack
             PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                   next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f));
-            if (gn_next && i == 2) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
+            if (gn_next && i == last) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
             pl.gemm_flops += 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.n_gemm += 1;
             pl.add_ffn_fused(op, "ffn_fused");
@@ -483,12 +536,12 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             e.bias = fw.b2;
             e.residual = x;
             e.out_f32 = x;
-            if (fuse && i < 2) {  // pre-norm of the next attention layer of this stack
+            if (fuse && i < last) {  // pre-norm of the next attention layer of this stack
                 e.ln_gamma = s.a[i + 1].ln_w;
                 e.ln_beta = s.a[i + 1].ln_b;
                 e.ln_out = ln;
             }
-            if (gn_next && i == 2) {   // statistics for the first GroupNorm of the resblock that follows
+            if (gn_next && i == last) {   // statistics for the first GroupNorm of the resblock that follows
                 e.gn_sums = gn_next;
                 e.gn_groups = 32;
                 e.gn_rows = T * H * W;

@@ -17,9 +17,9 @@ struct FfnW {   // PositionwiseFFN
     const float *ln_w, *ln_b, *b1, *b2;
     bf16 *w1, *w2;
 };
-struct StackW {  // StackCuboidSelfAttentionBlock: 3 x (attn, ffn)
-    AttnW a[3];
-    FfnW f[3];
+struct StackW {  // StackCuboidSelfAttentionBlock: n x (attn, ffn), n = number of cuboid layers of the level's pattern
+    std::vector<AttnW> a;
+    std::vector<FfnW> f;
 };
 
 class UNet {
@@ -27,7 +27,7 @@ public:
     struct Bufs;
     struct BatchPlan;
 
-    explicit UNet(const pd_unet_config& c);
+    UNet(const pd_unet_config& c, const pd_unet_pattern* pattern);
     ~UNet();
     int validate() const;
     int finalize();
@@ -42,6 +42,10 @@ public:
 
     pd_unet_config cfg;
     int C0, C1, T, TE;
+    // attention layers of each level's stack block (block_attn_patterns) and their geometry tables (built in finalize)
+    std::vector<CuboidLayerSpec> layers[2];
+    int padding_type = 0;   // 0 = 'zeros', 1 = 'ignore'
+    bool all_axial = true;
     WeightStore ws;
     bool finalized = false;
 
@@ -52,7 +56,7 @@ private:
     int pack_conv_w(const std::string& name, int co, int ci, int taps, int cipad, bf16** out);
     int pack_linear_w(const std::string& name, int n, int k, bf16** out);
     int finalize_resblock(const std::string& p, int cin, int cinpad, int cout, ResW* r);
-    int finalize_stack(const std::string& p, int dim, StackW* s);
+    int finalize_stack(const std::string& p, int dim, int lvl, StackW* s);
     int build_plan(int B, BatchPlan* bp);
     // `next`: the stack block that follows - when the level width is 256 its first LayerNorm is fused into the
     // resblock's conv2 epilogue (and add_stack skips that LayerNorm launch)
@@ -77,6 +81,8 @@ private:
 
     BatchPlan* building_ = nullptr;   // plan under construction (make_conv attaches stream-K workspaces to it)
     std::vector<std::unique_ptr<DevMem>> packed;
+    std::vector<std::unique_ptr<CuboidTablesDev>> cub_dev[2];   // per level, per layer (null for axial fast-path layers)
+    std::vector<int> cub_axis[2];                               // axial fast-path axis or -1
     std::map<std::pair<int, int>, std::unique_ptr<BatchPlan>> plans;  // (batch, replica)
     ResW first{}, down_res[2]{}, up_res[2]{};
     std::vector<StackW> down_stack[2], up_stack[2];

@@ -2,9 +2,10 @@
 (src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py:23-493) over the CUDA implementation.
 
 Same constructor argument names, `forward(x, t, cond, verbose=False)` contract, `state_dict()` key names and
-shapes. Only the configuration family the shipped SEVIR-LR config uses is built (axial self-attention pattern,
-two levels, patch-merge / upsample, GELU FFN, relative position bias, no global vectors); anything else raises
-NotImplementedError at construction - there is no fallback path.
+shapes. Built: two levels, patch-merge / upsample, GELU FFN, relative position bias, no global vectors, and every
+registered `block_attn_patterns` name (axial - the shipped SEVIR-LR config, on its own fast path - full, divided_st,
+video_swin_PxM, spatial_lg_M, axial_space_dilate_K; prediff_b200/patterns.py) with 'zeros' or 'ignore' padding;
+anything else raises NotImplementedError at construction - there is no fallback path.
 """
 import ctypes
 from typing import Sequence
@@ -14,6 +15,7 @@ from torch import nn
 
 from . import _lib as L
 from .module_tree import build_param_tree
+from . import patterns as _patterns
 from .weights import UNetConfig, relative_position_index, unet_param_spec
 
 
@@ -23,9 +25,18 @@ class _CUnetConfig(ctypes.Structure):
                 ("num_heads", ctypes.c_int32), ("max_batch", ctypes.c_int32)]
 
 
+_MAX_LAYERS = 8  # PD_MAX_ATTN_LAYERS
+
+
+class _CUnetPattern(ctypes.Structure):
+    _fields_ = [("n_layers", ctypes.c_int32 * 2), ("cuboid_size", ctypes.c_int32 * 3 * _MAX_LAYERS * 2),
+                ("strategy", ctypes.c_int32 * 3 * _MAX_LAYERS * 2), ("shift_size", ctypes.c_int32 * 3 * _MAX_LAYERS * 2),
+                ("padding_type", ctypes.c_int32)]
+
+
 def _unsupported(what):
-    raise NotImplementedError(f"prediff_b200.CuboidTransformerUNet: {what} is not built (only the shipped SEVIR-LR "
-                              "configuration family: axial pattern, 2 levels, no global vectors)")
+    raise NotImplementedError(f"prediff_b200.CuboidTransformerUNet: {what} is not built (only the SEVIR-LR "
+                              "configuration family: registered self-attention patterns, 2 levels, no global vectors)")
 
 
 class CuboidTransformerUNet(nn.Module):
@@ -45,8 +56,15 @@ class CuboidTransformerUNet(nn.Module):
         patterns = block_attn_patterns if isinstance(block_attn_patterns, (list, tuple)) else [block_attn_patterns] * len(depth)
         if len(depth) != 2:
             _unsupported(f"depth={list(depth)} (needs exactly two levels)")
-        if any(p != "axial" for p in patterns):
-            _unsupported(f"block_attn_patterns={patterns}")
+        if block_attn_patterns is None:
+            _unsupported("block_attn_patterns=None (explicit block_cuboid_size lists)")
+        for name in patterns:
+            try:
+                _patterns.get(name)
+            except KeyError:
+                _unsupported(f"block_attn_patterns={patterns}")
+        if padding_type not in ("zeros", "ignore"):
+            _unsupported(f"padding_type='{padding_type}'")
         if block_units is not None and list(block_units) != [base_units, 2 * base_units]:
             _unsupported(f"block_units={block_units}")
         checks = [(scale_alpha == 1.0, "scale_alpha != 1"), (downsample in (2, (1, 2, 2), [1, 2, 2]), "downsample != 2"),
@@ -61,7 +79,10 @@ class CuboidTransformerUNet(nn.Module):
             if not ok:
                 _unsupported(what)
         self.cfg = UNetConfig(t_in=T_in, t_out=T_out, h=H, w=W, c=C, base_units=base_units, depth=tuple(depth),
-                              num_heads=num_heads)
+                              num_heads=num_heads, patterns=tuple(patterns), padding_type=padding_type)
+        for lvl in range(2):
+            if len(self.cfg.layers(lvl)) > _MAX_LAYERS:
+                _unsupported(f"{len(self.cfg.layers(lvl))} attention layers per block")
         self.input_shape, self.target_shape = list(input_shape), list(target_shape)
         self.in_len, self.out_len = T_in, T_out
         self.max_batch = max_batch
@@ -83,7 +104,20 @@ class CuboidTransformerUNet(nn.Module):
             cc = _CUnetConfig(c.t_in, c.t_out, c.h, c.w, c.c, c.base_units, (ctypes.c_int32 * 2)(*c.depth), c.num_heads,
                               self.max_batch)
             h = ctypes.c_void_p()
-            L.check(L.lib().pd_unet_create(ctypes.byref(cc), ctypes.byref(h)))
+            if tuple(c.patterns) == ("axial", "axial") and c.padding_type == "zeros":
+                L.check(L.lib().pd_unet_create(ctypes.byref(cc), ctypes.byref(h)))
+            else:
+                pt = _CUnetPattern()
+                pt.padding_type = 0 if c.padding_type == "zeros" else 1
+                for lvl in range(2):
+                    layers = c.layers(lvl)
+                    pt.n_layers[lvl] = len(layers)
+                    for i, (size, strategy, shift) in enumerate(layers):
+                        for a in range(3):
+                            pt.cuboid_size[lvl][i][a] = size[a]
+                            pt.strategy[lvl][i][a] = 0 if strategy[a] == "l" else 1
+                            pt.shift_size[lvl][i][a] = shift[a]
+                L.check(L.lib().pd_unet_create_ex(ctypes.byref(cc), ctypes.byref(pt), ctypes.byref(h)))
             self._handle = h
             self._dirty = True
         return self._handle

@@ -95,7 +95,11 @@ def test_schedule_through_c_abi_is_bit_exact_vs_reference():
 def test_unsupported_configs_fail_loudly():
     from prediff_b200.unet import CuboidTransformerUNet
     with pytest.raises(NotImplementedError):
-        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], block_attn_patterns="video_swin_2x4")
+        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], block_attn_patterns="video_swin_3x5")  # not registered
+    with pytest.raises(NotImplementedError):
+        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], padding_type="nearest")
+    with pytest.raises(NotImplementedError):
+        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], num_global_vectors=8)
     with pytest.raises(NotImplementedError):
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], depth=[2, 2, 2])
     with pytest.raises(L.PDError):  # rejected by the C++ validate(): 24x24 latents do not tile
