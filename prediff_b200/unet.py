@@ -43,7 +43,9 @@ class CuboidTransformerUNet(nn.Module):
 
     def __init__(self, input_shape, target_shape, base_units=128, block_units=None, scale_alpha=1.0,
                  depth=(4, 4), downsample=2, downsample_type="patch_merge", upsample_type="upsample",
-                 upsample_kernel_size=3, block_attn_patterns="axial", num_heads=4, attn_drop=0.0, proj_drop=0.0,
+                 upsample_kernel_size=3, block_attn_patterns="axial", block_cuboid_size=((4, 4, 4), (4, 4, 4)),
+                 block_cuboid_strategy=(("l", "l", "l"), ("d", "d", "d")),
+                 block_cuboid_shift_size=((0, 0, 0), (0, 0, 0)), num_heads=4, attn_drop=0.0, proj_drop=0.0,
                  ffn_drop=0.0, ffn_activation="gelu", gated_ffn=False, norm_layer="layer_norm", use_inter_ffn=True,
                  hierarchical_pos_embed=False, pos_embed_type="t+h+w", padding_type="zeros", checkpoint_level=0,
                  use_relative_pos=True, self_attn_use_final_proj=True, num_global_vectors=0,
@@ -56,13 +58,23 @@ class CuboidTransformerUNet(nn.Module):
         patterns = block_attn_patterns if isinstance(block_attn_patterns, (list, tuple)) else [block_attn_patterns] * len(depth)
         if len(depth) != 2:
             _unsupported(f"depth={list(depth)} (needs exactly two levels)")
+        explicit = None
         if block_attn_patterns is None:
-            _unsupported("block_attn_patterns=None (explicit block_cuboid_size lists)")
-        for name in patterns:
-            try:
-                _patterns.get(name)
-            except KeyError:
-                _unsupported(f"block_attn_patterns={patterns}")
+            # explicit lists, shared by all blocks or one list per block (cuboid_transformer_unet.py:215-232)
+            def per_block(v):
+                return [list(v)] * 2 if not isinstance(v[0][0], (list, tuple)) else [list(b) for b in v]
+            sizes, strats, shifts = per_block(block_cuboid_size), per_block(block_cuboid_strategy), per_block(block_cuboid_shift_size)
+            if not (len(sizes) == len(strats) == len(shifts) == 2):
+                _unsupported("block_cuboid_* lists must describe exactly two blocks")
+            explicit = tuple(tuple((tuple(int(x) for x in a), tuple(b), tuple(int(x) for x in c))
+                                   for a, b, c in zip(sizes[i], strats[i], shifts[i])) for i in range(2))
+            patterns = ["explicit", "explicit"]
+        else:
+            for name in patterns:
+                try:
+                    _patterns.get(name)
+                except KeyError:
+                    _unsupported(f"block_attn_patterns={patterns}")
         if padding_type not in ("zeros", "ignore"):
             _unsupported(f"padding_type='{padding_type}'")
         if block_units is not None and list(block_units) != [base_units, 2 * base_units]:
@@ -79,7 +91,8 @@ class CuboidTransformerUNet(nn.Module):
             if not ok:
                 _unsupported(what)
         self.cfg = UNetConfig(t_in=T_in, t_out=T_out, h=H, w=W, c=C, base_units=base_units, depth=tuple(depth),
-                              num_heads=num_heads, patterns=tuple(patterns), padding_type=padding_type)
+                              num_heads=num_heads, patterns=tuple(patterns), padding_type=padding_type,
+                              explicit_layers=explicit)
         for lvl in range(2):
             if len(self.cfg.layers(lvl)) > _MAX_LAYERS:
                 _unsupported(f"{len(self.cfg.layers(lvl))} attention layers per block")

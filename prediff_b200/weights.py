@@ -25,6 +25,9 @@ class UNetConfig:
     # block_attn_patterns per level (names of cuboid_transformer_patterns.py) and padding_type ('zeros' | 'ignore')
     patterns: Tuple[str, str] = ("axial", "axial")
     padding_type: str = "zeros"
+    # block_attn_patterns=None in the reference: explicit per-level lists of (cuboid_size, strategy, shift_size)
+    # (block_cuboid_size / block_cuboid_strategy / block_cuboid_shift_size, cuboid_transformer_unet.py:215-232)
+    explicit_layers: Tuple = None
 
     @property
     def T(self):
@@ -42,6 +45,8 @@ class UNetConfig:
         """(cuboid_size, strategy, shift_size) of every attention layer of a level's StackCuboidSelfAttentionBlock:
         the level's pattern evaluated on its mem_shape (cuboid_transformer_unet.py:201-214, 387-404)."""
         from . import patterns as P
+        if self.explicit_layers is not None:
+            return [(tuple(a), tuple(b), tuple(c)) for a, b, c in self.explicit_layers[level]]
         return P.resolve(self.patterns[level], (self.T, self.h >> level, self.w >> level, self.units[level]))
 
     def cuboids(self, level):

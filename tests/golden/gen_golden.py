@@ -63,6 +63,12 @@ def install_stubs():
 def ref_unet(cfg):
     from prediff.models.cuboid_transformer import CuboidTransformerUNet
     pats = list(getattr(cfg, "patterns", ("axial", "axial")))
+    explicit = {}
+    if getattr(cfg, "explicit_layers", None) is not None:   # block_attn_patterns=None + explicit per-block lists
+        pats = None
+        explicit = dict(block_cuboid_size=[[a for a, _, _ in blk] for blk in cfg.explicit_layers],
+                        block_cuboid_strategy=[[b for _, b, _ in blk] for blk in cfg.explicit_layers],
+                        block_cuboid_shift_size=[[c for _, _, c in blk] for blk in cfg.explicit_layers])
     # arguments as in scripts/prediff/sevirlr/train_sevirlr_prediff.py:91-137 with cfg.yaml:157-206
     m = CuboidTransformerUNet(
         input_shape=[cfg.t_in, cfg.h, cfg.w, cfg.c], target_shape=[cfg.t_out, cfg.h, cfg.w, cfg.c],
@@ -72,7 +78,7 @@ def ref_unet(cfg):
         use_global_self_attn=True, separate_global_qkv=True, global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
         norm_layer="layer_norm", padding_type=getattr(cfg, "padding_type", "zeros"), checkpoint_level=0,
         pos_embed_type="t+h+w", use_relative_pos=True, self_attn_use_final_proj=True, time_embed_channels_mult=4,
-        time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0, unet_res_connect=True)
+        time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0, unet_res_connect=True, **explicit)
     sd = Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED)
     res = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
     assert not res.unexpected_keys, res.unexpected_keys
@@ -321,8 +327,12 @@ def gen_patterns():
         assert not res.unexpected_keys and res.missing_keys == ["relative_position_index"], res
         x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
         out[f"layer_{tag}"] = m(x)
-    for tag, pats, pad in PC.UNET_CASES:
-        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
+    for tag, pats, pad in PC.UNET_CASES + [("explicit", None, "ignore")]:
+        if pats is None:
+            cfg = dataclasses.replace(Wt.TINY_UNET, patterns=("explicit", "explicit"), padding_type=pad,
+                                      explicit_layers=PC.EXPLICIT_LAYERS)
+        else:
+            cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
         m = ref_unet(cfg)
         x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c)
         cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c)

@@ -20,6 +20,11 @@ UNET_CASES = [
     ("full_swin", ("full", "video_swin_2x8"), "ignore"),
 ]
 
+# block_attn_patterns=None: the reference constructor's default block_cuboid_size / strategy / shift_size
+# (cuboid_transformer_unet.py:35-40), the same lists for both blocks
+_DEFAULT_BLOCK = (((4, 4, 4), ("l", "l", "l"), (0, 0, 0)), ((4, 4, 4), ("d", "d", "d"), (0, 0, 0)))
+EXPLICIT_LAYERS = (_DEFAULT_BLOCK, _DEFAULT_BLOCK)
+
 
 def layer_spec(C, heads, size):
     n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)

@@ -46,10 +46,14 @@ def test_oracle_layer_vs_reference(case):
     assert maxrel(out, G[f"layer_{tag}"]) < 2e-5
 
 
-@pytest.mark.parametrize("case", PC.UNET_CASES, ids=[c[0] for c in PC.UNET_CASES])
+@pytest.mark.parametrize("case", PC.UNET_CASES + [("explicit", None, "ignore")], ids=[c[0] for c in PC.UNET_CASES] + ["explicit"])
 def test_oracle_unet_patterns_vs_reference(case):
     tag, pats, pad = case
-    cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
+    if pats is None:   # block_attn_patterns=None with the reference's default explicit lists
+        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=("explicit", "explicit"), padding_type=pad,
+                                  explicit_layers=PC.EXPLICIT_LAYERS)
+    else:
+        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
     sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED))
     x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c)
     cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c)

@@ -137,3 +137,24 @@ def test_unet_shipped_width_patterns_vs_oracle(pats, pad):
     # a batch and its shards give the same rows (no cross-sample op)
     out1 = m(x[1:].cuda(), t[1:].cuda(), cond[1:].cuda())
     assert torch.equal(out1[0], out[1])
+
+
+def test_unet_explicit_cuboid_lists_vs_oracle():
+    """block_attn_patterns=None with the reference's default block_cuboid_size / strategy / shift_size
+    (cuboid_transformer_unet.py:35-40: (4,4,4) 'l' then (4,4,4) 'd'; T = 13 is padded to 16 under the dilated split)."""
+    base = Wt.TINY_UNET
+    m = CuboidTransformerUNet(input_shape=[base.t_in, base.h, base.w, base.c], target_shape=[base.t_out, base.h, base.w, base.c],
+                              base_units=base.base_units, depth=list(base.depth), num_heads=base.num_heads,
+                              block_attn_patterns=None, padding_type="ignore", max_batch=2)
+    cfg = m.cfg
+    assert cfg.layers(0) == [((4, 4, 4), ("l", "l", "l"), (0, 0, 0)), ((4, 4, 4), ("d", "d", "d"), (0, 0, 0))]
+    sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED))
+    m.load_state_dict(sd, strict=False)
+    x = inp(41, 2, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(42, 2, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    t = torch.tensor([700, 50])
+    out = m.eval()(x.cuda(), t.cuda(), cond.cuda())
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, x, t, cond)
+    rel_rms, mx = errs(out, ref)
+    assert rel_rms < REL_RMS_TOL and mx < MAX_TOL, (rel_rms, mx)
