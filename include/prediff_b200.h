@@ -175,6 +175,17 @@ int pd_sample_loop_aligned(pd_sampler* s, pd_unet* unet, pd_ka* ka, float* z, co
                            const float* avg_x_gt, float guide_scale, int batch, int mode, int n_steps, float eta,
                            int k_begin, int k_end, void* stream);
 /* Number of independent sub-batches (parallel streams) the loop cuts a batch into (env PD_SUB_BATCHES, default 2). */
+/* Forward-only diffusion loss = LatentDiffusion.p_losses (latent_diffusion.py:517-551) for the eps-parameterization
+ * with a fixed logvar (learn_logvar = False): x_noisy = q_sample(x_start, t, noise) (:489-492), eps = UNet(x_noisy, t,
+ * cond), loss_simple_b = mean |noise - eps|^p per sample (p = 2 'l2', loss_l1 = 1 -> p = 1), then
+ * out4 = {mean loss_simple, loss_vlb = mean(lvlb_weights[t] loss_simple), loss = l_simple_weight * mean(loss_simple /
+ * exp(logvar) + logvar) + original_elbo_weight * loss_vlb, loss_gamma}. This is what validation_step evaluates through
+ * self(batch) (train_sevirlr_prediff.py:817-818); no gradients. All pointers on the device: x_start / noise
+ * [B][t_out][h][w][c], cond [B][t_in][h][w][c], t int64 [B], per_sample [B], out4 [4]. "lvlb_weights" is also
+ * available from pd_sampler_get_buffer. */
+int pd_diffusion_losses(pd_sampler* s, pd_unet* unet, const float* x_start, const float* cond, const int64_t* t,
+                        const float* noise, int batch, int loss_l1, float logvar, float l_simple_weight,
+                        float original_elbo_weight, float* per_sample, float* out4, void* stream);
 int pd_sampler_sub_batches(const pd_sampler* s, int batch);
 /* One reference p_sample step at integer timestep t (all batch rows share t): z <- p_sample(z, cond, t). */
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
@@ -245,6 +256,10 @@ int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t s
 int pd_op_cuboid_attention(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W, int C,
                            int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                            int padding_type, void* stream);
+/* q_sample (latent_diffusion.py:489-492): out = sqrt_alphas_cumprod[t_b] x_start + sqrt_one_minus_alphas_cumprod[t_b]
+ * noise, bit-exact vs the reference's fp32 tensor expression; tables fp32 [T] and t int64 [B] on the device. */
+int pd_op_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_alphas_cumprod,
+                   const float* sqrt_one_minus_alphas_cumprod, float* out, int B, int64_t n_per_sample, void* stream);
 int pd_op_sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef8,
                          int64_t n, void* stream);
 int pd_op_timestep_embedding(const int64_t* t, float* out, int B, int dim, void* stream);

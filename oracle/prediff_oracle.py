@@ -415,6 +415,40 @@ def sample_loop_ddim(sd, cfg, sched, z, cond, n_steps, eta=0.0, noise=None, guid
     return z
 
 
+# ----------------------------------------------------------------------------------------------- forward loss
+
+
+def lvlb_weights(sched, timesteps=1000, linear_start=1e-4, linear_end=2e-2):
+    """eps-parameterization branch of register_schedule (latent_diffusion.py:270-277): fp32 tensor arithmetic on the
+    registered buffers, alphas = fp32(1 - betas) from the float64 schedule, entry 0 replaced by entry 1."""
+    betas64 = np.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=np.float64) ** 2
+    alphas = torch.tensor(1.0 - betas64, dtype=torch.float32)
+    w = sched["betas"] ** 2 / (2 * sched["posterior_variance"] * alphas * (1 - sched["alphas_cumprod"]))
+    w[0] = w[1]
+    return w
+
+
+def q_sample(sched, x_start, t, noise):
+    """latent_diffusion.py:489-492."""
+    shape = [t.shape[0]] + [1] * (x_start.dim() - 1)
+    return sched["sqrt_alphas_cumprod"][t].reshape(shape) * x_start \
+        + sched["sqrt_one_minus_alphas_cumprod"][t].reshape(shape) * noise
+
+
+def p_losses(sd, cfg, sched, x_start, cond, t, noise, loss_type="l2", original_elbo_weight=0.0, l_simple_weight=1.0,
+             logvar_init=0.0):
+    """LatentDiffusion.p_losses (latent_diffusion.py:517-551), eps-parameterization, learn_logvar = False.
+    Returns dict(loss_simple, loss_vlb, loss, per_sample)."""
+    eps = unet_forward(sd, cfg, q_sample(sched, x_start, t, noise), t, cond)
+    d = (noise - eps).abs() if loss_type == "l1" else (noise - eps) ** 2
+    per_sample = d.mean(dim=tuple(range(1, d.dim())))
+    logvar_t = torch.full((t.shape[0],), float(logvar_init))
+    loss = l_simple_weight * (per_sample / torch.exp(logvar_t) + logvar_t).mean()
+    loss_vlb = (lvlb_weights(sched)[t] * per_sample).mean()
+    return dict(loss_simple=per_sample.mean(), loss_vlb=loss_vlb, loss=loss + original_elbo_weight * loss_vlb,
+                per_sample=per_sample)
+
+
 # ----------------------------------------------------------------------------------------------- knowledge alignment
 
 

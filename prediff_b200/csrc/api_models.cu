@@ -121,6 +121,14 @@ int pd_sample_loop_aligned(pd_sampler* s, pd_unet* unet, pd_ka* ka, float* z, co
     al.guide_scale = guide_scale;
     return s->impl.loop(&unet->impl, z, cond, noise, batch, mode, n_steps, eta, k_begin, k_end, S(stream), al);
 }
+int pd_diffusion_losses(pd_sampler* s, pd_unet* unet, const float* x_start, const float* cond, const int64_t* t,
+                        const float* noise, int batch, int loss_l1, float logvar, float l_simple_weight,
+                        float original_elbo_weight, float* per_sample, float* out4, void* stream) {
+    PD_CHECK(s && unet, PD_ERR_ARG, "pd_diffusion_losses: null handle");
+    PD_CHECK(unet->impl.finalized, PD_ERR_WEIGHT, "pd_diffusion_losses: pd_unet_finalize has not been called");
+    return s->impl.losses(&unet->impl, x_start, cond, t, noise, batch, loss_l1, logvar, l_simple_weight,
+                          original_elbo_weight, per_sample, out4, S(stream));
+}
 int pd_sampler_sub_batches(const pd_sampler* s, int batch) { return s ? s->impl.n_sub_for(batch) : 0; }
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream) {

@@ -172,6 +172,12 @@ int pd_op_cuboid_attention(const void* qkv, const float* bias_table, void* out, 
     return PD_OK;
 }
 
+int pd_op_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_alphas_cumprod,
+                   const float* sqrt_one_minus_alphas_cumprod, float* out, int B, int64_t n_per_sample, void* stream) {
+    PD_TRY(gemm_init());
+    return q_sample(x_start, noise, t, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, out, B, n_per_sample, S(stream));
+}
+
 int pd_op_sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef8,
                          int64_t n, void* stream) {
     PD_TRY(gemm_init());

@@ -182,6 +182,15 @@ int sevir_windows(const uint8_t* events, int event_base, int n_events, int H, in
 // noise_step_stride: elements between consecutive steps of the noise stack (0 -> n; larger when z is a sub-batch).
 int sampler_update(float* z, const float* eps, const float* noise, const float* guide, const float* coef,
                    const int* step, int64_t n, int64_t noise_step_stride, cudaStream_t st);
+// Forward diffusion (q_sample, latent_diffusion.py:489-492): out = sqrt_ac[t_b] x0 + sqrt_1mac[t_b] noise; tables and t
+// on the device, n elements per sample.
+int q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac,
+             float* out, int B, int64_t n, cudaStream_t st);
+// p_losses reductions (latent_diffusion.py:534-549): per_sample[b] = mean |target - pred|^p over the sample, then
+// out4 = {mean loss_simple, loss_vlb, loss, loss_gamma}.
+int diffusion_loss_reduce(const float* pred, const float* target, const int64_t* t, const float* lvlb, float logvar,
+                          float w_simple, float w_elbo, int l1, float* per_sample, float* out4, int B, int64_t n,
+                          cudaStream_t st);
 // *step += 1 (one thread): closes one iteration of the device-resident sampling loop.
 int advance_step(int* step, cudaStream_t st);
 

@@ -36,6 +36,48 @@ Sampler::Sampler(int num_timesteps, double linear_start, double linear_end) : T(
     put("posterior_log_variance_clipped", [&](int i) { return std::log(std::max(pv(i), 1e-20)); });
     put("posterior_mean_coef1", [&](int i) { return betas[i] * std::sqrt(ac_prev[i]) / (1.0 - ac[i]); });
     put("posterior_mean_coef2", [&](int i) { return (1.0 - ac_prev[i]) * std::sqrt(1.0 - betas[i]) / (1.0 - ac[i]); });
+    // lvlb_weights (eps-parameterization, latent_diffusion.py:270-277): fp32 tensor arithmetic on the registered buffers,
+    // betas^2 / (2 * posterior_variance * alphas * (1 - alphas_cumprod)), entry 0 replaced by entry 1
+    {
+        std::vector<float> w(T);
+        const std::vector<float>&b = buf_["betas"], &pvar = buf_["posterior_variance"], &acf = buf_["alphas_cumprod"];
+        for (int i = 0; i < T; ++i) {
+            const float alpha = (float)(1.0 - betas[i]);
+            float den = 2.f * pvar[i];
+            den = den * alpha;
+            den = den * (1.f - acf[i]);
+            w[i] = (b[i] * b[i]) / den;
+        }
+        if (T > 1) w[0] = w[1];
+        buf_["lvlb_weights"] = std::move(w);
+    }
+}
+
+int Sampler::losses(UNet* unet, const float* x_start, const float* cond, const int64_t* t, const float* noise, int B,
+                    int loss_l1, float logvar, float l_simple_weight, float elbo_weight, float* per_sample, float* out4,
+                    cudaStream_t st) {
+    PD_CHECK(unet && x_start && cond && t && noise && per_sample && out4, PD_ERR_ARG, "losses: null argument");
+    const int64_t n = (int64_t)unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    if (!loss_tab_.p) {
+        PD_TRY(loss_tab_.alloc((size_t)3 * T * sizeof(float)));
+        const char* names[3] = {"sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "lvlb_weights"};
+        for (int k = 0; k < 3; ++k)
+            PD_CUDA(cudaMemcpy(loss_tab_.as<float>() + (size_t)k * T, buf_[names[k]].data(), T * sizeof(float),
+                               cudaMemcpyHostToDevice));
+    }
+    const size_t need = (size_t)2 * B * n * sizeof(float);
+    if (loss_ws_.bytes < need) {
+        PD_CUDA(cudaStreamSynchronize(st));   // a previous call on this stream may still use the old workspace
+        PD_TRY(loss_ws_.alloc(need));
+    }
+    float* x_noisy = loss_ws_.as<float>();
+    float* eps = x_noisy + (size_t)B * n;
+    const float* tab = loss_tab_.as<float>();
+    PD_TRY(q_sample(x_start, noise, t, tab, tab + T, x_noisy, B, n, st));
+    PD_TRY(unet->forward(x_noisy, t, nullptr, cond, eps, B, st));
+    // eps-parameterization: target = noise (:527-530)
+    return diffusion_loss_reduce(eps, noise, t, tab + 2 * (size_t)T, logvar, l_simple_weight, elbo_weight, loss_l1,
+                                 per_sample, out4, B, n, st);
 }
 
 Sampler::~Sampler() {

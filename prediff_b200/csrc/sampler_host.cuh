@@ -28,6 +28,13 @@ public:
     int loop(UNet* unet, float* z, const float* cond, const float* noise, int B, int mode, int n_total, float eta,
              int k_begin, int k_end, cudaStream_t st, const Align& al = Align());
     int step_ddpm(UNet* unet, float* z, const float* cond, const float* noise, int B, int t, cudaStream_t st);
+    // Forward-only LatentDiffusion.p_losses (latent_diffusion.py:517-551; eps-parameterization, fixed logvar): q_sample
+    // -> UNet -> per-sample loss -> {loss_simple, loss_vlb, loss, loss_gamma}. All pointers on the device; t int64 [B];
+    // per_sample [B] and out4 [4] are outputs. This is the validation-loss path (validation_step -> self(batch)); no
+    // gradients are produced.
+    int losses(UNet* unet, const float* x_start, const float* cond, const int64_t* t, const float* noise, int B,
+               int loss_l1, float logvar, float l_simple_weight, float elbo_weight, float* per_sample, float* out4,
+               cudaStream_t st);
 
     int T;
     // number of concurrent sub-batches a batch of B is cut into (env PD_SUB_BATCHES, default 2, must divide B)
@@ -46,6 +53,7 @@ private:
 
     std::map<std::string, std::vector<float>> buf_;  // the reference's registered fp32 buffers
     DevMem coef_dev_, t_dev_, step_dev_, eps_dev_;
+    DevMem loss_tab_, loss_ws_;   // {sqrt_ac, sqrt_1mac, lvlb} tables; x_noisy + eps workspace of losses()
     // cached one-iteration graph
     cudaGraphExec_t graph_exec_ = nullptr;
     // sub-batch concurrency: the batch is cut into n_sub independent slices (samples never interact) that run the

@@ -66,7 +66,18 @@ class LatentDiffusion(nn.Module):
         self.scale_factor = scale_factor
         self.alignment_fn = None
         self.shorten_cond_schedule = False
+        # loss hyper-parameters of p_losses (latent_diffusion.py:134-150); only the forward (validation) loss is built
+        if loss_type not in ("l1", "l2"):
+            raise NotImplementedError(f"prediff_b200.LatentDiffusion: unknown loss type '{loss_type}'")
+        if learn_logvar:
+            raise NotImplementedError("prediff_b200.LatentDiffusion: learn_logvar=True is a training feature (not built)")
+        self.loss_type = loss_type
+        self.original_elbo_weight = original_elbo_weight
+        self.l_simple_weight = l_simple_weight
+        self.learn_logvar = False
+        self.logvar_init = float(logvar_init)
         self.register_schedule(timesteps=timesteps, linear_start=linear_start, linear_end=linear_end)
+        self.register_buffer("logvar", torch.full(fill_value=logvar_init, size=(self.num_timesteps,)))
         self.first_stage_model = first_stage_model
         if first_stage_model is not None:
             first_stage_model.eval()
@@ -93,6 +104,9 @@ class LatentDiffusion(nn.Module):
             buf = torch.empty(self.num_timesteps, dtype=torch.float32)
             L.check(L.lib().pd_sampler_get_buffer(self._sampler, name.encode(), L.ptr(buf)))
             self.register_buffer(name, buf)
+        w = torch.empty(self.num_timesteps, dtype=torch.float32)
+        L.check(L.lib().pd_sampler_get_buffer(self._sampler, b"lvlb_weights", L.ptr(w)))
+        self.register_buffer("lvlb_weights", w, persistent=False)   # latent_diffusion.py:277
 
     def __del__(self):
         try:
@@ -158,6 +172,64 @@ class LatentDiffusion(nn.Module):
         noise = torch.randn_like(x_start) if noise is None else noise
         return (self.extract_into_tensor(self.sqrt_alphas_cumprod.to(x_start.device), t, x_start.shape) * x_start +
                 self.extract_into_tensor(self.sqrt_one_minus_alphas_cumprod.to(x_start.device), t, x_start.shape) * noise)
+
+    # ---- forward (validation) loss: latent_diffusion.py:447-478, 494-551 ---------------------------------------
+    @property
+    def loss_mean_dim(self):
+        return tuple(i for i in range(len(self.layout)) if i != self.batch_axis)
+
+    def get_loss(self, pred, target, mean=True):
+        """latent_diffusion.py:494-509 (plain torch on whatever device the tensors live on)."""
+        loss = (target - pred).abs() if self.loss_type == "l1" else (target - pred) ** 2
+        return loss.mean() if mean else loss
+
+    def get_input(self, batch, **kwargs):
+        """Dataset dependent (latent_diffusion.py:419-435): returns (target sequence, {"y": context sequence})."""
+        return batch
+
+    @torch.no_grad()
+    def p_losses(self, x_start, cond, t, noise=None):
+        """latent_diffusion.py:517-551, forward only: (loss, {prefix/loss_simple, prefix/loss_vlb, prefix/loss}).
+        With the CUDA UNet the whole evaluation (q_sample, UNet, reductions) is one call into the library and the four
+        scalars stay on the device; with any other denoiser module the reference's arithmetic runs in torch."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        prefix = "train" if self.training else "val"
+        B = x_start.shape[0]
+        if self._native() and x_start.is_cuda:
+            x_start, cond, noise = (v.contiguous().float() for v in (x_start, cond, noise))
+            t = t.to(device=x_start.device, dtype=torch.int64).contiguous()
+            per_sample = torch.empty(B, device=x_start.device, dtype=torch.float32)
+            out4 = torch.empty(4, device=x_start.device, dtype=torch.float32)
+            with torch.cuda.device(x_start.device):
+                L.check(L.lib().pd_diffusion_losses(
+                    self._sampler, self.torch_nn_module.handle, L.ptr(x_start), L.ptr(cond), L.ptr(t), L.ptr(noise), B,
+                    1 if self.loss_type == "l1" else 0, ctypes.c_float(self.logvar_init), ctypes.c_float(self.l_simple_weight),
+                    ctypes.c_float(self.original_elbo_weight), L.ptr(per_sample), L.ptr(out4), L.stream_ptr()))
+            self.last_loss_per_sample = per_sample
+            return out4[2], {f"{prefix}/loss_simple": out4[0], f"{prefix}/loss_vlb": out4[1], f"{prefix}/loss": out4[2]}
+        x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
+        model_output = self.apply_model(x_noisy, t, cond)
+        loss_simple = self.get_loss(model_output, noise, mean=False).mean(dim=self.loss_mean_dim)
+        logvar_t = self.logvar.to(t.device)[t]
+        loss = self.l_simple_weight * (loss_simple / torch.exp(logvar_t) + logvar_t).mean()
+        loss_vlb = (self.lvlb_weights.to(t.device)[t] * loss_simple).mean()
+        loss = loss + self.original_elbo_weight * loss_vlb
+        return loss, {f"{prefix}/loss_simple": loss_simple.mean(), f"{prefix}/loss_vlb": loss_vlb, f"{prefix}/loss": loss}
+
+    @torch.no_grad()
+    def forward(self, batch, verbose=False, t=None, noise=None):
+        """latent_diffusion.py:447-478: target -> latents (posterior sample), t ~ U{0..T-1}, context -> latents,
+        p_losses. `t` / `noise` may be injected (parity tests); by default they are drawn where the reference draws."""
+        x, c = self.get_input(batch)
+        B = x.shape[self.batch_axis]
+        N, T = x.shape[0], x.shape[1]
+        frames = x.permute(0, 1, 4, 2, 3).reshape(N * T, x.shape[4], x.shape[2], x.shape[3])
+        z = self.encode_first_stage(frames)
+        z = z.reshape(N, T, *z.shape[1:]).permute(0, 1, 3, 4, 2).contiguous()
+        if t is None:
+            t = torch.randint(0, self.num_timesteps, (B,), device=z.device).long()
+        zc = self.cond_stage_forward(c) if self.cond_stage_model is not None else (c if torch.is_tensor(c) else c.get("y"))
+        return self.p_losses(z, zc, t, noise=noise)
 
     def _native_alignment(self, use_alignment, alignment_kwargs):
         """(alignment object, avg_x_gt [B] device tensor factory) when the registered alignment_fn is the

@@ -110,9 +110,10 @@ def ref_vae(cfg):
     return m.eval()
 
 
-def ref_ldm(unet, vae, ucfg, vcfg):
+def ref_ldm(unet, vae, ucfg, vcfg, **kw):
     from prediff.diffusion.latent_diffusion import LatentDiffusion
     return LatentDiffusion(
+        **kw,
         torch_nn_module=unet, layout="NTHWC", data_shape=(ucfg.t_out, vcfg.h, vcfg.w, 1), timesteps=1000,
         beta_schedule="linear", use_ema=False, log_every_t=100, clip_denoised=False, linear_start=1e-4,
         linear_end=2e-2, parameterization="eps", learn_logvar=False,
@@ -308,6 +309,37 @@ def gen_unet(tag, cfg, B, ts):
     save(f"unet_{tag}", t=t, out=out)
 
 
+LOSS_CASES = [("l2", dict(loss_type="l2")),
+              ("l1w", dict(loss_type="l1", original_elbo_weight=0.3, l_simple_weight=0.7, logvar_init=0.5))]
+
+
+@torch.no_grad()
+def gen_losses():
+    """Forward diffusion loss of the unmodified reference LatentDiffusion.p_losses (latent_diffusion.py:517-551) on the
+    tiny UNet with injected t / noise (what validation_step evaluates through self(batch)), plus the lvlb_weights
+    buffer (:270-277)."""
+    ucfg, vcfg = Wt.TINY_UNET, Wt.TINY_VAE
+    unet = ref_unet(ucfg)
+    B = 3
+    z = inp(881, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    zc = inp(882, B, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    noise = inp(883, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    t = torch.tensor([0, 431, 999], dtype=torch.long)
+    out = {"t": t}
+    for tag, kw in LOSS_CASES:
+        ldm = ref_ldm(unet, ref_vae(vcfg), ucfg, vcfg, **kw)   # .eval() -> 'val/' prefix; a fresh VAE per instance
+        # (the reference replaces first_stage_model.train with an unbound function, so a VAE cannot be reused)
+        loss, d = ldm.p_losses(z, zc, t, noise=noise)
+        out[f"{tag}_loss"] = loss
+        for k, v in d.items():
+            out[f"{tag}_{k.replace('/', '_')}"] = v
+        out["lvlb_weights"] = ldm.lvlb_weights
+        xn = ldm.q_sample(z, t, noise)
+        out["x_noisy_probe"] = xn[:, 0, 0, 0, :8]
+        print(f"losses {tag}: " + ", ".join(f"{k}={float(v):.6f}" for k, v in d.items()))
+    save("losses", **out)
+
+
 @torch.no_grad()
 def gen_patterns():
     """Other cuboid patterns: single CuboidSelfAttentionLayer outputs of the unmodified reference
@@ -449,5 +481,7 @@ if __name__ == "__main__":
         gen_loader()
     if "patterns" in todo:
         gen_patterns()
+    if "losses" in todo:
+        gen_losses()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

@@ -115,3 +115,15 @@ def test_no_gpu_means_error_not_fallback():
         m(torch.zeros(1, 6, 16, 16, 64), torch.zeros(1, dtype=torch.long), torch.zeros(1, 7, 16, 16, 64))
     with pytest.raises(L.PDError):
         L.init()
+
+
+def test_lvlb_weights_through_c_abi_bit_exact_vs_reference():
+    """The non-persistent lvlb_weights buffer (latent_diffusion.py:270-277) computed by the C++ sampler == the
+    reference's fp32 tensor arithmetic (tests/golden/losses.npz)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "losses.npz"))
+    h = ctypes.c_void_p()
+    L.check(L.lib().pd_sampler_create(1000, ctypes.c_double(1e-4), ctypes.c_double(2e-2), ctypes.byref(h)))
+    buf = np.empty(1000, dtype=np.float32)
+    L.check(L.lib().pd_sampler_get_buffer(h, b"lvlb_weights", buf.ctypes.data_as(ctypes.c_void_p)))
+    L.lib().pd_sampler_destroy(h)
+    assert np.array_equal(buf, g["lvlb_weights"])

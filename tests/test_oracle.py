@@ -177,3 +177,23 @@ def test_knowledge_alignment_vs_reference(tiny_unet_sd):
     guide = O.ka_mean_shift(sd, cfg, zT, ts, torch.full((2, 1), 0.3), cfg.guide_scale)
     z = O.p_sample_ddpm(sched, eps, zT, 900, noise[0], guide=guide)
     assert maxrel(z, g["z_aligned_step900"]) < 5e-5
+
+
+def test_forward_loss_vs_reference(tiny_unet_sd):
+    """p_losses / q_sample / lvlb_weights of the oracle vs the unmodified reference LatentDiffusion (losses.npz)."""
+    from tests.golden.gen_golden import LOSS_CASES
+    g = gold("losses")
+    cfg = Wt.TINY_UNET
+    sched = O.make_schedule()
+    assert np.array_equal(O.lvlb_weights(sched).numpy(), g["lvlb_weights"])
+    z, zc, noise = inp(881, 3, cfg.t_out, cfg.h, cfg.w, cfg.c), inp(882, 3, cfg.t_in, cfg.h, cfg.w, cfg.c), \
+        inp(883, 3, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    t = torch.as_tensor(g["t"])
+    assert np.array_equal(O.q_sample(sched, z, t, noise)[:, 0, 0, 0, :8].numpy(), g["x_noisy_probe"])
+    for tag, kw in LOSS_CASES:
+        with torch.no_grad():
+            r = O.p_losses(tiny_unet_sd, cfg, sched, z, zc, t, noise, **kw)
+        for k in ("loss_simple", "loss_vlb", "loss"):
+            want = float(g[f"{tag}_val_{k}"])
+            assert abs(float(r[k]) - want) <= 2e-5 * abs(want), (tag, k, float(r[k]), want)
+        assert abs(float(r["loss"]) - float(g[f"{tag}_loss"])) <= 2e-5 * abs(float(g[f"{tag}_loss"]))
