@@ -29,7 +29,8 @@ def test_q_sample_bit_exact():
     t = torch.tensor([0, 1, 500, 981, 999])
     out = torch.empty(B, n, device="cuda")
     sa, s1 = sched["sqrt_alphas_cumprod"].cuda(), sched["sqrt_one_minus_alphas_cumprod"].cuda()
-    L.check(L.lib().pd_op_q_sample(L.ptr(x.cuda()), L.ptr(noise.cuda()), L.ptr(t.cuda()), L.ptr(sa), L.ptr(s1), L.ptr(out),
+    xd, nd, td = x.cuda(), noise.cuda(), t.cuda()   # named: a temporary's memory would be reused by the next .cuda()
+    L.check(L.lib().pd_op_q_sample(L.ptr(xd), L.ptr(nd), L.ptr(td), L.ptr(sa), L.ptr(s1), L.ptr(out),
                                    B, ctypes.c_int64(n), L.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), O.q_sample(sched, x, t, noise))
