@@ -19,11 +19,19 @@ from prediff_b200.unet import CuboidTransformerUNet  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--tiny", action="store_true")
+ap.add_argument("--patterns", default="axial,axial", help="block_attn_patterns of the two levels")
+ap.add_argument("--padding", default="zeros", choices=["zeros", "ignore"])
+ap.add_argument("--depth", default=None, help="e.g. 1,1 (default: the config's)")
 args = ap.parse_args()
-cfg = Wt.TINY_UNET if args.tiny else Wt.UNetConfig()
+import dataclasses  # noqa: E402
+cfg = dataclasses.replace(Wt.TINY_UNET if args.tiny else Wt.UNetConfig(), patterns=tuple(args.patterns.split(",")),
+                          padding_type=args.padding)
+if args.depth:
+    cfg = dataclasses.replace(cfg, depth=tuple(int(v) for v in args.depth.split(",")))
 B = args.batch
 unet = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
-                             depth=list(cfg.depth), num_heads=cfg.num_heads, max_batch=B)
+                             depth=list(cfg.depth), num_heads=cfg.num_heads, block_attn_patterns=list(cfg.patterns),
+                             padding_type=cfg.padding_type, max_batch=B)
 unet.load_state_dict({k: torch.from_numpy(v) for k, v in Wt.seeded_state_dict(Wt.unet_param_spec(cfg), 1001).items()},
                      strict=False)
 rng = np.random.Generator(np.random.PCG64(1))

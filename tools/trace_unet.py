@@ -24,11 +24,15 @@ ap.add_argument("--out", default=None)
 ap.add_argument("--graph", action="store_true",
                 help="capture the stamped forward into a CUDA graph and replay it: launches are then issued by the GPU "
                      "front end, not by the host (an eager trace is host-launch-bound for kernels shorter than ~5 us)")
+ap.add_argument("--patterns", default="axial,axial",
+                help="block_attn_patterns of the two levels (any registered name, e.g. video_swin_2x8,spatial_lg_4)")
+ap.add_argument("--padding", default="zeros", choices=["zeros", "ignore"])
 args = ap.parse_args()
-cfg = Wt.UNetConfig()
+cfg = Wt.UNetConfig(patterns=tuple(args.patterns.split(",")), padding_type=args.padding)
 B = args.batch
 unet = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
-                             depth=list(cfg.depth), num_heads=cfg.num_heads, max_batch=B)
+                             depth=list(cfg.depth), num_heads=cfg.num_heads, block_attn_patterns=list(cfg.patterns),
+                             padding_type=cfg.padding_type, max_batch=B)
 unet.load_state_dict({k: torch.from_numpy(v) for k, v in Wt.seeded_state_dict(Wt.unet_param_spec(cfg), 1001).items()},
                      strict=False)
 rng = np.random.Generator(np.random.PCG64(1))
@@ -71,7 +75,7 @@ for name, us in zip(lab, d):
     a[0] += 1
     a[1] += us - slot
 total = sum(v[1] for v in agg.values())
-lines = [f"UNet forward, batch {B}{' (CUDA-graph replay)' if args.graph else ''}: {n} plan steps, {(s[-1] - s[0]) * 1e-3:.1f} us wall with stamps, "
+lines = [f"UNet forward, batch {B}, patterns {args.patterns} / {args.padding}{' (CUDA-graph replay)' if args.graph else ''}: {n} plan steps, {(s[-1] - s[0]) * 1e-3:.1f} us wall with stamps, "
          f"{total:.1f} us after removing {n} stamp slots of {slot:.2f} us",
          f"{'site':28s} {'n':>4s} {'avg us':>8s} {'total us':>9s} {'share':>6s}"]
 for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
