@@ -2,6 +2,7 @@
 // softmax, 0.25 % of the step's FLOPs), so it is a CUDA-core kernel that reads q/k/v straight out of the QKV
 // GEMM output with strided (axial) addressing - the reference's cuboid_reorder / reverse copies never exist.
 #include "ops.cuh"
+#include <cstdlib>
 
 namespace pd {
 namespace {
@@ -158,27 +159,31 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
 // shared memory in chunks of 64 with an online softmax; QK^T and PV on warp-level mma.sync m16n8k16 (bf16, fp32
 // accumulate). Padding slots contribute zero q/k/v rows (the reference pads after its LayerNorm and qkv has no bias).
 constexpr int kQTile = 64;
+constexpr int kMaxRelSmem = 24576;   // bias-table entries of one head staged in shared memory (96 KB) - covers the
+                                     // 25 x 31 x 31 table of full attention on the shipped 13 x 16 x 16 grid
 
+// K/V chunks are double-buffered (the gather of chunk c+1 is in flight under the math of chunk c) and, when it fits,
+// the head's column of the relative-position table sits in shared memory: at volume 3328 the per-score table gather
+// from L2 (one 32-byte sector per score, 1.2 GB per launch) was what bound the first version of this kernel.
 template <int HD>
 __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __restrict__ qkv,
                                                                const float* __restrict__ bias_table,
                                                                bf16* __restrict__ out, const int* __restrict__ tok,
                                                                const int* __restrict__ lab, const int* __restrict__ rel,
-                                                               int N, int C, int heads, int vol, int rel_off) {
+                                                               int N, int C, int heads, int vol, int rel_off,
+                                                               int n_rel_smem) {
     grid_dep_launch();
     grid_dep_wait();
     constexpr int LD = HD + 8;        // row pitch: +16 B keeps ldmatrix bank-conflict free
     constexpr int VPR = HD / 8;       // 16-byte vectors per row
     extern __shared__ __align__(16) uint8_t smem_cub[];
     bf16* sQ = reinterpret_cast<bf16*>(smem_cub);
-    bf16* sK = sQ + kQTile * LD;
-    bf16* sV = sK + kQTile * LD;
-    int* s_qtok = reinterpret_cast<int*>(sV + kQTile * LD);
+    bf16* sKV = sQ + kQTile * LD;                                  // [2 stages][K | V][64][LD]
+    int* s_qtok = reinterpret_cast<int*>(sKV + 4 * kQTile * LD);
     int* s_qlab = s_qtok + kQTile;
     int* s_qrel = s_qlab + kQTile;
-    int* s_ktok = s_qrel + kQTile;
-    int* s_klab = s_ktok + kQTile;
-    int* s_krel = s_klab + kQTile;
+    int* s_kmeta = s_qrel + kQTile;                                // [2 stages][tok | lab | rel][64]
+    float* s_bias = reinterpret_cast<float*>(s_kmeta + 6 * kQTile);   // [n_rel_smem] (this head's table column)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tq = lane & 3;
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
     const int* ctok = tok + (size_t)c * vol;
     const int* clab = lab + (size_t)c * vol;
     const bf16* base = qkv + (size_t)b * N * C3 + h * HD;
+    const bool bias_in_smem = n_rel_smem > 0;
 
     if (tid < kQTile) {
         const int i = q0 + tid;
@@ -196,38 +202,26 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
         s_qlab[tid] = in ? clab[i] : -1;
         s_qrel[tid] = in ? rel[i] : 0;
     }
-    __syncthreads();
-    for (int i = tid; i < kQTile * VPR; i += 128) {
-        const int r = i / VPR, v = i - r * VPR;
-        bf16* dst = sQ + r * LD + v * 8;
-        const int t = s_qtok[r];
-        if (t >= 0) cp_async16(dst, base + (size_t)t * C3 + v * 8);
-        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < n_rel_smem; i += 128) s_bias[i] = __ldg(bias_table + (size_t)i * heads + h);
 
-    const float scale = rsqrtf((float)HD);
-    const int r_lo = warp * 16 + g;
-    const int qlab[2] = {s_qlab[r_lo], s_qlab[r_lo + 8]};
-    const int qrel[2] = {s_qrel[r_lo] + rel_off, s_qrel[r_lo + 8] + rel_off};
-    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    float o[HD / 8][4];
-#pragma unroll
-    for (int jn = 0; jn < HD / 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
-
-    for (int k0 = 0; k0 < vol; k0 += kQTile) {
-        __syncthreads();  // every warp is done with the previous chunk
+    // chunk loader: slot metadata by the first 64 threads, then (after a block barrier) the row gathers by everyone
+    auto load_meta = [&](int k0, int stage) {
         if (tid < kQTile) {
             const int j = k0 + tid;
             const bool in = j < vol;
-            s_ktok[tid] = in ? ctok[j] : -1;
-            s_klab[tid] = in ? clab[j] : -1;   // slots past the cuboid's end are always masked
-            s_krel[tid] = in ? rel[j] : 0;
+            int* m = s_kmeta + stage * 3 * kQTile;
+            m[tid] = in ? ctok[j] : -1;
+            m[kQTile + tid] = in ? clab[j] : -1;   // slots past the cuboid's end are always masked
+            m[2 * kQTile + tid] = in ? rel[j] : 0;
         }
-        __syncthreads();
+    };
+    auto load_rows = [&](int stage) {
+        const int* m = s_kmeta + stage * 3 * kQTile;
+        bf16* sK = sKV + stage * 2 * kQTile * LD;
+        bf16* sV = sK + kQTile * LD;
         for (int i = tid; i < kQTile * VPR; i += 128) {
             const int r = i / VPR, v = i - r * VPR;
-            const int t = s_ktok[r];
+            const int t = m[r];
             bf16* dk = sK + r * LD + v * 8;
             bf16* dv = sV + r * LD + v * 8;
             if (t >= 0) {
@@ -239,8 +233,45 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                 *reinterpret_cast<uint4*>(dv) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
-        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    load_meta(0, 0);
+    __syncthreads();
+    for (int i = tid; i < kQTile * VPR; i += 128) {   // Q tile: same commit group as chunk 0
+        const int r = i / VPR, v = i - r * VPR;
+        bf16* dst = sQ + r * LD + v * 8;
+        const int t = s_qtok[r];
+        if (t >= 0) cp_async16(dst, base + (size_t)t * C3 + v * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    load_rows(0);
+
+    const float scale = rsqrtf((float)HD);
+    const int r_lo = warp * 16 + g;
+    const int qlab[2] = {s_qlab[r_lo], s_qlab[r_lo + 8]};
+    const int qrel[2] = {s_qrel[r_lo] + rel_off, s_qrel[r_lo + 8] + rel_off};
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[HD / 8][4];
+#pragma unroll
+    for (int jn = 0; jn < HD / 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
+
+    const int n_chunks = (vol + kQTile - 1) / kQTile;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int stage = ch & 1;
+        if (ch + 1 < n_chunks) {   // prefetch the next chunk into the other stage (its last readers passed the
+            load_meta((ch + 1) * kQTile, stage ^ 1);   // barrier that closes iteration ch - 1)
+            __syncthreads();
+            load_rows(stage ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
+        const bf16* sK = sKV + stage * 2 * kQTile * LD;
+        const bf16* sV = sK + kQTile * LD;
+        const int* s_klab = s_kmeta + stage * 3 * kQTile + kQTile;
+        const int* s_krel = s_klab + kQTile;
 
         // ---- S = Q K^T : 16 query rows x 64 keys per warp (8 key tiles of 8) ----
         float s[8][4];
@@ -258,24 +289,33 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                 mma_bf16_16816(s[2 * kb + 1], a, bb[2], bb[3]);
             }
         }
-        // ---- bias, mask, online softmax (thread: rows g / g+8, keys nt*8 + 2tq + {0,1}) ----
+        // ---- bias, mask (thread: rows g / g+8, keys nt*8 + 2tq + {0,1}) ----
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int jl = nt * 8 + 2 * tq + e;
+                const int kl = s_klab[jl], kr = s_krel[jl];
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    float v = -INFINITY;
+                    if (qlab[rh] >= 0 && kl == qlab[rh]) {
+                        const int idx = qrel[rh] - kr;
+                        const float bias = bias_in_smem ? s_bias[idx] : __ldg(bias_table + (size_t)idx * heads + h);
+                        v = s[nt][2 * rh + e] * scale + bias;
+                    }
+                    s[nt][2 * rh + e] = v;
+                    mx[rh] = fmaxf(mx[rh], v);
+                }
+            }
+        // ---- online softmax ----
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh) {
-            float mx = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int jl = nt * 8 + 2 * tq + e;
-                    const bool ok = qlab[rh] >= 0 && s_klab[jl] == qlab[rh];
-                    float v = -INFINITY;
-                    if (ok) v = s[nt][2 * rh + e] * scale + __ldg(bias_table + (size_t)(qrel[rh] - s_krel[jl]) * heads + h);
-                    s[nt][2 * rh + e] = v;
-                    mx = fmaxf(mx, v);
-                }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            const float m_new = fmaxf(m_run[rh], mx);
+            float m = mx[rh];
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            const float m_new = fmaxf(m_run[rh], m);
             const float alpha = (m_new == -INFINITY) ? 1.f : __expf(m_run[rh] - m_new);
             float sum = 0.f;
 #pragma unroll
@@ -313,6 +353,7 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                 mma_bf16_16816(o[jn + 1], pa, bb[2], bb[3]);
             }
         }
+        __syncthreads();   // this stage (rows + metadata) is free for the prefetch of chunk ch + 2
     }
     // ---- normalise and scatter the rows of real tokens (padding slots are dropped = the reference's unpadding) ----
 #pragma unroll
@@ -471,6 +512,7 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
     g->rel.resize(vol);
     for (int i = 0; i < vol; ++i) g->rel[i] = (i / (b1 * b2)) * s1 + ((i / b2) % b1) * s2 + i % b2;
     g->rel_off = (spec.size[0] - 1) * s1 + (b1 - 1) * s2 + (b2 - 1);
+    g->n_rel = (2 * spec.size[0] - 1) * s1;   // rows of relative_position_bias_table
     // the axial fast path: one non-unit axis spanning the whole dimension, no shift / padding / dilation effects
     g->axial_axis = -1;
     int non_unit = 0, ax = 0;
@@ -489,17 +531,21 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
     PD_CHECK(g.num_cuboids >= 1 && g.num_cuboids <= 65535 && B * heads <= 65535, PD_ERR_SHAPE,
              "cuboid_attention: %d cuboids, %d sample-heads exceed the grid limits", g.num_cuboids, B * heads);
     dim3 grid(ceil_div(g.volume, kQTile), g.num_cuboids, B * heads);
+    // the head's table column goes to shared memory when it fits (PD_CUBOID_GLOBAL_BIAS=1 keeps the global gather: A/B)
+    static const bool global_bias = getenv("PD_CUBOID_GLOBAL_BIAS") != nullptr;
+    const int n_rel_smem = (!global_bias && g.n_rel <= kMaxRelSmem) ? g.n_rel : 0;
 #define PD_LAUNCH_CUB(HDV)                                                                                          \
     do {                                                                                                            \
-        const size_t smem = (size_t)3 * kQTile * (HDV + 8) * sizeof(bf16) + 6 * kQTile * sizeof(int);              \
-        static bool attr_set = false;                                                                               \
-        if (!attr_set) {                                                                                            \
+        const size_t smem = (size_t)5 * kQTile * (HDV + 8) * sizeof(bf16) + 9 * kQTile * sizeof(int) +              \
+                            (size_t)n_rel_smem * sizeof(float);                                                     \
+        static size_t attr_bytes = 0;                                                                               \
+        if (smem > attr_bytes) {                                                                                    \
             PD_CUDA(cudaFuncSetAttribute(cuboid_attention_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                               \
-            attr_set = true;                                                                                        \
+            attr_bytes = smem;                                                                                      \
         }                                                                                                           \
         PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, N, C,    \
-                  heads, g.volume, g.rel_off);                                                                      \
+                  heads, g.volume, g.rel_off, n_rel_smem);                                                          \
     } while (0)
     switch (hd) {
         case 16: PD_LAUNCH_CUB(16); break;
@@ -530,6 +576,7 @@ int CuboidTablesDev::upload(const CuboidTables& t) {
     dev.num_cuboids = t.num_cuboids;
     dev.volume = t.volume;
     dev.rel_off = t.rel_off;
+    dev.n_rel = t.n_rel;
     return PD_OK;
 }
 CuboidTablesDev::~CuboidTablesDev() {

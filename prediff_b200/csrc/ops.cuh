@@ -38,7 +38,7 @@ struct CuboidLayerSpec {   // constructor arguments of one CuboidSelfAttentionLa
 };
 struct CuboidTables {      // host tables of one layer on a (T, H, W) grid
     int size[3], shift[3], pad[3];                 // effective size / shift (:563-592), end padding per axis
-    int num_cuboids = 0, volume = 0, rel_off = 0;
+    int num_cuboids = 0, volume = 0, rel_off = 0, n_rel = 0;
     int axial_axis = -1;                           // >= 0: the layer is exactly axial_attention() along that axis
     std::vector<int> tok;  // [num_cuboids * volume] token row inside a sample's [T*H*W] block, -1 = padding slot
     std::vector<int> lab;  // [num_cuboids * volume] shifted-window region label, -1 = masked out ('ignore' padding)
@@ -47,7 +47,7 @@ struct CuboidTables {      // host tables of one layer on a (T, H, W) grid
 int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int padding_type, CuboidTables* out);
 struct CuboidDev {         // device copies
     const int *tok = nullptr, *lab = nullptr, *rel = nullptr;
-    int num_cuboids = 0, volume = 0, rel_off = 0;
+    int num_cuboids = 0, volume = 0, rel_off = 0, n_rel = 0;   // n_rel: rows of the bias table
 };
 struct CuboidTablesDev {   // owner of the device copies
     void* mem = nullptr;
