@@ -159,27 +159,27 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
 // shared memory in chunks of 64 with an online softmax; QK^T and PV on warp-level mma.sync m16n8k16 (bf16, fp32
 // accumulate). Padding slots contribute zero q/k/v rows (the reference pads after its LayerNorm and qkv has no bias).
 constexpr int kQTile = 64;
-constexpr int kMaxRelSmem = 24576;   // bias-table entries of one head staged in shared memory (96 KB) - covers the
-                                     // 25 x 31 x 31 table of full attention on the shipped 13 x 16 x 16 grid
+constexpr int kMaxRelSmem = 4096;    // bias-table rows of one head staged in shared memory (<= 16 KB per block)
 
-// K/V chunks are double-buffered (the gather of chunk c+1 is in flight under the math of chunk c) and, when it fits,
-// the head's column of the relative-position table sits in shared memory: at volume 3328 the per-score table gather
-// from L2 (one 32-byte sector per score, 1.2 GB per launch) was what bound the first version of this kernel.
+// Two schedules, chosen by the launcher (see cuboid_attention): kv_stages == 2 double-buffers the K/V chunks (the gather
+// of chunk c+1 is in flight under the math of chunk c); kv_stages == 1 fetches a chunk after the previous one is
+// consumed and keeps the footprint at three tiles. n_rel_smem > 0: the head's column of the relative-position table
+// sits in shared memory instead of being gathered from L2 per score.
 template <int HD>
 __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __restrict__ qkv,
                                                                const float* __restrict__ bias_table,
                                                                bf16* __restrict__ out, const int* __restrict__ tok,
                                                                const int* __restrict__ lab, const int* __restrict__ rel,
                                                                int N, int C, int heads, int vol, int rel_off,
-                                                               int n_rel_smem) {
+                                                               int n_rel_smem, int kv_stages) {
     grid_dep_launch();
     grid_dep_wait();
     constexpr int LD = HD + 8;        // row pitch: +16 B keeps ldmatrix bank-conflict free
     constexpr int VPR = HD / 8;       // 16-byte vectors per row
     extern __shared__ __align__(16) uint8_t smem_cub[];
     bf16* sQ = reinterpret_cast<bf16*>(smem_cub);
-    bf16* sKV = sQ + kQTile * LD;                                  // [2 stages][K | V][64][LD]
-    int* s_qtok = reinterpret_cast<int*>(sKV + 4 * kQTile * LD);
+    bf16* sKV = sQ + kQTile * LD;                                  // [kv_stages][K | V][64][LD]
+    int* s_qtok = reinterpret_cast<int*>(sKV + kv_stages * 2 * kQTile * LD);
     int* s_qlab = s_qtok + kQTile;
     int* s_qrel = s_qlab + kQTile;
     int* s_kmeta = s_qrel + kQTile;                                // [2 stages][tok | lab | rel][64]
@@ -257,14 +257,20 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
     for (int jn = 0; jn < HD / 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
 
     const int n_chunks = (vol + kQTile - 1) / kQTile;
+    const bool two_stage = kv_stages == 2;
     for (int ch = 0; ch < n_chunks; ++ch) {
-        const int stage = ch & 1;
-        if (ch + 1 < n_chunks) {   // prefetch the next chunk into the other stage (its last readers passed the
-            load_meta((ch + 1) * kQTile, stage ^ 1);   // barrier that closes iteration ch - 1)
+        const int stage = two_stage ? (ch & 1) : 0;
+        if (two_stage && ch + 1 < n_chunks) {   // prefetch the next chunk into the other stage (its last readers
+            load_meta((ch + 1) * kQTile, stage ^ 1);   // passed the barrier that closes iteration ch - 1)
             __syncthreads();
             load_rows(stage ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
+            if (!two_stage && ch > 0) {   // single stage: the chunk is fetched after the previous one is consumed
+                load_meta(ch * kQTile, 0);
+                __syncthreads();
+                load_rows(0);
+            }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                 mma_bf16_16816(o[jn + 1], pa, bb[2], bb[3]);
             }
         }
-        __syncthreads();   // this stage (rows + metadata) is free for the prefetch of chunk ch + 2
+        __syncthreads();   // this stage (rows + metadata) is free for the next fetch into it
     }
     // ---- normalise and scatter the rows of real tokens (padding slots are dropped = the reference's unpadding) ----
 #pragma unroll
@@ -532,12 +538,22 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
              "cuboid_attention: %d cuboids, %d sample-heads exceed the grid limits", g.num_cuboids, B * heads);
     dim3 grid(ceil_div(g.volume, kQTile), g.num_cuboids, B * heads);
     // the head's table column goes to shared memory when it fits (PD_CUBOID_GLOBAL_BIAS=1 keeps the global gather: A/B)
+    // Schedule (measured on B200, batch 4, profiles/trace_r01f_* = single stage + global gather vs trace_r01g_* = two
+    // stages + table column in shared memory): volumes of 128-256 with small tables gain 25-30 % from the pipelined
+    // variant; a single-chunk cuboid has nothing to prefetch and only pays the second stage's shared memory (fewer
+    // resident blocks); the 24 025-row table of full attention costs 96 KB per block = one block per SM and was 1.7x
+    // slower than gathering from L2 with 6+ resident blocks. So: two stages only when there is more than one chunk, the
+    // table column in shared memory only up to kMaxRelSmem rows. PD_CUBOID_GLOBAL_BIAS / PD_CUBOID_ONE_STAGE force
+    // the other choice (A/B).
     static const bool global_bias = getenv("PD_CUBOID_GLOBAL_BIAS") != nullptr;
+    static const bool one_stage = getenv("PD_CUBOID_ONE_STAGE") != nullptr;
     const int n_rel_smem = (!global_bias && g.n_rel <= kMaxRelSmem) ? g.n_rel : 0;
+    const bool big_table = g.n_rel > kMaxRelSmem;
+    const int kv_stages = (g.volume > kQTile && !one_stage && !big_table) ? 2 : 1;
 #define PD_LAUNCH_CUB(HDV)                                                                                          \
     do {                                                                                                            \
-        const size_t smem = (size_t)5 * kQTile * (HDV + 8) * sizeof(bf16) + 9 * kQTile * sizeof(int) +              \
-                            (size_t)n_rel_smem * sizeof(float);                                                     \
+        const size_t smem = (size_t)(1 + 2 * kv_stages) * kQTile * (HDV + 8) * sizeof(bf16) +                       \
+                            9 * kQTile * sizeof(int) + (size_t)n_rel_smem * sizeof(float);                          \
         static size_t attr_bytes = 0;                                                                               \
         if (smem > attr_bytes) {                                                                                    \
             PD_CUDA(cudaFuncSetAttribute(cuboid_attention_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -545,7 +561,7 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
             attr_bytes = smem;                                                                                      \
         }                                                                                                           \
         PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, N, C,    \
-                  heads, g.volume, g.rel_off, n_rel_smem);                                                          \
+                  heads, g.volume, g.rel_off, n_rel_smem, kv_stages);                                               \
     } while (0)
     switch (hd) {
         case 16: PD_LAUNCH_CUB(16); break;
