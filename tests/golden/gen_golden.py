@@ -349,7 +349,7 @@ def gen_patterns():
     from prediff.models.cuboid_transformer.cuboid_transformer import CuboidSelfAttentionLayer
     import pattern_cases as PC
     out = {}
-    for tag, dims, C, heads, size, strat, shift, pad in PC.LAYER_CASES:
+    for tag, dims, C, heads, size, strat, shift, pad in PC.LAYER_CASES + PC.sweep_cases():
         m = CuboidSelfAttentionLayer(dim=C, num_heads=heads, cuboid_size=size, shift_size=shift, strategy=tuple(strat),
                                      padding_type=pad, qkv_bias=False, attn_drop=0.0, proj_drop=0.0,
                                      use_final_proj=True, norm_layer="layer_norm", use_global_vector=False,

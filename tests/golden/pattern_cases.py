@@ -30,3 +30,19 @@ def layer_spec(C, heads, size):
     n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
     return [("a.relative_position_bias_table", (n_rel, heads)), ("a.qkv.weight", (3 * C, C)),
             ("a.proj.weight", (C, C)), ("a.proj.bias", (C,)), ("a.norm.weight", (C,)), ("a.norm.bias", (C,))]
+
+
+def sweep_cases(n=32, seed=9009):
+    """Deterministic random sweep of small CuboidSelfAttentionLayer configurations (grid <= 6 x 7 x 7, C = 16, 2 heads):
+    random cuboid sizes (some larger than the grid -> clipped), strategies, shifts and both padding types."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for k in range(n):
+        dims = tuple(int(v) for v in rng.integers(2, [7, 8, 8]))
+        size = tuple(int(v) for v in rng.integers(1, [6, 6, 6]))
+        strat = "".join(rng.choice(["l", "d"]) for _ in range(3))
+        shift = tuple(int(rng.integers(0, max(1, s // 2 + 1))) for s in size)
+        pad = "zeros" if rng.integers(0, 2) == 0 else "ignore"
+        out.append((f"sweep{k}", dims, 16, 2, size, strat, shift, pad))
+    return out

@@ -37,7 +37,10 @@ def test_pattern_registry_names():
         [(13, 1, 1), (1, 4, 1), (1, 4, 1), (1, 1, 4), (1, 1, 4)]
 
 
-@pytest.mark.parametrize("case", PC.LAYER_CASES, ids=[c[0] for c in PC.LAYER_CASES])
+_ALL_LAYER_CASES = PC.LAYER_CASES + PC.sweep_cases()
+
+
+@pytest.mark.parametrize("case", _ALL_LAYER_CASES, ids=[c[0] for c in _ALL_LAYER_CASES])
 def test_oracle_layer_vs_reference(case):
     tag, dims, C, heads, size, strat, shift, pad = case
     sd = O.to_torch_sd(Wt.seeded_state_dict(PC.layer_spec(C, heads, size), PC.LAYER_SEED))
@@ -85,7 +88,7 @@ def attention_from_tables(qkv, table, heads, geo):
     return out[:, :-1].reshape(B, T, H, W, C)
 
 
-GEOM_CASES = [(c[1], c[3], c[4], c[5], c[6], c[7]) for c in PC.LAYER_CASES] + [
+GEOM_CASES = [(c[1], c[3], c[4], c[5], c[6], c[7]) for c in _ALL_LAYER_CASES] + [
     ((13, 16, 16), 4, (13, 1, 1), "lll", (0, 0, 0), "zeros"),
     ((13, 16, 16), 4, (1, 16, 16), "lll", (0, 0, 0), "ignore"),
     ((13, 8, 8), 4, (2, 8, 8), "lll", (1, 4, 4), "ignore"),
