@@ -127,3 +127,40 @@ def test_lvlb_weights_through_c_abi_bit_exact_vs_reference():
     L.check(L.lib().pd_sampler_get_buffer(h, b"lvlb_weights", buf.ctypes.data_as(ctypes.c_void_p)))
     L.lib().pd_sampler_destroy(h)
     assert np.array_equal(buf, g["lvlb_weights"])
+
+
+def test_pattern_and_loss_arguments_fail_loudly():
+    """Bad cuboid-layer specs / loss options are rejected with an error (no silent default, no fallback)."""
+    import torch.nn as nn
+    from prediff_b200.diffusion import LatentDiffusion
+    i3 = ctypes.c_int32 * 3
+    meta = (ctypes.c_int32 * 12)()
+    lib = L.lib()
+    # padding_type 2 ('nearest') is not built; cuboid sizes must be >= 1; strategies are 0 / 1
+    for size, strat, shift, pad in (((4, 4, 4), (0, 0, 0), (0, 0, 0), 2), ((0, 4, 4), (0, 0, 0), (0, 0, 0), 0),
+                                    ((4, 4, 4), (0, 2, 0), (0, 0, 0), 0), ((4, 4, 4), (0, 0, 0), (-1, 0, 0), 0)):
+        rc = lib.pd_cuboid_tables(13, 16, 16, i3(*size), i3(*strat), i3(*shift), pad, meta, None, None, None, ctypes.c_int64(0))
+        assert rc < 0 and lib.pd_last_error()
+    # output arrays too small for the tables
+    buf = np.zeros(8, np.int32)
+    rc = lib.pd_cuboid_tables(13, 16, 16, i3(4, 4, 4), i3(0, 0, 0), i3(0, 0, 0), 0, meta, buf.ctypes.data_as(ctypes.c_void_p),
+                              None, None, ctypes.c_int64(8))
+    assert rc < 0
+    # pd_unet_create_ex: number of attention layers per block outside 1..PD_MAX_ATTN_LAYERS
+    from prediff_b200.unet import _CUnetConfig, _CUnetPattern
+    cc = _CUnetConfig(7, 6, 16, 16, 64, 64, (ctypes.c_int32 * 2)(1, 1), 4, 2)
+    pt = _CUnetPattern()
+    pt.n_layers[0], pt.n_layers[1] = 0, 9
+    h = ctypes.c_void_p()
+    assert lib.pd_unet_create_ex(ctypes.byref(cc), ctypes.byref(pt), ctypes.byref(h)) < 0 and not h.value
+
+    class Eps(nn.Module):
+        def forward(self, x, t, c):
+            return x
+
+    for kw in (dict(loss_type="huber"), dict(learn_logvar=True), dict(parameterization="x0")):
+        with pytest.raises(NotImplementedError):
+            LatentDiffusion(torch_nn_module=Eps(), **kw)
+    ld = LatentDiffusion(torch_nn_module=Eps(), loss_type="l1", original_elbo_weight=0.5)
+    assert ld.lvlb_weights.shape == (1000,) and "lvlb_weights" not in ld.state_dict()   # non-persistent, as in the reference
+    assert tuple(ld.logvar.shape) == (1000,) and ld.loss_mean_dim == (1, 2, 3, 4)
