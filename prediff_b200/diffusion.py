@@ -7,8 +7,11 @@ Keeps the reference call surface used by the Lightning script (SURVEY.md section
 buffers - plus `ddim_sample_loop`, the 50-step DDIM the benchmark is quoted on (the reference has no DDIM
 sampler; SURVEY.md D1 / section 8 row S6 define it from the reference's own helper functions).
 
-Training-side members (losses, EMA, optimizers, Lightning hooks) are out of scope.
+Also mirrored, because the inference script's validation_step uses them: `forward` / `p_losses` (forward loss, no
+gradients) and `ema_scope` / `model_ema` (EMA weights swapped in for evaluation). Optimizers, backward passes and
+Lightning hooks are out of scope.
 """
+import contextlib
 import ctypes
 from typing import Any, Callable, Dict, Optional, Sequence
 
@@ -62,7 +65,12 @@ class LatentDiffusion(nn.Module):
         self.data_shape = tuple(data_shape)
         self.latent_shape = tuple(latent_shape)
         self.batch_axis, self.t_axis, self.h_axis, self.w_axis, self.c_axis = 0, 1, 2, 3, 4
-        self.use_ema = False  # EMA shadow weights are a training feature (utils/ema.py); out of scope
+        # EMA shadow weights (latent_diffusion.py:128-131): kept under the reference's buffer names so its checkpoints
+        # load; evaluation swaps them in through ema_scope()
+        self.use_ema = bool(use_ema)
+        if self.use_ema:
+            from .ema import LitEma
+            self.model_ema = LitEma(self.torch_nn_module, include_frozen=hasattr(self.torch_nn_module, "_dirty"))
         self.scale_factor = scale_factor
         self.alignment_fn = None
         self.shorten_cond_schedule = False
@@ -118,6 +126,34 @@ class LatentDiffusion(nn.Module):
     def set_alignment(self, alignment_fn: Callable = None):
         """latent_diffusion.py:169-180. Signature `alignment_fn(zt, t, zc=None, y=None, **kwargs)`."""
         self.alignment_fn = alignment_fn
+
+    def _weights_changed(self):
+        """The CUDA denoiser repacks its weights lazily; parameter writes through `.data` must be announced."""
+        if hasattr(self.torch_nn_module, "_dirty"):
+            self.torch_nn_module._dirty = True
+
+    @contextlib.contextmanager
+    def ema_scope(self, context=None):
+        """latent_diffusion.py:280-293: run the body with the EMA weights in the denoiser, then restore."""
+        if self.use_ema:
+            self.model_ema.store(self.torch_nn_module.parameters())
+            self.model_ema.copy_to(self.torch_nn_module)
+            self._weights_changed()
+            if context is not None:
+                print(f"{context}: Switched to EMA weights")
+        try:
+            yield None
+        finally:
+            if self.use_ema:
+                self.model_ema.restore(self.torch_nn_module.parameters())
+                self._weights_changed()
+                if context is not None:
+                    print(f"{context}: Restored training weights")
+
+    def on_train_batch_end(self, *args, **kwargs):
+        """latent_diffusion.py:484-486 (the update itself is plain tensor arithmetic; training is not built)."""
+        if self.use_ema:
+            self.model_ema(self.torch_nn_module)
 
     @property
     def einops_layout(self):

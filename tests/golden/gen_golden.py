@@ -309,6 +309,57 @@ def gen_unet(tag, cfg, B, ts):
     save(f"unet_{tag}", t=t, out=out)
 
 
+def ema_model(seed=5150):
+    """A small module with a frozen parameter and dotted parameter names, seeded."""
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(seed)
+    m = nn.Sequential(nn.Linear(6, 5), nn.Sequential(nn.LayerNorm(5), nn.Linear(5, 3, bias=False)))
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape, generator=g))
+    m[0].bias.requires_grad_(False)
+    return m
+
+
+def ema_drift(m, step):
+    """Deterministic parameter change standing in for an optimizer step."""
+    with torch.no_grad():
+        for i, p in enumerate(m.parameters()):
+            p.add_(0.01 * (step + 1) * torch.cos(torch.arange(p.numel(), dtype=torch.float32).reshape(p.shape) + i))
+
+
+@torch.no_grad()
+def gen_ema():
+    """Shadow parameters of the unmodified reference LitEma (src/prediff/utils/ema.py) after 1, 2 and 12 updates
+    (decay_t = min(decay, (1 + n) / (10 + n)) warm-up), and the store / copy_to / restore round trip."""
+    from prediff.utils.ema import LitEma
+    m = ema_model()
+    ema = LitEma(m, decay=0.9)
+    out = {"keys": np.array(sorted(k for k, _ in ema.named_buffers()))}
+    for step in range(12):
+        ema_drift(m, step)
+        ema(m)
+        if step + 1 in (1, 2, 12):
+            for k, v in ema.named_buffers():
+                out[f"s{step + 1}_{k}"] = v.clone()
+    before = [p.clone() for p in m.parameters()]
+    ema.store(m.parameters())
+    ema.copy_to(m)
+    out["swapped_0weight"] = m[0].weight.clone()
+    out["swapped_0bias_frozen"] = m[0].bias.clone()
+    ema.restore(m.parameters())
+    assert all(torch.equal(a, b) for a, b in zip(before, m.parameters()))
+    # every state_dict key (+ shape) of the reference LatentDiffusion(use_ema=True) on the tiny config: what a Lightning
+    # checkpoint of the PreDiff module carries for this class
+    ucfg, vcfg = Wt.TINY_UNET, Wt.TINY_VAE
+    ldm = ref_ldm(ref_unet(ucfg), ref_vae(vcfg), ucfg, vcfg)
+    ldm_ema = type(ldm)(torch_nn_module=ref_unet(ucfg), layout="NTHWC", data_shape=(ucfg.t_out, vcfg.h, vcfg.w, 1),
+                        use_ema=True, latent_shape=(ucfg.t_out, ucfg.h, ucfg.w, ucfg.c), first_stage_model=ref_vae(vcfg),
+                        cond_stage_model="__is_first_stage__")
+    out["ldm_state_dict_keys"] = np.array([f"{k}|{','.join(str(d) for d in v.shape)}" for k, v in ldm_ema.state_dict().items()])
+    save("ema", **out)
+
+
 LOSS_CASES = [("l2", dict(loss_type="l2")),
               ("l1w", dict(loss_type="l1", original_elbo_weight=0.3, l_simple_weight=0.7, logvar_init=0.5))]
 
@@ -483,5 +534,7 @@ if __name__ == "__main__":
         gen_patterns()
     if "losses" in todo:
         gen_losses()
+    if "ema" in todo:
+        gen_ema()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)
