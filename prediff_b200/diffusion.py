@@ -74,6 +74,7 @@ class LatentDiffusion(nn.Module):
         self.scale_factor = scale_factor
         self.alignment_fn = None
         self.shorten_cond_schedule = False
+        self.cond_stage_trainable = False   # forced off for '__is_first_stage__' in the reference too (:338-341)
         # loss hyper-parameters of p_losses (latent_diffusion.py:134-150); only the forward (validation) loss is built
         if loss_type not in ("l1", "l2"):
             raise NotImplementedError(f"prediff_b200.LatentDiffusion: unknown loss type '{loss_type}'")
