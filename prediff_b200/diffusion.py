@@ -167,6 +167,58 @@ class LatentDiffusion(nn.Module):
     def get_batch_latent_shape(self, batch_size=1):
         return (batch_size,) + tuple(self.latent_shape)
 
+    def get_batch_data_shape(self, batch_size=1):
+        """latent_diffusion.py:204-214."""
+        return (batch_size,) + tuple(self.data_shape)
+
+    @property
+    def einops_spatial_layout(self):
+        return "(N T) C H W"   # latent_diffusion.py:394-399 for the 5-d 'NTHWC' layout
+
+    @property
+    def device(self):
+        """Where the denoiser's work runs (LightningModule.device in the reference)."""
+        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        """latent_diffusion.py:381-391: posterior sample (or the tensor itself), times scale_factor."""
+        z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
+        if not torch.is_tensor(z):
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+        return self.scale_factor * z
+
+    # ---- the reference's step helpers (latent_diffusion.py:553-596), plain tensor expressions on the buffers. The
+    # device-resident loop evaluates the same formulas inside sampler_update_kernel; these exist for callers that use
+    # them directly (score correctors, visualisation) ----
+    def _buf(self, name, like):
+        return getattr(self, name).to(like.device)
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        return (self.extract_into_tensor(self._buf("sqrt_recip_alphas_cumprod", x_t), t, x_t.shape) * x_t -
+                self.extract_into_tensor(self._buf("sqrt_recipm1_alphas_cumprod", x_t), t, x_t.shape) * noise)
+
+    def q_posterior(self, x_start, x_t, t):
+        mean = (self.extract_into_tensor(self._buf("posterior_mean_coef1", x_t), t, x_t.shape) * x_start +
+                self.extract_into_tensor(self._buf("posterior_mean_coef2", x_t), t, x_t.shape) * x_t)
+        var = self.extract_into_tensor(self._buf("posterior_variance", x_t), t, x_t.shape)
+        log_var = self.extract_into_tensor(self._buf("posterior_log_variance_clipped", x_t), t, x_t.shape)
+        return mean, var, log_var
+
+    def p_mean_variance(self, zt, zc, t, clip_denoised: bool = False, return_x0=False, score_corrector=None,
+                        corrector_kwargs=None):
+        model_out = self.apply_model(zt, t, zc)
+        if score_corrector is not None:
+            model_out = score_corrector.modify_score(self, model_out, zt, t, zc, **(corrector_kwargs or {}))
+        z_recon = self.predict_start_from_noise(zt, t=t, noise=model_out)
+        if clip_denoised:
+            z_recon = z_recon.clamp(-1., 1.)
+        mean, var, log_var = self.q_posterior(x_start=z_recon, x_t=zt, t=t)
+        return (mean, var, log_var, z_recon) if return_x0 else (mean, var, log_var)
+
+    def aligned_mean(self, zt, t, zc, y, orig_mean, orig_log_var, **kwargs):
+        align_gradient = self.alignment_fn(zt, t, zc=zc, y=y, **kwargs)
+        return orig_mean - (0.5 * orig_log_var).exp() * align_gradient
+
     # ---- first stage glue (latent_diffusion.py:361-432) ------------------------------------------------------
     @torch.no_grad()
     def cond_stage_forward(self, c: Dict[str, Any]):

@@ -110,6 +110,17 @@ class CuboidTransformerUNet(nn.Module):
         self._handle = None
         self._dirty = True
 
+    # ---- shape properties of the reference class (cuboid_transformer_unet.py:377-404) -------------------------
+    @property
+    def data_shape(self):
+        c = self.cfg
+        return (c.t_in + c.t_out, c.h, c.w, c.c + 1)   # + the observed / target indicator channel
+
+    @property
+    def mem_shapes(self):
+        c = self.cfg
+        return [(c.T, c.h, c.w, c.units[0]), (c.T, c.h // 2, c.w // 2, c.units[1])]
+
     # ---- C++ handle management -----------------------------------------------------------------------------
     def _ensure_handle(self):
         if self._handle is None:

@@ -116,6 +116,14 @@ class AutoencoderKL(nn.Module):
                 L.check(L.lib().pd_vae_encode(self.handle, L.ptr(x[i:i + n]), L.ptr(out[i:i + n]), n, L.stream_ptr()))
         return out.permute(0, 3, 1, 2)
 
+    def enable_slicing(self):
+        """autoencoder_kl.py:91-98. Decoding already walks the batch in slices of `max_frames` frames with identical
+        results, so the flag only mirrors the reference attribute."""
+        self.use_slicing = True
+
+    def disable_slicing(self):
+        self.use_slicing = False
+
     def encode(self, x):
         """Returns the posterior (mode() = mean = first latent_channels channels; distributions.py:70-71)."""
         return reference_distribution_class()(self.encode_moments(x))

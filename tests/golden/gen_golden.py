@@ -360,6 +360,30 @@ def gen_ema():
     save("ema", **out)
 
 
+class DummyEps(torch.nn.Module):
+    """A closed-form stand-in denoiser for the step-helper goldens (no weights)."""
+
+    def forward(self, x, t, cond):
+        return 0.5 * torch.tanh(x) + 0.1 * cond.mean(dim=1, keepdim=True)[:, :, :, :, :x.shape[-1]]
+
+
+@torch.no_grad()
+def gen_helpers():
+    """predict_start_from_noise / q_posterior / p_mean_variance / aligned_mean of the unmodified reference
+    LatentDiffusion (latent_diffusion.py:553-596) with a closed-form denoiser."""
+    ldm = ref_ldm(DummyEps(), ref_vae(Wt.TINY_VAE), Wt.TINY_UNET, Wt.TINY_VAE)
+    B = 3
+    zt, zc, noise = inp(61, B, 6, 4, 4, 8), inp(62, B, 7, 4, 4, 8), inp(63, B, 6, 4, 4, 8)
+    t = torch.tensor([0, 431, 999], dtype=torch.long)
+    out = {"x0": ldm.predict_start_from_noise(zt, t, noise)}
+    out["qp_mean"], out["qp_var"], out["qp_logvar"] = ldm.q_posterior(noise, zt, t)
+    out["pm_mean"], out["pm_var"], out["pm_logvar"], out["pm_x0"] = ldm.p_mean_variance(zt, zc, t, clip_denoised=False, return_x0=True)
+    out["pm_mean_clipped"] = ldm.p_mean_variance(zt, zc, t, clip_denoised=True)[0]
+    ldm.set_alignment(lambda zt, t, zc=None, y=None, **kw: 0.2 * zt + kw["shift"])
+    out["aligned"] = ldm.aligned_mean(zt, t, zc, None, out["pm_mean"], out["pm_logvar"], shift=0.05)
+    save("helpers", **out)
+
+
 LOSS_CASES = [("l2", dict(loss_type="l2")),
               ("l1w", dict(loss_type="l1", original_elbo_weight=0.3, l_simple_weight=0.7, logvar_init=0.5))]
 
@@ -536,5 +560,7 @@ if __name__ == "__main__":
         gen_losses()
     if "ema" in todo:
         gen_ema()
+    if "helpers" in todo:
+        gen_helpers()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

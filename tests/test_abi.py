@@ -164,3 +164,16 @@ def test_pattern_and_loss_arguments_fail_loudly():
     ld = LatentDiffusion(torch_nn_module=Eps(), loss_type="l1", original_elbo_weight=0.5)
     assert ld.lvlb_weights.shape == (1000,) and "lvlb_weights" not in ld.state_dict()   # non-persistent, as in the reference
     assert tuple(ld.logvar.shape) == (1000,) and ld.loss_mean_dim == (1, 2, 3, 4)
+
+
+def test_shape_properties_of_the_reference_classes():
+    from prediff_b200.unet import CuboidTransformerUNet
+    from prediff_b200.vae import AutoencoderKL
+    m = CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], base_units=256, depth=[4, 4])
+    assert m.data_shape == (13, 16, 16, 65)                                   # cuboid_transformer_unet.py:377-384
+    assert m.mem_shapes == [(13, 16, 16, 256), (13, 8, 8, 512)]               # :386-404
+    v = AutoencoderKL()
+    v.enable_slicing()
+    assert v.use_slicing
+    v.disable_slicing()
+    assert not v.use_slicing

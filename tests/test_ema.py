@@ -75,3 +75,27 @@ def test_latent_diffusion_state_dict_keys_equal_the_reference():
     assert set(mine) == set(ref), (sorted(set(ref) - set(mine))[:5], sorted(set(mine) - set(ref))[:5])
     assert mine == ref
     ld.load_state_dict(ld.state_dict(), strict=True)
+
+
+def test_step_helper_methods_match_reference_bit_exactly():
+    """predict_start_from_noise / q_posterior / p_mean_variance / aligned_mean (latent_diffusion.py:553-596) of the
+    mirror vs the unmodified reference (tests/golden/helpers.npz), with a closed-form denoiser on CPU tensors."""
+    from tests.golden.gen_golden import DummyEps, inp
+    H = np.load(os.path.join(os.path.dirname(__file__), "golden", "helpers.npz"))
+    ld = LatentDiffusion(torch_nn_module=DummyEps())
+    zt, zc, noise = inp(61, 3, 6, 4, 4, 8), inp(62, 3, 7, 4, 4, 8), inp(63, 3, 6, 4, 4, 8)
+    t = torch.tensor([0, 431, 999], dtype=torch.long)
+
+    def same(a, key):
+        assert np.array_equal(a.numpy(), H[key]), key
+
+    same(ld.predict_start_from_noise(zt, t, noise), "x0")
+    for a, k in zip(ld.q_posterior(noise, zt, t), ("qp_mean", "qp_var", "qp_logvar")):
+        same(a, k)
+    for a, k in zip(ld.p_mean_variance(zt, zc, t, clip_denoised=False, return_x0=True), ("pm_mean", "pm_var", "pm_logvar", "pm_x0")):
+        same(a, k)
+    same(ld.p_mean_variance(zt, zc, t, clip_denoised=True)[0], "pm_mean_clipped")
+    ld.set_alignment(lambda zt, t, zc=None, y=None, **kw: 0.2 * zt + kw["shift"])
+    same(ld.aligned_mean(zt, t, zc, None, torch.from_numpy(H["pm_mean"]), torch.from_numpy(H["pm_logvar"]), shift=0.05), "aligned")
+    assert ld.get_batch_data_shape(5) == (5, 6, 128, 128, 1) and ld.einops_spatial_layout == "(N T) C H W"
+    assert torch.equal(ld.get_first_stage_encoding(zt), zt)
