@@ -39,7 +39,6 @@ class AutoencoderKL(nn.Module):
         self.use_slicing = False
         build_param_tree(self, vae_param_spec(self.cfg))
         self._handle = None
-        self.use_slicing = False   # autoencoder_kl.py:78
         self._dirty = True
 
     def _ensure_handle(self):
