@@ -78,15 +78,17 @@ class LatentDiffusion(nn.Module):
         # loss hyper-parameters of p_losses (latent_diffusion.py:134-150); only the forward (validation) loss is built
         if loss_type not in ("l1", "l2"):
             raise NotImplementedError(f"prediff_b200.LatentDiffusion: unknown loss type '{loss_type}'")
-        if learn_logvar:
-            raise NotImplementedError("prediff_b200.LatentDiffusion: learn_logvar=True is a training feature (not built)")
         self.loss_type = loss_type
         self.original_elbo_weight = original_elbo_weight
         self.l_simple_weight = l_simple_weight
-        self.learn_logvar = False
+        self.learn_logvar = bool(learn_logvar)   # the shipped config sets it (cfg.yaml:95); the values come from the checkpoint
         self.logvar_init = float(logvar_init)
         self.register_schedule(timesteps=timesteps, linear_start=linear_start, linear_end=linear_end)
-        self.register_buffer("logvar", torch.full(fill_value=logvar_init, size=(self.num_timesteps,)))
+        logvar = torch.full(fill_value=logvar_init, size=(self.num_timesteps,))
+        if self.learn_logvar:   # latent_diffusion.py:146-150: a parameter when learned, a buffer otherwise (same key)
+            self.logvar = nn.Parameter(logvar, requires_grad=True)
+        else:
+            self.register_buffer("logvar", logvar)
         self.first_stage_model = first_stage_model
         if first_stage_model is not None:
             first_stage_model.eval()
@@ -295,15 +297,28 @@ class LatentDiffusion(nn.Module):
                     1 if self.loss_type == "l1" else 0, ctypes.c_float(self.logvar_init), ctypes.c_float(self.l_simple_weight),
                     ctypes.c_float(self.original_elbo_weight), L.ptr(per_sample), L.ptr(out4), L.stream_ptr()))
             self.last_loss_per_sample = per_sample
-            return out4[2], {f"{prefix}/loss_simple": out4[0], f"{prefix}/loss_vlb": out4[1], f"{prefix}/loss": out4[2]}
+            if not self.learn_logvar:   # fixed logvar: the four scalars were reduced on the device by the same call
+                return out4[2], {f"{prefix}/loss_simple": out4[0], f"{prefix}/loss_vlb": out4[1], f"{prefix}/loss": out4[2]}
+            return self._loss_terms(per_sample, t, prefix)   # per-timestep logvar: B-element tensor arithmetic
         x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
         model_output = self.apply_model(x_noisy, t, cond)
         loss_simple = self.get_loss(model_output, noise, mean=False).mean(dim=self.loss_mean_dim)
-        logvar_t = self.logvar.to(t.device)[t]
-        loss = self.l_simple_weight * (loss_simple / torch.exp(logvar_t) + logvar_t).mean()
+        return self._loss_terms(loss_simple, t, prefix)
+
+    def _loss_terms(self, loss_simple, t, prefix):
+        """latent_diffusion.py:534-549 from the per-sample loss: logvar weighting, vlb term, the logged dict."""
+        logvar_t = self.logvar.detach().to(t.device)[t]
+        loss = loss_simple / torch.exp(logvar_t) + logvar_t
+        loss_dict = {f"{prefix}/loss_simple": loss_simple.mean()}
+        if self.learn_logvar:
+            loss_dict[f"{prefix}/loss_gamma"] = loss.mean()
+            loss_dict["logvar"] = self.logvar.data.mean()
+        loss = self.l_simple_weight * loss.mean()
         loss_vlb = (self.lvlb_weights.to(t.device)[t] * loss_simple).mean()
+        loss_dict[f"{prefix}/loss_vlb"] = loss_vlb
         loss = loss + self.original_elbo_weight * loss_vlb
-        return loss, {f"{prefix}/loss_simple": loss_simple.mean(), f"{prefix}/loss_vlb": loss_vlb, f"{prefix}/loss": loss}
+        loss_dict[f"{prefix}/loss"] = loss
+        return loss, loss_dict
 
     @torch.no_grad()
     def forward(self, batch, verbose=False, t=None, noise=None):

@@ -112,11 +112,12 @@ def ref_vae(cfg):
 
 def ref_ldm(unet, vae, ucfg, vcfg, **kw):
     from prediff.diffusion.latent_diffusion import LatentDiffusion
+    kw.setdefault("learn_logvar", False)
     return LatentDiffusion(
         **kw,
         torch_nn_module=unet, layout="NTHWC", data_shape=(ucfg.t_out, vcfg.h, vcfg.w, 1), timesteps=1000,
         beta_schedule="linear", use_ema=False, log_every_t=100, clip_denoised=False, linear_start=1e-4,
-        linear_end=2e-2, parameterization="eps", learn_logvar=False,
+        linear_end=2e-2, parameterization="eps",
         latent_shape=(ucfg.t_out, ucfg.h, ucfg.w, ucfg.c), first_stage_model=vae,
         cond_stage_model="__is_first_stage__", scale_factor=1.0).eval()
 
@@ -386,6 +387,12 @@ def gen_helpers():
 
 LOSS_CASES = [("l2", dict(loss_type="l2")),
               ("l1w", dict(loss_type="l1", original_elbo_weight=0.3, l_simple_weight=0.7, logvar_init=0.5))]
+# learn_logvar = True as in the shipped config (cfg.yaml:95), with per-timestep values standing in for a trained logvar
+LEARNED_LOGVAR_CASE = ("learned", dict(loss_type="l2", learn_logvar=True, original_elbo_weight=0.1))
+
+
+def learned_logvar_values():
+    return torch.linspace(-0.5, 0.5, 1000)
 
 
 @torch.no_grad()
@@ -401,9 +408,11 @@ def gen_losses():
     noise = inp(883, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
     t = torch.tensor([0, 431, 999], dtype=torch.long)
     out = {"t": t}
-    for tag, kw in LOSS_CASES:
+    for tag, kw in LOSS_CASES + [LEARNED_LOGVAR_CASE]:
         ldm = ref_ldm(unet, ref_vae(vcfg), ucfg, vcfg, **kw)   # .eval() -> 'val/' prefix; a fresh VAE per instance
         # (the reference replaces first_stage_model.train with an unbound function, so a VAE cannot be reused)
+        if kw.get("learn_logvar"):
+            ldm.logvar.data.copy_(learned_logvar_values())
         loss, d = ldm.p_losses(z, zc, t, noise=noise)
         out[f"{tag}_loss"] = loss
         for k, v in d.items():

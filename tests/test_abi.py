@@ -158,7 +158,7 @@ def test_pattern_and_loss_arguments_fail_loudly():
         def forward(self, x, t, c):
             return x
 
-    for kw in (dict(loss_type="huber"), dict(learn_logvar=True), dict(parameterization="x0")):
+    for kw in (dict(loss_type="huber"), dict(parameterization="x0"), dict(clip_denoised=True)):
         with pytest.raises(NotImplementedError):
             LatentDiffusion(torch_nn_module=Eps(), **kw)
     ld = LatentDiffusion(torch_nn_module=Eps(), loss_type="l1", original_elbo_weight=0.5)

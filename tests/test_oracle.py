@@ -197,3 +197,34 @@ def test_forward_loss_vs_reference(tiny_unet_sd):
             want = float(g[f"{tag}_val_{k}"])
             assert abs(float(r[k]) - want) <= 2e-5 * abs(want), (tag, k, float(r[k]), want)
         assert abs(float(r["loss"]) - float(g[f"{tag}_loss"])) <= 2e-5 * abs(float(g[f"{tag}_loss"]))
+
+
+def test_mirror_loss_terms_vs_reference_incl_learned_logvar(tiny_unet_sd):
+    """LatentDiffusion.p_losses of the mirror (tensor path, with the oracle UNet standing in as the denoiser module on
+    CPU) vs the unmodified reference: fixed logvar, weighted l1 + vlb, and learn_logvar = True as in the shipped
+    config (cfg.yaml:95) with per-timestep logvar values - dict keys, order and values."""
+    from prediff_b200.diffusion import LatentDiffusion
+    from tests.golden.gen_golden import LEARNED_LOGVAR_CASE, LOSS_CASES, learned_logvar_values
+    g = gold("losses")
+    cfg = Wt.TINY_UNET
+
+    class OracleEps(torch.nn.Module):
+        def forward(self, x, t, cond):
+            return O.unet_forward(tiny_unet_sd, cfg, x, t, cond)
+
+    z, zc, noise = inp(881, 3, cfg.t_out, cfg.h, cfg.w, cfg.c), inp(882, 3, cfg.t_in, cfg.h, cfg.w, cfg.c), \
+        inp(883, 3, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    t = torch.as_tensor(g["t"])
+    for tag, kw in LOSS_CASES + [LEARNED_LOGVAR_CASE]:
+        ld = LatentDiffusion(torch_nn_module=OracleEps(), **kw).eval()
+        if kw.get("learn_logvar"):
+            assert isinstance(ld.logvar, torch.nn.Parameter) and "logvar" in ld.state_dict()
+            ld.logvar.data.copy_(learned_logvar_values())
+        loss, d = ld.p_losses(z, zc, t, noise=noise)
+        want_keys = ["val/loss_simple"] + (["val/loss_gamma", "logvar"] if kw.get("learn_logvar") else []) + \
+            ["val/loss_vlb", "val/loss"]
+        assert list(d) == want_keys
+        for k, v in d.items():
+            want = float(g[f"{tag}_{k.replace('/', '_')}"])
+            assert abs(float(v) - want) <= 2e-5 * max(abs(want), 1e-3), (tag, k, float(v), want)
+        assert abs(float(loss) - float(g[f"{tag}_loss"])) <= 2e-5 * abs(float(g[f"{tag}_loss"]))
