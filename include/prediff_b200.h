@@ -69,7 +69,18 @@ int pd_unet_num_weights(const pd_unet* m);
 int pd_unet_weight_info(const pd_unet* m, int i, const char** name, int64_t shape[5]);
 /* Copies one fp32 tensor (host or device pointer, contiguous, reference layout) into the model. */
 int pd_unet_load_weight(pd_unet* m, const char* name, const float* data, const int64_t* shape, int ndim);
-/* Repacks all weights into kernel layouts (bf16, K-major, tap-major convs). Fails if any weight is missing. */
+/* Operand precision of the model's tensor-core GEMMs / convolutions (accumulation, residual stream, normalisation
+ * statistics, softmax and the sampler update are fp32 in both):
+ *   PD_PRECISION_BF16 (default): bf16 operands, tcgen05.mma kind::f16 - rel-RMS ~6e-3 per UNet step vs the fp32 reference;
+ *   PD_PRECISION_TF32: fp32 storage rounded to tf32, tcgen05.mma kind::tf32 (half the bf16 rate) and an fp32 attention
+ *     core - the reference's own GPU arithmetic (torch.set_float32_matmul_precision("high"): scripts/prediff/sevirlr/
+ *     cfg.yaml:32, train_sevirlr_prediff.py:1143), rel-RMS <= 2e-3 per step and after the 50-step loop.
+ * Call before pd_unet_finalize (a change un-finalizes the model). TF32 is built for the axial pattern (shipped config). */
+#define PD_PRECISION_BF16 0
+#define PD_PRECISION_TF32 1
+int pd_unet_set_precision(pd_unet* m, int precision);
+/* Repacks all weights into kernel layouts (bf16 or tf32-rounded fp32, K-major, tap-major convs). Fails if any weight is
+ * missing. */
 int pd_unet_finalize(pd_unet* m);
 /* forward(x, t, cond) -> eps   (cuboid_transformer_unet.py:406-493)
  *   x [B][t_out][h][w][c], t [B] int64, cond [B][t_in][h][w][c]  ->  out [B][t_out][h][w][c]; all device ptrs. */
@@ -85,6 +96,9 @@ int pd_unet_kernels_per_forward(pd_unet* m, int batch, int* n);
 /* Per-launch trace: one eager forward with a %globaltimer stamp kernel after every plan step. ns_dev[i] (device u64,
  * max_slots entries) = stamp after step i-1 (ns_dev[0] = start); labels (host, optional) receives one '\n'-terminated
  * label per step ("L0.stack.ffn1", "L1.res.conv2", ...). Returns the number of steps (>= 0) or a PD_ERR_* code. */
+/* Algorithmic FLOPs (2 x MACs) of every plan step, in pd_unet_trace_forward's step order (0 for non-GEMM steps); returns
+ * the number of steps or a PD_ERR_* code. Lets bench.py turn the per-launch trace into per-kernel roofline fractions. */
+int pd_unet_step_flops(pd_unet* m, int batch, double* flops, int max_slots);
 int pd_unet_trace_forward(pd_unet* m, const float* x, const int64_t* t, const float* cond, float* out, int batch,
                           void* stream, unsigned long long* ns_dev, int max_slots, char* labels, int labels_bytes);
 
@@ -159,7 +173,9 @@ int pd_sampler_get_buffer(const pd_sampler* s, const char* name, float* out);
  *   cond  [B][t_in][h][w][c]
  *   noise NULL (DDIM eta=0) or [n_steps][B*t_out*h*w*c] pre-generated N(0,1) (step k uses slice k)
  *   mode PD_MODE_*; n_steps: DDPM = number of ancestral steps (t = n_steps-1..0), DDIM = number of DDIM steps.
- * The loop is captured into a CUDA graph on first use for a given (unet, batch) and replayed. */
+ * The loop state lives in buffers owned by the sampler (z / cond are copied in, z is copied back), so the CUDA graph
+ * captured on first use for a given (unet weights generation, batch) is replayed whatever the caller's addresses are;
+ * loops of up to 64 steps are ONE graph launch, longer ones replay a one-iteration graph. */
 int pd_sample_loop(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int mode,
                    int n_steps, float eta, void* stream);
 /* Same, restricted to the executed steps [k_begin, k_end) of the n_steps-step schedule (k = 0 is the noisiest step);
@@ -187,6 +203,9 @@ int pd_diffusion_losses(pd_sampler* s, pd_unet* unet, const float* x_start, cons
                         const float* noise, int batch, int loss_l1, float logvar, float l_simple_weight,
                         float original_elbo_weight, float* per_sample, float* out4, void* stream);
 int pd_sampler_sub_batches(const pd_sampler* s, int batch);
+/* clip_denoised of p_mean_variance (latent_diffusion.py:580-581): when on, every DDPM step clamps its z_0 estimate to
+ * [-1, 1] before the posterior mean (inside the fused update kernel). Off by default, as in the shipped config. */
+int pd_sampler_set_clip_denoised(pd_sampler* s, int on);
 /* One reference p_sample step at integer timestep t (all batch rows share t): z <- p_sample(z, cond, t). */
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,
                         void* stream);
@@ -221,6 +240,22 @@ int pd_sevir_windows(const unsigned char* events_u8, int event_base, int n_event
 int pd_op_conv_gemm(const void* A_bf16, const void* Wt_bf16, int samples, int D, int H, int W, int C, int kt, int kh,
                     int kw, int N, const float* bias, const float* rowvec, const float* residual, float* out_f32,
                     void* out_bf16, int act, int block_n, void* stream);
+/* The same kernels with tf32 operands (PD_PRECISION_TF32): A fp32 [samples][D][H][W][C] (C % 32 == 0), Wt fp32
+ * [N][kt*kh*kw*C], fp32 output only; round_out = 1 stores the output rounded to tf32 (it feeds another tf32 GEMM);
+ * streamk_ctas_per_sample > 0 runs the stream-K schedule (N % 256 == 0, no activation). The tensor core reads the top 19
+ * bits of every operand word; pd_op_pack_tf32 / the producer kernels round to nearest beforehand. */
+int pd_op_conv_gemm_tf32(const float* A, const float* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
+                         int N, const float* bias, const float* rowvec, const float* residual, float* out_f32, int act,
+                         int round_out, int block_n, int streamk_ctas_per_sample, void* stream);
+/* Weight repack to tf32-rounded fp32: taps == 0: Linear fp32 [Co][Ci] -> [Co][Cipad]; taps > 0: conv fp32
+ * [Co][Ci][taps] -> [Co][taps][Cipad]. */
+int pd_op_pack_tf32(const float* w, float* out, int Co, int Ci, int taps, int Cipad, void* stream);
+/* Axial attention core in fp32 (qkv fp32 [B][T][H][W][3C] -> out fp32 [B][T][H][W][C], tf32-rounded). */
+int pd_op_axial_attention_f32(const float* qkv, const float* bias_table, float* out, int B, int T, int H, int W, int C,
+                              int heads, int axis, void* stream);
+/* kind 0: GroupNorm(+SiLU) x fp32 [S][R][C] -> y fp32 (tf32-rounded); kind 1: LayerNorm over C of the S*R rows. */
+int pd_op_norm_tf32(int kind, const float* x, const float* gamma, const float* beta, float* y, int S, int R, int C, int G,
+                    float eps, int silu, void* stream);
 /* x[M][256] += A[M][K] Wt[256][K]^T + bias, and ln_out[M][256] (bf16) = LayerNorm(x row, eps 1e-5) * gamma + beta
  * from the same epilogue (the fusion the UNet uses for proj / ffn_2 / conv2 -> next pre-norm at width 256). */
 int pd_op_linear_residual_ln(const void* A_bf16, const void* Wt_bf16, int M, int K, const float* bias, float* x_inout,

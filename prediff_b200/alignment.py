@@ -75,6 +75,7 @@ class NoisyCuboidTransformerEncoder(nn.Module):
         build_param_tree(self, ka_param_spec(self.cfg), bufs)
         self._handle = None
         self._dirty = True
+        self.register_load_state_dict_post_hook(type(self)._mark_dirty)
 
     # ---- C++ handle management ------------------------------------------------------------------------------
     def _ensure_handle(self):
@@ -98,10 +99,11 @@ class NoisyCuboidTransformerEncoder(nn.Module):
         L.check(lib.pd_ka_finalize(h))
         self._dirty = False
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        r = super().load_state_dict(state_dict, strict=strict, **kw)
+    def _mark_dirty(self, *unused):
+        """Parameters changed: the packed CUDA copies are stale. Registered as a load_state_dict post-hook, which torch
+        runs for this module also when a PARENT's load_state_dict recurses through it (nn.Module.load_state_dict never
+        calls a child's overridden load_state_dict)."""
         self._dirty = True
-        return r
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)

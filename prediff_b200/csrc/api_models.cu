@@ -51,6 +51,10 @@ int pd_unet_load_weight(pd_unet* m, const char* name, const float* data, const i
     m->impl.finalized = false;
     return m->impl.ws.load(name, data, shape, ndim);
 }
+int pd_unet_set_precision(pd_unet* m, int precision) {
+    PD_CHECK(m, PD_ERR_ARG, "pd_unet_set_precision: null model");
+    return m->impl.set_precision(precision);
+}
 int pd_unet_finalize(pd_unet* m) {
     PD_CHECK(m, PD_ERR_ARG, "pd_unet_finalize: null model");
     return m->impl.finalize();
@@ -83,6 +87,14 @@ int pd_unet_trace_forward(pd_unet* m, const float* x, const int64_t* t, const fl
     }
     PD_TRY(m->impl.forward(x, t, nullptr, cond, out, batch, S(stream), nullptr, 0, 0, ns_dev));
     return (int)lab.size();
+}
+int pd_unet_step_flops(pd_unet* m, int batch, double* flops, int max_slots) {
+    PD_CHECK(m && flops, PD_ERR_ARG, "pd_unet_step_flops: null argument");
+    std::vector<double> f;
+    PD_TRY(m->impl.plan_flops(batch, &f));
+    PD_CHECK((int)f.size() <= max_slots, PD_ERR_ARG, "pd_unet_step_flops: need %d slots", (int)f.size());
+    for (size_t i = 0; i < f.size(); ++i) flops[i] = f[i];
+    return (int)f.size();
 }
 int pd_unet_kernels_per_forward(pd_unet* m, int batch, int* n) {
     PD_CHECK(m && n, PD_ERR_ARG, "pd_unet_kernels_per_forward: null argument");
@@ -128,6 +140,11 @@ int pd_diffusion_losses(pd_sampler* s, pd_unet* unet, const float* x_start, cons
     PD_CHECK(unet->impl.finalized, PD_ERR_WEIGHT, "pd_diffusion_losses: pd_unet_finalize has not been called");
     return s->impl.losses(&unet->impl, x_start, cond, t, noise, batch, loss_l1, logvar, l_simple_weight,
                           original_elbo_weight, per_sample, out4, S(stream));
+}
+int pd_sampler_set_clip_denoised(pd_sampler* s, int on) {
+    PD_CHECK(s, PD_ERR_ARG, "pd_sampler_set_clip_denoised: null sampler");
+    s->impl.set_clip_denoised(on != 0);
+    return PD_OK;
 }
 int pd_sampler_sub_batches(const pd_sampler* s, int batch) { return s ? s->impl.n_sub_for(batch) : 0; }
 int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* cond, const float* noise, int batch, int t,

@@ -42,6 +42,72 @@ int pd_op_conv_gemm(const void* A, const void* Wt, int samples, int D, int H, in
     return rc;
 }
 
+// ---- TF32-class precision (PD_PRECISION_TF32): the same launchers with fp32 operands -----------------------------------
+int pd_op_conv_gemm_tf32(const float* A, const float* Wt, int samples, int D, int H, int W, int C, int kt, int kh, int kw,
+                         int N, const float* bias, const float* rowvec, const float* residual, float* out_f32, int act,
+                         int round_out, int block_n, int streamk_ctas_per_sample, void* stream) {
+    PD_TRY(gemm_init());
+    PD_CHECK(kt * kh * kw <= kMaxTaps, PD_ERR_SHAPE, "pd_op_conv_gemm_tf32: window too large");
+    GemmGeom g = GemmGeom::conv(samples, D, H, W, C, kt, kh, kw);
+    g.tf32 = 1;
+    GemmEpilogue e;
+    e.bias = bias; e.rowvec = rowvec; e.residual = residual; e.out_f32 = out_f32; e.act = act; e.round_tf32 = round_out;
+    if (streamk_ctas_per_sample > 0) {
+        GemmOp op;
+        PD_TRY(gemm_make(&op, A, g, Wt, N, e, 256));
+        std::vector<SkSeg> segs;
+        int n_slots = 0, n_flags = 0;
+        PD_TRY(gemm_streamk_schedule(op, streamk_ctas_per_sample, &segs, &n_slots, &n_flags));
+        SkSeg* dsegs = nullptr;
+        float* partials = nullptr;
+        int* flags = nullptr;
+        PD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dsegs), segs.size() * sizeof(SkSeg)));
+        PD_CUDA(cudaMalloc(reinterpret_cast<void**>(&partials), (size_t)(n_slots + 1) * kGemmBlockM * 256 * sizeof(float)));
+        PD_CUDA(cudaMalloc(reinterpret_cast<void**>(&flags), (size_t)n_flags * sizeof(int)));
+        PD_CUDA(cudaMemcpy(dsegs, segs.data(), segs.size() * sizeof(SkSeg), cudaMemcpyHostToDevice));
+        PD_CUDA(cudaMemset(flags, 0, (size_t)n_flags * sizeof(int)));
+        int rc = gemm_streamk_attach(&op, dsegs, (int)segs.size() / 2, partials, flags);
+        if (rc == PD_OK) rc = gemm_launch(op, S(stream));
+        cudaStreamSynchronize(S(stream));
+        cudaFree(dsegs); cudaFree(partials); cudaFree(flags);
+        return rc;
+    }
+    int* flags = nullptr;
+    const int nflags = block_n == 0 || block_n == 256 ? gemm_split_flags_needed(g, N) : 0;
+    if (nflags > 0) {
+        PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&flags), nflags * sizeof(int), S(stream)));
+        PD_CUDA(cudaMemsetAsync(flags, 0, nflags * sizeof(int), S(stream)));
+        e.split_flags = flags;
+    }
+    GemmOp op;
+    int rc = gemm_make(&op, A, g, Wt, N, e, block_n);
+    if (rc == PD_OK) rc = gemm_launch(op, S(stream));
+    if (flags) cudaFreeAsync(flags, S(stream));
+    return rc;
+}
+int pd_op_pack_tf32(const float* w, float* out, int Co, int Ci, int taps, int Cipad, void* stream) {
+    return taps == 0 ? pack_linear(w, out, Co, Ci, Cipad, S(stream), 1) : pack_conv(w, out, Co, Ci, taps, Cipad, S(stream), 1);
+}
+int pd_op_axial_attention_f32(const float* qkv, const float* bias_table, float* out, int B, int T, int H, int W, int C,
+                              int heads, int axis, void* stream) {
+    PD_TRY(gemm_init());
+    return axial_attention(qkv, bias_table, out, B, T, H, W, C, heads, axis, S(stream), 1);
+}
+int pd_op_norm_tf32(int kind, const float* x, const float* gamma, const float* beta, float* y, int Sn, int R, int C, int G,
+                    float eps, int silu, void* stream) {
+    PD_TRY(gemm_init());
+    if (kind == 1) return layer_norm(x, gamma, beta, y, Sn * R, C, eps, S(stream), 1);
+    PD_CHECK(kind == 0, PD_ERR_ARG, "pd_op_norm_tf32: kind 0 = GroupNorm(+SiLU), 1 = LayerNorm");
+    double* sums = nullptr;
+    const size_t bytes = (size_t)Sn * G * 2 * sizeof(double);
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sums), bytes, S(stream)));
+    PD_CUDA(cudaMemsetAsync(sums, 0, bytes, S(stream)));
+    int rc = gn_stats(x, sums, Sn, R, C, G, S(stream));
+    if (rc == PD_OK) rc = gn_apply(x, sums, gamma, beta, y, Sn, R, C, G, eps, silu, S(stream), 1);
+    cudaFreeAsync(sums, S(stream));
+    return rc;
+}
+
 int pd_op_linear_residual_ln_n(const void* A, const void* Wt, int M, int K, int N, const float* bias, float* x_inout,
                                const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, void* stream) {
     PD_TRY(gemm_init());

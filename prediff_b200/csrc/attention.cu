@@ -148,6 +148,118 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
     }
 }
 
+// fp32 variant for the TF32-class precision mode (PD_PRECISION_TF32): q|k|v arrive as fp32 from the QKV GEMM and the
+// whole core (scores, bias, softmax, PV) runs in fp32 on the CUDA cores - 1.62 of the step's 653 GFLOP, so there is
+// nothing to win with tensor cores, and nothing of the reference's fp32 attention arithmetic is rounded away. The output
+// is the projection GEMM's A operand: fp32 rounded to tf32. One block per line, one warp per head; lane pair (2i, 2i+1)
+// owns query row i: the pair splits the 16 keys for the scores and the head channels for PV.
+template <int HD>
+__global__ void __launch_bounds__(128) axial_attention_f32_kernel(const float* __restrict__ qkv,
+                                                                  const float* __restrict__ bias_table,
+                                                                  float* __restrict__ out, int T, int H, int W, int C,
+                                                                  int heads, int axis) {
+    grid_dep_launch();
+    grid_dep_wait();
+    extern __shared__ __align__(16) uint8_t smem_att[];
+    float* s_qkv = reinterpret_cast<float*>(smem_att);  // [16][3C + 4]
+    const int C3 = 3 * C;
+    const int ld = C3 + 4;
+    int L, stride, base;
+    {
+        const int line = blockIdx.x;
+        if (axis == 0) {
+            L = T; stride = H * W;
+            const int hw = line % (H * W), b = line / (H * W);
+            base = b * T * H * W + hw;
+        } else if (axis == 1) {
+            L = H; stride = W;
+            const int w = line % W, bt = line / W;
+            base = bt * H * W + w;
+        } else {
+            L = W; stride = 1;
+            base = line * W;
+        }
+    }
+    {
+        const int vec_per_row = C3 / 4;
+        const int total = kMaxLine * vec_per_row;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int r = i / vec_per_row, v = i - r * vec_per_row;
+            float* dst = s_qkv + (size_t)r * ld + v * 4;
+            if (r < L) cp_async16(dst, qkv + (size_t)(base + r * stride) * C3 + v * 4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = lane >> 1, jh = lane & 1;
+    const float scale = rsqrtf((float)HD);
+    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
+        const float* sq = s_qkv + (size_t)i * ld + h * HD;
+        const float* sk = s_qkv + C + h * HD + (size_t)(jh * 8) * ld;
+        const float* sv = s_qkv + 2 * C + h * HD + jh * (HD / 2);
+        float sc[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) sc[jj] = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < HD; d += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(sq + d);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float4 k = *reinterpret_cast<const float4*>(sk + (size_t)jj * ld + d);
+                sc[jj] = fmaf(q.x, k.x, fmaf(q.y, k.y, fmaf(q.z, k.z, fmaf(q.w, k.w, sc[jj]))));
+            }
+        }
+        // reference order (cuboid_transformer.py:849-861): q * scale, then q k^T, + bias, softmax
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = jh * 8 + jj;
+            if (j < L && i < L) sc[jj] = sc[jj] * scale + __ldg(bias_table + (i - j + L - 1) * heads + h);
+            else sc[jj] = -INFINITY;
+            mx = fmaxf(mx, sc[jj]);
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        if (mx == -INFINITY) mx = 0.f;
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            sc[jj] = expf(sc[jj] - mx);
+            sum += sc[jj];
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        float p[16];   // the full probability row of query i, key order
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const float mine = sc[jj] * inv;
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            p[jj] = jh ? other : mine;
+            p[8 + jj] = jh ? mine : other;
+        }
+        float4 acc[HD / 8];
+#pragma unroll
+        for (int dd = 0; dd < HD / 8; ++dd) acc[dd] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float pj = p[j];
+#pragma unroll
+            for (int dd = 0; dd < HD / 8; ++dd) {
+                const float4 v = *reinterpret_cast<const float4*>(sv + (size_t)j * ld + 4 * dd);
+                acc[dd].x = fmaf(pj, v.x, acc[dd].x); acc[dd].y = fmaf(pj, v.y, acc[dd].y);
+                acc[dd].z = fmaf(pj, v.z, acc[dd].z); acc[dd].w = fmaf(pj, v.w, acc[dd].w);
+            }
+        }
+        if (i < L) {
+            float4* o = reinterpret_cast<float4*>(out + (size_t)(base + i * stride) * C + h * HD + jh * (HD / 2));
+#pragma unroll
+            for (int dd = 0; dd < HD / 8; ++dd)
+                o[dd] = make_float4(tf32_rna(acc[dd].x), tf32_rna(acc[dd].y), tf32_rna(acc[dd].z), tf32_rna(acc[dd].w));
+        }
+    }
+}
+
 // ---- general cuboid attention ---------------------------------------------------------------------------------
 // Any cuboid size / strategy ('l' local, 'd' dilated) / shifted window / end padding of CuboidSelfAttentionLayer
 // (cuboid_transformer.py:812-966). The reference pads, rolls and reorders the activations into
@@ -430,8 +542,8 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
 
 }  // namespace
 
-int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int T, int H, int W, int C, int heads,
-                    int axis, cudaStream_t st) {
+int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int B, int T, int H, int W, int C, int heads,
+                    int axis, cudaStream_t st, int f32) {
     PD_CHECK(axis >= 0 && axis <= 2, PD_ERR_ARG, "axial_attention: axis %d", axis);
     const int L = axis == 0 ? T : (axis == 1 ? H : W);
     PD_CHECK(L >= 1 && L <= kMaxLine, PD_ERR_SHAPE,
@@ -439,8 +551,36 @@ int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, 
     PD_CHECK(C % heads == 0 && C % 8 == 0, PD_ERR_SHAPE, "axial_attention: C=%d heads=%d", C, heads);
     const int hd = C / heads;
     const int lines = B * T * H * W / L;
-    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16);
     const int threads = heads * 32 > 128 ? 128 : heads * 32;
+    if (f32) {
+        const float* qkv = static_cast<const float*>(qkv_v);
+        float* out = static_cast<float*>(out_v);
+        const size_t smem = (size_t)kMaxLine * (3 * C + 4) * sizeof(float);
+        PD_CHECK(smem <= 200 * 1024, PD_ERR_SHAPE, "axial_attention (fp32): line of %zu bytes does not fit in smem", smem);
+#define PD_LAUNCH_AXF(HDV)                                                                                              \
+    do {                                                                                                                \
+        static bool attr_set = false;                                                                                   \
+        if (!attr_set) {                                                                                                \
+            PD_CUDA(cudaFuncSetAttribute(axial_attention_f32_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         200 * 1024));                                                                  \
+            attr_set = true;                                                                                            \
+        }                                                                                                               \
+        PD_LAUNCH((axial_attention_f32_kernel<HDV>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, axis); \
+    } while (0)
+        switch (hd) {
+            case 16: PD_LAUNCH_AXF(16); break;
+            case 32: PD_LAUNCH_AXF(32); break;
+            case 64: PD_LAUNCH_AXF(64); break;
+            case 128: PD_LAUNCH_AXF(128); break;
+            default: set_error("axial_attention: unsupported head dim %d", hd); return PD_ERR_SHAPE;
+        }
+#undef PD_LAUNCH_AXF
+        PD_LAUNCH_CHECK();
+        return PD_OK;
+    }
+    const bf16* qkv = static_cast<const bf16*>(qkv_v);
+    bf16* out = static_cast<bf16*>(out_v);
+    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16);
 #define PD_LAUNCH_AX(HDV)                                                                                            \
     do {                                                                                                             \
         static bool attr_set = false;                                                                                \

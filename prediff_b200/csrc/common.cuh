@@ -132,6 +132,31 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(0.5f, x, fmaf(-h, e, h));
 }
 
+// ---- operand precision ------------------------------------------------------------------------------------------
+// The tensor-core GEMMs take bf16 operands (default) or tf32 operands (fp32 containers; `precision` = PD_PRECISION_TF32:
+// the reference's own GPU arithmetic, cfg.yaml:32 float32_matmul_precision "high"). Every producer of a GEMM operand
+// (norm / activation / attention / cast kernels, operand-producing GEMM epilogues, the weight repack) stores either
+// bf16, or fp32 rounded to the nearest tf32 - so the tensor core's truncation of the low 13 mantissa bits is exact
+// instead of a one-sided error.
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// Stores 4 consecutive operand elements at element index 4 * i4 of y: bf16 (8 bytes) or tf32-rounded fp32 (16 bytes).
+template <bool F32>
+__device__ __forceinline__ void store_operand4(void* y, size_t i4, float a, float b, float c, float d) {
+    if constexpr (F32) {
+        reinterpret_cast<float4*>(y)[i4] = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
+    } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(y)[i4] = pk;
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

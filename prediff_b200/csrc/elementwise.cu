@@ -12,9 +12,10 @@ inline int ew_blocks(int64_t work_items) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+template <bool F32>
 __global__ void __launch_bounds__(kEwThreads) unet_assemble_kernel(const float* __restrict__ x,
                                                                    const float* __restrict__ cond,
-                                                                   float* __restrict__ of, bf16* __restrict__ ob,
+                                                                   float* __restrict__ of, void* __restrict__ ob,
                                                                    int B, int Tx, int Tc, int HW, int C, int Cpad) {
     grid_dep_launch();
     grid_dep_wait();
@@ -36,12 +37,7 @@ __global__ void __launch_bounds__(kEwThreads) unet_assemble_kernel(const float* 
             v.x = t < Tc ? 1.f : 0.f;  // observed-frame indicator channel
         }
         if (of) reinterpret_cast<float4*>(of)[i] = v;
-        if (ob) {
-            uint2 pk;
-            pk.x = pack_bf16x2(v.x, v.y);
-            pk.y = pack_bf16x2(v.z, v.w);
-            reinterpret_cast<uint2*>(ob)[i] = pk;
-        }
+        if (ob) store_operand4<F32>(ob, (size_t)i, v.x, v.y, v.z, v.w);
     }
 }
 
@@ -70,7 +66,8 @@ __global__ void __launch_bounds__(kEwThreads) pos_embed_kernel(float* __restrict
     }
 }
 
-__global__ void __launch_bounds__(kEwThreads) upsample2x_kernel(const float* __restrict__ x, bf16* __restrict__ y, int F,
+template <bool F32>
+__global__ void __launch_bounds__(kEwThreads) upsample2x_kernel(const float* __restrict__ x, void* __restrict__ y, int F,
                                                                 int H, int W, int C) {
     grid_dep_launch();
     grid_dep_wait();
@@ -84,14 +81,12 @@ __global__ void __launch_bounds__(kEwThreads) upsample2x_kernel(const float* __r
         const int h = (int)(pos % H2);
         const int f = (int)(pos / H2);
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)f * H + (h >> 1)) * W + (w >> 1)) * C) + c4);
-        uint2 pk;
-        pk.x = pack_bf16x2(v.x, v.y);
-        pk.y = pack_bf16x2(v.z, v.w);
-        reinterpret_cast<uint2*>(y)[i] = pk;
+        store_operand4<F32>(y, (size_t)i, v.x, v.y, v.z, v.w);
     }
 }
 
-__global__ void __launch_bounds__(kEwThreads) cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int S,
+template <bool F32>
+__global__ void __launch_bounds__(kEwThreads) cast_bf16_kernel(const float* __restrict__ x, void* __restrict__ y, int S,
                                                                int64_t RC4, int64_t in_stride) {
     grid_dep_launch();
     grid_dep_wait();
@@ -99,10 +94,7 @@ __global__ void __launch_bounds__(kEwThreads) cast_bf16_kernel(const float* __re
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = i / RC4, e = i - s * RC4;
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + s * in_stride) + e);
-        uint2 pk;
-        pk.x = pack_bf16x2(v.x, v.y);
-        pk.y = pack_bf16x2(v.z, v.w);
-        reinterpret_cast<uint2*>(y)[i] = pk;
+        store_operand4<F32>(y, (size_t)i, v.x, v.y, v.z, v.w);
     }
 }
 
@@ -233,33 +225,42 @@ __global__ void __launch_bounds__(256) conv3x3_c1_out_kernel(const bf16* __restr
     }
 }
 
-__global__ void pack_linear_kernel(const float* __restrict__ w, bf16* __restrict__ out, int N, int K, int Kpad) {
+template <bool F32>
+__device__ __forceinline__ void store_operand1(void* y, int64_t i, float v) {
+    if constexpr (F32) reinterpret_cast<float*>(y)[i] = tf32_rna(v);
+    else reinterpret_cast<bf16*>(y)[i] = __float2bfloat16_rn(v);
+}
+
+template <bool F32>
+__global__ void pack_linear_kernel(const float* __restrict__ w, void* __restrict__ out, int N, int K, int Kpad) {
     const int64_t total = (int64_t)N * Kpad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % Kpad);
         const int64_t n = i / Kpad;
-        out[i] = __float2bfloat16_rn(k < K ? w[n * K + k] : 0.f);
+        store_operand1<F32>(out, i, k < K ? w[n * K + k] : 0.f);
     }
 }
 
-__global__ void pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci, int taps,
+template <bool F32>
+__global__ void pack_conv_kernel(const float* __restrict__ w, void* __restrict__ out, int Co, int Ci, int taps,
                                  int Cipad) {
     const int64_t total = (int64_t)Co * taps * Cipad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int ci = (int)(i % Cipad);
         const int tap = (int)((i / Cipad) % taps);
         const int64_t co = i / ((int64_t)Cipad * taps);
-        out[i] = __float2bfloat16_rn(ci < Ci ? w[(co * Ci + ci) * taps + tap] : 0.f);
+        store_operand1<F32>(out, i, ci < Ci ? w[(co * Ci + ci) * taps + tap] : 0.f);
     }
 }
 
 }  // namespace
 
-int unet_assemble(const float* x, const float* cond, float* out_f32, bf16* out_bf16, int B, int Tx, int Tc, int HW,
-                  int C, int Cpad, cudaStream_t st) {
+int unet_assemble(const float* x, const float* cond, float* out_f32, void* out_bf16, int B, int Tx, int Tc, int HW,
+                  int C, int Cpad, cudaStream_t st, int op_f32) {
     PD_CHECK(C % 4 == 0 && Cpad % 4 == 0 && Cpad > C, PD_ERR_SHAPE, "unet_assemble: C=%d Cpad=%d", C, Cpad);
     const int64_t total = (int64_t)B * (Tx + Tc) * HW * (Cpad / 4);
-    PD_LAUNCH(unet_assemble_kernel, ew_blocks(total), kEwThreads, 0, st, x, cond, out_f32, out_bf16, B, Tx, Tc, HW, C, Cpad);
+    if (op_f32) PD_LAUNCH(unet_assemble_kernel<true>, ew_blocks(total), kEwThreads, 0, st, x, cond, out_f32, out_bf16, B, Tx, Tc, HW, C, Cpad);
+    else PD_LAUNCH(unet_assemble_kernel<false>, ew_blocks(total), kEwThreads, 0, st, x, cond, out_f32, out_bf16, B, Tx, Tc, HW, C, Cpad);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -273,18 +274,20 @@ int pos_embed_add(float* x, const float* Te, const float* He, const float* We, i
     return PD_OK;
 }
 
-int upsample2x_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st) {
+int upsample2x_cast(const float* x, void* y, int F, int H, int W, int C, cudaStream_t st, int y_f32) {
     PD_CHECK(C % 4 == 0, PD_ERR_SHAPE, "upsample2x_cast: C=%d", C);
     const int64_t total = (int64_t)F * 4 * H * W * (C / 4);
-    PD_LAUNCH(upsample2x_kernel, ew_blocks(total), kEwThreads, 0, st, x, y, F, H, W, C);
+    if (y_f32) PD_LAUNCH(upsample2x_kernel<true>, ew_blocks(total), kEwThreads, 0, st, x, y, F, H, W, C);
+    else PD_LAUNCH(upsample2x_kernel<false>, ew_blocks(total), kEwThreads, 0, st, x, y, F, H, W, C);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
-int cast_bf16(const float* x, bf16* y, int S, int64_t RC, int64_t in_sample_stride, cudaStream_t st) {
+int cast_bf16(const float* x, void* y, int S, int64_t RC, int64_t in_sample_stride, cudaStream_t st, int y_f32) {
     PD_CHECK(RC % 4 == 0 && in_sample_stride % 4 == 0, PD_ERR_SHAPE, "cast_bf16: sizes must be multiples of 4");
     const int64_t total = (int64_t)S * (RC / 4);
-    PD_LAUNCH(cast_bf16_kernel, ew_blocks(total), kEwThreads, 0, st, x, y, S, RC / 4, in_sample_stride);
+    if (y_f32) PD_LAUNCH(cast_bf16_kernel<true>, ew_blocks(total), kEwThreads, 0, st, x, y, S, RC / 4, in_sample_stride);
+    else PD_LAUNCH(cast_bf16_kernel<false>, ew_blocks(total), kEwThreads, 0, st, x, y, S, RC / 4, in_sample_stride);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -330,14 +333,16 @@ int conv3x3_c1_out(const bf16* x, const float* w, float bias, float* y, int F, i
     return PD_OK;
 }
 
-int pack_linear(const float* w, bf16* out, int N, int K, int Kpad, cudaStream_t st) {
-    pack_linear_kernel<<<ew_blocks((int64_t)N * Kpad), kEwThreads, 0, st>>>(w, out, N, K, Kpad);
+int pack_linear(const float* w, void* out, int N, int K, int Kpad, cudaStream_t st, int out_f32) {
+    if (out_f32) pack_linear_kernel<true><<<ew_blocks((int64_t)N * Kpad), kEwThreads, 0, st>>>(w, out, N, K, Kpad);
+    else pack_linear_kernel<false><<<ew_blocks((int64_t)N * Kpad), kEwThreads, 0, st>>>(w, out, N, K, Kpad);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
-int pack_conv(const float* w, bf16* out, int Co, int Ci, int taps, int Cipad, cudaStream_t st) {
-    pack_conv_kernel<<<ew_blocks((int64_t)Co * taps * Cipad), kEwThreads, 0, st>>>(w, out, Co, Ci, taps, Cipad);
+int pack_conv(const float* w, void* out, int Co, int Ci, int taps, int Cipad, cudaStream_t st, int out_f32) {
+    if (out_f32) pack_conv_kernel<true><<<ew_blocks((int64_t)Co * taps * Cipad), kEwThreads, 0, st>>>(w, out, Co, Ci, taps, Cipad);
+    else pack_conv_kernel<false><<<ew_blocks((int64_t)Co * taps * Cipad), kEwThreads, 0, st>>>(w, out, Co, Ci, taps, Cipad);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -110,7 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         b_pre = num_k < STAGES ? num_k : STAGES;
         for (int it = 0; it < b_pre; ++it) {
             ptx::mbar_arrive_expect_tx(&full_bar[it], C::kStageBytes);
-            ptx::tma_load_3d(smem + it * C::kStageBytes + kABytes, &tmap_b, &full_bar[it], (k_begin + it) * kGemmBlockK,
+            ptx::tma_load_3d(smem + it * C::kStageBytes + kABytes, &tmap_b, &full_bar[it], (k_begin + it) * p.kblk,
                              n0, 0);
         }
     }
@@ -147,15 +147,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
                 }
-                ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
+                ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * p.kblk, x0 + p.dx[tap], y0 + p.dy[tap],
                                  z0 + p.dz[tap], sample);
-                if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], (k_begin + it) * kGemmBlockK, n0, bz);
+                if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], (k_begin + it) * p.kblk, n0, bz);
                 if (++cb == p.cblks) { cb = 0; ++tap; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kGemmBlockM, BN);
+            const bool tf32 = p.tf32 != 0;   // 4 MMAs per 128-byte k-block either way: 16 bf16 or 8 tf32 per instruction
+            const uint32_t idesc = tf32 ? ptx::make_idesc_tf32(kGemmBlockM, BN) : ptx::make_idesc_bf16(kGemmBlockM, BN);
             for (int it = 0; it < num_k; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -168,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int k = 0; k < kGemmBlockK / 16; ++k) {
                     const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
                     const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
-                    ptx::umma_f16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    ptx::umma_ss(tf32, tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
                 }
                 ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
             }
@@ -296,6 +297,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
                         } else if (act == ACT_SILU) {
                             a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
+                        }
+                        if (p.round_out) {   // this output is the next tf32 GEMM's operand
+                            a.x = tf32_rna(a.x); a.y = tf32_rna(a.y); a.z = tf32_rna(a.z); a.w = tf32_rna(a.w);
                         }
                         float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
                         if (has_res) {
@@ -760,17 +764,21 @@ int tmap_encode_sw128(CUtensorMap* m, bool is_bf16, int rank, const void* ptr, c
 
 int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split) {
     const int out_D = g.out_D ? g.out_D : g.D;
-    const int num_k = g.ntaps * (g.C / kGemmBlockK);
+    const int num_k = g.ntaps * (g.C / g.kblk());
     if ((num_k < 128 && force_split != 2) || N % 256 != 0) return 0;
     return ceil_div(out_D * g.H * g.W, kGemmBlockM) * g.samples * (N / 256);
 }
 
-int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int N, const GemmEpilogue& e,
+int gemm_make(GemmOp* op, const void* A, const GemmGeom& g, const void* Wt, int N, const GemmEpilogue& e,
               int force_block_n) {
     PD_TRY(gemm_init());
     PD_CHECK(A && Wt, PD_ERR_ARG, "gemm_make: null operand");
-    PD_CHECK(g.C > 0 && g.C % kGemmBlockK == 0, PD_ERR_SHAPE, "gemm: channels per tap (%d) must be a multiple of 64",
-             g.C);
+    const int kblk = g.kblk();
+    const int esz = g.tf32 ? 4 : 2;   // operand element size
+    const CUtensorMapDataType op_dtype = g.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    PD_CHECK(g.C > 0 && g.C % kblk == 0, PD_ERR_SHAPE, "gemm: channels per tap (%d) must be a multiple of %d", g.C, kblk);
+    PD_CHECK(!g.tf32 || (!e.out_bf16 && !e.ln_out), PD_ERR_ARG,
+             "gemm: tf32 operands go with fp32 outputs only (no bf16 output, no fused bf16 LayerNorm output)");
     PD_CHECK(N > 0 && N % 32 == 0, PD_ERR_SHAPE, "gemm: N (%d) must be a multiple of 32", N);
     PD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, PD_ERR_SHAPE, "gemm: ntaps %d out of range", g.ntaps);
     PD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0, PD_ERR_ARG,
@@ -799,15 +807,15 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     const int64_t sN = g.sN ? g.sN : sD * g.D;
     {
         cuuint64_t dims[5] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)g.samples};
-        cuuint64_t strides[4] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sD * 2, (cuuint64_t)sN * 2};
-        cuuint32_t box[5] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+        cuuint64_t strides[4] = {(cuuint64_t)sW * esz, (cuuint64_t)sH * esz, (cuuint64_t)sD * esz, (cuuint64_t)sN * esz};
+        cuuint32_t box[5] = {(cuuint32_t)kblk, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
         cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        CUresult r = g_encode(&op->tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<bf16*>(A), dims, strides, box,
+        CUresult r = g_encode(&op->tmap_a, op_dtype, 5, const_cast<void*>(A), dims, strides, box,
                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA,
                  "cuTensorMapEncodeTiled(A) failed: %d (dims %d,%d,%d,%d,%d box %d,%d,%d,%d)", (int)r, g.C, g.W, g.H, g.D,
-                 g.samples, kGemmBlockK, bw, bh, bd);
+                 g.samples, kblk, bw, bh, bd);
     }
 
     // ---- tile shape -------------------------------------------------------------------------------------------
@@ -827,7 +835,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         if (const char* s = getenv("PD_GEMM_BN")) bn = atoi(s);
         if (bn && N % bn != 0) bn = 0;
     }
-    const int num_k = g.ntaps * (g.C / kGemmBlockK);
+    const int num_k = g.ntaps * (g.C / kblk);
     if (!bn && e.split_flags && gemm_split_flags_needed(g, N, e.force_split) > 0 && e.out_f32 && e.act == ACT_NONE)
         bn = 256;
     if (!bn && e.gn_sums && N % 256 == 0) bn = 256;   // the statistics epilogue exists for the 256-wide, 4-stage kernel
@@ -854,10 +862,10 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
         const int nb = g.b_sample_stride ? g.samples : 1;
         const int64_t bs = g.b_sample_stride ? g.b_sample_stride : ldb * N;
         cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)N, (cuuint64_t)nb};
-        cuuint64_t strides[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)bs * 2};
-        cuuint32_t box[3] = {(cuuint32_t)kGemmBlockK, (cuuint32_t)bn, 1};
+        cuuint64_t strides[2] = {(cuuint64_t)ldb * esz, (cuuint64_t)bs * esz};
+        cuuint32_t box[3] = {(cuuint32_t)kblk, (cuuint32_t)bn, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = g_encode(&op->tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(Wt), dims, strides, box,
+        CUresult r = g_encode(&op->tmap_b, op_dtype, 3, const_cast<void*>(Wt), dims, strides, box,
                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
@@ -880,7 +888,10 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.W = g.W;
     p.HW = g.H * g.W;
     p.ntaps = g.ntaps;
-    p.cblks = g.C / kGemmBlockK;
+    p.cblks = g.C / kblk;
+    p.tf32 = g.tf32 ? 1 : 0;
+    p.kblk = kblk;
+    p.round_out = e.round_tf32;
     p.b_batched = g.b_sample_stride ? 1 : 0;
     memcpy(p.dz, g.dz, sizeof(p.dz));
     memcpy(p.dy, g.dy, sizeof(p.dy));
@@ -922,7 +933,7 @@ int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int 
     p.split_flags = e.split_flags;
     if (!g.b_sample_stride && (g.ldb == 0 || g.ldb == (int64_t)g.ntaps * g.C)) {   // a plain weight matrix [N][K]
         op->own_w.p[0] = reinterpret_cast<const uint8_t*>(Wt);
-        op->own_w.n[0] = (uint32_t)((size_t)N * g.ntaps * g.C * 2);
+        op->own_w.n[0] = (uint32_t)((size_t)N * g.ntaps * g.C * esz);
     }
     p.gn_sums = e.gn_sums;
     p.gn_groups = e.gn_groups;

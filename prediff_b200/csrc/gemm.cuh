@@ -14,7 +14,8 @@
 namespace pd {
 
 constexpr int kGemmBlockM = 128;
-constexpr int kGemmBlockK = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int kGemmBlockK = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row (tf32 operands: 32 fp32 = the same 128 bytes)
+constexpr int kGemmBlockKTf32 = 32;
 constexpr int kMaxTaps = 27;
 
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
@@ -31,6 +32,10 @@ struct GemmGeom {
     // B operand: row stride in elements (0 -> ntaps*C) and, for a per-sample B (attention: K or V^T of that
     // sample instead of shared weights), the element stride between samples (0 -> shared)
     int64_t ldb = 0, b_sample_stride = 0;
+    // Operand precision: 0 = bf16 operands (A and Wt are bf16), 1 = tf32 (A and Wt are fp32 holding tf32-rounded values;
+    // tcgen05.mma kind::tf32 at half the bf16 rate, K block = 32 elements). C must be a multiple of 64 / 32.
+    int tf32 = 0;
+    int kblk() const { return tf32 ? kGemmBlockKTf32 : kGemmBlockK; }
 
     static GemmGeom linear(int M, int K) {
         GemmGeom g;
@@ -79,6 +84,7 @@ struct GemmEpilogue {
     bf16* out_bf16 = nullptr;         // [M][ldo]   (needs N % 64 == 0, no residual)
     int ldo = 0;                      // row stride of residual/out in elements (0 -> N)
     int act = ACT_NONE;               // applied after bias/rowvec, before the residual add
+    int round_tf32 = 0;               // fp32 output that feeds a tf32 GEMM: store round-to-nearest tf32 values
     // Optional fused LayerNorm of the OUTPUT rows (needs out_f32; N == 256: one CTA owns whole rows; N == 512: the two
     // CTAs of a row form a thread-block cluster and exchange their row sums through distributed shared memory):
     // ln_out[M][N] bf16 = LN(out row) * ln_gamma + ln_beta - the next layer's pre-norm, saving its kernel + a pass.
@@ -102,6 +108,8 @@ struct GemmKernelParams {
     int rows_per_sample, tiles_per_sample, samples;
     int N, H, W, HW;
     int ntaps, cblks, b_batched;
+    int tf32, kblk;            // operand precision (GemmGeom::tf32) and elements per 128-byte k-block (64 bf16 / 32 tf32)
+    int round_out;             // GemmEpilogue::round_tf32
     int8_t dz[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps];
     const float* bias;
     const float* rowvec;
@@ -145,8 +153,9 @@ struct GemmOp {
     WRange own_w = {};   // this op's weight bytes (what the preceding GEMM should prefetch)
 };
 
-// Builds tensor maps + launch geometry. `A` is bf16 [samples][D][H][W][C]; `Wt` is bf16 [N][ntaps*C] (K-major).
-int gemm_make(GemmOp* op, const bf16* A, const GemmGeom& g, const bf16* Wt, int N, const GemmEpilogue& e,
+// Builds tensor maps + launch geometry. `A` is bf16 (fp32 if g.tf32) [samples][D][H][W][C]; `Wt` is bf16 (fp32 if g.tf32)
+// [N][ntaps*C] (K-major).
+int gemm_make(GemmOp* op, const void* A, const GemmGeom& g, const void* Wt, int N, const GemmEpilogue& e,
               int force_block_n = 0);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
 // Points an already-built op at new output / residual buffers of the same shape (per-call user pointers).

@@ -87,7 +87,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         b_pre = seg0.k_end - seg0.k_begin < STAGES ? seg0.k_end - seg0.k_begin : STAGES;
         for (int it = 0; it < b_pre; ++it) {
             ptx::mbar_arrive_expect_tx(&full_bar[it], kStageBytes);
-            ptx::tma_load_3d(smem + it * kStageBytes + kABytes, &tmap_b, &full_bar[it], (seg0.k_begin + it) * kGemmBlockK,
+            ptx::tma_load_3d(smem + it * kStageBytes + kABytes, &tmap_b, &full_bar[it], (seg0.k_begin + it) * p.kblk,
                              seg0.n_tile * BN, 0);
         }
     }
@@ -127,16 +127,17 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                         ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                     }
-                    ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * kGemmBlockK, x0 + p.dx[tap], y0 + p.dy[tap],
+                    ptx::tma_load_5d(sa, &tmap_a, &full_bar[s], cb * p.kblk, x0 + p.dx[tap], y0 + p.dy[tap],
                                      z0 + p.dz[tap], sample);
-                    if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * kGemmBlockK, n0, 0);
+                    if (it >= b_pre) ptx::tma_load_3d(sa + kABytes, &tmap_b, &full_bar[s], k * p.kblk, n0, 0);
                     if (++cb == p.cblks) { cb = 0; ++tap; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kGemmBlockM, BN);
+            const bool tf32 = p.tf32 != 0;
+            const uint32_t idesc = tf32 ? ptx::make_idesc_tf32(kGemmBlockM, BN) : ptx::make_idesc_bf16(kGemmBlockM, BN);
             int it = 0;
 #pragma unroll 1
             for (int sg = 0; sg < 2; ++sg) {
@@ -152,9 +153,9 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
                     for (int kk = 0; kk < kGemmBlockK / 16; ++kk)
-                        ptx::umma_f16(tmem_d, ptx::make_smem_desc_sw128(a_addr + kk * 32),
-                                      ptx::make_smem_desc_sw128(b_addr + kk * 32), idesc,
-                                      (k != sgm.k_begin || kk != 0) ? 1u : 0u);
+                        ptx::umma_ss(tf32, tmem_d, ptx::make_smem_desc_sw128(a_addr + kk * 32),
+                                     ptx::make_smem_desc_sw128(b_addr + kk * 32), idesc,
+                                     (k != sgm.k_begin || kk != 0) ? 1u : 0u);
                     ptx::umma_commit(&empty_bar[s]);
                 }
                 ptx::umma_commit(&tmem_full[sg]);

@@ -198,6 +198,7 @@ int KANet::finalize() {
     PD_TRY(gemm_init());
     PD_TRY(validate());
     PD_TRY(ws.check_complete());
+    ++generation;
     packed.clear();
     plans.clear();
     PD_TRY(finalize_resblock("first_proj", cfg.c, C0, &first, &first_b));

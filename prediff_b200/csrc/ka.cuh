@@ -38,6 +38,7 @@ public:
     int C0, C1, T, TE;
     WeightStore ws;
     bool finalized = false;
+    unsigned long long generation = 0;   // see UNet::generation
 
 private:
     void declare_weights();

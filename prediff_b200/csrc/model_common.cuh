@@ -140,6 +140,7 @@ struct Plan {
     std::vector<Step> steps;
     std::vector<uint8_t> kinds;
     std::vector<std::string> labels;   // one per step: kernel class + site, for the per-launch trace
+    std::vector<double> flops;         // one per step: algorithmic FLOPs of a GEMM-family step (0 otherwise)
     std::string scope;                 // prefix applied to labels added from now on (e.g. "L0.res")
     double gemm_flops = 0;
     int n_gemm = 0;
@@ -182,6 +183,7 @@ struct Plan {
         steps.push_back(std::move(s));
         kinds.push_back(k);
         labels.push_back(scope.empty() ? std::string(label) : scope + "." + label);
+        flops.push_back(0.0);
     }
     void add(Step s, const char* label) { add(std::move(s), STEP_KERNEL, label); }
     // GEMM-family steps in launch order, for the L2 weight prefetch chain (common.cuh): `own` = the step's weight ranges,
@@ -196,6 +198,7 @@ struct Plan {
         ++n_gemm;
         auto sp = std::make_shared<GemmOp>(op);
         add([sp](cudaStream_t st) { return gemm_launch(*sp, st); }, STEP_GEMM, label);
+        flops.back() = op.flops;
         weight_users.push_back({[sp](const WRange& r) { sp->p.pf = r; }, op.own_w});
     }
     void add_ffn_fused(const FfnFusedOp& op, const char* label) {

@@ -55,10 +55,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
 // y = act((x - mean) * rstd * gamma + beta) -> bf16. Same thread/row mapping as the stats kernel; a thread's channel
 // quad is fixed, so mean/rstd/gamma/beta are computed once per thread (no smem, no block barrier) while its row
 // loads are already in flight.
+template <bool F32>   // F32: tf32-rounded fp32 operand instead of bf16 (common.cuh)
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __restrict__ x,
                                                               const double* __restrict__ sums,
                                                               const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, bf16* __restrict__ y,
+                                                              const float* __restrict__ beta, void* __restrict__ y,
                                                               int R, int C, int G, float eps, int silu) {
     grid_dep_launch();
     grid_dep_wait();
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __res
             sh[k] = btv[k] - mean * sc[k];
         }
     }
-    uint2* ybase = reinterpret_cast<uint2*>(y + ((size_t)s * R) * C) + tc;
+    const size_t ybase4 = ((size_t)s * R) * c4n + tc;   // float4 / bf16x4 index of (row 0, my channel quad)
 #pragma unroll
     for (int i = 0; i < kGnIters; ++i) {
         const int r = r0 + i * lanes_r;
@@ -112,10 +113,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __res
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] = silu_f(o[k]);
             }
-            uint2 pk;
-            pk.x = pack_bf16x2(o[0], o[1]);
-            pk.y = pack_bf16x2(o[2], o[3]);
-            ybase[(size_t)r * c4n] = pk;
+            store_operand4<F32>(y, ybase4 + (size_t)r * c4n, o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -123,9 +121,9 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const float* __res
 // One warp per kLnRows consecutive output rows, NV float4 per lane per row: all row loads are issued before any
 // reduction so that enough bytes are in flight. GATHER: PatchMerging3D 2x2 space-to-depth on the fly.
 constexpr int kLnRows = 4;
-template <int NV, bool GATHER>
+template <int NV, bool GATHER, bool F32>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, bf16* __restrict__ y, int P,
+                                                         const float* __restrict__ beta, void* __restrict__ y, int P,
                                                          int C, float eps, int H, int W, int Cs) {
     grid_dep_launch();
     grid_dep_wait();
@@ -185,35 +183,33 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
         }
         const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
         if (row < P) {
-            uint2* out = reinterpret_cast<uint2*>(y + (size_t)row * C);
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int c4 = lane + i * 32;
                 if (c4 < c4n) {
                     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
                     const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-                    uint2 pk;
-                    pk.x = pack_bf16x2((v[rr][i].x - mean) * rstd * gm.x + bt.x, (v[rr][i].y - mean) * rstd * gm.y + bt.y);
-                    pk.y = pack_bf16x2((v[rr][i].z - mean) * rstd * gm.z + bt.z, (v[rr][i].w - mean) * rstd * gm.w + bt.w);
-                    out[c4] = pk;
+                    store_operand4<F32>(y, (size_t)row * c4n + c4, (v[rr][i].x - mean) * rstd * gm.x + bt.x,
+                                        (v[rr][i].y - mean) * rstd * gm.y + bt.y, (v[rr][i].z - mean) * rstd * gm.z + bt.z,
+                                        (v[rr][i].w - mean) * rstd * gm.w + bt.w);
                 }
             }
         }
     }
 }
 
-template <bool GATHER>
-int launch_ln(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, float eps, int H, int W,
+template <bool GATHER, bool F32>
+int launch_ln(const float* x, const float* gamma, const float* beta, void* y, int P, int C, float eps, int H, int W,
               int Cs, cudaStream_t st) {
     PD_CHECK(C % 4 == 0 && C >= 4 && C <= 2048, PD_ERR_SHAPE, "layer_norm: unsupported C=%d", C);
     const int nv = ceil_div(C, 128);
     const int rows_per_warp = nv <= 4 ? kLnRows : 1;
     const int blocks = ceil_div(ceil_div(P, rows_per_warp), 8);
-    if (nv <= 1) PD_LAUNCH((layer_norm_kernel<1, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else if (nv <= 2) PD_LAUNCH((layer_norm_kernel<2, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else if (nv <= 4) PD_LAUNCH((layer_norm_kernel<4, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else if (nv <= 8) PD_LAUNCH((layer_norm_kernel<8, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
-    else PD_LAUNCH((layer_norm_kernel<16, GATHER>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    if (nv <= 1) PD_LAUNCH((layer_norm_kernel<1, GATHER, F32>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 2) PD_LAUNCH((layer_norm_kernel<2, GATHER, F32>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 4) PD_LAUNCH((layer_norm_kernel<4, GATHER, F32>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else if (nv <= 8) PD_LAUNCH((layer_norm_kernel<8, GATHER, F32>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
+    else PD_LAUNCH((layer_norm_kernel<16, GATHER, F32>), blocks, 256, 0, st, x, gamma, beta, y, P, C, eps, H, W, Cs);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -230,25 +226,28 @@ int gn_stats(const float* x, double* sums, int S, int R, int C, int G, cudaStrea
     return PD_OK;
 }
 
-int gn_apply(const float* x, const double* sums, const float* gamma, const float* beta, bf16* y, int S, int R, int C,
-             int G, float eps, int silu, cudaStream_t st) {
+int gn_apply(const float* x, const double* sums, const float* gamma, const float* beta, void* y, int S, int R, int C,
+             int G, float eps, int silu, cudaStream_t st, int y_f32) {
     PD_CHECK(C % 4 == 0 && G > 0 && C % G == 0 && G <= 128, PD_ERR_SHAPE, "gn_apply: unsupported C=%d G=%d", C, G);
     PD_CHECK(kGnThreads % (C / 4) == 0 && C / 4 <= kGnThreads, PD_ERR_SHAPE, "gn_apply: unsupported C=%d", C);
     dim3 grid(ceil_div(R, (kGnThreads / (C / 4)) * kGnIters), S);
-    PD_LAUNCH(gn_apply_kernel, grid, kGnThreads, 0, st, x, sums, gamma, beta, y, R, C, G, eps, silu);
+    if (y_f32) PD_LAUNCH(gn_apply_kernel<true>, grid, kGnThreads, 0, st, x, sums, gamma, beta, y, R, C, G, eps, silu);
+    else PD_LAUNCH(gn_apply_kernel<false>, grid, kGnThreads, 0, st, x, sums, gamma, beta, y, R, C, G, eps, silu);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
-int layer_norm(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, float eps,
-               cudaStream_t st) {
-    return launch_ln<false>(x, gamma, beta, y, P, C, eps, 0, 0, 0, st);
+int layer_norm(const float* x, const float* gamma, const float* beta, void* y, int P, int C, float eps,
+               cudaStream_t st, int y_f32) {
+    return y_f32 ? launch_ln<false, true>(x, gamma, beta, y, P, C, eps, 0, 0, 0, st)
+                 : launch_ln<false, false>(x, gamma, beta, y, P, C, eps, 0, 0, 0, st);
 }
 
-int patch_merge_ln(const float* x, const float* gamma, const float* beta, bf16* y, int BT, int H, int W, int C,
-                   float eps, cudaStream_t st) {
+int patch_merge_ln(const float* x, const float* gamma, const float* beta, void* y, int BT, int H, int W, int C,
+                   float eps, cudaStream_t st, int y_f32) {
     PD_CHECK(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, PD_ERR_SHAPE, "patch_merge_ln: H, W must be even (got %d, %d)", H, W);
-    return launch_ln<true>(x, gamma, beta, y, BT * (H / 2) * (W / 2), 4 * C, eps, H, W, C, st);
+    return y_f32 ? launch_ln<true, true>(x, gamma, beta, y, BT * (H / 2) * (W / 2), 4 * C, eps, H, W, C, st)
+                 : launch_ln<true, false>(x, gamma, beta, y, BT * (H / 2) * (W / 2), 4 * C, eps, H, W, C, st);
 }
 
 }  // namespace pd

@@ -12,23 +12,25 @@ namespace pd {
 // Reference: torch.nn.GroupNorm in time_embed.py:90-92,116-118 and taming/resnet.py:403,419.
 int gn_stats(const float* x, double* sums, int S, int R, int C, int G, cudaStream_t st);
 // y = act((x - mean) * rstd * gamma + beta) -> bf16 [S][R][C]; mean/rstd derived from sums (biased variance).
-int gn_apply(const float* x, const double* sums, const float* gamma, const float* beta, bf16* y, int S, int R, int C,
-             int G, float eps, int silu, cudaStream_t st);
+// y_f32 (here and below): the operand is written as tf32-rounded fp32 instead of bf16 (PD_PRECISION_TF32, common.cuh)
+int gn_apply(const float* x, const double* sums, const float* gamma, const float* beta, void* y, int S, int R, int C,
+             int G, float eps, int silu, cudaStream_t st, int y_f32 = 0);
 // LayerNorm over the last dim (eps 1e-5): fp32 [P][C] -> bf16 [P][C]. C in {64,128,256,512,1024,2048}.
 // Reference: models/utils.py:218 (nn.LayerNorm) as used by cuboid_transformer.py:813,195.
-int layer_norm(const float* x, const float* gamma, const float* beta, bf16* y, int P, int C, float eps,
-               cudaStream_t st);
+int layer_norm(const float* x, const float* gamma, const float* beta, void* y, int P, int C, float eps,
+               cudaStream_t st, int y_f32 = 0);
 // PatchMerging3D gather + LayerNorm(4C): x fp32 [B*T][H][W][C] -> bf16 [B*T][H/2][W/2][4C], merged channel order
 // (dh, dw, c). Reference: cuboid_transformer.py:286-294.
-int patch_merge_ln(const float* x, const float* gamma, const float* beta, bf16* y, int BT, int H, int W, int C,
-                   float eps, cudaStream_t st);
+int patch_merge_ln(const float* x, const float* gamma, const float* beta, void* y, int BT, int H, int W, int C,
+                   float eps, cudaStream_t st, int y_f32 = 0);
 
 // ---- attention (attention.cu) ------------------------------------------------------------------------------
 // Axial cuboid self-attention core: qkv bf16 [B][T][H][W][3C] (q|k|v, head-major), one softmax per line along
 // `axis` (0=T, 1=H, 2=W) and head, relative-position bias table fp32 [2L-1][heads]; out bf16 [B][T][H][W][C].
 // Reference: cuboid_transformer.py:849-861,949 with cuboids (T,1,1)/(1,H,1)/(1,1,W) (patterns.py:34-36).
-int axial_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int T, int H, int W, int C, int heads,
-                    int axis, cudaStream_t st);
+// f32 = 1: qkv and out are fp32 (out tf32-rounded) and the whole core runs in fp32 on the CUDA cores.
+int axial_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
+                    int axis, cudaStream_t st, int f32 = 0);
 // General cuboid self-attention core (any cuboid size, 'l' / 'd' strategy, shifted windows, end padding with
 // padding_type 'zeros' (0) or 'ignore' (1)): cuboid_transformer.py:812-966 without global vectors.
 struct CuboidLayerSpec {   // constructor arguments of one CuboidSelfAttentionLayer
@@ -69,16 +71,16 @@ int transpose_bf16(const bf16* in, bf16* out, int S, int R, int C, int ld_in, cu
 // ---- elementwise / data movement (elementwise.cu) ----------------------------------------------------------
 // UNet input assembly (cuboid_transformer_unet.py:425-428): cat(cond, x) on T, append the observed-indicator
 // channel, zero-pad channels to Cpad. Writes fp32 and bf16 copies [B][Tc+Tx][HW][Cpad].
-int unet_assemble(const float* x, const float* cond, float* out_f32, bf16* out_bf16, int B, int Tx, int Tc, int HW,
-                  int C, int Cpad, cudaStream_t st);
+int unet_assemble(const float* x, const float* cond, float* out_f32, void* out_op, int B, int Tx, int Tc, int HW,
+                  int C, int Cpad, cudaStream_t st, int op_f32 = 0);
 // x[b,t,h,w,:] += Temb[t] + Hemb[h] + Wemb[w]   (cuboid_transformer.py:78-85)
 int pos_embed_add(float* x, const float* Te, const float* He, const float* We, int B, int T, int H, int W, int C,
                   cudaStream_t st);
 // nearest 2x spatial upsample + cast: fp32 [F][H][W][C] -> bf16 [F][2H][2W][C]  (cuboid_transformer.py:340,373;
 // taming/resnet.py:128)
-int upsample2x_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st);
+int upsample2x_cast(const float* x, void* y, int F, int H, int W, int C, cudaStream_t st, int y_f32 = 0);
 // fp32 -> bf16 cast of a [S][R][C] slice taken from x with sample stride `in_sample_stride` elements.
-int cast_bf16(const float* x, bf16* y, int S, int64_t RC, int64_t in_sample_stride, cudaStream_t st);
+int cast_bf16(const float* x, void* y, int S, int64_t RC, int64_t in_sample_stride, cudaStream_t st, int y_f32 = 0);
 // Downsample2D prep (taming/resnet.py:183-188): fp32 [F][H][W][C] -> bf16 parity planes [F][4][H/2][W/2][C],
 // plane = (y%2)*2 + (x%2), so the stride-2 3x3 conv becomes 9 unit-stride shifted loads.
 int parity_split_cast(const float* x, bf16* y, int F, int H, int W, int C, cudaStream_t st);
@@ -96,9 +98,9 @@ int conv3x3_c1_out(const bf16* x, const float* w, float bias, float* y, int F, i
 
 // ---- weight repacking (elementwise.cu) ---------------------------------------------------------------------
 // fp32 [N][K] -> bf16 [N][Kpad] (zero padded)
-int pack_linear(const float* w, bf16* out, int N, int K, int Kpad, cudaStream_t st);
+int pack_linear(const float* w, void* out, int N, int K, int Kpad, cudaStream_t st, int out_f32 = 0);
 // fp32 [Co][Ci][taps] -> bf16 [Co][taps][Cipad]
-int pack_conv(const float* w, bf16* out, int Co, int Ci, int taps, int Cipad, cudaStream_t st);
+int pack_conv(const float* w, void* out, int Co, int Ci, int taps, int Cipad, cudaStream_t st, int out_f32 = 0);
 
 // ---- input-gradient kernels (backward.cu) - knowledge-alignment guidance only ---------------------------------
 // GroupNorm(+SiLU) backward: x, dy fp32 [S][R][C]; sums = forward (sum, sumsq); bsums = zeroed scratch [S][G][2].

@@ -208,6 +208,25 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::tf32: fp32 containers in shared memory, the tensor core reads sign + 8 exponent + 10 mantissa bits of each
+// (K = 8 per instruction = the same 32 bytes of a 128-byte swizzle row as 16 bf16), fp32 accumulate. Half the bf16 rate.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// bf16 or tf32 operands, chosen at run time by the (single) issuing thread
+__device__ __forceinline__ void umma_ss(bool tf32, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    if (tf32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -262,6 +281,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
            | (1u << 10)                           // B format: bf16
            | (static_cast<uint32_t>(n >> 3) << 17)  // N / 8
            | (static_cast<uint32_t>(m >> 4) << 24); // M / 16
+}
+
+// kind::tf32: tf32 x tf32 -> fp32 (a/b format 2), both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
         if (noise) noise += (size_t)k * noise_step_stride;
     }
     const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], c4 = coef[4], c5 = coef[5], c6 = coef[6];
+    const bool clip = coef[7] != 0.f;   // clip_denoised (latent_diffusion.py:580-581): z_0 estimate clamped to [-1, 1]
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 zv = reinterpret_cast<const float4*>(z)[i];
         const float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
@@ -33,7 +34,8 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
         const float gi[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float z0 = c0 * zi[k] - c1 * ei[k];
+            float z0 = c0 * zi[k] - c1 * ei[k];
+            if (clip) z0 = fminf(fmaxf(z0, -1.f), 1.f);
             float m = c2 * z0 + c3 * zi[k] + c4 * ei[k];
             m -= c6 * gi[k];
             zi[k] = m + c5 * ni[k];

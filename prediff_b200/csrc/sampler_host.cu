@@ -114,7 +114,10 @@ int Sampler::leave(cudaStream_t user) {
 
 void Sampler::drop_graph() {
     if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    if (graph_loop_) cudaGraphExecDestroy(graph_loop_);
     graph_exec_ = nullptr;
+    graph_loop_ = nullptr;
+    graph_loop_steps_ = 0;
 }
 
 int Sampler::get_buffer(const char* name, float* out) const {
@@ -143,6 +146,7 @@ int Sampler::coefficients(int mode, int n_steps, float eta, std::vector<float>* 
             c[0] = r[t]; c[1] = rm1[t]; c[2] = c1[t]; c[3] = c2[t]; c[4] = 0.f;
             c[5] = t == 0 ? 0.f : sigma;   // no noise when t == 0 (latent_diffusion.py:624-626)
             c[6] = sigma;                  // aligned_mean: mean - exp(0.5 logvar) * grad (:594-595)
+            c[7] = clip_ ? 1.f : 0.f;      // clip_denoised: z_recon.clamp_(-1, 1) (:580-581)
             (*ts)[k] = t;
         }
     } else if (mode == PD_MODE_DDIM) {
@@ -277,55 +281,104 @@ int Sampler::loop(UNet* unet, float* z, const float* cond, const float* noise, i
     return rc != PD_OK ? rc : rl;
 }
 
+// Captures `iterations` consecutive loop iterations on the internal state buffers into one executable graph.
+int Sampler::capture(cudaStream_t st, UNet* unet, const float* noise, int B, const Align& al, int iterations,
+                     cudaGraphExec_t* out) {
+    cudaGraph_t graph = nullptr;
+    PD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = PD_OK;
+    for (int i = 0; i < iterations && rc == PD_OK; ++i)
+        rc = one_iteration(unet, z_buf_.as<float>(), cond_buf_.as<float>(), noise, B, st, al);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != PD_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    PD_CUDA(ce);
+    const cudaError_t ie = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    PD_CUDA(ie);
+    return PD_OK;
+}
+
 int Sampler::loop_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int mode,
-                     int n_total, float eta, int k_begin, int k_end, const Align& al) {
-    std::vector<float> rows;
-    std::vector<int64_t> ts;
-    PD_TRY(coefficients(mode, n_total, eta, &rows, &ts));
+                     int n_total, float eta, int k_begin, int k_end, const Align& al_user) {
+    PD_CHECK(unet->finalized, PD_ERR_STATE, "sample_loop: pd_unet_finalize() has not been called since the last weight load");
+    PD_CHECK(!al_user.ka || al_user.ka->finalized, PD_ERR_STATE, "sample_loop: pd_ka_finalize() has not been called");
     PD_CHECK(0 <= k_begin && k_begin <= k_end && k_end <= n_total, PD_ERR_ARG, "sample_loop: bad step range [%d, %d)",
              k_begin, k_end);
     if (k_begin == k_end) return PD_OK;
-    rows = std::vector<float>(rows.begin() + (size_t)k_begin * 8, rows.begin() + (size_t)k_end * 8);
-    ts = std::vector<int64_t>(ts.begin() + k_begin, ts.begin() + k_end);
     const int n_steps = k_end - k_begin;
-    bool needs_noise = false;
-    for (int k = 0; k < n_steps; ++k) needs_noise |= rows[(size_t)k * 8 + 5] != 0.f;
-    PD_CHECK(!needs_noise || noise, PD_ERR_ARG, "sample_loop: this sampler is stochastic; pass the noise stack");
-    const size_t n = (size_t)B * unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    const size_t per = (size_t)unet->cfg.t_out * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    const size_t per_c = (size_t)unet->cfg.t_in * unet->cfg.h * unet->cfg.w * unet->cfg.c;
+    const size_t n = (size_t)B * per;
     if (eps_dev_.bytes < n * sizeof(float)) {
         PD_TRY(eps_dev_.alloc(n * sizeof(float)));
         drop_graph();
     }
-    PD_TRY(upload_tables(rows, ts, B, st));
+    // coefficient rows + timesteps of the executed range: resident on the device, re-uploaded only when the request changes
+    TableKey tk;
+    tk.valid = true; tk.mode = mode; tk.n_total = n_total; tk.k_begin = k_begin; tk.k_end = k_end; tk.B = B; tk.eta = eta;
+    if (!(tk == table_key_)) {
+        std::vector<float> rows;
+        std::vector<int64_t> ts;
+        PD_TRY(coefficients(mode, n_total, eta, &rows, &ts));
+        rows = std::vector<float>(rows.begin() + (size_t)k_begin * 8, rows.begin() + (size_t)k_end * 8);
+        ts = std::vector<int64_t>(ts.begin() + k_begin, ts.begin() + k_end);
+        table_needs_noise_ = false;
+        for (int k = 0; k < n_steps; ++k) table_needs_noise_ |= rows[(size_t)k * 8 + 5] != 0.f;
+        table_key_.valid = false;
+        PD_TRY(upload_tables(rows, ts, B, st));
+        table_key_ = tk;
+    }
+    PD_CHECK(!table_needs_noise_ || noise, PD_ERR_ARG, "sample_loop: this sampler is stochastic; pass the noise stack");
+    PD_CUDA(cudaMemsetAsync(step_dev_.p, 0, sizeof(int), st));
 
     const bool use_graph = getenv("PD_NO_GRAPH") == nullptr && n_steps > 2;
-    int k = 0;
-    if (use_graph) {
-        const Key key{unet, z, cond, noise, al.ka, al.avg_x_gt, B, al.guide_scale};
-        if (!graph_exec_ || !(key == graph_key_)) {
-            drop_graph();
-            // first iteration runs eagerly (also performs any lazy one-time kernel attribute setup) ...
-            PD_TRY(one_iteration(unet, z, cond, noise, B, st, al));
-            k = 1;
-            // ... then one iteration is captured and replayed; the step index lives on the device
-            cudaGraph_t graph = nullptr;
-            PD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = one_iteration(unet, z, cond, noise, B, st, al);
-            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-            if (rc != PD_OK) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc;
-            }
-            PD_CUDA(ce);
-            const cudaError_t ie = cudaGraphInstantiate(&graph_exec_, graph, 0);
-            cudaGraphDestroy(graph);
-            PD_CUDA(ie);
-            graph_key_ = key;
-        }
-        for (; k < n_steps; ++k) PD_CUDA(cudaGraphLaunch(graph_exec_, st));
-    } else {
-        for (; k < n_steps; ++k) PD_TRY(one_iteration(unet, z, cond, noise, B, st, al));
+    if (!use_graph) {
+        for (int k = 0; k < n_steps; ++k) PD_TRY(one_iteration(unet, z, cond, noise, B, st, al_user));
+        return PD_OK;
     }
+    // ---- graph path: the loop state lives in the sampler's own buffers --------------------------------------------
+    if (z_buf_.bytes < n * sizeof(float) || cond_buf_.bytes < (size_t)B * per_c * sizeof(float) ||
+        target_buf_.bytes < (size_t)B * sizeof(float)) {
+        PD_CUDA(cudaStreamSynchronize(st));
+        drop_graph();
+        if (z_buf_.bytes < n * sizeof(float)) PD_TRY(z_buf_.alloc(n * sizeof(float)));
+        if (cond_buf_.bytes < (size_t)B * per_c * sizeof(float)) PD_TRY(cond_buf_.alloc((size_t)B * per_c * sizeof(float)));
+        if (target_buf_.bytes < (size_t)B * sizeof(float)) PD_TRY(target_buf_.alloc((size_t)B * sizeof(float)));
+    }
+    Align al = al_user;
+    if (al.ka) {
+        PD_CUDA(cudaMemcpyAsync(target_buf_.p, al_user.avg_x_gt, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        al.avg_x_gt = target_buf_.as<float>();
+    }
+    PD_CUDA(cudaMemcpyAsync(cond_buf_.p, cond, (size_t)B * per_c * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const Key key{unet, noise, al.ka, unet->generation, al.ka ? al.ka->generation : 0ull, B, al.guide_scale};
+    if (!(key == graph_key_) || (!graph_exec_ && !graph_loop_)) {
+        drop_graph();
+        // one throw-away eager iteration on the internal buffers: performs every lazy one-time setup (plans, arenas,
+        // kernel attributes) outside of stream capture; z_buf_ is (re)loaded below
+        PD_CUDA(cudaMemcpyAsync(z_buf_.p, z, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PD_TRY(one_iteration(unet, z_buf_.as<float>(), cond_buf_.as<float>(), noise, B, st, al));
+        PD_CUDA(cudaMemsetAsync(step_dev_.p, 0, sizeof(int), st));
+        graph_key_ = key;
+    }
+    PD_CUDA(cudaMemcpyAsync(z_buf_.p, z, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (n_steps <= kWholeLoopMaxSteps && getenv("PD_NO_LOOP_GRAPH") == nullptr) {
+        // the whole loop is ONE graph launch (50-step DDIM: 50 x 286 kernel nodes)
+        if (!graph_loop_ || graph_loop_steps_ != n_steps) {
+            if (graph_loop_) cudaGraphExecDestroy(graph_loop_);
+            graph_loop_ = nullptr;
+            PD_TRY(capture(st, unet, noise, B, al, n_steps, &graph_loop_));
+            graph_loop_steps_ = n_steps;
+        }
+        PD_CUDA(cudaGraphLaunch(graph_loop_, st));
+    } else {
+        if (!graph_exec_) PD_TRY(capture(st, unet, noise, B, al, 1, &graph_exec_));
+        for (int k = 0; k < n_steps; ++k) PD_CUDA(cudaGraphLaunch(graph_exec_, st));
+    }
+    PD_CUDA(cudaMemcpyAsync(z, z_buf_.p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return PD_OK;
 }
 
@@ -350,6 +403,7 @@ int Sampler::step_on(cudaStream_t st, UNet* unet, float* z, const float* cond, c
         PD_TRY(eps_dev_.alloc(n * sizeof(float)));
         drop_graph();
     }
+    table_key_.valid = false;
     PD_TRY(upload_tables(rows, ts, B, st));
     return one_iteration(unet, z, cond, noise, B, st);
 }

@@ -37,6 +37,9 @@ public:
                cudaStream_t st);
 
     int T;
+    // clip_denoised of p_mean_variance (latent_diffusion.py:580-581): z_0 estimate clamped to [-1, 1] inside the update
+    void set_clip_denoised(bool on) { if (on != clip_) { clip_ = on; table_key_.valid = false; } }
+    bool clip_denoised() const { return clip_; }
     // number of concurrent sub-batches a batch of B is cut into (env PD_SUB_BATCHES, default 2, must divide B)
     int n_sub_for(int B) const;
 
@@ -47,15 +50,36 @@ private:
                 int n_total, float eta, int k_begin, int k_end, const Align& al);
     int step_on(cudaStream_t st, UNet* unet, float* z, const float* cond, const float* noise, int B, int t);
     int upload_tables(const std::vector<float>& rows, const std::vector<int64_t>& ts, int B, cudaStream_t st);
+    int capture(cudaStream_t st, UNet* unet, const float* noise, int B, const Align& al, int iterations,
+                cudaGraphExec_t* out);
     int one_iteration(UNet* unet, float* z, const float* cond, const float* noise, int B, cudaStream_t st,
                       const Align& al = Align());
     void drop_graph();
 
     std::map<std::string, std::vector<float>> buf_;  // the reference's registered fp32 buffers
     DevMem coef_dev_, t_dev_, step_dev_, eps_dev_;
+    // Stable device homes of the loop state: the captured graphs only ever see these addresses (the caller's z / cond /
+    // avg_x_gt are copied in before the first replay and z is copied back after the last), so a graph survives any
+    // change of the caller's tensor addresses.
+    DevMem z_buf_, cond_buf_, target_buf_;
+    bool clip_ = false;
+    // what the resident coefficient / timestep tables currently hold (re-uploaded only when this changes)
+    struct TableKey {
+        bool valid = false;
+        int mode = 0, n_total = 0, k_begin = 0, k_end = 0, B = 0;
+        float eta = 0.f;
+        bool operator==(const TableKey& o) const {
+            return valid && o.valid && mode == o.mode && n_total == o.n_total && k_begin == o.k_begin && k_end == o.k_end &&
+                   B == o.B && eta == o.eta;
+        }
+    } table_key_;
+    bool table_needs_noise_ = false;
     DevMem loss_tab_, loss_ws_;   // {sqrt_ac, sqrt_1mac, lvlb} tables; x_noisy + eps workspace of losses()
-    // cached one-iteration graph
-    cudaGraphExec_t graph_exec_ = nullptr;
+    // cached graphs: one iteration (replayed n times: long DDPM stretches) and a whole loop of graph_loop_steps_
+    // iterations (one launch per loop: the 50-step DDIM benchmark)
+    cudaGraphExec_t graph_exec_ = nullptr, graph_loop_ = nullptr;
+    int graph_loop_steps_ = 0;
+    static constexpr int kWholeLoopMaxSteps = 64;
     // sub-batch concurrency: the batch is cut into n_sub independent slices (samples never interact) that run the
     // same launch sequence on parallel streams, so one slice's prologue / epilogue bubbles are filled by another's work
     static constexpr int kMaxSub = 4;
@@ -65,13 +89,16 @@ private:
     cudaEvent_t ev_ka_ = nullptr;
     cudaStream_t loop_stream_ = nullptr;
     cudaEvent_t ev_in_ = nullptr, ev_out_ = nullptr;
+    // A graph is valid for one (UNet, its weight generation, KA net, its generation, batch, noise stack, guide scale):
+    // finalize() frees the packed weights and activation arenas the captured kernels point at and bumps the generation.
     struct Key {
-        const void *unet, *z, *cond, *noise, *ka, *target;
+        const void *unet, *noise, *ka;
+        unsigned long long unet_gen, ka_gen;
         int B;
         float gs;
         bool operator==(const Key& o) const {
-            return unet == o.unet && z == o.z && cond == o.cond && noise == o.noise && B == o.B && ka == o.ka &&
-                   target == o.target && gs == o.gs;
+            return unet == o.unet && noise == o.noise && B == o.B && ka == o.ka && unet_gen == o.unet_gen &&
+                   ka_gen == o.ka_gen && gs == o.gs;
         }
     } graph_key_{};
 };

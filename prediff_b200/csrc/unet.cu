@@ -152,6 +152,13 @@ void UNet::declare_weights() {
     ws.declare("final_proj.bias", {cfg.c});
 }
 
+int UNet::set_precision(int prec) {
+    PD_CHECK(prec == PD_PRECISION_BF16 || prec == PD_PRECISION_TF32, PD_ERR_ARG, "unet: unknown precision %d", prec);
+    if (prec != precision) finalized = false;
+    precision = prec;
+    return PD_OK;
+}
+
 int UNet::validate() const {
     PD_CHECK(cfg.t_in > 0 && cfg.t_out > 0 && T <= 16, PD_ERR_SHAPE, "unet: t_in + t_out = %d must be <= 16", T);
     PD_CHECK(cfg.h <= 16 && cfg.w <= 16 && cfg.h % 2 == 0 && cfg.w % 2 == 0, PD_ERR_SHAPE,
@@ -182,17 +189,17 @@ int UNet::pack_conv_w(const std::string& name, int co, int ci, int taps, int cip
     const float* w = ws.get(name);
     if (!w) return PD_ERR_WEIGHT;
     packed.emplace_back(new DevMem());
-    PD_TRY(packed.back()->alloc((size_t)co * taps * cipad * sizeof(bf16)));
+    PD_TRY(packed.back()->alloc((size_t)co * taps * cipad * op_bytes()));
     *out = packed.back()->as<bf16>();
-    return pack_conv(w, *out, co, ci, taps, cipad, 0);
+    return pack_conv(w, *out, co, ci, taps, cipad, 0, precision);
 }
 int UNet::pack_linear_w(const std::string& name, int n, int k, bf16** out) {
     const float* w = ws.get(name);
     if (!w) return PD_ERR_WEIGHT;
     packed.emplace_back(new DevMem());
-    PD_TRY(packed.back()->alloc((size_t)n * k * sizeof(bf16)));
+    PD_TRY(packed.back()->alloc((size_t)n * k * op_bytes()));
     *out = packed.back()->as<bf16>();
-    return pack_linear(w, *out, n, k, k, 0);
+    return pack_linear(w, *out, n, k, k, 0, precision);
 }
 
 #define PD_GETW(dst, name)                      \
@@ -239,6 +246,7 @@ int UNet::finalize() {
     PD_TRY(gemm_init());
     PD_TRY(validate());
     PD_TRY(ws.check_complete());
+    ++generation;
     packed.clear();
     plans.clear();
     const int cin = cfg.c + 1;
@@ -302,6 +310,9 @@ int UNet::finalize() {
             PD_TRY(build_cuboid_tables(T, cfg.h >> lvl, cfg.w >> lvl, sp, padding_type, &g));
             cub_axis[lvl].push_back(g.axial_axis);
             cub_dev[lvl].emplace_back(nullptr);
+            PD_CHECK(g.axial_axis >= 0 || !precision, PD_ERR_ARG,
+                     "unet: PD_PRECISION_TF32 is built for the axial pattern (the shipped config); other cuboid patterns run "
+                     "with bf16 operands");
             if (g.axial_axis < 0) {
                 cub_dev[lvl].back().reset(new CuboidTablesDev());
                 PD_TRY(cub_dev[lvl].back()->upload(g));
@@ -323,23 +334,26 @@ int UNet::finalize() {
 // ---- plan construction --------------------------------------------------------------------------------------
 template <class A>
 void UNet::carve(A& ar, int B, Bufs* b) const {
+    // operand buffers: bf16, or fp32 (tf32-rounded) at twice the bytes
+    const size_t opx = precision ? 2 : 1;
+    auto take_op = [&](size_t n) { return ar.template take<bf16>(n * opx); };
     const size_t P0 = (size_t)B * T * cfg.h * cfg.w, P1 = P0 / 4;
     const size_t P[2] = {P0, P1};
     const int C[2] = {C0, C1};
     b->xin_f32 = ar.template take<float>(P0 * kCinPad);
-    b->xin_bf16 = ar.template take<bf16>(P0 * kCinPad);
+    b->xin_bf16 = take_op(P0 * kCinPad);
     for (int l = 0; l < 2; ++l) {
         b->x[l] = ar.template take<float>(P[l] * C[l]);
         b->h[l] = ar.template take<float>(P[l] * C[l]);
-        b->a[l] = ar.template take<bf16>(P[l] * (size_t)(l == 0 && C0 < kCinPad ? kCinPad : C[l]));
-        b->ln[l] = ar.template take<bf16>(P[l] * C[l]);
-        b->qkv[l] = ar.template take<bf16>(P[l] * 3 * C[l]);
-        b->att[l] = ar.template take<bf16>(P[l] * C[l]);
-        b->mid[l] = ar.template take<bf16>(P[l] * 4 * C[l]);
+        b->a[l] = take_op(P[l] * (size_t)(l == 0 && C0 < kCinPad ? kCinPad : C[l]));
+        b->ln[l] = take_op(P[l] * C[l]);
+        b->qkv[l] = take_op(P[l] * 3 * C[l]);
+        b->att[l] = take_op(P[l] * C[l]);
+        b->mid[l] = take_op(P[l] * 4 * C[l]);
     }
-    b->pm = ar.template take<bf16>(P1 * 4 * C0);
-    b->up = ar.template take<bf16>(P0 * C1);
-    b->fin = ar.template take<bf16>((size_t)B * cfg.t_out * cfg.h * cfg.w * C0);
+    b->pm = take_op(P1 * 4 * C0);
+    b->up = take_op(P0 * C1);
+    b->fin = take_op((size_t)B * cfg.t_out * cfg.h * cfg.w * C0);
     b->e0 = ar.template take<float>((size_t)B * C0);
     b->e1 = ar.template take<float>((size_t)B * TE);
     b->temb = ar.template take<float>((size_t)B * TE);
@@ -351,11 +365,12 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
 // Long-K fp32-output convolutions are scheduled stream-K: 36 CTAs per sample whatever the batch (the cut - hence the
 // summation order - depends on the layer shape only, so results stay bit-identical between a batch and its shards).
 // Falls back to the plain / split-K kernel when the shape is not eligible.
-int UNet::make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b,
+int UNet::make_conv(GemmOp* op, const void* a, const GemmGeom& g_in, const void* w, int N, GemmEpilogue e, const Bufs& b,
                     bool* gn_fused) {
     BatchPlan* bp = building_;
+    const GemmGeom g = geom(g_in);
     if (gn_fused) *gn_fused = e.gn_sums != nullptr;
-    const int num_k = g.ntaps * (g.C / kGemmBlockK);
+    const int num_k = g.ntaps * (g.C / g.kblk());
     static const bool enabled = getenv("PD_NO_STREAMK") == nullptr;
     if (enabled && bp && g.ntaps > 1 && num_k >= 64 && N % 256 == 0 && e.out_f32 && e.act == ACT_NONE &&
         (!e.ln_gamma || N == 256)) {
@@ -404,10 +419,11 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
     double* s1 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
     double* s2 = b.gn_sums + (size_t)(*gn_slot)++ * B * 128 * 2;
     const float *g1w = r.gn1_w, *g1b = r.gn1_b, *g2w = r.gn2_w, *g2b = r.gn2_b;
+    const int prec = precision;
     pl.scope = strf("L%d.res", lvl);
     // the statistics of x were accumulated by the epilogue that produced it (gn_slot_for_next / GemmEpilogue::gn_sums)
     if (!x_stats_ready) pl.add([=](cudaStream_t st) { return gn_stats(x, s1, B, R, C, 32, st); }, "gn_stats");
-    pl.add([=](cudaStream_t st) { return gn_apply(x, s1, g1w, g1b, a, B, R, C, 32, 1e-5f, 1, st); }, "gn_apply");
+    pl.add([=](cudaStream_t st) { return gn_apply(x, s1, g1w, g1b, a, B, R, C, 32, 1e-5f, 1, st, prec); }, "gn_apply");
     bool h_stats_ready = false;
     {
         GemmEpilogue e;
@@ -426,7 +442,7 @@ int UNet::add_resblock(Plan& pl, const Bufs& b, int B, int lvl, const ResW& r, i
         pl.add_gemm(op, "conv1");
     }
     if (!h_stats_ready) pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R, C, 32, st); }, "gn_stats");
-    pl.add([=](cudaStream_t st) { return gn_apply(h, s2, g2w, g2b, a, B, R, C, 32, 1e-5f, 1, st); }, "gn_apply");
+    pl.add([=](cudaStream_t st) { return gn_apply(h, s2, g2w, g2b, a, B, R, C, 32, 1e-5f, 1, st, prec); }, "gn_apply");
     {
         GemmEpilogue e;
         e.bias = r.conv2_b;
@@ -455,6 +471,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
     pl.scope = strf("L%d.stack", lvl);
     const int n_layers = (int)s.a.size(), last = n_layers - 1;
     const int N_tok = T * H * W;
+    const int prec = precision;
     for (int i = 0; i < n_layers; ++i) {
         const AttnW& aw = s.a[i];
         const FfnW& fw = s.f[i];
@@ -462,24 +479,25 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
         // x = x + proj(attn(LN(x)))   (cuboid_transformer.py:1151, 813-952). With C == 256 the LayerNorm was
         // produced by the epilogue of the GEMM that last wrote x (conv2 / previous ffn_2).
         const bool ln_ready = fuse && (i > 0 || ln_fusable_conv(lvl));
-        if (!ln_ready) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
+        if (!ln_ready) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st, prec); }, "ln");
         {
             GemmEpilogue e;
-            e.out_bf16 = qkv;
+            operand_out(e, qkv);
+            if (prec) e.round_tf32 = 0;   // q|k|v feed the fp32 attention core, not a tensor-core GEMM
             GemmOp op;
-            PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), aw.qkv_w, 3 * C, e));
+            PD_TRY(gemm_make(&op, ln, geom(GemmGeom::linear(P, C)), aw.qkv_w, 3 * C, e));
             pl.add_gemm(op, "qkv");
         }
         if (cub_axis[lvl][i] >= 0) {
             const int axis = cub_axis[lvl][i];
-            pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st); },
+            pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st, prec); },
                    axis == 0 ? "attn_T" : (axis == 1 ? "attn_H" : "attn_W"));
         } else {   // any other cuboid (shifted / padded / dilated / multi-axis): gather tables + flash-style kernel
             const CuboidDev cd = cub_dev[lvl][i]->dev;
             pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
                    "attn_cuboid");
         }
-        if (C == 256 && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {
+        if (C == 256 && !prec && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {
             // width 256: projection + residual + pre-norm + FFN (+ the next layer's LayerNorm) in ONE kernel per row
             // tile - x1 = x + proj(att) lives in TMEM and seeds the FFN-2 accumulator (ffn_fused.cu, PROJ variant)
             FfnProjArgs pa;
@@ -489,9 +507,11 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                   next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f, nullptr, &pa));
             if (gn_next && i == last) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
-            pl.gemm_flops += 2.0 * (double)P * C * C + 2.0 * 2.0 * (double)P * C * 4 * C;
+            const double fl = 2.0 * (double)P * C * C + 2.0 * 2.0 * (double)P * C * 4 * C;
+            pl.gemm_flops += fl;
             pl.n_gemm += 1;
             pl.add_ffn_fused(op, "proj_ffn_fused");
+            pl.flops.back() = fl;
             continue;
         }
         {
@@ -505,30 +525,32 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
                 e.ln_out = ln;
             }
             GemmOp op;
-            PD_TRY(gemm_make(&op, att, GemmGeom::linear(P, C), aw.proj_w, C, e));
+            PD_TRY(gemm_make(&op, att, geom(GemmGeom::linear(P, C)), aw.proj_w, C, e));
             pl.add_gemm(op, "proj");
         }
         // x = x + W2 gelu(W1 LN(x) + b1) + b2   (cuboid_transformer.py:195-205)
-        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st); }, "ln");
-        if (C == 256 && getenv("PD_NO_FFN_FUSION") == nullptr) {
+        if (!fuse) pl.add([=](cudaStream_t st) { return layer_norm(x, fw.ln_w, fw.ln_b, ln, P, C, 1e-5f, st, prec); }, "ln");
+        if (C == 256 && !prec && getenv("PD_NO_FFN_FUSION") == nullptr) {
             // width 256: both GEMMs + GELU (+ the next layer's LayerNorm) in one kernel; `mid` never leaves the SM
             FfnFusedOp op;
             const bool next_ln = i < last;   // pre-norm of the next attention layer of this stack
             PD_TRY(ffn_fused_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                   next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f));
             if (gn_next && i == last) PD_TRY(ffn_fused_set_gn(&op, gn_next, 32, T * H * W));
-            pl.gemm_flops += 2.0 * 2.0 * (double)P * C * 4 * C;
+            const double fl = 2.0 * 2.0 * (double)P * C * 4 * C;
+            pl.gemm_flops += fl;
             pl.n_gemm += 1;
             pl.add_ffn_fused(op, "ffn_fused");
+            pl.flops.back() = fl;
             continue;
         }
         {
             GemmEpilogue e;
             e.bias = fw.b1;
             e.act = ACT_GELU;
-            e.out_bf16 = mid;
+            operand_out(e, mid);
             GemmOp op;
-            PD_TRY(gemm_make(&op, ln, GemmGeom::linear(P, C), fw.w1, 4 * C, e));
+            PD_TRY(gemm_make(&op, ln, geom(GemmGeom::linear(P, C)), fw.w1, 4 * C, e));
             pl.add_gemm(op, "ffn1");
         }
         {
@@ -547,7 +569,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
                 e.gn_rows = T * H * W;
             }
             GemmOp op;
-            PD_TRY(gemm_make(&op, mid, GemmGeom::linear(P, 4 * C), fw.w2, C, e));
+            PD_TRY(gemm_make(&op, mid, geom(GemmGeom::linear(P, 4 * C)), fw.w2, C, e));
             pl.add_gemm(op, "ffn2");
         }
     }
@@ -600,15 +622,16 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         float *h = b.h[0], *x = b.x[0];
         const ResW r = first;
         const int c0 = C0;
+        const int prec = precision;
         pl.scope = "first";
         pl.add([=](cudaStream_t st) { return gn_stats(xin, s1, B, R0, kCinPad, kCinPad, st); }, "gn_stats");
-        pl.add([=](cudaStream_t st) { return gn_apply(xin, s1, r.gn1_w, r.gn1_b, a, B, R0, kCinPad, kCinPad, 1e-5f, 1, st); }, "gn_apply");
+        pl.add([=](cudaStream_t st) { return gn_apply(xin, s1, r.gn1_w, r.gn1_b, a, B, R0, kCinPad, kCinPad, 1e-5f, 1, st, prec); }, "gn_apply");
         {
             GemmEpilogue e;
             e.bias = r.conv1_b;
             e.out_f32 = h;
             GemmOp op;
-            PD_TRY(gemm_make(&op, a, GemmGeom::conv(B, T, H, W, kCinPad, 3, 3, 3), r.conv1_w, C0, e));
+            PD_TRY(gemm_make(&op, a, geom(GemmGeom::conv(B, T, H, W, kCinPad, 3, 3, 3)), r.conv1_w, C0, e));
             pl.add_gemm(op, "conv1");
         }
         {   // 1x1x1 skip conv on the raw (un-normalised) input
@@ -616,11 +639,11 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             e.bias = first_skip_b;
             e.out_f32 = x;
             GemmOp op;
-            PD_TRY(gemm_make(&op, b.xin_bf16, GemmGeom::conv(B, T, H, W, kCinPad, 1, 1, 1), first_skip_w, C0, e));
+            PD_TRY(gemm_make(&op, b.xin_bf16, geom(GemmGeom::conv(B, T, H, W, kCinPad, 1, 1, 1)), first_skip_w, C0, e));
             pl.add_gemm(op, "skip");
         }
         pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R0, c0, 32, st); }, "gn_stats");
-        pl.add([=](cudaStream_t st) { return gn_apply(h, s2, r.gn2_w, r.gn2_b, a, B, R0, c0, 32, 1e-5f, 1, st); }, "gn_apply");
+        pl.add([=](cudaStream_t st) { return gn_apply(h, s2, r.gn2_w, r.gn2_b, a, B, R0, c0, 32, 1e-5f, 1, st, prec); }, "gn_apply");
         {
             GemmEpilogue e;
             e.bias = r.conv2_b;
@@ -653,8 +676,8 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     {   // PatchMerging3D: x0 stays intact and doubles as the U-Net skip tensor
         const float *x0 = b.x[0], *lw = pm_ln_w, *lb = pm_ln_b;
         bf16* pm = b.pm;
-        const int BT = B * T, c0 = C0;
-        pl.add([=](cudaStream_t st) { return patch_merge_ln(x0, lw, lb, pm, BT, H, W, c0, 1e-5f, st); }, "down.merge_ln");
+        const int BT = B * T, c0 = C0, prec = precision;
+        pl.add([=](cudaStream_t st) { return patch_merge_ln(x0, lw, lb, pm, BT, H, W, c0, 1e-5f, st, prec); }, "down.merge_ln");
         GemmEpilogue e;
         e.out_f32 = b.x[1];
         e.gn_sums = cfg.depth[1] > 0 ? next_slot(C1, R1) : nullptr;
@@ -662,7 +685,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         e.gn_rows = R1;
         x_ready = e.gn_sums != nullptr;
         GemmOp op;
-        PD_TRY(gemm_make(&op, pm, GemmGeom::linear(B * T * HW / 4, 4 * C0), pm_w, C1, e));
+        PD_TRY(gemm_make(&op, pm, geom(GemmGeom::linear(B * T * HW / 4, 4 * C0)), pm_w, C1, e));
         pl.add_gemm(op, "down.reduction");
     }
     for (int d = 0; d < cfg.depth[1]; ++d) {
@@ -681,8 +704,8 @@ int UNet::build_plan(int B, BatchPlan* bp) {
     {   // Upsample3DLayer (nearest 2x + Conv2d 3x3 per frame) with the U-Net skip add fused as the residual
         const float* x1 = b.x[1];
         bf16* up = b.up;
-        const int BT = B * T, c1 = C1;
-        pl.add([=](cudaStream_t st) { return upsample2x_cast(x1, up, BT, H / 2, W / 2, c1, st); }, "up.nearest");
+        const int BT = B * T, c1 = C1, prec = precision;
+        pl.add([=](cudaStream_t st) { return upsample2x_cast(x1, up, BT, H / 2, W / 2, c1, st, prec); }, "up.nearest");
         GemmEpilogue e;
         e.bias = up_b;
         e.residual = b.x[0];
@@ -706,15 +729,17 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         const float* x0 = b.x[0];
         bf16* fin = b.fin;
         const int64_t rc = (int64_t)cfg.t_out * HW * C0, stride = (int64_t)T * HW * C0, off = (int64_t)cfg.t_in * HW * C0;
-        pl.add([=](cudaStream_t st) { return cast_bf16(x0 + off, fin, B, rc, stride, st); }, "final.cast");
+        const int prec = precision;
+        pl.add([=](cudaStream_t st) { return cast_bf16(x0 + off, fin, B, rc, stride, st, prec); }, "final.cast");
         GemmEpilogue e;
         e.bias = final_b;
         e.out_f32 = b.h[0];  // placeholder; re-bound to the caller's tensor per call
-        PD_TRY(gemm_make(&bp->final_op, fin, GemmGeom::linear(B * cfg.t_out * HW, C0), final_w, cfg.c, e));
+        PD_TRY(gemm_make(&bp->final_op, fin, geom(GemmGeom::linear(B * cfg.t_out * HW, C0)), final_w, cfg.c, e));
         pl.gemm_flops += bp->final_op.flops;
         ++pl.n_gemm;
         bp->out_slot = pl.steps.size();
         pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM, "final.proj");  // placeholder: final GEMM, bound per call
+        pl.flops.back() = bp->final_op.flops;
     }
     if (getenv("PD_NO_L2_PREFETCH") == nullptr) pl.link_prefetch();
     if (getenv("PD_NO_TEMB_FORK") == nullptr) {   // time-embedding MLP beside first_proj; joined at the first conv that adds it
@@ -754,7 +779,8 @@ int UNet::forward(const float* x, const int64_t* t, const int* step, const float
     const int Tx = cfg.t_out, Tc = cfg.t_in, HW = cfg.h * cfg.w, C = cfg.c;
     float* xf = b.xin_f32;
     bf16* xb = b.xin_bf16;
-    bp->plan.steps[bp->in_slot] = [=](cudaStream_t s) { return unet_assemble(x, cond, xf, xb, B, Tx, Tc, HW, C, kCinPad, s); };
+    const int prec = precision;
+    bp->plan.steps[bp->in_slot] = [=](cudaStream_t s) { return unet_assemble(x, cond, xf, xb, B, Tx, Tc, HW, C, kCinPad, s, prec); };
     GemmOp fop = bp->final_op;
     PD_TRY(gemm_bind_output(&fop, out, nullptr, nullptr));
     bp->plan.steps[bp->out_slot] = [fop](cudaStream_t s) { return gemm_launch(fop, s); };
@@ -767,6 +793,13 @@ int UNet::plan_labels(int B, std::vector<std::string>* out) {
     BatchPlan* bp = nullptr;
     PD_TRY(get_plan(B, &bp));
     *out = bp->plan.labels;
+    return PD_OK;
+}
+
+int UNet::plan_flops(int B, std::vector<double>* out) {
+    BatchPlan* bp = nullptr;
+    PD_TRY(get_plan(B, &bp));
+    *out = bp->plan.flops;
     return PD_OK;
 }
 

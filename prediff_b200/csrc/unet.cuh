@@ -5,6 +5,8 @@
 
 namespace pd {
 
+// Operand pointers (`bf16*` members below, activation buffers in the plans) hold bf16 data, or fp32 data rounded to tf32
+// when the model's precision is PD_PRECISION_TF32 (the buffers are then sized 4 bytes per element).
 struct ResW {   // TimeEmbedResBlock
     const float *gn1_w, *gn1_b, *conv1_b, *gn2_w, *gn2_b, *conv2_b;
     bf16 *conv1_w, *conv2_w;
@@ -31,12 +33,17 @@ public:
     ~UNet();
     int validate() const;
     int finalize();
+    // Operand precision of every tensor-core GEMM of the model (PD_PRECISION_*): bf16 (default) or tf32 - the
+    // reference's own GPU arithmetic (cfg.yaml:32; train_sevirlr_prediff.py:1143). Takes effect at the next finalize().
+    int set_precision(int prec);
+    int precision = 0;
     // t: device int64; if `step` (device int) is given, t is a table and row *step is used (sampler loop)
     // replica: independent workspace index (sub-batches of one call running concurrently on different streams);
     // t_stride: row length of the t table when `step` is given (0 -> B)
     int forward(const float* x, const int64_t* t, const int* step, const float* cond, float* out, int B, cudaStream_t st,
                 PlanProfile* prof = nullptr, int replica = 0, int t_stride = 0, unsigned long long* trace_ns = nullptr);
     int plan_labels(int B, std::vector<std::string>* out);   // one label per plan step (trace_ns has size + 1 slots)
+    int plan_flops(int B, std::vector<double>* out);          // algorithmic FLOPs per plan step (0 for non-GEMM steps)
     int kernels_per_forward(int B, int* n);
     int get_plan(int B, BatchPlan** out, int replica = 0);
 
@@ -48,6 +55,9 @@ public:
     bool all_axial = true;
     WeightStore ws;
     bool finalized = false;
+    // bumped by every finalize(): packed weights and plans (activation arenas) of older generations are gone, so anything
+    // that cached device addresses of this model (the sampler's CUDA graphs) must be rebuilt
+    unsigned long long generation = 0;
 
 private:
     void declare_weights();
@@ -65,16 +75,24 @@ private:
                      const StackW* next, bool x_stats_ready);
     // gn_next: statistics table of the resblock that follows the stack (filled by the stack's last kernel), or null
     int add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, double* gn_next);
-    int make_conv(GemmOp* op, const bf16* a, const GemmGeom& g, const bf16* w, int N, GemmEpilogue e, const Bufs& b,
+    int make_conv(GemmOp* op, const void* a, const GemmGeom& g, const void* w, int N, GemmEpilogue e, const Bufs& b,
                   bool* gn_fused = nullptr);
     // The LayerNorm that follows a GEMM is computed in that GEMM's epilogue when a CTA (width 256) or a 2-CTA cluster
     // (width 512) owns whole rows; the resblock's conv2 only when it is not split-K (27 * C / 64 < 128 k-blocks).
     bool ln_fusable(int lvl) const {
+        if (precision) return false;   // the fused LayerNorm epilogue writes bf16; tf32 mode runs layer_norm launches
         const int c = lvl ? C1 : C0;
         static const bool no_cluster = getenv("PD_NO_LN_CLUSTER") != nullptr;   // A/B: separate LayerNorm launches at 512
         return c == 256 || (c == 512 && !no_cluster);
     }
-    bool ln_fusable_conv(int lvl) const { const int c = lvl ? C1 : C0; return c == 256; }
+    bool ln_fusable_conv(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 && !precision; }
+    // GEMM geometry / operand-output helpers for the model's precision
+    GemmGeom geom(GemmGeom g) const { g.tf32 = precision; return g; }
+    void operand_out(GemmEpilogue& e, bf16* buf) const {
+        if (precision) { e.out_f32 = reinterpret_cast<float*>(buf); e.round_tf32 = 1; }
+        else e.out_bf16 = buf;
+    }
+    size_t op_bytes() const { return precision ? 4 : 2; }
     int num_gn_slots() const;
     template <class A>
     void carve(A& ar, int B, Bufs* b) const;

@@ -53,10 +53,13 @@ class LatentDiffusion(nn.Module):
             raise NotImplementedError("prediff_b200.LatentDiffusion: only the 'linear' beta schedule with v_posterior=0")
         if layout != "NTHWC":
             raise NotImplementedError("prediff_b200.LatentDiffusion: layout must be 'NTHWC'")
-        if clip_denoised:
-            raise NotImplementedError("prediff_b200.LatentDiffusion: clip_denoised=True is not built")
         if num_timesteps_cond not in (None, 1):
             raise NotImplementedError("prediff_b200.LatentDiffusion: shorten_cond_schedule is not built")
+        if scale_by_std:   # the reference registers a 'scale_factor' buffer (a state_dict key) and rescales on the first batch
+            raise NotImplementedError("prediff_b200.LatentDiffusion: scale_by_std=True is not built")
+        if cond_stage_forward not in (None, "encode"):
+            raise NotImplementedError(f"prediff_b200.LatentDiffusion: cond_stage_forward='{cond_stage_forward}' is not built "
+                                      "(the context is always encoded with first_stage_model.encode)")
         self.parameterization = parameterization
         self.clip_denoised = clip_denoised
         self.log_every_t = log_every_t
@@ -84,6 +87,8 @@ class LatentDiffusion(nn.Module):
         self.learn_logvar = bool(learn_logvar)   # the shipped config sets it (cfg.yaml:95); the values come from the checkpoint
         self.logvar_init = float(logvar_init)
         self.register_schedule(timesteps=timesteps, linear_start=linear_start, linear_end=linear_end)
+        if self.clip_denoised:   # latent_diffusion.py:580-581, applied inside the fused update kernel
+            L.check(L.lib().pd_sampler_set_clip_denoised(self._sampler, 1))
         logvar = torch.full(fill_value=logvar_init, size=(self.num_timesteps,))
         if self.learn_logvar:   # latent_diffusion.py:146-150: a parameter when learned, a buffer otherwise (same key)
             self.logvar = nn.Parameter(logvar, requires_grad=True)
@@ -241,11 +246,17 @@ class LatentDiffusion(nn.Module):
         return (self.scale_factor * z).detach()
 
     @torch.no_grad()
-    def decode_first_stage(self, z):
-        """(N,T,h,w,c) latents -> (N,T,H,W,C) pixels (latent_diffusion.py:423-432)."""
+    def decode_first_stage(self, z, out=None):
+        """(N,T,h,w,c) latents -> (N,T,H,W,C) pixels (latent_diffusion.py:423-432). `out` (optional): a contiguous fp32
+        (N,T,H,W,1) buffer the CUDA decoder writes into directly (one pixel channel: 'NTHWC' and '(NT)CHW' are the same
+        bytes) - used for the in-place ensemble all-gather (prediff_b200/dist.py)."""
         z = 1. / self.scale_factor * z
         N, T = z.shape[0], z.shape[1]
         frames = z.permute(0, 1, 4, 2, 3).reshape(N * T, z.shape[4], z.shape[2], z.shape[3])
+        if out is not None:
+            assert out.is_contiguous() and out.shape[0] == N and out.shape[1] == T and out.shape[4] == 1
+            self.first_stage_model.decode(frames, out=out.view(N * T, 1, out.shape[2], out.shape[3]))
+            return out
         out = self.first_stage_model.decode(frames)
         return out.reshape(N, T, *out.shape[1:]).permute(0, 1, 3, 4, 2).contiguous()
 
@@ -297,9 +308,10 @@ class LatentDiffusion(nn.Module):
                     1 if self.loss_type == "l1" else 0, ctypes.c_float(self.logvar_init), ctypes.c_float(self.l_simple_weight),
                     ctypes.c_float(self.original_elbo_weight), L.ptr(per_sample), L.ptr(out4), L.stream_ptr()))
             self.last_loss_per_sample = per_sample
-            if not self.learn_logvar:   # fixed logvar: the four scalars were reduced on the device by the same call
-                return out4[2], {f"{prefix}/loss_simple": out4[0], f"{prefix}/loss_vlb": out4[1], f"{prefix}/loss": out4[2]}
-            return self._loss_terms(per_sample, t, prefix)   # per-timestep logvar: B-element tensor arithmetic
+            self.last_loss_fused = out4   # the kernel's own scalars (computed with the scalar logvar_init)
+            # the reference reads logvar[t] from the persistent buffer / parameter (a checkpoint may hold values that
+            # differ from logvar_init), so the logged terms are B-element tensor arithmetic on the per-sample losses
+            return self._loss_terms(per_sample, t, prefix)
         x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
         model_output = self.apply_model(x_noisy, t, cond)
         loss_simple = self.get_loss(model_output, noise, mean=False).mean(dim=self.loss_mean_dim)
@@ -368,29 +380,77 @@ class LatentDiffusion(nn.Module):
         assert t.numel() == B, "avg_x_gt must hold one value per sample"
         return t.contiguous()
 
+    def _coef_row(self, t_int: int, clip: bool, device):
+        """The update kernel's coefficient row for ancestral timestep t (csrc/sampler_host.cu Sampler::coefficients):
+        z0 = c0 z - c1 eps (clamped if c7); z <- c2 z0 + c3 z + c5 noise - c6 guide."""
+        lv = float(self.posterior_log_variance_clipped[t_int])
+        sigma = float(np.exp(np.float32(0.5) * np.float32(lv)))
+        row = [float(self.sqrt_recip_alphas_cumprod[t_int]), float(self.sqrt_recipm1_alphas_cumprod[t_int]),
+               float(self.posterior_mean_coef1[t_int]), float(self.posterior_mean_coef2[t_int]), 0.0,
+               0.0 if t_int == 0 else sigma, sigma, 1.0 if clip else 0.0]
+        return torch.tensor(row, dtype=torch.float32, device=device)
+
     @torch.no_grad()
     def p_sample(self, zt, zc, t, y=None, use_alignment=False, alignment_kwargs=None, clip_denoised=False,
                  return_x0=False, temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
-                 noise=None):
+                 noise=None, _t_int=None):
         """One ancestral step (latent_diffusion.py:598-631). `noise` may be injected for parity tests; otherwise it
-        is drawn with torch.randn exactly where the reference draws it."""
-        assert not clip_denoised and score_corrector is None and noise_dropout == 0.
+        is drawn with torch.randn exactly where the reference draws it.
+
+        With the CUDA UNet the step runs through the C ABI: `pd_sample_step_ddpm` (UNet + fused update in one call), or -
+        with a foreign `alignment_fn` / a score corrector - the UNet, the caller's function and then the fused update
+        kernel (`pd_op_sampler_update`). Only `return_x0=True` and non-CUDA denoisers evaluate the reference's tensor
+        expressions in torch."""
         B = zt.shape[0]
-        eps = self.apply_model(zt, t, zc)
         dev = zt.device
-        ex = lambda name: self.extract_into_tensor(getattr(self, name).to(dev), t, zt.shape)  # noqa: E731
-        z0 = ex("sqrt_recip_alphas_cumprod") * zt - ex("sqrt_recipm1_alphas_cumprod") * eps
-        mean = ex("posterior_mean_coef1") * z0 + ex("posterior_mean_coef2") * zt
-        logvar = ex("posterior_log_variance_clipped")
-        if use_alignment:
-            g = self.alignment_fn(zt, t, zc=zc, y=y, **(alignment_kwargs or {}))
-            mean = mean - (0.5 * logvar).exp() * g
         if noise is None:
-            noise = torch.randn(zt.shape, device=dev)
+            noise = torch.randn(zt.shape, device=dev)   # noise_like (diffusion/utils.py:118-119)
         noise = noise * temperature
+        if noise_dropout > 0.:
+            noise = torch.nn.functional.dropout(noise, p=noise_dropout)
+        clip = bool(clip_denoised)   # the reference's p_sample uses its argument only; p_sample_loop passes self.clip_denoised
+        native = self._native() and zt.is_cuda and not return_x0
+        if native:
+            ti = int(t[0]) if _t_int is None else int(_t_int)   # the reference's loop passes torch.full((B,), i)
+            native = _t_int is not None or bool((t == ti).all())
+        if native:
+            z = zt.contiguous().float().clone()   # the caller's zt must stay intact (SURVEY 8b ownership)
+            zc_, nz = zc.contiguous().float(), noise.contiguous().float()
+            align = self._native_alignment(use_alignment, alignment_kwargs)
+            lib = L.lib()
+            with torch.cuda.device(dev):
+                L.check(lib.pd_sampler_set_clip_denoised(self._sampler, 1 if clip else 0))
+                try:
+                    if score_corrector is None and (not use_alignment or align is not None):
+                        if align is None:
+                            L.check(lib.pd_sample_step_ddpm(self._sampler, self.torch_nn_module.handle, L.ptr(z), L.ptr(zc_),
+                                                            L.ptr(nz), B, ti, L.stream_ptr()))
+                        else:   # timestep ti = executed step 0 of a (ti + 1)-step ancestral schedule
+                            target = self._target_vector(alignment_kwargs, B, dev)
+                            self._run_range(z, zc_, nz[None].contiguous(), PD_MODE_DDPM, ti + 1, 0.0, 0, 1, align, target)
+                    else:
+                        eps = self.apply_model(zt, t, zc)
+                        if score_corrector is not None:
+                            eps = score_corrector.modify_score(self, eps, zt, t, zc, **(corrector_kwargs or {}))
+                        g = None
+                        if use_alignment:
+                            g = self.alignment_fn(zt, t, zc=zc, y=y, **(alignment_kwargs or {})).contiguous().float()
+                        coef = self._coef_row(ti, clip, dev)
+                        eps = eps.contiguous().float()
+                        L.check(lib.pd_op_sampler_update(L.ptr(z), L.ptr(eps), L.ptr(nz), L.ptr(g), L.ptr(coef),
+                                                         ctypes.c_int64(z.numel()), L.stream_ptr()))
+                finally:
+                    L.check(lib.pd_sampler_set_clip_denoised(self._sampler, 1 if self.clip_denoised else 0))
+            return z
+        outputs = self.p_mean_variance(zt=zt, zc=zc, t=t, clip_denoised=clip, return_x0=return_x0,
+                                       score_corrector=score_corrector, corrector_kwargs=corrector_kwargs)
+        mean, _, logvar = outputs[:3]
+        if use_alignment:
+            mean = self.aligned_mean(zt=zt, t=t, zc=zc, y=y, orig_mean=mean, orig_log_var=logvar,
+                                     **(alignment_kwargs or {}))
         nonzero = (1 - (t == 0).float()).reshape(B, *((1,) * (zt.dim() - 1)))
         out = mean + nonzero * (0.5 * logvar).exp() * noise
-        return (out, z0) if return_x0 else out
+        return (out, outputs[3]) if return_x0 else out
 
     @torch.no_grad()
     def p_sample_loop(self, cond, shape, y=None, use_alignment=False, alignment_kwargs=None,
@@ -420,7 +480,8 @@ class LatentDiffusion(nn.Module):
             for k, i in enumerate(reversed(range(timesteps))):
                 ts = torch.full((B,), i, device=device, dtype=torch.long)
                 img = self.p_sample(zt=img, zc=cond, t=ts, y=y, use_alignment=use_alignment,
-                                    alignment_kwargs=alignment_kwargs, noise=None if noise is None else noise[k])
+                                    alignment_kwargs=alignment_kwargs, clip_denoised=self.clip_denoised,
+                                    noise=None if noise is None else noise[k], _t_int=i)
                 if mask is not None:
                     img = self.q_sample(x0, ts) * mask + (1. - mask) * img
                 if i % log_every_t == 0 or i == timesteps - 1:
@@ -485,7 +546,7 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def sample(self, cond, batch_size=16, use_alignment=False, alignment_kwargs=None, return_intermediates=False,
                x_T=None, verbose=False, timesteps=None, mask=None, x0=None, shape=None, return_decoded=True,
-               sampler="ddpm", ddim_steps=50, ddim_eta=0.0, **kwargs):
+               sampler="ddpm", ddim_steps=50, ddim_eta=0.0, out=None, **kwargs):
         """latent_diffusion.py:686-724: encode the context, run the loop, decode. `sampler="ddim"` selects the
         DDIM loop (not in the reference; default stays the reference's ancestral sampler)."""
         if use_alignment:
@@ -516,5 +577,5 @@ class LatentDiffusion(nn.Module):
                 samples, inter = output
                 output = [self.decode_first_stage(samples), [self.decode_first_stage(e) for e in inter]]
             else:
-                output = self.decode_first_stage(output)
+                output = self.decode_first_stage(output) if out is None else self.decode_first_stage(output, out=out)
         return output

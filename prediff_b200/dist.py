@@ -4,7 +4,7 @@ Every ensemble member is an independent chain (no cross-sample op in the UNet, V
 with NO data-path collective: the global z_T is drawn from one seed and sliced contiguously by rank, weights are
 replicated, and exactly one all-gather of the decoded frames happens at the end. One process per GPU
 (torch.distributed, NCCL on GPUs; the same code runs under gloo on CPU for the host-logic tests)."""
-from typing import Callable, Tuple
+from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -23,14 +23,28 @@ def world_info():
     return 0, 1
 
 
-def sample_ensemble(run_local: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], z_T: torch.Tensor,
-                    cond: torch.Tensor) -> torch.Tensor:
+def sample_ensemble(run_local: Callable[..., torch.Tensor], z_T: torch.Tensor, cond: torch.Tensor,
+                    gathered: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Runs `run_local(z_T[lo:hi], cond[lo:hi]) -> frames` on this rank's rows of the GLOBAL inputs and all-gathers
     the decoded frames so every rank returns the full (G, ...) tensor. Results are invariant to the world size
-    because rows never interact. Ragged splits (G % world != 0) are padded to the largest shard for the gather."""
+    because rows never interact. Ragged splits (G % world != 0) are padded to the largest shard for the gather.
+
+    In-place variant: with a persistent `gathered` buffer of shape (G, ...) and G % world == 0,
+    `run_local(z, c, out=gathered[lo:hi])` is asked to write its frames straight into this rank's slice (the decoder's
+    last kernel does, `LatentDiffusion.sample(out=...)`), and the all-gather runs in place on that buffer - no
+    allocation and no staging copy per call."""
     rank, world = world_info()
     G = z_T.shape[0]
     lo, hi = shard_bounds(G, rank, world)
+    if gathered is not None and G % world == 0 and hi > lo:
+        assert gathered.shape[0] == G and gathered.is_contiguous()
+        mine = gathered[lo:hi]
+        res = run_local(z_T[lo:hi], cond[lo:hi], out=mine)
+        if res.data_ptr() != mine.data_ptr():   # run_local ignored `out`
+            mine.copy_(res)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, mine)
+        return gathered
     local = run_local(z_T[lo:hi], cond[lo:hi]) if hi > lo else None
     if world == 1:
         return local

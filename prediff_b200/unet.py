@@ -50,8 +50,15 @@ class CuboidTransformerUNet(nn.Module):
                  hierarchical_pos_embed=False, pos_embed_type="t+h+w", padding_type="zeros", checkpoint_level=0,
                  use_relative_pos=True, self_attn_use_final_proj=True, num_global_vectors=0,
                  time_embed_channels_mult=4, time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0,
-                 unet_res_connect=True, max_batch=32, **ignored_init_modes):
+                 unet_res_connect=True, max_batch=32, precision=None, **ignored_init_modes):
+        """`precision` (not a reference argument): "bf16" (default; env PD_PRECISION overrides the default) or "tf32" -
+        the operand precision of the tensor-core GEMMs, see pd_unet_set_precision in include/prediff_b200.h."""
         super().__init__()
+        import os
+        precision = precision or os.environ.get("PD_PRECISION", "bf16")
+        if precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
+        self.precision = precision
         T_in, H, W, C = input_shape
         T_out, H2, W2, C2 = target_shape
         assert (H, W, C) == (H2, W2, C2)
@@ -109,6 +116,7 @@ class CuboidTransformerUNet(nn.Module):
         build_param_tree(self, unet_param_spec(self.cfg), bufs)
         self._handle = None
         self._dirty = True
+        self.register_load_state_dict_post_hook(type(self)._mark_dirty)
 
     # ---- shape properties of the reference class (cuboid_transformer_unet.py:377-404) -------------------------
     @property
@@ -154,13 +162,15 @@ class CuboidTransformerUNet(nn.Module):
             t = p.detach().contiguous().float()
             shape = (ctypes.c_int64 * t.dim())(*t.shape)
             L.check(lib.pd_unet_load_weight(h, name.encode(), L.ptr(t), shape, t.dim()))
+        L.check(lib.pd_unet_set_precision(h, 1 if self.precision == "tf32" else 0))
         L.check(lib.pd_unet_finalize(h))
         self._dirty = False
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        r = super().load_state_dict(state_dict, strict=strict, **kw)
+    def _mark_dirty(self, *unused):
+        """Parameters changed: the packed CUDA copies are stale. Registered as a load_state_dict post-hook, which torch
+        runs for this module also when a PARENT's load_state_dict recurses through it (nn.Module.load_state_dict never
+        calls a child's overridden load_state_dict)."""
         self._dirty = True
-        return r
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)

@@ -40,6 +40,7 @@ class AutoencoderKL(nn.Module):
         build_param_tree(self, vae_param_spec(self.cfg))
         self._handle = None
         self._dirty = True
+        self.register_load_state_dict_post_hook(type(self)._mark_dirty)
 
     def _ensure_handle(self):
         if self._handle is None:
@@ -62,10 +63,11 @@ class AutoencoderKL(nn.Module):
         L.check(lib.pd_vae_finalize(h))
         self._dirty = False
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        r = super().load_state_dict(state_dict, strict=strict, **kw)
+    def _mark_dirty(self, *unused):
+        """Parameters changed: the packed CUDA copies are stale. Registered as a load_state_dict post-hook, which torch
+        runs for this module also when a PARENT's load_state_dict recurses through it (nn.Module.load_state_dict never
+        calls a child's overridden load_state_dict)."""
         self._dirty = True
-        return r
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)
@@ -129,14 +131,20 @@ class AutoencoderKL(nn.Module):
         return reference_distribution_class()(self.encode_moments(x))
 
     @torch.no_grad()
-    def decode(self, z):
-        """z (N, latent, H/8, W/8) -> (N, 1, H, W) = Decoder(post_quant_conv(z)) (autoencoder_kl.py:86-113)."""
+    def decode(self, z, out=None):
+        """z (N, latent, H/8, W/8) -> (N, 1, H, W) = Decoder(post_quant_conv(z)) (autoencoder_kl.py:86-113).
+        `out` (optional, contiguous fp32 (N, 1, H, W)): the decoder's last kernel writes the frames there - e.g. this
+        rank's slice of the ensemble's all-gather buffer, so the collective needs no staging copy."""
         self._check(z)
         c = self.cfg
         N = z.shape[0]
         assert tuple(z.shape[1:]) == (c.latent_channels, c.h // 8, c.w // 8), f"z shape {tuple(z.shape)}"
         zl = z.permute(0, 2, 3, 1).contiguous().float()
-        out = torch.empty(N, 1, c.h, c.w, device=z.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(N, 1, c.h, c.w, device=z.device, dtype=torch.float32)
+        else:
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and \
+                tuple(out.shape) == (N, 1, c.h, c.w), f"decode(out=): bad buffer {tuple(out.shape)} {out.dtype}"
         with torch.cuda.device(z.device):
             for i in range(0, N, self.max_frames):
                 n = min(self.max_frames, N - i)

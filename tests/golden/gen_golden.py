@@ -511,6 +511,76 @@ def gen_loop_tiny():
 
 
 @torch.no_grad()
+def gen_loop_extra():
+    """Round-2 pins: (1) clip_denoised=True through the reference's p_sample / p_sample_loop (latent_diffusion.py:580-581),
+    tiny config, RNG injected; (2) the reference's own sample() at the SHIPPED sizes: 7 context frames 128x128 -> encode
+    -> 4 ancestral steps -> decode; (3) the same full-size encode / decode around the S6 50-step DDIM (reference UNet +
+    the reference's DDIM helpers), i.e. what `sample(sampler="ddim")` must reproduce end to end."""
+    import prediff.diffusion.latent_diffusion as LD
+    import prediff.diffusion.utils as U
+    out = {}
+    ucfg, vcfg = Wt.TINY_UNET, Wt.TINY_VAE
+    ldm = ref_ldm(ref_unet(ucfg), ref_vae(vcfg), ucfg, vcfg)
+    B, n_steps = 2, 4
+    zT = inp(777, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    cond = inp(778, B, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    noise = inp(779, n_steps, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    calls = {"k": 0, "noise": noise}
+
+    def fake_noise_like(shape, device):
+        k = calls["k"]
+        calls["k"] += 1
+        assert tuple(shape) == tuple(calls["noise"][k].shape)
+        return calls["noise"][k].clone()
+
+    orig = LD.noise_like
+    LD.noise_like = fake_noise_like
+    try:
+        t = torch.full((B,), 100, dtype=torch.long)
+        # t = 100 and a half-scale z_t: about a quarter of the z_0 estimate is clamped, the rest passes through
+        out["z_step100_clip"] = ldm.p_sample(zt=zT.clone() * 0.5, zc=cond, t=t, clip_denoised=True)
+        calls["k"] = 0
+        out["z_step100_clip_x0"] = ldm.p_sample(zt=zT.clone() * 0.5, zc=cond, t=t, clip_denoised=True, return_x0=True)[1]
+        calls["k"] = 0
+        ldm.clip_denoised = True
+        out["z0_clip"] = ldm.p_sample_loop(cond=cond, shape=tuple(zT.shape), x_T=zT.clone(), timesteps=n_steps)
+        ldm.clip_denoised = False
+        frac = ((out["z_step100_clip_x0"].abs() == 1.0).float().mean()).item()
+        print(f"loop_extra: clip_denoised clamps {100 * frac:.1f}% of the z_0 estimate at t=100")
+        # ---- shipped sizes, batch 1 ----
+        fu, fv = Wt.UNetConfig(), Wt.VAEConfig()
+        unet_f = ref_unet(fu)
+        ldm_f = ref_ldm(unet_f, ref_vae(fv), fu, fv)
+        y = inp(880, 1, fu.t_in, fv.h, fv.w, 1, uniform=True)
+        zT_f = inp(881, 1, fu.t_out, fu.h, fu.w, fu.c)
+        calls["noise"] = inp(882, n_steps, 1, fu.t_out, fu.h, fu.w, fu.c)
+        calls["k"] = 0
+        t0 = time.time()
+        out["full_sample_ddpm4"] = ldm_f.sample(cond={"y": y}, batch_size=1, x_T=zT_f.clone(), timesteps=n_steps)
+        zc = ldm_f.cond_stage_forward({"y": y})
+        out["full_zc"] = zc
+        print(f"loop_extra: full-size sample() with 4 ancestral steps: {time.time() - t0:.0f}s", flush=True)
+    finally:
+        LD.noise_like = orig
+    betas = U.make_beta_schedule("linear", 1000, linear_start=1e-4, linear_end=2e-2)
+    ac = np.cumprod(1.0 - betas, axis=0).astype(np.float32)
+    ts = U.make_ddim_timesteps("uniform", 50, 1000, verbose=False)
+    sig, a, ap = U.make_ddim_sampling_parameters(ac, ts, 0.0, verbose=False)
+    z = zT_f.clone()
+    t0 = time.time()
+    for k, i in enumerate(reversed(range(len(ts)))):
+        t = torch.full((1,), int(ts[i]), dtype=torch.long)
+        eps = unet_f(z, t, zc)
+        z0 = (z - float(np.sqrt(1.0 - a[i])) * eps) / float(np.sqrt(a[i]))
+        z = float(np.sqrt(ap[i])) * z0 + float(np.sqrt(1.0 - ap[i] - sig[i] ** 2)) * eps
+        if k % 10 == 0:
+            print(f"loop_extra: full ddim step {k + 1}/50 ({time.time() - t0:.0f}s)", flush=True)
+    out["full_ddim50_z0"] = z
+    out["full_sample_ddim50"] = ldm_f.decode_first_stage(z)
+    save("loop_extra", **out)
+
+
+@torch.no_grad()
 def gen_ddim(tag, cfg, B, n_steps):
     """S6 DDIM (eta = 0) with the reference UNet module and the reference's DDIM helper functions."""
     import prediff.diffusion.utils as U
@@ -571,5 +641,7 @@ if __name__ == "__main__":
         gen_ema()
     if "helpers" in todo:
         gen_helpers()
+    if "loop_extra" in todo:
+        gen_loop_extra()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

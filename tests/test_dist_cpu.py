@@ -34,6 +34,16 @@ def _worker(rank, world, port, G, q):
     z = torch.randn(G, 6, 5, generator=g)   # global z_T from ONE seed, identical on every rank
     c = torch.randn(G, 7, 5, generator=g)
     out = sample_ensemble(_fake_chain, z, c)
+    if G % world == 0:   # in-place variant: the chain writes into this rank's slice of a persistent buffer
+        buf = torch.full((G, 3, 5), float("nan"))
+
+        def chain_out(zz, cc, out):
+            out.copy_(_fake_chain(zz, cc))
+            return out
+
+        for _ in range(2):   # the buffer is reused across calls
+            got = sample_ensemble(chain_out, z, c, gathered=buf)
+            assert got.data_ptr() == buf.data_ptr() and torch.equal(got, out)
     if rank == 0:
         q.put(out)
     dist.destroy_process_group()

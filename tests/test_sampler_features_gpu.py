@@ -45,9 +45,9 @@ def test_default_noise_is_the_reference_randn_stream(ldm):
     for i in reversed(range(5)):
         img = ldm.p_sample(zt=img, zc=cond, t=torch.full((2,), i, device="cuda"))
     assert torch.equal(x_T2, x_T)
-    # same noise, same math; the torch elementwise update rounds differently from the fused kernel and the bf16 UNet
-    # amplifies that over 5 steps
-    assert torch.allclose(img, a, rtol=0, atol=3e-3 * a.abs().max().item())
+    # same noise, same kernels: p_sample runs through pd_sample_step_ddpm (UNet + the fused update), so the host-driven
+    # route reproduces the device-resident loop bit for bit
+    assert torch.equal(img, a)
 
 
 def test_start_T_callbacks_and_intermediates(ldm):
