@@ -11,6 +11,11 @@ GPU per step; `value` = sample-steps/s over all GPUs with z_T / context latents 
 metric through LatentDiffusion.sample() from pinned host frames to pinned host forecasts (VAE encode + loop +
 VAE decode + the final all-gather + both copies inside the timed region). Weights are seeded random (no
 checkpoints offline), data synthetic. Prints ONE JSON line on rank 0.
+
+The headline arm runs bf16 tensor-core operands (tolerance: rel-RMS 7e-3 per step / 8e-3 after the loop vs the fp32
+reference, tests/test_*_gpu.py); `tf32_arm` in the same line is the like-for-like arm for the reference's own TF32 GPU
+arithmetic (kind::tf32 operands, rel-RMS <= 2e-3, tests/test_tf32_gpu.py), measured beside it and held against a
+measured TF32 peak (profiles/tf32_peak_r02.json). `single_step_b1` is BASELINE.json configs[1].
 """
 import ctypes
 import argparse
@@ -49,35 +54,54 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons through NVML (no process forks) at 1 Hz while a timed region runs. Only
+    local rank 0 samples: in round 1 every rank forked nvidia-smi 5 times a second during the kernel-only leg, which
+    alone cost 2.8 % at 8 GPUs."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.index, self.stop_flag, self.rows, self.enabled, self.h = index, threading.Event(), [], enabled, None
+        if enabled:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nv = pynvml
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                self.h = None
+
+    def sample(self):
+        try:
+            mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.rows.append((mhz, mask))
+        except Exception:
+            pass
 
     def run(self):
+        if self.h is None:
+            return
         while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+            self.sample()
+            self.stop_flag.wait(1.0)
 
     def summary(self):
         self.stop_flag.set()
-        self.join(timeout=3)
+        if self.is_alive():
+            self.join(timeout=3)
+        if self.h is not None:
+            self.sample()
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable" if self.enabled else "sampled on local rank 0 only"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for n, bit in self.REASONS if any(r[1] & bit for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows),
+                "how": "NVML, 1 Hz, local rank 0, during the kernel-only and end-to-end timed regions"}
 
 
 def run_reference_arm(args):
@@ -112,7 +136,8 @@ def run_reference_arm(args):
         one(k)
     dt = time.perf_counter() - t0
     value = B * args.steps / dt
-    sample = f"{args.steps} of the {args.ddim_steps} denoise steps of one batch-{B} DDIM loop (UNet forward + DDIM update)"
+    sample = (f"{args.steps} of the {args.ddim_steps} denoise steps of one batch-{B} DDIM loop (UNet forward + DDIM update); the "
+              "VAE encode / decode that the GPU arm's e2e includes are NOT timed here, so the e2e ratio is conservative")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -151,10 +176,10 @@ CUBOID_GFLOP_PER_SAMPLE_STEP = 252.9   # StackCuboidSelfAttentionBlock incl. FFN
 
 
 def graph_trace(unet, B, x, t, cond, out):
-    """{site label: (launches, us)} of one UNet forward replayed as a CUDA graph with a stamp kernel after every launch."""
+    """One UNet forward replayed as a CUDA graph with a %globaltimer stamp kernel after every launch.
+    Returns ({site: [launches, us, flops]}, stamp_slot_us): us = raw stamp-to-stamp interval minus the stamp slot (the
+    smallest interval seen: the stamp kernel's own node, ~1.8 us); flops = algorithmic FLOPs of the site's launches."""
     import collections
-    import numpy as np
-    import torch
     from prediff_b200 import _lib as L
     slots = 2048
     ns = torch.zeros(slots, device=x.device, dtype=torch.int64)
@@ -176,14 +201,60 @@ def graph_trace(unet, B, x, t, cond, out):
         g.replay()
     torch.cuda.synchronize()
     lab = labels.value.decode().split("\n")[:n[0]]
+    fl = (ctypes.c_double * slots)()
+    nf = L.lib().pd_unet_step_flops(unet.handle, B, fl, slots)
+    if nf < 0:
+        L.check(nf)
     d = np.diff(ns.cpu().numpy()[:n[0] + 1]).astype(np.float64) * 1e-3
     slot = float(d.min())
     agg = collections.OrderedDict()
-    for name, us in zip(lab, d):
-        a = agg.setdefault(name, [0, 0.0])
+    for i, (name, us) in enumerate(zip(lab, d)):
+        a = agg.setdefault(name, [0, 0.0, 0.0])
         a[0] += 1
         a[1] += us - slot
-    return agg
+        a[2] += fl[i] if i < nf else 0.0
+    return agg, slot
+
+
+def load_json(rel):
+    path = os.path.join(ROOT, rel)
+    return json.load(open(path)) if os.path.exists(path) else None
+
+
+def build_unet(ucfg, B, precision):
+    from prediff_b200.unet import CuboidTransformerUNet
+    unet = CuboidTransformerUNet([ucfg.t_in, ucfg.h, ucfg.w, ucfg.c], [ucfg.t_out, ucfg.h, ucfg.w, ucfg.c],
+                                 base_units=ucfg.base_units, depth=list(ucfg.depth), num_heads=ucfg.num_heads,
+                                 block_attn_patterns="axial", max_batch=B, precision=precision)
+    unet.load_state_dict({k: torch.from_numpy(v) for k, v in
+                          Wt.seeded_state_dict(Wt.unet_param_spec(ucfg), UNET_SEED).items()}, strict=False)
+    return unet
+
+
+def single_step_latency(unet, ucfg, dev, iters=200, warm=20):
+    """BASELINE.json configs[1]: one denoise step, batch 1, CUDA-graph replay, CUDA events."""
+    x = torch.from_numpy(np_inp(1234, 1, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)).to(dev)
+    cond = torch.from_numpy(np_inp(1235, 1, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)).to(dev)
+    t = torch.full((1,), 500, device=dev, dtype=torch.int64)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        unet(x, t, cond)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            unet(x, t, cond)
+        for _ in range(warm):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"workload": "single CuboidTransformerUNet denoise step, batch 1, 13x16x16 latent (BASELINE.json configs[1])",
+            "iters": iters, "warmup": warm, "ms": ms, "value": 1e3 / ms, "unit": UNIT,
+            "tflops": GFLOP_PER_SAMPLE_STEP / ms, "timing": "CUDA-graph replay of pd_unet_forward, CUDA events"}
 
 
 def main():
@@ -196,6 +267,8 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ka", action="store_true", help="skip the knowledge-alignment (configs[3]) leg")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the TF32-class arm")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs[1] latency and the per-kernel trace")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -203,10 +276,7 @@ def main():
     import torch.distributed as dist
     from prediff_b200 import _lib as L
     from prediff_b200.diffusion import LatentDiffusion
-    from prediff_b200.dist import sample_ensemble
-    from prediff_b200.unet import CuboidTransformerUNet
     from prediff_b200.vae import AutoencoderKL
-    import ctypes
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,11 +293,7 @@ def main():
     K, B, S = args.steps, args.batch, args.ddim_steps
 
     ucfg, vcfg = Wt.UNetConfig(), Wt.VAEConfig()
-    unet = CuboidTransformerUNet([ucfg.t_in, ucfg.h, ucfg.w, ucfg.c], [ucfg.t_out, ucfg.h, ucfg.w, ucfg.c],
-                                 base_units=ucfg.base_units, depth=list(ucfg.depth), num_heads=ucfg.num_heads,
-                                 block_attn_patterns="axial", max_batch=B)
-    unet.load_state_dict({k: torch.from_numpy(v) for k, v in
-                          Wt.seeded_state_dict(Wt.unet_param_spec(ucfg), UNET_SEED).items()}, strict=False)
+    unet = build_unet(ucfg, B, "bf16")
     vae = AutoencoderKL(block_out_channels=vcfg.block_out_channels, layers_per_block=vcfg.layers_per_block,
                         latent_channels=vcfg.latent_channels, sample_size=(vcfg.h, vcfg.w), max_frames=B * ucfg.t_in)
     vae.load_state_dict({k: torch.from_numpy(v) for k, v in
@@ -237,8 +303,10 @@ def main():
 
     # ---- kernel-only leg: latents resident in HBM -----------------------------------------------------------
     G = B * world                                                   # global ensemble, sliced by rank
-    zT = torch.from_numpy(np_inp(4242, G, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c))[rank * B:(rank + 1) * B].to(dev)
-    zc = torch.from_numpy(np_inp(4243, G, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c))[rank * B:(rank + 1) * B].to(dev)
+    lo, hi = rank * B, (rank + 1) * B
+    zT_all = torch.from_numpy(np_inp(4242, G, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c))
+    zT = zT_all[lo:hi].to(dev)
+    zc = torch.from_numpy(np_inp(4243, G, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c))[lo:hi].to(dev)
     shape = tuple(zT.shape)
 
     def barrier():
@@ -246,40 +314,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_loops(model, n_loops, **kw):
+        """n_loops back-to-back device-resident loops, CUDA events on the launching stream, max over ranks (ms)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_loops):
+            model.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0, **kw)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
     for _ in range(W):
         ldm.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0)
-    barrier()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=(local_rank == 0))
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        z0 = ldm.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0)
-    e1.record()
-    barrier()
-    clk = clocks.summary()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = ms.item()
+    ms = timed_loops(ldm, K)
     value = world * B * S * K / (ms * 1e-3)
 
     # ---- end-to-end leg: pinned host frames -> sample() -> pinned host forecasts ----------------------------
-    y_host = torch.from_numpy(np_inp(780, G, ucfg.t_in, vcfg.h, vcfg.w, 1, uniform=True))[rank * B:(rank + 1) * B].pin_memory()
+    # The ensemble's gathered frames live in ONE persistent device buffer: the VAE decoder's last kernel writes this rank's
+    # forecasts straight into its slice (sample(out=...)) and the path's single collective - the all-gather of decoded
+    # frames (SURVEY.md 8e) - runs in place on it: no allocation, no staging copy.
+    y_all = torch.from_numpy(np_inp(780, G, ucfg.t_in, vcfg.h, vcfg.w, 1, uniform=True))
+    y_host = y_all[lo:hi].clone().pin_memory()
     zT_host = zT.cpu().pin_memory()
     out_host = torch.empty(G, ucfg.t_out, vcfg.h, vcfg.w, 1).pin_memory()
+    gathered = torch.empty(G, ucfg.t_out, vcfg.h, vcfg.w, 1, device=dev)
+    mine = gathered[lo:hi]
 
     def e2e_step():
         y = y_host.to(dev, non_blocking=True)
         zt = zT_host.to(dev, non_blocking=True)
-        frames = ldm.sample(cond={"y": y}, batch_size=B, x_T=zt, sampler="ddim", ddim_steps=S, ddim_eta=0.0)
-        if world > 1:   # the path's one collective: all-gather of the decoded frames
-            full = torch.empty((G,) + tuple(frames.shape[1:]), device=dev)
-            dist.all_gather_into_tensor(full, frames.contiguous())
-        else:
-            full = frames
-        out_host.copy_(full, non_blocking=True)
-        return full
+        ldm.sample(cond={"y": y}, batch_size=B, x_T=zt, sampler="ddim", ddim_steps=S, ddim_eta=0.0, out=mine)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, mine)
+        out_host.copy_(gathered, non_blocking=True)
 
     for _ in range(W):
         e2e_step()
@@ -290,6 +363,7 @@ def main():
         e2e_step()
     e1.record()
     barrier()
+    clk = clocks.summary()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
@@ -297,6 +371,17 @@ def main():
     e2e_value = world * B * S * K / (ms_e2e * 1e-3)
     h2d = y_host.numel() * 4 + zT_host.numel() * 4
     d2h = out_host.numel() * 4
+
+    # ---- shard invariance: the gathered (G, 6, 128, 128, 1) frames of the N-GPU run
+    # equal, bit for bit, what ONE GPU computes for the same global seed (rank 0 recomputes every shard locally) ------
+    shard_invariant = None
+    if world > 1 and rank == 0:
+        ref = torch.empty_like(gathered)
+        for r in range(world):
+            ldm.sample(cond={"y": y_all[r * B:(r + 1) * B].to(dev)}, batch_size=B, x_T=zT_all[r * B:(r + 1) * B].to(dev),
+                       sampler="ddim", ddim_steps=S, ddim_eta=0.0, out=ref[r * B:(r + 1) * B])
+        torch.cuda.synchronize()
+        shard_invariant = bool(torch.equal(ref, gathered)) and bool(torch.equal(out_host, ref.cpu()))
 
     # ---- BASELINE.json configs[3]: the same loop with knowledge-alignment guidance (KA forward + backward each step) ----
     ka_line = None
@@ -315,51 +400,57 @@ def main():
         Kk = max(2, min(K, 5))
         for _ in range(2):
             ldm.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0, use_alignment=True, alignment_kwargs=kw)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(Kk):
-            ldm.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0, use_alignment=True, alignment_kwargs=kw)
-        e1.record()
-        barrier()
-        ms_ka = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms_ka, op=dist.ReduceOp.MAX)
+        ms_ka = timed_loops(ldm, Kk, use_alignment=True, alignment_kwargs=kw)
         nf, nb = ctypes.c_int(), ctypes.c_int()
         L.check(L.lib().pd_ka_kernels(al.model.handle, B, ctypes.byref(nf), ctypes.byref(nb)))
         ka_line = {"workload": f"PreDiff-KA: {S}-step DDIM with knowledge-alignment guidance, batch={B} per GPU "
                                "(BASELINE.json configs[3]); KA forward + input-gradient backward every step, run on a "
                                "second stream beside the UNet",
-                   "value": world * B * S * Kk / (ms_ka.item() * 1e-3), "unit": UNIT, "loops": Kk,
-                   "ms_per_step": ms_ka.item() / Kk, "ka_kernels_per_step": nf.value + nb.value,
+                   "value": world * B * S * Kk / (ms_ka * 1e-3), "unit": UNIT, "loops": Kk,
+                   "ms_per_step": ms_ka / Kk, "ka_kernels_per_step": nf.value + nb.value,
                    "gflop_per_sample_step": GFLOP_PER_SAMPLE_STEP + 22.95}
         ldm.set_alignment(None)
 
-    # ---- per-kernel-class device time of one UNet forward (events around every launch) -----------------------
-    stats = (ctypes.c_double * 5)()
-    t = torch.full((B,), 981, device=dev, dtype=torch.int64)
-    eps = torch.empty_like(zT)
-    for _ in range(2):
-        L.check(L.lib().pd_unet_profile_forward(unet.handle, L.ptr(zT), L.ptr(t), L.ptr(zc), L.ptr(eps), B,
-                                                L.stream_ptr(), stats))
-    gemm_ms, n_gemm, other_ms, n_other, gemm_flops = list(stats)
-    # the same forward as a CUDA-graph replay with a %globaltimer stamp after every launch (tools/trace_unet.py --graph):
-    # launches are issued by the GPU front end, so kernels shorter than the ~5 us host launch cost are timed correctly
-    trace = graph_trace(unet, B, zT, t, zc, eps)
-    gemm_sites = ("conv1", "conv2", "qkv", "proj", "ffn1", "ffn2", "proj_ffn_fused", "ffn_fused", "skip", "up.conv",
-                  "down.reduction", "final.proj")
-    tr_gemm = [v for k, v in trace.items() if k.split(".")[-1] in gemm_sites or k in gemm_sites]
-    tr_other = [v for k, v in trace.items() if not (k.split(".")[-1] in gemm_sites or k in gemm_sites)]
-    tr_stack = [v for k, v in trace.items() if ".stack." in k]
-    gemm_ms = sum(v[1] for v in tr_gemm) * 1e-3
-    other_ms = sum(v[1] for v in tr_other) * 1e-3
-    n_gemm, n_other = sum(v[0] for v in tr_gemm), sum(v[0] for v in tr_other if v[1] > 0)
-    stack_ms = sum(v[1] for v in tr_stack) * 1e-3
+    # ---- TF32-class arm: the same loop with kind::tf32 operands (the reference's own GPU arithmetic) --------------
+    tf32_line, unet_tf32 = None, None
+    if not args.no_tf32:
+        unet_tf32 = build_unet(ucfg, B, "tf32")
+        ldm_tf32 = LatentDiffusion(torch_nn_module=unet_tf32, latent_shape=(ucfg.t_out, ucfg.h, ucfg.w, ucfg.c))
+        Kt = max(2, min(K, 5))
+        for _ in range(3):
+            ldm_tf32.ddim_sample_loop(cond=zc, shape=shape, x_T=zT, ddim_steps=S, eta=0.0)
+        ms_t = timed_loops(ldm_tf32, Kt)
+        v_t = world * B * S * Kt / (ms_t * 1e-3)
+        tp = load_json("profiles/tf32_peak_r02.json")
+        tf32_line = {"value": v_t, "unit": UNIT, "dtype": "tf32", "loops": Kt, "ms_per_step": ms_t / Kt,
+                     "numerics": "tcgen05.mma kind::tf32 on fp32 storage rounded to tf32, fp32 accumulate / residual stream / "
+                                 "attention core; rel-RMS <= 2e-3 per UNet step and after the 50-step loop vs the fp32 "
+                                 "reference (tests/test_tf32_gpu.py) - like-for-like with the reference's TF32 runs",
+                     "roofline": None if tp is None else {
+                         "bound": "tensor", "achieved": v_t / world * GFLOP_PER_SAMPLE_STEP * 1e-3,
+                         "peak": tp["tf32_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": v_t / world * GFLOP_PER_SAMPLE_STEP * 1e-3 / tp["tf32_tflops_sustained"],
+                         "peak_source": "measured sustained cuBLAS TF32 8192^3 on this pool (profiles/tf32_peak_r02.json; "
+                                        f"burst {tp['tf32_tflops']:.0f})"}}
+
+    # ---- per-launch device time of one UNet forward + BASELINE.json configs[1] -----------------------------------
     nk = ctypes.c_int()
     n_sub = L.lib().pd_sampler_sub_batches(ldm._sampler, B)   # concurrent sub-batches inside the loop
     L.check(L.lib().pd_unet_kernels_per_forward(unet.handle, B // n_sub, ctypes.byref(nk)))
     launches_per_loop_step = n_sub * (nk.value + 1) + 1   # per sub-batch: UNet + sampler_update; + advance_step
     gpu_launches = launches_per_loop_step * S * K
+    extras = {}
+    if not args.no_extras:
+        t = torch.full((B,), 981, device=dev, dtype=torch.int64)
+        eps = torch.empty_like(zT)
+        # a CUDA-graph replay of one forward with a %globaltimer stamp after every launch (tools/trace_unet.py --graph):
+        # launches are issued by the GPU front end, so kernels shorter than the ~5 us host launch cost are timed correctly
+        trace, slot = graph_trace(unet, B, zT, t, zc, eps)
+        extras["trace"] = (trace, slot)
+        if rank == 0 and world == 1:
+            extras["b1"] = single_step_latency(unet, ucfg, dev)
+            if unet_tf32 is not None:
+                extras["b1_tf32"] = single_step_latency(unet_tf32, ucfg, dev, iters=100)
 
     if rank != 0:
         if world > 1:
@@ -367,46 +458,94 @@ def main():
         return
     peaks = measured_peaks()
     achieved = value / world * GFLOP_PER_SAMPLE_STEP * 1e-3            # TFLOP/s per GPU, algorithmic FLOPs
-    traffic = None
-    prof_json = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof_json):
-        traffic = json.load(open(prof_json)).get("gemm_tc_kernel_dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic latents / frames (numpy PCG64 seeds), seeded random weights of the shipped SEVIR-LR architecture",
         "config": {"workload": f"SEVIR-LR 50-step DDIM (eta=0) p_sample_loop, batch={B} per GPU (BASELINE.json configs[2])",
                    "step": f"one {S}-step DDIM loop over a batch of {B} forecasts per GPU = {B * S} UNet evaluations",
-                   "ensemble": f"{G} members, {B} per rank, no data-path collective; one all-gather of decoded frames in e2e",
+                   "ensemble": f"{G} members, {B} per rank, no data-path collective; one in-place all-gather of decoded frames in e2e",
                    "l2": "inputs exceed L2: 274 MB of bf16 UNet weights are re-streamed every denoise step (L2 = 126 MB)",
-                   "numerics": "bf16 tensor-core operands, fp32 accumulate, fp32 residual stream", "cuda_graph": True,
-                   "sub_batches": n_sub},
+                   "numerics": "bf16 tensor-core operands, fp32 accumulate, fp32 residual stream (rel-RMS 7e-3 per step vs the "
+                               "fp32 reference); the like-for-like TF32 arm is in tf32_arm",
+                   "cuda_graph": f"the whole {S}-step loop is one graph launch", "sub_batches": n_sub},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K, "api": "LatentDiffusion.sample(cond={'y': frames}, sampler='ddim')"},
+                "ms_per_step": ms_e2e / K, "api": "LatentDiffusion.sample(cond={'y': frames}, sampler='ddim', out=<slice of the "
+                "gathered buffer>) + in-place all_gather_into_tensor"},
         "gpu_launches": gpu_launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tensor_tflops"], "traffic": traffic,
+                     "frac": achieved / peaks["tensor_tflops"], "traffic": None,
                      "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
-                     "definition": "sample-steps/s per GPU x 653.43 GFLOP (SURVEY.md 8d) / sustained bf16 peak",
-                     "dominant_kernel": {"name": "tcgen05 implicit-GEMM family: gemm_tc_kernel, gemm_tc_persistent_kernel, conv_streamk_kernel, ffn_fused_kernel (conv3d/conv2d/linear)",
-                                         "launches_per_forward": int(n_gemm), "ms_per_forward": gemm_ms,
-                                         "avg_launch_us": 1e3 * gemm_ms / max(n_gemm, 1),
-                                         "tflops": gemm_flops / (gemm_ms * 1e-3) * 1e-12,
-                                         "frac_of_peak": gemm_flops / (gemm_ms * 1e-3) * 1e-12 / peaks["tensor_tflops"],
-                                         "share_of_forward": gemm_ms / (gemm_ms + other_ms)},
-                     "other_kernels": {"launches_per_forward": int(n_other), "ms_per_forward": other_ms},
-                     "kernel_timing": f"per-launch globaltimer stamps inside a CUDA-graph replay of one batch-{B} forward "
-                                      "(one stamp-kernel slot subtracted per launch)",
-                     # north_star's "cuboid-attention roofline": the StackCuboidSelfAttentionBlock subset (LayerNorm, QKV,
-                     # axial attention, projection, FFN of all 24 + 24 layers = 252.9 of the 653.43 GFLOP),
-                     # timed in place inside the same replay
-                     "cuboid_attention_blocks": {
-                         "gflop_per_sample_step": CUBOID_GFLOP_PER_SAMPLE_STEP, "ms_per_forward": stack_ms,
-                         "tflops": CUBOID_GFLOP_PER_SAMPLE_STEP * B / stack_ms,   # GFLOP / ms = TFLOP/s
-                         "frac_of_peak": CUBOID_GFLOP_PER_SAMPLE_STEP * B / stack_ms / peaks["tensor_tflops"],
-                         "share_of_forward": stack_ms / (gemm_ms + other_ms)}},
+                     "definition": "sample-steps/s per GPU x 653.43 GFLOP (SURVEY.md 8d) / sustained bf16 peak"},
     }
+    if shard_invariant is not None:
+        line["shard_invariant"] = shard_invariant
+    if "trace" in extras:
+        trace, slot = extras["trace"]
+        gemm_sites = ("conv1", "conv2", "qkv", "proj", "ffn1", "ffn2", "proj_ffn_fused", "ffn_fused", "skip", "up.conv",
+                      "down.reduction", "final.proj")
+        is_gemm = lambda k: k.split(".")[-1] in gemm_sites or k in gemm_sites   # noqa: E731
+        n_launch = sum(v[0] for v in trace.values())
+        kern_ms = sum(v[1] for v in trace.values()) * 1e-3
+        step_ms = ms / K / S                                  # one denoise step inside the timed loop
+        # what the trace's slot subtraction hides: per-node dispatch overhead inside the loop's graph
+        overhead_ms = max(step_ms - kern_ms, 0.0)
+        per_launch_overhead_us = 1e3 * overhead_ms / max(n_launch, 1)
+        dram = load_json("profiles/kernel_dram_r02.json") or {}
+        kernels = []
+        for name, (cnt, us, fl) in sorted(trace.items(), key=lambda kv: -kv[1][1]):
+            if cnt == 0 or us <= 0:
+                continue
+            ent = {"site": name, "launches": cnt, "avg_us": us / cnt, "share_of_step": us * 1e-3 / step_ms}
+            if fl > 0:
+                ent["gflop_per_launch"] = fl / cnt * 1e-9
+                ent["tflops"] = fl / (us * 1e-6) * 1e-12
+                ent["frac_of_peak"] = ent["tflops"] / peaks["tensor_tflops"]
+                ent["frac_incl_launch_overhead"] = fl / ((us + cnt * per_launch_overhead_us) * 1e-6) * 1e-12 / peaks["tensor_tflops"]
+            if name in dram:
+                ent["dram_bytes_per_launch"] = dram[name].get("dram_bytes")
+                ent["algorithmic_bytes_per_launch"] = dram[name].get("algorithmic_bytes")
+                ent["kernel"] = dram[name].get("kernel")
+            kernels.append(ent)
+        g_us = sum(v[1] for k, v in trace.items() if is_gemm(k))
+        g_fl = sum(v[2] for k, v in trace.items() if is_gemm(k))
+        g_n = sum(v[0] for k, v in trace.items() if is_gemm(k))
+        stack_ms = sum(v[1] for k, v in trace.items() if ".stack." in k) * 1e-3
+        top = kernels[0] if kernels else None
+        line["roofline"].update({
+            "traffic": top.get("dram_bytes_per_launch") if top else None,
+            "traffic_kernel": top["site"] if top else None,
+            "kernel_timing": f"per-launch %globaltimer stamps inside a CUDA-graph replay of one batch-{B} forward; avg_us = "
+                             f"stamp interval - the stamp kernel's own slot ({slot:.2f} us); launch overhead reported separately",
+            "launch_overhead": {"launches_per_step": n_launch, "kernel_ms_per_step": kern_ms, "in_loop_step_ms": step_ms,
+                                "overhead_ms_per_step": overhead_ms, "per_launch_us": per_launch_overhead_us,
+                                "share_of_step": overhead_ms / step_ms},
+            "dominant_kernel": {"name": "tcgen05 implicit-GEMM family: gemm_tc_kernel, gemm_tc_persistent_kernel, "
+                                        "conv_streamk_kernel, ffn_fused_kernel (conv3d/conv2d/linear)",
+                                "launches_per_forward": int(g_n), "ms_per_forward": g_us * 1e-3,
+                                "avg_launch_us": g_us / max(g_n, 1), "tflops": g_fl / (g_us * 1e-6) * 1e-12,
+                                "frac_of_peak": g_fl / (g_us * 1e-6) * 1e-12 / peaks["tensor_tflops"],
+                                "frac_incl_launch_overhead": g_fl / ((g_us + g_n * per_launch_overhead_us) * 1e-6) * 1e-12
+                                / peaks["tensor_tflops"],
+                                "share_of_step": g_us * 1e-3 / step_ms},
+            "kernels": kernels[:16],
+            # north_star's "cuboid-attention roofline": the StackCuboidSelfAttentionBlock subset (LayerNorm, QKV, axial
+            # attention, projection, FFN of all 24 + 24 layers = 252.9 of the 653.43 GFLOP), in place
+            "cuboid_attention_blocks": {
+                "gflop_per_sample_step": CUBOID_GFLOP_PER_SAMPLE_STEP, "ms_per_forward": stack_ms,
+                "tflops": CUBOID_GFLOP_PER_SAMPLE_STEP * B / stack_ms,
+                "frac_of_peak": CUBOID_GFLOP_PER_SAMPLE_STEP * B / stack_ms / peaks["tensor_tflops"],
+                "share_of_step": stack_ms / step_ms}})
+    if "b1" in extras:
+        b1 = extras["b1"]
+        b1["frac_of_peak"] = b1["tflops"] / peaks["tensor_tflops"]
+        if "b1_tf32" in extras:
+            b1["tf32"] = {k: extras["b1_tf32"][k] for k in ("ms", "value", "tflops", "iters")}
+        line["single_step_b1"] = b1
+    if tf32_line is not None:
+        tf32_line["vs_bf16_arm"] = tf32_line["value"] / value
+        line["tf32_arm"] = tf32_line
     if ka_line is not None:
         ka_line["slowdown_vs_unguided"] = (ka_line["ms_per_step"]) / (ms / K)
         line["knowledge_alignment"] = ka_line

@@ -291,6 +291,13 @@ int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t s
 int pd_op_cuboid_attention(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W, int C,
                            int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                            int padding_type, void* stream);
+/* Same with the kernel chosen explicitly: impl 0 = as the models choose, 1 = warp-level mma.sync kernel (any head dim /
+ * volume), 2 = tcgen05 tile kernel (csrc/attention_tc.cu: 128-query tile per (cuboid, head, sample), S and O accumulators in
+ * TMEM, K/V chunks of 128 keys through a swizzled shared-memory ring, softmax warps reading their row with tcgen05.ld;
+ * head dim 64 or 128). The models use it for cuboid volumes >= 128 (video_swin_PxM, divided_st, full). */
+int pd_op_cuboid_attention_impl(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W,
+                                int C, int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                                int padding_type, int impl, void* stream);
 /* q_sample (latent_diffusion.py:489-492): out = sqrt_alphas_cumprod[t_b] x_start + sqrt_one_minus_alphas_cumprod[t_b]
  * noise, bit-exact vs the reference's fp32 tensor expression; tables fp32 [T] and t int64 [B] on the device. */
 int pd_op_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_alphas_cumprod,

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprediff_b200.so")
+# PD_LIB_PATH: another build of the same library (A/B measurements of two builds on one box, tools/ab.sh)
+LIB_PATH = os.environ.get("PD_LIB_PATH") or os.path.join(_HERE, "libprediff_b200.so")
 
 _lib = None
 

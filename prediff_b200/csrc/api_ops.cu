@@ -221,7 +221,15 @@ int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t s
 int pd_op_cuboid_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
                            const int32_t size[3], const int32_t strategy[3], const int32_t shift[3], int padding_type,
                            void* stream) {
+    return pd_op_cuboid_attention_impl(qkv, bias_table, out, B, T, H, W, C, heads, size, strategy, shift, padding_type, 0,
+                                       stream);
+}
+
+int pd_op_cuboid_attention_impl(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C,
+                                int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                                int padding_type, int impl, void* stream) {
     PD_TRY(gemm_init());
+    PD_CHECK(impl >= 0 && impl <= 2, PD_ERR_ARG, "pd_op_cuboid_attention_impl: impl %d (0 auto, 1 mma.sync, 2 tcgen05)", impl);
     CuboidLayerSpec sp;
     for (int a = 0; a < 3; ++a) {
         sp.size[a] = size[a];
@@ -233,7 +241,7 @@ int pd_op_cuboid_attention(const void* qkv, const float* bias_table, void* out, 
     CuboidTablesDev d;
     PD_TRY(d.upload(g));
     PD_TRY(cuboid_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T * H * W, C, heads, d.dev,
-                            S(stream)));
+                            S(stream), impl));
     PD_CUDA(cudaStreamSynchronize(S(stream)));   // the tables are freed on return
     return PD_OK;
 }

@@ -671,9 +671,11 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
 }
 
 int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
-                     const CuboidDev& g, cudaStream_t st) {
+                     const CuboidDev& g, cudaStream_t st, int impl) {
     PD_CHECK(C % heads == 0, PD_ERR_SHAPE, "cuboid_attention: C=%d heads=%d", C, heads);
     const int hd = C / heads;
+    if (impl == 2 || (impl == 0 && cuboid_attention_tc_eligible(hd, g.volume)))
+        return cuboid_attention_tc(qkv, bias_table, out, B, N, C, heads, g, st);
     PD_CHECK(g.num_cuboids >= 1 && g.num_cuboids <= 65535 && B * heads <= 65535, PD_ERR_SHAPE,
              "cuboid_attention: %d cuboids, %d sample-heads exceed the grid limits", g.num_cuboids, B * heads);
     dim3 grid(ceil_div(g.volume, kQTile), g.num_cuboids, B * heads);

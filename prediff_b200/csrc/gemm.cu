@@ -8,6 +8,7 @@
 #include "ptx.cuh"
 #include <cudaTypedefs.h>
 #include <cstdlib>
+#include <type_traits>
 
 namespace pd {
 
@@ -155,24 +156,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const bool tf32 = p.tf32 != 0;   // 4 MMAs per 128-byte k-block either way: 16 bf16 or 8 tf32 per instruction
-            const uint32_t idesc = tf32 ? ptx::make_idesc_tf32(kGemmBlockM, BN) : ptx::make_idesc_bf16(kGemmBlockM, BN);
-            for (int it = 0; it < num_k; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                ptx::mbar_wait(&full_bar[s], ph);
-                ptx::tc_fence_after();
-                if (it == 0) PD_STAMP(2);
-                const uint32_t a_addr = ptx::smem_u32(smem + s * C::kStageBytes);
-                const uint32_t b_addr = a_addr + kABytes;
+            // 4 MMAs per 128-byte k-block either way: 16 bf16 or 8 tf32 per instruction
+            auto issue = [&](auto tf32_tag) {
+                constexpr bool TF32 = decltype(tf32_tag)::value;
+                constexpr uint32_t idesc = TF32 ? ptx::make_idesc_tf32(kGemmBlockM, BN) : ptx::make_idesc_bf16(kGemmBlockM, BN);
+                for (int it = 0; it < num_k; ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after();
+                    if (it == 0) PD_STAMP(2);
+                    const uint32_t a_addr = ptx::smem_u32(smem + s * C::kStageBytes);
+                    const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-                for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                    const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
-                    const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
-                    ptx::umma_ss(tf32, tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                        const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32);
+                        const uint64_t db = ptx::make_smem_desc_sw128(b_addr + k * 32);
+                        ptx::umma_ss<TF32>(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
                 }
-                ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
-            }
+            };
+            if (p.tf32) issue(std::true_type{});
+            else issue(std::false_type{});
             ptx::umma_commit(tmem_full_bar);      // accumulator complete
             PD_STAMP(3);
         }

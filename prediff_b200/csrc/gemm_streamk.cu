@@ -13,6 +13,7 @@
 // Results are deterministic (fixed summation order) and batch-invariant (the cut depends on the layer shape only).
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include <type_traits>
 
 namespace pd {
 namespace {
@@ -136,31 +137,35 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const bool tf32 = p.tf32 != 0;
-            const uint32_t idesc = tf32 ? ptx::make_idesc_tf32(kGemmBlockM, BN) : ptx::make_idesc_bf16(kGemmBlockM, BN);
-            int it = 0;
+            auto issue = [&](auto tf32_tag) {   // the precision picks the loop, not the instruction (ptx.cuh umma_ss)
+                constexpr bool TF32 = decltype(tf32_tag)::value;
+                constexpr uint32_t idesc = TF32 ? ptx::make_idesc_tf32(kGemmBlockM, BN) : ptx::make_idesc_bf16(kGemmBlockM, BN);
+                int it = 0;
 #pragma unroll 1
-            for (int sg = 0; sg < 2; ++sg) {
-                const SkSeg sgm = sg ? seg1 : seg0;
-                if (sgm.role == SK_NONE) continue;
-                const uint32_t tmem_d = tmem_base + sg * BN;   // the two segments use different accumulators
-                for (int k = sgm.k_begin; k < sgm.k_end; ++k, ++it) {
-                    const int s = it % STAGES;
-                    ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                    ptx::tc_fence_after();
-                    if (it == 0) SK_STAMP(2);
-                    const uint32_t a_addr = ptx::smem_u32(smem + s * kStageBytes);
-                    const uint32_t b_addr = a_addr + kABytes;
+                for (int sg = 0; sg < 2; ++sg) {
+                    const SkSeg sgm = sg ? seg1 : seg0;
+                    if (sgm.role == SK_NONE) continue;
+                    const uint32_t tmem_d = tmem_base + sg * BN;   // the two segments use different accumulators
+                    for (int k = sgm.k_begin; k < sgm.k_end; ++k, ++it) {
+                        const int s = it % STAGES;
+                        ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                        ptx::tc_fence_after();
+                        if (it == 0) SK_STAMP(2);
+                        const uint32_t a_addr = ptx::smem_u32(smem + s * kStageBytes);
+                        const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-                    for (int kk = 0; kk < kGemmBlockK / 16; ++kk)
-                        ptx::umma_ss(tf32, tmem_d, ptx::make_smem_desc_sw128(a_addr + kk * 32),
-                                     ptx::make_smem_desc_sw128(b_addr + kk * 32), idesc,
-                                     (k != sgm.k_begin || kk != 0) ? 1u : 0u);
-                    ptx::umma_commit(&empty_bar[s]);
+                        for (int kk = 0; kk < kGemmBlockK / 16; ++kk)
+                            ptx::umma_ss<TF32>(tmem_d, ptx::make_smem_desc_sw128(a_addr + kk * 32),
+                                               ptx::make_smem_desc_sw128(b_addr + kk * 32), idesc,
+                                               (k != sgm.k_begin || kk != 0) ? 1u : 0u);
+                        ptx::umma_commit(&empty_bar[s]);
+                    }
+                    ptx::umma_commit(&tmem_full[sg]);
+                    SK_STAMP(sg ? 6 : 3);
                 }
-                ptx::umma_commit(&tmem_full[sg]);
-                SK_STAMP(sg ? 6 : 3);
-            }
+            };
+            if (p.tf32) issue(std::true_type{});
+            else issue(std::false_type{});
         }
     } else {
         const int e = warp - 2;

@@ -61,8 +61,15 @@ struct CuboidTablesDev {   // owner of the device copies
     int upload(const CuboidTables& t);
 };
 // qkv bf16 [B][N][3C] (N = T*H*W tokens per sample, q|k|v head-major), bias_table fp32 [n_rel][heads] -> out bf16 [B][N][C]
+// impl: 0 = choose (tcgen05 tile kernel when eligible, see below), 1 = warp-level mma.sync kernel, 2 = tcgen05 tile kernel
 int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
-                     const CuboidDev& g, cudaStream_t st);
+                     const CuboidDev& g, cudaStream_t st, int impl = 0);
+// The same contract on tcgen05 tensor-core tiles (attention_tc.cu): 128-query tile per (cuboid, head, sample), S and O in
+// TMEM, K / V chunks of 128 keys in a swizzled shared-memory ring. Eligible for head dims 64 / 128 and volumes >= 128
+// (cuboid_attention() dispatches to it; PD_CUBOID_NO_TC=1 keeps the mma.sync kernel for A/B runs).
+bool cuboid_attention_tc_eligible(int hd, int volume);
+int cuboid_attention_tc(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
+                        const CuboidDev& g, cudaStream_t st);
 // Row softmax for the VAE AttentionBlock: s fp32 [rows][L] -> p bf16 [rows][L], p = softmax(scale * s).
 int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st);
 // Batched transpose bf16: in [S][R][ld_in] (first C columns used) -> out [S][C][R].

@@ -221,10 +221,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// bf16 or tf32 operands, chosen at run time by the (single) issuing thread
-__device__ __forceinline__ void umma_ss(bool tf32, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// bf16 or tf32 operands as a COMPILE-TIME choice: the issue loops are instantiated twice and the run-time precision flag
+// picks the loop, not the instruction (a branch between the two asm statements inside the loop made ptxas predicate both
+// UTCHMMAs behind ELECT / R2UR.BROADCAST waterfall loops - the single issuing thread then could not keep up with the
+// tensor core: every long-K GEMM ran ~20 % slower, measured).
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                         uint32_t accumulate) {
-    if (tf32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+    if constexpr (TF32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
     else umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.

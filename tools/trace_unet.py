@@ -18,6 +18,13 @@ from prediff_b200 import _lib as L  # noqa: E402
 from prediff_b200 import weights as Wt  # noqa: E402
 from prediff_b200.unet import CuboidTransformerUNet  # noqa: E402
 
+if os.environ.get("PD_LIB_PATH"):   # A/B against an older build of the library: entry points added since are no-ops
+    for _name in ("pd_unet_set_precision",):
+        try:
+            getattr(L.lib(), _name)
+        except AttributeError:
+            setattr(L.lib(), _name, lambda *a: 0)
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--out", default=None)
@@ -27,12 +34,13 @@ ap.add_argument("--graph", action="store_true",
 ap.add_argument("--patterns", default="axial,axial",
                 help="block_attn_patterns of the two levels (any registered name, e.g. video_swin_2x8,spatial_lg_4)")
 ap.add_argument("--padding", default="zeros", choices=["zeros", "ignore"])
+ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
 args = ap.parse_args()
 cfg = Wt.UNetConfig(patterns=tuple(args.patterns.split(",")), padding_type=args.padding)
 B = args.batch
 unet = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
                              depth=list(cfg.depth), num_heads=cfg.num_heads, block_attn_patterns=list(cfg.patterns),
-                             padding_type=cfg.padding_type, max_batch=B)
+                             padding_type=cfg.padding_type, max_batch=B, precision=args.precision)
 unet.load_state_dict({k: torch.from_numpy(v) for k, v in Wt.seeded_state_dict(Wt.unet_param_spec(cfg), 1001).items()},
                      strict=False)
 rng = np.random.Generator(np.random.PCG64(1))
@@ -75,7 +83,7 @@ for name, us in zip(lab, d):
     a[0] += 1
     a[1] += us - slot
 total = sum(v[1] for v in agg.values())
-lines = [f"UNet forward, batch {B}, patterns {args.patterns} / {args.padding}{' (CUDA-graph replay)' if args.graph else ''}: {n} plan steps, {(s[-1] - s[0]) * 1e-3:.1f} us wall with stamps, "
+lines = [f"UNet forward, batch {B}, {args.precision} operands, patterns {args.patterns} / {args.padding}{' (CUDA-graph replay)' if args.graph else ''}: {n} plan steps, {(s[-1] - s[0]) * 1e-3:.1f} us wall with stamps, "
          f"{total:.1f} us after removing {n} stamp slots of {slot:.2f} us",
          f"{'site':28s} {'n':>4s} {'avg us':>8s} {'total us':>9s} {'share':>6s}"]
 for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
