@@ -221,6 +221,14 @@ int pd_sample_step_ddpm(pd_sampler* s, pd_unet* unet, float* z, const float* con
 int pd_sevir_eval_update(const float* pred, const float* target, int64_t* counts, double* sums, int N, int T, int H,
                          int W, int pool, const float* thresholds_host, int n_thresholds, void* stream);
 
+/* SSIM beside it (train_sevirlr_prediff.py:229-230 `torchmetrics.image.StructuralSimilarityIndexMeasure()`, updated with
+ * "(b t) c h w" frames at :964-965; torchmetrics==1.2.0 per setup.py:33, functional/image/ssim.py): 11 x 11 Gaussian window,
+ * sigma 1.5, k1 0.01, k2 0.03, borders cropped by 5, per-image mean, reduction elementwise_mean. pred / target fp32
+ * [N][H][W] (one channel) on the device; data_range <= 0 means None (max of the two value ranges of this batch).
+ * state (device double [2]) += {sum of the per-image SSIM values, N}; SSIM = state[0] / state[1]. */
+int pd_ssim_update(const float* pred, const float* target, int N, int H, int W, float data_range, double* state,
+                   void* stream);
+
 /* ---- input side (reference: src/prediff/datasets/sevir/sevir_dataloader.py:834-877 SEVIRDataLoader._idx_sample in
  *      'sequent' mode, :610-650 preprocess_data_dict, :71-84 change_layout, constants :25-44) ------------------------- */
 /* events_u8: raw VIL events as stored in the SEVIR-LR HDF5 files, uint8 [n_events][H][W][T_raw] ('NHWT') on the device,

@@ -246,6 +246,12 @@ int pd_op_cuboid_attention_impl(const void* qkv, const float* bias_table, void* 
     return PD_OK;
 }
 
+int pd_ssim_update(const float* pred, const float* target, int N, int H, int W, float data_range, double* state,
+                   void* stream) {
+    PD_TRY(gemm_init());
+    return ssim_update(pred, target, N, H, W, data_range, state, S(stream));
+}
+
 int pd_op_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_alphas_cumprod,
                    const float* sqrt_one_minus_alphas_cumprod, float* out, int B, int64_t n_per_sample, void* stream) {
     PD_TRY(gemm_init());

@@ -163,12 +163,23 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
     }
 }
 
-// VAE encoder conv_in: single input channel, 3x3, pad 1. One thread per (pixel, 4 output channels).
+// VAE encoder conv_in: single input channel, 3x3, pad 1 - write-bound (4 * Cout bytes per pixel out, 4 bytes in). One
+// thread per (pixel, 4 output channels): the 32 lanes of a warp share a pixel (its 9 taps are broadcast loads) and write
+// 512 contiguous bytes; the weights sit in shared memory as [tap][Cout] so a lane's four channels are one LDS.128 per tap.
+// (Round 1 read its 36 weights per thread through __ldg with a 36-byte stride: 541 us for 28 frames = 5 % of the HBM
+// peak, profiles/ncu_r02_vae_summary.txt.)
 __global__ void __launch_bounds__(kEwThreads) conv3x3_c1_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ y,
                                                                    int F, int H, int W, int Cout) {
+    extern __shared__ float s_w[];   // [9][Cout] + bias [Cout]
+    for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
+        const int tap = i / Cout, c = i - tap * Cout;
+        s_w[i] = w[(size_t)c * 9 + tap];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[9 * Cout + i] = bias[i];
     grid_dep_launch();
     grid_dep_wait();
+    __syncthreads();
     const int c4n = Cout >> 2;
     const int64_t total = (int64_t)F * H * W * c4n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -177,51 +188,75 @@ __global__ void __launch_bounds__(kEwThreads) conv3x3_c1_in_kernel(const float* 
         const int px = (int)(pos % W); pos /= W;
         const int py = (int)(pos % H);
         const int f = (int)(pos / H);
-        float acc[4] = {bias[c], bias[c + 1], bias[c + 2], bias[c + 3]};
+        float4 acc = *reinterpret_cast<const float4*>(s_w + 9 * Cout + c);
+        const float* xf = x + (size_t)f * H * W;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int yy = py + ky - 1, xx = px + kx - 1;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                    const float v = __ldg(x + ((size_t)f * H + yy) * W + xx);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[k] = fmaf(v, __ldg(w + (size_t)(c + k) * 9 + ky * 3 + kx), acc[k]);
-                }
+                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xf + (size_t)yy * W + xx) : 0.f;
+                const float4 ww = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * Cout + c);
+                acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
+                acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
             }
-        reinterpret_cast<float4*>(y)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(y)[i] = acc;
     }
 }
 
-// VAE decoder conv_out: Cin -> 1. One warp per output pixel; lanes split the channels.
+// VAE decoder conv_out: Cin -> 1, 3x3, pad 1 - read-bound (2 * Cin bytes per pixel in, 4 bytes out). A block owns a
+// 14 x 14 output tile = a 16 x 16 input tile with halo, one input pixel per thread: the thread reads its pixel's Cin
+// channels once (contiguous) and forms the pixel's 9 per-tap dot products against the weights in shared memory (broadcast
+// LDS.128); the 14 x 14 outputs are then sums of 9 shared-memory values. Every activation is read once (plus the 31 % halo)
+// instead of nine times through a warp-per-pixel reduction (round 1: 461 us for 24 frames = 4 % of the HBM peak).
+constexpr int kCoTile = 14;
 __global__ void __launch_bounds__(256) conv3x3_c1_out_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                              float bias, float* __restrict__ y, int F, int H, int W,
                                                              int Cin) {
+    extern __shared__ float s_co[];   // weights [9][Cin], then per-pixel taps [256][9]
+    float* s_w = s_co;
+    float* s_t = s_co + 9 * Cin;
+    for (int i = threadIdx.x; i < 9 * Cin; i += blockDim.x) s_w[i] = w[i];
     grid_dep_launch();
     grid_dep_wait();
-    const int64_t total = (int64_t)F * H * W;
-    const int lane = threadIdx.x & 31;
-    for (int64_t pix = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; pix < total;
-         pix += ((int64_t)gridDim.x * blockDim.x) >> 5) {
-        const int px = (int)(pix % W);
-        const int py = (int)((pix / W) % H);
-        const int64_t f = pix / ((int64_t)W * H);
-        float acc = 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const bf16* src = x + (((size_t)f * H + yy) * W + xx) * Cin;
-            const float* wt = w + (size_t)tap * Cin;
-            for (int c = lane * 4; c < Cin; c += 128) {
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(src + c));
-                const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(wt + c));
-                acc = fmaf(a.x, ww.x, acc); acc = fmaf(a.y, ww.y, acc);
-                acc = fmaf(b.x, ww.z, acc); acc = fmaf(b.y, ww.w, acc);
+    __syncthreads();
+    const int tiles_x = (W + kCoTile - 1) / kCoTile, tiles_y = (H + kCoTile - 1) / kCoTile;
+    const int f = blockIdx.x / (tiles_x * tiles_y);
+    const int tt = blockIdx.x - f * tiles_x * tiles_y;
+    const int y0 = (tt / tiles_x) * kCoTile, x0 = (tt % tiles_x) * kCoTile;
+    const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+    const int iy = y0 + ly - 1, ix = x0 + lx - 1;
+    float t[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) t[k] = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + (((size_t)f * H + iy) * W + ix) * Cin);
+        for (int c8 = 0; c8 < Cin / 8; ++c8) {
+            const uint4 u = __ldg(src + c8);
+            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * Cin + c8 * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + k * Cin + c8 * 8 + 4);
+                t[k] = fmaf(a0.x, w0.x, fmaf(a0.y, w0.y, fmaf(a1.x, w0.z, fmaf(a1.y, w0.w, t[k]))));
+                t[k] = fmaf(a2.x, w1.x, fmaf(a2.y, w1.y, fmaf(a3.x, w1.z, fmaf(a3.y, w1.w, t[k]))));
             }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) y[pix] = acc + bias;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_t[threadIdx.x * 9 + k] = t[k];
+    __syncthreads();
+    // output (oy, ox) of the tile = input-tile position (oy + 1, ox + 1); tap (ky, kx) reads input (oy + ky, ox + kx)
+    if (ly < kCoTile && lx < kCoTile) {
+        const int oy = y0 + ly, ox = x0 + lx;
+        if (oy < H && ox < W) {
+            float acc = bias;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) acc += s_t[((ly + ky) * 16 + (lx + kx)) * 9 + ky * 3 + kx];
+            y[((size_t)f * H + oy) * W + ox] = acc;
+        }
     }
 }
 
@@ -320,15 +355,16 @@ int conv3x3_c1_in(const float* x, const float* w, const float* bias, float* y, i
                   cudaStream_t st) {
     PD_CHECK(Cout % 4 == 0, PD_ERR_SHAPE, "conv3x3_c1_in: Cout=%d", Cout);
     const int64_t total = (int64_t)F * H * W * (Cout / 4);
-    PD_LAUNCH(conv3x3_c1_in_kernel, ew_blocks(total), kEwThreads, 0, st, x, w, bias, y, F, H, W, Cout);
+    PD_CHECK(Cout <= 1024, PD_ERR_SHAPE, "conv3x3_c1_in: Cout=%d", Cout);
+    PD_LAUNCH(conv3x3_c1_in_kernel, ew_blocks(total), kEwThreads, (size_t)10 * Cout * sizeof(float), st, x, w, bias, y, F, H, W, Cout);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
 
 int conv3x3_c1_out(const bf16* x, const float* w, float bias, float* y, int F, int H, int W, int Cin, cudaStream_t st) {
-    PD_CHECK(Cin % 4 == 0, PD_ERR_SHAPE, "conv3x3_c1_out: Cin=%d", Cin);
-    const int64_t total = (int64_t)F * H * W * 32;
-    PD_LAUNCH(conv3x3_c1_out_kernel, ew_blocks(total), 256, 0, st, x, w, bias, y, F, H, W, Cin);
+    PD_CHECK(Cin % 8 == 0 && Cin <= 512, PD_ERR_SHAPE, "conv3x3_c1_out: Cin=%d (multiple of 8, <= 512)", Cin);
+    const int tiles = ceil_div(W, kCoTile) * ceil_div(H, kCoTile);
+    PD_LAUNCH(conv3x3_c1_out_kernel, F * tiles, 256, (size_t)(9 * Cin + 256 * 9) * sizeof(float), st, x, w, bias, y, F, H, W, Cin);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

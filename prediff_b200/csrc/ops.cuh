@@ -176,6 +176,11 @@ int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 int sevir_eval_update(const float* pred, const float* target, long long* counts, double* sums, int N, int T, int H, int W,
                       int pool, const float* thresholds, int n_thr, cudaStream_t st);
 
+// SSIM of torchmetrics.image.StructuralSimilarityIndexMeasure() (defaults) for single-channel frames: pred / target fp32
+// [N][H][W]; data_range <= 0 = None (taken from the batch); state double [2] += {sum of per-image SSIM, N}.
+int ssim_update(const float* pred, const float* target, int N, int H, int W, float data_range, double* state,
+                cudaStream_t st);
+
 // ---- input side (io.cu) ------------------------------------------------------------------------------------
 // Raw uint8 VIL events [n_events][H][W][T_raw] (events event_base .. event_base + n_events - 1) -> sequent windows
 // first_seq .. first_seq + batch - 1 as fp32 [batch][seq_len][H][W] = scale * (x + offset) (sevir_dataloader.py:834-877,

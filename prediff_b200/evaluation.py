@@ -115,3 +115,47 @@ class SEVIRSkillScore:
             score_avg = score_avg / len(self.threshold_list)
             ret["avg"][m] = score_avg if self.mode in ("0", "1") else np.mean(score_avg).item()
         return ret
+
+
+class StructuralSimilarityIndexMeasure:
+    """Mirror of `torchmetrics.image.StructuralSimilarityIndexMeasure()` as the inference script uses it
+    (train_sevirlr_prediff.py:229-230: default arguments; :964-965: `self.test_ssim(pred_seq_bchw, target_seq_bchw)` with
+    "(b t) c h w" frames) over the on-device kernel `pd_ssim_update` (csrc/eval.cu): 11 x 11 Gaussian window (sigma 1.5),
+    k1 = 0.01, k2 = 0.03, `data_range=None` (taken from each update's batch), per-image mean over the interior, reduction
+    'elementwise_mean'. One pixel channel (SEVIR VIL frames). The state (sum of per-image SSIM, image count) stays on the
+    device and is summed across ranks in `compute()` like the reference's `dist_reduce_fx="sum"` states."""
+
+    def __init__(self, gaussian_kernel=True, sigma=1.5, kernel_size=11, reduction="elementwise_mean", data_range=None,
+                 k1=0.01, k2=0.03, **unused):
+        if not gaussian_kernel or sigma != 1.5 or kernel_size != 11 or reduction != "elementwise_mean" or (k1, k2) != (0.01, 0.03):
+            raise NotImplementedError("prediff_b200.StructuralSimilarityIndexMeasure: only the torchmetrics defaults are built")
+        if isinstance(data_range, (tuple, list)):
+            raise NotImplementedError("prediff_b200.StructuralSimilarityIndexMeasure: clamping data_range tuples are not built")
+        self.data_range = data_range
+        self._state = None
+
+    def reset(self):
+        self._state = None
+
+    @torch.no_grad()
+    def update(self, preds: torch.Tensor, target: torch.Tensor):
+        if not preds.is_cuda:
+            raise L.PDError("prediff_b200.StructuralSimilarityIndexMeasure runs on a CUDA (sm_100) device only; got a CPU tensor")
+        assert preds.dim() == 4 and preds.shape[1] == 1 and preds.shape == target.shape, "expected (B, 1, H, W) frames"
+        p = preds.detach().contiguous().float()
+        t = target.detach().to(p.device).contiguous().float()
+        if self._state is None:
+            self._state = torch.zeros(2, dtype=torch.float64, device=p.device)
+        with torch.cuda.device(p.device):
+            L.check(L.lib().pd_ssim_update(L.ptr(p), L.ptr(t), p.shape[0], p.shape[2], p.shape[3],
+                                           ctypes.c_float(-1.0 if self.data_range is None else float(self.data_range)),
+                                           L.ptr(self._state), L.stream_ptr()))
+
+    __call__ = update   # the script calls the metric object (forward = update + batch value); only the state is kept here
+
+    def compute(self):
+        assert self._state is not None, "compute() before any update()"
+        st = self._state.clone()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(st, op=torch.distributed.ReduceOp.SUM)
+        return (st[0] / st[1]).float()

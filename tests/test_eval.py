@@ -107,3 +107,72 @@ def test_gpu_counts_match_oracle_random(N, T, H, W, pool, layout):
     ok = ~(np.isnan(tb) | np.isnan(pb))
     for i, th in enumerate(THR):
         assert (ref[i, :, 0] + ref[i, :, 1]).sum() == ((tb >= th) & ok).sum()
+
+
+# ---- SSIM (torchmetrics 1.2.0 StructuralSimilarityIndexMeasure defaults; restated algorithm, see oracle/eval_oracle.py) ----
+def _ssim_direct(p, t, data_range):
+    """The definition evaluated with plain double loops (float64): Gaussian-weighted local moments over the 11 x 11 window,
+    interior pixels only - an independent check of the oracle's conv2d / padding / cropping arithmetic."""
+    g = np.exp(-((np.arange(11) - 5) / 1.5) ** 2 / 2)
+    g = g / g.sum()
+    w = np.outer(g, g)
+    H, W = p.shape
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    vals = []
+    for y in range(5, H - 5):
+        for x in range(5, W - 5):
+            a, b = p[y - 5:y + 6, x - 5:x + 6], t[y - 5:y + 6, x - 5:x + 6]
+            ma, mb = (w * a).sum(), (w * b).sum()
+            va, vb, vab = (w * a * a).sum() - ma * ma, (w * b * b).sum() - mb * mb, (w * a * b).sum() - ma * mb
+            vals.append(((2 * ma * mb + c1) * (2 * vab + c2)) / ((ma * ma + mb * mb + c1) * (va + vb + c2)))
+    return float(np.mean(vals))
+
+
+def _ssim_inputs(seed=808, B=3, H=40, W=36):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = rng.random((B, 1, H, W), dtype=np.float32)
+    p = np.clip(t + 0.2 * rng.standard_normal((B, 1, H, W)).astype(np.float32), 0, 1).astype(np.float32)
+    return torch.from_numpy(p), torch.from_numpy(t)
+
+
+def test_ssim_oracle_known_answers():
+    p, t = _ssim_inputs()
+    assert torch.allclose(EO.ssim_per_image(t, t), torch.ones(3), atol=1e-6)          # identical images
+    s = EO.ssim_per_image(p, t)
+    dr = float(max(p.max() - p.min(), t.max() - t.min()))
+    for b in range(3):
+        assert abs(float(s[b]) - _ssim_direct(p[b, 0].double().numpy(), t[b, 0].double().numpy(), dr)) < 2e-5
+    # the reflect-padded border is cropped away again: changing what the padding mode would see changes nothing as long
+    # as the pixels themselves are the same (the interior only reads real pixels)
+    s_fixed = EO.ssim_per_image(p, t, data_range=1.0)
+    assert abs(float(s_fixed[0]) - _ssim_direct(p[0, 0].double().numpy(), t[0, 0].double().numpy(), 1.0)) < 2e-5
+    st = EO.SSIMState()
+    st.update(p[:2], t[:2])
+    st.update(p[2:], t[2:])   # data_range is taken per update batch
+    want = (float(EO.ssim_per_image(p[:2], t[:2]).sum()) + float(EO.ssim_per_image(p[2:], t[2:]).sum())) / 3
+    assert abs(st.compute() - want) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 40, 36), (12, 128, 128), (1, 11 + 32, 11 + 33)])
+def test_gpu_ssim_matches_oracle(shape):
+    from prediff_b200.evaluation import StructuralSimilarityIndexMeasure
+    B, H, W = shape
+    p, t = _ssim_inputs(seed=909, B=B, H=H, W=W)
+    m = StructuralSimilarityIndexMeasure()
+    o = EO.SSIMState()
+    for lo, hi in ((0, max(1, B // 2)), (max(1, B // 2), B)):
+        if hi > lo:
+            m(p[lo:hi].cuda(), t[lo:hi].cuda())
+            o.update(p[lo:hi], t[lo:hi])
+    got, want = float(m.compute()), o.compute()
+    print(f"ssim {shape}: cuda {got:.7f} oracle {want:.7f}")
+    assert abs(got - want) < 2e-5
+    fixed = StructuralSimilarityIndexMeasure(data_range=1.0)
+    fixed.update(p.cuda(), t.cuda())
+    assert abs(float(fixed.compute()) - float(EO.ssim_per_image(p, t, data_range=1.0).mean())) < 2e-5
+    same = StructuralSimilarityIndexMeasure()
+    same.update(t.cuda(), t.cuda())
+    assert abs(float(same.compute()) - 1.0) < 1e-6
+    with pytest.raises(NotImplementedError):
+        StructuralSimilarityIndexMeasure(kernel_size=7)
