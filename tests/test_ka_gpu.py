@@ -7,7 +7,8 @@
   device-resident loop; the DDIM-KA loop (S6) vs the oracle.
 
 Tolerances: bf16 tensor-core operands in forward *and* backward GEMMs (fp32 accumulate / residual / norms). Measured
-on B200: pred rel-RMS 2.0e-3, guidance rel-RMS 1.1e-2 (max 1.5e-2 of abs-max); bars are 1.5e-2 / 4e-2."""
+on B200: pred rel-RMS 2.0e-3, guidance rel-RMS 1.1e-2 (max 1.5e-2 of abs-max); bars are ~2x the
+measured values: 5e-3 for the prediction, 2.5e-2 / 4e-2 for the guidance."""
 import os
 
 import numpy as np
@@ -211,12 +212,12 @@ def test_ka_forward_and_guidance_vs_reference_golden(ka):
     assert pred.shape == (4, cfg.t, 1)
     r, m = errs(pred, g["pred"])
     print(f"KA forward vs reference: rel_rms={r:.3e} max={m:.3e}")
-    assert r < 1.5e-2 and m < 4e-2
+    assert r < 5e-3 and m < 2e-2
     grad = al.get_mean_shift(zt, t, avg_x_gt=torch.full((4, 1), 0.3))
     assert grad.shape == zt.shape
     r, m = errs(grad, g["grad"])
     print(f"KA guidance vs reference get_mean_shift: rel_rms={r:.3e} max={m:.3e}")
-    assert r < 4e-2 and m < 8e-2
+    assert r < 2.5e-2 and m < 4e-2
     val = al.alignment_fn(zt, t, avg_x_gt=torch.full((4, 1), 0.3, device=DEV))
     ref_val = np.linalg.norm(g["pred"].mean(axis=1) - 0.3)
     assert abs(val.item() - ref_val) < 2e-2 * abs(ref_val) + 1e-3
@@ -231,7 +232,7 @@ def test_ka_guidance_vs_oracle_fresh_inputs_and_batch_coupling(ka):
     grad, val = al.model.mean_shift(zt.cuda(), t.cuda(), tgt.cuda(), cfg.guide_scale, return_value=True)
     r, m = errs(grad, ref)
     print(f"KA guidance vs oracle (B=2): rel_rms={r:.3e} max={m:.3e}")
-    assert r < 4e-2 and m < 8e-2
+    assert r < 2.5e-2 and m < 4e-2
     with torch.no_grad():
         ref_val = O.ka_alignment_value(sd, cfg, zt, t, tgt).item()
     assert abs(val.item() - ref_val) < 2e-2 * abs(ref_val) + 1e-3
@@ -239,7 +240,7 @@ def test_ka_guidance_vs_oracle_fresh_inputs_and_batch_coupling(ka):
     g1 = al.model.mean_shift(zt[:1].cuda(), t[:1].cuda(), tgt[:1].cuda(), cfg.guide_scale)
     ref1 = O.ka_mean_shift(sd, cfg, zt[:1], t[:1], tgt[:1], cfg.guide_scale)
     r1, _ = errs(g1, ref1)
-    assert r1 < 4e-2
+    assert r1 < 2.5e-2
     assert not torch.allclose(g1[0], grad[0], rtol=1e-2, atol=0)
     # re-run determinism
     g2 = al.model.mean_shift(zt.cuda(), t.cuda(), tgt.cuda(), cfg.guide_scale)

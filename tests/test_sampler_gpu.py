@@ -16,7 +16,8 @@ from tests.test_vae_gpu import make_vae
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 # loop tolerances: per-step bf16 error saturates over the chain (5.5e-3 after 50 DDIM steps)
-LOOP_RMS_TOL, LOOP_MAX_TOL = 2.5e-2, 8e-2
+# measured on B200 (profiles/parity_r02.txt): 50-step DDIM full config 7.8e-3 (max 9.0e-3), tiny 5.6e-3, sample() frames 7.0e-3
+LOOP_RMS_TOL, LOOP_MAX_TOL = 1.2e-2, 2.5e-2
 
 
 @pytest.fixture(scope="module")

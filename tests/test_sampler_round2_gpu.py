@@ -20,7 +20,9 @@ pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "loop_extra.npz"))
 CFG = Wt.TINY_UNET
 # bf16 operands (default precision); see tests/test_tf32_gpu.py for the TF32-class bars
-LOOP_RMS_TOL, LOOP_MAX_TOL = 2.5e-2, 8e-2
+# latents: as tests/test_sampler_gpu.py; decoded full-size frames after encode -> 50 steps -> decode measure 1.6e-2 (bf16 VAE on both sides)
+LOOP_RMS_TOL, LOOP_MAX_TOL = 1.2e-2, 2.5e-2
+FRAME_RMS_TOL, FRAME_MAX_TOL = 2.5e-2, 4e-2
 
 
 def _tiny_inputs(scale=1.0):
@@ -166,4 +168,4 @@ def test_full_size_sample_vs_reference():
     r50, m50 = errs(dec50, G["full_sample_ddim50"])
     print(f"full-size sample(): zc rel_rms={rz:.3e}; ddpm-4 frames rel_rms={r4:.3e} max={m4:.3e}; "
           f"ddim-50 frames rel_rms={r50:.3e} max={m50:.3e}")
-    assert rz < 1.5e-2 and r4 < LOOP_RMS_TOL and m4 < LOOP_MAX_TOL and r50 < LOOP_RMS_TOL and m50 < LOOP_MAX_TOL
+    assert rz < 1.5e-2 and r4 < LOOP_RMS_TOL and m4 < LOOP_MAX_TOL and r50 < FRAME_RMS_TOL and m50 < FRAME_MAX_TOL

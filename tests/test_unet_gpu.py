@@ -3,7 +3,8 @@
 
 Tolerance: the CUDA path feeds bf16 operands to the tensor cores (fp32 accumulate, fp32 residual stream); the
 reference's own GPU numerics are TF32. SURVEY.md section 7 measured bf16-operand emulation at rel-RMS 6.8e-3 per UNet
-step; the bars here are rel-RMS <= 1.5e-2 and max-abs error <= 4e-2 of the output's abs-max."""
+step; measured on B200 6.4e-3 - 6.9e-3 (profiles/parity_r02.txt). The bars here are ~1.5x the measured values: rel-RMS
+<= 1.2e-2 and max-abs error <= 2.5e-2 of the output's abs-max. The like-for-like TF32 mode is held to 2e-3 in test_tf32_gpu.py."""
 import os
 
 import numpy as np
@@ -17,7 +18,8 @@ from tests.golden.gen_golden import UNET_SEED, inp
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
-REL_RMS_TOL, MAX_TOL = 1.5e-2, 4e-2
+# measured on B200 (profiles/parity_r02.txt): UNet step rel-RMS 6.4e-3 - 6.9e-3, max 7.7e-3; VAE (same bars) 9e-3 - ~1.5x those
+REL_RMS_TOL, MAX_TOL = 1.2e-2, 2.5e-2
 
 
 def errs(out, ref):

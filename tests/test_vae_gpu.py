@@ -1,5 +1,6 @@
 """GPU parity: AutoencoderKL CUDA path vs golden outputs of the unmodified reference and vs the CPU oracle.
-Tolerances (bf16 tensor-core operands, fp32 accumulate / residual stream): rel-RMS <= 1.5e-2, max <= 4e-2 of abs-max."""
+Tolerances (bf16 tensor-core operands, fp32 accumulate / residual stream; measured 9e-3 on B200): rel-RMS <= 1.4e-2,
+max <= 4e-2 of abs-max."""
 import os
 
 import numpy as np
@@ -10,7 +11,9 @@ from oracle import prediff_oracle as O
 from prediff_b200 import weights as Wt
 from prediff_b200.vae import AutoencoderKL
 from tests.golden.gen_golden import VAE_SEED, inp
-from tests.test_unet_gpu import MAX_TOL, REL_RMS_TOL, errs
+from tests.test_unet_gpu import errs
+
+REL_RMS_TOL, MAX_TOL = 1.4e-2, 4e-2
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
