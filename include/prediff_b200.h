@@ -360,6 +360,15 @@ int pd_op_ffn_fused_phases(const void* ln_in_bf16, const void* W1_bf16, const fl
                            const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
                            int M, unsigned long long* stamps32, void* stream);
 
+/* Fused PositionwiseFFN at width 512 / hidden 2048 (the level-1 width of the shipped UNet): x[M][512] += W2 GELU(W1 ln_in +
+ * b1) + b2 in one kernel whose hidden dimension is split over a 4-CTA thread-block cluster (each CTA: 512 hidden columns
+ * GELU'd into shared memory, a 128 x 512 partial of FFN-2 in TMEM, reduce-scatter of the four partials through
+ * distributed shared memory in rank order); if ln_gamma is given, ln_out[M][512] (bf16) = LayerNorm(new x row); if gn_sums
+ * is given, the GroupNorm statistics of the new rows are added to gn_sums[samples][gn_groups][2] (gn_rows rows per
+ * sample). W1 bf16 [2048][512], W2 bf16 [512][2048]. */
+int pd_op_ffn_cluster(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
+                      float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, double* gn_sums,
+                      int gn_groups, int gn_rows, int M, void* stream);
 /* The same kernel with the attention output projection fused in front (CuboidSelfAttentionLayer proj +
  * StackCuboidSelfAttentionBlock residual, cuboid_transformer.py:952,1151, then PositionwiseFFN :182-208):
  *   x1 = x + att Wp^T + bp;  x <- x1 + W2 GELU(W1 LayerNorm(x1; ln1) + b1) + b2;  ln_out = LayerNorm(x; ln) (optional).

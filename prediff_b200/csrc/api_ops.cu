@@ -246,6 +246,18 @@ int pd_op_cuboid_attention_impl(const void* qkv, const float* bias_table, void* 
     return PD_OK;
 }
 
+int pd_op_ffn_cluster(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
+                      float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, double* gn_sums,
+                      int gn_groups, int gn_rows, int M, void* stream) {
+    PD_TRY(gemm_init());
+    FfnClusterOp op;
+    PD_TRY(ffn_cluster_make(&op, static_cast<const bf16*>(ln_in_bf16), M, static_cast<const bf16*>(W1_bf16), b1,
+                            static_cast<const bf16*>(W2_bf16), b2, x_inout, ln_gamma, ln_beta, static_cast<bf16*>(ln_out_bf16),
+                            1e-5f));
+    if (gn_sums) PD_TRY(ffn_cluster_set_gn(&op, gn_sums, gn_groups, gn_rows));
+    return ffn_cluster_launch(op, S(stream));
+}
+
 int pd_ssim_update(const float* pred, const float* target, int N, int H, int W, float data_range, double* state,
                    void* stream) {
     PD_TRY(gemm_init());

@@ -206,6 +206,11 @@ struct Plan {
         add([sp](cudaStream_t st) { return ffn_fused_launch(*sp, st); }, STEP_GEMM, label);
         weight_users.push_back({[sp](const WRange& r) { ffn_fused_set_prefetch(sp.get(), r); }, ffn_fused_weights(op)});
     }
+    void add_ffn_cluster(const FfnClusterOp& op, const char* label) {
+        auto sp = std::make_shared<FfnClusterOp>(op);
+        add([sp](cudaStream_t st) { return ffn_cluster_launch(*sp, st); }, STEP_GEMM, label);
+        weight_users.push_back({[](const WRange&) {}, ffn_cluster_weights(op)});   // it is prefetched for, it prefetches nothing
+    }
     // Every GEMM-family step requests the weights of the next one (the last wraps around to the first of the next pass).
     void link_prefetch() {
         const size_t n = weight_users.size();

@@ -169,6 +169,19 @@ void ffn_fused_set_prefetch(FfnFusedOp* op, const WRange& next);
 WRange ffn_fused_weights(const FfnFusedOp& op);
 int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 
+// ---- fused FFN for the width-512 level (ffn_cluster.cu) ------------------------------------------------------------
+// x[M][512] += W2 GELU(W1 ln + b1) + b2 in one kernel, hidden dimension (2048) split over a 4-CTA cluster with a
+// distributed-shared-memory reduce-scatter, optionally followed by the fused LayerNorm of the new rows -> ln_out (bf16)
+// and the GroupNorm statistics of the new rows. ln_in bf16 [M][512]; W1 bf16 [2048][512]; W2 bf16 [512][2048].
+struct FfnClusterOp {
+    alignas(64) unsigned char storage[768];
+};
+int ffn_cluster_make(FfnClusterOp* op, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
+                     const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out, float ln_eps);
+int ffn_cluster_set_gn(FfnClusterOp* op, double* gn_sums, int groups, int rows_per_sample);
+WRange ffn_cluster_weights(const FfnClusterOp& op);
+int ffn_cluster_launch(const FfnClusterOp& op, cudaStream_t st);
+
 // ---- evaluation (eval.cu) ----------------------------------------------------------------------------------
 // SEVIR skill-score contingency counts + error sums, accumulated on the device (evaluation.py:197-245).
 // pred / target fp32 [N][T][H][W] in [0,1]; counts int64 [n_thr][T][3] (hits, misses, false alarms) and sums double [2]

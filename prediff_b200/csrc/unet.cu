@@ -544,6 +544,21 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             pl.flops.back() = fl;
             continue;
         }
+        if (C == 512 && !prec && fuse && getenv("PD_NO_L1_FFN_FUSION") == nullptr) {
+            // width 512: FFN-1 + GELU + FFN-2 + residual (+ the next layer's LayerNorm, + the next resblock's GroupNorm
+            // statistics) in one kernel, hidden dimension split over a 4-CTA cluster (ffn_cluster.cu)
+            FfnClusterOp op;
+            const bool next_ln = i < last;
+            PD_TRY(ffn_cluster_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
+                                    next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f));
+            if (gn_next && i == last) PD_TRY(ffn_cluster_set_gn(&op, gn_next, 32, T * H * W));
+            const double fl = 2.0 * 2.0 * (double)P * C * 4 * C;
+            pl.gemm_flops += fl;
+            pl.n_gemm += 1;
+            pl.add_ffn_cluster(op, "ffn_cluster");
+            pl.flops.back() = fl;
+            continue;
+        }
         {
             GemmEpilogue e;
             e.bias = fw.b1;

@@ -134,6 +134,53 @@ def test_ffn_fused(M, with_ln):
     assert torch.equal(xo, xo2)
 
 
+@pytest.mark.parametrize("M,rows,with_ln,with_gn", [(3328, 832, True, False), (3328, 832, False, True), (832, 832, True, True),
+                                                    (128, 128, True, False), (1664, 832, False, False)])
+def test_ffn_cluster(M, rows, with_ln, with_gn):
+    """Width-512 FFN in one kernel, hidden dimension split over a 4-CTA cluster with a DSMEM reduce-scatter
+    (csrc/ffn_cluster.cu): x += W2 gelu(W1 ln + b1) + b2 (+ LayerNorm of the result, + GroupNorm statistics)."""
+    C, Hd = 512, 2048
+    ln_in = _randn(M, C, seed=1).bfloat16()
+    w1 = _randn(Hd, C, seed=2, scale=C ** -0.5).bfloat16()
+    w2 = _randn(C, Hd, seed=3, scale=Hd ** -0.5).bfloat16()
+    b1, b2 = 0.1 * _randn(Hd, seed=4), 0.1 * _randn(C, seed=5)
+    x = _randn(M, C, seed=6) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * _randn(C, seed=7), 0.1 * _randn(C, seed=8)
+    mid = F.gelu(ln_in.float() @ w1.float().t() + b1).bfloat16().float()
+    ref_x = x + mid @ w2.float().t() + b2
+    ref_ln = F.layer_norm(ref_x, (C,), gamma, beta, 1e-5)
+
+    def run():
+        xo = x.clone()
+        ln = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+        sums = torch.zeros(M // rows, 32, 2, device=DEV, dtype=torch.float64)
+        _sync_check(L.lib().pd_op_ffn_cluster(L.ptr(ln_in), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(xo),
+                                              L.ptr(gamma) if with_ln else None, L.ptr(beta) if with_ln else None,
+                                              L.ptr(ln) if with_ln else None, L.ptr(sums) if with_gn else None, 32, rows, M,
+                                              L.stream_ptr()))
+        return xo, ln, sums
+
+    xo, ln, sums = run()
+    assert rel_err(xo, ref_x) < 2e-3     # bf16 rounding of `mid` can flip at ties between the two implementations
+    if with_ln:
+        assert rel_err(ln, ref_ln) < 8e-3
+    if with_gn:
+        g = xo.double().reshape(M // rows, rows, 32, C // 32)
+        want = torch.stack([g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))], dim=-1)
+        assert torch.allclose(sums, want, rtol=2e-6, atol=1e-3)
+    xo2, ln2, _ = run()                  # deterministic: partials are added in rank order
+    assert torch.equal(xo, xo2) and torch.equal(ln, ln2)
+    if M > rows:                         # batch invariance: the first sample alone gives the same rows
+        M1 = rows
+        x1 = x[:M1].clone()
+        l1 = torch.zeros(M1, C, device=DEV, dtype=torch.bfloat16)
+        a1 = ln_in[:M1].contiguous()
+        _sync_check(L.lib().pd_op_ffn_cluster(L.ptr(a1), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(x1),
+                                              L.ptr(gamma) if with_ln else None, L.ptr(beta) if with_ln else None,
+                                              L.ptr(l1) if with_ln else None, None, 32, rows, M1, L.stream_ptr()))
+        assert torch.equal(x1, xo[:M1])
+
+
 @pytest.mark.parametrize("M,with_ln", [(13312, True), (3328, False), (1000, True)])
 def test_proj_ffn_fused(M, with_ln):
     """Attention projection + residual + pre-norm + FFN (+ next LayerNorm) in one kernel."""
