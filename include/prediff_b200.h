@@ -369,6 +369,14 @@ int pd_op_ffn_fused_phases(const void* ln_in_bf16, const void* W1_bf16, const fl
 int pd_op_ffn_cluster(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
                       float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, double* gn_sums,
                       int gn_groups, int gn_rows, int M, void* stream);
+/* pd_op_ffn_cluster with clock64() phase stamps of CTA 0 written to stamps32[32]: [0] entry, [1] dependency wait passed,
+ * [2]/[4] G1(c) accumulator complete, [3]/[5] E1(c) done, [6] partial complete, [8] slices
+ * sent, [9] cluster barrier passed, [10] rows reduced and written, [11] LayerNorm barrier passed, [12] done; MMA thread: [16]
+ * first operands landed, [17]/[18] G1(c) issued, [19]/[20] before / after the wait for E1(1), [21] G2 issued. Profiling aid
+ * (tools/ffn_cluster_phases.py). */
+int pd_op_ffn_cluster_phases(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
+                             const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
+                             int M, unsigned long long* stamps32, void* stream);
 /* The same kernel with the attention output projection fused in front (CuboidSelfAttentionLayer proj +
  * StackCuboidSelfAttentionBlock residual, cuboid_transformer.py:952,1151, then PositionwiseFFN :182-208):
  *   x1 = x + att Wp^T + bp;  x <- x1 + W2 GELU(W1 LayerNorm(x1; ln1) + b1) + b2;  ln_out = LayerNorm(x; ln) (optional).

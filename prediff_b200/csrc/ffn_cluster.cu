@@ -5,19 +5,25 @@
 // SMs, bf16 `mid` round trip) + FFN-2 GEMM (K = 2048 on 104 CTAs): 26 row tiles x 4 = 104 CTAs, one launch.
 //
 // CTA j of a cluster owns the 128 rows of its row tile and hidden columns [512 j, 512 j + 512):
-//   G1   acc[c] (TMEM columns [256 c, +256)) = ln . W1[512 j + 256 c ...]^T, c = 0, 1: K = 512 in 8 k-blocks through a
-//        2-stage TMA ring (A k-block 16 KB + W1 tile 32 KB);
+//   G1   acc[c] (TMEM columns [256 c, +256)) = ln . W1[512 j + 256 c ...]^T, c = 0, 1: K = 512 in 8 k-blocks of (A 16 KB + W1
+//        tile 32 KB). The TMA ring borrows the still-unused hidden-slice region: FOUR stages during G1(0), three during
+//        G1(1) (a round trip of a 48 KB stage is ~2 000 cycles under load; two stages ran at 820-925 cycles per k-block
+//        against the tensor core's 512);
 //   E1   acc[c] + b1 -> GELU -> bf16 -> 128-byte-swizzled K-major tiles: the CTA's 128 x 512 hidden slice (128 KB of
 //        shared memory) = the A operand of G2; E1(0) runs under G1(1);
 //   G2   partial[128 x 512] (all 512 TMEM columns, re-used) = hidden slice . W2[:, 512 j ...]^T: 8 k-blocks x 2 output halves
-//        of 256; the first four (k-block, half 0) steps only need E1(0) and run under E1(1);
-//   R    reduce-scatter through distributed shared memory: after a cluster barrier (every CTA's MMAs are done, so the hidden
-//        slice / ring are dead) each CTA stores the 128 x 128 slices of its partial that belong to the other three CTAs
-//        into their shared memory (st.shared::cluster); after a second barrier CTA j adds the four partials of output
-//        columns [128 j, +128) in RANK ORDER (deterministic, batch-invariant), + b2 + residual -> x;
-//   LN   row statistics over the 512 columns: per-CTA partial sums exchanged through DSMEM, third barrier, totals in rank
-//        order -> LayerNorm of the CTA's 128 columns -> bf16 (the next layer's pre-norm); optional GroupNorm statistics
-//        of the new x rows for the resblock that follows the stack (common.cuh gn_chunk_accumulate).
+//        of 256 through three 32 KB stages; the first four (k-block, half 0) steps only need E1(0) and run under E1(1);
+//   R    reduce-scatter of the four partials THROUGH L2: each CTA writes the three 128 x 128 slices of its partial that
+//        belong to the other CTAs to a global workspace (thread = row, consecutive lanes -> consecutive 16 bytes), one
+//        cluster barrier (release / acquire), then CTA j adds the four partials of output columns [128 j, +128) in RANK
+//        ORDER (deterministic, batch-invariant) + b2 + residual -> x. (The first version exchanged the slices through
+//        distributed shared memory: 192 KB out and 192 KB in per SM at the SM-to-SM network's ~17 B/clk took 22 k cycles,
+//        and the row-per-thread global read-modify-write of x another 21 k - measured with the phase stamps below; the
+//        kernel was slower than the two GEMMs it replaced. Now the residual tile arrives by TMA into swizzled slabs, is
+//        combined in place and bulk-stored.)
+//   LN   row statistics over the 512 columns: per-CTA partial sums exchanged through DSMEM (8 bytes per row), cluster
+//        barrier, totals in rank order -> LayerNorm of the CTA's 128 columns -> bf16 slab -> TMA store (the next layer's
+//        pre-norm); optional GroupNorm statistics of the new x rows for the resblock that follows the stack.
 //   warp 0: TMA producer; warp 1: TMEM allocation + one lane issuing tcgen05.mma 128 x 256 x 16; warps 2-9: E1 / R / LN
 //   (thread = row; warps w and w + 4 share a TMEM lane quarter and split the columns).
 #include "gemm.cuh"
@@ -35,72 +41,89 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileA = 128 * 64 * 2;         // 16 KB
 constexpr int kTileW = 256 * 64 * 2;         // 32 KB
 constexpr int kStage = kTileA + kTileW;      // 48 KB
-constexpr int kStages = 2;
-constexpr int kRingBytes = kStages * kStage; // 96 KB
+constexpr int kRingBytes = 2 * kStage;       // 96 KB: G1 slots 0 and 1, later the three W2 stages of G2
 constexpr int kMidBytes = 8 * kTileA;        // 128 KB: eight k-blocks of the GELU'd hidden slice
 constexpr int kPipeBytes = kRingBytes + kMidBytes;   // 224 KB
-// reduce phase (aliases ring + mid): three incoming 128 x 128 fp32 slices, rows padded to 132 floats (conflict-free
-// row-per-thread float4 access), then the LayerNorm exchange buffers
-constexpr int kRecvLd = kOs + 4;
-constexpr int kRecvSlot = 128 * kRecvLd * 4;             // 67 584 B
-constexpr int kOffLnX = 3 * kRecvSlot;                   // [2][128] float2: the two column halves of a row inside the CTA
-constexpr int kOffLnPeer = kOffLnX + 2 * 128 * 8;        // [4][128] float2: per-CTA row sums, by sender rank
+// G1 stage slots: 0, 1 = the ring; 2 ("X") = hidden-slice tiles 4-6 (written by E1(1), i.e. after all of G1); 3 ("Y") =
+// hidden-slice tiles 0-2 (written by E1(0): usable during G1(0) only)
+__host__ __device__ constexpr int slot_off(int s) { return s == 0 ? 0 : s == 1 ? kStage : s == 2 ? kRingBytes + 4 * kTileA : kRingBytes; }
+// k-block `it` (0-15: 8 of G1(0), 8 of G1(1)) -> slot and how often that slot has been used before
+__host__ __device__ constexpr int g1_slot(int it) { return it < 8 ? (it & 3) : (it - 8) % 3; }
+__host__ __device__ constexpr int g1_use(int it) { return it < 8 ? (it >> 2) : 2 + (it - 8) / 3; }
+constexpr int kG1Pre = 4;                    // W1 tiles requested before the dependency wait
+constexpr int kG2Stages = 3;
+// reduce phase (aliases the dead ring + hidden slice): per epilogue warp two fp32 slabs (32 rows x 32 columns, 128-byte
+// swizzled rows: residual in by TMA, result out by TMA) and one bf16 slab (32 rows x 64 columns) for the LayerNorm output
+constexpr int kOffSlabF = 0;                              // 8 warps x 2 x 4 KB
+constexpr int kOffSlabB = kOffSlabF + kEpiWarps * 2 * 4096;   // 8 warps x 4 KB
+constexpr int kOffLnX = kOffSlabB + kEpiWarps * 4096;     // [2][128] float2: the two column halves of a row inside the CTA
+constexpr int kOffLnPeer = kOffLnX + 2 * 128 * 8;         // [4][128] float2: per-CTA row sums, by sender rank
 static_assert(kOffLnPeer + kCl * 128 * 8 <= kPipeBytes, "reduce buffers must fit in the dead ring + mid region");
 constexpr int kBarBytes = 512;
 constexpr int kSmem = kPipeBytes + 1024 + kBarBytes;
+constexpr size_t kWsFloatsPerTile = (size_t)kCl * (kCl - 1) * 128 * kOs;   // 4 destinations x 3 senders x 128 x 128
 
 struct FfnClParams {
     const float* b1;
     const float* b2;
     const float* ln_gamma;   // null: no fused LayerNorm output
     const float* ln_beta;
-    bf16* ln_out;
-    float* x;                // [M][512] fp32: residual in, result out
+    float* ws;               // [tiles][4 dst][3 src][32 cells][128 rows] float4: partial slices in flight between CTAs
     float ln_eps;
     int M;
     double* gn_sums;
     int gn_cpg, gn_groups, gn_rows;
+    unsigned long long* dbg;   // optional clock64() stamps of CTA 0 (tools/ffn_cluster_phases.py): see PD_CSTAMP sites
 };
 
-__device__ __forceinline__ void st_cluster_f32x4(uint32_t cluster_addr, float4 v) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-
-// receive slot of sender s in CTA d (s != d): senders in rank order, skipping d itself
+// receive slot of sender s at destination d (s != d): senders in rank order, skipping d itself
 __device__ __forceinline__ int recv_slot(int s, int d) { return s < d ? s : s - 1; }
 
 template <bool GN>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
-                   const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ FfnClParams p) {
+                   const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x,
+                   const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ FfnClParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sRing = smem;
     uint8_t* sMid = smem + kRingBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes);
-    uint64_t* w_full = bars;                 // [2]
-    uint64_t* w_empty = w_full + kStages;    // [2]
-    uint64_t* acc_full = w_empty + kStages;  // [2]: G1(c) complete
+    uint64_t* w_full = bars;                 // [4]: G1 slots
+    uint64_t* w_empty = w_full + 4;          // [4]
+    uint64_t* v_full = w_empty + 4;          // [3]: G2 stages
+    uint64_t* v_empty = v_full + kG2Stages;  // [3]
+    uint64_t* acc_full = v_empty + kG2Stages;   // [2]: G1(c) complete
     uint64_t* mid_full = acc_full + 2;       // [2]: E1(c) has written its four k-blocks (and read acc[c] out)
-    uint64_t* acc2_full = mid_full + 2;      // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
+    uint64_t* acc2_full = mid_full + 2;      // [2]: output columns [0, 256) of the partial complete / all of it
+    uint64_t* res_bar = acc2_full + 2;       // [8 warps][2]: residual slabs landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int j = (int)ptx::cluster_ctarank();            // hidden slice / output-column slice of this CTA
-    const int row_tile = (blockIdx.x / kCl) * 128;
+    const int tile = blockIdx.x / kCl;
+    const int row_tile = tile * 128;
+    unsigned long long* dbg = blockIdx.x == 0 ? p.dbg : nullptr;
+#define PD_CSTAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+    const bool stamper = threadIdx.x == 64;   // lane 0 of the first epilogue warp
+    if (stamper) PD_CSTAMP(0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < 4; ++s) {
             ptx::mbar_init(&w_full[s], 1);
             ptx::mbar_init(&w_empty[s], 1);
+        }
+        for (int s = 0; s < kG2Stages; ++s) {
+            ptx::mbar_init(&v_full[s], 1);
+            ptx::mbar_init(&v_empty[s], 1);
         }
         for (int c = 0; c < 2; ++c) {
             ptx::mbar_init(&acc_full[c], 1);
             ptx::mbar_init(&mid_full[c], kEpiWarps);
         }
-        ptx::mbar_init(acc2_full, 1);
+        ptx::mbar_init(&acc2_full[0], 1);
+        ptx::mbar_init(&acc2_full[1], 1);
+        for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&res_bar[s], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -108,12 +131,15 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_w1);
         ptx::prefetch_tmap(&tmap_w2);
+        ptx::prefetch_tmap(&tmap_x);
+        ptx::prefetch_tmap(&tmap_ln);
     }
     // weight tiles of the first stages do not depend on the preceding kernel: requested before the dependency wait
     if (threadIdx.x == 0) {
-        for (int kb = 0; kb < kStages; ++kb) {
-            ptx::mbar_arrive_expect_tx(&w_full[kb], kStage);
-            ptx::tma_load_2d(sRing + kb * kStage + kTileA, &tmap_w1, &w_full[kb], kb * 64, j * kHs);
+#pragma unroll
+        for (int it = 0; it < kG1Pre; ++it) {
+            ptx::mbar_arrive_expect_tx(&w_full[g1_slot(it)], kStage);
+            ptx::tma_load_2d(smem + slot_off(g1_slot(it)) + kTileA, &tmap_w1, &w_full[g1_slot(it)], it * 64, j * kHs);
         }
     }
     if (warp == 1) {
@@ -126,6 +152,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     grid_dep_launch();
     grid_dep_wait();
+    if (stamper) PD_CSTAMP(1);
 
     // G2 step order: (k-block, output half); the first four steps need E1(0) only
     auto g2_step = [](int i, int* kb, int* nh) {
@@ -137,63 +164,71 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int c = 0; c < 2; ++c)
-                for (int kb = 0; kb < 8; ++kb, ++it) {
-                    const int s = it % kStages;
-                    uint8_t* st = sRing + s * kStage;
-                    if (it >= kStages) {   // the first kStages W1 tiles were requested in the prologue
-                        ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
-                        ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, j * kHs + c * 256);
-                    }
-                    ptx::tma_load_3d(st, &tmap_a, &w_full[s], kb * 64, row_tile, 0);
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int c = it >> 3, kb = it & 7, s = g1_slot(it), u = g1_use(it);
+                uint8_t* st = smem + slot_off(s);
+                if (it >= kG1Pre) {   // the first W1 tiles were requested in the prologue
+                    if (u > 0) ptx::mbar_wait(&w_empty[s], (u - 1) & 1);
+                    ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
+                    ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, j * kHs + c * 256);
                 }
-            for (int i = 0; i < 16; ++i, ++it) {
+                ptx::tma_load_3d(st, &tmap_a, &w_full[s], kb * 64, row_tile, 0);
+            }
+            // G2 stages alias ring slots 0 / 1: their last G1 uses (k-blocks 14 and 15) must have been consumed
+            ptx::mbar_wait(&w_empty[0], g1_use(14) & 1);
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
                 int kb, nh;
                 g2_step(i, &kb, &nh);
-                const int s = it % kStages;
-                ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
-                ptx::mbar_arrive_expect_tx(&w_full[s], kTileW);
-                ptx::tma_load_2d(sRing + s * kStage + kTileA, &tmap_w2, &w_full[s], j * kHs + kb * 64, nh * 256);
+                const int s = i % kG2Stages, u = i / kG2Stages;
+                if (i == 1) ptx::mbar_wait(&w_empty[1], g1_use(15) & 1);
+                if (u > 0) ptx::mbar_wait(&v_empty[s], (u - 1) & 1);
+                ptx::mbar_arrive_expect_tx(&v_full[s], kTileW);
+                ptx::tma_load_2d(smem + s * kTileW, &tmap_w2, &v_full[s], j * kHs + kb * 64, nh * 256);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256);
-            int it = 0;
-            for (int c = 0; c < 2; ++c) {
-                for (int kb = 0; kb < 8; ++kb, ++it) {
-                    const int s = it % kStages;
-                    ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sRing + s * kStage);
-                    const uint32_t b_addr = a_addr + kTileA;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ptx::umma_f16(tmem_base + c * 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
-                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&w_empty[s]);
+            for (int it = 0; it < 16; ++it) {
+                const int c = it >> 3, kb = it & 7, s = g1_slot(it), u = g1_use(it);
+                ptx::mbar_wait(&w_full[s], u & 1);
+                ptx::tc_fence_after();
+                if (it == 0) PD_CSTAMP(16);
+                const uint32_t a_addr = ptx::smem_u32(smem + slot_off(s));
+                const uint32_t b_addr = a_addr + kTileA;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_f16(tmem_base + c * 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
+                                  ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_commit(&w_empty[s]);
+                if (kb == 7) {
+                    ptx::umma_commit(&acc_full[c]);
+                    PD_CSTAMP(17 + c);
                 }
-                ptx::umma_commit(&acc_full[c]);
             }
-            for (int i = 0; i < 16; ++i, ++it) {
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
                 int kb, nh;
                 g2_step(i, &kb, &nh);
                 if (i == 0) { ptx::mbar_wait(&mid_full[0], 0); ptx::tc_fence_after(); }   // hidden k-blocks 0-3, acc[0] read out
-                if (i == 4) { ptx::mbar_wait(&mid_full[1], 0); ptx::tc_fence_after(); }   // k-blocks 4-7, acc[1] read out
-                const int s = it % kStages;
-                ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
+                if (i == 4) { PD_CSTAMP(19); ptx::mbar_wait(&mid_full[1], 0); ptx::tc_fence_after(); PD_CSTAMP(20); }   // 4-7
+                const int s = i % kG2Stages;
+                ptx::mbar_wait(&v_full[s], (i / kG2Stages) & 1);
                 ptx::tc_fence_after();
                 const uint32_t a_addr = ptx::smem_u32(sMid + kb * kTileA);
-                const uint32_t b_addr = ptx::smem_u32(sRing + s * kStage + kTileA);
+                const uint32_t b_addr = ptx::smem_u32(smem + s * kTileW);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     ptx::umma_f16(tmem_base + nh * 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
                                   ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(&w_empty[s]);
+                ptx::umma_commit(&v_empty[s]);
+                if (i == 11) ptx::umma_commit(&acc2_full[0]);   // output half 0 has seen all eight k-blocks
             }
-            ptx::umma_commit(acc2_full);
+            ptx::umma_commit(&acc2_full[1]);
+            PD_CSTAMP(21);
         }
     } else {
         // ---- E1: GELU'd hidden slice -> swizzled A tiles of G2 ----
@@ -204,6 +239,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int c = 0; c < 2; ++c) {
             ptx::mbar_wait(&acc_full[c], 0);
             ptx::tc_fence_after();
+            if (stamper) PD_CSTAMP(2 + 2 * c);
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {          // phase h: hidden columns [128 h, 128 h + 128) of the 256-wide sub-chunk
                 const int col = h * 128 + half * 64;   // this warp's 64 columns = k-block (4 c + 2 h + half) of the slice
@@ -233,23 +269,40 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&mid_full[c]);
+            if (stamper) PD_CSTAMP(3 + 2 * c);
         }
-        ptx::mbar_wait(acc2_full, 0);       // this CTA's partial is complete; ring and hidden slice are dead
-        ptx::tc_fence_after();
     }
 
-    // ---- R: reduce-scatter of the four partials through distributed shared memory ----
-    ptx::cluster_sync_all();                // every CTA of the cluster is past its MMAs: their ring / mid regions may be written
+    // ---- R: reduce-scatter of the four partials through the L2-resident workspace ----
     const int e = warp - 2, q = warp & 3, half = e >> 2;
     const int r = q * 32 + lane;            // row inside the tile (epilogue threads)
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t recv_base = ptx::smem_u32(smem);
+    const int col0 = j * kOs + half * 64;   // the thread's 64 finished columns
+    const int row0 = row_tile + q * 32;     // the warp's 32 rows
+    uint8_t* slabF = smem + kOffSlabF + (warp >= 2 ? e : 0) * (2 * 4096);
+    uint8_t* slabB = smem + kOffSlabB + (warp >= 2 ? e : 0) * 4096;
+    uint64_t* my_bar = res_bar + 2 * (warp >= 2 ? e : 0);
+    float4* ws4 = reinterpret_cast<float4*>(p.ws) + (size_t)tile * (kWsFloatsPerTile / 4);
     if (warp >= 2) {
+        // slices for the owners of output columns [0, 256) leave while G2 still works on columns [256, 512)
 #pragma unroll 1
-        for (int dd = 1; dd < kCl; ++dd) {
-            const int d = (j + dd) & (kCl - 1);                       // destination CTA: owner of output columns [128 d, +128)
-            const uint32_t dst = ptx::mapa(recv_base + (uint32_t)(recv_slot(j, d) * kRecvSlot + r * kRecvLd * 4 + half * 64 * 4),
-                                           (uint32_t)d);
+        for (int d = 0; d < kCl; ++d) {                               // destination CTA: owner of output columns [128 d, +128)
+            if (d == 0) { ptx::mbar_wait(&acc2_full[0], 0); ptx::tc_fence_after(); }
+            if (d == 2) {
+                ptx::mbar_wait(&acc2_full[1], 0);   // this CTA's partial is complete; ring and hidden slice are dead
+                ptx::tc_fence_after();
+                if (stamper) PD_CSTAMP(6);
+                if (lane == 0) {   // residual rows of the warp's two 32-column groups (rows past M arrive as zeros)
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        ptx::mbar_arrive_expect_tx(&my_bar[g], 4096);
+                        ptx::tma_load_3d(slabF + g * 4096, &tmap_x, &my_bar[g], col0 + g * 32, row0, 0);
+                    }
+                }
+            }
+            if (d == j) continue;
+            float4* dst = ws4 + (size_t)((d * 3 + recv_slot(j, d)) * 32 + half * 16) * 128 + r;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 uint32_t v[32];
@@ -257,68 +310,87 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    st_cluster_f32x4(dst + (uint32_t)((g * 32 + 4 * i) * 4),
-                                     make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                 __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+                    dst[(g * 8 + i) * 128] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
             }
         }
+        if (stamper) PD_CSTAMP(8);
     }
-    ptx::cluster_sync_all();                // all slices have landed (release / acquire at cluster scope)
-    float val[64];                          // the thread's 64 finished values: row r, columns 128 j + 64 half + [0, 64)
+    ptx::cluster_sync_all();                // release / acquire at cluster scope: every CTA's slices are visible
+    if (stamper) PD_CSTAMP(9);
     float s1 = 0.f, s2 = 0.f;
-    const int grow = row_tile + r;
-    const bool row_ok = grow < p.M;
-    const int col0 = j * kOs + half * 64;
+    const bool row_ok = row_tile + r < p.M;
     if (warp >= 2) {
+        const float4* src = ws4 + (size_t)(j * 3 * 32 + half * 16) * 128 + r;   // + (slot * 32 + cell) * 128
+        // four batches of four 16-byte cells (batch b: column group g = b >> 1, cells 4 (b & 1) + [0, 4)); the loads of
+        // batch b + 1 are in flight while batch b is combined (24 x 16 bytes per thread against ~1 000 cycles of L2 latency)
+        float4 part[2][3][4];
+        auto fetch = [&](int b, float4 (&dstp)[3][4]) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(t_lane + (uint32_t)(col0 + g * 32), v);
-            ptx::tmem_ld_wait();
+            for (int sl = 0; sl < 3; ++sl)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) dstp[sl][i] = __ldcg(src + (size_t)(sl * 32 + b * 4 + i) * 128);
+        };
+        fetch(0, part[0]);
+        uint32_t v[32];
+        float gs[8], gq[8];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int g = b >> 1, hb = b & 1;
+            if (b + 1 < 4) fetch(b + 1, part[(b + 1) & 1]);
+            if (hb == 0) {
+                ptx::tmem_ld_32x32(t_lane + (uint32_t)(col0 + g * 32), v);
+                ptx::tmem_ld_wait();
+                ptx::mbar_wait(&my_bar[g], 0);
+            }
+            uint8_t* my_row = slabF + g * 4096 + lane * 128;
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const int i = hb * 4 + ii;
+                const float4 own = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                const float4 (&pt)[3][4] = part[b & 1];
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int s = 0; s < kCl; ++s) {   // rank order, whoever computes: deterministic and batch-invariant
+                    // slot of sender s at this destination: s < j -> s, s > j -> s - 1 (j is uniform per CTA)
                     float4 t;
-                    if (s == j) {
-                        t = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                        __uint_as_float(v[4 * i + 3]));
-                    } else {
-                        t = *reinterpret_cast<const float4*>(smem + recv_slot(s, j) * kRecvSlot + r * kRecvLd * 4 +
-                                                             (half * 64 + g * 32 + 4 * i) * 4);
-                    }
+                    if (s == 0) t = j == 0 ? own : pt[0][ii];
+                    else if (s == 1) t = j == 1 ? own : (j < 1 ? pt[0][ii] : pt[1][ii]);
+                    else if (s == 2) t = j == 2 ? own : (j < 2 ? pt[1][ii] : pt[2][ii]);
+                    else t = j == 3 ? own : pt[2][ii];
                     if (s == 0) acc = t;
                     else { acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
                 }
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + g * 32 + 4 * i));
-                float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_ok) res = *reinterpret_cast<const float4*>(p.x + (size_t)grow * kC + col0 + g * 32 + 4 * i);
+                float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                const float4 res = *cell;
                 acc.x = (acc.x + bb.x) + res.x; acc.y = (acc.y + bb.y) + res.y;
                 acc.z = (acc.z + bb.z) + res.z; acc.w = (acc.w + bb.w) + res.w;
-                if (row_ok) *reinterpret_cast<float4*>(p.x + (size_t)grow * kC + col0 + g * 32 + 4 * i) = acc;
-                val[g * 32 + 4 * i] = acc.x; val[g * 32 + 4 * i + 1] = acc.y;
-                val[g * 32 + 4 * i + 2] = acc.z; val[g * 32 + 4 * i + 3] = acc.w;
-                s1 += (acc.x + acc.y) + (acc.z + acc.w);
-                s2 += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+                *cell = acc;
+                gs[i] = (acc.x + acc.y) + (acc.z + acc.w);
+                gq[i] = (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+                s1 += gs[i];
+                s2 += gq[i];
             }
-            if constexpr (GN) {   // statistics for the GroupNorm that reads this output (the warp's 32 rows: one sample)
-                float gs[8], gq[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float a = val[g * 32 + 4 * i], b = val[g * 32 + 4 * i + 1], c = val[g * 32 + 4 * i + 2],
-                                d = val[g * 32 + 4 * i + 3];
-                    gs[i] = (a + b) + (c + d);
-                    gq[i] = (a * a + b * b) + (c * c + d * d);
+            if (hb == 1) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_3d(&tmap_x, slabF + g * 4096, col0 + g * 32, row0, 0);   // rows past M are clipped
+                    ptx::bulk_commit();
                 }
-                const int shift = p.gn_cpg == 8 ? 3 : (p.gn_cpg == 16 ? 4 : 5);
-                const int gsample = (row_tile + q * 32) / p.gn_rows;
-                if (row_tile + q * 32 < p.M)
-                    gn_chunk_accumulate(gs, gq, row_ok, p.gn_cpg,
-                                        p.gn_sums + ((size_t)gsample * p.gn_groups + ((col0 + g * 32) >> shift)) * 2, lane);
+                if constexpr (GN) {   // statistics for the GroupNorm that reads this output (the warp's 32 rows: one sample)
+                    const int shift = p.gn_cpg == 8 ? 3 : (p.gn_cpg == 16 ? 4 : 5);
+                    const int gsample = row0 / p.gn_rows;
+                    if (row0 < p.M)
+                        gn_chunk_accumulate(gs, gq, row_ok, p.gn_cpg,
+                                            p.gn_sums + ((size_t)gsample * p.gn_groups + ((col0 + g * 32) >> shift)) * 2, lane);
+                }
             }
         }
     }
+    if (stamper) PD_CSTAMP(10);
     if (p.ln_gamma != nullptr) {
         // ---- LN: row statistics over all 512 columns = 2 threads x 4 CTAs ----
         float2* ln_x = reinterpret_cast<float2*>(smem + kOffLnX);
@@ -339,6 +411,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
         ptx::cluster_sync_all();
+        if (stamper) PD_CSTAMP(11);
         if (warp >= 2) {
             float tot1 = 0.f, tot2 = 0.f;
 #pragma unroll
@@ -350,34 +423,43 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const float mean = tot1 * (1.0f / kC);
             const float var = fmaxf(tot2 * (1.0f / kC) - mean * mean, 0.f);
             const float rstd = rsqrtf(var + p.ln_eps);
-            if (row_ok) {
-                bf16* dst = p.ln_out + (size_t)grow * kC + col0;
+            uint8_t* brow = slabB + lane * 128;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {   // 8 values -> one 16-byte store
-                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i));
-                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i + 4));
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i + 4));
-                    const float* a = val + 8 * i;
-                    uint4 pk;
-                    pk.x = pack_bf16x2(fmaf((a[0] - mean) * rstd, g0.x, b0.x), fmaf((a[1] - mean) * rstd, g0.y, b0.y));
-                    pk.y = pack_bf16x2(fmaf((a[2] - mean) * rstd, g0.z, b0.z), fmaf((a[3] - mean) * rstd, g0.w, b0.w));
-                    pk.z = pack_bf16x2(fmaf((a[4] - mean) * rstd, g1.x, b1.x), fmaf((a[5] - mean) * rstd, g1.y, b1.y));
-                    pk.w = pack_bf16x2(fmaf((a[6] - mean) * rstd, g1.z, b1.z), fmaf((a[7] - mean) * rstd, g1.w, b1.w));
-                    *reinterpret_cast<uint4*>(dst + 8 * i) = pk;
-                }
+            for (int i = 0; i < 8; ++i) {   // 8 values (two cells of the fp32 slabs) -> one 16-byte cell of the bf16 slab
+                const uint8_t* frow = slabF + (i >> 2) * 4096 + lane * 128;
+                const float4 a0 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * (i & 3)) ^ sw) << 4));
+                const float4 a1 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * (i & 3) + 1) ^ sw) << 4));
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i + 4));
+                uint4 pk;
+                pk.x = pack_bf16x2(fmaf((a0.x - mean) * rstd, g0.x, b0.x), fmaf((a0.y - mean) * rstd, g0.y, b0.y));
+                pk.y = pack_bf16x2(fmaf((a0.z - mean) * rstd, g0.z, b0.z), fmaf((a0.w - mean) * rstd, g0.w, b0.w));
+                pk.z = pack_bf16x2(fmaf((a1.x - mean) * rstd, g1.x, b1.x), fmaf((a1.y - mean) * rstd, g1.y, b1.y));
+                pk.w = pack_bf16x2(fmaf((a1.z - mean) * rstd, g1.z, b1.z), fmaf((a1.w - mean) * rstd, g1.w, b1.w));
+                *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(i) ^ sw) << 4)) = pk;
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_3d(&tmap_ln, slabB, col0, row0, 0);
+                ptx::bulk_commit();
             }
         }
     }
-    // nobody may exit while a peer can still write into this CTA's shared memory / read its own: all DSMEM traffic is
-    // complete at the barriers above (the LN exchange's is followed by a cluster barrier; without LN the second barrier)
+    if (warp >= 2 && lane == 0) ptx::bulk_wait_read<0>();   // the slabs must outlive the bulk stores' reads
+    // nobody may exit while a peer can still write into this CTA's shared memory: the only DSMEM traffic is the LayerNorm
+    // exchange, which is complete at the cluster barrier that follows it
+    if (stamper) PD_CSTAMP(12);
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+#undef PD_CSTAMP
 }
 
 struct FfnClusterOpImpl {
-    CUtensorMap tmap_a, tmap_w1, tmap_w2;
+    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln;
     FfnClParams p;
     int tiles;
     WRange own_w;
@@ -386,11 +468,14 @@ static_assert(sizeof(FfnClusterOpImpl) <= sizeof(FfnClusterOp), "FfnClusterOp st
 
 }  // namespace
 
+size_t ffn_cluster_workspace_bytes(int M) { return (size_t)ceil_div(M, 128) * kWsFloatsPerTile * sizeof(float); }
+
 int ffn_cluster_make(FfnClusterOp* op_, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
-                     const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out, float ln_eps) {
+                     const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out, float ln_eps,
+                     float* workspace) {
     PD_TRY(gemm_init());
     FfnClusterOpImpl* op = reinterpret_cast<FfnClusterOpImpl*>(op_);
-    PD_CHECK(ln_in && w1 && b1 && w2 && b2 && x_inout && M >= 1, PD_ERR_ARG, "ffn_cluster: null argument");
+    PD_CHECK(ln_in && w1 && b1 && w2 && b2 && x_inout && workspace && M >= 1, PD_ERR_ARG, "ffn_cluster: null argument");
     PD_CHECK((ln_gamma != nullptr) == (ln_out != nullptr) && (ln_gamma != nullptr) == (ln_beta != nullptr), PD_ERR_ARG,
              "ffn_cluster: LayerNorm output needs gamma, beta and the output tensor");
     static bool attr_set = false;
@@ -407,9 +492,16 @@ int ffn_cluster_make(FfnClusterOp* op_, const bf16* ln_in, int M, const bf16* w1
     const uint32_t box[2] = {64, 256};
     PD_TRY(tmap_encode_sw128(&op->tmap_w1, true, 2, w1, d1, s1, box));
     PD_TRY(tmap_encode_sw128(&op->tmap_w2, true, 2, w2, d2, s2, box));
-    op->p.b1 = b1; op->p.b2 = b2; op->p.ln_gamma = ln_gamma; op->p.ln_beta = ln_beta; op->p.ln_out = ln_out;
-    op->p.x = x_inout; op->p.ln_eps = ln_eps; op->p.M = M;
+    // epilogue slabs: 32 rows x 128 bytes (32 fp32 columns of x / 64 bf16 columns of the LayerNorm output)
+    const uint64_t dims_x[3] = {kC, (uint64_t)M, 1}, st_x[2] = {kC * 4, (uint64_t)kC * 4 * M};
+    const uint32_t box_x[3] = {32, 32, 1};
+    PD_TRY(tmap_encode_sw128(&op->tmap_x, false, 3, x_inout, dims_x, st_x, box_x));
+    const uint32_t box_ln[3] = {64, 32, 1};
+    PD_TRY(tmap_encode_sw128(&op->tmap_ln, true, 3, ln_out ? ln_out : ln_in, dims_a, st_a, box_ln));
+    op->p.b1 = b1; op->p.b2 = b2; op->p.ln_gamma = ln_gamma; op->p.ln_beta = ln_beta;
+    op->p.ws = workspace; op->p.ln_eps = ln_eps; op->p.M = M;
     op->p.gn_sums = nullptr; op->p.gn_cpg = op->p.gn_groups = op->p.gn_rows = 0;
+    op->p.dbg = nullptr;
     op->tiles = ceil_div(M, 128);
     op->own_w = WRange{};
     op->own_w.p[0] = reinterpret_cast<const uint8_t*>(w1); op->own_w.n[0] = (uint32_t)((size_t)kHid * kC * 2);
@@ -424,16 +516,20 @@ int ffn_cluster_set_gn(FfnClusterOp* op_, double* gn_sums, int groups, int rows)
     return PD_OK;
 }
 
+void ffn_cluster_set_dbg(FfnClusterOp* op_, unsigned long long* stamps) {
+    reinterpret_cast<FfnClusterOpImpl*>(op_)->p.dbg = stamps;
+}
+
 WRange ffn_cluster_weights(const FfnClusterOp& op_) { return reinterpret_cast<const FfnClusterOpImpl&>(op_).own_w; }
 
 int ffn_cluster_launch(const FfnClusterOp& op_, cudaStream_t st) {
     const FfnClusterOpImpl& op = reinterpret_cast<const FfnClusterOpImpl&>(op_);
     if (op.p.gn_sums)
         PD_CUDA(launch_pdl(ffn_cluster_kernel<true>, dim3(op.tiles * kCl), dim3(kThreads), (size_t)kSmem, st, dim3(kCl, 1, 1),
-                           op.tmap_a, op.tmap_w1, op.tmap_w2, op.p));
+                           op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.p));
     else
         PD_CUDA(launch_pdl(ffn_cluster_kernel<false>, dim3(op.tiles * kCl), dim3(kThreads), (size_t)kSmem, st, dim3(kCl, 1, 1),
-                           op.tmap_a, op.tmap_w1, op.tmap_w2, op.p));
+                           op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.p));
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

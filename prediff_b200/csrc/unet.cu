@@ -51,6 +51,7 @@ struct UNet::BatchPlan {
     std::vector<std::unique_ptr<DevMem>> sk_mem;
     DevMem sk_partials;
     int sk_slots = 0;
+    DevMem ffn_ws;   // partial slices of the width-512 cluster FFN (ffn_cluster.cu), shared by the plan's FFN launches
     GemmOp final_op;
     size_t t_slot = 0, in_slot = 0, out_slot = 0;
     Bufs& bufs_storage() { return bufs; }
@@ -549,8 +550,13 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             // statistics) in one kernel, hidden dimension split over a 4-CTA cluster (ffn_cluster.cu)
             FfnClusterOp op;
             const bool next_ln = i < last;
+            if (building_->ffn_ws.bytes < ffn_cluster_workspace_bytes(P)) {
+                PD_CHECK(building_->ffn_ws.p == nullptr, PD_ERR_STATE, "unet: cluster-FFN workspace sized twice");
+                PD_TRY(building_->ffn_ws.alloc(ffn_cluster_workspace_bytes(P)));
+            }
             PD_TRY(ffn_cluster_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
-                                    next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f));
+                                    next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f,
+                                    building_->ffn_ws.as<float>()));
             if (gn_next && i == last) PD_TRY(ffn_cluster_set_gn(&op, gn_next, 32, T * H * W));
             const double fl = 2.0 * 2.0 * (double)P * C * 4 * C;
             pl.gemm_flops += fl;
