@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -130,6 +131,28 @@ __device__ __forceinline__ float gelu_fast(float x) {
     const float e = ex2_approx(p);       // erfc(|x| / sqrt 2)
     const float h = 0.5f * fabsf(x);
     return fmaf(0.5f, x, fmaf(-h, e, h));
+}
+
+// Two GELUs whose results are stored as bf16 (the A operand of the next GEMM), returned as a packed bf16x2: the same
+// max(x, 0) - 0.5 |x| 2^P(|x|) identity, with the exponent polynomial evaluated for both values at once in half2
+// (degree 4: in fp16 arithmetic the error floor is ~1e-3 in P whatever the degree) and everything that touches the
+// magnitude of the result - the exponential, |x|, the final multiply-add - in fp32. 9.5 instructions per element instead
+// of 14.75 (the fused-FFN GELU epilogues are issue-bound: two warps per scheduler, 128 elements per thread and chunk).
+// Error vs the exact GELU after the bf16 rounding: rel-RMS 1.530e-3 against 1.529e-3 for exact -> bf16 (2.5 M points,
+// N(0, 1.5) and uniform [-8, 8]; tools/gelu_half2_check.py); 12 % of the results differ by one bf16 ulp.
+__device__ __forceinline__ uint32_t gelu_pair_bf16(float x0, float x1) {
+    const __half2 xh = __floats2half2_rn(x0, x1);
+    const __half2 ax = __hmin2(__habs2(xh), __float2half2_rn(5.939697f));
+    __half2 p = __hfma2(__float2half2_rn(3.7584315550e-03f), ax, __float2half2_rn(-4.3446286322e-02f));
+    p = __hfma2(p, ax, __float2half2_rn(-4.6924023712e-01f));
+    p = __hfma2(p, ax, __float2half2_rn(-1.1464713489f));
+    p = __hfma2(p, ax, __float2half2_rn(-6.8215604968e-04f));
+    const float2 pf = __half22float2(p);
+    const float e0 = ex2_approx(pf.x), e1 = ex2_approx(pf.y);   // erfc(|x| / sqrt 2)
+    const float r0 = fmaf(-0.5f * fabsf(x0), e0, fmaxf(x0, 0.f));
+    const float r1 = fmaf(-0.5f * fabsf(x1), e1, fmaxf(x1, 0.f));
+    __nv_bfloat162 t = __floats2bfloat162_rn(r0, r1);
+    return *reinterpret_cast<uint32_t*>(&t);
 }
 
 // ---- operand precision ------------------------------------------------------------------------------------------

@@ -420,18 +420,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const float* bias = b1_s + c * kChunk + col;
 #pragma unroll
                 for (int cell = 0; cell < 8; ++cell) {
-                    float a[8];
-                    const float4 bv0 = *reinterpret_cast<const float4*>(bias + cell * 8);
-                    const float4 bv1 = *reinterpret_cast<const float4*>(bias + cell * 8 + 4);
+                    const float4 bv0 = *(reinterpret_cast<const float4*>(bias + cell * 8));
+                    const float4 bv1 = *(reinterpret_cast<const float4*>(bias + cell * 8 + 4));
                     const float bb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t raw = cell < 4 ? v0[cell * 8 + k] : v1[(cell - 4) * 8 + k];
-                        a[k] = gelu_fast(__uint_as_float(raw) + bb[k]);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t r0 = cell < 4 ? v0[cell * 8 + 2 * k] : v1[(cell - 4) * 8 + 2 * k];
+                        const uint32_t r1 = cell < 4 ? v0[cell * 8 + 2 * k + 1] : v1[(cell - 4) * 8 + 2 * k + 1];
+                        pk[k] = gelu_pair_bf16(__uint_as_float(r0) + bb[2 * k], __uint_as_float(r1) + bb[2 * k + 1]);
                     }
                     *reinterpret_cast<uint4*>(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4)) =
-                        make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]),
-                                   pack_bf16x2(a[6], a[7]));
+                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
                 ptx::fence_proxy_async();
                 __syncwarp();

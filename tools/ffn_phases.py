@@ -28,3 +28,21 @@ print("MMA warp ready @%d, A landed @%d" % (s[1] - t0, s[2] - t0))
 for c in range(4):
     print(f"chunk {c}: E1 begin @{s[12 + 2 * c] - t0:6d} dur {s[13 + 2 * c] - s[12 + 2 * c]:5d} | G2 issued @{s[3 + c] - t0:6d}")
 print(f"acc2 complete @{s[28] - t0}, final epilogue {s[29] - s[28]} cycles, exit @{s[30] - t0}")
+
+# the PROJ variant (attention projection + residual + pre-norm fused in front): the level-0 stack kernel
+att = torch.randn(M, C, device=dev).bfloat16()
+wp = (torch.randn(C, C, device=dev) * C ** -0.5).bfloat16()
+bp = torch.randn(C, device=dev) * 0.1
+scratch = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+st.zero_()
+for _ in range(3):
+    L.check(L.lib().pd_op_proj_ffn_fused(L.ptr(att), L.ptr(wp), L.ptr(bp), L.ptr(g), L.ptr(b), L.ptr(scratch), L.ptr(w1),
+                                         L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(x), L.ptr(g), L.ptr(b), L.ptr(ln), M,
+                                         L.ptr(st), L.stream_ptr()))
+torch.cuda.synchronize()
+s = st.cpu().tolist()
+t0 = s[0]
+print("PROJ variant: MMA warp ready @%d, G1(0) issued @%d" % (s[1] - t0, s[2] - t0))
+for c in range(4):
+    print(f"chunk {c}: E1 begin @{s[12 + 2 * c] - t0:6d} dur {s[13 + 2 * c] - s[12 + 2 * c]:5d} | G2 issued @{s[3 + c] - t0:6d}")
+print(f"acc2 complete @{s[28] - t0}, final epilogue {s[29] - s[28]} cycles, exit @{s[30] - t0}")
