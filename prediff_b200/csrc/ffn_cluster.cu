@@ -247,7 +247,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 ptx::tmem_ld_32x32(t_lane + c * 256 + col, v0);
                 ptx::tmem_ld_32x32(t_lane + c * 256 + col + 32, v1);
                 ptx::tmem_ld_wait();
-                uint8_t* my_row = sMid + (c * 4 + h * 2 + half) * kTileA + (q * 32 + lane) * 128;
+                const uint32_t my_row = ptx::smem_u32(sMid + (c * 4 + h * 2 + half) * kTileA + (q * 32 + lane) * 128);
                 const float* bias = p.b1 + j * kHs + c * 256 + col;
 #pragma unroll
                 for (int cell = 0; cell < 8; ++cell) {
@@ -261,8 +261,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const uint32_t r1 = cell < 4 ? v0[cell * 8 + 2 * k + 1] : v1[(cell - 4) * 8 + 2 * k + 1];
                         pk[k] = gelu_pair_bf16(__uint_as_float(r0) + bb[2 * k], __uint_as_float(r1) + bb[2 * k + 1]);
                     }
-                    *reinterpret_cast<uint4*>(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4)) =
-                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    ptx::st_shared_v4(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
             }
             ptx::fence_proxy_async();

@@ -4,12 +4,18 @@
 // input `ln` produced by the preceding epilogue. Replaces the FFN-1 GEMM (bf16 `mid` round trip through HBM/L2:
 // 27 MB written + read per call at batch 4) and the FFN-2 GEMM.
 //
-//   warp 0    : TMA producer - 3-stage ring of 48 KB stages: GEMM-1 stages carry an A k-block (128 x 64) + a W1 tile
-//               (256 hidden rows x 64), GEMM-2 stages a W2 tile (256 output rows x 64)
+//   warp 0    : TMA producer - the A operand of GEMM-1 (128 x 256 bf16 = four 16 KB k-block tiles) is RESIDENT in shared
+//               memory for all four hidden chunks; a 3-stage ring of 32 KB stages carries nothing but weight tiles (W1 tile
+//               = 256 hidden rows x 64, W2 tile = 256 output rows x 64, PROJ: Wp tiles first), so every ring load is
+//               independent of the preceding kernel and of this kernel's own epilogues. (Until round 2 the A k-blocks
+//               travelled with the W1 tiles in 48 KB stages and were re-read for every chunk; one trip of a stage round
+//               the ring - commit, producer wake-up, two TMA issues at ~270 cycles each, ~800 cycles of transfer, consumer
+//               wake-up - took ~1 500 cycles, so three stages sustained one k-block per ~730 cycles against the tensor
+//               core's 512, with ONE CTA on the chip as with 148: tools/micro/tma_latency.cu, tools/ffn_phases.py.)
 //   warp 1    : one lane issues tcgen05.mma 128 x 256 x 16 (an N = 128 MMA costs the same ~128 cycles, measured):
 //                 G1(c):  acc1  = ln . W1[c]^T                       c = 0..3, 256 hidden columns per chunk
 //                 G2h(c): acc2 += gelu_c[:, 128h : 128h+128] . W2[:, ...]^T   (two K halves, each as soon as it is ready)
-//               order G1(0) | G1(c+1) G2h0(c) G2h1(c) | ... : GEMM-1 of the next chunk and the first half of GEMM-2 run
+//               order G1(0) | G2h0(c) G1(c+1) G2h1(c) | ... : the first half of GEMM-2 and GEMM-1 of the next chunk run
 //               under the second half of this chunk's GELU epilogue
 //   warps 2-9 : E1(c), two phases of 128 hidden columns: acc1 (TMEM) -> + b1 -> GELU -> bf16 -> 128B-swizzled K-major
 //               smem tiles = the A operand of G2(c); acc1 is handed back right after the second phase's TMEM loads;
@@ -30,14 +36,16 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileA = 128 * 64 * 2;         // 16 KB: 128 rows x 64 bf16
 constexpr int kTileW = 256 * 64 * 2;         // 32 KB: 256 rows x 64 bf16
-constexpr int kStage = kTileA + kTileW;      // 48 KB
+constexpr int kABytes = 4 * kTileA;          // 64 KB: the resident A operand (four k-blocks)
 constexpr int kStages = 3;
-constexpr int kRingBytes = kStages * kStage; // 144 KB
+constexpr int kRingBytes = kStages * kTileW; // 96 KB
 constexpr int kMidBytes = 4 * kTileA;        // 64 KB: four k-blocks of the GELU'd chunk
-constexpr int kPipeBytes = kRingBytes + kMidBytes;   // 208 KB
-constexpr int kBarBytes = 1024;
-constexpr int kSmem = kPipeBytes + 1024 + kBarBytes + kHid * 4 + kC * 4 + 2 * kC * 4 + kEpiWarps * 32 * 8;
-static_assert(kRingBytes >= kEpiWarps * 4 * 4096, "fp32 epilogue slabs alias the ring");
+constexpr int kPipeBytes = kABytes + kRingBytes + kMidBytes;   // 224 KB
+constexpr int kBarBytes = 512;
+// the dynamic shared memory window is declared 1024-byte aligned (checked at kernel start): no alignment slack
+constexpr int kSmem = kPipeBytes + kBarBytes + kEpiWarps * 32 * 8;
+static_assert(kSmem <= 232448, "over the 227 KB per-CTA limit");
+static_assert(kABytes + kRingBytes >= kEpiWarps * 4 * 4096, "fp32 epilogue slabs alias A + the ring");
 static_assert(kMidBytes >= kEpiWarps * 2 * 4096, "bf16 LayerNorm slabs alias mid");
 
 struct FfnParams {
@@ -58,23 +66,24 @@ struct FfnParams {
     WRange pf;               // weights of the next GEMM of the plan, requested into L2 at kernel start (common.cuh)
 };
 
-// PROJ = false: A operand of GEMM-1 is the (already normalised) tensor behind tmap_a; acc2 starts at zero and the
-//               residual is added in the final epilogue.
+// PROJ = false: the A operand of GEMM-1 is the (already normalised) tensor behind tmap_a, loaded once; acc2 starts at zero
+//               and the residual is added in the final epilogue.
 // PROJ = true : the kernel first builds x1 = x + bp + att . Wp^T in the acc2 columns of TMEM (the epilogue warps preset
-//               acc2 with x + bp through tcgen05.st while the first operands are in flight, GEMM-0 accumulates on top),
-//               normalises it (the FFN's pre-norm) into the bf16 tensor behind tmap_a - an L2-resident round trip of the
-//               tile's own rows - and GEMM-2 keeps accumulating onto x1, so no residual is ever re-loaded.
+//               acc2 with x + bp through tcgen05.st while the first operands are in flight; GEMM-0 reads `att` from the
+//               resident A tiles and accumulates on top), normalises it (the FFN's pre-norm) straight into the resident A
+//               tiles as swizzled bf16 - no round trip through global memory - and GEMM-2 keeps accumulating onto x1, so
+//               no residual is ever re-loaded.
 template <bool PROJ, bool GN>   // GN: also accumulate GroupNorm statistics of the new x rows (FfnParams::gn_sums)
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x,
                  const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ CUtensorMap tmap_att,
-                 const __grid_constant__ CUtensorMap tmap_wp, const __grid_constant__ CUtensorMap tmap_ln1st,
+                 const __grid_constant__ CUtensorMap tmap_wp,
                  const __grid_constant__ FfnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sRing = smem;
-    uint8_t* sMid = smem + kRingBytes;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sRing = smem + kABytes;
+    uint8_t* sMid = smem + kABytes + kRingBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPipeBytes);
     uint64_t* w_full = bars;                 // [kStages]
     uint64_t* w_empty = w_full + kStages;    // [kStages]
@@ -84,14 +93,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* mid_empty = mid_full + 2;      // [2]
     uint64_t* acc2_full = mid_empty + 2;     // [1] (PROJ: phase 0 = x1 complete, phase 1 = FFN complete)
     uint64_t* acc2_init = acc2_full + 1;     // [1] PROJ: acc2 preset with x + bp
-    uint64_t* ln1_ready = acc2_init + 1;     // [1] PROJ: LayerNorm(x1) stored behind tmap_a
-    uint64_t* res_bar = ln1_ready + 1;       // [kEpiWarps][4]
+    uint64_t* a_full = acc2_init + 1;        // [1] the A tiles have landed (PROJ: `att`; else the pre-norm input)
+    uint64_t* a_ready = a_full + 1;          // [1] PROJ: LayerNorm(x1) written into the A tiles by the epilogue warps
+    uint64_t* res_bar = a_ready + 1;         // [kEpiWarps][4]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * kEpiWarps);
-    float* b1_s = reinterpret_cast<float*>(smem + kPipeBytes + kBarBytes);   // [1024]
-    float* b2_s = b1_s + kHid;                                               // [256]
-    float* ln_g = b2_s + kC;
-    float* ln_b = ln_g + kC;
-    float2* ln_x = reinterpret_cast<float2*>(ln_b + kC);
+    static_assert((15 + 4 * kEpiWarps) * 8 + 4 <= kBarBytes, "barrier block too small");
+    float2* ln_x = reinterpret_cast<float2*>(smem + kPipeBytes + kBarBytes);
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled tiles need the declared alignment
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -114,7 +122,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         ptx::mbar_init(acc2_full, 1);
         ptx::mbar_init(acc2_init, kEpiWarps);
-        ptx::mbar_init(ln1_ready, kEpiWarps);
+        ptx::mbar_init(a_full, 1);
+        ptx::mbar_init(a_ready, kEpiWarps);
         for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -128,16 +137,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (PROJ) {
             ptx::prefetch_tmap(&tmap_att);
             ptx::prefetch_tmap(&tmap_wp);
-            ptx::prefetch_tmap(&tmap_ln1st);
         }
     }
-    // Weight tiles of the first kStages stages (Wp when PROJ, else W1 chunk 0) do not depend on the preceding kernel:
-    // requested before the dependency wait (common.cuh); the activation halves follow after it.
+    // The first kStages weight tiles (Wp when PROJ, else W1 chunk 0) do not depend on the preceding kernel: requested
+    // before the dependency wait (common.cuh); the activation tiles follow after it.
     if (threadIdx.x == 0) {
         for (int kb = 0; kb < kStages; ++kb) {
-            ptx::mbar_arrive_expect_tx(&w_full[kb], kStage);
-            if (PROJ) ptx::tma_load_2d(sRing + kb * kStage + kTileA, &tmap_wp, &w_full[kb], kb * 64, 0);
-            else ptx::tma_load_2d(sRing + kb * kStage + kTileA, &tmap_w1, &w_full[kb], kb * 64, 0);
+            ptx::mbar_arrive_expect_tx(&w_full[kb], kTileW);
+            ptx::tma_load_2d(sRing + kb * kTileW, PROJ ? &tmap_wp : &tmap_w1, &w_full[kb], kb * 64, 0);
         }
     }
     if (warp == 1) {
@@ -155,50 +162,29 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
+            // the resident A operand: `att` for GEMM-0 (PROJ; the epilogue warps overwrite it with LayerNorm(x1) afterwards)
+            // or the pre-norm input of GEMM-1
+            ptx::mbar_arrive_expect_tx(a_full, kABytes);
+            for (int kb = 0; kb < 4; ++kb)
+                ptx::tma_load_3d(sA + kb * kTileA, PROJ ? &tmap_att : &tmap_a, a_full, kb * 64, row_tile, 0);
             int it = 0;
-            if (PROJ) {   // GEMM-0: att k-block + Wp tile per stage
-                for (int kb = 0; kb < 4; ++kb, ++it) {
-                    const int s = it % kStages;
-                    uint8_t* st = sRing + s * kStage;
-                    if (it >= kStages) {
-                        ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
-                        ptx::tma_load_2d(st + kTileA, &tmap_wp, &w_full[s], kb * 64, 0);
-                    }
-                    ptx::tma_load_3d(st, &tmap_att, &w_full[s], kb * 64, row_tile, 0);
-                }
-            }
-            bool a_ready = !PROJ;
-            auto g1 = [&](int c) {   // 4 stages: A k-block + W1[c] tile
-                for (int kb = 0; kb < 4; ++kb, ++it) {
-                    const int s = it % kStages;
-                    uint8_t* st = sRing + s * kStage;
-                    if (PROJ || it >= kStages) {   // !PROJ: the first kStages W1 tiles were requested in the prologue
-                        ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
-                        ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, c * kChunk);
-                    }
-                    if (!a_ready) {   // PROJ: the A operand is LayerNorm(x1), written by this CTA's epilogue warps
-                        ptx::mbar_wait(ln1_ready, 0);
-                        a_ready = true;
-                    }
-                    ptx::tma_load_3d(st, &tmap_a, &w_full[s], kb * 64, row_tile, 0);
-                }
-            };
-            auto g2h = [&](int c, int h) {   // 2 stages: W2 tiles for hidden columns c*256 + h*128 + {0, 64}
-                for (int kb = 0; kb < 2; ++kb, ++it) {
-                    const int s = it % kStages;
+            auto wload = [&](const CUtensorMap* m, int c0, int c1) {   // the next weight tile of the ring
+                const int s = it % kStages;
+                if (it >= kStages) {   // the first kStages tiles were requested in the prologue
                     ptx::mbar_wait(&w_empty[s], ((it / kStages) & 1) ^ 1);
-                    uint8_t* st = sRing + s * kStage;
                     ptx::mbar_arrive_expect_tx(&w_full[s], kTileW);
-                    ptx::tma_load_2d(st + kTileA, &tmap_w2, &w_full[s], c * kChunk + h * 128 + kb * 64, 0);
+                    ptx::tma_load_2d(sRing + s * kTileW, m, &w_full[s], c0, c1);
                 }
+                ++it;
             };
-            g1(0);
+            if (PROJ)
+                for (int kb = 0; kb < 4; ++kb) wload(&tmap_wp, kb * 64, 0);
+            for (int kb = 0; kb < 4; ++kb) wload(&tmap_w1, kb * 64, 0);
             for (int c = 0; c < kNumChunks; ++c) {
-                if (c + 1 < kNumChunks) g1(c + 1);
-                g2h(c, 0);
-                g2h(c, 1);
+                for (int kb = 0; kb < 2; ++kb) wload(&tmap_w2, c * kChunk + kb * 64, 0);
+                if (c + 1 < kNumChunks)
+                    for (int kb = 0; kb < 4; ++kb) wload(&tmap_w1, kb * 64, (c + 1) * kChunk);
+                for (int kb = 0; kb < 2; ++kb) wload(&tmap_w2, c * kChunk + 128 + kb * 64, 0);
             }
         }
     } else if (warp == 1) {
@@ -212,8 +198,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int s = it % kStages;
                     ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sRing + s * kStage);
-                    const uint32_t b_addr = a_addr + kTileA;
+                    const uint32_t a_addr = ptx::smem_u32(sA + kb * kTileA);
+                    const uint32_t b_addr = ptx::smem_u32(sRing + s * kTileW);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_addr + k * 32),
@@ -230,7 +216,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
                     ptx::tc_fence_after();
                     const uint32_t a_addr = ptx::smem_u32(sMid + (h * 2 + kb) * kTileA);
-                    const uint32_t b_addr = ptx::smem_u32(sRing + s * kStage + kTileA);
+                    const uint32_t b_addr = ptx::smem_u32(sRing + s * kTileW);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // PROJ: acc2 already holds x1, always accumulate
                         ptx::umma_f16(tmem_base + 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
@@ -241,6 +227,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::umma_commit(&mid_empty[h]);
             };
             PD_FSTAMP(1);
+            ptx::mbar_wait(a_full, 0);
+            ptx::tc_fence_after();
             if (PROJ) {   // GEMM-0: acc2 (preset with x + bp) += att . Wp^T
                 ptx::mbar_wait(acc2_init, 0);
                 ptx::tc_fence_after();
@@ -248,8 +236,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int s = it % kStages;
                     ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(sRing + s * kStage);
-                    const uint32_t b_addr = a_addr + kTileA;
+                    const uint32_t a_addr = ptx::smem_u32(sA + kb * kTileA);
+                    const uint32_t b_addr = ptx::smem_u32(sRing + s * kTileW);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_f16(tmem_base + 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
@@ -257,12 +245,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     ptx::umma_commit(&w_empty[s]);
                 }
                 ptx::umma_commit(acc2_full);   // phase 0: x1 complete
+                ptx::mbar_wait(a_ready, 0);    // the epilogue warps have replaced `att` by LayerNorm(x1) in the A tiles
+                ptx::tc_fence_after();
             }
             g1(0);
             PD_FSTAMP(2);
             for (int c = 0; c < kNumChunks; ++c) {
-                if (c + 1 < kNumChunks) g1(c + 1);   // its operands were prefetched while this warp waited for E1(c)
+                // first K half of GEMM-2 as soon as E1(c) phase 0 has written it (it runs under phase 1 and frees those
+                // k-blocks long before E1(c + 1) needs them), then GEMM-1 of the next chunk (phase 1 has read acc1 out by
+                // then), the second K half when E1(c) is done. (G1(c + 1) used to come first: E1(c + 1) then waited ~1 000
+                // cycles per chunk for G2h0(c) - 19 % of the epilogue warps' samples in the ncu source view.)
                 g2h(c, 0);
+                if (c + 1 < kNumChunks) g1(c + 1);
                 g2h(c, 1);
                 PD_FSTAMP(3 + c);          // G2(c) issued
             }
@@ -284,21 +278,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::tma_load_3d(islab + j * 4096, &tmap_x, &my_bar[2 * r + j], (c_begin + 2 * r + j) * 32, row0, 0);
             }
         };
-        if (PROJ && lane == 0) load_x_round(0);    // in flight while the bias / LayerNorm vectors are staged below
-        {   // stage b1 / b2 / gamma / beta: all of a thread's loads are issued before the first store (one latency, not 4-7)
-            constexpr int kPer = kHid / (32 * kEpiWarps);   // 4
-            float t1[kPer];
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) t1[k] = __ldg(p.b1 + et + k * 32 * kEpiWarps);
-            const float t2 = __ldg(p.b2 + et);
-            const float tg = p.ln_gamma ? __ldg(p.ln_gamma + et) : 0.f, tb = p.ln_gamma ? __ldg(p.ln_beta + et) : 0.f;
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) b1_s[et + k * 32 * kEpiWarps] = t1[k];
-            b2_s[et] = t2;
-            if (p.ln_gamma) { ln_g[et] = tg; ln_b[et] = tb; }
-        }
-        static_assert(kC == 32 * kEpiWarps && kHid % (32 * kEpiWarps) == 0, "vector staging assumes 256 epilogue threads");
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (PROJ && lane == 0) load_x_round(0);
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (PROJ) {
             // ---- preset acc2 with x + bp (two rounds of two 4 KB slabs per warp through the idle mid region) ----
@@ -328,7 +308,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc2_init);
-            // ---- E0: x1 = acc2 after GEMM-0; LayerNorm(x1) -> bf16 -> global (the A operand of GEMM-1) ----
+            // ---- E0: x1 = acc2 after GEMM-0; LayerNorm(x1) -> bf16 -> the resident A tiles (the A operand of GEMM-1) ----
             ptx::mbar_wait(acc2_full, 0);
             ptx::tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
@@ -355,8 +335,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float rstd = rsqrtf(var + p.ln_eps);
             asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // ln_x is reused by the final epilogue
 #pragma unroll 1
-            for (int j = 0; j < 2; ++j) {          // bf16 slab j = my chunks 2j, 2j+1 (64 columns)
-                uint8_t* brow = islab + j * 4096 + lane * 128;
+            for (int j = 0; j < 2; ++j) {          // A tile (k-block) 2 half + j = my chunks 2j, 2j+1 (64 columns)
+                const uint32_t arow = ptx::smem_u32(sA + (half * 2 + j) * kTileA + (q * 32 + lane) * 128);
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int colbase = (c_begin + 2 * j + cc) * 32;
@@ -372,30 +352,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         float a[8];
 #pragma unroll
                         for (int t = 0; t < 8; ++t) a[t] = __uint_as_float(v[8 * k + t]);
-                        uint4 pk;
-                        pk.x = pack_bf16x2(fmaf((a[0] - mean) * rstd, g0.x, b0.x), fmaf((a[1] - mean) * rstd, g0.y, b0.y));
-                        pk.y = pack_bf16x2(fmaf((a[2] - mean) * rstd, g0.z, b0.z), fmaf((a[3] - mean) * rstd, g0.w, b0.w));
-                        pk.z = pack_bf16x2(fmaf((a[4] - mean) * rstd, g1v.x, b1v.x), fmaf((a[5] - mean) * rstd, g1v.y, b1v.y));
-                        pk.w = pack_bf16x2(fmaf((a[6] - mean) * rstd, g1v.z, b1v.z), fmaf((a[7] - mean) * rstd, g1v.w, b1v.w));
-                        *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(cc * 4 + k) ^ sw) << 4)) = pk;
+                        ptx::st_shared_v4(arow + ((static_cast<uint32_t>(cc * 4 + k) ^ sw) << 4),
+                                          pack_bf16x2(fmaf((a[0] - mean) * rstd, g0.x, b0.x), fmaf((a[1] - mean) * rstd, g0.y, b0.y)),
+                                          pack_bf16x2(fmaf((a[2] - mean) * rstd, g0.z, b0.z), fmaf((a[3] - mean) * rstd, g0.w, b0.w)),
+                                          pack_bf16x2(fmaf((a[4] - mean) * rstd, g1v.x, b1v.x), fmaf((a[5] - mean) * rstd, g1v.y, b1v.y)),
+                                          pack_bf16x2(fmaf((a[6] - mean) * rstd, g1v.z, b1v.z), fmaf((a[7] - mean) * rstd, g1v.w, b1v.w)));
                     }
                 }
             }
+            // generic-proxy writes -> visible to the tensor core's (async-proxy) reads of the A tiles
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                // tmap_ln1st: the tensor behind tmap_a, addressed with 64-column x 32-row store boxes
-                ptx::tma_store_3d(&tmap_ln1st, islab, (c_begin + 0) * 32, row0, 0);
-                ptx::tma_store_3d(&tmap_ln1st, islab + 4096, (c_begin + 2) * 32, row0, 0);
-                ptx::bulk_commit();
-                // written (not just read): the producer will TMA-load it back. Both sides are async-proxy accesses to
-                // global memory ordered by the wait + the mbarrier hand-off; the full-proxy fence that used to sit here
-                // (MEMBAR.GPU + CCTL.IVALL, ~1.4 us per launch in the ncu source view) is not needed
-                ptx::bulk_wait_all<0>();
-                ptx::mbar_arrive(ln1_ready);
-            }
-            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a_ready);
         }
         // ---- E1: GELU chunks -> swizzled A tiles of GEMM-2 ----
 #pragma unroll 1
@@ -416,12 +385,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (lane == 0) ptx::mbar_arrive(acc1_empty);
                 }
                 ptx::mbar_wait(&mid_empty[h], (c & 1) ^ 1);           // G2h(c - 1) no longer reads these k-blocks
-                uint8_t* my_row = sMid + (h * 2 + half) * kTileA + (q * 32 + lane) * 128;
-                const float* bias = b1_s + c * kChunk + col;
+                const uint32_t my_row = ptx::smem_u32(sMid + (h * 2 + half) * kTileA + (q * 32 + lane) * 128);
+                const float* bias = p.b1 + c * kChunk + col;   // read-only global path: loads the compiler is free to hoist
 #pragma unroll
                 for (int cell = 0; cell < 8; ++cell) {
-                    const float4 bv0 = *(reinterpret_cast<const float4*>(bias + cell * 8));
-                    const float4 bv1 = *(reinterpret_cast<const float4*>(bias + cell * 8 + 4));
+                    const float4 bv0 = __ldg(reinterpret_cast<const float4*>(bias + cell * 8));
+                    const float4 bv1 = __ldg(reinterpret_cast<const float4*>(bias + cell * 8 + 4));
                     const float bb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
                     uint32_t pk[4];
 #pragma unroll
@@ -430,8 +399,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const uint32_t r1 = cell < 4 ? v0[cell * 8 + 2 * k + 1] : v1[(cell - 4) * 8 + 2 * k + 1];
                         pk[k] = gelu_pair_bf16(__uint_as_float(r0) + bb[2 * k], __uint_as_float(r1) + bb[2 * k + 1]);
                     }
-                    *reinterpret_cast<uint4*>(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4)) =
-                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    ptx::st_shared_v4(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -443,7 +411,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::mbar_wait(acc2_full, PROJ ? 1 : 0);
         ptx::tc_fence_after();
         if (et == 0) PD_FSTAMP(28);               // accumulator 2 complete
-        uint8_t* slabs = smem + e * (4 * 4096);                    // aliases the ring (all MMAs have completed)
+        uint8_t* slabs = smem + e * (4 * 4096);                    // aliases A + the ring (all MMAs have completed)
         if (!PROJ && lane == 0) {                                  // PROJ: the residual is already inside acc2
             for (int idx = 0; idx < 4; ++idx) {
                 ptx::mbar_arrive_expect_tx(&my_bar[idx], 4096);
@@ -463,7 +431,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint8_t* my_row = slab + lane * 128;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 bb = *reinterpret_cast<const float4*>(b2_s + c * 32 + 4 * i);
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32 + 4 * i));
                 float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
                 const float4 r = PROJ ? make_float4(0.f, 0.f, 0.f, 0.f) : *cell;
                 float4 a = make_float4(__uint_as_float(v[4 * i]) + bb.x + r.x, __uint_as_float(v[4 * i + 1]) + bb.y + r.y,
@@ -501,10 +469,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int k = 0; k < 4; ++k) {
                         const float4 a0 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k) ^ sw) << 4));
                         const float4 a1 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k + 1) ^ sw) << 4));
-                        const float4 g0 = *reinterpret_cast<const float4*>(ln_g + colbase + 8 * k);
-                        const float4 g1 = *reinterpret_cast<const float4*>(ln_g + colbase + 8 * k + 4);
-                        const float4 b0 = *reinterpret_cast<const float4*>(ln_b + colbase + 8 * k);
-                        const float4 b1v = *reinterpret_cast<const float4*>(ln_b + colbase + 8 * k + 4);
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + colbase + 8 * k));
+                        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + colbase + 8 * k + 4));
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + colbase + 8 * k));
+                        const float4 b1v = __ldg(reinterpret_cast<const float4*>(p.ln_beta + colbase + 8 * k + 4));
                         uint4 pk;
                         pk.x = pack_bf16x2(fmaf((a0.x - mean) * rstd, g0.x, b0.x), fmaf((a0.y - mean) * rstd, g0.y, b0.y));
                         pk.y = pack_bf16x2(fmaf((a0.z - mean) * rstd, g0.z, b0.z), fmaf((a0.w - mean) * rstd, g0.w, b0.w));
@@ -536,7 +504,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }  // namespace
 
 struct FfnFusedOpImpl {
-    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln, tmap_att, tmap_wp, tmap_ln1st;
+    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln, tmap_att, tmap_wp;
     FfnParams p;
     WRange own_w;
     int tiles;
@@ -565,7 +533,6 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
     const uint32_t box_ld[3] = {64, 128, 1}, box_st[3] = {64, 32, 1};
     // A of GEMM-1: ln [M][256] bf16, boxes of 128 rows x 64 columns (PROJ: written by the kernel itself first)
     PD_TRY(tmap_encode_sw128(&op->tmap_a, true, 3, ln_in, dims_b, st_b, box_ld));
-    PD_TRY(tmap_encode_sw128(&op->tmap_ln1st, true, 3, ln_in, dims_b, st_b, box_st));
     {   // W1 [1024][256] (K-major), W2 [256][1024], Wp [256][256]: boxes of 256 rows x 64 K
         const uint64_t d1[2] = {kC, kHid}, s1[1] = {kC * 2};
         const uint64_t d2[2] = {kHid, kC}, s2[1] = {kHid * 2};
@@ -585,7 +552,7 @@ int ffn_fused_make(FfnFusedOp* op_, const bf16* ln_in, int M, const bf16* w1, co
         const uint32_t box[3] = {32, 32, 1};
         PD_TRY(tmap_encode_sw128(&op->tmap_x, false, 3, x_inout, dims, st, box));
     }
-    op->tmap_ln = op->tmap_ln1st;
+    op->tmap_ln = op->tmap_a;
     if (ln_out) PD_TRY(tmap_encode_sw128(&op->tmap_ln, true, 3, ln_out, dims_b, st_b, box_st));
     op->p.b1 = b1;
     op->p.b2 = b2;
@@ -626,7 +593,7 @@ int ffn_fused_launch(const FfnFusedOp& op_, cudaStream_t st) {
     const FfnFusedOpImpl& op = reinterpret_cast<const FfnFusedOpImpl&>(op_);
 #define PD_FFN_LAUNCH(PROJ, GN)                                                                                          \
     PD_LAUNCH((ffn_fused_kernel<PROJ, GN>), op.tiles, kThreads, kSmem, st, op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x,     \
-              op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1st, op.p)
+              op.tmap_ln, op.tmap_att, op.tmap_wp, op.p)
     if (op.proj) {
         if (op.p.gn_sums) PD_FFN_LAUNCH(true, true);
         else PD_FFN_LAUNCH(true, false);

@@ -122,6 +122,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
 }
 
+// 16-byte store to a shared-window address. The kernels reach shared memory through a manually aligned generic pointer, so
+// plain C++ stores compile to generic ST.E, which the compiler must keep ordered against every other generic load; not
+// volatile-ordered against ordinary loads, but kept in program order with the other `asm volatile` statements (fences,
+// mbarrier arrives).
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from prediff_b200 import _lib as L  # noqa: E402
 
 L.init()
-M, C, H = 13312, 256, 1024
+M, C, H = int(os.environ.get("M", 13312)), 256, 1024
 dev = "cuda"
 ln_in = torch.randn(M, C, device=dev).bfloat16()
 w1 = (torch.randn(H, C, device=dev) * C ** -0.5).bfloat16()
