@@ -15,8 +15,8 @@
 //   warp 1    : one lane issues tcgen05.mma 128 x 256 x 16 (an N = 128 MMA costs the same ~128 cycles, measured):
 //                 G1(c):  acc1  = ln . W1[c]^T                       c = 0..3, 256 hidden columns per chunk
 //                 G2h(c): acc2 += gelu_c[:, 128h : 128h+128] . W2[:, ...]^T   (two K halves, each as soon as it is ready)
-//               order G1(0) | G2h0(c) G1(c+1) G2h1(c) | ... : the first half of GEMM-2 and GEMM-1 of the next chunk run
-//               under the second half of this chunk's GELU epilogue
+//               order G1(0) | G1(c+1) G2h0(c) G2h1(c) | ... : GEMM-1 of the next chunk runs under the first half of this
+//               chunk's GELU epilogue (acc1 is copied to registers at once), the first half of GEMM-2 under the second
 //   warps 2-9 : E1(c), two phases of 128 hidden columns: acc1 (TMEM) -> + b1 -> GELU -> bf16 -> 128B-swizzled K-major
 //               smem tiles = the A operand of G2(c); acc1 is handed back right after the second phase's TMEM loads;
 //               final: acc2 -> + b2 + residual (TMA-loaded) -> x (TMA store) -> fused LayerNorm -> bf16 (TMA store)
@@ -181,9 +181,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int kb = 0; kb < 4; ++kb) wload(&tmap_wp, kb * 64, 0);
             for (int kb = 0; kb < 4; ++kb) wload(&tmap_w1, kb * 64, 0);
             for (int c = 0; c < kNumChunks; ++c) {
-                for (int kb = 0; kb < 2; ++kb) wload(&tmap_w2, c * kChunk + kb * 64, 0);
                 if (c + 1 < kNumChunks)
                     for (int kb = 0; kb < 4; ++kb) wload(&tmap_w1, kb * 64, (c + 1) * kChunk);
+                for (int kb = 0; kb < 2; ++kb) wload(&tmap_w2, c * kChunk + kb * 64, 0);
                 for (int kb = 0; kb < 2; ++kb) wload(&tmap_w2, c * kChunk + 128 + kb * 64, 0);
             }
         }
@@ -251,12 +251,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             g1(0);
             PD_FSTAMP(2);
             for (int c = 0; c < kNumChunks; ++c) {
-                // first K half of GEMM-2 as soon as E1(c) phase 0 has written it (it runs under phase 1 and frees those
-                // k-blocks long before E1(c + 1) needs them), then GEMM-1 of the next chunk (phase 1 has read acc1 out by
-                // then), the second K half when E1(c) is done. (G1(c + 1) used to come first: E1(c + 1) then waited ~1 000
-                // cycles per chunk for G2h0(c) - 19 % of the epilogue warps' samples in the ncu source view.)
-                g2h(c, 0);
+                // GEMM-1 of the next chunk first: E1(c) hands acc1 back as soon as it has copied its columns to registers,
+                // so G1(c + 1) runs under phase 0 of E1(c), the two K halves of GEMM-2 under phase 1 / phase 0 of E1(c + 1)
                 if (c + 1 < kNumChunks) g1(c + 1);
+                g2h(c, 0);
                 g2h(c, 1);
                 PD_FSTAMP(3 + c);          // G2(c) issued
             }
@@ -372,18 +370,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::mbar_wait(acc1_full, c & 1);
             ptx::tc_fence_after();
             if (et == 0) PD_FSTAMP(12 + 2 * c);   // E1(c) begins
-#pragma unroll 1
+            // the thread's 2 x 64 accumulator columns of both phases leave TMEM at once, so that GEMM-1 of the next chunk can
+            // start under phase 0 already (with acc1 handed back only after phase 1's loads, E1(c) phase 0 -> G2h0(c) ->
+            // G1(c + 1) -> E1(c + 1) was the critical path: 6 150 cycles per chunk with a 5 000-cycle epilogue)
+            uint32_t va[2][32], vb[2][32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                ptx::tmem_ld_32x32(t_lane + h * 128 + half * 64, va[h]);
+                ptx::tmem_ld_32x32(t_lane + h * 128 + half * 64 + 32, vb[h]);
+            }
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc1_empty);
+#pragma unroll
             for (int h = 0; h < 2; ++h) {          // phase h: hidden columns [128 h, 128 h + 128) of the chunk
                 const int col = h * 128 + half * 64;   // this warp's 64 columns = k-block (2 h + half) of mid
-                uint32_t v0[32], v1[32];
-                ptx::tmem_ld_32x32(t_lane + col, v0);
-                ptx::tmem_ld_32x32(t_lane + col + 32, v1);
-                ptx::tmem_ld_wait();
-                if (h == 1) {                      // every TMEM read of this chunk is done: G1(c + 1) may overwrite acc1
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(acc1_empty);
-                }
+                const uint32_t (&v0)[32] = va[h];
+                const uint32_t (&v1)[32] = vb[h];
                 ptx::mbar_wait(&mid_empty[h], (c & 1) ^ 1);           // G2h(c - 1) no longer reads these k-blocks
                 const uint32_t my_row = ptx::smem_u32(sMid + (h * 2 + half) * kTileA + (q * 32 + lane) * 128);
                 const float* bias = p.b1 + c * kChunk + col;   // read-only global path: loads the compiler is free to hoist
