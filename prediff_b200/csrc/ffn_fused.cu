@@ -32,8 +32,15 @@ constexpr int kC = 256;            // model width (K of GEMM-1, N of GEMM-2)
 constexpr int kHid = 1024;         // hidden width
 constexpr int kChunk = 256;        // hidden columns per chunk
 constexpr int kNumChunks = kHid / kChunk;
-constexpr int kEpiWarps = 8;
+#ifndef PD_FFN_EPI_WARPS
+#define PD_FFN_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = PD_FFN_EPI_WARPS;   // 8 or 16: kParts warps share a TMEM lane quarter and split its columns
+constexpr int kParts = kEpiWarps / 4;
+constexpr int kCh = 8 / kParts;               // 32-column chunks of the 256-wide row per thread (prologue / final epilogue)
+constexpr int kIs = 16 / kEpiWarps;           // 4 KB slabs per warp that fit into the 64 KB mid region
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: two or four per TMEM lane quarter");
 constexpr int kTileA = 128 * 64 * 2;         // 16 KB: 128 rows x 64 bf16
 constexpr int kTileW = 256 * 64 * 2;         // 32 KB: 256 rows x 64 bf16
 constexpr int kABytes = 4 * kTileA;          // 64 KB: the resident A operand (four k-blocks)
@@ -43,10 +50,11 @@ constexpr int kMidBytes = 4 * kTileA;        // 64 KB: four k-blocks of the GELU
 constexpr int kPipeBytes = kABytes + kRingBytes + kMidBytes;   // 224 KB
 constexpr int kBarBytes = 512;
 // the dynamic shared memory window is declared 1024-byte aligned (checked at kernel start): no alignment slack
-constexpr int kSmem = kPipeBytes + kBarBytes + kEpiWarps * 32 * 8;
+constexpr int kSmem = kPipeBytes + kBarBytes;
 static_assert(kSmem <= 232448, "over the 227 KB per-CTA limit");
-static_assert(kABytes + kRingBytes >= kEpiWarps * 4 * 4096, "fp32 epilogue slabs alias A + the ring");
-static_assert(kMidBytes >= kEpiWarps * 2 * 4096, "bf16 LayerNorm slabs alias mid");
+static_assert(kABytes + kRingBytes >= kEpiWarps * kCh * 4096 + 4 * kParts * 32 * 8,
+              "fp32 epilogue slabs + the row-statistics exchange alias A + the ring");
+static_assert(kMidBytes >= kEpiWarps * (kCh / 2) * 4096 && kMidBytes >= kEpiWarps * kIs * 4096, "bf16 / residual slabs alias mid");
 
 struct FfnParams {
     const float* b1;
@@ -95,10 +103,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc2_init = acc2_full + 1;     // [1] PROJ: acc2 preset with x + bp
     uint64_t* a_full = acc2_init + 1;        // [1] the A tiles have landed (PROJ: `att`; else the pre-norm input)
     uint64_t* a_ready = a_full + 1;          // [1] PROJ: LayerNorm(x1) written into the A tiles by the epilogue warps
-    uint64_t* res_bar = a_ready + 1;         // [kEpiWarps][4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * kEpiWarps);
-    static_assert((15 + 4 * kEpiWarps) * 8 + 4 <= kBarBytes, "barrier block too small");
-    float2* ln_x = reinterpret_cast<float2*>(smem + kPipeBytes + kBarBytes);
+    uint64_t* res_bar = a_ready + 1;         // [kEpiWarps][kCh]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kCh * kEpiWarps);
+    static_assert((15 + kCh * kEpiWarps) * 8 + 4 <= kBarBytes, "barrier block too small");
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();   // the swizzled tiles need the declared alignment
 
     const int warp = threadIdx.x >> 5;
@@ -124,7 +131,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::mbar_init(acc2_init, kEpiWarps);
         ptx::mbar_init(a_full, 1);
         ptx::mbar_init(a_ready, kEpiWarps);
-        for (int i = 0; i < 4 * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < kCh * kEpiWarps; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -262,31 +269,46 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else {
         const int e = warp - 2;
-        const int q = warp & 3;          // TMEM lane quarter
-        const int half = e >> 2;         // column half
+        const int q = warp & 3;          // TMEM lane quarter (fixed by the hardware: warp index modulo 4)
+        const int part = e >> 2;         // which of the kParts column ranges of the quarter's rows this warp owns
         const int et = threadIdx.x - 64;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
         const int row0 = row_tile + q * 32;
-        const int c_begin = half * 4;              // this warp's four 32-column chunks of the 256-wide row
-        uint64_t* my_bar = res_bar + 4 * e;
-        uint8_t* islab = sMid + e * (2 * 4096);
-        auto load_x_round = [&](int r) {           // PROJ: two residual slabs of this warp's rows -> the idle mid region
-            for (int j = 0; j < 2; ++j) {
-                ptx::mbar_arrive_expect_tx(&my_bar[2 * r + j], 4096);
-                ptx::tma_load_3d(islab + j * 4096, &tmap_x, &my_bar[2 * r + j], (c_begin + 2 * r + j) * 32, row0, 0);
+        const int c_begin = part * kCh;            // this warp's kCh 32-column chunks of the 256-wide row
+        uint64_t* my_bar = res_bar + kCh * e;
+        uint8_t* islab = sMid + e * (kIs * 4096);
+        const int ln_slot = (q * kParts) * 32 + lane;   // + part * 32: the row's partial sums, one per column range
+        // row statistics of the 256-wide row from the kParts threads that share it (fixed order: identical in all of them)
+        auto row_stats = [&](float2* ln_x, float s1, float s2, float* mean, float* rstd) {
+            ln_x[ln_slot + part * 32] = make_float2(s1, s2);
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < kParts; ++pp) {
+                const float2 o = ln_x[ln_slot + pp * 32];
+                t1 = pp == 0 ? o.x : t1 + o.x;
+                t2 = pp == 0 ? o.y : t2 + o.y;
+            }
+            *mean = t1 * (1.0f / kC);
+            *rstd = rsqrtf(fmaxf(t2 * (1.0f / kC) - *mean * *mean, 0.f) + p.ln_eps);
+        };
+        auto load_x_round = [&](int r) {           // PROJ: kIs residual slabs of this warp's rows -> the idle mid region
+            for (int j = 0; j < kIs; ++j) {
+                ptx::mbar_arrive_expect_tx(&my_bar[kIs * r + j], 4096);
+                ptx::tma_load_3d(islab + j * 4096, &tmap_x, &my_bar[kIs * r + j], (c_begin + kIs * r + j) * 32, row0, 0);
             }
         };
         if (PROJ && lane == 0) load_x_round(0);
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (PROJ) {
-            // ---- preset acc2 with x + bp (two rounds of two 4 KB slabs per warp through the idle mid region) ----
+            // ---- preset acc2 with x + bp (rounds of kIs 4 KB slabs per warp through the idle mid region) ----
 #pragma unroll 1
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < kCh / kIs; ++r) {
                 if (lane == 0 && r > 0) load_x_round(r);
 #pragma unroll 1
-                for (int j = 0; j < 2; ++j) {
-                    const int c = c_begin + 2 * r + j;
-                    ptx::mbar_wait(&my_bar[2 * r + j], 0);
+                for (int j = 0; j < kIs; ++j) {
+                    const int c = c_begin + kIs * r + j;
+                    ptx::mbar_wait(&my_bar[kIs * r + j], 0);
                     const uint8_t* my_row = islab + j * 4096 + lane * 128;
                     uint32_t v[32];
 #pragma unroll
@@ -300,18 +322,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                     ptx::tmem_st_32x32(t_lane + 256 + c * 32, v);
                 }
-                __syncwarp();   // both slabs consumed before the next round overwrites them
+                __syncwarp();   // the slabs are consumed before the next round overwrites them
             }
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc2_init);
             // ---- E0: x1 = acc2 after GEMM-0; LayerNorm(x1) -> bf16 -> the resident A tiles (the A operand of GEMM-1) ----
-            ptx::mbar_wait(acc2_full, 0);
+            ptx::mbar_wait(acc2_full, 0);   // every warp is past its preset: mid is idle until E1(0)
             ptx::tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-            for (int idx = 0; idx < 4; ++idx) {
+            for (int idx = 0; idx < kCh; ++idx) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(t_lane + 256 + (c_begin + idx) * 32, v);
                 ptx::tmem_ld_wait();
@@ -325,16 +347,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
                 s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
             }
-            ln_x[(q * 2 + half) * 32 + lane] = make_float2(s1, s2);
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-            const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
-            const float mean = (s1 + o.x) * (1.0f / kC);
-            const float var = fmaxf((s2 + o.y) * (1.0f / kC) - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + p.ln_eps);
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // ln_x is reused by the final epilogue
+            float mean, rstd;
+            row_stats(reinterpret_cast<float2*>(sMid), s1, s2, &mean, &rstd);
 #pragma unroll 1
-            for (int j = 0; j < 2; ++j) {          // A tile (k-block) 2 half + j = my chunks 2j, 2j+1 (64 columns)
-                const uint32_t arow = ptx::smem_u32(sA + (half * 2 + j) * kTileA + (q * 32 + lane) * 128);
+            for (int j = 0; j < kCh / 2; ++j) {    // A tile (k-block) c_begin / 2 + j = my chunks 2j, 2j+1 (64 columns)
+                const uint32_t arow = ptx::smem_u32(sA + (c_begin / 2 + j) * kTileA + (q * 32 + lane) * 128);
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int colbase = (c_begin + 2 * j + cc) * 32;
@@ -358,52 +375,54 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             }
-            // generic-proxy writes -> visible to the tensor core's (async-proxy) reads of the A tiles
+            // generic-proxy writes -> visible to the tensor core's (async-proxy) reads of the A tiles. The partial sums in
+            // mid were read by the quarter's threads before any of them got here (row_stats' barrier precedes its reads,
+            // and E1(0) of a warp starts after a_ready, i.e. after every warp's arrival below)
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(a_ready);
         }
         // ---- E1: GELU chunks -> swizzled A tiles of GEMM-2 ----
+        constexpr int kColsPh = 128 / kParts;      // hidden columns per thread and phase (64 or 32)
+        constexpr int kLdPh = kColsPh / 32;
+        const int mid_kb = (part * kColsPh) / 64;  // k-block (of the phase's two) and first 16-byte cell the columns fall into
+        const int cell0 = ((part * kColsPh) % 64) / 8;
 #pragma unroll 1
         for (int c = 0; c < kNumChunks; ++c) {
             ptx::mbar_wait(acc1_full, c & 1);
             ptx::tc_fence_after();
             if (et == 0) PD_FSTAMP(12 + 2 * c);   // E1(c) begins
-            // the thread's 2 x 64 accumulator columns of both phases leave TMEM at once, so that GEMM-1 of the next chunk can
+            // the thread's accumulator columns of both phases leave TMEM at once, so that GEMM-1 of the next chunk can
             // start under phase 0 already (with acc1 handed back only after phase 1's loads, E1(c) phase 0 -> G2h0(c) ->
             // G1(c + 1) -> E1(c + 1) was the critical path: 6 150 cycles per chunk with a 5 000-cycle epilogue)
-            uint32_t va[2][32], vb[2][32];
+            uint32_t va[2][kLdPh][32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                ptx::tmem_ld_32x32(t_lane + h * 128 + half * 64, va[h]);
-                ptx::tmem_ld_32x32(t_lane + h * 128 + half * 64 + 32, vb[h]);
-            }
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int l = 0; l < kLdPh; ++l) ptx::tmem_ld_32x32(t_lane + h * 128 + part * kColsPh + l * 32, va[h][l]);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc1_empty);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {          // phase h: hidden columns [128 h, 128 h + 128) of the chunk
-                const int col = h * 128 + half * 64;   // this warp's 64 columns = k-block (2 h + half) of mid
-                const uint32_t (&v0)[32] = va[h];
-                const uint32_t (&v1)[32] = vb[h];
                 ptx::mbar_wait(&mid_empty[h], (c & 1) ^ 1);           // G2h(c - 1) no longer reads these k-blocks
-                const uint32_t my_row = ptx::smem_u32(sMid + (h * 2 + half) * kTileA + (q * 32 + lane) * 128);
-                const float* bias = p.b1 + c * kChunk + col;   // read-only global path: loads the compiler is free to hoist
+                const uint32_t my_row = ptx::smem_u32(sMid + (h * 2 + mid_kb) * kTileA + (q * 32 + lane) * 128);
+                const float* bias = p.b1 + c * kChunk + h * 128 + part * kColsPh;   // read-only path: hoistable loads
 #pragma unroll
-                for (int cell = 0; cell < 8; ++cell) {
+                for (int cell = 0; cell < kColsPh / 8; ++cell) {
                     const float4 bv0 = __ldg(reinterpret_cast<const float4*>(bias + cell * 8));
                     const float4 bv1 = __ldg(reinterpret_cast<const float4*>(bias + cell * 8 + 4));
                     const float bb[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
                     uint32_t pk[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint32_t r0 = cell < 4 ? v0[cell * 8 + 2 * k] : v1[(cell - 4) * 8 + 2 * k];
-                        const uint32_t r1 = cell < 4 ? v0[cell * 8 + 2 * k + 1] : v1[(cell - 4) * 8 + 2 * k + 1];
+                        const uint32_t r0 = va[h][cell / 4][(cell % 4) * 8 + 2 * k];
+                        const uint32_t r1 = va[h][cell / 4][(cell % 4) * 8 + 2 * k + 1];
                         pk[k] = gelu_pair_bf16(__uint_as_float(r0) + bb[2 * k], __uint_as_float(r1) + bb[2 * k + 1]);
                     }
-                    ptx::st_shared_v4(my_row + ((static_cast<uint32_t>(cell) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    ptx::st_shared_v4(my_row + ((static_cast<uint32_t>(cell0 + cell) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -415,9 +434,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::mbar_wait(acc2_full, PROJ ? 1 : 0);
         ptx::tc_fence_after();
         if (et == 0) PD_FSTAMP(28);               // accumulator 2 complete
-        uint8_t* slabs = smem + e * (4 * 4096);                    // aliases A + the ring (all MMAs have completed)
+        uint8_t* slabs = smem + e * (kCh * 4096);                  // aliases A + the ring (all MMAs have completed)
         if (!PROJ && lane == 0) {                                  // PROJ: the residual is already inside acc2
-            for (int idx = 0; idx < 4; ++idx) {
+            for (int idx = 0; idx < kCh; ++idx) {
                 ptx::mbar_arrive_expect_tx(&my_bar[idx], 4096);
                 ptx::tma_load_3d(slabs + idx * 4096, &tmap_x, &my_bar[idx], (c_begin + idx) * 32, row0, 0);
             }
@@ -425,7 +444,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float ln_s1 = 0.f, ln_s2 = 0.f;
         const int gsample = GN ? row0 / p.gn_rows : 0;   // GroupNorm sample of my rows
 #pragma unroll 1
-        for (int idx = 0; idx < 4; ++idx) {
+        for (int idx = 0; idx < kCh; ++idx) {
             const int c = c_begin + idx;
             uint8_t* slab = slabs + idx * 4096;
             uint32_t v[32];
@@ -455,15 +474,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
         if (p.ln_gamma) {
-            ln_x[(q * 2 + half) * 32 + lane] = make_float2(ln_s1, ln_s2);
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-            const float2 o = ln_x[(q * 2 + (half ^ 1)) * 32 + lane];
-            const float mean = (ln_s1 + o.x) * (1.0f / kC);
-            const float var = fmaxf((ln_s2 + o.y) * (1.0f / kC) - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + p.ln_eps);
-            uint8_t* bslabs = sMid + e * (2 * 4096);               // aliases mid
+            float mean, rstd;   // partial sums cross in the dead tail of the ring (the fp32 slabs end at kEpiWarps * kCh * 4 KB)
+            row_stats(reinterpret_cast<float2*>(smem + kEpiWarps * kCh * 4096), ln_s1, ln_s2, &mean, &rstd);
+            uint8_t* bslabs = sMid + e * ((kCh / 2) * 4096);       // aliases mid
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < kCh / 2; ++j) {
                 uint8_t* brow = bslabs + j * 4096 + lane * 128;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -489,8 +504,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                ptx::tma_store_3d(&tmap_ln, bslabs, (c_begin + 0) * 32, row0, 0);
-                ptx::tma_store_3d(&tmap_ln, bslabs + 4096, (c_begin + 2) * 32, row0, 0);
+#pragma unroll
+                for (int j = 0; j < kCh / 2; ++j) ptx::tma_store_3d(&tmap_ln, bslabs + j * 4096, (c_begin + 2 * j) * 32, row0, 0);
                 ptx::bulk_commit();
             }
         }
