@@ -76,11 +76,11 @@ struct FfnParams {
 
 // PROJ = false: the A operand of GEMM-1 is the (already normalised) tensor behind tmap_a, loaded once; acc2 starts at zero
 //               and the residual is added in the final epilogue.
-// PROJ = true : the kernel first builds x1 = x + bp + att . Wp^T in the acc2 columns of TMEM (the epilogue warps preset
-//               acc2 with x + bp through tcgen05.st while the first operands are in flight; GEMM-0 reads `att` from the
-//               resident A tiles and accumulates on top), normalises it (the FFN's pre-norm) straight into the resident A
-//               tiles as swizzled bf16 - no round trip through global memory - and GEMM-2 keeps accumulating onto x1, so
-//               no residual is ever re-loaded.
+// PROJ = true : the kernel first builds x1 = (x + bp) + att . Wp^T in the acc2 columns of TMEM (GEMM-0 reads `att` from the
+//               resident A tiles; meanwhile the epilogue warps park x + bp in the idle acc1 columns through tcgen05.st and
+//               add the two afterwards), normalises it (the FFN's pre-norm) straight into the resident A tiles as swizzled
+//               bf16 - no round trip through global memory - and GEMM-2 keeps accumulating onto x1, so no residual is ever
+//               re-loaded.
 template <bool PROJ, bool GN>   // GN: also accumulate GroupNorm statistics of the new x rows (FfnParams::gn_sums)
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
@@ -100,7 +100,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* mid_full = acc1_empty + 1;     // [2] (K halves)
     uint64_t* mid_empty = mid_full + 2;      // [2]
     uint64_t* acc2_full = mid_empty + 2;     // [1] (PROJ: phase 0 = x1 complete, phase 1 = FFN complete)
-    uint64_t* acc2_init = acc2_full + 1;     // [1] PROJ: acc2 preset with x + bp
+    uint64_t* acc2_init = acc2_full + 1;     // [1] unused
     uint64_t* a_full = acc2_init + 1;        // [1] the A tiles have landed (PROJ: `att`; else the pre-norm input)
     uint64_t* a_ready = a_full + 1;          // [1] PROJ: LayerNorm(x1) written into the A tiles by the epilogue warps
     uint64_t* res_bar = a_ready + 1;         // [kEpiWarps][kCh]
@@ -157,6 +157,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
+    }
+    if (warp >= 2) {
+        // the bias / LayerNorm vectors (10 KB of parameters, independent of the preceding kernel) into L1 now: the epilogues
+        // read them through the read-only path in the middle of dependent chains (the normalising pass of E0 took 3 000
+        // cycles for 64 values per thread, most of it L2 latency on these vectors)
+        const int t = threadIdx.x - 64;   // one 128-byte line per thread
+        if (t < 32) ptx::prefetch_l1(p.b1 + t * 32);
+        else if (t < 40) ptx::prefetch_l1(p.b2 + (t - 32) * 32);
+        else if (t < 48) { if (p.ln_gamma) ptx::prefetch_l1(p.ln_gamma + (t - 40) * 32); }
+        else if (t < 56) { if (p.ln_gamma) ptx::prefetch_l1(p.ln_beta + (t - 48) * 32); }
+        else if (PROJ && t < 64) ptx::prefetch_l1(p.bp + (t - 56) * 32);
+        else if (PROJ && t < 72) ptx::prefetch_l1(p.ln1_gamma + (t - 64) * 32);
+        else if (PROJ && t < 80) ptx::prefetch_l1(p.ln1_beta + (t - 72) * 32);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -236,9 +249,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             PD_FSTAMP(1);
             ptx::mbar_wait(a_full, 0);
             ptx::tc_fence_after();
-            if (PROJ) {   // GEMM-0: acc2 (preset with x + bp) += att . Wp^T
-                ptx::mbar_wait(acc2_init, 0);
-                ptx::tc_fence_after();
+            PD_FSTAMP(11);                // A tiles landed
+            if (PROJ) {   // GEMM-0: acc2 = att . Wp^T (the epilogue warps park x + bp in the idle acc1 columns meanwhile)
                 for (int kb = 0; kb < 4; ++kb, ++it) {
                     const int s = it % kStages;
                     ptx::mbar_wait(&w_full[s], (it / kStages) & 1);
@@ -248,11 +260,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_f16(tmem_base + 256, ptx::make_smem_desc_sw128(a_addr + k * 32),
-                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, 1u);
+                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(&w_empty[s]);
                 }
-                ptx::umma_commit(acc2_full);   // phase 0: x1 complete
-                ptx::mbar_wait(a_ready, 0);    // the epilogue warps have replaced `att` by LayerNorm(x1) in the A tiles
+                ptx::umma_commit(acc2_full);   // phase 0: att . Wp^T complete
+                PD_FSTAMP(20);            // GEMM-0 issued
+                // the epilogue warps have put x1 into acc2, replaced `att` by LayerNorm(x1) in the A tiles and read acc1 out
+                ptx::mbar_wait(a_ready, 0);
                 ptx::tc_fence_after();
             }
             g1(0);
@@ -301,7 +315,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (PROJ && lane == 0) load_x_round(0);
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (PROJ) {
-            // ---- preset acc2 with x + bp (rounds of kIs 4 KB slabs per warp through the idle mid region) ----
+            // ---- x + bp -> the idle acc1 columns (rounds of kIs 4 KB slabs per warp through the idle mid region), while
+            //      GEMM-0 runs: nothing of this is on its critical path (round 2 preset acc2 itself, GEMM-0 waited for it) ----
 #pragma unroll 1
             for (int r = 0; r < kCh / kIs; ++r) {
                 if (lane == 0 && r > 0) load_x_round(r);
@@ -320,35 +335,42 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         v[4 * i + 2] = __float_as_uint(xv.z + bb.z);
                         v[4 * i + 3] = __float_as_uint(xv.w + bb.w);
                     }
-                    ptx::tmem_st_32x32(t_lane + 256 + c * 32, v);
+                    ptx::tmem_st_32x32(t_lane + c * 32, v);
                 }
                 __syncwarp();   // the slabs are consumed before the next round overwrites them
             }
             ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acc2_init);
-            // ---- E0: x1 = acc2 after GEMM-0; LayerNorm(x1) -> bf16 -> the resident A tiles (the A operand of GEMM-1) ----
-            ptx::mbar_wait(acc2_full, 0);   // every warp is past its preset: mid is idle until E1(0)
+            // the row-statistics exchange below crosses in the first bytes of mid: every warp must be done with its slabs
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            if (et == 0) PD_FSTAMP(7);    // x + bp parked
+            // ---- E0: x1 = (x + bp) + att . Wp^T -> acc2 (GEMM-2 accumulates on top); LayerNorm(x1) -> bf16 -> the resident
+            //      A tiles (the A operand of GEMM-1) ----
+            ptx::mbar_wait(acc2_full, 0);
             ptx::tc_fence_after();
+            if (et == 0) PD_FSTAMP(8);    // GEMM-0 complete
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
             for (int idx = 0; idx < kCh; ++idx) {
-                uint32_t v[32];
+                uint32_t v[32], w[32];
                 ptx::tmem_ld_32x32(t_lane + 256 + (c_begin + idx) * 32, v);
+                ptx::tmem_ld_32x32(t_lane + (c_begin + idx) * 32, w);
                 ptx::tmem_ld_wait();
                 float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains, not one of 32
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float a = __uint_as_float(v[i]);
+                    const float a = __uint_as_float(w[i]) + __uint_as_float(v[i]);
+                    v[i] = __float_as_uint(a);
                     p1[i & 3] += a;
                     p2[i & 3] = fmaf(a, a, p2[i & 3]);
                 }
+                ptx::tmem_st_32x32(t_lane + 256 + (c_begin + idx) * 32, v);
                 s1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
                 s2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
             }
+            ptx::tmem_st_wait();   // the normalising pass below reads x1 back; GEMM-2 accumulates onto it after a_ready
             float mean, rstd;
             row_stats(reinterpret_cast<float2*>(sMid), s1, s2, &mean, &rstd);
+            if (et == 0) PD_FSTAMP(9);    // x1 in acc2, row statistics known
 #pragma unroll 1
             for (int j = 0; j < kCh / 2; ++j) {    // A tile (k-block) c_begin / 2 + j = my chunks 2j, 2j+1 (64 columns)
                 const uint32_t arow = ptx::smem_u32(sA + (c_begin / 2 + j) * kTileA + (q * 32 + lane) * 128);
@@ -382,6 +404,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(a_ready);
+            if (et == 0) PD_FSTAMP(10);   // LayerNorm(x1) in the A tiles
         }
         // ---- E1: GELU chunks -> swizzled A tiles of GEMM-2 ----
         constexpr int kColsPh = 128 / kParts;      // hidden columns per thread and phase (64 or 32)

@@ -130,6 +130,10 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* gptr) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(gptr));
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

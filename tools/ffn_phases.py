@@ -43,6 +43,8 @@ torch.cuda.synchronize()
 s = st.cpu().tolist()
 t0 = s[0]
 print("PROJ variant: MMA warp ready @%d, G1(0) issued @%d" % (s[1] - t0, s[2] - t0))
+print("  prologue from 'ready': A landed +%d, GEMM-0 issued +%d | x + bp parked +%d, GEMM-0 complete +%d, stats +%d, A tiles written +%d"
+      % tuple(s[i] - s[1] for i in (11, 20, 7, 8, 9, 10)))
 for c in range(4):
     print(f"chunk {c}: E1 begin @{s[12 + 2 * c] - t0:6d} dur {s[13 + 2 * c] - s[12 + 2 * c]:5d} | G2 issued @{s[3 + c] - t0:6d}")
 print(f"acc2 complete @{s[28] - t0}, final epilogue {s[29] - s[28]} cycles, exit @{s[30] - t0}")
