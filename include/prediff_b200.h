@@ -377,6 +377,15 @@ int pd_op_ffn_cluster(const void* ln_in_bf16, const void* W1_bf16, const float* 
 int pd_op_ffn_cluster_phases(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                              const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
                              int M, unsigned long long* stamps32, void* stream);
+/* Fused QKV projection + axial attention core (csrc/qkv_attn.cu): out[B][T][H][W][C] (bf16) = softmax(q k^T / sqrt(hd) +
+ * bias) v along `axis` (0 = T, 1 = H, 2 = W; line length <= 16) with q|k|v = ln Wqkv^T formed inside the kernel (rounded to
+ * bf16 as the separate QKV GEMM would). ln bf16 [B][T][H][W][C], Wqkv bf16 [3C][C] (rows: q, k, v; head-major inside each),
+ * bias_table fp32 [2L-1][heads]. Replaces CuboidSelfAttentionLayer.forward's qkv Linear + attention for the axial cuboids
+ * (cuboid_transformer.py:812-861, 949). stamps32 (may be NULL): clock64() phase stamps of CTA (0,0): [0] entry, [1]
+ * dependency wait passed, [2] first head's accumulator complete, [3] staged, [4] first head's lines done, [5] all heads
+ * done; MMA thread: [16] first operands landed, [17] first head issued (tools/qkv_attn_phases.py). */
+int pd_op_qkv_attn(const void* ln_bf16, const void* Wqkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H,
+                   int W, int C, int heads, int axis, unsigned long long* stamps32, void* stream);
 /* The same kernel with the attention output projection fused in front (CuboidSelfAttentionLayer proj +
  * StackCuboidSelfAttentionBlock residual, cuboid_transformer.py:952,1151, then PositionwiseFFN :182-208):
  *   x1 = x + att Wp^T + bp;  x <- x1 + W2 GELU(W1 LayerNorm(x1; ln1) + b1) + b2;  ln_out = LayerNorm(x; ln) (optional).

@@ -370,6 +370,16 @@ int pd_op_gelu_bwd(const float* pre, const void* dy_bf16, void* dpre_bf16, int64
     return gelu_bwd(pre, static_cast<const bf16*>(dy_bf16), static_cast<bf16*>(dpre_bf16), n, S(stream));
 }
 
+int pd_op_qkv_attn(const void* ln_bf16, const void* Wqkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H,
+                   int W, int C, int heads, int axis, unsigned long long* stamps32, void* stream) {
+    PD_TRY(gemm_init());
+    QkvAttnOp op;
+    PD_TRY(qkv_attn_make(&op, static_cast<const bf16*>(ln_bf16), static_cast<const bf16*>(Wqkv_bf16), bias_table,
+                         static_cast<bf16*>(out_bf16), B, T, H, W, C, heads, axis));
+    qkv_attn_set_dbg(&op, stamps32);
+    return qkv_attn_launch(op, S(stream));
+}
+
 int pd_op_axial_attention_bwd(const void* qkv, const float* bias_table, const void* dout, void* dqkv, int B, int T, int H,
                               int W, int C, int heads, int axis, void* stream) {
     PD_TRY(gemm_init());

@@ -211,6 +211,15 @@ struct Plan {
         add([sp](cudaStream_t st) { return ffn_cluster_launch(*sp, st); }, STEP_GEMM, label);
         weight_users.push_back({[](const WRange&) {}, ffn_cluster_weights(op)});   // it is prefetched for, it prefetches nothing
     }
+    void add_qkv_attn(const QkvAttnOp& op, const char* label) {
+        const double fl = qkv_attn_flops(op);
+        gemm_flops += fl;
+        ++n_gemm;
+        auto sp = std::make_shared<QkvAttnOp>(op);
+        add([sp](cudaStream_t st) { return qkv_attn_launch(*sp, st); }, STEP_GEMM, label);
+        flops.back() = fl;
+        weight_users.push_back({[sp](const WRange& r) { qkv_attn_set_prefetch(sp.get(), r); }, qkv_attn_weights(op)});
+    }
     // Every GEMM-family step requests the weights of the next one (the last wraps around to the first of the next pass).
     void link_prefetch() {
         const size_t n = weight_users.size();

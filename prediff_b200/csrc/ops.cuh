@@ -187,6 +187,23 @@ void ffn_cluster_set_dbg(FfnClusterOp* op, unsigned long long* stamps32);   // c
 WRange ffn_cluster_weights(const FfnClusterOp& op);
 int ffn_cluster_launch(const FfnClusterOp& op, cudaStream_t st);
 
+// ---- fused QKV projection + axial attention core (qkv_attn.cu) -----------------------------------------------------
+// att[B][T][H][W][C] (bf16) = axial attention along `axis` (0 = T, 1 = H, 2 = W; line length <= 16) of q|k|v = ln Wqkv^T
+// (no bias), heads of C / heads channels, relative-position bias table [2 L - 1][heads]: the QKV GEMM and
+// axial_attention() in one kernel, bit-identical to that pair (q|k|v are rounded to bf16 before the attention core there
+// as here). ln bf16 [B][T][H][W][C]; Wqkv bf16 [3 C][C]. Reference: cuboid_transformer.py:812-861, 949.
+struct QkvAttnOp {
+    alignas(64) unsigned char storage[768];
+};
+bool qkv_attn_supported(int T, int H, int W, int C, int heads, int axis);
+int qkv_attn_make(QkvAttnOp* op, const bf16* ln, const bf16* wqkv, const float* bias_table, bf16* out, int B, int T, int H,
+                  int W, int C, int heads, int axis);
+void qkv_attn_set_prefetch(QkvAttnOp* op, const WRange& next);
+void qkv_attn_set_dbg(QkvAttnOp* op, unsigned long long* stamps32);   // clock64() phase stamps of CTA (0, 0)
+WRange qkv_attn_weights(const QkvAttnOp& op);
+double qkv_attn_flops(const QkvAttnOp& op);
+int qkv_attn_launch(const QkvAttnOp& op, cudaStream_t st);
+
 // ---- evaluation (eval.cu) ----------------------------------------------------------------------------------
 // SEVIR skill-score contingency counts + error sums, accumulated on the device (evaluation.py:197-245).
 // pred / target fp32 [N][T][H][W] in [0,1]; counts int64 [n_thr][T][3] (hits, misses, false alarms) and sums double [2]

@@ -481,6 +481,14 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
         // produced by the epilogue of the GEMM that last wrote x (conv2 / previous ffn_2).
         const bool ln_ready = fuse && (i > 0 || ln_fusable_conv(lvl));
         if (!ln_ready) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st, prec); }, "ln");
+        if (cub_axis[lvl][i] >= 0 && !prec && qkv_attn_supported(Tn, H, W, C, heads, cub_axis[lvl][i]) &&
+            getenv("PD_NO_QKV_ATTN_FUSION") == nullptr) {
+            // axial layer, bf16 operands: QKV projection + attention core in one kernel (qkv_attn.cu); q|k|v never exist
+            const int axis = cub_axis[lvl][i];
+            QkvAttnOp op;
+            PD_TRY(qkv_attn_make(&op, ln, static_cast<const bf16*>(aw.qkv_w), aw.table, att, B, Tn, H, W, C, heads, axis));
+            pl.add_qkv_attn(op, axis == 0 ? "qkv_attn_T" : (axis == 1 ? "qkv_attn_H" : "qkv_attn_W"));
+        } else {
         {
             GemmEpilogue e;
             operand_out(e, qkv);
@@ -497,6 +505,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             const CuboidDev cd = cub_dev[lvl][i]->dev;
             pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
                    "attn_cuboid");
+        }
         }
         if (C == 256 && !prec && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {
             // width 256: projection + residual + pre-norm + FFN (+ the next layer's LayerNorm) in ONE kernel per row

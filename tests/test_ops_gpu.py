@@ -437,6 +437,34 @@ def test_axial_attention(T, H, W, C, heads, axis):
     assert rel_err(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("B,T,H,W,C,heads", [(4, 13, 16, 16, 256, 4), (1, 13, 16, 16, 256, 4), (4, 13, 8, 8, 512, 4),
+                                             (2, 13, 16, 16, 64, 4), (2, 6, 16, 16, 128, 4), (3, 5, 12, 10, 128, 2),
+                                             (2, 13, 8, 8, 128, 4)])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_qkv_attn_fused(B, T, H, W, C, heads, axis):
+    """Fused QKV projection + axial attention core (csrc/qkv_attn.cu) against (1) the pair of kernels it replaces - the
+    QKV GEMM with bf16 output and axial_attention: bit-identical - and (2) a torch fp32 reference of the layer's core
+    (cuboid_transformer.py:812-861, 949) on the bf16-rounded q|k|v."""
+    ln = _randn(B, T, H, W, C, seed=171).bfloat16()
+    wqkv = _randn(3 * C, C, seed=172, scale=C ** -0.5).bfloat16()
+    Lx = (T, H, W)[axis]
+    table = _randn(2 * Lx - 1, heads, seed=173)
+    out = torch.full((B, T, H, W, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_qkv_attn(L.ptr(ln), L.ptr(wqkv), L.ptr(table), L.ptr(out), B, T, H, W, C, heads, axis, None,
+                                       L.stream_ptr()))
+    M = B * T * H * W
+    qkv = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    _sync_check(L.lib().pd_op_conv_gemm(L.ptr(ln), L.ptr(wqkv), 1, 1, 1, M, C, 1, 1, 1, 3 * C, None, None, None, None,
+                                        L.ptr(qkv), 0, 0, L.stream_ptr()))
+    pair = torch.empty_like(out)
+    _sync_check(L.lib().pd_op_axial_attention(L.ptr(qkv), L.ptr(table), L.ptr(pair), B, T, H, W, C, heads, axis,
+                                              L.stream_ptr()))
+    assert torch.isfinite(out.float()).all()
+    assert torch.equal(out, pair), f"max diff vs the unfused pair {(out.float() - pair.float()).abs().max().item()}"
+    ref = _axial_ref(qkv.view(B, T, H, W, 3 * C), table, B, T, H, W, C, heads, axis)
+    assert rel_err(out, ref) < 8e-3
+
+
 # ------------------------------------------------------------------------------------------------ small ops
 def test_sampler_update():
     n = 4 * 6 * 16 * 16 * 64
