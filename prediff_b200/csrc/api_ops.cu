@@ -376,7 +376,10 @@ int pd_op_qkv_attn(const void* ln_bf16, const void* Wqkv_bf16, const float* bias
     QkvAttnOp op;
     PD_TRY(qkv_attn_make(&op, static_cast<const bf16*>(ln_bf16), static_cast<const bf16*>(Wqkv_bf16), bias_table,
                          static_cast<bf16*>(out_bf16), B, T, H, W, C, heads, axis));
-    qkv_attn_set_dbg(&op, stamps32);
+    // PD_QKV_DBG_CTA="x,y": the CTA that writes the stamps (default 0,0)
+    int cx = 0, cy = 0;
+    if (const char* e = getenv("PD_QKV_DBG_CTA")) sscanf(e, "%d,%d", &cx, &cy);
+    qkv_attn_set_dbg(&op, stamps32, cx, cy);
     return qkv_attn_launch(op, S(stream));
 }
 

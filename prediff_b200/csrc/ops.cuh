@@ -199,7 +199,7 @@ bool qkv_attn_supported(int T, int H, int W, int C, int heads, int axis);
 int qkv_attn_make(QkvAttnOp* op, const bf16* ln, const bf16* wqkv, const float* bias_table, bf16* out, int B, int T, int H,
                   int W, int C, int heads, int axis);
 void qkv_attn_set_prefetch(QkvAttnOp* op, const WRange& next);
-void qkv_attn_set_dbg(QkvAttnOp* op, unsigned long long* stamps32);   // clock64() phase stamps of CTA (0, 0)
+void qkv_attn_set_dbg(QkvAttnOp* op, unsigned long long* stamps32, int cta_x = 0, int cta_y = 0);   // phase stamps of one CTA
 WRange qkv_attn_weights(const QkvAttnOp& op);
 double qkv_attn_flops(const QkvAttnOp& op);
 int qkv_attn_launch(const QkvAttnOp& op, cudaStream_t st);

@@ -51,6 +51,7 @@ struct QkvAttnParams {
     int ring_off, bar_off;
     WRange pf;
     unsigned long long* dbg;
+    int dbg_x, dbg_y;          // the CTA that writes the stamps
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t a) {
@@ -114,10 +115,27 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int L = p.L;
     const int n_lines = rows_box / L;
     const int gstride = p.axis == 2 ? 1 : (p.axis == 1 ? p.W : p.H * p.W);   // tokens between positions of a line
-    unsigned long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? p.dbg : nullptr;
+    unsigned long long* dbg = (p.dbg && (int)blockIdx.x == p.dbg_x && (int)blockIdx.y == p.dbg_y) ? p.dbg : nullptr;
 #define PD_QSTAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
     const bool stamper = threadIdx.x == 64;
     if (stamper) PD_QSTAMP(0);
+    if (stamper && p.dbg && p.dbg_x < 0) {   // every CTA: entry time + SM id (buffer of 32 + 3 * CTAs words)
+        unsigned long long gt;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* d = p.dbg + 32 + 3 * (blockIdx.y * gridDim.x + blockIdx.x);
+        d[0] = gt;
+        d[2] = smid;
+    }
+    if (stamper && dbg) {
+        unsigned long long gt;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[8] = gt;
+        dbg[11] = smid;
+    }
     if (threadIdx.x == 32) prefetch_l2_share(p.pf, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
 
     if (threadIdx.x == 0) {
@@ -424,6 +442,17 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::ALLOC);
+    if (stamper && p.dbg && p.dbg_x < 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[32 + 3 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = gt;
+    }
+    if (stamper && dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[9] = gt;
+        dbg[10] = clock64();
+    }
 #undef PD_QSTAMP
 }
 
@@ -437,11 +466,13 @@ struct QkvAttnOpImpl {
 };
 static_assert(sizeof(QkvAttnOpImpl) <= sizeof(QkvAttnOp), "QkvAttnOp storage too small");
 
-// largest divisor of n that is <= cap (>= 1)
-int best_divisor(int n, int cap) {
-    for (int d = cap < n ? cap : n; d >= 1; --d)
-        if (n % d == 0) return d;
-    return 1;
+// smallest box extent <= cap that covers n in the fewest boxes (the last box may hang over the edge: TMA zero-fills the
+// rows, the kernel skips the lines)
+int fewest_boxes(int n, int cap) {
+    if (cap < 1) cap = 1;
+    if (cap > n) cap = n;
+    const int boxes = (n + cap - 1) / cap;
+    return (n + boxes - 1) / boxes;
 }
 
 template <int HD>
@@ -480,7 +511,7 @@ int qkv_attn_make(QkvAttnOp* op_, const bf16* ln, const bf16* wqkv, const float*
     p.bias_table = bias_table; p.out = out;
     p.T = T; p.H = H; p.W = W; p.C = C; p.heads = heads; p.axis = axis;
     p.L = axis == 0 ? T : (axis == 1 ? H : W);
-    // token box: full extent along the attended axis, then grow W, H, T (in that order) by divisors up to 128 rows
+    // token box: full extent along the attended axis, then grow W, H, T (in that order) up to 128 rows
     int box[3] = {1, 1, 1};            // W, H, T
     const int dim[3] = {W, H, T};
     const int ax = 2 - axis;           // index into box[] / dim[]
@@ -488,7 +519,7 @@ int qkv_attn_make(QkvAttnOp* op_, const bf16* ln, const bf16* wqkv, const float*
     int rows = box[ax];
     for (int d = 0; d < 3; ++d) {
         if (d == ax) continue;
-        box[d] = best_divisor(dim[d], 128 / rows);
+        box[d] = fewest_boxes(dim[d], 128 / rows);
         rows *= box[d];
     }
     p.bw = box[0]; p.bh = box[1]; p.bt = box[2];
@@ -550,7 +581,12 @@ int qkv_attn_make(QkvAttnOp* op_, const bf16* ln, const bf16* wqkv, const float*
 }
 
 void qkv_attn_set_prefetch(QkvAttnOp* op_, const WRange& next) { reinterpret_cast<QkvAttnOpImpl*>(op_)->p.pf = next; }
-void qkv_attn_set_dbg(QkvAttnOp* op_, unsigned long long* stamps) { reinterpret_cast<QkvAttnOpImpl*>(op_)->p.dbg = stamps; }
+void qkv_attn_set_dbg(QkvAttnOp* op_, unsigned long long* stamps, int cta_x, int cta_y) {
+    QkvAttnOpImpl* op = reinterpret_cast<QkvAttnOpImpl*>(op_);
+    op->p.dbg = stamps;
+    op->p.dbg_x = cta_x;
+    op->p.dbg_y = cta_y;
+}
 WRange qkv_attn_weights(const QkvAttnOp& op_) { return reinterpret_cast<const QkvAttnOpImpl&>(op_).own_w; }
 double qkv_attn_flops(const QkvAttnOp& op_) {
     const QkvAttnParams& p = reinterpret_cast<const QkvAttnOpImpl&>(op_).p;
