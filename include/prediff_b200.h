@@ -377,6 +377,16 @@ int pd_op_ffn_cluster(const void* ln_in_bf16, const void* W1_bf16, const float* 
 int pd_op_ffn_cluster_phases(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16,
                              const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16,
                              int M, unsigned long long* stamps32, void* stream);
+/* pd_op_ffn_cluster with the attention output projection fused in front (width 512; CuboidSelfAttentionLayer proj +
+ * StackCuboidSelfAttentionBlock residual, cuboid_transformer.py:952,1151, then PositionwiseFFN :182-208):
+ *   x1 = x + att Wp^T + bp;  x <- x1 + W2 GELU(W1 LayerNorm(x1; ln1) + b1) + b2;  ln_out = LayerNorm(x; ln) (optional).
+ * Each CTA of the 4-CTA cluster forms 128 columns of x1; LayerNorm(x1) crosses L2 through ln_scratch_bf16 [M][512] (may be
+ * the ln_out buffer). Extra stamps: [22] first G0 operands landed, [23] G0 issued, [24] x1 complete, [25] E0 done. */
+int pd_op_proj_ffn_cluster(const void* att_bf16, const void* Wp_bf16, const float* bp, const float* ln1_gamma,
+                           const float* ln1_beta, void* ln_scratch_bf16, const void* W1_bf16, const float* b1,
+                           const void* W2_bf16, const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta,
+                           void* ln_out_bf16, double* gn_sums, int gn_groups, int gn_rows, int M, unsigned long long* stamps32,
+                           void* stream);
 /* Fused QKV projection + axial attention core (csrc/qkv_attn.cu): out[B][T][H][W][C] (bf16) = softmax(q k^T / sqrt(hd) +
  * bias) v along `axis` (0 = T, 1 = H, 2 = W; line length <= 16) with q|k|v = ln Wqkv^T formed inside the kernel (rounded to
  * bf16 as the separate QKV GEMM would). ln bf16 [B][T][H][W][C], Wqkv bf16 [3C][C] (rows: q, k, v; head-major inside each),

@@ -249,7 +249,8 @@ int pd_op_cuboid_attention_impl(const void* qkv, const float* bias_table, void* 
 // one launch with a stream-ordered temporary workspace (the models keep one per plan instead)
 static int ffn_cluster_once(const void* ln_in_bf16, const void* W1_bf16, const float* b1, const void* W2_bf16, const float* b2,
                             float* x_inout, const float* ln_gamma, const float* ln_beta, void* ln_out_bf16, double* gn_sums,
-                            int gn_groups, int gn_rows, int M, unsigned long long* stamps32, void* stream) {
+                            int gn_groups, int gn_rows, int M, unsigned long long* stamps32, void* stream,
+                            const FfnProjArgs* proj = nullptr) {
     PD_TRY(gemm_init());
     PD_CHECK(M >= 1, PD_ERR_ARG, "ffn_cluster: M must be positive");
     cudaStream_t st = S(stream);
@@ -258,7 +259,7 @@ static int ffn_cluster_once(const void* ln_in_bf16, const void* W1_bf16, const f
     FfnClusterOp op;
     int rc = ffn_cluster_make(&op, static_cast<const bf16*>(ln_in_bf16), M, static_cast<const bf16*>(W1_bf16), b1,
                               static_cast<const bf16*>(W2_bf16), b2, x_inout, ln_gamma, ln_beta,
-                              static_cast<bf16*>(ln_out_bf16), 1e-5f, ws);
+                              static_cast<bf16*>(ln_out_bf16), 1e-5f, ws, proj);
     if (rc == PD_OK && gn_sums) rc = ffn_cluster_set_gn(&op, gn_sums, gn_groups, gn_rows);
     if (rc == PD_OK) {
         ffn_cluster_set_dbg(&op, stamps32);
@@ -280,6 +281,20 @@ int pd_op_ffn_cluster_phases(const void* ln_in_bf16, const void* W1_bf16, const 
                              int M, unsigned long long* stamps32, void* stream) {
     return ffn_cluster_once(ln_in_bf16, W1_bf16, b1, W2_bf16, b2, x_inout, ln_gamma, ln_beta, ln_out_bf16, nullptr, 0, 0, M,
                             stamps32, stream);
+}
+
+int pd_op_proj_ffn_cluster(const void* att_bf16, const void* Wp_bf16, const float* bp, const float* ln1_gamma,
+                           const float* ln1_beta, void* ln_scratch_bf16, const void* W1_bf16, const float* b1,
+                           const void* W2_bf16, const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta,
+                           void* ln_out_bf16, double* gn_sums, int gn_groups, int gn_rows, int M, unsigned long long* stamps32,
+                           void* stream) {
+    PD_CHECK(att_bf16 && Wp_bf16 && bp && ln1_gamma && ln1_beta && ln_scratch_bf16, PD_ERR_ARG,
+             "proj_ffn_cluster: null projection argument");
+    FfnProjArgs pa;
+    pa.att = static_cast<const bf16*>(att_bf16); pa.wp = static_cast<const bf16*>(Wp_bf16); pa.bp = bp;
+    pa.ln1_gamma = ln1_gamma; pa.ln1_beta = ln1_beta;
+    return ffn_cluster_once(ln_scratch_bf16, W1_bf16, b1, W2_bf16, b2, x_inout, ln_gamma, ln_beta, ln_out_bf16, gn_sums,
+                            gn_groups, gn_rows, M, stamps32, stream, &pa);
 }
 
 int pd_ssim_update(const float* pred, const float* target, int N, int H, int W, float data_range, double* state,

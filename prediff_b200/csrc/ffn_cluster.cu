@@ -61,6 +61,16 @@ constexpr int kOffLnPeer = kOffLnX + 2 * 128 * 8;         // [4][128] float2: pe
 static_assert(kOffLnPeer + kCl * 128 * 8 <= kPipeBytes, "reduce buffers must fit in the dead ring + mid region");
 constexpr int kBarBytes = 512;
 constexpr int kSmem = kPipeBytes + 1024 + kBarBytes;
+// PROJ variant, phase G0 (x1 = x + att Wp^T + bp for the CTA's 128 output columns): four stages of (att tile 16 KB + Wp tile
+// 16 KB) = the 96 KB ring + hidden-slice tiles 4-5; E0's residual / LayerNorm slabs sit in hidden-slice tiles 0-3 (8 KB per
+// warp) and its row-statistics exchange in tile 7 - all of it dead again before E1 writes the hidden slice.
+constexpr int kTileP = 128 * 64 * 2;         // Wp tile: 128 output rows x 64
+constexpr int kStage0 = kTileA + kTileP;     // 32 KB
+__host__ __device__ constexpr int g0_off(int s) { return s < 3 ? s * kStage0 : kRingBytes + 4 * kTileA; }
+constexpr int kOffSlab0 = kRingBytes;                      // 8 warps x 2 x 4 KB (fp32; the first one is re-used for bf16)
+constexpr int kOffLn0X = kRingBytes + 7 * kTileA;          // [2][128] float2 (tile 7: no G1 slot covers it)
+constexpr int kOffLn0Peer = kOffLn0X + 2 * 128 * 8;        // [4][128] float2
+constexpr int kG1PreProj = 3;                // W1 tiles requested once G0 is complete (slot 3 still holds E0's slabs)
 constexpr size_t kWsFloatsPerTile = (size_t)kCl * (kCl - 1) * 128 * kOs;   // 4 destinations x 3 senders x 128 x 128
 
 struct FfnClParams {
@@ -74,16 +84,22 @@ struct FfnClParams {
     double* gn_sums;
     int gn_cpg, gn_groups, gn_rows;
     unsigned long long* dbg;   // optional clock64() stamps of CTA 0 (tools/ffn_cluster_phases.py): see PD_CSTAMP sites
+    // PROJ variant: attention output projection + residual + the FFN's pre-norm in front (x1 = x + att Wp^T + bp)
+    const float* bp;
+    const float* ln1_gamma;
+    const float* ln1_beta;
 };
 
 // receive slot of sender s at destination d (s != d): senders in rank order, skipping d itself
 __device__ __forceinline__ int recv_slot(int s, int d) { return s < d ? s : s - 1; }
 
-template <bool GN>
+template <bool PROJ, bool GN>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                    const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x,
-                   const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ FfnClParams p) {
+                   const __grid_constant__ CUtensorMap tmap_ln, const __grid_constant__ CUtensorMap tmap_att,
+                   const __grid_constant__ CUtensorMap tmap_wp, const __grid_constant__ CUtensorMap tmap_ln1,
+                   const __grid_constant__ FfnClParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sMid = smem + kRingBytes;
@@ -96,7 +112,12 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint64_t* mid_full = acc_full + 2;       // [2]: E1(c) has written its four k-blocks (and read acc[c] out)
     uint64_t* acc2_full = mid_full + 2;      // [2]: output columns [0, 256) of the partial complete / all of it
     uint64_t* res_bar = acc2_full + 2;       // [8 warps][2]: residual slabs landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+    uint64_t* g0_full = res_bar + 2 * kEpiWarps;   // [4]: PROJ, G0 stages
+    uint64_t* g0_empty = g0_full + 4;           // [4]
+    uint64_t* acc0_full = g0_empty + 4;         // [1]: x1 columns complete in TMEM columns [0, 128)
+    uint64_t* stat_bar = acc0_full + 1;         // [1]: the three peers' row sums of x1 have landed (st.async complete_tx)
+    uint64_t* ln_ready = stat_bar + 1;          // [1]: every CTA of the cluster has published its LayerNorm(x1) slice
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_ready + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -124,6 +145,16 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::mbar_init(&acc2_full[0], 1);
         ptx::mbar_init(&acc2_full[1], 1);
         for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&res_bar[s], 1);
+        if (PROJ) {
+            for (int s = 0; s < 4; ++s) {
+                ptx::mbar_init(&g0_full[s], 1);
+                ptx::mbar_init(&g0_empty[s], 1);
+            }
+            ptx::mbar_init(acc0_full, 1);
+            ptx::mbar_init(stat_bar, 1);
+            ptx::mbar_init(ln_ready, kCl);
+            ptx::mbar_arrive_expect_tx(stat_bar, (kCl - 1) * 128 * 8);   // armed before any peer can send
+        }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
     }
@@ -133,13 +164,26 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::prefetch_tmap(&tmap_w2);
         ptx::prefetch_tmap(&tmap_x);
         ptx::prefetch_tmap(&tmap_ln);
+        if (PROJ) {
+            ptx::prefetch_tmap(&tmap_att);
+            ptx::prefetch_tmap(&tmap_wp);
+            ptx::prefetch_tmap(&tmap_ln1);
+        }
     }
     // weight tiles of the first stages do not depend on the preceding kernel: requested before the dependency wait
     if (threadIdx.x == 0) {
+        if (PROJ) {
 #pragma unroll
-        for (int it = 0; it < kG1Pre; ++it) {
-            ptx::mbar_arrive_expect_tx(&w_full[g1_slot(it)], kStage);
-            ptx::tma_load_2d(smem + slot_off(g1_slot(it)) + kTileA, &tmap_w1, &w_full[g1_slot(it)], it * 64, j * kHs);
+            for (int it = 0; it < 4; ++it) {
+                ptx::mbar_arrive_expect_tx(&g0_full[it], kStage0);
+                ptx::tma_load_2d(smem + g0_off(it) + kTileA, &tmap_wp, &g0_full[it], it * 64, j * kOs);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < kG1Pre; ++it) {
+                ptx::mbar_arrive_expect_tx(&w_full[g1_slot(it)], kStage);
+                ptx::tma_load_2d(smem + slot_off(g1_slot(it)) + kTileA, &tmap_w1, &w_full[g1_slot(it)], it * 64, j * kHs);
+            }
         }
     }
     if (warp == 1) {
@@ -150,6 +194,14 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PROJ: peers exchange row sums / arrivals through this CTA's barriers long before the first full cluster barrier -
+    // split-phase: arrive now (the barrier initialisation above is published by fence.mbarrier_init), wait before the
+    // first remote access
+    if (PROJ) ptx::cluster_arrive();
+    if (PROJ && warp == 2 && lane < 12) {   // the CTA's 128 columns of bp / ln1 gamma / ln1 beta -> L1 (4 lines each)
+        const float* v = lane < 4 ? p.bp : (lane < 8 ? p.ln1_gamma : p.ln1_beta);
+        ptx::prefetch_l1(v + j * kOs + (lane & 3) * 32);
+    }
     grid_dep_launch();
     grid_dep_wait();
     if (stamper) PD_CSTAMP(1);
@@ -164,11 +216,34 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
+            constexpr int n_pre = PROJ ? kG1PreProj : kG1Pre;
+            if (PROJ) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {   // G0: att k-block + Wp tile per stage
+                    const int s = it & 3;
+                    uint8_t* st = smem + g0_off(s);
+                    if (it >= 4) {
+                        ptx::mbar_wait(&g0_empty[s], 0);
+                        ptx::mbar_arrive_expect_tx(&g0_full[s], kStage0);
+                        ptx::tma_load_2d(st + kTileA, &tmap_wp, &g0_full[s], it * 64, j * kOs);
+                    }
+                    ptx::tma_load_3d(st, &tmap_att, &g0_full[s], it * 64, row_tile, 0);
+                }
+                ptx::mbar_wait(acc0_full, 0);   // every G0 MMA has completed: the G0 stages are dead
+#pragma unroll
+                for (int it = 0; it < n_pre; ++it) {
+                    ptx::mbar_arrive_expect_tx(&w_full[g1_slot(it)], kStage);
+                    ptx::tma_load_2d(smem + slot_off(g1_slot(it)) + kTileA, &tmap_w1, &w_full[g1_slot(it)], it * 64, j * kHs);
+                }
+                // LayerNorm(x1) of the whole row tile = the four CTAs' slices, published through L2
+                ptx::mbar_wait_cluster(ln_ready, 0);
+                ptx::fence_proxy_async_all();
+            }
 #pragma unroll
             for (int it = 0; it < 16; ++it) {
                 const int c = it >> 3, kb = it & 7, s = g1_slot(it), u = g1_use(it);
                 uint8_t* st = smem + slot_off(s);
-                if (it >= kG1Pre) {   // the first W1 tiles were requested in the prologue
+                if (it >= n_pre) {   // the first W1 tiles were requested in the prologue (PROJ: right after G0)
                     if (u > 0) ptx::mbar_wait(&w_empty[s], (u - 1) & 1);
                     ptx::mbar_arrive_expect_tx(&w_full[s], kStage);
                     ptx::tma_load_2d(st + kTileA, &tmap_w1, &w_full[s], kb * 64, j * kHs + c * 256);
@@ -191,6 +266,25 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256);
+            if (PROJ) {   // G0: TMEM columns [0, 128) = att . Wp[128 j ...]^T
+                constexpr uint32_t idesc0 = ptx::make_idesc_bf16(128, kOs);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int s = it & 3;
+                    ptx::mbar_wait(&g0_full[s], (it >> 2) & 1);
+                    ptx::tc_fence_after();
+                    if (it == 0) PD_CSTAMP(22);
+                    const uint32_t a_addr = ptx::smem_u32(smem + g0_off(s));
+                    const uint32_t b_addr = a_addr + kTileA;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_base, ptx::make_smem_desc_sw128(a_addr + k * 32),
+                                      ptx::make_smem_desc_sw128(b_addr + k * 32), idesc0, (it | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&g0_empty[s]);
+                }
+                ptx::umma_commit(acc0_full);
+                PD_CSTAMP(23);
+            }
 #pragma unroll
             for (int it = 0; it < 16; ++it) {
                 const int c = it >> 3, kb = it & 7, s = g1_slot(it), u = g1_use(it);
@@ -231,10 +325,132 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             PD_CSTAMP(21);
         }
     } else {
-        // ---- E1: GELU'd hidden slice -> swizzled A tiles of G2 ----
         const int q = warp & 3, half = (warp - 2) >> 2;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        if (PROJ) {
+            // ---- E0: x1 = (att Wp^T + bp) + x for the CTA's 128 columns -> x; LayerNorm(x1) -> the pre-norm tensor ----
+            const int e0 = warp - 2, r0 = q * 32 + lane;
+            const int c0 = j * kOs + half * 64, rw0 = row_tile + q * 32;
+            uint8_t* slab = smem + kOffSlab0 + e0 * 8192;          // two fp32 slabs (32 rows x 32 columns, swizzled rows)
+            uint64_t* rb = res_bar + 2 * e0;
+            if (lane == 0) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    ptx::mbar_arrive_expect_tx(&rb[g], 4096);
+                    ptx::tma_load_3d(slab + g * 4096, &tmap_x, &rb[g], c0 + g * 32, rw0, 0);
+                }
+            }
+            ptx::mbar_wait(acc0_full, 0);
+            ptx::tc_fence_after();
+            if (stamper) PD_CSTAMP(24);
+            float xr[64];
+            {
+                uint32_t v0[32], v1[32];
+                ptx::tmem_ld_32x32(t_lane + half * 64, v0);
+                ptx::tmem_ld_32x32(t_lane + half * 64 + 32, v1);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { xr[i] = __uint_as_float(v0[i]); xr[32 + i] = __uint_as_float(v1[i]); }
+            }
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                ptx::mbar_wait(&rb[g], 0);
+                uint8_t* my_row = slab + g * 4096 + lane * 128;
+                // all eight residual cells first: a generic-address store between two loads would serialise them (the
+                // compiler must assume they alias)
+                float4 resv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    resv[i] = *reinterpret_cast<const float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bp + c0 + g * 32 + 4 * i));
+                    float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                    const float4 res = resv[i];
+                    float4 a;
+                    a.x = (xr[g * 32 + 4 * i] + bb.x) + res.x; a.y = (xr[g * 32 + 4 * i + 1] + bb.y) + res.y;
+                    a.z = (xr[g * 32 + 4 * i + 2] + bb.z) + res.z; a.w = (xr[g * 32 + 4 * i + 3] + bb.w) + res.w;
+                    *cell = a;
+                    xr[g * 32 + 4 * i] = a.x; xr[g * 32 + 4 * i + 1] = a.y; xr[g * 32 + 4 * i + 2] = a.z; xr[g * 32 + 4 * i + 3] = a.w;
+                    s1 += (a.x + a.y) + (a.z + a.w);
+                    s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+                }
+            }
+            if (stamper) PD_CSTAMP(26);
+            // row statistics over the 512 columns: two threads per row inside the CTA, then the four CTAs (st.async onto the
+            // peers' armed barriers: no release fence on the sending side)
+            float2* ln_x = reinterpret_cast<float2*>(smem + kOffLn0X);
+            float2* ln_peer = reinterpret_cast<float2*>(smem + kOffLn0Peer);
+            ln_x[half * 128 + r0] = make_float2(s1, s2);
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            const float2 o = ln_x[(half ^ 1) * 128 + r0];
+            const float t1 = half == 0 ? s1 + o.x : o.x + s1, t2 = half == 0 ? s2 + o.y : o.y + s2;
+            ptx::cluster_wait();   // peers have initialised their barriers (arrive at kernel start)
+            if (half == 0) {
+#pragma unroll
+                for (int dd = 1; dd < kCl; ++dd) {
+                    const uint32_t d = (uint32_t)((j + dd) & (kCl - 1));
+                    ptx::st_async_cluster_f32x2(ptx::mapa(ptx::smem_u32(&ln_peer[j * 128 + r0]), d), t1, t2,
+                                                ptx::mapa(ptx::smem_u32(stat_bar), d));
+                }
+            }
+            ptx::mbar_wait_cluster(stat_bar, 0);
+            float tot1 = 0.f, tot2 = 0.f;
+#pragma unroll
+            for (int sdr = 0; sdr < kCl; ++sdr) {   // rank order, the CTA's own total in its place
+                float2 t = ln_peer[sdr * 128 + r0];
+                if (sdr == j) t = make_float2(t1, t2);
+                tot1 = sdr == 0 ? t.x : tot1 + t.x;
+                tot2 = sdr == 0 ? t.y : tot2 + t.y;
+            }
+            const float mean = tot1 * (1.0f / kC);
+            const float var = fmaxf(tot2 * (1.0f / kC) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + p.ln_eps);
+            if (stamper) PD_CSTAMP(27);
+            // bf16 slab: the (still empty) A part of G1's ring slots 0 / 1 - refilled only after ln_ready
+            uint8_t* bslab = smem + (e0 < 4 ? 0 : kStage) + (e0 & 3) * 4096;
+            uint8_t* brow = bslab + lane * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln1_gamma + c0 + 8 * i));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln1_gamma + c0 + 8 * i + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln1_beta + c0 + 8 * i));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln1_beta + c0 + 8 * i + 4));
+                uint4 pk;
+                pk.x = pack_bf16x2(fmaf((xr[8 * i] - mean) * rstd, g0.x, b0.x), fmaf((xr[8 * i + 1] - mean) * rstd, g0.y, b0.y));
+                pk.y = pack_bf16x2(fmaf((xr[8 * i + 2] - mean) * rstd, g0.z, b0.z), fmaf((xr[8 * i + 3] - mean) * rstd, g0.w, b0.w));
+                pk.z = pack_bf16x2(fmaf((xr[8 * i + 4] - mean) * rstd, g1.x, b1.x), fmaf((xr[8 * i + 5] - mean) * rstd, g1.y, b1.y));
+                pk.w = pack_bf16x2(fmaf((xr[8 * i + 6] - mean) * rstd, g1.z, b1.z), fmaf((xr[8 * i + 7] - mean) * rstd, g1.w, b1.w));
+                *reinterpret_cast<uint4*>(brow + ((static_cast<uint32_t>(i) ^ sw) << 4)) = pk;
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_3d(&tmap_ln1, bslab, c0, rw0, 0);
+                ptx::bulk_commit();
+                // x1 -> x behind it (only the reduce phase at the end of the kernel reads it back): a younger bulk group
+#pragma unroll
+                for (int g = 0; g < 2; ++g) ptx::tma_store_3d(&tmap_x, slab + g * 4096, c0 + g * 32, rw0, 0);   // rows past M are clipped
+                ptx::bulk_commit();
+                ptx::bulk_wait_all<1>();            // LayerNorm(x1) of this warp's rows is written
+                if (stamper) PD_CSTAMP(28);
+            }
+            // one release per CTA: the eight warps' slabs are complete at the named barrier, one thread then arrives on the
+            // ln_ready barrier of every CTA of the cluster (release at cluster scope; the readers acquire, then fence the
+            // async proxy before their TMA loads)
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            if (threadIdx.x == 64) {
+#pragma unroll
+                for (int d = 0; d < kCl; ++d) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(ln_ready), (uint32_t)d));
+            }
+            if (lane == 0) ptx::bulk_wait_read<0>();   // the x stores have read the slabs: E1 may overwrite them
+            __syncwarp();
+            if (stamper) PD_CSTAMP(25);
+        }
+        // ---- E1: GELU'd hidden slice -> swizzled A tiles of G2 ----
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             ptx::mbar_wait(&acc_full[c], 0);
@@ -315,6 +531,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         if (stamper) PD_CSTAMP(8);
     }
+    if (PROJ && warp < 2) ptx::cluster_wait();   // second half of the split-phase barrier of the prologue (epilogue warps: E0)
     ptx::cluster_sync_all();                // release / acquire at cluster scope: every CTA's slices are visible
     if (stamper) PD_CSTAMP(9);
     float s1 = 0.f, s2 = 0.f;
@@ -340,9 +557,13 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (hb == 0) {
                 ptx::tmem_ld_32x32(t_lane + (uint32_t)(col0 + g * 32), v);
                 ptx::tmem_ld_wait();
-                ptx::mbar_wait(&my_bar[g], 0);
+                ptx::mbar_wait(&my_bar[g], PROJ ? 1 : 0);
             }
             uint8_t* my_row = slabF + g * 4096 + lane * 128;
+            float4 resv[4];   // loads before the stores of the batch (generic addresses: a store in between serialises them)
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+                resv[ii] = *reinterpret_cast<const float4*>(my_row + ((static_cast<uint32_t>(hb * 4 + ii) ^ sw) << 4));
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int i = hb * 4 + ii;
@@ -363,7 +584,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 }
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + g * 32 + 4 * i));
                 float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
-                const float4 res = *cell;
+                const float4 res = resv[ii];
                 acc.x = (acc.x + bb.x) + res.x; acc.y = (acc.y + bb.y) + res.y;
                 acc.z = (acc.z + bb.z) + res.z; acc.w = (acc.w + bb.w) + res.w;
                 *cell = acc;
@@ -458,9 +679,10 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 }
 
 struct FfnClusterOpImpl {
-    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln;
+    CUtensorMap tmap_a, tmap_w1, tmap_w2, tmap_x, tmap_ln, tmap_att, tmap_wp, tmap_ln1;
     FfnClParams p;
     int tiles;
+    int proj;
     WRange own_w;
 };
 static_assert(sizeof(FfnClusterOpImpl) <= sizeof(FfnClusterOp), "FfnClusterOp storage too small");
@@ -471,16 +693,20 @@ size_t ffn_cluster_workspace_bytes(int M) { return (size_t)ceil_div(M, 128) * kW
 
 int ffn_cluster_make(FfnClusterOp* op_, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
                      const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out, float ln_eps,
-                     float* workspace) {
+                     float* workspace, const FfnProjArgs* proj) {
     PD_TRY(gemm_init());
     FfnClusterOpImpl* op = reinterpret_cast<FfnClusterOpImpl*>(op_);
     PD_CHECK(ln_in && w1 && b1 && w2 && b2 && x_inout && workspace && M >= 1, PD_ERR_ARG, "ffn_cluster: null argument");
     PD_CHECK((ln_gamma != nullptr) == (ln_out != nullptr) && (ln_gamma != nullptr) == (ln_beta != nullptr), PD_ERR_ARG,
              "ffn_cluster: LayerNorm output needs gamma, beta and the output tensor");
+    PD_CHECK(!proj || (proj->att && proj->wp && proj->bp && proj->ln1_gamma && proj->ln1_beta), PD_ERR_ARG,
+             "ffn_cluster: incomplete projection arguments");
     static bool attr_set = false;
     if (!attr_set) {
-        PD_CUDA(cudaFuncSetAttribute(ffn_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        PD_CUDA(cudaFuncSetAttribute(ffn_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(ffn_cluster_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(ffn_cluster_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(ffn_cluster_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        PD_CUDA(cudaFuncSetAttribute(ffn_cluster_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
     const uint64_t dims_a[3] = {kC, (uint64_t)M, 1}, st_a[2] = {kC * 2, (uint64_t)kC * 2 * M};
@@ -497,6 +723,17 @@ int ffn_cluster_make(FfnClusterOp* op_, const bf16* ln_in, int M, const bf16* w1
     PD_TRY(tmap_encode_sw128(&op->tmap_x, false, 3, x_inout, dims_x, st_x, box_x));
     const uint32_t box_ln[3] = {64, 32, 1};
     PD_TRY(tmap_encode_sw128(&op->tmap_ln, true, 3, ln_out ? ln_out : ln_in, dims_a, st_a, box_ln));
+    op->proj = proj != nullptr;
+    op->tmap_att = op->tmap_a; op->tmap_wp = op->tmap_w1; op->tmap_ln1 = op->tmap_ln;
+    op->p.bp = op->p.ln1_gamma = op->p.ln1_beta = nullptr;
+    if (proj) {   // x1 = x + att Wp^T + bp; LayerNorm(x1; ln1) -> ln_in (the tensor G1 then loads as its A operand)
+        PD_TRY(tmap_encode_sw128(&op->tmap_att, true, 3, proj->att, dims_a, st_a, box_a));
+        const uint64_t dp[2] = {kC, kC}, sp[1] = {kC * 2};     // Wp [512][512]
+        const uint32_t boxp[2] = {64, (uint32_t)kOs};
+        PD_TRY(tmap_encode_sw128(&op->tmap_wp, true, 2, proj->wp, dp, sp, boxp));
+        PD_TRY(tmap_encode_sw128(&op->tmap_ln1, true, 3, ln_in, dims_a, st_a, box_ln));
+        op->p.bp = proj->bp; op->p.ln1_gamma = proj->ln1_gamma; op->p.ln1_beta = proj->ln1_beta;
+    }
     op->p.b1 = b1; op->p.b2 = b2; op->p.ln_gamma = ln_gamma; op->p.ln_beta = ln_beta;
     op->p.ws = workspace; op->p.ln_eps = ln_eps; op->p.M = M;
     op->p.gn_sums = nullptr; op->p.gn_cpg = op->p.gn_groups = op->p.gn_rows = 0;
@@ -505,6 +742,7 @@ int ffn_cluster_make(FfnClusterOp* op_, const bf16* ln_in, int M, const bf16* w1
     op->own_w = WRange{};
     op->own_w.p[0] = reinterpret_cast<const uint8_t*>(w1); op->own_w.n[0] = (uint32_t)((size_t)kHid * kC * 2);
     op->own_w.p[1] = reinterpret_cast<const uint8_t*>(w2); op->own_w.n[1] = (uint32_t)((size_t)kHid * kC * 2);
+    if (proj) { op->own_w.p[2] = reinterpret_cast<const uint8_t*>(proj->wp); op->own_w.n[2] = (uint32_t)((size_t)kC * kC * 2); }
     return PD_OK;
 }
 
@@ -523,12 +761,17 @@ WRange ffn_cluster_weights(const FfnClusterOp& op_) { return reinterpret_cast<co
 
 int ffn_cluster_launch(const FfnClusterOp& op_, cudaStream_t st) {
     const FfnClusterOpImpl& op = reinterpret_cast<const FfnClusterOpImpl&>(op_);
-    if (op.p.gn_sums)
-        PD_CUDA(launch_pdl(ffn_cluster_kernel<true>, dim3(op.tiles * kCl), dim3(kThreads), (size_t)kSmem, st, dim3(kCl, 1, 1),
-                           op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.p));
-    else
-        PD_CUDA(launch_pdl(ffn_cluster_kernel<false>, dim3(op.tiles * kCl), dim3(kThreads), (size_t)kSmem, st, dim3(kCl, 1, 1),
-                           op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.p));
+#define PD_FCL_LAUNCH(PROJ, GN)                                                                                           \
+    PD_CUDA(launch_pdl(ffn_cluster_kernel<PROJ, GN>, dim3(op.tiles * kCl), dim3(kThreads), (size_t)kSmem, st, dim3(kCl, 1, 1), \
+                       op.tmap_a, op.tmap_w1, op.tmap_w2, op.tmap_x, op.tmap_ln, op.tmap_att, op.tmap_wp, op.tmap_ln1, op.p))
+    if (op.proj) {
+        if (op.p.gn_sums) PD_FCL_LAUNCH(true, true);
+        else PD_FCL_LAUNCH(true, false);
+    } else {
+        if (op.p.gn_sums) PD_FCL_LAUNCH(false, true);
+        else PD_FCL_LAUNCH(false, false);
+    }
+#undef PD_FCL_LAUNCH
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

@@ -174,14 +174,17 @@ int ffn_fused_launch(const FfnFusedOp& op, cudaStream_t st);
 // distributed-shared-memory reduce-scatter, optionally followed by the fused LayerNorm of the new rows -> ln_out (bf16)
 // and the GroupNorm statistics of the new rows. ln_in bf16 [M][512]; W1 bf16 [2048][512]; W2 bf16 [512][2048].
 struct FfnClusterOp {
-    alignas(64) unsigned char storage[1024];
+    alignas(64) unsigned char storage[1536];
 };
+// Optional front-end (FfnProjArgs, width 512 here): x1 = x + att Wp^T + bp and the FFN's pre-norm LayerNorm(x1) are computed
+// by the kernel as well - each CTA of the cluster its 128 output columns, row sums exchanged through distributed shared
+// memory, the normalised slices published to `ln_in` (then a scratch tensor) through L2 and loaded back by all four CTAs.
 // `workspace`: ffn_cluster_workspace_bytes(M) bytes of device memory the partial slices cross L2 in (may be shared by ops
 // that run one at a time on a stream).
 size_t ffn_cluster_workspace_bytes(int M);
 int ffn_cluster_make(FfnClusterOp* op, const bf16* ln_in, int M, const bf16* w1, const float* b1, const bf16* w2,
                      const float* b2, float* x_inout, const float* ln_gamma, const float* ln_beta, bf16* ln_out, float ln_eps,
-                     float* workspace);
+                     float* workspace, const FfnProjArgs* proj = nullptr);
 int ffn_cluster_set_gn(FfnClusterOp* op, double* gn_sums, int groups, int rows_per_sample);
 void ffn_cluster_set_dbg(FfnClusterOp* op, unsigned long long* stamps32);   // clock64() phase stamps of CTA 0
 WRange ffn_cluster_weights(const FfnClusterOp& op);

@@ -524,7 +524,10 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             pl.flops.back() = fl;
             continue;
         }
-        {
+        // width 512: the projection + residual + pre-norm move into the cluster FFN kernel below (ffn_cluster.cu, PROJ)
+        const bool l1_fused = C == 512 && !prec && fuse && getenv("PD_NO_L1_FFN_FUSION") == nullptr;
+        const bool l1_proj = l1_fused && getenv("PD_NO_L1_PROJ_FUSION") == nullptr;
+        if (!l1_proj) {
             GemmEpilogue e;
             e.bias = aw.proj_b;
             e.residual = x;
@@ -554,7 +557,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             pl.flops.back() = fl;
             continue;
         }
-        if (C == 512 && !prec && fuse && getenv("PD_NO_L1_FFN_FUSION") == nullptr) {
+        if (l1_fused) {
             // width 512: FFN-1 + GELU + FFN-2 + residual (+ the next layer's LayerNorm, + the next resblock's GroupNorm
             // statistics) in one kernel, hidden dimension split over a 4-CTA cluster (ffn_cluster.cu)
             FfnClusterOp op;
@@ -563,14 +566,16 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
                 PD_CHECK(building_->ffn_ws.p == nullptr, PD_ERR_STATE, "unet: cluster-FFN workspace sized twice");
                 PD_TRY(building_->ffn_ws.alloc(ffn_cluster_workspace_bytes(P)));
             }
+            FfnProjArgs pa;
+            pa.att = att; pa.wp = aw.proj_w; pa.bp = aw.proj_b; pa.ln1_gamma = fw.ln_w; pa.ln1_beta = fw.ln_b;
             PD_TRY(ffn_cluster_make(&op, ln, P, fw.w1, fw.b1, fw.w2, fw.b2, x, next_ln ? s.a[i + 1].ln_w : nullptr,
                                     next_ln ? s.a[i + 1].ln_b : nullptr, next_ln ? ln : nullptr, 1e-5f,
-                                    building_->ffn_ws.as<float>()));
+                                    building_->ffn_ws.as<float>(), l1_proj ? &pa : nullptr));
             if (gn_next && i == last) PD_TRY(ffn_cluster_set_gn(&op, gn_next, 32, T * H * W));
-            const double fl = 2.0 * 2.0 * (double)P * C * 4 * C;
+            const double fl = 2.0 * 2.0 * (double)P * C * 4 * C + (l1_proj ? 2.0 * (double)P * C * C : 0.0);
             pl.gemm_flops += fl;
             pl.n_gemm += 1;
-            pl.add_ffn_cluster(op, "ffn_cluster");
+            pl.add_ffn_cluster(op, l1_proj ? "proj_ffn_cluster" : "ffn_cluster");
             pl.flops.back() = fl;
             continue;
         }

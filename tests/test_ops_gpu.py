@@ -181,6 +181,55 @@ def test_ffn_cluster(M, rows, with_ln, with_gn):
         assert torch.equal(x1, xo[:M1])
 
 
+@pytest.mark.parametrize("M,rows,with_ln,with_gn", [(3328, 832, True, False), (3328, 832, False, True), (832, 832, True, True),
+                                                    (1000, 1000, True, False)])
+def test_proj_ffn_cluster(M, rows, with_ln, with_gn):
+    """Width-512 attention projection + residual + pre-norm + FFN (+ next LayerNorm, + GroupNorm statistics) in the cluster
+    kernel (csrc/ffn_cluster.cu, PROJ variant): x1 = x + att Wp^T + bp; x = x1 + W2 gelu(W1 LN(x1) + b1) + b2."""
+    C, Hd = 512, 2048
+    att = _randn(M, C, seed=11).bfloat16()
+    wp = _randn(C, C, seed=12, scale=C ** -0.5).bfloat16()
+    bp = 0.1 * _randn(C, seed=13)
+    g1, be1 = 1 + 0.1 * _randn(C, seed=14), 0.1 * _randn(C, seed=15)
+    w1 = _randn(Hd, C, seed=2, scale=C ** -0.5).bfloat16()
+    w2 = _randn(C, Hd, seed=3, scale=Hd ** -0.5).bfloat16()
+    b1, b2 = 0.1 * _randn(Hd, seed=4), 0.1 * _randn(C, seed=5)
+    x = _randn(M, C, seed=6) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * _randn(C, seed=7), 0.1 * _randn(C, seed=8)
+    x1 = x + att.float() @ wp.float().t() + bp
+    ln1 = F.layer_norm(x1, (C,), g1, be1, 1e-5).bfloat16().float()
+    mid = F.gelu(ln1 @ w1.float().t() + b1).bfloat16().float()
+    ref_x = x1 + mid @ w2.float().t() + b2
+    ref_ln = F.layer_norm(ref_x, (C,), gamma, beta, 1e-5)
+
+    def run(Mr=M):
+        xo = x[:Mr].clone()
+        scratch = torch.zeros(Mr, C, device=DEV, dtype=torch.bfloat16)
+        ln = torch.zeros(Mr, C, device=DEV, dtype=torch.bfloat16)
+        sums = torch.zeros(max(Mr // rows, 1), 32, 2, device=DEV, dtype=torch.float64)
+        a = att[:Mr].contiguous()
+        _sync_check(L.lib().pd_op_proj_ffn_cluster(
+            L.ptr(a), L.ptr(wp), L.ptr(bp), L.ptr(g1), L.ptr(be1), L.ptr(scratch), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2),
+            L.ptr(xo), L.ptr(gamma) if with_ln else None, L.ptr(beta) if with_ln else None, L.ptr(ln) if with_ln else None,
+            L.ptr(sums) if with_gn else None, 32, rows, Mr, None, L.stream_ptr()))
+        return xo, ln, sums, scratch
+
+    xo, ln, sums, scratch = run()
+    assert rel_err(scratch, ln1) < 8e-3  # the pre-norm the kernel published (bf16)
+    assert rel_err(xo, ref_x) < 3e-3     # bf16 roundings of LN(x1) / `mid` can flip at ties between the implementations
+    if with_ln:
+        assert rel_err(ln, ref_ln) < 8e-3
+    if with_gn:
+        g = xo.double().reshape(M // rows, rows, 32, C // 32)
+        want = torch.stack([g.sum(dim=(1, 3)), (g * g).sum(dim=(1, 3))], dim=-1)
+        assert torch.allclose(sums, want, rtol=2e-6, atol=1e-3)
+    xo2, ln2, _, _ = run()               # deterministic: row sums and partials are combined in rank order
+    assert torch.equal(xo, xo2) and torch.equal(ln, ln2)
+    if M > rows:                         # batch invariance: the first sample alone gives the same rows
+        x1o, _, _, _ = run(rows)
+        assert torch.equal(x1o, xo[:rows])
+
+
 @pytest.mark.parametrize("M,with_ln", [(13312, True), (3328, False), (1000, True)])
 def test_proj_ffn_fused(M, with_ln):
     """Attention projection + residual + pre-norm + FFN (+ next LayerNorm) in one kernel."""

@@ -18,10 +18,18 @@ x = torch.randn(M, C, device=dev)
 g, b = torch.ones(C, device=dev), torch.zeros(C, device=dev)
 ln = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
 st = torch.zeros(32, device=dev, dtype=torch.int64)
+PROJ = int(os.environ.get("PROJ", 0))   # 1: the variant with the attention projection fused in front
+att = torch.randn(M, C, device=dev).bfloat16()
+wp = (torch.randn(C, C, device=dev) * C ** -0.5).bfloat16()
+bp = torch.randn(C, device=dev) * 0.1
 
 
 def call(stamps):
-    if stamps is None:
+    if PROJ:
+        L.check(L.lib().pd_op_proj_ffn_cluster(L.ptr(att), L.ptr(wp), L.ptr(bp), L.ptr(g), L.ptr(b), L.ptr(ln_in), L.ptr(w1),
+                                               L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(x), L.ptr(g), L.ptr(b), L.ptr(ln), None,
+                                               32, 832, M, L.ptr(stamps), L.stream_ptr()))
+    elif stamps is None:
         L.check(L.lib().pd_op_ffn_cluster(L.ptr(ln_in), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(x), L.ptr(g),
                                           L.ptr(b), L.ptr(ln), None, 32, 832, M, L.stream_ptr()))
     else:
@@ -38,6 +46,8 @@ names = {1: "dependency wait passed", 2: "G1(0) complete", 3: "E1(0) done", 4: "
          6: "partial complete", 8: "slices sent", 9: "cluster barrier", 10: "rows reduced",
          11: "LN barrier", 12: "done", 16: "MMA: first operands landed", 17: "MMA: G1(0) issued", 18: "MMA: G1(1) issued",
          19: "MMA: waits for E1(1)", 20: "MMA: E1(1) there", 21: "MMA: G2 issued"}
+if PROJ:
+    names.update({22: "MMA: first G0 operands landed", 23: "MMA: G0 issued", 24: "x1 complete", 25: "E0 done (LN(x1) published)", 26: "E0: x1 rows combined", 27: "E0: row sums exchanged", 28: "E0: LN(x1) store complete"})
 for i in sorted(names, key=lambda i: s[i]):
     print(f"{s[i] - t0:7d}  {names[i]}")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
