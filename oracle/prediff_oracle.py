@@ -379,11 +379,21 @@ def p_sample_ddpm(sched, eps, z, t, noise, guide=None):
     return mean + nonzero * (0.5 * logvar).exp() * noise
 
 
-def sample_loop_ddpm(sd, cfg, sched, z, cond, noise, n_steps):
+def cond_schedule_ids(num_timesteps_cond, timesteps=1000):
+    """make_cond_schedule (latent_diffusion.py:295-299)."""
+    ids = torch.full((timesteps,), timesteps - 1, dtype=torch.long)
+    ids[:num_timesteps_cond] = torch.round(torch.linspace(0, timesteps - 1, num_timesteps_cond)).long()
+    return ids
+
+
+def sample_loop_ddpm(sd, cfg, sched, z, cond, noise, n_steps, cond_ids=None, cond_noise=None):
     """p_sample_loop (latent_diffusion.py:633-684) with `timesteps=n_steps`, x_T = z, and the per-step
-    torch.randn replaced by the pre-generated noise[k] (k-th executed step)."""
+    torch.randn replaced by the pre-generated noise[k] (k-th executed step). cond_ids / cond_noise: the
+    shorten_cond_schedule branch (:665-667) - the context is re-noised, cumulatively, before every step."""
     for k, i in enumerate(reversed(range(n_steps))):
         t = torch.full((z.shape[0],), i, dtype=torch.long)
+        if cond_ids is not None:
+            cond = q_sample(sched, cond, cond_ids[t], cond_noise[k])
         eps = unet_forward(sd, cfg, z, t, cond)
         z = p_sample_ddpm(sched, eps, z, i, noise[k])
     return z

@@ -53,8 +53,6 @@ class LatentDiffusion(nn.Module):
             raise NotImplementedError("prediff_b200.LatentDiffusion: only the 'linear' beta schedule with v_posterior=0")
         if layout != "NTHWC":
             raise NotImplementedError("prediff_b200.LatentDiffusion: layout must be 'NTHWC'")
-        if num_timesteps_cond not in (None, 1):
-            raise NotImplementedError("prediff_b200.LatentDiffusion: shorten_cond_schedule is not built")
         if scale_by_std:   # the reference registers a 'scale_factor' buffer (a state_dict key) and rescales on the first batch
             raise NotImplementedError("prediff_b200.LatentDiffusion: scale_by_std=True is not built")
         if cond_stage_forward not in (None, "encode"):
@@ -76,7 +74,10 @@ class LatentDiffusion(nn.Module):
             self.model_ema = LitEma(self.torch_nn_module, include_frozen=hasattr(self.torch_nn_module, "_dirty"))
         self.scale_factor = scale_factor
         self.alignment_fn = None
-        self.shorten_cond_schedule = False
+        # latent_diffusion.py:153-157: with num_timesteps_cond > 1 the sampling loop re-noises the context every step
+        self.num_timesteps_cond = 1 if num_timesteps_cond is None else int(num_timesteps_cond)
+        assert self.num_timesteps_cond <= timesteps
+        self.shorten_cond_schedule = self.num_timesteps_cond > 1
         self.cond_stage_trainable = False   # forced off for '__is_first_stage__' in the reference too (:338-341)
         # loss hyper-parameters of p_losses (latent_diffusion.py:134-150); only the forward (validation) loss is built
         if loss_type not in ("l1", "l2"):
@@ -89,6 +90,8 @@ class LatentDiffusion(nn.Module):
         self.register_schedule(timesteps=timesteps, linear_start=linear_start, linear_end=linear_end)
         if self.clip_denoised:   # latent_diffusion.py:580-581, applied inside the fused update kernel
             L.check(L.lib().pd_sampler_set_clip_denoised(self._sampler, 1))
+        if self.shorten_cond_schedule:
+            self.make_cond_schedule()
         logvar = torch.full(fill_value=logvar_init, size=(self.num_timesteps,))
         if self.learn_logvar:   # latent_diffusion.py:146-150: a parameter when learned, a buffer otherwise (same key)
             self.logvar = nn.Parameter(logvar, requires_grad=True)
@@ -105,6 +108,13 @@ class LatentDiffusion(nn.Module):
             self._cond_is_first_stage = False
         else:
             raise NotImplementedError("prediff_b200.LatentDiffusion: cond_stage_model must be '__is_first_stage__' or None")
+
+    def make_cond_schedule(self):
+        """latent_diffusion.py:295-299 (buffer `cond_ids`, a state_dict key of the reference)."""
+        cond_ids = torch.full(size=(self.num_timesteps,), fill_value=self.num_timesteps - 1, dtype=torch.long)
+        ids = torch.round(torch.linspace(0, self.num_timesteps - 1, self.num_timesteps_cond)).long()
+        cond_ids[:self.num_timesteps_cond] = ids
+        self.register_buffer("cond_ids", cond_ids)
 
     # ---- schedule -------------------------------------------------------------------------------------------
     def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
@@ -344,6 +354,10 @@ class LatentDiffusion(nn.Module):
         z = z.reshape(N, T, *z.shape[1:]).permute(0, 1, 3, 4, 2).contiguous()
         if t is None:
             t = torch.randint(0, self.num_timesteps, (B,), device=z.device).long()
+        if self.shorten_cond_schedule and self.cond_stage_model is not None:
+            # latent_diffusion.py:469-471 calls torch.randn_like(c.float()) on the context DICT: the reference raises here
+            raise NotImplementedError("prediff_b200.LatentDiffusion.forward: shorten_cond_schedule (the reference's own "
+                                      "forward fails with a dict context; only the sampling loop uses the option)")
         zc = self.cond_stage_forward(c) if self.cond_stage_model is not None else (c if torch.is_tensor(c) else c.get("y"))
         return self.p_losses(z, zc, t, noise=noise)
 
@@ -455,8 +469,12 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample_loop(self, cond, shape, y=None, use_alignment=False, alignment_kwargs=None,
                       return_intermediates=False, x_T=None, verbose=False, callback=None, timesteps=None, mask=None,
-                      x0=None, img_callback=None, start_T=None, log_every_t=None, noise=None):
+                      x0=None, img_callback=None, start_T=None, log_every_t=None, noise=None, cond_noise=None):
         """DDPM ancestral loop, t = timesteps-1 .. 0 (latent_diffusion.py:633-684).
+
+        With `shorten_cond_schedule` (num_timesteps_cond > 1) the context is re-noised before every step,
+        cond <- q_sample(cond, cond_ids[t]) - cumulatively, as the reference does (:665-667); the draws are
+        torch.randn_like(cond) in the reference's order, or `cond_noise` [steps, *cond.shape] (parity tests).
 
         With the CUDA UNet and no alignment / inpainting the stretches between logging points run as one
         device-resident loop; the per-step noise is pre-drawn with the same torch.randn calls, in the same order,
@@ -474,11 +492,16 @@ class LatentDiffusion(nn.Module):
             assert x0 is not None and x0.shape[2:3] == mask.shape[2:3]
         cond = cond.contiguous().float()
         align = self._native_alignment(use_alignment, alignment_kwargs) if self._native() else None
-        host_driven = (use_alignment and align is None) or mask is not None or not self._native()
+        host_driven = (use_alignment and align is None) or mask is not None or not self._native() or \
+            self.shorten_cond_schedule
         target = self._target_vector(alignment_kwargs, B, device) if align is not None else None
         if host_driven:
             for k, i in enumerate(reversed(range(timesteps))):
                 ts = torch.full((B,), i, device=device, dtype=torch.long)
+                if self.shorten_cond_schedule:
+                    tc = self.cond_ids.to(device)[ts]
+                    cond = self.q_sample(x_start=cond, t=tc,
+                                         noise=torch.randn_like(cond) if cond_noise is None else cond_noise[k])
                 img = self.p_sample(zt=img, zc=cond, t=ts, y=y, use_alignment=use_alignment,
                                     alignment_kwargs=alignment_kwargs, clip_denoised=self.clip_denoised,
                                     noise=None if noise is None else noise[k], _t_int=i)

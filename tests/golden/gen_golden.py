@@ -511,6 +511,45 @@ def gen_loop_tiny():
 
 
 @torch.no_grad()
+def gen_loop_shorten():
+    """Reference p_sample_loop with num_timesteps_cond = 4 (shorten_cond_schedule, latent_diffusion.py:153-157, 295-299,
+    665-667): the context latents are re-noised before every step. Tiny config; both RNG streams injected (noise_like for
+    the ancestral noise, torch.randn_like for the context noise)."""
+    import prediff.diffusion.latent_diffusion as LD
+    ucfg, vcfg = Wt.TINY_UNET, Wt.TINY_VAE
+    ldm = ref_ldm(ref_unet(ucfg), ref_vae(vcfg), ucfg, vcfg, num_timesteps_cond=4)
+    assert ldm.shorten_cond_schedule
+    B, n_steps = 2, 4
+    zT = inp(777, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    cond = inp(778, B, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    noise = inp(779, n_steps, B, ucfg.t_out, ucfg.h, ucfg.w, ucfg.c)
+    cnoise = inp(781, n_steps, B, ucfg.t_in, ucfg.h, ucfg.w, ucfg.c)
+    calls = {"k": 0, "c": 0}
+
+    def fake_noise_like(shape, device):
+        k = calls["k"]
+        calls["k"] += 1
+        return noise[k].clone()
+
+    def fake_randn_like(x, **kw):
+        c = calls["c"]
+        calls["c"] += 1
+        assert tuple(x.shape) == tuple(cnoise[c].shape)
+        return cnoise[c].clone()
+
+    orig, orig_rl = LD.noise_like, torch.randn_like
+    LD.noise_like = fake_noise_like
+    torch.randn_like = fake_randn_like
+    try:
+        z0 = ldm.p_sample_loop(cond=cond, shape=tuple(zT.shape), x_T=zT.clone(), timesteps=n_steps)
+    finally:
+        LD.noise_like = orig
+        torch.randn_like = orig_rl
+    assert calls["k"] == n_steps and calls["c"] == n_steps
+    save("loop_shorten", z0=z0, cond_ids=ldm.cond_ids)
+
+
+@torch.no_grad()
 def gen_loop_extra():
     """Round-2 pins: (1) clip_denoised=True through the reference's p_sample / p_sample_loop (latent_diffusion.py:580-581),
     tiny config, RNG injected; (2) the reference's own sample() at the SHIPPED sizes: 7 context frames 128x128 -> encode
@@ -643,5 +682,7 @@ if __name__ == "__main__":
         gen_helpers()
     if "loop_extra" in todo:
         gen_loop_extra()
+    if "loop_shorten" in todo:
+        gen_loop_shorten()
     if "ddim_full" in todo:
         gen_ddim("full", FULL_U, 4, 50)

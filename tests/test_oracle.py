@@ -94,6 +94,24 @@ def test_ddpm_loop_and_step_tiny_vs_reference(tiny_unet_sd):
     assert maxrel(zs, g["z_step900"]) < 2e-5
 
 
+def test_ddpm_loop_shorten_cond_schedule_vs_reference(tiny_unet_sd):
+    """num_timesteps_cond = 4: the reference re-noises the context before every step (latent_diffusion.py:295-299,
+    665-667); golden from the unmodified p_sample_loop with both RNG streams injected."""
+    cfg = Wt.TINY_UNET
+    g = gold("loop_shorten")
+    sched = O.make_schedule()
+    B, n_steps = 2, 4
+    zT = inp(777, B, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(778, B, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    noise = inp(779, n_steps, B, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cnoise = inp(781, n_steps, B, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    ids = O.cond_schedule_ids(4)
+    assert torch.equal(ids, torch.as_tensor(g["cond_ids"]))
+    with torch.no_grad():
+        z0 = O.sample_loop_ddpm(tiny_unet_sd, cfg, sched, zT.clone(), cond, noise, n_steps, cond_ids=ids, cond_noise=cnoise)
+    assert maxrel(z0, g["z0"]) < 5e-5
+
+
 def test_sample_end_to_end_tiny_vs_reference(tiny_unet_sd):
     """LatentDiffusion.sample(): encode context (mode) -> DDPM loop -> decode (latent_diffusion.py:686-724)."""
     cfg = Wt.TINY_UNET

@@ -32,6 +32,25 @@ def _tiny_inputs(scale=1.0):
     return zT, cond, noise
 
 
+def test_shorten_cond_schedule_loop_vs_reference():
+    """num_timesteps_cond = 4 (latent_diffusion.py:153-157, 295-299, 665-667): the context latents are re-noised before
+    every ancestral step; golden of the unmodified p_sample_loop with both RNG streams injected."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "loop_shorten.npz"))
+    unet, _ = make_unet(CFG)
+    ldm = LatentDiffusion(torch_nn_module=unet, num_timesteps_cond=4)
+    assert ldm.shorten_cond_schedule and np.array_equal(ldm.cond_ids.numpy(), g["cond_ids"])
+    assert "cond_ids" in ldm.state_dict()
+    zT, cond, noise = _tiny_inputs()
+    cnoise = inp(781, 4, 2, CFG.t_in, CFG.h, CFG.w, CFG.c).cuda()
+    z0 = ldm.p_sample_loop(cond=cond, shape=tuple(zT.shape), x_T=zT, timesteps=4, noise=noise, cond_noise=cnoise)
+    r, m = errs(z0, g["z0"])
+    plain = LatentDiffusion(torch_nn_module=unet).p_sample_loop(cond=cond, shape=tuple(zT.shape), x_T=zT, timesteps=4,
+                                                                noise=noise)
+    r_plain, _ = errs(plain, g["z0"])
+    print(f"shorten_cond_schedule 4-step loop: rel_rms={r:.3e} max={m:.3e} (fixed context: {r_plain:.3e})")
+    assert r < LOOP_RMS_TOL and m < LOOP_MAX_TOL and r_plain > 5 * r
+
+
 def test_clip_denoised_step_and_loop_vs_reference():
     """latent_diffusion.py:580-581: z_recon.clamp_(-1, 1) inside p_mean_variance, here inside the fused update kernel."""
     unet, _ = make_unet(CFG)
