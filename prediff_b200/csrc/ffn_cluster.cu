@@ -644,11 +644,14 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const float var = fmaxf(tot2 * (1.0f / kC) - mean * mean, 0.f);
             const float rstd = rsqrtf(var + p.ln_eps);
             uint8_t* brow = slabB + lane * 128;
+            float4 av[16];   // loads before the stores (generic addresses)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                av[i] = *reinterpret_cast<const float4*>(slabF + (i >> 3) * 4096 + lane * 128 + ((static_cast<uint32_t>(i & 7) ^ sw) << 4));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {   // 8 values (two cells of the fp32 slabs) -> one 16-byte cell of the bf16 slab
-                const uint8_t* frow = slabF + (i >> 2) * 4096 + lane * 128;
-                const float4 a0 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * (i & 3)) ^ sw) << 4));
-                const float4 a1 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * (i & 3) + 1) ^ sw) << 4));
+                const float4 a0 = av[2 * i];
+                const float4 a1 = av[2 * i + 1];
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i));
                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i + 4));
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i));

@@ -475,16 +475,25 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (!PROJ) ptx::mbar_wait(&my_bar[idx], 0);
             ptx::tmem_ld_wait();
             uint8_t* my_row = slab + lane * 128;
+            // the residual cells first: through generic addresses a store between two loads serialises them
+            float4 resv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                resv[i] = PROJ ? make_float4(0.f, 0.f, 0.f, 0.f)
+                               : *reinterpret_cast<const float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
+            float gs[8], gq[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + c * 32 + 4 * i));
                 float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
-                const float4 r = PROJ ? make_float4(0.f, 0.f, 0.f, 0.f) : *cell;
+                const float4 r = resv[i];
                 float4 a = make_float4(__uint_as_float(v[4 * i]) + bb.x + r.x, __uint_as_float(v[4 * i + 1]) + bb.y + r.y,
                                        __uint_as_float(v[4 * i + 2]) + bb.z + r.z, __uint_as_float(v[4 * i + 3]) + bb.w + r.w);
                 *cell = a;
-                ln_s1 += (a.x + a.y) + (a.z + a.w);
-                ln_s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+                gs[i] = (a.x + a.y) + (a.z + a.w);
+                gq[i] = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+                ln_s1 += gs[i];
+                ln_s2 += gq[i];
             }
             ptx::fence_proxy_async();
             __syncwarp();
@@ -493,7 +502,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::bulk_commit();
             }
             if constexpr (GN) if (row0 < p.M) {
-                gn_chunk_from_slab(my_row, sw, row0 + lane < p.M, p.gn_sums, p.gn_cpg, p.gn_groups, gsample, c * 32, lane);
+                const int shift = p.gn_cpg == 8 ? 3 : (p.gn_cpg == 16 ? 4 : 5);
+                gn_chunk_accumulate(gs, gq, row0 + lane < p.M, p.gn_cpg,
+                                    p.gn_sums + ((size_t)gsample * p.gn_groups + ((c * 32) >> shift)) * 2, lane);
             }
         }
         if (p.ln_gamma) {
@@ -503,14 +514,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < kCh / 2; ++j) {
                 uint8_t* brow = bslabs + j * 4096 + lane * 128;
+                float4 av[2][8];   // loads before the stores (generic addresses)
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const uint8_t* frow = slabs + (2 * j + cc) * 4096 + lane * 128;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        av[cc][i] = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(i) ^ sw) << 4));
+                }
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
                     const int colbase = (c_begin + 2 * j + cc) * 32;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k) ^ sw) << 4));
-                        const float4 a1 = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(2 * k + 1) ^ sw) << 4));
+                        const float4 a0 = av[cc][2 * k];
+                        const float4 a1 = av[cc][2 * k + 1];
                         const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + colbase + 8 * k));
                         const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + colbase + 8 * k + 4));
                         const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + colbase + 8 * k));

@@ -263,6 +263,13 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (has_res) ptx::mbar_wait(&my_bar[idx], 0);
                 ptx::tmem_ld_wait();
                 uint8_t* my_row = slab + lane * 128;
+                // the residual cells first: through generic addresses a store between two loads serialises them
+                float4 resv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    resv[i] = has_res ? *reinterpret_cast<const float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                float gs[8], gq[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float4 b = *reinterpret_cast<const float4*>(vec_s + c * 32 + 4 * i);
@@ -272,12 +279,14 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                            (__uint_as_float(v[4 * i + 3]) + part[i].w) + b.w);
                     float4* cell = reinterpret_cast<float4*>(my_row + ((static_cast<uint32_t>(i) ^ sw) << 4));
                     if (has_res) {
-                        const float4 r = *cell;
+                        const float4 r = resv[i];
                         a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
                     }
                     *cell = a;
-                    ln_s1 += (a.x + a.y) + (a.z + a.w);
-                    ln_s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+                    gs[i] = (a.x + a.y) + (a.z + a.w);
+                    gq[i] = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+                    ln_s1 += gs[i];
+                    ln_s2 += gq[i];
                 }
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -286,8 +295,9 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::bulk_commit();
                 }
                 if constexpr (GN) if (row0 < p.rows_per_sample) {   // statistics for the GroupNorm that reads this output
-                    gn_chunk_from_slab(my_row, sw, row0 + lane < p.rows_per_sample, p.gn_sums, p.gn_cpg, p.gn_groups,
-                                       gsample, n0 + c * 32, lane);
+                    const int shift = p.gn_cpg == 8 ? 3 : (p.gn_cpg == 16 ? 4 : 5);
+                    gn_chunk_accumulate(gs, gq, row0 + lane < p.rows_per_sample, p.gn_cpg,
+                                        p.gn_sums + ((size_t)gsample * p.gn_groups + ((n0 + c * 32) >> shift)) * 2, lane);
                 }
             }
             if (p.ln_gamma) {   // fused LayerNorm of the finished rows (N == 256: this CTA owns whole rows)
