@@ -223,63 +223,6 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-            // The tile's other parts were dumped by CTAs that ran them as their FIRST segment, i.e. about when this CTA
-            // started the mainloop of this segment: their sum (fixed order: increasing k range) is formed NOW, underneath that
-            // mainloop, and parked in the CTA's other TMEM accumulator (free: a CTA has at most two segments and the dump of
-            // the first has been read out by these same warps) - the L2 round trips (n_part per chunk, ~800 cycles each: 13.6 k
-            // cycles of epilogue at level 1) leave the critical path, the arithmetic below is unchanged.
-            const uint32_t t_park = tmem_base + (1 - sg) * BN + (static_cast<uint32_t>(q * 32) << 16);
-            if (sgm.n_part > 0) {
-                if (et == 0)
-                    while (ptx::ld_acquire_gpu(flags + sgm.flag) < sgm.n_part) {}
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-#pragma unroll 1
-                for (int idx = 0; idx < 4; ++idx) {
-                    const int c = c_begin + idx;
-                    // up to three parts of the chunk in flight together (registers are free here), summed in part order
-                    constexpr size_t kPartStride = (size_t)kGemmBlockM * BN / 4;   // float4 per partial tile
-                    const float4* src = reinterpret_cast<const float4*>(partials + (size_t)sgm.slot * (kGemmBlockM * BN)) +
-                                        (size_t)(c * 8) * kGemmBlockM + row;
-                    float4 t0[8], t1[8], t2[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) t0[i] = __ldcg(src + (size_t)i * kGemmBlockM);
-                    if (sgm.n_part >= 2) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) t1[i] = __ldcg(src + kPartStride + (size_t)i * kGemmBlockM);
-                    }
-                    if (sgm.n_part >= 3) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) t2[i] = __ldcg(src + 2 * kPartStride + (size_t)i * kGemmBlockM);
-                    }
-                    float4 part[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)   // 0 + t0 as the one-at-a-time loop formed it
-                        part[i] = make_float4(0.f + t0[i].x, 0.f + t0[i].y, 0.f + t0[i].z, 0.f + t0[i].w);
-                    if (sgm.n_part >= 2) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { part[i].x += t1[i].x; part[i].y += t1[i].y; part[i].z += t1[i].z; part[i].w += t1[i].w; }
-                    }
-                    if (sgm.n_part >= 3) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { part[i].x += t2[i].x; part[i].y += t2[i].y; part[i].z += t2[i].z; part[i].w += t2[i].w; }
-                    }
-                    for (int pp = 3; pp < sgm.n_part; ++pp) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = __ldcg(src + pp * kPartStride + (size_t)i * kGemmBlockM);
-                            part[i].x += t.x; part[i].y += t.y; part[i].z += t.z; part[i].w += t.w;
-                        }
-                    }
-                    uint32_t pv[32];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        pv[4 * i] = __float_as_uint(part[i].x); pv[4 * i + 1] = __float_as_uint(part[i].y);
-                        pv[4 * i + 2] = __float_as_uint(part[i].z); pv[4 * i + 3] = __float_as_uint(part[i].w);
-                    }
-                    ptx::tmem_st_32x32(t_park + c * 32, pv);
-                }
-                ptx::tmem_st_wait();
-            }
             ptx::mbar_wait(&tmem_full[sg], 0);   // last segment: every mainloop of this CTA is finished, the ring is idle
             ptx::tc_fence_after();
             if (et == 0) SK_STAMP(sg ? 7 : 4);
@@ -292,6 +235,11 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::tma_load_3d(slabs + idx * 4096, &tmap_res, &my_bar[idx], n0 + (c_begin + idx) * 32, row0, sample);
                 }
             }
+            if (sgm.n_part > 0) {   // the other parts of this tile were dumped long ago (they are first segments)
+                if (et == 0)
+                    while (ptx::ld_acquire_gpu(flags + sgm.flag) < sgm.n_part) {}
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            }
             if (et == 0) SK_STAMP(8);
             float ln_s1 = 0.f, ln_s2 = 0.f;
             const int gsample = GN ? (sample * p.rows_per_sample + row0) / p.gn_rows : 0;   // GroupNorm sample of my rows
@@ -299,17 +247,21 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int idx = 0; idx < 4; ++idx) {
                 const int c = c_begin + idx;
                 uint8_t* slab = slabs + idx * 4096;
-                uint32_t v[32], pv[32];
+                uint32_t v[32];
                 ptx::tmem_ld_32x32(t_lane + c * 32, v);
-                if (sgm.n_part > 0) ptx::tmem_ld_32x32(t_park + c * 32, pv);   // the parked sum of the other parts
-                if (has_res) ptx::mbar_wait(&my_bar[idx], 0);
-                ptx::tmem_ld_wait();
                 float4 part[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    part[i] = sgm.n_part > 0 ? make_float4(__uint_as_float(pv[4 * i]), __uint_as_float(pv[4 * i + 1]),
-                                                           __uint_as_float(pv[4 * i + 2]), __uint_as_float(pv[4 * i + 3]))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i) part[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int pp = 0; pp < sgm.n_part; ++pp) {   // fixed order: increasing k range
+                    const float4* src = reinterpret_cast<const float4*>(partials + (size_t)(sgm.slot + pp) * (kGemmBlockM * BN));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 t = __ldcg(src + (size_t)(c * 8 + i) * kGemmBlockM + row);
+                        part[i].x += t.x; part[i].y += t.y; part[i].z += t.z; part[i].w += t.w;
+                    }
+                }
+                if (has_res) ptx::mbar_wait(&my_bar[idx], 0);
+                ptx::tmem_ld_wait();
                 uint8_t* my_row = slab + lane * 128;
                 // the residual cells first: through generic addresses a store between two loads serialises them
                 float4 resv[8];
