@@ -289,13 +289,19 @@ int pd_op_patch_merge_ln(const float* x, const float* gamma, const float* beta, 
 int pd_op_axial_attention(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W,
                           int C, int heads, int axis, void* stream);
 /* General cuboid self-attention: any cuboid_size / strategy (0 = 'l', 1 = 'd') / shift_size of
- * CuboidSelfAttentionLayer (cuboid_transformer.py:595-966, no global vectors), padding_type 0 = 'zeros', 1 = 'ignore'.
+ * CuboidSelfAttentionLayer (cuboid_transformer.py:595-966, no global vectors), padding_type 0 = 'zeros', 1 = 'ignore',
+ * 2 = 'nearest' (models/utils.py:228-270: the padded grid is a nearest-neighbour resampling of the tokens).
  * pd_cuboid_tables is host-only (no GPU): fills meta = {effective size[3], effective shift[3], pad[3], num_cuboids,
  * volume, rel_off} and, when non-null, tok / lab [num_cuboids*volume] and rel [volume] (see csrc/ops.cuh); returns
  * 1 + axis when the layer is the axial fast path, 0 when it takes the general kernel, < 0 on error.
  * pd_op_cuboid_attention: qkv bf16 [B][T][H][W][3C] -> out bf16 [B][T][H][W][C], bias_table fp32 [n_rel][heads]. */
 int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                      int padding_type, int32_t meta[12], int32_t* tok, int32_t* lab, int32_t* rel, int64_t capacity);
+/* padding_type 2 ('nearest') only: dst [num_cuboids*volume] = the token each slot's result is written to (-1 = nobody) -
+ * `tok` of pd_cuboid_tables is then the token the slot's q|k|v rows copy. Returns 1 if the layer has such a table (padding
+ * on some axis), 0 if results go to `tok` as for the other padding types (dst untouched), < 0 on error. */
+int pd_cuboid_tables_dst(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                         int padding_type, int32_t* dst, int64_t capacity);
 int pd_op_cuboid_attention(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W, int C,
                            int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                            int padding_type, void* stream);

@@ -176,7 +176,10 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
         view = [1, 1, 1, 1, 1]
         view[1 + a] = padded[a]
         region = region * 3 + lab.view(view)
-    y = F.pad(qkv, (0, 0, 0, pad[2], 0, pad[1], 0, pad[0]))
+    if padding_type == "nearest" and any(pad):   # _generalize_padding (models/utils.py:228-258): resample to the padded size
+        y = F.interpolate(qkv.permute(0, 4, 1, 2, 3), size=tuple(padded)).permute(0, 2, 3, 4, 1)
+    else:
+        y = F.pad(qkv, (0, 0, 0, pad[2], 0, pad[1], 0, pad[0]))
     real = F.pad(real, (0, 0, 0, pad[2], 0, pad[1], 0, pad[0]))
     if any(s > 0 for s in shift):
         y = torch.roll(y, shifts=[-s for s in shift], dims=(1, 2, 3))
@@ -202,12 +205,15 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
     o = _from_cuboids(o, size, strategy, padded)
     if any(s_ > 0 for s_ in shift):
         o = torch.roll(o, shifts=list(shift), dims=(1, 2, 3))
+    if padding_type == "nearest" and any(pad):   # _generalize_unpadding (:261-270): resample back
+        return F.interpolate(o.permute(0, 4, 1, 2, 3), size=(T, H, W)).permute(0, 2, 3, 4, 1).contiguous()
     return o[:, :T, :H, :W].contiguous()
 
 
 def cuboid_attention(sd, p, x, heads, size0, strategy, shift0, padding_type="zeros"):
     """CuboidSelfAttentionLayer.forward (cuboid_transformer.py:812-966) for any cuboid size / strategy / shift with
-    'zeros' or 'ignore' padding: LN -> qkv (no bias) -> cuboid_attention_core -> proj. x: (B, T, H, W, C)."""
+    'zeros', 'ignore' or 'nearest' padding: LN -> qkv (no bias) -> cuboid_attention_core -> proj. x: (B, T, H, W, C).
+    ('nearest' resamples AFTER the LayerNorm; qkv is per token without bias, so resampling its output is the same thing.)"""
     C = x.shape[-1]
     y = F.layer_norm(x, (C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
     o = cuboid_attention_core(F.linear(y, sd[f"{p}.qkv.weight"]), sd[f"{p}.relative_position_bias_table"], heads,

@@ -218,6 +218,22 @@ int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t s
     return g.axial_axis >= 0 ? 1 + g.axial_axis : 0;
 }
 
+int pd_cuboid_tables_dst(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                         int padding_type, int32_t* dst, int64_t capacity) {
+    CuboidLayerSpec sp;
+    for (int a = 0; a < 3; ++a) {
+        sp.size[a] = size[a];
+        sp.strategy[a] = strategy[a];
+        sp.shift[a] = shift[a];
+    }
+    CuboidTables g;
+    PD_TRY(build_cuboid_tables(T, H, W, sp, padding_type, &g));
+    PD_CHECK(dst && (int64_t)g.dst.size() <= capacity, PD_ERR_ARG, "pd_cuboid_tables_dst: capacity %lld < %zu",
+             (long long)capacity, g.dst.size());
+    if (!g.dst.empty()) memcpy(dst, g.dst.data(), g.dst.size() * sizeof(int));
+    return (int)(g.dst.empty() ? 0 : 1);
+}
+
 int pd_op_cuboid_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
                            const int32_t size[3], const int32_t strategy[3], const int32_t shift[3], int padding_type,
                            void* stream) {

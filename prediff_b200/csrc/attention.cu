@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                                                                const float* __restrict__ bias_table,
                                                                bf16* __restrict__ out, const int* __restrict__ tok,
                                                                const int* __restrict__ lab, const int* __restrict__ rel,
-                                                               int N, int C, int heads, int vol, int rel_off,
-                                                               int n_rel_smem, int kv_stages) {
+                                                               const int* __restrict__ dstp, int N, int C, int heads, int vol,
+                                                               int rel_off, int n_rel_smem, int kv_stages) {
     grid_dep_launch();
     grid_dep_wait();
     constexpr int LD = HD + 8;        // row pitch: +16 B keeps ldmatrix bank-conflict free
@@ -476,7 +476,9 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
     // ---- normalise and scatter the rows of real tokens (padding slots are dropped = the reference's unpadding) ----
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
-        const int t = s_qtok[r_lo + 8 * rh];
+        const int r = r_lo + 8 * rh;
+        // 'nearest' padding: the slot's destination differs from the token its rows were copied from
+        const int t = dstp ? (q0 + r < vol ? dstp[(size_t)c * vol + q0 + r] : -1) : s_qtok[r];
         if (t < 0) continue;
         const float inv = l_run[rh] > 0.f ? 1.f / l_run[rh] : 0.f;
         bf16* dst = out + ((size_t)b * N + t) * C + h * HD + 2 * tq;
@@ -607,8 +609,8 @@ int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int
 // Host-side geometry of one CuboidSelfAttentionLayer (same tables as prediff_b200/patterns.py::layer_geometry; both are
 // tested against the unmodified reference's cuboid_reorder / compute_cuboid_self_attention_mask).
 int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int padding_type, CuboidTables* g) {
-    PD_CHECK(padding_type == 0 || padding_type == 1, PD_ERR_ARG,
-             "cuboid attention: padding_type %d (0 = zeros, 1 = ignore; 'nearest' is not built)", padding_type);
+    PD_CHECK(padding_type >= 0 && padding_type <= 2, PD_ERR_ARG,
+             "cuboid attention: padding_type %d (0 = zeros, 1 = ignore, 2 = nearest)", padding_type);
     const int dims[3] = {T, H, W};
     int n[3], padded[3];
     for (int a = 0; a < 3; ++a) {
@@ -631,6 +633,29 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
     g->volume = vol;
     g->tok.assign((size_t)nc * vol, -1);
     g->lab.assign((size_t)nc * vol, -1);
+    g->dst.clear();
+    // 'nearest' (models/utils.py:228-270): the padded grid is F.interpolate(x, size = padded) - position o copies token
+    // floor(o * dims / padded) - and the result is F.interpolate(y, size = dims): token t takes position
+    // floor(t * padded / dims). Both with torch's float32 index arithmetic (scale = in / out, src = min(floorf(dst * scale),
+    // in - 1)). Without padding on an axis both maps are the identity.
+    const bool nearest = padding_type == 2 && (g->pad[0] > 0 || g->pad[1] > 0 || g->pad[2] > 0);
+    std::vector<int> near_src[3], near_dst[3];   // per axis: padded position -> source token / destination token (-1: none)
+    if (nearest) {
+        g->dst.assign((size_t)nc * vol, -1);
+        for (int a = 0; a < 3; ++a) {
+            near_src[a].resize(padded[a]);
+            near_dst[a].assign(padded[a], -1);
+            const float up = (float)dims[a] / (float)padded[a], down = (float)padded[a] / (float)dims[a];
+            for (int o = 0; o < padded[a]; ++o) {
+                const int sidx = (int)floorf((float)o * up);
+                near_src[a][o] = sidx < dims[a] - 1 ? sidx : dims[a] - 1;
+            }
+            for (int t = 0; t < dims[a]; ++t) {
+                const int o = (int)floorf((float)t * down);
+                near_dst[a][o < padded[a] - 1 ? o : padded[a] - 1] = t;
+            }
+        }
+    }
     const bool any_shift = g->shift[0] > 0 || g->shift[1] > 0 || g->shift[2] > 0;
     for (int c = 0; c < nc; ++c) {
         const int cub[3] = {c / (n[1] * n[2]), (c / n[2]) % n[1], c % n[2]};
@@ -648,6 +673,14 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
                 valid = valid && src[a] < dims[a];
             }
             const size_t k = (size_t)c * vol + i;
+            if (nearest) {   // src[] is the position in the padded (un-rolled) grid
+                const int st[3] = {near_src[0][src[0]], near_src[1][src[1]], near_src[2][src[2]]};
+                const int dt[3] = {near_dst[0][src[0]], near_dst[1][src[1]], near_dst[2][src[2]]};
+                g->tok[k] = (st[0] * H + st[1]) * W + st[2];
+                g->dst[k] = (dt[0] >= 0 && dt[1] >= 0 && dt[2] >= 0) ? (dt[0] * H + dt[1]) * W + dt[2] : -1;
+                g->lab[k] = label;
+                continue;
+            }
             g->tok[k] = valid ? (src[0] * H + src[1]) * W + src[2] : -1;
             g->lab[k] = (!valid && padding_type == 1) ? -1 : label;
         }
@@ -702,8 +735,8 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
                                          (int)smem));                                                               \
             attr_bytes = smem;                                                                                      \
         }                                                                                                           \
-        PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, N, C,    \
-                  heads, g.volume, g.rel_off, n_rel_smem, kv_stages);                                               \
+        PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, g.dst, N, \
+                  C, heads, g.volume, g.rel_off, n_rel_smem, kv_stages);                                            \
     } while (0)
     switch (hd) {
         case 16: PD_LAUNCH_CUB(16); break;
@@ -718,10 +751,10 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
 }
 
 int CuboidTablesDev::upload(const CuboidTables& t) {
-    const size_t nt = t.tok.size(), nr = t.rel.size();
-    if (cudaMalloc(&mem, (2 * nt + nr) * sizeof(int)) != cudaSuccess) {
+    const size_t nt = t.tok.size(), nr = t.rel.size(), nd = t.dst.size();
+    if (cudaMalloc(&mem, (2 * nt + nr + nd) * sizeof(int)) != cudaSuccess) {
         mem = nullptr;
-        set_error("cuboid tables: cudaMalloc of %zu ints failed", 2 * nt + nr);
+        set_error("cuboid tables: cudaMalloc of %zu ints failed", 2 * nt + nr + nd);
         return PD_ERR_CUDA;
     }
     int* p = static_cast<int*>(mem);
@@ -731,6 +764,11 @@ int CuboidTablesDev::upload(const CuboidTables& t) {
     dev.tok = p;
     dev.lab = p + nt;
     dev.rel = p + 2 * nt;
+    dev.dst = nullptr;
+    if (nd) {
+        PD_CUDA(cudaMemcpy(p + 2 * nt + nr, t.dst.data(), nd * sizeof(int), cudaMemcpyHostToDevice));
+        dev.dst = p + 2 * nt + nr;
+    }
     dev.num_cuboids = t.num_cuboids;
     dev.volume = t.volume;
     dev.rel_off = t.rel_off;

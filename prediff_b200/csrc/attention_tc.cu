@@ -93,8 +93,8 @@ struct TcCfg {
 template <int HD, bool MULTI>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 cuboid_attention_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias_table, bf16* __restrict__ out,
-                           const int* __restrict__ tok, const int* __restrict__ lab, const int* __restrict__ rel, int N, int C,
-                           int heads, int vol, int rel_off, int n_rel) {
+                           const int* __restrict__ tok, const int* __restrict__ lab, const int* __restrict__ rel,
+                           const int* __restrict__ dstp, int N, int C, int heads, int vol, int rel_off, int n_rel) {
     using Cfg = TcCfg<HD, MULTI>;
     constexpr int ST = Cfg::kStages, SB = Cfg::kSBufs, MST = Cfg::kMetaStages;
     extern __shared__ uint8_t smem_raw[];
@@ -425,7 +425,8 @@ cuboid_attention_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict
         const float l_tot = l_run + xl[(hf ^ 1) * kTile + r];
         ptx::mbar_wait(o_done, (n_chunks - 1) & 1);
         ptx::tc_fence_after();
-        const int t = s_qtok[r];
+        // 'nearest' padding: the slot's destination differs from the token its rows were copied from
+        const int t = dstp ? (q0 + r < vol ? dstp[(size_t)cub * vol + q0 + r] : -1) : s_qtok[r];
         const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
         bf16* dst = out + ((size_t)b * N + (t >= 0 ? t : 0)) * C + h * HD + hf * OH;
 #pragma unroll
@@ -461,7 +462,7 @@ int launch_tc(const bf16* qkv, const float* bias_table, bf16* out, int B, int N,
     }
     dim3 grid(ceil_div(g.volume, kTile), g.num_cuboids, B * heads);
     PD_LAUNCH((cuboid_attention_tc_kernel<HD, MULTI>), grid, kThreadsTc, Cfg::kSmem, st, qkv, bias_table, out, g.tok, g.lab,
-              g.rel, N, C, heads, g.volume, g.rel_off, g.n_rel);
+              g.rel, g.dst, N, C, heads, g.volume, g.rel_off, g.n_rel);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }

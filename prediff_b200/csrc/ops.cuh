@@ -45,10 +45,15 @@ struct CuboidTables {      // host tables of one layer on a (T, H, W) grid
     std::vector<int> tok;  // [num_cuboids * volume] token row inside a sample's [T*H*W] block, -1 = padding slot
     std::vector<int> lab;  // [num_cuboids * volume] shifted-window region label, -1 = masked out ('ignore' padding)
     std::vector<int> rel;  // [volume] relative_position_index[i][j] == rel[i] - rel[j] + rel_off
+    // padding_type 'nearest' only (empty otherwise): the slot's result is written to token dst (-1 = to nobody); `tok` is
+    // then the token the slot's q|k|v rows are COPIES of (the reference resamples the grid with F.interpolate before the
+    // attention and back after it, models/utils.py:228-270)
+    std::vector<int> dst;
 };
 int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int padding_type, CuboidTables* out);
 struct CuboidDev {         // device copies
     const int *tok = nullptr, *lab = nullptr, *rel = nullptr;
+    const int* dst = nullptr;                                  // null: results go to `tok` (every padding type but 'nearest')
     int num_cuboids = 0, volume = 0, rel_off = 0, n_rel = 0;   // n_rel: rows of the bias table
 };
 struct CuboidTablesDev {   // owner of the device copies

@@ -176,7 +176,8 @@ int UNet::validate() const {
     PD_CHECK(hd0 == 16 || hd0 == 32 || hd0 == 64, PD_ERR_SHAPE, "unet: head dim %d unsupported", hd0);
     PD_CHECK(cfg.depth[0] >= 1 && cfg.depth[1] >= 1, PD_ERR_SHAPE, "unet: depth");
     PD_CHECK(cfg.max_batch >= 1, PD_ERR_SHAPE, "unet: max_batch");
-    PD_CHECK(padding_type == 0 || padding_type == 1, PD_ERR_ARG, "unet: padding_type %d (0 'zeros' | 1 'ignore')", padding_type);
+    PD_CHECK(padding_type >= 0 && padding_type <= 2, PD_ERR_ARG, "unet: padding_type %d (0 'zeros' | 1 'ignore' | 2 'nearest')",
+             padding_type);
     for (int lvl = 0; lvl < 2; ++lvl)
         for (const CuboidLayerSpec& sp : layers[lvl])
             for (int a = 0; a < 3; ++a)

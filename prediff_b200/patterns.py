@@ -110,11 +110,12 @@ def layer_geometry(data_shape, size0, strategy, shift0, padding_type="zeros"):
                  lab  int32 (num_cuboids * volume): shifted-window region label; -1 = masked out (padding, 'ignore'),
                  rel  int32 (volume): code of the in-cuboid position such that
                       relative_position_index[i, j] == rel[i] - rel[j] + rel_off,
-                 rel_off int).
+                 rel_off int,
+                 dst  int32 (num_cuboids * volume) or None: 'nearest' padding only - the token the slot's result is written to).
     The label / validity rules restate compute_cuboid_self_attention_mask (cuboid_transformer.py:470-528):
     mask[c, i, j] = lab[c, i] == lab[c, j] and both >= 0.
     """
-    assert padding_type in ("zeros", "ignore")
+    assert padding_type in ("zeros", "ignore", "nearest")
     dims = tuple(int(v) for v in data_shape)
     size, shift = effective_size_shift(dims, size0, shift0, strategy)
     pad = tuple((size[a] - dims[a] % size[a]) % size[a] for a in range(3))
@@ -123,6 +124,20 @@ def layer_geometry(data_shape, size0, strategy, shift0, padding_type="zeros"):
     nc, vol = n[0] * n[1] * n[2], size[0] * size[1] * size[2]
     tok = np.empty((nc, vol), np.int32)
     lab = np.empty((nc, vol), np.int32)
+    # 'nearest' (models/utils.py:228-270): padded position o copies token floor(o * dims / padded) (F.interpolate to the
+    # padded size) and token t takes the result of position floor(t * padded / dims) (F.interpolate back), both in torch's
+    # float32 index arithmetic; `dst` is then the token a slot's result goes to (-1: nobody) and `tok` the token it copies
+    nearest = padding_type == "nearest" and any(pad)
+    dst = np.full((nc, vol), -1, np.int32) if nearest else None
+    if nearest:
+        near_src, near_dst = [], []
+        for a in range(3):
+            up, down = np.float32(dims[a]) / np.float32(padded[a]), np.float32(padded[a]) / np.float32(dims[a])
+            near_src.append([min(int(np.floor(np.float32(o) * up)), dims[a] - 1) for o in range(padded[a])])
+            d = [-1] * padded[a]
+            for t in range(dims[a]):
+                d[min(int(np.floor(np.float32(t) * down)), padded[a] - 1)] = t
+            near_dst.append(d)
     any_shift = any(s > 0 for s in shift)
     for c in range(nc):
         cub = (c // (n[1] * n[2]), (c // n[2]) % n[1], c % n[2])
@@ -141,6 +156,13 @@ def layer_geometry(data_shape, size0, strategy, shift0, padding_type="zeros"):
                 o = (p + shift[a]) % padded[a] if any_shift else p   # torch.roll(x, -shift): rolled[p] = x[p + shift]
                 valid = valid and o < dims[a]
                 src.append(o)
+            if nearest:   # src = position in the padded (un-rolled) grid
+                st = [near_src[a][src[a]] for a in range(3)]
+                dt = [near_dst[a][src[a]] for a in range(3)]
+                tok[c, i] = (st[0] * dims[1] + st[1]) * dims[2] + st[2]
+                dst[c, i] = (dt[0] * dims[1] + dt[1]) * dims[2] + dt[2] if min(dt) >= 0 else -1
+                lab[c, i] = label
+                continue
             tok[c, i] = (src[0] * dims[1] + src[1]) * dims[2] + src[2] if valid else -1
             lab[c, i] = -1 if (not valid and padding_type == "ignore") else label
     b0 = tuple(int(v) for v in size0)   # the index buffer is built from the constructor's cuboid size and sliced
@@ -149,4 +171,4 @@ def layer_geometry(data_shape, size0, strategy, shift0, padding_type="zeros"):
     rel = ((i // (b0[1] * b0[2])) * s1 + ((i // b0[2]) % b0[1]) * s2 + i % b0[2]).astype(np.int32)
     rel_off = (b0[0] - 1) * s1 + (b0[1] - 1) * s2 + (b0[2] - 1)
     return dict(size=size, shift=shift, pad=pad, num_cuboids=nc, volume=vol, tok=tok.reshape(-1), lab=lab.reshape(-1),
-                rel=rel, rel_off=int(rel_off))
+                rel=rel, rel_off=int(rel_off), dst=None if dst is None else dst.reshape(-1))

@@ -4,7 +4,7 @@
 Same constructor argument names, `forward(x, t, cond, verbose=False)` contract, `state_dict()` key names and
 shapes. Built: two levels, patch-merge / upsample, GELU FFN, relative position bias, no global vectors, and every
 registered `block_attn_patterns` name (axial - the shipped SEVIR-LR config, on its own fast path - full, divided_st,
-video_swin_PxM, spatial_lg_M, axial_space_dilate_K; prediff_b200/patterns.py) with 'zeros' or 'ignore' padding;
+video_swin_PxM, spatial_lg_M, axial_space_dilate_K; prediff_b200/patterns.py) with 'zeros', 'ignore' or 'nearest' padding;
 anything else raises NotImplementedError at construction - there is no fallback path.
 """
 import ctypes
@@ -82,7 +82,7 @@ class CuboidTransformerUNet(nn.Module):
                     _patterns.get(name)
                 except KeyError:
                     _unsupported(f"block_attn_patterns={patterns}")
-        if padding_type not in ("zeros", "ignore"):
+        if padding_type not in ("zeros", "ignore", "nearest"):
             _unsupported(f"padding_type='{padding_type}'")
         if block_units is not None and list(block_units) != [base_units, 2 * base_units]:
             _unsupported(f"block_units={block_units}")
@@ -140,7 +140,7 @@ class CuboidTransformerUNet(nn.Module):
                 L.check(L.lib().pd_unet_create(ctypes.byref(cc), ctypes.byref(h)))
             else:
                 pt = _CUnetPattern()
-                pt.padding_type = 0 if c.padding_type == "zeros" else 1
+                pt.padding_type = {"zeros": 0, "ignore": 1, "nearest": 2}[c.padding_type]
                 for lvl in range(2):
                     layers = c.layers(lvl)
                     pt.n_layers[lvl] = len(layers)

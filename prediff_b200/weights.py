@@ -22,7 +22,7 @@ class UNetConfig:
     base_units: int = 256
     depth: Tuple[int, int] = (4, 4)
     num_heads: int = 4
-    # block_attn_patterns per level (names of cuboid_transformer_patterns.py) and padding_type ('zeros' | 'ignore')
+    # block_attn_patterns per level (names of cuboid_transformer_patterns.py) and padding_type ('zeros' | 'ignore' | 'nearest')
     patterns: Tuple[str, str] = ("axial", "axial")
     padding_type: str = "zeros"
     # block_attn_patterns=None in the reference: explicit per-level lists of (cuboid_size, strategy, shift_size)

@@ -459,6 +459,34 @@ def gen_patterns():
 
 
 @torch.no_grad()
+def gen_patterns_nearest():
+    """padding_type='nearest' (models/utils.py:228-270): outputs of the unmodified CuboidSelfAttentionLayer and of the
+    unmodified reference UNet (tiny config, a pattern that pads T = 13)."""
+    import dataclasses
+    from prediff.models.cuboid_transformer.cuboid_transformer import CuboidSelfAttentionLayer
+    import pattern_cases as PC
+    out = {}
+    for tag, dims, C, heads, size, strat, shift, pad in PC.NEAREST_LAYER_CASES:
+        m = CuboidSelfAttentionLayer(dim=C, num_heads=heads, cuboid_size=size, shift_size=shift, strategy=tuple(strat),
+                                     padding_type=pad, qkv_bias=False, attn_drop=0.0, proj_drop=0.0,
+                                     use_final_proj=True, norm_layer="layer_norm", use_global_vector=False,
+                                     checkpoint_level=0, use_relative_pos=True).eval()
+        sd = Wt.seeded_state_dict(PC.layer_spec(C, heads, size), PC.LAYER_SEED)
+        res = m.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not res.unexpected_keys and res.missing_keys == ["relative_position_index"], res
+        x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+        out[f"layer_{tag}"] = m(x)
+    for tag, pats, pad in PC.NEAREST_UNET_CASES:
+        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
+        m = ref_unet(cfg)
+        x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c)
+        cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c)
+        out[f"unet_{tag}"] = m(x, torch.tensor([500], dtype=torch.long), cond)
+        print(f"patterns_nearest unet_{tag}: out std {out[f'unet_{tag}'].std():.3f}")
+    save("patterns_nearest", **out)
+
+
+@torch.no_grad()
 def gen_vae(tag, cfg, N):
     m = ref_vae(cfg)
     x = inp(4321, N, 1, cfg.h, cfg.w, uniform=True)
@@ -674,6 +702,8 @@ if __name__ == "__main__":
         gen_loader()
     if "patterns" in todo:
         gen_patterns()
+    if "patterns_nearest" in todo:
+        gen_patterns_nearest()
     if "losses" in todo:
         gen_losses()
     if "ema" in todo:

@@ -13,6 +13,20 @@ LAYER_CASES = [
 ]
 LAYER_SEED = 4004
 
+# padding_type='nearest' (models/utils.py:228-270: the grid is resampled with F.interpolate before and after the attention);
+# goldens in patterns_nearest.npz. Same tuple layout as LAYER_CASES.
+NEAREST_LAYER_CASES = [
+    ("swin_pad_shift_n", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "nearest"),
+    ("dilated_n", (13, 8, 8), 32, 2, (2, 4, 4), "ddd", (0, 0, 0), "nearest"),
+    ("mixed_ragged_n", (6, 7, 9), 32, 2, (4, 3, 4), "ldl", (2, 1, 2), "nearest"),
+    ("ragged_all_n", (5, 7, 9), 16, 2, (3, 4, 5), "lld", (1, 2, 0), "nearest"),
+    ("clipped_n", (5, 6, 6), 32, 2, (8, 4, 8), "lll", (4, 2, 4), "nearest"),
+    ("nopad_n", (4, 8, 8), 32, 2, (2, 4, 4), "lll", (1, 2, 2), "nearest"),
+    ("swin2x8_hd64_n", (13, 8, 8), 128, 2, (2, 8, 8), "lll", (1, 4, 4), "nearest"),
+]
+# tiny UNet with a pattern that pads T = 13 (video_swin_2x8: cuboids of 2 frames), B = 1, t = 500
+NEAREST_UNET_CASES = [("swin_n", ("video_swin_2x8", "video_swin_2x8"), "nearest")]
+
 # (tag, block_attn_patterns, padding_type): tiny UNet (base_units 64, depth (1, 1)), B = 1, t = 500
 UNET_CASES = [
     ("swin_lg", ("video_swin_4x4", "spatial_lg_4"), "zeros"),

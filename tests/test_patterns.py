@@ -15,6 +15,7 @@ from tests.golden import pattern_cases as PC
 from tests.golden.gen_golden import UNET_SEED, inp
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "patterns.npz"))
+GN = np.load(os.path.join(os.path.dirname(__file__), "golden", "patterns_nearest.npz"))   # padding_type='nearest'
 
 
 def maxrel(a, b):
@@ -49,7 +50,20 @@ def test_oracle_layer_vs_reference(case):
     assert maxrel(out, G[f"layer_{tag}"]) < 2e-5
 
 
-@pytest.mark.parametrize("case", PC.UNET_CASES + [("explicit", None, "ignore")], ids=[c[0] for c in PC.UNET_CASES] + ["explicit"])
+@pytest.mark.parametrize("case", PC.NEAREST_LAYER_CASES, ids=[c[0] for c in PC.NEAREST_LAYER_CASES])
+def test_oracle_layer_nearest_vs_reference(case):
+    """padding_type='nearest' (models/utils.py:228-270) against the unmodified CuboidSelfAttentionLayer."""
+    tag, dims, C, heads, size, strat, shift, pad = case
+    sd = O.to_torch_sd(Wt.seeded_state_dict(PC.layer_spec(C, heads, size), PC.LAYER_SEED))
+    x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+    out = O.cuboid_attention(sd, "a", x, heads, size, tuple(strat), shift, pad)
+    assert maxrel(out, GN[f"layer_{tag}"]) < 2e-5
+
+
+_ALL_UNET_CASES = PC.UNET_CASES + [("explicit", None, "ignore")] + PC.NEAREST_UNET_CASES
+
+
+@pytest.mark.parametrize("case", _ALL_UNET_CASES, ids=[c[0] for c in _ALL_UNET_CASES])
 def test_oracle_unet_patterns_vs_reference(case):
     tag, pats, pad = case
     if pats is None:   # block_attn_patterns=None with the reference's default explicit lists
@@ -61,7 +75,7 @@ def test_oracle_unet_patterns_vs_reference(case):
     x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c)
     cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c)
     out = O.unet_forward(sd, cfg, x, torch.tensor([500]), cond)
-    assert maxrel(out, G[f"unet_{tag}"]) < 1e-4
+    assert maxrel(out, (GN if pad == "nearest" else G)[f"unet_{tag}"]) < 1e-4
 
 
 def attention_from_tables(qkv, table, heads, geo):
@@ -84,11 +98,16 @@ def attention_from_tables(qkv, table, heads, geo):
         den = p.sum(-1, keepdims=True)
         p = np.where(den > 0, p / np.where(den > 0, den, 1.0), 0.0)
         o = (p @ v).transpose(0, 2, 1, 3).reshape(B, vol, C)
-        out[:, tok[c]] = o   # padded tokens land in the scratch row
+        if geo.get("dst") is not None:   # 'nearest': slots write to their destination token (-1 = the scratch row)
+            out[:, geo["dst"].reshape(nc, vol)[c]] = o
+        else:
+            out[:, tok[c]] = o   # padded tokens land in the scratch row
     return out[:, :-1].reshape(B, T, H, W, C)
 
 
-GEOM_CASES = [(c[1], c[3], c[4], c[5], c[6], c[7]) for c in _ALL_LAYER_CASES] + [
+GEOM_CASES = [(c[1], c[3], c[4], c[5], c[6], c[7]) for c in _ALL_LAYER_CASES + PC.NEAREST_LAYER_CASES] + [
+    ((13, 16, 16), 4, (2, 8, 8), "lll", (1, 4, 4), "nearest"),
+    ((13, 8, 8), 4, (4, 4, 4), "dld", (0, 2, 0), "nearest"),
     ((13, 16, 16), 4, (13, 1, 1), "lll", (0, 0, 0), "zeros"),
     ((13, 16, 16), 4, (1, 16, 16), "lll", (0, 0, 0), "ignore"),
     ((13, 8, 8), 4, (2, 8, 8), "lll", (1, 4, 4), "ignore"),
@@ -109,8 +128,8 @@ def test_geometry_tables_vs_oracle(case):
     geo = P.layer_geometry(dims, size, tuple(strat), shift, pad)
     got = attention_from_tables(qkv, table, heads, geo)
     assert maxrel(got, want) < 1e-5
-    # every real token belongs to exactly one cuboid slot
-    t = geo["tok"][geo["tok"] >= 0]
+    # every real token belongs to exactly one cuboid slot ('nearest': is written by exactly one slot)
+    t = geo["tok"][geo["tok"] >= 0] if geo["dst"] is None else geo["dst"][geo["dst"] >= 0]
     assert np.array_equal(np.sort(t), np.arange(dims[0] * dims[1] * dims[2]))
 
 
@@ -126,12 +145,19 @@ def test_c_abi_tables_equal_python_tables(case):
     n = geo["num_cuboids"] * geo["volume"]
     tok, lab, rel = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(geo["volume"], np.int32)
     rc = L.lib().pd_cuboid_tables(*dims, i3(*size), i3(*[0 if s == "l" else 1 for s in strat]), i3(*shift),
-                                  0 if pad == "zeros" else 1, meta, tok.ctypes.data_as(ctypes.c_void_p),
+                                  {"zeros": 0, "ignore": 1, "nearest": 2}[pad], meta, tok.ctypes.data_as(ctypes.c_void_p),
                                   lab.ctypes.data_as(ctypes.c_void_p), rel.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n))
     assert rc >= 0
     assert tuple(meta[0:3]) == geo["size"] and tuple(meta[3:6]) == geo["shift"] and tuple(meta[6:9]) == geo["pad"]
     assert (meta[9], meta[10], meta[11]) == (geo["num_cuboids"], geo["volume"], geo["rel_off"])
     assert np.array_equal(tok, geo["tok"]) and np.array_equal(lab, geo["lab"]) and np.array_equal(rel, geo["rel"])
+    dst = np.full(n, -7, np.int32)
+    rd = L.lib().pd_cuboid_tables_dst(*dims, i3(*size), i3(*[0 if s == "l" else 1 for s in strat]), i3(*shift),
+                                      {"zeros": 0, "ignore": 1, "nearest": 2}[pad], dst.ctypes.data_as(ctypes.c_void_p),
+                                      ctypes.c_int64(n))
+    assert rd == (0 if geo["dst"] is None else 1)
+    if geo["dst"] is not None:
+        assert np.array_equal(dst, geo["dst"])
     is_axial = sum(s > 1 for s in geo["size"]) == 1 and geo["size"] == tuple(size) and max(geo["size"]) <= 16 \
         and all(geo["size"][a] in (1, dims[a]) for a in range(3)) and not any(geo["shift"])
     assert (rc > 0) == is_axial

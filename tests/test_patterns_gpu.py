@@ -1,6 +1,6 @@
 """GPU parity for the non-axial cuboid patterns, through the C ABI:
   - pd_op_cuboid_attention (general cuboid attention kernel) vs the reference-pinned oracle core on the same bf16 q|k|v,
-    for shifted / padded / dilated / clipped / multi-chunk cuboids, head dims 16..128, 'zeros' and 'ignore' padding;
+    for shifted / padded / dilated / clipped / multi-chunk cuboids, head dims 16..128, 'zeros', 'ignore' and 'nearest' padding;
   - the general kernel vs the axial fast-path kernel on axial layers;
   - CuboidTransformerUNet built with non-axial block_attn_patterns vs goldens of the unmodified reference UNet and vs
     the oracle at the shipped widths (256 / 512: fused FFN and cluster-LayerNorm paths with 1, 2 and 5 layers per block).
@@ -23,6 +23,7 @@ from tests.golden.gen_golden import UNET_SEED, inp
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "patterns.npz"))
+GN = np.load(os.path.join(os.path.dirname(__file__), "golden", "patterns_nearest.npz"))   # padding_type='nearest'
 REL_RMS_TOL, MAX_TOL = 1.5e-2, 4e-2
 I3 = ctypes.c_int32 * 3
 
@@ -41,7 +42,7 @@ def run_op(qkv, table, dims, C, heads, size, strat, shift, pad, impl=0):
     out = torch.full((B, *dims, C), float("nan"), device="cuda", dtype=torch.bfloat16)
     L.check(L.lib().pd_op_cuboid_attention_impl(L.ptr(qkv), L.ptr(table), L.ptr(out), B, *dims, C, heads, I3(*size),
                                                 I3(*[0 if s == "l" else 1 for s in strat]), I3(*shift),
-                                                0 if pad == "zeros" else 1, impl, L.stream_ptr()))
+                                                {"zeros": 0, "ignore": 1, "nearest": 2}[pad], impl, L.stream_ptr()))
     torch.cuda.synchronize()
     return out
 
@@ -58,6 +59,8 @@ TC_CASES = [
     ((13, 16, 16), 4, 64, (4, 4, 4), "lll", (2, 2, 2), "ignore"),     # volume 64 < one tile: half-empty tile, masked tail
     ((13, 16, 16), 2, 64, (4, 8, 8), "ldd", (0, 0, 0), "zeros"),      # dilated gather, volume 256, T 13 -> 16 zero slots
     ((6, 7, 9), 2, 64, (4, 7, 9), "lll", (2, 3, 4), "ignore"),        # ragged grid, volume 252, shifted
+    ((13, 8, 8), 4, 128, (2, 8, 8), "lll", (1, 4, 4), "nearest"),     # 'nearest': T 13 -> 14 by resampling, shifted
+    ((13, 16, 16), 4, 64, (4, 8, 8), "ldd", (0, 0, 0), "nearest"),    # 'nearest' + dilated gather, T 13 -> 16
 ]
 
 
@@ -96,6 +99,9 @@ OP_CASES = [
     ((5, 6, 6), 2, 32, (8, 4, 8), "lll", (4, 2, 4), "ignore"),        # cuboid clipped to the data (index-buffer quirk)
     ((13, 16, 16), 4, 64, (13, 16, 16), "lll", (0, 0, 0), "zeros"),   # full attention: one 3328-token cuboid, 52 chunks
     ((13, 16, 16), 4, 16, (13, 1, 1), "lll", (0, 0, 0), "zeros"),     # axial layer through the general kernel
+    ((13, 16, 16), 4, 64, (4, 4, 4), "lll", (2, 2, 2), "nearest"),    # 'nearest' padding (models/utils.py:228-270)
+    ((6, 7, 9), 2, 16, (4, 3, 4), "ldl", (2, 1, 2), "nearest"),
+    ((5, 7, 9), 2, 32, (3, 4, 5), "lld", (1, 2, 0), "nearest"),
 ]
 
 
@@ -141,7 +147,7 @@ def make_unet(cfg, max_batch=2):
     return m.eval(), sd
 
 
-@pytest.mark.parametrize("case", PC.UNET_CASES, ids=[c[0] for c in PC.UNET_CASES])
+@pytest.mark.parametrize("case", PC.UNET_CASES + PC.NEAREST_UNET_CASES, ids=[c[0] for c in PC.UNET_CASES + PC.NEAREST_UNET_CASES])
 def test_unet_patterns_vs_reference_golden(case):
     tag, pats, pad = case
     cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad)
@@ -149,14 +155,15 @@ def test_unet_patterns_vs_reference_golden(case):
     x = inp(1234, 1, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
     cond = inp(1235, 1, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()
     out = m(x, torch.tensor([500], device="cuda"), cond)
-    rel_rms, mx = errs(out, G[f"unet_{tag}"])
+    rel_rms, mx = errs(out, (GN if pad == "nearest" else G)[f"unet_{tag}"])
     assert rel_rms < REL_RMS_TOL and mx < MAX_TOL, (rel_rms, mx)
 
 
 @pytest.mark.parametrize("pats,pad", [(("video_swin_2x8", "video_swin_2x8"), "ignore"),
+                                      (("video_swin_2x8", "video_swin_2x8"), "nearest"),
                                       (("divided_st", "axial_space_dilate_2"), "zeros"),
                                       (("full", "spatial_lg_4"), "zeros")],
-                         ids=["swin2x8", "dst_dilate", "full_lg"])
+                         ids=["swin2x8", "swin2x8_nearest", "dst_dilate", "full_lg"])
 def test_unet_shipped_width_patterns_vs_oracle(pats, pad):
     """Width 256 / 512 (head dims 64 / 128; fused projection+FFN kernel at level 0, cluster LayerNorm at level 1) with
     1, 2, 3 and 5 attention layers per stack block."""
