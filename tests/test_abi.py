@@ -97,7 +97,7 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError):
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], block_attn_patterns="video_swin_3x5")  # not registered
     with pytest.raises(NotImplementedError):
-        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], padding_type="nearest")
+        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], padding_type="reflect")   # not one of the reference's three
     with pytest.raises(NotImplementedError):
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], num_global_vectors=8)
     with pytest.raises(NotImplementedError):
