@@ -136,8 +136,8 @@ def test_pattern_and_loss_arguments_fail_loudly():
     i3 = ctypes.c_int32 * 3
     meta = (ctypes.c_int32 * 12)()
     lib = L.lib()
-    # padding_type 2 ('nearest') is not built; cuboid sizes must be >= 1; strategies are 0 / 1
-    for size, strat, shift, pad in (((4, 4, 4), (0, 0, 0), (0, 0, 0), 2), ((0, 4, 4), (0, 0, 0), (0, 0, 0), 0),
+    # padding_type is 0 / 1 / 2; cuboid sizes must be >= 1; strategies are 0 / 1
+    for size, strat, shift, pad in (((4, 4, 4), (0, 0, 0), (0, 0, 0), 3), ((0, 4, 4), (0, 0, 0), (0, 0, 0), 0),
                                     ((4, 4, 4), (0, 2, 0), (0, 0, 0), 0), ((4, 4, 4), (0, 0, 0), (-1, 0, 0), 0)):
         rc = lib.pd_cuboid_tables(13, 16, 16, i3(*size), i3(*strat), i3(*shift), pad, meta, None, None, None, ctypes.c_int64(0))
         assert rc < 0 and lib.pd_last_error()
