@@ -159,10 +159,11 @@ def test_pattern_and_loss_arguments_fail_loudly():
             return x
 
     for kw in (dict(loss_type="huber"), dict(parameterization="x0"), dict(scale_by_std=True),
-               dict(cond_stage_forward="encode_first"), dict(num_timesteps_cond=4)):
+               dict(cond_stage_forward="encode_first")):
         with pytest.raises(NotImplementedError):
             LatentDiffusion(torch_nn_module=Eps(), **kw)
     assert LatentDiffusion(torch_nn_module=Eps(), clip_denoised=True).clip_denoised   # built: clamp inside the update kernel
+    assert LatentDiffusion(torch_nn_module=Eps(), num_timesteps_cond=4).shorten_cond_schedule   # built: sampling loop only
     ld = LatentDiffusion(torch_nn_module=Eps(), loss_type="l1", original_elbo_weight=0.5)
     assert ld.lvlb_weights.shape == (1000,) and "lvlb_weights" not in ld.state_dict()   # non-persistent, as in the reference
     assert tuple(ld.logvar.shape) == (1000,) and ld.loss_mean_dim == (1, 2, 3, 4)
