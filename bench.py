@@ -483,8 +483,8 @@ def main():
         line["shard_invariant"] = shard_invariant
     if "trace" in extras:
         trace, slot = extras["trace"]
-        gemm_sites = ("conv1", "conv2", "qkv", "proj", "ffn1", "ffn2", "proj_ffn_fused", "ffn_fused", "skip", "up.conv",
-                      "down.reduction", "final.proj")
+        gemm_sites = ("conv1", "conv2", "qkv", "proj", "ffn1", "ffn2", "proj_ffn_fused", "ffn_fused", "proj_ffn_cluster",
+                      "ffn_cluster", "qkv_attn_T", "qkv_attn_H", "qkv_attn_W", "skip", "up.conv", "down.reduction", "final.proj")
         is_gemm = lambda k: k.split(".")[-1] in gemm_sites or k in gemm_sites   # noqa: E731
         n_launch = sum(v[0] for v in trace.values())
         kern_ms = sum(v[1] for v in trace.values()) * 1e-3
@@ -521,8 +521,8 @@ def main():
             "launch_overhead": {"launches_per_step": n_launch, "kernel_ms_per_step": kern_ms, "in_loop_step_ms": step_ms,
                                 "overhead_ms_per_step": overhead_ms, "per_launch_us": per_launch_overhead_us,
                                 "share_of_step": overhead_ms / step_ms},
-            "dominant_kernel": {"name": "tcgen05 implicit-GEMM family: gemm_tc_kernel, gemm_tc_persistent_kernel, "
-                                        "conv_streamk_kernel, ffn_fused_kernel (conv3d/conv2d/linear)",
+            "dominant_kernel": {"name": "tcgen05 implicit-GEMM family: conv_streamk_kernel, ffn_fused_kernel, ffn_cluster_kernel, "
+                                        "qkv_attn_kernel, gemm_tc_kernel (conv3d / conv2d / linear / fused transformer layers)",
                                 "launches_per_forward": int(g_n), "ms_per_forward": g_us * 1e-3,
                                 "avg_launch_us": g_us / max(g_n, 1), "tflops": g_fl / (g_us * 1e-6) * 1e-12,
                                 "frac_of_peak": g_fl / (g_us * 1e-6) * 1e-12 / peaks["tensor_tflops"],
