@@ -118,7 +118,8 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint64_t* stat_bar = acc0_full + 1;         // [1]: the three peers' row sums of x1 have landed (st.async complete_tx)
     uint64_t* ln_ready = stat_bar + 1;          // [1]: every CTA of the cluster has published its LayerNorm(x1) slice
     uint64_t* stat2_bar = ln_ready + 1;         // [1]: the three peers' row sums of the final x have landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat2_bar + 1);
+    uint64_t* slices_ready = stat2_bar + 1;     // [1]: the three peers have written this CTA's slices of their partials
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slices_ready + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -147,7 +148,8 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         ptx::mbar_init(&acc2_full[1], 1);
         for (int s = 0; s < 2 * kEpiWarps; ++s) ptx::mbar_init(&res_bar[s], 1);
         ptx::mbar_init(stat2_bar, 1);
-        ptx::mbar_arrive_expect_tx(stat2_bar, (kCl - 1) * 128 * 8);   // armed long before the reduce phase's cluster barrier
+        ptx::mbar_arrive_expect_tx(stat2_bar, (kCl - 1) * 128 * 8);   // armed long before any peer reaches its final LayerNorm
+        ptx::mbar_init(slices_ready, kCl - 1);
         if (PROJ) {
             for (int s = 0; s < 4; ++s) {
                 ptx::mbar_init(&g0_full[s], 1);
@@ -197,10 +199,10 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // PROJ: peers exchange row sums / arrivals through this CTA's barriers long before the first full cluster barrier -
-    // split-phase: arrive now (the barrier initialisation above is published by fence.mbarrier_init), wait before the
-    // first remote access
-    if (PROJ) ptx::cluster_arrive();
+    // Peers exchange row sums / arrivals through this CTA's barriers and the kernel has no full cluster barrier at all:
+    // split-phase - arrive now (the barrier initialisation above is published by fence.mbarrier_init), wait before the
+    // first remote access (E0 in the PROJ variant, the hand-over of the partial slices otherwise)
+    ptx::cluster_arrive();
     if (PROJ && warp == 2 && lane < 12) {   // the CTA's 128 columns of bp / ln1 gamma / ln1 beta -> L1 (4 lines each)
         const float* v = lane < 4 ? p.bp : (lane < 8 ? p.ln1_gamma : p.ln1_beta);
         ptx::prefetch_l1(v + j * kOs + (lane & 3) * 32);
@@ -503,6 +505,7 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint64_t* my_bar = res_bar + 2 * (warp >= 2 ? e : 0);
     float4* ws4 = reinterpret_cast<float4*>(p.ws) + (size_t)tile * (kWsFloatsPerTile / 4);
     if (warp >= 2) {
+        if (!PROJ) ptx::cluster_wait();   // peers have initialised their barriers (PROJ: waited for in E0)
         // slices for the owners of output columns [0, 256) leave while G2 still works on columns [256, 512)
 #pragma unroll 1
         for (int d = 0; d < kCl; ++d) {                               // destination CTA: owner of output columns [128 d, +128)
@@ -533,9 +536,19 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
         if (stamper) PD_CSTAMP(8);
+        // hand-over: the CTA barrier orders the eight warps' stores before one thread, whose fence + releasing arrivals on the
+        // three peers' barriers publish them (cumulativity); each CTA then waits for ITS three senders only - no cluster-wide
+        // barrier (the full barrier.cluster here cost 4.4 k cycles and held everybody for the slowest CTA's last slice)
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (threadIdx.x == 64) {
+            __threadfence();
+#pragma unroll
+            for (int dd = 1; dd < kCl; ++dd)
+                ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(slices_ready), (uint32_t)((j + dd) & (kCl - 1))));
+        }
+        ptx::mbar_wait_cluster(slices_ready, 0);
     }
-    if (PROJ && warp < 2) ptx::cluster_wait();   // second half of the split-phase barrier of the prologue (epilogue warps: E0)
-    ptx::cluster_sync_all();                // release / acquire at cluster scope: every CTA's slices are visible
+    if (warp < 2) ptx::cluster_wait();      // second half of the split-phase barrier of the prologue
     if (stamper) PD_CSTAMP(9);
     float s1 = 0.f, s2 = 0.f;
     const bool row_ok = row_tile + r < p.M;
@@ -676,8 +689,8 @@ ffn_cluster_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
     }
     if (warp >= 2 && lane == 0) ptx::bulk_wait_read<0>();   // the slabs must outlive the bulk stores' reads
-    // nobody may exit while a peer can still write into this CTA's shared memory: the only DSMEM traffic is the LayerNorm
-    // exchange, which is complete at the cluster barrier that follows it
+    // nobody exits while a peer can still write into its shared memory: every remote access (row sums, barrier arrivals) is
+    // one the receiving CTA waits for before it goes on
     if (stamper) PD_CSTAMP(12);
     ptx::tc_fence_before();
     __syncthreads();
