@@ -1,10 +1,17 @@
 // Fused PositionwiseFFN for the width-512 level: x <- x + W2 GELU(W1 ln + b1) + b2 and the LayerNorm that follows, in ONE
 // kernel, with the hidden dimension (2048) split over a 4-CTA thread-block cluster (VERDICT r01 "next" 2).
 // Reference: PositionwiseFFN.forward (src/prediff/models/cuboid_transformer/cuboid_transformer.py:182-208), pre-norm input
-// `ln` produced by the preceding projection epilogue. Replaces the level-1 FFN-1 GEMM (persistent kernel, 208 tiles on 148
-// SMs, bf16 `mid` round trip) + FFN-2 GEMM (K = 2048 on 104 CTAs): 26 row tiles x 4 = 104 CTAs, one launch.
+// `ln` produced by the preceding projection epilogue - or, PROJ variant, by the kernel itself: the attention output projection
+// + residual + pre-norm (cuboid_transformer.py:952, 1151) run in front (G0 / E0 below). Replaces the level-1 projection GEMM,
+// FFN-1 GEMM (persistent kernel, 208 tiles on 148 SMs, bf16 `mid` round trip) and FFN-2 GEMM (K = 2048 on 104 CTAs): 26 row
+// tiles x 4 = 104 CTAs, one launch.
 //
 // CTA j of a cluster owns the 128 rows of its row tile and hidden columns [512 j, 512 j + 512):
+//   G0   (PROJ) TMEM columns [0, 128) = att . Wp[128 j ...]^T: eight k-blocks of (att 16 KB + Wp tile 16 KB) through four
+//        stages laid over the ring and hidden-slice tiles 4-5;
+//   E0   (PROJ) x1 = (G0 + bp) + x for the CTA's 128 columns -> x (TMA); row sums of x1 exchanged with st.async onto the
+//        peers' armed barriers; LayerNorm(x1) slice -> bf16 slab -> TMA store into `ln`, one releasing arrival per CTA on
+//        every CTA's ln_ready barrier; all four CTAs then load the complete normalised tile as the A operand of G1;
 //   G1   acc[c] (TMEM columns [256 c, +256)) = ln . W1[512 j + 256 c ...]^T, c = 0, 1: K = 512 in 8 k-blocks of (A 16 KB + W1
 //        tile 32 KB). The TMA ring borrows the still-unused hidden-slice region: FOUR stages during G1(0), three during
 //        G1(1) (a round trip of a 48 KB stage is ~2 000 cycles under load; two stages ran at 820-925 cycles per k-block
@@ -14,18 +21,20 @@
 //   G2   partial[128 x 512] (all 512 TMEM columns, re-used) = hidden slice . W2[:, 512 j ...]^T: 8 k-blocks x 2 output halves
 //        of 256 through three 32 KB stages; the first four (k-block, half 0) steps only need E1(0) and run under E1(1);
 //   R    reduce-scatter of the four partials THROUGH L2: each CTA writes the three 128 x 128 slices of its partial that
-//        belong to the other CTAs to a global workspace (thread = row, consecutive lanes -> consecutive 16 bytes), one
-//        cluster barrier (release / acquire), then CTA j adds the four partials of output columns [128 j, +128) in RANK
+//        belong to the other CTAs to a global workspace (thread = row, consecutive lanes -> consecutive 16 bytes), a
+//        releasing arrival on each destination's barrier, then CTA j adds the four partials of output columns [128 j, +128) in RANK
 //        ORDER (deterministic, batch-invariant) + b2 + residual -> x. (The first version exchanged the slices through
 //        distributed shared memory: 192 KB out and 192 KB in per SM at the SM-to-SM network's ~17 B/clk took 22 k cycles,
 //        and the row-per-thread global read-modify-write of x another 21 k - measured with the phase stamps below; the
 //        kernel was slower than the two GEMMs it replaced. Now the residual tile arrives by TMA into swizzled slabs, is
 //        combined in place and bulk-stored.)
-//   LN   row statistics over the 512 columns: per-CTA partial sums exchanged through DSMEM (8 bytes per row), cluster
-//        barrier, totals in rank order -> LayerNorm of the CTA's 128 columns -> bf16 slab -> TMA store (the next layer's
+//   LN   row statistics over the 512 columns: per-CTA partial sums exchanged through DSMEM (st.async, 8 bytes per row, onto
+//        the receiver's armed barrier), totals in rank order -> LayerNorm of the CTA's 128 columns -> bf16 slab -> TMA store (the next layer's
 //        pre-norm); optional GroupNorm statistics of the new x rows for the resblock that follows the stack.
-//   warp 0: TMA producer; warp 1: TMEM allocation + one lane issuing tcgen05.mma 128 x 256 x 16; warps 2-9: E1 / R / LN
-//   (thread = row; warps w and w + 4 share a TMEM lane quarter and split the columns).
+//   warp 0: TMA producer; warp 1: TMEM allocation + one lane issuing tcgen05.mma 128 x 256 x 16; warps 2-9: E0 / E1 / R / LN
+//   (thread = row; warps w and w + 4 share a TMEM lane quarter and split the columns). The kernel has no cluster-wide
+//   barrier besides the split-phase one that publishes the mbarrier initialisation: every remote access is one the
+//   receiving CTA waits for.
 #include "gemm.cuh"
 #include "ops.cuh"
 #include "ptx.cuh"
