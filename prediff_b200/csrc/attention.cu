@@ -25,6 +25,18 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// D(16x8, f32) += A(16x8, tf32, row) * B(8x8, tf32, col)
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x = hi + lo with hi, lo representable in tf32 (hi = rna(x), lo = rna(x - hi)): the 3xTF32 operand split
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gsrc) : "memory");
@@ -151,111 +163,149 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
 // fp32 variant for the TF32-class precision mode (PD_PRECISION_TF32): q|k|v arrive as fp32 from the QKV GEMM and the
 // whole core (scores, bias, softmax, PV) runs in fp32 on the CUDA cores - 1.62 of the step's 653 GFLOP, so there is
 // nothing to win with tensor cores, and nothing of the reference's fp32 attention arithmetic is rounded away. The output
-// is the projection GEMM's A operand: fp32 rounded to tf32. One block per line, one warp per head; lane pair (2i, 2i+1)
-// owns query row i: the pair splits the 16 keys for the scores and the head channels for PV.
-template <int HD>
+// is the projection GEMM's A operand: fp32 rounded to tf32. One block per line, one warp per head. Round 2: the two products
+// run on mma.sync m16n8k8 with the 3xTF32 operand split (x = hi + lo, hi*hi + hi*lo + lo*hi, fp32 accumulate): fp32-accurate
+// (the test bars did not move) at ~650 instead of ~1 450 instructions per (line, head) - the FMA version was issue-bound at 20 %
+// occupancy (ncu: 35 % issue slots busy, 28 us per level-0 launch).
+template <int HD, bool PAIR>   // PAIR: two lines of <= 8 tokens per block
 __global__ void __launch_bounds__(128) axial_attention_f32_kernel(const float* __restrict__ qkv,
                                                                   const float* __restrict__ bias_table,
                                                                   float* __restrict__ out, int T, int H, int W, int C,
-                                                                  int heads, int axis) {
+                                                                  int heads, int axis, int total_lines) {
     grid_dep_launch();
     grid_dep_wait();
     extern __shared__ __align__(16) uint8_t smem_att[];
     float* s_qkv = reinterpret_cast<float*>(smem_att);  // [16][3C + 4]
     const int C3 = 3 * C;
     const int ld = C3 + 4;
-    int L, stride, base;
-    {
-        const int line = blockIdx.x;
+    // Lines of <= 8 tokens travel in pairs (rows 0-7 / 8-15 of the 16-row MMA tile, scores across the two masked out): a block
+    // is `lpb` lines; slot row r = (line r / rows_per, position r % rows_per).
+    const int L = axis == 0 ? T : (axis == 1 ? H : W);
+    const int stride = axis == 0 ? H * W : (axis == 1 ? W : 1);
+    constexpr int lpb = PAIR ? 2 : 1, rows_per = kMaxLine / lpb;
+    int base_of[lpb];
+#pragma unroll
+    for (int u = 0; u < lpb; ++u) {
+        const int line = blockIdx.x * lpb + u;
+        int b0;
         if (axis == 0) {
-            L = T; stride = H * W;
             const int hw = line % (H * W), b = line / (H * W);
-            base = b * T * H * W + hw;
+            b0 = b * T * H * W + hw;
         } else if (axis == 1) {
-            L = H; stride = W;
             const int w = line % W, bt = line / W;
-            base = bt * H * W + w;
+            b0 = bt * H * W + w;
         } else {
-            L = W; stride = 1;
-            base = line * W;
+            b0 = line * W;
         }
+        base_of[u] = line < total_lines ? b0 : -1;
     }
     {
         const int vec_per_row = C3 / 4;
         const int total = kMaxLine * vec_per_row;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int r = i / vec_per_row, v = i - r * vec_per_row;
+            const int u = r / rows_per, pos = r - u * rows_per;
+            const int bu = PAIR ? (u ? base_of[lpb - 1] : base_of[0]) : base_of[0];
             float* dst = s_qkv + (size_t)r * ld + v * 4;
-            if (r < L) cp_async16(dst, qkv + (size_t)(base + r * stride) * C3 + v * 4);
+            if (pos < L && bu >= 0) cp_async16(dst, qkv + (size_t)(bu + pos * stride) * C3 + v * 4);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int i = lane >> 1, jh = lane & 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, tq = lane & 3;
     const float scale = rsqrtf((float)HD);
-    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
-        const float* sq = s_qkv + (size_t)i * ld + h * HD;
-        const float* sk = s_qkv + C + h * HD + (size_t)(jh * 8) * ld;
-        const float* sv = s_qkv + 2 * C + h * HD + jh * (HD / 2);
-        float sc[8];
+    // per-warp scratch for the probability tile (C-fragment layout -> A-fragment layout of the second product)
+    float* s_p = s_qkv + (size_t)kMaxLine * ld + warp * (16 * 20);
+    for (int h = warp; h < heads; h += blockDim.x >> 5) {
+        const float* sq = s_qkv + h * HD;
+        const float* sk = s_qkv + C + h * HD;
+        const float* sv = s_qkv + 2 * C + h * HD;
+        // ---- S = Q K^T (16 x 16, K = HD) on mma.sync m16n8k8 with split operands x = hi + lo (both tf32): hi*hi + hi*lo +
+        // lo*hi carries ~21 mantissa bits per product, fp32 accumulate - the result is fp32-accurate ----
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int kk = 0; kk < HD / 8; ++kk) {
+            uint32_t ah[4], al[4];
+            split_tf32(sq[(size_t)g * ld + 8 * kk + tq], ah[0], al[0]);
+            split_tf32(sq[(size_t)(g + 8) * ld + 8 * kk + tq], ah[1], al[1]);
+            split_tf32(sq[(size_t)g * ld + 8 * kk + tq + 4], ah[2], al[2]);
+            split_tf32(sq[(size_t)(g + 8) * ld + 8 * kk + tq + 4], ah[3], al[3]);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) sc[jj] = 0.f;
-#pragma unroll 4
-        for (int d = 0; d < HD; d += 4) {
-            const float4 q = *reinterpret_cast<const float4*>(sq + d);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const float4 k = *reinterpret_cast<const float4*>(sk + (size_t)jj * ld + d);
-                sc[jj] = fmaf(q.x, k.x, fmaf(q.y, k.y, fmaf(q.z, k.z, fmaf(q.w, k.w, sc[jj]))));
+            for (int nt = 0; nt < 2; ++nt) {
+                uint32_t bh[2], bl[2];
+                split_tf32(sk[(size_t)(g + 8 * nt) * ld + 8 * kk + tq], bh[0], bl[0]);
+                split_tf32(sk[(size_t)(g + 8 * nt) * ld + 8 * kk + tq + 4], bh[1], bl[1]);
+                float (&acc)[4] = nt ? s1 : s0;
+                mma_tf32_1688(acc, al, bh[0], bh[1]);
+                mma_tf32_1688(acc, ah, bl[0], bl[1]);
+                mma_tf32_1688(acc, ah, bh[0], bh[1]);
             }
         }
+        // thread holds rows g, g+8; keys {2tq, 2tq+1} (s0) and {8+2tq, 9+2tq} (s1)
         // reference order (cuboid_transformer.py:849-861): q * scale, then q k^T, + bias, softmax
-        float mx = -INFINITY;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int j = jh * 8 + jj;
-            if (j < L && i < L) sc[jj] = sc[jj] * scale + __ldg(bias_table + (i - j + L - 1) * heads + h);
-            else sc[jj] = -INFINITY;
-            mx = fmaxf(mx, sc[jj]);
-        }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        if (mx == -INFINITY) mx = 0.f;
-        float sum = 0.f;
+        for (int rh = 0; rh < 2; ++rh) {
+            const int i = g + 8 * rh;
+            const int iu = i / rows_per, ip = i - iu * rows_per;   // (line of the pair, position) of the query slot
+            float v[4] = {s0[2 * rh], s0[2 * rh + 1], s1[2 * rh], s1[2 * rh + 1]};
+            const int j[4] = {2 * tq, 2 * tq + 1, 8 + 2 * tq, 9 + 2 * tq};
+            float mx = -INFINITY;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            sc[jj] = expf(sc[jj] - mx);
-            sum += sc[jj];
-        }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        const float inv = sum > 0.f ? 1.f / sum : 0.f;
-        float p[16];   // the full probability row of query i, key order
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const float mine = sc[jj] * inv;
-            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            p[jj] = jh ? other : mine;
-            p[8 + jj] = jh ? mine : other;
-        }
-        float4 acc[HD / 8];
-#pragma unroll
-        for (int dd = 0; dd < HD / 8; ++dd) acc[dd] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float pj = p[j];
-#pragma unroll
-            for (int dd = 0; dd < HD / 8; ++dd) {
-                const float4 v = *reinterpret_cast<const float4*>(sv + (size_t)j * ld + 4 * dd);
-                acc[dd].x = fmaf(pj, v.x, acc[dd].x); acc[dd].y = fmaf(pj, v.y, acc[dd].y);
-                acc[dd].z = fmaf(pj, v.z, acc[dd].z); acc[dd].w = fmaf(pj, v.w, acc[dd].w);
+            for (int k = 0; k < 4; ++k) {
+                const int ju = j[k] / rows_per, jp = j[k] - ju * rows_per;
+                if (ju == iu && jp < L && ip < L) v[k] = v[k] * scale + __ldg(bias_table + (ip - jp + L - 1) * heads + h);
+                else v[k] = -INFINITY;
+                mx = fmaxf(mx, v[k]);
             }
-        }
-        if (i < L) {
-            float4* o = reinterpret_cast<float4*>(out + (size_t)(base + i * stride) * C + h * HD + jh * (HD / 2));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            if (mx == -INFINITY) mx = 0.f;
+            float sum = 0.f;
 #pragma unroll
-            for (int dd = 0; dd < HD / 8; ++dd)
-                o[dd] = make_float4(tf32_rna(acc[dd].x), tf32_rna(acc[dd].y), tf32_rna(acc[dd].z), tf32_rna(acc[dd].w));
+            for (int k = 0; k < 4; ++k) {
+                v[k] = expf(v[k] - mx);
+                sum += v[k];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = sum > 0.f ? 1.f / sum : 0.f;
+            float* pr = s_p + i * 20;
+            *reinterpret_cast<float2*>(pr + 2 * tq) = make_float2(v[0] * inv, v[1] * inv);
+            *reinterpret_cast<float2*>(pr + 8 + 2 * tq) = make_float2(v[2] * inv, v[3] * inv);
+        }
+        __syncwarp();
+        // ---- O = P V (16 x HD, K = 16 keys), same split ----
+        uint32_t ph[2][4], pl[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            split_tf32(s_p[g * 20 + 8 * ks + tq], ph[ks][0], pl[ks][0]);
+            split_tf32(s_p[(g + 8) * 20 + 8 * ks + tq], ph[ks][1], pl[ks][1]);
+            split_tf32(s_p[g * 20 + 8 * ks + tq + 4], ph[ks][2], pl[ks][2]);
+            split_tf32(s_p[(g + 8) * 20 + 8 * ks + tq + 4], ph[ks][3], pl[ks][3]);
+        }
+        __syncwarp();   // the scratch tile is free for the next head
+        // slot rows g and g + 8 -> (line, position) -> token
+        const int u_lo = g / rows_per, p_lo = g - u_lo * rows_per, u_hi = (g + 8) / rows_per, p_hi = g + 8 - u_hi * rows_per;
+        const int b_lo = base_of[0], b_hi = base_of[lpb - 1];   // rows 0-7 / 8-15 (the same line unless PAIR)
+        const bool ok_lo = p_lo < L && b_lo >= 0, ok_hi = p_hi < L && b_hi >= 0;
+        float* o_lo = out + (size_t)((ok_lo ? b_lo : 0) + p_lo * stride) * C + h * HD + 2 * tq;
+        float* o_hi = out + (size_t)((ok_hi ? b_hi : 0) + p_hi * stride) * C + h * HD + 2 * tq;
+#pragma unroll 2
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t bh[2], bl[2];
+                split_tf32(sv[(size_t)(8 * ks + tq) * ld + 8 * nt + g], bh[0], bl[0]);
+                split_tf32(sv[(size_t)(8 * ks + tq + 4) * ld + 8 * nt + g], bh[1], bl[1]);
+                mma_tf32_1688(o, pl[ks], bh[0], bh[1]);
+                mma_tf32_1688(o, ph[ks], bl[0], bl[1]);
+                mma_tf32_1688(o, ph[ks], bh[0], bh[1]);
+            }
+            if (ok_lo) *reinterpret_cast<float2*>(o_lo + 8 * nt) = make_float2(tf32_rna(o[0]), tf32_rna(o[1]));
+            if (ok_hi) *reinterpret_cast<float2*>(o_hi + 8 * nt) = make_float2(tf32_rna(o[2]), tf32_rna(o[3]));
         }
     }
 }
@@ -557,17 +607,24 @@ int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int
     if (f32) {
         const float* qkv = static_cast<const float*>(qkv_v);
         float* out = static_cast<float*>(out_v);
-        const size_t smem = (size_t)kMaxLine * (3 * C + 4) * sizeof(float);
+        const size_t smem = (size_t)kMaxLine * (3 * C + 4) * sizeof(float) + (size_t)(threads / 32) * 16 * 20 * sizeof(float);
         PD_CHECK(smem <= 200 * 1024, PD_ERR_SHAPE, "axial_attention (fp32): line of %zu bytes does not fit in smem", smem);
 #define PD_LAUNCH_AXF(HDV)                                                                                              \
     do {                                                                                                                \
         static bool attr_set = false;                                                                                   \
         if (!attr_set) {                                                                                                \
-            PD_CUDA(cudaFuncSetAttribute(axial_attention_f32_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+            PD_CUDA(cudaFuncSetAttribute(axial_attention_f32_kernel<HDV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         200 * 1024));                                                                  \
+            PD_CUDA(cudaFuncSetAttribute(axial_attention_f32_kernel<HDV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                          200 * 1024));                                                                  \
             attr_set = true;                                                                                            \
         }                                                                                                               \
-        PD_LAUNCH((axial_attention_f32_kernel<HDV>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, axis); \
+        if (L <= 8)                                                                                                     \
+            PD_LAUNCH((axial_attention_f32_kernel<HDV, true>), (lines + 1) / 2, threads, smem, st, qkv, bias_table, out, T, H, W, \
+                      C, heads, axis, lines);                                                                           \
+        else                                                                                                            \
+            PD_LAUNCH((axial_attention_f32_kernel<HDV, false>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C,   \
+                      heads, axis, lines);                                                                              \
     } while (0)
         switch (hd) {
             case 16: PD_LAUNCH_AXF(16); break;
