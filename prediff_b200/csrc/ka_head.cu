@@ -11,15 +11,20 @@ namespace {
 constexpr int kMaxTok = 96;
 
 // tok[f][0][c] = mean_p o[f][p][c] + pos[0][c]; tok[f][1+p][c] = o[f][p][c] + pos[1+p][c], o = silu(GN(x)).
-// One block per frame; thread = channel (coalesced rows).
-__global__ void __launch_bounds__(256) ka_tokens_kernel(const float* __restrict__ x, const double* __restrict__ sums,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        const float* __restrict__ pos /*[1+R][C]*/, bf16* __restrict__ tok,
-                                                        int R, int C, int G, float eps) {
+// One block per frame; thread = (token group, channel): kTokGroups groups walk the tokens interleaved (coalesced rows), their
+// partial sums of the mean token are combined in group order (deterministic). (One group per frame - 24 blocks of 256 threads,
+// each thread a serial walk over all tokens - took 41 us)
+constexpr int kTokGroups = 4;
+__global__ void __launch_bounds__(256 * kTokGroups) ka_tokens_kernel(const float* __restrict__ x, const double* __restrict__ sums,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const float* __restrict__ pos /*[1+R][C]*/,
+                                                                     bf16* __restrict__ tok, int R, int C, int G, float eps) {
+    extern __shared__ float s_acc[];   // [kTokGroups][C]
     const int f = blockIdx.x;
+    const int tg = threadIdx.x / 256, c0 = threadIdx.x % 256;
     const int cpg = C / G;
     const double n = (double)R * cpg;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = c0; c < C; c += 256) {
         const int g = c / cpg;
         const double m = sums[((size_t)f * G + g) * 2] / n;
         double var = sums[((size_t)f * G + g) * 2 + 1] / n - m * m;
@@ -29,43 +34,56 @@ __global__ void __launch_bounds__(256) ka_tokens_kernel(const float* __restrict_
         const float* xp = x + (size_t)f * R * C + c;
         bf16* tp = tok + (size_t)f * (R + 1) * C + c;
         float acc = 0.f;
-        for (int p = 0; p < R; ++p) {
+        for (int p = tg; p < R; p += kTokGroups) {
             const float u = fmaf(xp[(size_t)p * C], sc, sh);
             const float o = u / (1.0f + __expf(-u));
             acc += o;
             tp[(size_t)(p + 1) * C] = __float2bfloat16_rn(o + pos[(size_t)(p + 1) * C + c]);
         }
-        tp[0] = __float2bfloat16_rn(acc / (float)R + pos[c]);
+        s_acc[tg * C + c] = acc;
+    }
+    __syncthreads();
+    if (tg == 0) {
+        for (int c = c0; c < C; c += 256) {
+            float acc = s_acc[c];
+#pragma unroll
+            for (int k = 1; k < kTokGroups; ++k) acc += s_acc[k * C + c];
+            tok[(size_t)f * (R + 1) * C + c] = __float2bfloat16_rn(acc / (float)R + pos[c]);
+        }
     }
 }
 
-// One block per frame, one warp per head. qkv fp32 [F][L][3C] (q | k | v, head-major channels).
+// One block per frame, kSub warps per head (the tokens of a head interleaved over them; partial results combined in warp
+// order: deterministic). qkv fp32 [F][L][3C] (q | k | v, head-major channels).
 // w = softmax_s(scale^2 q0 . k_s); a = sum_s w_s v_s; out[f] = cw . a + cb. Saves w for the backward.
-__global__ void __launch_bounds__(256) ka_pool_kernel(const float* __restrict__ qkv, const float* __restrict__ cw, float cb,
-                                                      float* __restrict__ wsave, float* __restrict__ out, int L, int C,
-                                                      int heads) {
+constexpr int kSub = 4;
+__global__ void __launch_bounds__(32 * 8 * kSub) ka_pool_kernel(const float* __restrict__ qkv, const float* __restrict__ cw,
+                                                                float cb, float* __restrict__ wsave, float* __restrict__ out,
+                                                                int L, int C, int heads) {
     __shared__ float s_w[8][kMaxTok];
+    __shared__ float s_a[8][kSub][128];
     __shared__ float s_part[8];
     const int f = blockIdx.x;
-    const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int h = wid / kSub, sub = wid - h * kSub;   // blockDim = 32 * kSub * heads
     const int ch = C / heads;
     const float scale2 = rsqrtf((float)ch);   // (1/sqrt(sqrt(ch)))^2, models.py:37
     const float* base = qkv + (size_t)f * L * 3 * C;
-    float part = 0.f;
-    if (h < heads) {
-        float q[4];
-        for (int i = 0; i < 4; ++i) q[i] = (lane + 32 * i < ch) ? base[h * ch + lane + 32 * i] : 0.f;
+    float q[4];
+    for (int i = 0; i < 4; ++i) q[i] = (lane + 32 * i < ch) ? base[h * ch + lane + 32 * i] : 0.f;
+    for (int s = sub; s < L; s += kSub) {
+        const float* k = base + (size_t)s * 3 * C + C + h * ch;
+        float d = 0.f;
+        for (int i = 0; i < 4; ++i)
+            if (lane + 32 * i < ch) d = fmaf(q[i], k[lane + 32 * i], d);
+        d = warp_sum(d) * scale2;
+        if (lane == 0) s_w[h][s] = d;
+    }
+    __syncthreads();
+    if (sub == 0) {   // softmax over the head's L logits
         float mx = -INFINITY;
-        for (int s = 0; s < L; ++s) {
-            const float* k = base + (size_t)s * 3 * C + C + h * ch;
-            float d = 0.f;
-            for (int i = 0; i < 4; ++i)
-                if (lane + 32 * i < ch) d = fmaf(q[i], k[lane + 32 * i], d);
-            d = warp_sum(d) * scale2;
-            if (lane == 0) s_w[h][s] = d;
-            mx = fmaxf(mx, d);
-        }
-        __syncwarp();
+        for (int s = lane; s < L; s += 32) mx = fmaxf(mx, s_w[h][s]);
+        mx = warp_max(mx);
         float sum = 0.f;
         for (int s = lane; s < L; s += 32) {
             const float e = __expf(s_w[h][s] - mx);
@@ -74,18 +92,29 @@ __global__ void __launch_bounds__(256) ka_pool_kernel(const float* __restrict__ 
         }
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
-        __syncwarp();
         for (int s = lane; s < L; s += 32) {
             const float w = s_w[h][s] * inv;
             s_w[h][s] = w;
             wsave[((size_t)f * heads + h) * L + s] = w;
         }
-        __syncwarp();
+    }
+    __syncthreads();
+    for (int i = 0; i < 4; ++i) {
+        const int d = lane + 32 * i;
+        float a = 0.f;
+        if (d < ch)
+            for (int s = sub; s < L; s += kSub) a = fmaf(s_w[h][s], base[(size_t)s * 3 * C + 2 * C + h * ch + d], a);
+        if (d < 128) s_a[h][sub][d] = a;
+    }
+    __syncthreads();
+    if (sub == 0) {
+        float part = 0.f;
         for (int i = 0; i < 4; ++i) {
             const int d = lane + 32 * i;
             if (d < ch) {
-                float a = 0.f;
-                for (int s = 0; s < L; ++s) a = fmaf(s_w[h][s], base[(size_t)s * 3 * C + 2 * C + h * ch + d], a);
+                float a = s_a[h][0][d];
+#pragma unroll
+                for (int k = 1; k < kSub; ++k) a += s_a[h][k][d];
                 part = fmaf(cw[h * ch + d], a, part);
             }
         }
@@ -122,14 +151,16 @@ __global__ void ka_loss_grad_kernel(const float* __restrict__ out, const float* 
     for (int i = threadIdx.x; i < B * T; i += blockDim.x) dout[i] = s_diff[i / T] * inv;
 }
 
-// Backward of ka_pool: dqkv bf16 [F][L][3C] (dq is non-zero for token 0 only).
-__global__ void __launch_bounds__(256) ka_pool_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ cw,
-                                                          const float* __restrict__ wsave, const float* __restrict__ dout,
-                                                          bf16* __restrict__ dqkv, int L, int C, int heads) {
+// Backward of ka_pool: dqkv bf16 [F][L][3C] (dq is non-zero for token 0 only). Same block shape as ka_pool_kernel: kSub warps per
+// head share the tokens; the two reductions over tokens (dot, dq) are combined in warp order.
+__global__ void __launch_bounds__(32 * 8 * kSub) ka_pool_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ cw,
+                                                                    const float* __restrict__ wsave, const float* __restrict__ dout,
+                                                                    bf16* __restrict__ dqkv, int L, int C, int heads) {
     __shared__ float s_dl[8][kMaxTok];
+    __shared__ float s_dq[8][kSub][128];
     const int f = blockIdx.x;
-    const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
-    if (h >= heads) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int h = wid / kSub, sub = wid - h * kSub;
     const int ch = C / heads;
     const float scale2 = rsqrtf((float)ch);
     const float* base = qkv + (size_t)f * L * 3 * C;
@@ -142,33 +173,48 @@ __global__ void __launch_bounds__(256) ka_pool_bwd_kernel(const float* __restric
         da[i] = d < ch ? go * cw[h * ch + d] : 0.f;
         q[i] = d < ch ? base[h * ch + d] : 0.f;
     }
-    // dw_s = da . v_s ; dot = sum_s w_s dw_s
-    float dot = 0.f;
-    for (int s = 0; s < L; ++s) {
+    // dw_s = da . v_s
+    for (int s = sub; s < L; s += kSub) {
         const float* v = base + (size_t)s * 3 * C + 2 * C + h * ch;
         float d = 0.f;
         for (int i = 0; i < 4; ++i)
             if (lane + 32 * i < ch) d = fmaf(da[i], v[lane + 32 * i], d);
         d = warp_sum(d);
         if (lane == 0) s_dl[h][s] = d;
-        dot = fmaf(w[s], d, dot);
     }
-    __syncwarp();
-    for (int s = lane; s < L; s += 32) s_dl[h][s] = w[s] * (s_dl[h][s] - dot) * scale2;   // d logit_s * scale^2
-    __syncwarp();
+    __syncthreads();
+    // dot = sum_s w_s dw_s, in token order on every warp of the head (identical values)
+    float dot = 0.f;
+    for (int s = 0; s < L; ++s) dot = fmaf(w[s], s_dl[h][s], dot);
+    __syncthreads();
+    if (sub == 0)
+        for (int s = lane; s < L; s += 32) s_dl[h][s] = w[s] * (s_dl[h][s] - dot) * scale2;   // d logit_s * scale^2
+    __syncthreads();
     for (int i = 0; i < 4; ++i) {
         const int d = lane + 32 * i;
-        if (d >= ch) continue;
         float dq = 0.f;
-        for (int s = 0; s < L; ++s) {
-            const float dl = s_dl[h][s];
-            dq = fmaf(dl, base[(size_t)s * 3 * C + C + h * ch + d], dq);
-            bf16* o = obase + (size_t)s * 3 * C + h * ch + d;
-            if (s > 0) o[0] = __float2bfloat16_rn(0.f);
-            o[C] = __float2bfloat16_rn(dl * q[i]);
-            o[2 * C] = __float2bfloat16_rn(w[s] * da[i]);
+        if (d < ch) {
+            for (int s = sub; s < L; s += kSub) {
+                const float dl = s_dl[h][s];
+                dq = fmaf(dl, base[(size_t)s * 3 * C + C + h * ch + d], dq);
+                bf16* o = obase + (size_t)s * 3 * C + h * ch + d;
+                if (s > 0) o[0] = __float2bfloat16_rn(0.f);
+                o[C] = __float2bfloat16_rn(dl * q[i]);
+                o[2 * C] = __float2bfloat16_rn(w[s] * da[i]);
+            }
         }
-        obase[h * ch + d] = __float2bfloat16_rn(dq);
+        if (d < 128) s_dq[h][sub][d] = dq;
+    }
+    __syncthreads();
+    if (sub == 0) {
+        for (int i = 0; i < 4; ++i) {
+            const int d = lane + 32 * i;
+            if (d >= ch) continue;
+            float dq = s_dq[h][0][d];
+#pragma unroll
+            for (int k = 1; k < kSub; ++k) dq += s_dq[h][k][d];
+            obase[h * ch + d] = __float2bfloat16_rn(dq);
+        }
     }
 }
 
@@ -204,7 +250,7 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
 int ka_tokens(const float* x, const double* sums, const float* gamma, const float* beta, const float* pos_tc, bf16* tok,
               int F, int R, int C, int G, float eps, cudaStream_t st) {
     PD_CHECK(G > 0 && C % G == 0, PD_ERR_SHAPE, "ka_tokens: C=%d G=%d", C, G);
-    ka_tokens_kernel<<<F, 256, 0, st>>>(x, sums, gamma, beta, pos_tc, tok, R, C, G, eps);
+    ka_tokens_kernel<<<F, 256 * kTokGroups, (size_t)kTokGroups * C * sizeof(float), st>>>(x, sums, gamma, beta, pos_tc, tok, R, C, G, eps);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -213,7 +259,7 @@ int ka_pool(const float* qkv, const float* cw, float cb, float* wsave, float* ou
             cudaStream_t st) {
     PD_CHECK(heads >= 1 && heads <= 8 && C % heads == 0 && C / heads <= 128 && L <= kMaxTok, PD_ERR_SHAPE,
              "ka_pool: C=%d heads=%d L=%d", C, heads, L);
-    ka_pool_kernel<<<F, 32 * heads, 0, st>>>(qkv, cw, cb, wsave, out, L, C, heads);
+    ka_pool_kernel<<<F, 32 * kSub * heads, 0, st>>>(qkv, cw, cb, wsave, out, L, C, heads);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
@@ -230,7 +276,7 @@ int ka_pool_bwd(const float* qkv, const float* cw, const float* wsave, const flo
                 int heads, cudaStream_t st) {
     PD_CHECK(heads >= 1 && heads <= 8 && C % heads == 0 && C / heads <= 128 && L <= kMaxTok, PD_ERR_SHAPE,
              "ka_pool_bwd: C=%d heads=%d L=%d", C, heads, L);
-    ka_pool_bwd_kernel<<<F, 32 * heads, 0, st>>>(qkv, cw, wsave, dout, dqkv, L, C, heads);
+    ka_pool_bwd_kernel<<<F, 32 * kSub * heads, 0, st>>>(qkv, cw, wsave, dout, dqkv, L, C, heads);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
