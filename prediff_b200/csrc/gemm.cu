@@ -778,6 +778,13 @@ int tmap_encode_sw128(CUtensorMap* m, bool is_bf16, int rank, const void* ptr, c
     return PD_OK;
 }
 
+// Tile-shape preference of gemm_make for the ops built from now on (set around the construction of a plan): 0 = fill the
+// machine (narrow tiles when a wide one would leave more than half of the SMs idle), 1 = widest tile that divides N - for a
+// network that runs BESIDE another one (the knowledge-alignment net next to the UNet): a 128 x 32 tcgen05.mma costs the same
+// ~128 cycles as 128 x 256, so the wide tile has the same latency on 8 x fewer SMs.
+static int g_tile_pref = 0;
+void gemm_set_tile_preference(int wide) { g_tile_pref = wide; }
+
 int gemm_split_flags_needed(const GemmGeom& g, int N, int force_split) {
     const int out_D = g.out_D ? g.out_D : g.D;
     const int num_k = g.ntaps * (g.C / g.kblk());
@@ -866,7 +873,7 @@ int gemm_make(GemmOp* op, const void* A, const GemmGeom& g, const void* Wt, int 
         for (int c : cands) {
             if (N % c != 0 || (e.out_bf16 && c < 64)) continue;
             if (c >= 64 || !smallest) smallest = c;
-            if ((int64_t)m_tiles * (N / c) >= kNumSMs / 2) { bn = c; break; }
+            if ((int64_t)m_tiles * (N / c) >= kNumSMs / 2 || g_tile_pref == 1) { bn = c; break; }
         }
         if (!bn) bn = smallest;
     }

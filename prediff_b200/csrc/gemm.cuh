@@ -158,6 +158,7 @@ struct GemmOp {
 int gemm_make(GemmOp* op, const void* A, const GemmGeom& g, const void* Wt, int N, const GemmEpilogue& e,
               int force_block_n = 0);
 int gemm_launch(const GemmOp& op, cudaStream_t stream);
+void gemm_set_tile_preference(int wide);   // see gemm.cu
 // Points an already-built op at new output / residual buffers of the same shape (per-call user pointers).
 int gemm_bind_output(GemmOp* op, float* out_f32, bf16* out_bf16, const float* residual);
 // Number of ints gemm_make may need in GemmEpilogue::split_flags for this geometry (0 if it will not split).

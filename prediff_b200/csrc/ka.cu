@@ -3,6 +3,7 @@
 // (AttentionPool3d), sevir.py:55-104 (alignment_fn / get_mean_shift), alignment_pl.py:423-446 (autograd.grad).
 // The trunk is the same kernel set as the UNet encoder half (gemm.cu / norm.cu / attention.cu); the backward
 // runs every GEMM as a dgrad with transposed (Linear) or tap-reversed (Conv3d) weights packed once at finalize.
+#include <cstdlib>
 #include "ka.cuh"
 
 namespace pd {
@@ -321,6 +322,11 @@ void KANet::carve(A& ar, int B, Bufs* b) const {
 }
 
 int KANet::build_plan(int B, BatchPlan* bp) {
+    // wide GEMM tiles: the guidance runs beside the UNet and should hold as few SMs as it can (gemm.cu)
+    struct TilePref {
+        TilePref() { gemm_set_tile_preference(getenv("PD_KA_NARROW_TILES") ? 0 : 1); }
+        ~TilePref() { gemm_set_tile_preference(0); }
+    } tile_pref;
     ArenaSizer sz;
     {
         Bufs tmp;
