@@ -662,10 +662,17 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.scope = "first";
         pl.add([=](cudaStream_t st) { return gn_stats(xin, s1, B, R0, kCinPad, kCinPad, st); }, "gn_stats");
         pl.add([=](cudaStream_t st) { return gn_apply(xin, s1, r.gn1_w, r.gn1_b, a, B, R0, kCinPad, kCinPad, 1e-5f, 1, st, prec); }, "gn_apply");
+        bool h_stats = false;
         {
             GemmEpilogue e;
             e.bias = r.conv1_b;
             e.out_f32 = h;
+            if (gn_fusion_on() && !prec && gemm_gn_fusable(C0, 32, R0)) {   // statistics of h for the second GroupNorm
+                e.gn_sums = s2;
+                e.gn_groups = 32;
+                e.gn_rows = R0;
+                h_stats = true;
+            }
             GemmOp op;
             PD_TRY(gemm_make(&op, a, geom(GemmGeom::conv(B, T, H, W, kCinPad, 3, 3, 3)), r.conv1_w, C0, e));
             pl.add_gemm(op, "conv1");
@@ -678,7 +685,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             PD_TRY(gemm_make(&op, b.xin_bf16, geom(GemmGeom::conv(B, T, H, W, kCinPad, 1, 1, 1)), first_skip_w, C0, e));
             pl.add_gemm(op, "skip");
         }
-        pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R0, c0, 32, st); }, "gn_stats");
+        if (!h_stats) pl.add([=](cudaStream_t st) { return gn_stats(h, s2, B, R0, c0, 32, st); }, "gn_stats");
         pl.add([=](cudaStream_t st) { return gn_apply(h, s2, r.gn2_w, r.gn2_b, a, B, R0, c0, 32, 1e-5f, 1, st, prec); }, "gn_apply");
         {
             GemmEpilogue e;
