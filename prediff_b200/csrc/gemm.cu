@@ -374,6 +374,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         const float mean = tot1 * inv_n;
                         const float var = fmaxf(tot2 * inv_n - mean * mean, 0.f);
                         const float rstd = rsqrtf(var + p.ln_eps);
+                        if (p.tf32) {
+                            // tf32 operands: the normalised rows are the next GEMM's fp32 operand - formed in place in the fp32
+                            // slabs once the bulk stores of x have read them, rounded to tf32, stored through the fp32 map
+                            if (lane == 0) ptx::bulk_wait_read<0>();
+                            __syncwarp();
+#pragma unroll
+                            for (int idx = 0; idx < kPerHalf; ++idx) {
+                                uint8_t* frow = slabs + idx * 4096 + lane * 128;
+                                const int colbase = (c_begin + idx) * 32;
+                                float4 av[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    av[i] = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(i) ^ sw) << 4));
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 g0 = *reinterpret_cast<const float4*>(ln_g + colbase + 4 * i);
+                                    const float4 b0 = *reinterpret_cast<const float4*>(ln_b + colbase + 4 * i);
+                                    float4 o;
+                                    o.x = tf32_rna(fmaf((av[i].x - mean) * rstd, g0.x, b0.x));
+                                    o.y = tf32_rna(fmaf((av[i].y - mean) * rstd, g0.y, b0.y));
+                                    o.z = tf32_rna(fmaf((av[i].z - mean) * rstd, g0.z, b0.z));
+                                    o.w = tf32_rna(fmaf((av[i].w - mean) * rstd, g0.w, b0.w));
+                                    *reinterpret_cast<float4*>(frow + ((static_cast<uint32_t>(i) ^ sw) << 4)) = o;
+                                }
+                            }
+                            ptx::fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+#pragma unroll
+                                for (int idx = 0; idx < kPerHalf; ++idx)
+                                    ptx::tma_store_3d(&tmap_ln, slabs + idx * 4096, n0 + (c_begin + idx) * 32, row0, sample);
+                                ptx::bulk_commit();
+                            }
+                        } else {
                         uint8_t* bslabs = smem + kEpiWarps * kPerHalf * 4096 + e * (kBf * 4096);   // kBf bf16 slabs per warp
 #pragma unroll
                         for (int j = 0; j < kBf; ++j) {        // bf16 slab j = my fp32 chunks 2j, 2j+1 (64 columns)
@@ -406,6 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             for (int j = 0; j < kBf; ++j)
                                 ptx::tma_store_3d(&tmap_ln, bslabs + j * 4096, n0 + (c_begin + 2 * j) * 32, row0, sample);
                             ptx::bulk_commit();
+                        }
                         }
                     }
                 }
@@ -800,8 +835,8 @@ int gemm_make(GemmOp* op, const void* A, const GemmGeom& g, const void* Wt, int 
     const int esz = g.tf32 ? 4 : 2;   // operand element size
     const CUtensorMapDataType op_dtype = g.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     PD_CHECK(g.C > 0 && g.C % kblk == 0, PD_ERR_SHAPE, "gemm: channels per tap (%d) must be a multiple of %d", g.C, kblk);
-    PD_CHECK(!g.tf32 || (!e.out_bf16 && !e.ln_out), PD_ERR_ARG,
-             "gemm: tf32 operands go with fp32 outputs only (no bf16 output, no fused bf16 LayerNorm output)");
+    PD_CHECK(!g.tf32 || !e.out_bf16, PD_ERR_ARG,
+             "gemm: tf32 operands go with fp32 outputs only (the fused LayerNorm output is then fp32 rounded to tf32)");
     PD_CHECK(N > 0 && N % 32 == 0, PD_ERR_SHAPE, "gemm: N (%d) must be a multiple of 32", N);
     PD_CHECK(g.ntaps >= 1 && g.ntaps <= kMaxTaps, PD_ERR_SHAPE, "gemm: ntaps %d out of range", g.ntaps);
     PD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0, PD_ERR_ARG,
@@ -945,10 +980,13 @@ int gemm_make(GemmOp* op, const void* A, const GemmGeom& g, const void* Wt, int 
     op->tmap_ln = op->tmap_out;
     if (want_ln) {
         cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows_per_sample, (cuuint64_t)g.samples};
-        cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * 2 * rows_per_sample};
-        cuuint32_t box[3] = {64, 32, 1};
+        // bf16 operands: ln_out is bf16 [M][N]; tf32 operands: the same pointer holds fp32 (rounded to tf32), boxes of 32 columns
+        const cuuint64_t lsz = g.tf32 ? 4 : 2;
+        cuuint64_t strides[2] = {(cuuint64_t)N * lsz, (cuuint64_t)N * lsz * rows_per_sample};
+        cuuint32_t box[3] = {g.tf32 ? 32u : 64u, 32, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = g_encode(&op->tmap_ln, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, e.ln_out, dims, strides, box, es,
+        CUresult r = g_encode(&op->tmap_ln, g.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                              e.ln_out, dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         PD_CHECK(r == CUDA_SUCCESS, PD_ERR_CUDA, "cuTensorMapEncodeTiled(ln) failed: %d", (int)r);

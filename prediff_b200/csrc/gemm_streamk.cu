@@ -307,6 +307,38 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float mean = (ln_s1 + o.x) * (1.0f / BN);
                 const float var = fmaxf((ln_s2 + o.y) * (1.0f / BN) - mean * mean, 0.f);
                 const float rstd = rsqrtf(var + p.ln_eps);
+                if (p.tf32) {   // fp32 (tf32-rounded) operand for the next GEMM, formed in place in the fp32 slabs (see gemm.cu)
+                    if (lane == 0) ptx::bulk_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int idx = 0; idx < 4; ++idx) {
+                        uint8_t* frow = slabs + idx * 4096 + lane * 128;
+                        const int colbase = (c_begin + idx) * 32;
+                        float4 av[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            av[i] = *reinterpret_cast<const float4*>(frow + ((static_cast<uint32_t>(i) ^ sw) << 4));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 g0 = *reinterpret_cast<const float4*>(ln_g + colbase + 4 * i);
+                            const float4 b0 = *reinterpret_cast<const float4*>(ln_b + colbase + 4 * i);
+                            float4 o;
+                            o.x = tf32_rna(fmaf((av[i].x - mean) * rstd, g0.x, b0.x));
+                            o.y = tf32_rna(fmaf((av[i].y - mean) * rstd, g0.y, b0.y));
+                            o.z = tf32_rna(fmaf((av[i].z - mean) * rstd, g0.z, b0.z));
+                            o.w = tf32_rna(fmaf((av[i].w - mean) * rstd, g0.w, b0.w));
+                            *reinterpret_cast<float4*>(frow + ((static_cast<uint32_t>(i) ^ sw) << 4)) = o;
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int idx = 0; idx < 4; ++idx)
+                            ptx::tma_store_3d(&tmap_ln, slabs + idx * 4096, n0 + (c_begin + idx) * 32, row0, sample);
+                        ptx::bulk_commit();
+                    }
+                } else {
                 uint8_t* bslabs = smem + kEpiWarps * 4 * 4096 + e * (2 * 4096);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -338,6 +370,7 @@ conv_streamk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::tma_store_3d(&tmap_ln, bslabs, n0 + (c_begin + 0) * 32, row0, sample);
                     ptx::tma_store_3d(&tmap_ln, bslabs + 4096, n0 + (c_begin + 2) * 32, row0, sample);
                     ptx::bulk_commit();
+                }
                 }
             }
             if (sgm.n_part > 0) {   // re-arm the tile's flag for the next launch

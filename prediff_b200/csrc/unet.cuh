@@ -80,12 +80,13 @@ private:
     // The LayerNorm that follows a GEMM is computed in that GEMM's epilogue when a CTA (width 256) or a 2-CTA cluster
     // (width 512) owns whole rows; the resblock's conv2 only when it is not split-K (27 * C / 64 < 128 k-blocks).
     bool ln_fusable(int lvl) const {
-        if (precision) return false;   // the fused LayerNorm epilogue writes bf16; tf32 mode runs layer_norm launches
+        static const bool no_tf32_ln = getenv("PD_NO_TF32_LN_FUSION") != nullptr;   // A/B: layer_norm launches in tf32 mode
+        if (precision && no_tf32_ln) return false;
         const int c = lvl ? C1 : C0;
         static const bool no_cluster = getenv("PD_NO_LN_CLUSTER") != nullptr;   // A/B: separate LayerNorm launches at 512
         return c == 256 || (c == 512 && !no_cluster);
     }
-    bool ln_fusable_conv(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 && !precision; }
+    bool ln_fusable_conv(int lvl) const { const int c = lvl ? C1 : C0; return c == 256 && (!precision || ln_fusable(lvl)); }
     // GEMM geometry / operand-output helpers for the model's precision
     GemmGeom geom(GemmGeom g) const { g.tf32 = precision; return g; }
     void operand_out(GemmEpilogue& e, bf16* buf) const {
