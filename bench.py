@@ -175,6 +175,31 @@ def cpu_baseline_leg(args, budget_s=25.0):
 CUBOID_GFLOP_PER_SAMPLE_STEP = 252.9   # StackCuboidSelfAttentionBlock incl. FFN
 
 
+def algorithmic_bytes(site, B):
+    """Bytes one launch of a call site must move if every operand is read once and every result written once (shipped
+    config: 13 x 16 x 16 tokens of width 256 at level 0, 13 x 8 x 8 of width 512 at level 1; bf16 operands / weights, fp32
+    residual stream). None for sites without a closed form here. Compared with the measured DRAM bytes in `kernels`:
+    below it when an operand was still in the 126 MB L2, above it when something is re-read from HBM."""
+    lvl = 1 if site.startswith("L1.") else 0
+    M, C = B * 13 * (64 if lvl else 256), (512 if lvl else 256)
+    kind = site.split(".")[-1]
+    act16, act32 = M * C * 2, M * C * 4
+    if kind in ("conv1", "conv2") and site[:2] in ("L0", "L1"):
+        w = 27 * C * C * 2
+        # conv1: a (bf16) + W -> h (fp32); conv2: a + W + residual x -> x (+ the fused bf16 LayerNorm at width 256)
+        return act16 + w + act32 + (act32 + (act16 if C == 256 else 0) if kind == "conv2" else 0)
+    if kind in ("proj_ffn_fused", "proj_ffn_cluster"):
+        w = (C * C + 2 * C * 4 * C) * 2
+        return act16 + w + 2 * act32 + act16          # att + weights + x in / out + next LayerNorm out
+    if kind.startswith("qkv_attn"):
+        return act16 + 3 * C * C * 2 + act16          # ln + Wqkv -> att
+    if kind == "gn_apply" and site[:2] in ("L0", "L1"):
+        return act32 + act16
+    if kind == "ln":
+        return act32 + act16
+    return None
+
+
 def graph_trace(unet, B, x, t, cond, out):
     """One UNet forward replayed as a CUDA graph with a %globaltimer stamp kernel after every launch.
     Returns ({site: [launches, us, flops]}, stamp_slot_us): us = raw stamp-to-stamp interval minus the stamp slot (the
@@ -503,9 +528,9 @@ def main():
                 ent["tflops"] = fl / (us * 1e-6) * 1e-12
                 ent["frac_of_peak"] = ent["tflops"] / peaks["tensor_tflops"]
                 ent["frac_incl_launch_overhead"] = fl / ((us + cnt * per_launch_overhead_us) * 1e-6) * 1e-12 / peaks["tensor_tflops"]
+            ent["algorithmic_bytes_per_launch"] = algorithmic_bytes(name, B)
             if name in dram:
-                ent["dram_bytes_per_launch"] = dram[name].get("dram_bytes")
-                ent["algorithmic_bytes_per_launch"] = dram[name].get("algorithmic_bytes")
+                ent["dram_bytes_per_launch"] = dram[name].get("dram_bytes")   # ncu pass at batch 4 (profiles/kernel_dram_r02.json)
                 ent["kernel"] = dram[name].get("kernel")
             kernels.append(ent)
         g_us = sum(v[1] for k, v in trace.items() if is_gemm(k))
