@@ -246,11 +246,12 @@ def load_json(rel):
     return json.load(open(path)) if os.path.exists(path) else None
 
 
-def build_unet(ucfg, B, precision):
+def build_unet(ucfg, B, precision, streamk_ctas_per_sample=0):
     from prediff_b200.unet import CuboidTransformerUNet
     unet = CuboidTransformerUNet([ucfg.t_in, ucfg.h, ucfg.w, ucfg.c], [ucfg.t_out, ucfg.h, ucfg.w, ucfg.c],
                                  base_units=ucfg.base_units, depth=list(ucfg.depth), num_heads=ucfg.num_heads,
-                                 block_attn_patterns="axial", max_batch=B, precision=precision)
+                                 block_attn_patterns="axial", max_batch=B, precision=precision,
+                                 streamk_ctas_per_sample=streamk_ctas_per_sample)
     unet.load_state_dict({k: torch.from_numpy(v) for k, v in
                           Wt.seeded_state_dict(Wt.unet_param_spec(ucfg), UNET_SEED).items()}, strict=False)
     return unet
@@ -474,6 +475,13 @@ def main():
         extras["trace"] = (trace, slot)
         if rank == 0 and world == 1:
             extras["b1"] = single_step_latency(unet, ucfg, dev)
+            # the same step on a model built for single samples: 72 stream-K CTAs per sample instead of the batch-invariant 36
+            # (pd_unet_set_streamk_ctas; another fixed summation order, so not bit-identical to the batch-4 cut)
+            unet_b1 = build_unet(ucfg, 1, "bf16", streamk_ctas_per_sample=72)
+            extras["b1"]["latency_cut"] = {k: v for k, v in single_step_latency(unet_b1, ucfg, dev).items()
+                                           if k in ("ms", "value", "tflops")}
+            extras["b1"]["latency_cut"]["streamk_ctas_per_sample"] = 72
+            del unet_b1
             if unet_tf32 is not None:
                 extras["b1_tf32"] = single_step_latency(unet_tf32, ucfg, dev, iters=100)
 

@@ -79,6 +79,11 @@ int pd_unet_load_weight(pd_unet* m, const char* name, const float* data, const i
 #define PD_PRECISION_BF16 0
 #define PD_PRECISION_TF32 1
 int pd_unet_set_precision(pd_unet* m, int precision);
+/* CTAs per sample of the stream-K schedule of the long-K convolutions (0 = the default, 36: the same cut for every batch, so
+ * a sample's result is bit-identical whatever batch it runs in - the shard-invariance property of the multi-GPU path). A
+ * model that serves single samples may ask for more (72: 3.45 -> 3.19 ms per batch-1 denoise step); results then differ
+ * from the default cut's in the last bits (another fixed summation order), never between runs. Call before pd_unet_finalize. */
+int pd_unet_set_streamk_ctas(pd_unet* m, int ctas_per_sample);
 /* Repacks all weights into kernel layouts (bf16 or tf32-rounded fp32, K-major, tap-major convs). Fails if any weight is
  * missing. */
 int pd_unet_finalize(pd_unet* m);

@@ -55,6 +55,10 @@ int pd_unet_set_precision(pd_unet* m, int precision) {
     PD_CHECK(m, PD_ERR_ARG, "pd_unet_set_precision: null model");
     return m->impl.set_precision(precision);
 }
+int pd_unet_set_streamk_ctas(pd_unet* m, int ctas_per_sample) {
+    PD_CHECK(m, PD_ERR_ARG, "pd_unet_set_streamk_ctas: null model");
+    return m->impl.set_streamk_ctas(ctas_per_sample);
+}
 int pd_unet_finalize(pd_unet* m) {
     PD_CHECK(m, PD_ERR_ARG, "pd_unet_finalize: null model");
     return m->impl.finalize();

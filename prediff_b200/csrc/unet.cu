@@ -160,6 +160,17 @@ int UNet::set_precision(int prec) {
     return PD_OK;
 }
 
+// CTAs per sample of the stream-K convolutions. The default (36) is what every batch uses, so a sample's result does not depend
+// on the batch it is in (bit-exact shard invariance). A model that only ever serves single samples can trade that property for
+// latency: 72 CTAs per sample fill 72 instead of 36 SMs at batch 1 (3.45 -> 3.19 ms per denoise step, BASELINE.json configs[1]);
+// its results differ from the default cut's in the last bits (another fixed summation order), never between runs.
+int UNet::set_streamk_ctas(int n) {
+    PD_CHECK(n >= 0 && n <= 4 * kNumSMs, PD_ERR_ARG, "unet: %d stream-K CTAs per sample", n);
+    if (n != streamk_cps) finalized = false;   // plans are rebuilt (and the weight generation bumped) by the next finalize
+    streamk_cps = n;
+    return PD_OK;
+}
+
 int UNet::validate() const {
     PD_CHECK(cfg.t_in > 0 && cfg.t_out > 0 && T <= 16, PD_ERR_SHAPE, "unet: t_in + t_out = %d must be <= 16", T);
     PD_CHECK(cfg.h <= 16 && cfg.w <= 16 && cfg.h % 2 == 0 && cfg.w % 2 == 0, PD_ERR_SHAPE,
@@ -380,11 +391,12 @@ int UNet::make_conv(GemmOp* op, const void* a, const GemmGeom& g_in, const void*
         PD_TRY(gemm_make(&sk, a, g, w, N, e, 256));
         std::vector<SkSeg> segs;
         int n_slots = 0, n_flags = 0;
-        if (gemm_streamk_schedule(sk, kStreamKCtasPerSample, &segs, &n_slots, &n_flags) == PD_OK) {
+        const int cps = streamk_cps > 0 ? streamk_cps : kStreamKCtasPerSample;
+        if (gemm_streamk_schedule(sk, cps, &segs, &n_slots, &n_flags) == PD_OK) {
             if (n_slots + 1 > bp->sk_slots) {
                 // grown only while the plan is being built; ops attached earlier keep a stale pointer, so size it once
                 PD_CHECK(bp->sk_slots == 0, PD_ERR_STATE, "unet: stream-K workspace sized twice");
-                bp->sk_slots = kStreamKCtasPerSample * g.samples + 1;
+                bp->sk_slots = cps * g.samples + 1;
                 PD_CHECK(n_slots + 1 <= bp->sk_slots, PD_ERR_STATE, "unet: stream-K slot bound");
                 PD_TRY(bp->sk_partials.alloc((size_t)bp->sk_slots * kGemmBlockM * 256 * sizeof(float)));
             }

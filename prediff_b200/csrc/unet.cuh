@@ -36,7 +36,9 @@ public:
     // Operand precision of every tensor-core GEMM of the model (PD_PRECISION_*): bf16 (default) or tf32 - the
     // reference's own GPU arithmetic (cfg.yaml:32; train_sevirlr_prediff.py:1143). Takes effect at the next finalize().
     int set_precision(int prec);
+    int set_streamk_ctas(int n);
     int precision = 0;
+    int streamk_cps = 0;   // CTAs per sample of the stream-K cut (0 = default, see set_streamk_ctas)
     // t: device int64; if `step` (device int) is given, t is a table and row *step is used (sampler loop)
     // replica: independent workspace index (sub-batches of one call running concurrently on different streams);
     // t_stride: row length of the t table when `step` is given (0 -> B)

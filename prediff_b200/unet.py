@@ -50,15 +50,18 @@ class CuboidTransformerUNet(nn.Module):
                  hierarchical_pos_embed=False, pos_embed_type="t+h+w", padding_type="zeros", checkpoint_level=0,
                  use_relative_pos=True, self_attn_use_final_proj=True, num_global_vectors=0,
                  time_embed_channels_mult=4, time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0,
-                 unet_res_connect=True, max_batch=32, precision=None, **ignored_init_modes):
+                 unet_res_connect=True, max_batch=32, precision=None, streamk_ctas_per_sample=0, **ignored_init_modes):
         """`precision` (not a reference argument): "bf16" (default; env PD_PRECISION overrides the default) or "tf32" -
-        the operand precision of the tensor-core GEMMs, see pd_unet_set_precision in include/prediff_b200.h."""
+        the operand precision of the tensor-core GEMMs, see pd_unet_set_precision in include/prediff_b200.h.
+        `streamk_ctas_per_sample` (not a reference argument): 0 = default cut (batch-invariant results); e.g. 72 for a model
+        that only serves single samples (pd_unet_set_streamk_ctas)."""
         super().__init__()
         import os
         precision = precision or os.environ.get("PD_PRECISION", "bf16")
         if precision not in ("bf16", "tf32"):
             raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
         self.precision = precision
+        self.streamk_ctas_per_sample = int(streamk_ctas_per_sample)
         T_in, H, W, C = input_shape
         T_out, H2, W2, C2 = target_shape
         assert (H, W, C) == (H2, W2, C2)
@@ -163,6 +166,7 @@ class CuboidTransformerUNet(nn.Module):
             shape = (ctypes.c_int64 * t.dim())(*t.shape)
             L.check(lib.pd_unet_load_weight(h, name.encode(), L.ptr(t), shape, t.dim()))
         L.check(lib.pd_unet_set_precision(h, 1 if self.precision == "tf32" else 0))
+        L.check(lib.pd_unet_set_streamk_ctas(h, self.streamk_ctas_per_sample))
         L.check(lib.pd_unet_finalize(h))
         self._dirty = False
 
