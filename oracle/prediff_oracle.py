@@ -145,13 +145,19 @@ def _from_cuboids(y, size, strategy, padded):
     return y.permute(perm + [7]).reshape(B, padded[0], padded[1], padded[2], C)
 
 
-def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_type="zeros"):
-    """The attention core of CuboidSelfAttentionLayer.forward (cuboid_transformer.py:812-966, no global vectors)
+def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_type="zeros", gqkv=None,
+                          global_self_attn=False):
+    """The attention core of CuboidSelfAttentionLayer.forward (cuboid_transformer.py:812-966; global vectors: below)
     from the per-token q|k|v rows: qkv (B, T, H, W, 3C), taken BEFORE padding (qkv has no bias, so the zero rows the
     reference pads after its LayerNorm map to zero q, k, v) -> (B, T, H, W, C) before the final projection.
     Cuboid size / shift update :563-592; zero padding at the end of each axis; roll by -shift; reorder; mask =
     same shifted-window region (and, for 'ignore', both tokens real) :470-528; bias = table[index[:vol, :vol]]
-    with the index built from the constructor's cuboid size :714-734, 855-861; masked_softmax :531-560."""
+    with the index built from the constructor's cuboid size :714-734, 855-861; masked_softmax :531-560.
+    gqkv (B, K, 3C): q|k|v rows of the K global vectors (use_global_vector with the shared global_qkv net, :893-901) ->
+    returns (o, new_global (B, K, C) before global_proj). Local queries see the K global keys as extra, never-masked
+    columns (:902-913); the global queries attend over ALL num_cuboids * volume slots in cuboid order (+ the global keys
+    with global_self_attn), and under 'ignore' padding the slot mask is the padded, rolled validity grid flattened in
+    RASTER order - the reference applies it to the cuboid-ordered keys as it is (:915-945), so does this."""
     B, T, H, W, C3 = qkv.shape
     C, hd = C3 // 3, C3 // 3 // heads
     dims = (T, H, W)
@@ -199,15 +205,52 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
     rel = ((ct[:, None] - ct[None] + bt - 1) * (2 * bh - 1) + (ch[:, None] - ch[None] + bh - 1)) * (2 * bw - 1) \
         + (cw[:, None] - cw[None] + bw - 1)
     s = s + table[rel].permute(2, 0, 1)[:, None]
+    new_g = None
+    if gqkv is not None:
+        K = gqkv.shape[1]
+        gq, gk, gv = gqkv.reshape(B, 1, K, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)   # (B, heads, 1, K, hd)
+        s = torch.cat([s, (q * hd ** -0.5) @ gk.transpose(-1, -2)], dim=-1)          # (B, heads, nc, vol, vol + K)
+        mask = F.pad(mask, (0, K), value=True)
+        v_lg = torch.cat([v, gv.expand(B, heads, nc, K, hd)], dim=3)
+        # global queries over every slot (:928-945)
+        s2 = (gq.squeeze(2) * hd ** -0.5) @ k.reshape(B, heads, nc * vol, hd).transpose(-1, -2)   # (B, heads, K, nc * vol)
+        m2 = real.reshape(-1) > 0 if padding_type == "ignore" else None            # raster order (see the docstring)
+        v2 = v.reshape(B, heads, nc * vol, hd)
+        if global_self_attn:
+            s2 = torch.cat([s2, (gq.squeeze(2) * hd ** -0.5) @ gk.squeeze(2).transpose(-1, -2)], dim=-1)
+            m2 = F.pad(m2, (0, K), value=True) if m2 is not None else None
+            v2 = torch.cat([v2, gv.squeeze(2)], dim=2)
+        if m2 is not None:
+            p2 = torch.softmax(s2.masked_fill(~m2, -1e18), dim=-1) * m2
+        else:
+            p2 = torch.softmax(s2, dim=-1)
+        new_g = (p2 @ v2).permute(0, 2, 1, 3).reshape(B, K, C)
+    else:
+        v_lg = v
     s = s.masked_fill(~mask, -1e18)
     p = torch.softmax(s, dim=-1) * mask
-    o = (p @ v).permute(0, 2, 3, 1, 4).reshape(B, nc, vol, C)
+    o = (p @ v_lg).permute(0, 2, 3, 1, 4).reshape(B, nc, vol, C)
     o = _from_cuboids(o, size, strategy, padded)
     if any(s_ > 0 for s_ in shift):
         o = torch.roll(o, shifts=list(shift), dims=(1, 2, 3))
     if padding_type == "nearest" and any(pad):   # _generalize_unpadding (:261-270): resample back
-        return F.interpolate(o.permute(0, 4, 1, 2, 3), size=(T, H, W)).permute(0, 2, 3, 4, 1).contiguous()
-    return o[:, :T, :H, :W].contiguous()
+        o = F.interpolate(o.permute(0, 4, 1, 2, 3), size=(T, H, W)).permute(0, 2, 3, 4, 1).contiguous()
+    else:
+        o = o[:, :T, :H, :W].contiguous()
+    return o if gqkv is None else (o, new_g)
+
+
+def cuboid_attention_gv(sd, p, x, g, heads, size0, strategy, shift0, padding_type="zeros", global_self_attn=False):
+    """CuboidSelfAttentionLayer.forward with use_global_vector, separate_global_qkv=False (cuboid_transformer.py:812-966):
+    x (B, T, H, W, C), g (B, K, C) -> (x_out, g_out), both BEFORE the residual adds of the stack block."""
+    C = x.shape[-1]
+    y = F.layer_norm(x, (C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
+    gn = F.layer_norm(g, (C,), sd[f"{p}.global_vec_norm.weight"], sd[f"{p}.global_vec_norm.bias"], 1e-5)
+    o, ng = cuboid_attention_core(F.linear(y, sd[f"{p}.qkv.weight"]), sd[f"{p}.relative_position_bias_table"], heads,
+                                  size0, strategy, shift0, padding_type, gqkv=F.linear(gn, sd[f"{p}.global_qkv.weight"]),
+                                  global_self_attn=global_self_attn)
+    return (F.linear(o, sd[f"{p}.proj.weight"], sd[f"{p}.proj.bias"]),
+            F.linear(ng, sd[f"{p}.global_proj.weight"], sd[f"{p}.global_proj.bias"]))
 
 
 def cuboid_attention(sd, p, x, heads, size0, strategy, shift0, padding_type="zeros"):
@@ -221,9 +264,19 @@ def cuboid_attention(sd, p, x, heads, size0, strategy, shift0, padding_type="zer
     return F.linear(o, sd[f"{p}.proj.weight"], sd[f"{p}.proj.bias"])
 
 
-def stack_block(sd, p, x, heads, layers=None, padding_type="zeros"):
+def stack_block(sd, p, x, heads, layers=None, padding_type="zeros", g=None, global_ffn=True, global_self_attn=False):
     """StackCuboidSelfAttentionBlock.forward with use_inter_ffn (cuboid_transformer.py:1147-1156). `layers`: list of
-    (cuboid_size, strategy, shift_size) (None = the axial pattern of the shipped config)."""
+    (cuboid_size, strategy, shift_size) (None = the axial pattern of the shipped config). g (B, K, C): global vectors
+    (:1130-1145) -> returns (x, g)."""
+    if g is not None:
+        for i, (size, strategy, shift) in enumerate(layers):
+            xo, go = cuboid_attention_gv(sd, f"{p}.attn_l.{i}", x, g, heads, size, strategy, shift, padding_type,
+                                         global_self_attn)
+            x, g = x + xo, g + go
+            x = ffn(sd, f"{p}.ffn_l.{i}", x)
+            if global_ffn:
+                g = ffn(sd, f"{p}.global_ffn_l.{i}", g)
+        return x, g
     if layers is None:
         for i in range(3):
             x = x + axial_attention(sd, f"{p}.attn_l.{i}", x, heads, i)
@@ -257,7 +310,8 @@ def unet_forward(sd, cfg, x, t, cond):
     x (B,T_out,H,W,C), t (B,) int64, cond (B,T_in,H,W,C) -> (B,T_out,H,W,C)."""
     heads = cfg.num_heads
     pats = tuple(getattr(cfg, "patterns", ("axial", "axial")))
-    layers = [None if pats[lvl] == "axial" else cfg.layers(lvl) for lvl in range(2)]
+    K = getattr(cfg, "num_global_vectors", 0)
+    layers = [None if pats[lvl] == "axial" and not K else cfg.layers(lvl) for lvl in range(2)]
     x = torch.cat([cond, x], dim=1)
     ind = torch.ones_like(x[..., :1])
     ind[:, cfg.t_in:] = 0.0
@@ -274,19 +328,28 @@ def unet_forward(sd, cfg, x, t, cond):
     e = F.linear(e, sd["time_embed.layer.0.weight"], sd["time_embed.layer.0.bias"])
     t_emb = F.linear(F.silu(e), sd["time_embed.layer.2.weight"], sd["time_embed.layer.2.bias"])
 
+    # global vectors (cuboid_transformer_unet.py:432-434, 449-450, 489-490): carried beside x, projected between levels
+    gvec = [sd["init_global_vectors"].expand(B, K, C) if K else None]
+
     def level(name_t, name_s, lvl, x):
         g = _gn_groups(cfg.units[lvl])
         for d in range(cfg.depth[lvl]):
             x = _res_block3d(sd, f"{name_t}.{lvl}", x.permute(0, 4, 1, 2, 3), t_emb, g, g).permute(0, 2, 3, 4, 1)
-            x = stack_block(sd, f"{name_s}.{lvl}.{d}", x, heads, layers[lvl], getattr(cfg, "padding_type", "zeros"))
+            r = stack_block(sd, f"{name_s}.{lvl}.{d}", x, heads, layers[lvl], getattr(cfg, "padding_type", "zeros"),
+                            gvec[0], getattr(cfg, "use_global_vector_ffn", True), getattr(cfg, "use_global_self_attn", False))
+            x, gvec[0] = r if K else (r, None)
         return x
 
     x = level("down_time_embed_blocks", "down_self_blocks", 0, x)
     skip = x
     x = patch_merge(sd, "downsample_layers.0", x)
+    if K:
+        gvec[0] = F.linear(gvec[0], sd["down_layer_global_proj.0.weight"], sd["down_layer_global_proj.0.bias"])
     x = level("down_time_embed_blocks", "down_self_blocks", 1, x)
     x = level("up_time_embed_blocks", "up_self_blocks", 1, x)
     x = upsample3d(sd, "upsample_layers.0", x)
+    if K:
+        gvec[0] = F.linear(gvec[0], sd["up_layer_global_proj.0.weight"], sd["up_layer_global_proj.0.bias"])
     x = x + skip
     x = level("up_time_embed_blocks", "up_self_blocks", 0, x)
     return F.linear(x[:, cfg.t_in:], sd["final_proj.weight"], sd["final_proj.bias"])

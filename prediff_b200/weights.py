@@ -28,6 +28,11 @@ class UNetConfig:
     # block_attn_patterns=None in the reference: explicit per-level lists of (cuboid_size, strategy, shift_size)
     # (block_cuboid_size / block_cuboid_strategy / block_cuboid_shift_size, cuboid_transformer_unet.py:215-232)
     explicit_layers: Tuple = None
+    # global vectors (cuboid_transformer_unet.py:55-60, cuboid_transformer.py:864-945): K learned vectors per sample that
+    # every cuboid attends to and that attend to the whole grid; shared q|k|v net (separate_global_qkv=False), ratio 1
+    num_global_vectors: int = 0
+    use_global_vector_ffn: bool = True
+    use_global_self_attn: bool = False
 
     @property
     def T(self):
@@ -110,19 +115,28 @@ def _resblock3d(prefix, cin, cout, temb) -> Spec:
     return s
 
 
-def _stack_block(prefix, dim, heads, cuboids) -> Spec:
+def _stack_block(prefix, dim, heads, cuboids, gv=False, gv_ffn=False) -> Spec:
+    """gv: the block carries global vectors (global_qkv / global_proj / global_vec_norm per attention layer,
+    cuboid_transformer.py:777-810); gv_ffn: and a PositionwiseFFN for them per layer (global_ffn_l, :1054-1068)."""
     s: Spec = []
-    for i in range(len(cuboids)):
-        p = f"{prefix}.ffn_l.{i}"
-        s += [(f"{p}.ffn_1.weight", (4 * dim, dim)), (f"{p}.ffn_1.bias", (4 * dim,)),
-              (f"{p}.ffn_2.weight", (dim, 4 * dim)), (f"{p}.ffn_2.bias", (dim,)),
-              (f"{p}.layer_norm.weight", (dim,)), (f"{p}.layer_norm.bias", (dim,))]
+    for name in ("ffn_l",) + (("global_ffn_l",) if gv and gv_ffn else ()):
+        for i in range(len(cuboids)):
+            p = f"{prefix}.{name}.{i}"
+            s += [(f"{p}.ffn_1.weight", (4 * dim, dim)), (f"{p}.ffn_1.bias", (4 * dim,)),
+                  (f"{p}.ffn_2.weight", (dim, 4 * dim)), (f"{p}.ffn_2.bias", (dim,)),
+                  (f"{p}.layer_norm.weight", (dim,)), (f"{p}.layer_norm.bias", (dim,))]
     for i, (bt, bh, bw) in enumerate(cuboids):
         p = f"{prefix}.attn_l.{i}"
         s += [(f"{p}.relative_position_bias_table", ((2 * bt - 1) * (2 * bh - 1) * (2 * bw - 1), heads)),
-              (f"{p}.qkv.weight", (3 * dim, dim)),
-              (f"{p}.proj.weight", (dim, dim)), (f"{p}.proj.bias", (dim,)),
-              (f"{p}.norm.weight", (dim,)), (f"{p}.norm.bias", (dim,))]
+              (f"{p}.qkv.weight", (3 * dim, dim))]
+        if gv:
+            s += [(f"{p}.global_qkv.weight", (3 * dim, dim))]
+        s += [(f"{p}.proj.weight", (dim, dim)), (f"{p}.proj.bias", (dim,))]
+        if gv:
+            s += [(f"{p}.global_proj.weight", (dim, dim)), (f"{p}.global_proj.bias", (dim,))]
+        s += [(f"{p}.norm.weight", (dim,)), (f"{p}.norm.bias", (dim,))]
+        if gv:
+            s += [(f"{p}.global_vec_norm.weight", (dim,)), (f"{p}.global_vec_norm.bias", (dim,))]
     return s
 
 
@@ -132,6 +146,9 @@ def unet_param_spec(cfg: UNetConfig) -> Spec:
     u0, u1 = cfg.units
     te = cfg.temb_channels
     s: Spec = []
+    gv = cfg.num_global_vectors > 0
+    if gv:
+        s += [("init_global_vectors", (cfg.num_global_vectors, u0))]
     s += _resblock3d("first_proj", cfg.c + 1, u0, 0)
     s += [("pos_embed.T_embed.weight", (cfg.T, u0)), ("pos_embed.H_embed.weight", (cfg.h, u0)),
           ("pos_embed.W_embed.weight", (cfg.w, u0))]
@@ -139,11 +156,15 @@ def unet_param_spec(cfg: UNetConfig) -> Spec:
           ("time_embed.layer.2.weight", (te, te)), ("time_embed.layer.2.bias", (te,))]
     s += [("downsample_layers.0.reduction.weight", (u1, 4 * u0)), ("downsample_layers.0.norm.weight", (4 * u0,)),
           ("downsample_layers.0.norm.bias", (4 * u0,))]
+    if gv:
+        s += [("down_layer_global_proj.0.weight", (u1, u0)), ("down_layer_global_proj.0.bias", (u1,))]
     s += [("upsample_layers.0.conv.weight", (u0, u1, 3, 3)), ("upsample_layers.0.conv.bias", (u0,))]
+    if gv:
+        s += [("up_layer_global_proj.0.weight", (u0, u1)), ("up_layer_global_proj.0.bias", (u0,))]
     for name in ("down_self_blocks", "up_self_blocks"):
         for lvl, dim in enumerate((u0, u1)):
             for d in range(cfg.depth[lvl]):
-                s += _stack_block(f"{name}.{lvl}.{d}", dim, cfg.num_heads, cfg.cuboids(lvl))
+                s += _stack_block(f"{name}.{lvl}.{d}", dim, cfg.num_heads, cfg.cuboids(lvl), gv, cfg.use_global_vector_ffn)
     for name in ("down_time_embed_blocks", "up_time_embed_blocks"):
         for lvl, dim in enumerate((u0, u1)):
             s += _resblock3d(f"{name}.{lvl}", dim, dim, te)
@@ -237,7 +258,7 @@ def _is_norm_weight(name: str) -> bool:
     if parts[-1] != "weight":
         return False
     owner = parts[-2]
-    if owner in ("norm", "layer_norm", "norm1", "norm2", "group_norm", "conv_norm_out"):
+    if owner in ("norm", "layer_norm", "norm1", "norm2", "group_norm", "conv_norm_out", "global_vec_norm"):
         return True
     if name == "out.0.weight":  # GroupNorm of the knowledge-alignment read-out head
         return True

@@ -74,8 +74,10 @@ def ref_unet(cfg):
         input_shape=[cfg.t_in, cfg.h, cfg.w, cfg.c], target_shape=[cfg.t_out, cfg.h, cfg.w, cfg.c],
         base_units=cfg.base_units, scale_alpha=1.0, num_heads=cfg.num_heads, attn_drop=0.1, proj_drop=0.1, ffn_drop=0.1,
         downsample=2, downsample_type="patch_merge", upsample_type="upsample", upsample_kernel_size=3,
-        depth=list(cfg.depth), block_attn_patterns=pats, num_global_vectors=0, use_global_vector_ffn=False,
-        use_global_self_attn=True, separate_global_qkv=True, global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
+        depth=list(cfg.depth), block_attn_patterns=pats, num_global_vectors=getattr(cfg, "num_global_vectors", 0),
+        use_global_vector_ffn=getattr(cfg, "use_global_vector_ffn", True) if getattr(cfg, "num_global_vectors", 0) else False,
+        use_global_self_attn=getattr(cfg, "use_global_self_attn", False) if getattr(cfg, "num_global_vectors", 0) else True,
+        separate_global_qkv=not getattr(cfg, "num_global_vectors", 0), global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
         norm_layer="layer_norm", padding_type=getattr(cfg, "padding_type", "zeros"), checkpoint_level=0,
         pos_embed_type="t+h+w", use_relative_pos=True, self_attn_use_final_proj=True, time_embed_channels_mult=4,
         time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0, unet_res_connect=True, **explicit)
@@ -487,6 +489,43 @@ def gen_patterns_nearest():
 
 
 @torch.no_grad()
+def gen_global_vectors():
+    """Global vectors (cuboid_transformer.py:864-945, cuboid_transformer_unet.py:124-126, 432-434, 449-450, 489-490): outputs
+    (x_out, new_global_vector) of the unmodified CuboidSelfAttentionLayer with use_global_vector=True, and forwards of the
+    unmodified reference UNet built with num_global_vectors > 0."""
+    import contextlib
+    import dataclasses
+    import io
+    from prediff.models.cuboid_transformer.cuboid_transformer import CuboidSelfAttentionLayer
+    import pattern_cases as PC
+    out = {}
+    for tag, dims, C, heads, size, strat, shift, pad, K, gsa in PC.GV_LAYER_CASES:
+        m = CuboidSelfAttentionLayer(dim=C, num_heads=heads, cuboid_size=size, shift_size=shift, strategy=tuple(strat),
+                                     padding_type=pad, qkv_bias=False, attn_drop=0.0, proj_drop=0.0,
+                                     use_final_proj=True, norm_layer="layer_norm", use_global_vector=True,
+                                     use_global_self_attn=gsa, separate_global_qkv=False, global_dim_ratio=1,
+                                     checkpoint_level=0, use_relative_pos=True).eval()
+        sd = Wt.seeded_state_dict(PC.gv_layer_spec(C, heads, size), PC.LAYER_SEED)
+        res = m.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not res.unexpected_keys and res.missing_keys == ["relative_position_index"], res
+        x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+        g = inp(PC.LAYER_SEED + 2, 2, K, C)
+        xo, go = m(x, g)
+        out[f"layer_{tag}_x"], out[f"layer_{tag}_g"] = xo, go
+        print(f"global_vectors layer_{tag}: x std {xo.std():.3f}, g std {go.std():.3f}")
+    for tag, pats, pad, K, gffn, gsa in PC.GV_UNET_CASES:
+        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad, num_global_vectors=K,
+                                  use_global_vector_ffn=gffn, use_global_self_attn=gsa)
+        m = ref_unet(cfg)
+        x = inp(1234, 2, cfg.t_out, cfg.h, cfg.w, cfg.c)
+        cond = inp(1235, 2, cfg.t_in, cfg.h, cfg.w, cfg.c)
+        with contextlib.redirect_stdout(io.StringIO()):   # the reference forward prints shapes on this path (:451-452)
+            out[f"unet_{tag}"] = m(x, torch.tensor([500, 37], dtype=torch.long), cond)
+        print(f"global_vectors unet_{tag}: out std {out[f'unet_{tag}'].std():.3f}")
+    save("global_vectors", **out)
+
+
+@torch.no_grad()
 def gen_vae(tag, cfg, N):
     m = ref_vae(cfg)
     x = inp(4321, N, 1, cfg.h, cfg.w, uniform=True)
@@ -704,6 +743,8 @@ if __name__ == "__main__":
         gen_patterns()
     if "patterns_nearest" in todo:
         gen_patterns_nearest()
+    if "global_vectors" in todo:
+        gen_global_vectors()
     if "losses" in todo:
         gen_losses()
     if "ema" in todo:

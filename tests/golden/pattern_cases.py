@@ -40,6 +40,35 @@ _DEFAULT_BLOCK = (((4, 4, 4), ("l", "l", "l"), (0, 0, 0)), ((4, 4, 4), ("d", "d"
 EXPLICIT_LAYERS = (_DEFAULT_BLOCK, _DEFAULT_BLOCK)
 
 
+# global vectors (cuboid_transformer.py:864-945), goldens in global_vectors.npz:
+# (tag, (T, H, W), C, heads, cuboid_size, strategy, shift_size, padding_type, num_global, use_global_self_attn)
+GV_LAYER_CASES = [
+    ("gv_axial_t", (13, 8, 8), 32, 2, (13, 1, 1), "lll", (0, 0, 0), "zeros", 4, False),
+    ("gv_swin_z", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "zeros", 4, False),       # padded slots take part (zero rows)
+    ("gv_swin_i", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "ignore", 4, True),        # raster-order slot mask, shifted
+    ("gv_dilated_i", (13, 8, 8), 32, 2, (2, 4, 4), "ddd", (0, 0, 0), "ignore", 8, False),    # mask order != slot order
+    ("gv_ragged_z", (6, 7, 9), 32, 2, (4, 3, 4), "ldl", (2, 1, 2), "zeros", 3, True),
+    ("gv_ragged_i", (6, 7, 9), 32, 2, (4, 3, 4), "ldl", (2, 1, 2), "ignore", 5, False),
+    ("gv_swin_n", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "nearest", 4, True),       # resampled copies take part
+    ("gv_plane_hd32", (3, 8, 8), 64, 2, (1, 8, 8), "lll", (0, 0, 0), "zeros", 8, True),
+    ("gv_full_hd64", (5, 8, 8), 128, 2, (5, 8, 8), "lll", (0, 0, 0), "ignore", 16, True),    # 320-slot cuboid: 5 key chunks + globals
+]
+# (tag, block_attn_patterns, padding_type, num_global_vectors, use_global_vector_ffn, use_global_self_attn): tiny UNet, B = 2
+GV_UNET_CASES = [
+    ("gv_axial", ("axial", "axial"), "zeros", 4, True, False),
+    ("gv_swin_sa", ("video_swin_2x8", "spatial_lg_4"), "ignore", 8, True, True),
+    ("gv_dst_noffn", ("divided_st", "axial_space_dilate_2"), "nearest", 2, False, True),
+]
+
+
+def gv_layer_spec(C, heads, size):
+    n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
+    return [("a.relative_position_bias_table", (n_rel, heads)), ("a.qkv.weight", (3 * C, C)),
+            ("a.global_qkv.weight", (3 * C, C)), ("a.proj.weight", (C, C)), ("a.proj.bias", (C,)),
+            ("a.global_proj.weight", (C, C)), ("a.global_proj.bias", (C,)), ("a.norm.weight", (C,)), ("a.norm.bias", (C,)),
+            ("a.global_vec_norm.weight", (C,)), ("a.global_vec_norm.bias", (C,))]
+
+
 def layer_spec(C, heads, size):
     n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
     return [("a.relative_position_bias_table", (n_rel, heads)), ("a.qkv.weight", (3 * C, C)),

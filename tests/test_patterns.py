@@ -78,6 +78,38 @@ def test_oracle_unet_patterns_vs_reference(case):
     assert maxrel(out, (GN if pad == "nearest" else G)[f"unet_{tag}"]) < 1e-4
 
 
+GV = np.load(os.path.join(os.path.dirname(__file__), "golden", "global_vectors.npz"))   # use_global_vector=True
+
+
+@pytest.mark.parametrize("case", PC.GV_LAYER_CASES, ids=[c[0] for c in PC.GV_LAYER_CASES])
+def test_oracle_layer_global_vectors_vs_reference(case):
+    """Global vectors (cuboid_transformer.py:864-945) against the unmodified CuboidSelfAttentionLayer(use_global_vector=True):
+    both outputs, the token grid and the new global vectors."""
+    tag, dims, C, heads, size, strat, shift, pad, K, gsa = case
+    sd = O.to_torch_sd(Wt.seeded_state_dict(PC.gv_layer_spec(C, heads, size), PC.LAYER_SEED))
+    x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+    g = inp(PC.LAYER_SEED + 2, 2, K, C)
+    xo, go = O.cuboid_attention_gv(sd, "a", x, g, heads, size, tuple(strat), shift, pad, gsa)
+    assert maxrel(xo, GV[f"layer_{tag}_x"]) < 2e-5
+    assert maxrel(go, GV[f"layer_{tag}_g"]) < 2e-5
+
+
+def gv_unet_cfg(case):
+    tag, pats, pad, K, gffn, gsa = case
+    return dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad, num_global_vectors=K,
+                               use_global_vector_ffn=gffn, use_global_self_attn=gsa)
+
+
+@pytest.mark.parametrize("case", PC.GV_UNET_CASES, ids=[c[0] for c in PC.GV_UNET_CASES])
+def test_oracle_unet_global_vectors_vs_reference(case):
+    cfg = gv_unet_cfg(case)
+    sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED))
+    x = inp(1234, 2, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(1235, 2, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    out = O.unet_forward(sd, cfg, x, torch.tensor([500, 37]), cond)
+    assert maxrel(out, GV[f"unet_{case[0]}"]) < 1e-4
+
+
 def attention_from_tables(qkv, table, heads, geo):
     """What the CUDA kernel computes, in numpy: gather rows by `tok`, mask by `lab`, bias by `rel`."""
     B, T, H, W, C3 = qkv.shape
