@@ -62,6 +62,13 @@ typedef struct pd_unet_pattern {
     int32_t padding_type;
 } pd_unet_pattern;
 int pd_unet_create_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern, pd_unet** out);
+/* ... with global vectors (cuboid_transformer_unet.py:55-60, 124-126: num_global_vectors > 0, separate_global_qkv=False,
+ * global_dim_ratio=1): num_global_vectors in 1..32; use_global_vector_ffn / use_global_self_attn as the reference's
+ * constructor arguments. pattern may be NULL (axial, 'zeros'). Adds the state_dict keys init_global_vectors,
+ * {down,up}_layer_global_proj.0.*, <block>.attn_l.i.{global_qkv,global_proj,global_vec_norm}.* and <block>.global_ffn_l.i.*.
+ * bf16 operand precision only. */
+int pd_unet_create_gv(const pd_unet_config* cfg, const pd_unet_pattern* pattern, int num_global_vectors,
+                      int use_global_vector_ffn, int use_global_self_attn, pd_unet** out);
 void pd_unet_destroy(pd_unet* m);
 /* Number of state_dict entries the model expects; name/shape of entry i (reference key names, e.g.
  * "down_self_blocks.0.1.attn_l.2.qkv.weight"). shape has up to 5 dims; returns ndim. */
@@ -317,6 +324,26 @@ int pd_op_cuboid_attention(const void* qkv_bf16, const float* bias_table, void* 
 int pd_op_cuboid_attention_impl(const void* qkv_bf16, const float* bias_table, void* out_bf16, int B, int T, int H, int W,
                                 int C, int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                                 int padding_type, int impl, void* stream);
+/* Global vectors (cuboid_transformer.py:864-945, use_global_vector with the shared global_qkv net): K <= 32 vectors per
+ * sample that every cuboid's queries see as extra, never-masked keys and whose own queries attend over all num_cuboids *
+ * volume slots (+ themselves with use_global_self_attn).
+ * pd_cuboid_tables_gmask (host-only): padding_type 1 ('ignore') only - gmask [num_cuboids*volume], 1 = the slot is visible to
+ *   the global queries: the validity of the padded, rolled frame flattened in raster order, applied to the cuboid-ordered
+ *   slots as the reference does (:915-924). Returns 1 if the layer has such a mask, 0 if every slot is visible, < 0 on error.
+ * pd_op_gv_linear: out[r][n] = (res ? res[r][n] : 0) + act(sum_k f(in[r][k]) W[n][k] + bias[n]) on the M = B * K global rows,
+ *   fp32 on the reference-layout fp32 weight [N][K]; f = LayerNorm(ln_gamma, ln_beta, 1e-5) if ln_gamma (global_vec_norm /
+ *   the global FFN's pre-norm; K <= 512), act 1 = GELU(erf); out_f32 / out_bf16: either or both; res may alias out_f32.
+ * pd_op_cuboid_attention_gv: qkv bf16 [B][T][H][W][3C] and the global rows' q|k|v (gqkv_f32 [B][K][3C] and its bf16 copy)
+ *   -> out bf16 [B][T][H][W][C] (local + local-to-global attention, :902-913) and gout fp32 [B][K][C] (global-to-local
+ *   (+ global-to-global) attention, :928-945), both before their output projections. */
+int pd_cuboid_tables_gmask(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                           int padding_type, int32_t* gmask, int64_t capacity);
+int pd_op_gv_linear(const float* in, const float* ln_gamma, const float* ln_beta, const float* W, const float* bias,
+                    const float* res, float* out_f32, void* out_bf16, int M, int K, int N, int act, void* stream);
+int pd_op_cuboid_attention_gv(const void* qkv_bf16, const float* bias_table, const float* gqkv_f32, const void* gqkv_bf16,
+                              void* out_bf16, float* gout, int B, int T, int H, int W, int C, int heads, const int32_t size[3],
+                              const int32_t strategy[3], const int32_t shift[3], int padding_type, int n_global, int self_attn,
+                              void* stream);
 /* q_sample (latent_diffusion.py:489-492): out = sqrt_alphas_cumprod[t_b] x_start + sqrt_one_minus_alphas_cumprod[t_b]
  * noise, bit-exact vs the reference's fp32 tensor expression; tables fp32 [T] and t int64 [B] on the device. */
 int pd_op_q_sample(const float* x_start, const float* noise, const int64_t* t, const float* sqrt_alphas_cumprod,

@@ -234,6 +234,59 @@ int pd_cuboid_tables_dst(int T, int H, int W, const int32_t size[3], const int32
     return (int)(g.dst.empty() ? 0 : 1);
 }
 
+int pd_cuboid_tables_gmask(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                           int padding_type, int32_t* gmask, int64_t capacity) {
+    CuboidLayerSpec sp;
+    for (int a = 0; a < 3; ++a) {
+        sp.size[a] = size[a];
+        sp.strategy[a] = strategy[a];
+        sp.shift[a] = shift[a];
+    }
+    CuboidTables g;
+    PD_TRY(build_cuboid_tables(T, H, W, sp, padding_type, &g));
+    PD_CHECK(gmask && (int64_t)g.gmask.size() <= capacity, PD_ERR_ARG, "pd_cuboid_tables_gmask: capacity %lld < %zu",
+             (long long)capacity, g.gmask.size());
+    if (!g.gmask.empty()) memcpy(gmask, g.gmask.data(), g.gmask.size() * sizeof(int));
+    return (int)(g.gmask.empty() ? 0 : 1);
+}
+
+int pd_op_gv_linear(const float* in, const float* ln_gamma, const float* ln_beta, const float* W, const float* bias,
+                    const float* res, float* out_f32, void* out_bf16, int M, int K, int N, int act, void* stream) {
+    return gv_linear(in, ln_gamma, ln_beta, W, bias, res, out_f32, static_cast<bf16*>(out_bf16), M, K, N, act, S(stream));
+}
+
+int pd_op_cuboid_attention_gv(const void* qkv, const float* bias_table, const float* gqkv_f32, const void* gqkv_bf16, void* out,
+                              float* gout, int B, int T, int H, int W, int C, int heads, const int32_t size[3],
+                              const int32_t strategy[3], const int32_t shift[3], int padding_type, int n_global, int self_attn,
+                              void* stream) {
+    PD_TRY(gemm_init());
+    PD_CHECK(qkv && bias_table && gqkv_f32 && gqkv_bf16 && out && gout, PD_ERR_ARG, "pd_op_cuboid_attention_gv: null pointer");
+    PD_CHECK(C % heads == 0 && heads >= 1, PD_ERR_SHAPE, "pd_op_cuboid_attention_gv: C=%d heads=%d", C, heads);
+    CuboidLayerSpec sp;
+    for (int a = 0; a < 3; ++a) {
+        sp.size[a] = size[a];
+        sp.strategy[a] = strategy[a];
+        sp.shift[a] = shift[a];
+    }
+    CuboidTables g;
+    PD_TRY(build_cuboid_tables(T, H, W, sp, padding_type, &g));
+    CuboidTablesDev d;
+    PD_TRY(d.upload(g));
+    cudaStream_t st = S(stream);
+    const int n_keys = g.num_cuboids * g.volume + (self_attn ? n_global : 0);
+    float* ws = nullptr;
+    PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws),
+                            global_attention_workspace_floats(B, heads, n_global, C / heads, n_keys) * sizeof(float) + 16, st));
+    int rc = cuboid_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T * H * W, C, heads, d.dev,
+                              st, 1, static_cast<const bf16*>(gqkv_bf16), n_global);
+    if (rc == PD_OK)
+        rc = global_attention(gqkv_f32, static_cast<const bf16*>(qkv), static_cast<const bf16*>(gqkv_bf16), gout, ws, B, T * H * W,
+                              C, heads, n_global, self_attn, d.dev, st);
+    cudaFreeAsync(ws, st);
+    PD_CUDA(cudaStreamSynchronize(st));   // the tables are freed on return
+    return rc;
+}
+
 int pd_op_cuboid_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
                            const int32_t size[3], const int32_t strategy[3], const int32_t shift[3], int padding_type,
                            void* stream) {

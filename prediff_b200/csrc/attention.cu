@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(128) axial_attention_f32_kernel(const float* _
 // shared memory in chunks of 64 with an online softmax; QK^T and PV on warp-level mma.sync m16n8k16 (bf16, fp32
 // accumulate). Padding slots contribute zero q/k/v rows (the reference pads after its LayerNorm and qkv has no bias).
 constexpr int kQTile = 64;
+constexpr int kGlobalRow = 1 << 30;   // key metadata of the global-vector chunk: row = kGlobalRow + index, label = kGlobalLab
+constexpr int kGlobalLab = -2;
 constexpr int kMaxRelSmem = 4096;    // bias-table rows of one head staged in shared memory (<= 16 KB per block)
 
 // Two schedules, chosen by the launcher (see cuboid_attention): kv_stages == 2 double-buffers the K/V chunks (the gather
@@ -333,7 +335,8 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                                                                bf16* __restrict__ out, const int* __restrict__ tok,
                                                                const int* __restrict__ lab, const int* __restrict__ rel,
                                                                const int* __restrict__ dstp, int N, int C, int heads, int vol,
-                                                               int rel_off, int n_rel_smem, int kv_stages) {
+                                                               int rel_off, int n_rel_smem, int kv_stages,
+                                                               const bf16* __restrict__ gkv, int n_global) {
     grid_dep_launch();
     grid_dep_wait();
     constexpr int LD = HD + 8;        // row pitch: +16 B keeps ldmatrix bank-conflict free
@@ -356,6 +359,9 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
     const int* clab = lab + (size_t)c * vol;
     const bf16* base = qkv + (size_t)b * N * C3 + h * HD;
     const bool bias_in_smem = n_rel_smem > 0;
+    // global vectors (cuboid_transformer.py:902-913): after the cuboid's own slots every query sees the n_global <= 64 global
+    // keys (q|k|v rows gkv [B][n_global][3C]) as one more key chunk - never masked, no position bias
+    const bf16* gbase = n_global > 0 ? gkv + (size_t)b * n_global * C3 + h * HD : nullptr;
 
     if (tid < kQTile) {
         const int i = q0 + tid;
@@ -367,14 +373,23 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
     for (int i = tid; i < n_rel_smem; i += 128) s_bias[i] = __ldg(bias_table + (size_t)i * heads + h);
 
     // chunk loader: slot metadata by the first 64 threads, then (after a block barrier) the row gathers by everyone
-    auto load_meta = [&](int k0, int stage) {
+    const int n_chunks = (vol + kQTile - 1) / kQTile;
+    const int n_total = n_chunks + (n_global > 0 ? 1 : 0);
+    auto load_meta = [&](int ch, int stage) {
         if (tid < kQTile) {
-            const int j = k0 + tid;
-            const bool in = j < vol;
             int* m = s_kmeta + stage * 3 * kQTile;
-            m[tid] = in ? ctok[j] : -1;
-            m[kQTile + tid] = in ? clab[j] : -1;   // slots past the cuboid's end are always masked
-            m[2 * kQTile + tid] = in ? rel[j] : 0;
+            if (ch < n_chunks) {
+                const int j = ch * kQTile + tid;
+                const bool in = j < vol;
+                m[tid] = in ? ctok[j] : -1;
+                m[kQTile + tid] = in ? clab[j] : -1;   // slots past the cuboid's end are always masked
+                m[2 * kQTile + tid] = in ? rel[j] : 0;
+            } else {   // the global keys
+                const bool in = tid < n_global;
+                m[tid] = in ? kGlobalRow + tid : -1;
+                m[kQTile + tid] = in ? kGlobalLab : -1;
+                m[2 * kQTile + tid] = 0;
+            }
         }
     };
     auto load_rows = [&](int stage) {
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
             bf16* dk = sK + r * LD + v * 8;
             bf16* dv = sV + r * LD + v * 8;
             if (t >= 0) {
-                const bf16* src = base + (size_t)t * C3 + v * 8;
+                const bf16* src = (t >= kGlobalRow ? gbase + (size_t)(t - kGlobalRow) * C3 : base + (size_t)t * C3) + v * 8;
                 cp_async16(dk, src + C);
                 cp_async16(dv, src + 2 * C);
             } else {
@@ -418,18 +433,17 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
 #pragma unroll
     for (int jn = 0; jn < HD / 8; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
 
-    const int n_chunks = (vol + kQTile - 1) / kQTile;
     const bool two_stage = kv_stages == 2;
-    for (int ch = 0; ch < n_chunks; ++ch) {
+    for (int ch = 0; ch < n_total; ++ch) {
         const int stage = two_stage ? (ch & 1) : 0;
-        if (two_stage && ch + 1 < n_chunks) {   // prefetch the next chunk into the other stage (its last readers
-            load_meta((ch + 1) * kQTile, stage ^ 1);   // passed the barrier that closes iteration ch - 1)
+        if (two_stage && ch + 1 < n_total) {   // prefetch the next chunk into the other stage (its last readers
+            load_meta(ch + 1, stage ^ 1);          // passed the barrier that closes iteration ch - 1)
             __syncthreads();
             load_rows(stage ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             if (!two_stage && ch > 0) {   // single stage: the chunk is fetched after the previous one is consumed
-                load_meta(ch * kQTile, 0);
+                load_meta(ch, 0);
                 __syncthreads();
                 load_rows(0);
             }
@@ -468,7 +482,9 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
 #pragma unroll
                 for (int rh = 0; rh < 2; ++rh) {
                     float v = -INFINITY;
-                    if (qlab[rh] >= 0 && kl == qlab[rh]) {
+                    if (kl == kGlobalLab) {
+                        v = s[nt][2 * rh + e] * scale;
+                    } else if (qlab[rh] >= 0 && kl == qlab[rh]) {
                         const int idx = qrel[rh] - kr;
                         const float bias = bias_in_smem ? s_bias[idx] : __ldg(bias_table + (size_t)idx * heads + h);
                         v = s[nt][2 * rh + e] * scale + bias;
@@ -691,6 +707,7 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
     g->tok.assign((size_t)nc * vol, -1);
     g->lab.assign((size_t)nc * vol, -1);
     g->dst.clear();
+    g->gmask.clear();
     // 'nearest' (models/utils.py:228-270): the padded grid is F.interpolate(x, size = padded) - position o copies token
     // floor(o * dims / padded) - and the result is F.interpolate(y, size = dims): token t takes position
     // floor(t * padded / dims). Both with torch's float32 index arithmetic (scale = in / out, src = min(floorf(dst * scale),
@@ -742,6 +759,17 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
             g->lab[k] = (!valid && padding_type == 1) ? -1 : label;
         }
     }
+    // global vectors, 'ignore' padding (:915-924): the mask of the global queries over the nc * vol slots is the validity grid
+    // of the padded, rolled frame flattened in RASTER order - the reference applies it to the cuboid-ordered keys unchanged
+    if (padding_type == 1) {
+        g->gmask.resize((size_t)nc * vol);
+        for (int s = 0; s < nc * vol; ++s) {
+            const int p[3] = {s / (padded[1] * padded[2]), (s / padded[2]) % padded[1], s % padded[2]};
+            bool valid = true;
+            for (int a = 0; a < 3; ++a) valid = valid && (any_shift ? (p[a] + g->shift[a]) % padded[a] : p[a]) < dims[a];
+            g->gmask[s] = valid ? 1 : 0;
+        }
+    }
     // relative_position_index[:vol, :vol] is built from the CONSTRUCTOR's cuboid size (:714-734, 855-857)
     const int b1 = spec.size[1], b2 = spec.size[2];
     const int s1 = (2 * b1 - 1) * (2 * b2 - 1), s2 = 2 * b2 - 1;
@@ -761,10 +789,12 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
 }
 
 int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
-                     const CuboidDev& g, cudaStream_t st, int impl) {
+                     const CuboidDev& g, cudaStream_t st, int impl, const bf16* gkv, int n_global) {
     PD_CHECK(C % heads == 0, PD_ERR_SHAPE, "cuboid_attention: C=%d heads=%d", C, heads);
     const int hd = C / heads;
-    if (impl == 2 || (impl == 0 && cuboid_attention_tc_eligible(hd, g.volume)))
+    PD_CHECK(n_global >= 0 && n_global <= kQTile && (n_global == 0 || (gkv && impl != 2)), PD_ERR_ARG,
+             "cuboid_attention: %d global vectors (at most %d, on the mma.sync kernel)", n_global, kQTile);
+    if (n_global == 0 && (impl == 2 || (impl == 0 && cuboid_attention_tc_eligible(hd, g.volume))))
         return cuboid_attention_tc(qkv, bias_table, out, B, N, C, heads, g, st);
     PD_CHECK(g.num_cuboids >= 1 && g.num_cuboids <= 65535 && B * heads <= 65535, PD_ERR_SHAPE,
              "cuboid_attention: %d cuboids, %d sample-heads exceed the grid limits", g.num_cuboids, B * heads);
@@ -793,7 +823,7 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
             attr_bytes = smem;                                                                                      \
         }                                                                                                           \
         PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, g.dst, N, \
-                  C, heads, g.volume, g.rel_off, n_rel_smem, kv_stages);                                            \
+                  C, heads, g.volume, g.rel_off, n_rel_smem, kv_stages, gkv, n_global);                             \
     } while (0)
     switch (hd) {
         case 16: PD_LAUNCH_CUB(16); break;
@@ -808,10 +838,10 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
 }
 
 int CuboidTablesDev::upload(const CuboidTables& t) {
-    const size_t nt = t.tok.size(), nr = t.rel.size(), nd = t.dst.size();
-    if (cudaMalloc(&mem, (2 * nt + nr + nd) * sizeof(int)) != cudaSuccess) {
+    const size_t nt = t.tok.size(), nr = t.rel.size(), nd = t.dst.size(), ng = t.gmask.size();
+    if (cudaMalloc(&mem, (2 * nt + nr + nd + ng) * sizeof(int)) != cudaSuccess) {
         mem = nullptr;
-        set_error("cuboid tables: cudaMalloc of %zu ints failed", 2 * nt + nr + nd);
+        set_error("cuboid tables: cudaMalloc of %zu ints failed", 2 * nt + nr + nd + ng);
         return PD_ERR_CUDA;
     }
     int* p = static_cast<int*>(mem);
@@ -825,6 +855,11 @@ int CuboidTablesDev::upload(const CuboidTables& t) {
     if (nd) {
         PD_CUDA(cudaMemcpy(p + 2 * nt + nr, t.dst.data(), nd * sizeof(int), cudaMemcpyHostToDevice));
         dev.dst = p + 2 * nt + nr;
+    }
+    dev.gmask = nullptr;
+    if (ng) {
+        PD_CUDA(cudaMemcpy(p + 2 * nt + nr + nd, t.gmask.data(), ng * sizeof(int), cudaMemcpyHostToDevice));
+        dev.gmask = p + 2 * nt + nr + nd;
     }
     dev.num_cuboids = t.num_cuboids;
     dev.volume = t.volume;

@@ -49,11 +49,15 @@ struct CuboidTables {      // host tables of one layer on a (T, H, W) grid
     // then the token the slot's q|k|v rows are COPIES of (the reference resamples the grid with F.interpolate before the
     // attention and back after it, models/utils.py:228-270)
     std::vector<int> dst;
+    // padding_type 'ignore' only (empty otherwise): [num_cuboids * volume] 1 = the slot is visible to the global vectors'
+    // queries (cuboid_transformer.py:915-924; raster-order validity of the padded, rolled frame, see build_cuboid_tables)
+    std::vector<int> gmask;
 };
 int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int padding_type, CuboidTables* out);
 struct CuboidDev {         // device copies
     const int *tok = nullptr, *lab = nullptr, *rel = nullptr;
     const int* dst = nullptr;                                  // null: results go to `tok` (every padding type but 'nearest')
+    const int* gmask = nullptr;                                // null: every slot is visible to the global queries
     int num_cuboids = 0, volume = 0, rel_off = 0, n_rel = 0;   // n_rel: rows of the bias table
 };
 struct CuboidTablesDev {   // owner of the device copies
@@ -67,14 +71,31 @@ struct CuboidTablesDev {   // owner of the device copies
 };
 // qkv bf16 [B][N][3C] (N = T*H*W tokens per sample, q|k|v head-major), bias_table fp32 [n_rel][heads] -> out bf16 [B][N][C]
 // impl: 0 = choose (tcgen05 tile kernel when eligible, see below), 1 = warp-level mma.sync kernel, 2 = tcgen05 tile kernel
+// gkv / n_global: q|k|v rows of the sample's global vectors, bf16 [B][n_global][3C] (n_global <= 64) - every query also
+// attends to their keys, unmasked and without position bias (cuboid_transformer.py:902-913); mma.sync kernel only
 int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
-                     const CuboidDev& g, cudaStream_t st, int impl = 0);
+                     const CuboidDev& g, cudaStream_t st, int impl = 0, const bf16* gkv = nullptr, int n_global = 0);
 // The same contract on tcgen05 tensor-core tiles (attention_tc.cu): 128-query tile per (cuboid, head, sample), S and O in
 // TMEM, K / V chunks of 128 keys in a swizzled shared-memory ring. Eligible for head dims 64 / 128 and volumes >= 128
 // (cuboid_attention() dispatches to it; PD_CUBOID_NO_TC=1 keeps the mma.sync kernel for A/B runs).
 bool cuboid_attention_tc_eligible(int hd, int volume);
 int cuboid_attention_tc(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
                         const CuboidDev& g, cudaStream_t st);
+// ---- global vectors (global_vec.cu; cuboid_transformer.py:864-945, 1130-1145) ------------------------------------------
+// out[r][n] = (res ? res[r][n] : 0) + act( sum_k f(in[r][k]) W[n][k] + bias[n] ) on M = B * K rows, fp32 on the fp32 weights
+// as loaded; f = LayerNorm(ln_gamma, ln_beta, eps 1e-5) when ln_gamma is given (K <= 512), act 1 = GELU (erf). res may alias
+// out_f32. out_f32 / out_bf16: either or both.
+int gv_linear(const float* in, const float* ln_gamma, const float* ln_beta, const float* W, const float* bias, const float* res,
+              float* out_f32, bf16* out_bf16, int M, int K, int N, int act, cudaStream_t st);
+// g[b] = init for every sample (init_global_vectors.expand, cuboid_transformer_unet.py:432-434)
+int gv_broadcast(const float* init, float* g, int B, int K, int C, cudaStream_t st);
+// The global queries' attention (:928-945): gqkv fp32 [B][K][3C] (q part used, scaled by hd^-0.5 inside), local q|k|v bf16
+// [B][N][3C] gathered through the layer's slot table (padding slots: zero rows, hidden under 'ignore' by g.gmask), and with
+// self_attn the global keys / values gkv bf16 [B][K][3C] appended -> out fp32 [B][K][C] (before global_proj).
+// workspace: global_attention_workspace_floats(...) floats. K <= 32.
+size_t global_attention_workspace_floats(int B, int heads, int K, int hd, int n_keys);
+int global_attention(const float* gqkv, const bf16* qkv, const bf16* gkv, float* out, float* workspace, int B, int N, int C,
+                     int heads, int K, int self_attn, const CuboidDev& g, cudaStream_t st);
 // Row softmax for the VAE AttentionBlock: s fp32 [rows][L] -> p bf16 [rows][L], p = softmax(scale * s).
 int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st);
 // Batched transpose bf16: in [S][R][ld_in] (first C columns used) -> out [S][C][R].

@@ -21,6 +21,10 @@ struct UNet::Bufs {
     float *xin_f32, *x[2], *h[2];
     bf16 *xin_bf16, *a[2], *ln[2], *qkv[2], *att[2], *mid[2], *pm, *up, *fin;
     float *e0, *e1, *temb, *embs;
+    // global vectors: the vectors per level [B * K][C], their q|k|v rows (fp32 + the bf16 copy the cuboid kernel reads as
+    // keys / values), the global queries' attention output, the global FFN's hidden rows, split partials of that attention
+    float *gv[2] = {nullptr, nullptr}, *g_qkv = nullptr, *g_att = nullptr, *g_mid = nullptr, *g_ws = nullptr;
+    bf16* g_qkv_bf16 = nullptr;
     double* gn_sums;
     int* split_flags;  // split-K tile handshake flags, shared by all convs of the plan (kernels run one at a time)
 };
@@ -59,7 +63,8 @@ struct UNet::BatchPlan {
 
 UNet::~UNet() = default;
 
-UNet::UNet(const pd_unet_config& c, const pd_unet_pattern* pattern) : cfg(c) {
+UNet::UNet(const pd_unet_config& c, const pd_unet_pattern* pattern, int n_global_, int global_ffn_, int global_self_attn_)
+    : cfg(c), n_global(n_global_), global_ffn(global_ffn_ != 0), global_self_attn(global_self_attn_ != 0) {
     C0 = cfg.base_units;
     C1 = 2 * cfg.base_units;
     T = cfg.t_in + cfg.t_out;
@@ -105,8 +110,10 @@ void UNet::declare_resblock(const std::string& p, int cin, int cout, bool emb) {
 
 void UNet::declare_stack(const std::string& p, int dim, int lvl) {
     const int n = (int)layers[lvl].size();
+    const char* ffn_lists[2] = {".ffn_l.%d", ".global_ffn_l.%d"};   // registration order of the reference (:1039-1068)
+    for (int which = 0; which < (n_global > 0 && global_ffn ? 2 : 1); ++which)
     for (int i = 0; i < n; ++i) {
-        const std::string f = p + strf(".ffn_l.%d", i);
+        const std::string f = p + strf(ffn_lists[which], i);
         ws.declare(f + ".ffn_1.weight", {4 * dim, dim});
         ws.declare(f + ".ffn_1.bias", {4 * dim});
         ws.declare(f + ".ffn_2.weight", {dim, 4 * dim});
@@ -120,15 +127,25 @@ void UNet::declare_stack(const std::string& p, int dim, int lvl) {
         ws.declare(a + ".relative_position_bias_table",
                    {(2 * std::max(sz[0], 1) - 1) * (2 * std::max(sz[1], 1) - 1) * (2 * std::max(sz[2], 1) - 1), cfg.num_heads});
         ws.declare(a + ".qkv.weight", {3 * dim, dim});
+        if (n_global > 0) ws.declare(a + ".global_qkv.weight", {3 * dim, dim});
         ws.declare(a + ".proj.weight", {dim, dim});
         ws.declare(a + ".proj.bias", {dim});
+        if (n_global > 0) {
+            ws.declare(a + ".global_proj.weight", {dim, dim});
+            ws.declare(a + ".global_proj.bias", {dim});
+        }
         ws.declare(a + ".norm.weight", {dim});
         ws.declare(a + ".norm.bias", {dim});
+        if (n_global > 0) {
+            ws.declare(a + ".global_vec_norm.weight", {dim});
+            ws.declare(a + ".global_vec_norm.bias", {dim});
+        }
     }
 }
 
 // Same names, shapes and order as the reference's state_dict() (minus derived int64 buffers).
 void UNet::declare_weights() {
+    if (n_global > 0) ws.declare("init_global_vectors", {n_global, C0});
     declare_resblock("first_proj", cfg.c + 1, C0, false);
     ws.declare("pos_embed.T_embed.weight", {T, C0});
     ws.declare("pos_embed.H_embed.weight", {cfg.h, C0});
@@ -140,8 +157,16 @@ void UNet::declare_weights() {
     ws.declare("downsample_layers.0.reduction.weight", {C1, 4 * C0});
     ws.declare("downsample_layers.0.norm.weight", {4 * C0});
     ws.declare("downsample_layers.0.norm.bias", {4 * C0});
+    if (n_global > 0) {
+        ws.declare("down_layer_global_proj.0.weight", {C1, C0});
+        ws.declare("down_layer_global_proj.0.bias", {C1});
+    }
     ws.declare("upsample_layers.0.conv.weight", {C0, C1, 3, 3});
     ws.declare("upsample_layers.0.conv.bias", {C0});
+    if (n_global > 0) {
+        ws.declare("up_layer_global_proj.0.weight", {C0, C1});
+        ws.declare("up_layer_global_proj.0.bias", {C0});
+    }
     const char* sb[2] = {"down_self_blocks", "up_self_blocks"};
     for (const char* n : sb)
         for (int lvl = 0; lvl < 2; ++lvl)
@@ -189,6 +214,8 @@ int UNet::validate() const {
     PD_CHECK(cfg.max_batch >= 1, PD_ERR_SHAPE, "unet: max_batch");
     PD_CHECK(padding_type >= 0 && padding_type <= 2, PD_ERR_ARG, "unet: padding_type %d (0 'zeros' | 1 'ignore' | 2 'nearest')",
              padding_type);
+    PD_CHECK(n_global >= 0 && n_global <= 32, PD_ERR_ARG, "unet: %d global vectors (0..32 are built)", n_global);
+    PD_CHECK(n_global == 0 || C1 <= 512, PD_ERR_SHAPE, "unet: global vectors need a level-1 width <= 512 (got %d)", C1);
     for (int lvl = 0; lvl < 2; ++lvl)
         for (const CuboidLayerSpec& sp : layers[lvl])
             for (int a = 0; a < 3; ++a)
@@ -251,6 +278,26 @@ int UNet::finalize_stack(const std::string& p, int dim, int lvl, StackW* s) {
         PD_GETW(s->f[i].b2, f + ".ffn_2.bias");
         PD_TRY(pack_linear_w(f + ".ffn_1.weight", 4 * dim, dim, &s->f[i].w1));
         PD_TRY(pack_linear_w(f + ".ffn_2.weight", dim, 4 * dim, &s->f[i].w2));
+        if (n_global > 0) {
+            PD_GETW(s->a[i].g_ln_w, a + ".global_vec_norm.weight");
+            PD_GETW(s->a[i].g_ln_b, a + ".global_vec_norm.bias");
+            PD_GETW(s->a[i].g_qkv_w, a + ".global_qkv.weight");
+            PD_GETW(s->a[i].g_proj_w, a + ".global_proj.weight");
+            PD_GETW(s->a[i].g_proj_b, a + ".global_proj.bias");
+        }
+    }
+    s->gf.clear();
+    if (n_global > 0 && global_ffn) {
+        s->gf.assign(n, GFfnW{});
+        for (int i = 0; i < n; ++i) {
+            const std::string f = p + strf(".global_ffn_l.%d", i);
+            PD_GETW(s->gf[i].ln_w, f + ".layer_norm.weight");
+            PD_GETW(s->gf[i].ln_b, f + ".layer_norm.bias");
+            PD_GETW(s->gf[i].w1, f + ".ffn_1.weight");
+            PD_GETW(s->gf[i].b1, f + ".ffn_1.bias");
+            PD_GETW(s->gf[i].w2, f + ".ffn_2.weight");
+            PD_GETW(s->gf[i].b2, f + ".ffn_2.bias");
+        }
     }
     return PD_OK;
 }
@@ -323,14 +370,22 @@ int UNet::finalize() {
             PD_TRY(build_cuboid_tables(T, cfg.h >> lvl, cfg.w >> lvl, sp, padding_type, &g));
             cub_axis[lvl].push_back(g.axial_axis);
             cub_dev[lvl].emplace_back(nullptr);
-            PD_CHECK(g.axial_axis >= 0 || !precision, PD_ERR_ARG,
-                     "unet: PD_PRECISION_TF32 is built for the axial pattern (the shipped config); other cuboid patterns run "
-                     "with bf16 operands");
-            if (g.axial_axis < 0) {
+            PD_CHECK((g.axial_axis >= 0 && n_global == 0) || !precision, PD_ERR_ARG,
+                     "unet: PD_PRECISION_TF32 is built for the axial pattern without global vectors (the shipped config); other "
+                     "cuboid patterns and global vectors run with bf16 operands");
+            if (n_global > 0) cub_axis[lvl].back() = -1;   // the global keys ride the general kernel, axial layers included
+            if (g.axial_axis < 0 || n_global > 0) {
                 cub_dev[lvl].back().reset(new CuboidTablesDev());
                 PD_TRY(cub_dev[lvl].back()->upload(g));
             }
         }
+    }
+    if (n_global > 0) {
+        PD_GETW(gv_init, "init_global_vectors");
+        PD_GETW(gv_down_w, "down_layer_global_proj.0.weight");
+        PD_GETW(gv_down_b, "down_layer_global_proj.0.bias");
+        PD_GETW(gv_up_w, "up_layer_global_proj.0.weight");
+        PD_GETW(gv_up_b, "up_layer_global_proj.0.bias");
     }
     PD_GETW(pm_ln_w, "downsample_layers.0.norm.weight");
     PD_GETW(pm_ln_b, "downsample_layers.0.norm.bias");
@@ -371,6 +426,21 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
     b->e1 = ar.template take<float>((size_t)B * TE);
     b->temb = ar.template take<float>((size_t)B * TE);
     b->embs = ar.template take<float>((size_t)B * emb_total);
+    if (n_global > 0) {   // global vectors: B * K rows per level + their q|k|v, attention output, FFN hidden, split partials
+        const size_t M = (size_t)B * n_global;
+        for (int l = 0; l < 2; ++l) b->gv[l] = ar.template take<float>(M * C[l]);
+        b->g_qkv = ar.template take<float>(M * 3 * C1);
+        b->g_qkv_bf16 = ar.template take<bf16>(M * 3 * C1);
+        b->g_att = ar.template take<float>(M * C1);
+        b->g_mid = ar.template take<float>(M * 4 * C1);
+        size_t wsf = 0;
+        for (int l = 0; l < 2; ++l)
+            for (const auto& cd : cub_dev[l])
+                if (cd)
+                    wsf = std::max(wsf, global_attention_workspace_floats(B, cfg.num_heads, n_global, C[l] / cfg.num_heads,
+                                                                          cd->dev.num_cuboids * cd->dev.volume + n_global));
+        b->g_ws = ar.template take<float>(wsf);
+    }
     b->gn_sums = ar.template take<double>((size_t)num_gn_slots() * B * 128 * 2);
     b->split_flags = ar.template take<int>(kSplitFlagInts);
 }
@@ -494,6 +564,15 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
         // produced by the epilogue of the GEMM that last wrote x (conv2 / previous ffn_2).
         const bool ln_ready = fuse && (i > 0 || ln_fusable_conv(lvl));
         if (!ln_ready) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st, prec); }, "ln");
+        // global vectors (cuboid_transformer.py:819-822, 893-901): q|k|v rows of LayerNorm(global_vectors) through the shared
+        // global_qkv net - fp32 for the global queries, a bf16 copy as the extra keys / values of every cuboid
+        const int Kg = n_global, Mg = B * n_global, gsa = global_self_attn ? 1 : 0;
+        float *gv = b.gv[lvl], *g_qkv = b.g_qkv, *g_att = b.g_att, *g_mid = b.g_mid, *g_ws = b.g_ws;
+        bf16* g_qkv_bf16 = b.g_qkv_bf16;
+        if (Kg > 0)
+            pl.add([=](cudaStream_t st) {
+                return gv_linear(gv, aw.g_ln_w, aw.g_ln_b, aw.g_qkv_w, nullptr, nullptr, g_qkv, g_qkv_bf16, Mg, C, 3 * C, 0, st);
+            }, "gv.qkv");
         if (cub_axis[lvl][i] >= 0 && !prec && qkv_attn_supported(Tn, H, W, C, heads, cub_axis[lvl][i]) &&
             getenv("PD_NO_QKV_ATTN_FUSION") == nullptr) {
             // axial layer, bf16 operands: QKV projection + attention core in one kernel (qkv_attn.cu); q|k|v never exist
@@ -516,6 +595,28 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
                    axis == 0 ? "attn_T" : (axis == 1 ? "attn_H" : "attn_W"));
         } else {   // any other cuboid (shifted / padded / dilated / multi-axis): gather tables + flash-style kernel
             const CuboidDev cd = cub_dev[lvl][i]->dev;
+            if (Kg > 0) {
+                pl.add([=](cudaStream_t st) {
+                    return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st, 1, g_qkv_bf16, Kg);
+                }, "attn_cuboid_gv");
+                // the global vectors' own update (:928-945, 951-952, 1137): attention over every slot (+ themselves), then
+                // global_vectors += global_proj(.)
+                pl.add([=](cudaStream_t st) {
+                    return global_attention(g_qkv, qkv, g_qkv_bf16, g_att, g_ws, B, N_tok, C, heads, Kg, gsa, cd, st);
+                }, "gv.attn");
+                pl.add([=](cudaStream_t st) {
+                    return gv_linear(g_att, nullptr, nullptr, aw.g_proj_w, aw.g_proj_b, gv, gv, nullptr, Mg, C, C, 0, st);
+                }, "gv.proj");
+                if (!s.gf.empty()) {   // global_ffn_l[i] (:1143-1144): pre-norm FFN with GELU on the K rows
+                    const GFfnW gw = s.gf[i];
+                    pl.add([=](cudaStream_t st) {
+                        return gv_linear(gv, gw.ln_w, gw.ln_b, gw.w1, gw.b1, nullptr, g_mid, nullptr, Mg, C, 4 * C, 1, st);
+                    }, "gv.ffn1");
+                    pl.add([=](cudaStream_t st) {
+                        return gv_linear(g_mid, nullptr, nullptr, gw.w2, gw.b2, gv, gv, nullptr, Mg, 4 * C, C, 0, st);
+                    }, "gv.ffn2");
+                }
+            } else
             pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
                    "attn_cuboid");
         }
@@ -711,6 +812,12 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         const float *pt = pos_T, *ph = pos_H, *pw = pos_W;
         const int Tn = T;
         pl.add([=](cudaStream_t st) { return pos_embed_add(x, pt, ph, pw, B, Tn, H, W, c0, st); }, "pos_embed");
+        if (n_global > 0) {   // init_global_vectors.expand(batch, K, C) (cuboid_transformer_unet.py:432-434)
+            const float* gi = gv_init;
+            float* gv0 = b.gv[0];
+            const int Kg = n_global;
+            pl.add([=](cudaStream_t st) { return gv_broadcast(gi, gv0, B, Kg, c0, st); }, "gv.init");
+        }
         pl.scope.clear();
     }
     // ---- down path ----
@@ -742,6 +849,13 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         GemmOp op;
         PD_TRY(gemm_make(&op, pm, geom(GemmGeom::linear(B * T * HW / 4, 4 * C0)), pm_w, C1, e));
         pl.add_gemm(op, "down.reduction");
+        if (n_global > 0) {   // down_layer_global_proj (cuboid_transformer_unet.py:449-450)
+            const float *w = gv_down_w, *bb = gv_down_b;
+            float *g0 = b.gv[0], *g1 = b.gv[1];
+            const int Mg = B * n_global, c0 = C0, c1 = C1;
+            pl.add([=](cudaStream_t st) { return gv_linear(g0, nullptr, nullptr, w, bb, nullptr, g1, nullptr, Mg, c0, c1, 0, st); },
+                   "down.gv_proj");
+        }
     }
     for (int d = 0; d < cfg.depth[1]; ++d) {
         PD_TRY(add_resblock(pl, b, B, 1, down_res[1], 1, &gn_slot, &down_stack[1][d], x_ready));
@@ -771,6 +885,13 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         GemmOp op;
         PD_TRY(make_conv(&op, up, GemmGeom::conv(B, T, H, W, C1, 1, 3, 3), up_w, C0, e, b, &x_ready));
         pl.add_gemm(op, "up.conv");
+        if (n_global > 0) {   // up_layer_global_proj (cuboid_transformer_unet.py:489-490)
+            const float *w = gv_up_w, *bb = gv_up_b;
+            float *g0 = b.gv[0], *g1 = b.gv[1];
+            const int Mg = B * n_global, c0 = C0, c1 = C1;
+            pl.add([=](cudaStream_t st) { return gv_linear(g1, nullptr, nullptr, w, bb, nullptr, g0, nullptr, Mg, c1, c0, 0, st); },
+                   "up.gv_proj");
+        }
     }
     for (int d = 0; d < cfg.depth[0]; ++d) {
         PD_TRY(add_resblock(pl, b, B, 0, up_res[0], 2, &gn_slot, &up_stack[0][d], x_ready));

@@ -14,14 +14,20 @@ struct ResW {   // TimeEmbedResBlock
 struct AttnW {  // CuboidSelfAttentionLayer
     const float *ln_w, *ln_b, *table, *proj_b;
     bf16 *qkv_w, *proj_w;
+    // global vectors (fp32 weights in the reference layout, used as loaded): global_vec_norm, global_qkv, global_proj
+    const float *g_ln_w = nullptr, *g_ln_b = nullptr, *g_qkv_w = nullptr, *g_proj_w = nullptr, *g_proj_b = nullptr;
 };
 struct FfnW {   // PositionwiseFFN
     const float *ln_w, *ln_b, *b1, *b2;
     bf16 *w1, *w2;
 };
+struct GFfnW {  // PositionwiseFFN of the global vectors (global_ffn_l), fp32 weights as loaded
+    const float *ln_w, *ln_b, *w1, *b1, *w2, *b2;
+};
 struct StackW {  // StackCuboidSelfAttentionBlock: n x (attn, ffn), n = number of cuboid layers of the level's pattern
     std::vector<AttnW> a;
     std::vector<FfnW> f;
+    std::vector<GFfnW> gf;   // empty without global vectors / use_global_vector_ffn
 };
 
 class UNet {
@@ -29,7 +35,8 @@ public:
     struct Bufs;
     struct BatchPlan;
 
-    UNet(const pd_unet_config& c, const pd_unet_pattern* pattern);
+    // n_global > 0: global vectors (cuboid_transformer_unet.py:55-60 with separate_global_qkv=False, global_dim_ratio=1)
+    UNet(const pd_unet_config& c, const pd_unet_pattern* pattern, int n_global = 0, int global_ffn = 1, int global_self_attn = 0);
     ~UNet();
     int validate() const;
     int finalize();
@@ -53,7 +60,9 @@ public:
     int C0, C1, T, TE;
     // attention layers of each level's stack block (block_attn_patterns) and their geometry tables (built in finalize)
     std::vector<CuboidLayerSpec> layers[2];
-    int padding_type = 0;   // 0 = 'zeros', 1 = 'ignore'
+    int padding_type = 0;   // 0 = 'zeros', 1 = 'ignore', 2 = 'nearest'
+    int n_global = 0;       // num_global_vectors
+    bool global_ffn = true, global_self_attn = false;
     bool all_axial = true;
     WeightStore ws;
     bool finalized = false;
@@ -111,6 +120,7 @@ private:
     const float *first_skip_b = nullptr, *pos_T = nullptr, *pos_H = nullptr, *pos_W = nullptr;
     const float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
     const float *pm_ln_w = nullptr, *pm_ln_b = nullptr, *up_b = nullptr, *final_b = nullptr;
+    const float *gv_init = nullptr, *gv_down_w = nullptr, *gv_down_b = nullptr, *gv_up_w = nullptr, *gv_up_b = nullptr;
     DevMem first_gn_pad, emb_cat;
     int emb_total = 0, emb_off[4] = {0, 0, 0, 0};
 };

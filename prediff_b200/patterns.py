@@ -111,7 +111,10 @@ def layer_geometry(data_shape, size0, strategy, shift0, padding_type="zeros"):
                  rel  int32 (volume): code of the in-cuboid position such that
                       relative_position_index[i, j] == rel[i] - rel[j] + rel_off,
                  rel_off int,
-                 dst  int32 (num_cuboids * volume) or None: 'nearest' padding only - the token the slot's result is written to).
+                 dst  int32 (num_cuboids * volume) or None: 'nearest' padding only - the token the slot's result is written to,
+                 gmask int32 (num_cuboids * volume) or None: 'ignore' padding only - 1 = the slot is visible to the queries of
+                      the global vectors. The reference flattens the validity grid of the padded, rolled frame in RASTER
+                      order and applies it to the cuboid-ordered keys as it is (cuboid_transformer.py:915-945); so is this).
     The label / validity rules restate compute_cuboid_self_attention_mask (cuboid_transformer.py:470-528):
     mask[c, i, j] = lab[c, i] == lab[c, j] and both >= 0.
     """
@@ -165,10 +168,17 @@ def layer_geometry(data_shape, size0, strategy, shift0, padding_type="zeros"):
                 continue
             tok[c, i] = (src[0] * dims[1] + src[1]) * dims[2] + src[2] if valid else -1
             lab[c, i] = -1 if (not valid and padding_type == "ignore") else label
+    gmask = None
+    if padding_type == "ignore":
+        g = np.zeros(padded, np.int32)
+        g[:dims[0], :dims[1], :dims[2]] = 1
+        if any_shift:
+            g = np.roll(g, [-v for v in shift], (0, 1, 2))
+        gmask = np.ascontiguousarray(g).reshape(-1)
     b0 = tuple(int(v) for v in size0)   # the index buffer is built from the constructor's cuboid size and sliced
     s1, s2 = (2 * b0[1] - 1) * (2 * b0[2] - 1), 2 * b0[2] - 1
     i = np.arange(vol)
     rel = ((i // (b0[1] * b0[2])) * s1 + ((i // b0[2]) % b0[1]) * s2 + i % b0[2]).astype(np.int32)
     rel_off = (b0[0] - 1) * s1 + (b0[1] - 1) * s2 + (b0[2] - 1)
     return dict(size=size, shift=shift, pad=pad, num_cuboids=nc, volume=vol, tok=tok.reshape(-1), lab=lab.reshape(-1),
-                rel=rel, rel_off=int(rel_off), dst=None if dst is None else dst.reshape(-1))
+                rel=rel, rel_off=int(rel_off), dst=None if dst is None else dst.reshape(-1), gmask=gmask)

@@ -2,7 +2,8 @@
 (src/prediff/models/cuboid_transformer/cuboid_transformer_unet.py:23-493) over the CUDA implementation.
 
 Same constructor argument names, `forward(x, t, cond, verbose=False)` contract, `state_dict()` key names and
-shapes. Built: two levels, patch-merge / upsample, GELU FFN, relative position bias, no global vectors, and every
+shapes. Built: two levels, patch-merge / upsample, GELU FFN, relative position bias, global vectors (num_global_vectors
+<= 32 with the shared global_qkv net: separate_global_qkv=False, global_dim_ratio=1), and every
 registered `block_attn_patterns` name (axial - the shipped SEVIR-LR config, on its own fast path - full, divided_st,
 video_swin_PxM, spatial_lg_M, axial_space_dilate_K; prediff_b200/patterns.py) with 'zeros', 'ignore' or 'nearest' padding;
 anything else raises NotImplementedError at construction - there is no fallback path.
@@ -36,7 +37,8 @@ class _CUnetPattern(ctypes.Structure):
 
 def _unsupported(what):
     raise NotImplementedError(f"prediff_b200.CuboidTransformerUNet: {what} is not built (only the SEVIR-LR "
-                              "configuration family: registered self-attention patterns, 2 levels, no global vectors)")
+                              "configuration family: registered self-attention patterns, 2 levels, global vectors with the "
+                              "shared q|k|v net)")
 
 
 class CuboidTransformerUNet(nn.Module):
@@ -48,7 +50,8 @@ class CuboidTransformerUNet(nn.Module):
                  block_cuboid_shift_size=((0, 0, 0), (0, 0, 0)), num_heads=4, attn_drop=0.0, proj_drop=0.0,
                  ffn_drop=0.0, ffn_activation="gelu", gated_ffn=False, norm_layer="layer_norm", use_inter_ffn=True,
                  hierarchical_pos_embed=False, pos_embed_type="t+h+w", padding_type="zeros", checkpoint_level=0,
-                 use_relative_pos=True, self_attn_use_final_proj=True, num_global_vectors=0,
+                 use_relative_pos=True, self_attn_use_final_proj=True, num_global_vectors=0, use_global_vector_ffn=True,
+                 use_global_self_attn=False, separate_global_qkv=False, global_dim_ratio=1,
                  time_embed_channels_mult=4, time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0,
                  unet_res_connect=True, max_batch=32, precision=None, streamk_ctas_per_sample=0, **ignored_init_modes):
         """`precision` (not a reference argument): "bf16" (default; env PD_PRECISION overrides the default) or "tf32" -
@@ -95,14 +98,21 @@ class CuboidTransformerUNet(nn.Module):
                   (not gated_ffn, "gated_ffn"), (norm_layer == "layer_norm", "norm_layer"), (use_inter_ffn, "use_inter_ffn"),
                   (not hierarchical_pos_embed, "hierarchical_pos_embed"), (pos_embed_type == "t+h+w", "pos_embed_type"),
                   (use_relative_pos, "use_relative_pos=False"), (self_attn_use_final_proj, "self_attn_use_final_proj"),
-                  (not num_global_vectors, "global vectors"), (time_embed_channels_mult == 4, "time_embed_channels_mult"),
+                  (0 <= int(num_global_vectors or 0) <= 32, "num_global_vectors > 32"),
+                  (not num_global_vectors or not separate_global_qkv, "separate_global_qkv=True"),
+                  (not num_global_vectors or global_dim_ratio == 1, "global_dim_ratio != 1"),
+                  (not num_global_vectors or precision == "bf16", "global vectors with precision='tf32'"),
+                  (time_embed_channels_mult == 4, "time_embed_channels_mult"),
                   (not time_embed_use_scale_shift_norm, "scale-shift norm"), (unet_res_connect, "unet_res_connect=False")]
         for ok, what in checks:
             if not ok:
                 _unsupported(what)
         self.cfg = UNetConfig(t_in=T_in, t_out=T_out, h=H, w=W, c=C, base_units=base_units, depth=tuple(depth),
                               num_heads=num_heads, patterns=tuple(patterns), padding_type=padding_type,
-                              explicit_layers=explicit)
+                              explicit_layers=explicit, num_global_vectors=int(num_global_vectors or 0),
+                              use_global_vector_ffn=bool(use_global_vector_ffn), use_global_self_attn=bool(use_global_self_attn))
+        self.num_global_vectors = self.cfg.num_global_vectors
+        self.use_global_vector = self.num_global_vectors > 0
         for lvl in range(2):
             if len(self.cfg.layers(lvl)) > _MAX_LAYERS:
                 _unsupported(f"{len(self.cfg.layers(lvl))} attention layers per block")
@@ -139,7 +149,7 @@ class CuboidTransformerUNet(nn.Module):
             cc = _CUnetConfig(c.t_in, c.t_out, c.h, c.w, c.c, c.base_units, (ctypes.c_int32 * 2)(*c.depth), c.num_heads,
                               self.max_batch)
             h = ctypes.c_void_p()
-            if tuple(c.patterns) == ("axial", "axial") and c.padding_type == "zeros":
+            if tuple(c.patterns) == ("axial", "axial") and c.padding_type == "zeros" and not c.num_global_vectors:
                 L.check(L.lib().pd_unet_create(ctypes.byref(cc), ctypes.byref(h)))
             else:
                 pt = _CUnetPattern()
@@ -152,7 +162,8 @@ class CuboidTransformerUNet(nn.Module):
                             pt.cuboid_size[lvl][i][a] = size[a]
                             pt.strategy[lvl][i][a] = 0 if strategy[a] == "l" else 1
                             pt.shift_size[lvl][i][a] = shift[a]
-                L.check(L.lib().pd_unet_create_ex(ctypes.byref(cc), ctypes.byref(pt), ctypes.byref(h)))
+                L.check(L.lib().pd_unet_create_gv(ctypes.byref(cc), ctypes.byref(pt), c.num_global_vectors,
+                                                  int(c.use_global_vector_ffn), int(c.use_global_self_attn), ctypes.byref(h)))
             self._handle = h
             self._dirty = True
         return self._handle

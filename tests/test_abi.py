@@ -39,6 +39,19 @@ def test_unet_and_vae_weight_specs_match_reference_keys():
         spec = [(n, tuple(s)) for n, s in Wt.unet_param_spec(cfg)]
         assert m.weight_spec_from_library() == spec
         assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == spec
+    # global vectors (cuboid_transformer_unet.py:124-126, 167-191; cuboid_transformer.py:777-810, 1054-1068): the extra keys, in
+    # the reference's registration order (pinned against the reference's state_dict by tests/golden/gen_golden.py::ref_unet)
+    import dataclasses
+    for gffn, pats in ((True, ("axial", "axial")), (False, ("video_swin_2x8", "spatial_lg_4"))):
+        cfg = dataclasses.replace(Wt.TINY_UNET, num_global_vectors=4, use_global_vector_ffn=gffn, patterns=pats)
+        m = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
+                                  depth=list(cfg.depth), num_heads=cfg.num_heads, block_attn_patterns=list(pats),
+                                  num_global_vectors=4, use_global_vector_ffn=gffn, use_global_self_attn=True)
+        spec = [(n, tuple(s)) for n, s in Wt.unet_param_spec(cfg)]
+        assert spec[0] == ("init_global_vectors", (4, 64))
+        assert m.weight_spec_from_library() == spec
+        assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == spec
+        assert any(".global_ffn_l." in n for n, _ in spec) == gffn
     full = Wt.UNetConfig()
     assert sum(int(np.prod(s)) for _, s in Wt.unet_param_spec(full)) == 136817538
     for cfg in (Wt.TINY_VAE, Wt.VAEConfig()):
@@ -98,8 +111,10 @@ def test_unsupported_configs_fail_loudly():
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], block_attn_patterns="video_swin_3x5")  # not registered
     with pytest.raises(NotImplementedError):
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], padding_type="reflect")   # not one of the reference's three
-    with pytest.raises(NotImplementedError):
-        CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], num_global_vectors=8)
+    for kw in (dict(num_global_vectors=8, separate_global_qkv=True), dict(num_global_vectors=8, global_dim_ratio=2),
+               dict(num_global_vectors=33), dict(num_global_vectors=8, precision="tf32")):
+        with pytest.raises(NotImplementedError):
+            CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], **kw)
     with pytest.raises(NotImplementedError):
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], depth=[2, 2, 2])
     with pytest.raises(L.PDError):  # rejected by the C++ validate(): 24x24 latents do not tile

@@ -165,6 +165,50 @@ def test_geometry_tables_vs_oracle(case):
     assert np.array_equal(np.sort(t), np.arange(dims[0] * dims[1] * dims[2]))
 
 
+def global_attention_from_tables(qkv, gqkv, heads, geo, self_attn):
+    """What the CUDA path computes for the global vectors, in numpy: every cuboid's queries see the K global keys as extra
+    unmasked columns; the global queries attend over the slot list (`tok`, hidden where `gmask` is 0) + themselves."""
+    B, T, H, W, C3 = qkv.shape
+    C, hd = C3 // 3, C3 // 3 // heads
+    K = gqkv.shape[1]
+    tok, gm = geo["tok"], geo["gmask"]
+    rows = np.concatenate([qkv.reshape(B, T * H * W, C3), np.zeros((B, 1, C3), qkv.dtype)], axis=1).astype(np.float64)
+    g = gqkv.astype(np.float64).reshape(B, K, 3, heads, hd)
+    y = rows[:, tok].reshape(B, -1, 3, heads, hd)                      # (B, slots, 3, heads, hd), tok == -1: the zero row
+    k_all, v_all = y[:, :, 1], y[:, :, 2]
+    vis = np.ones(len(tok), bool) if gm is None else gm > 0
+    if self_attn:
+        k_all, v_all = np.concatenate([k_all, g[:, :, 1]], 1), np.concatenate([v_all, g[:, :, 2]], 1)
+        vis = np.concatenate([vis, np.ones(K, bool)])
+    s = np.einsum("bqhd,bkhd->bhqk", g[:, :, 0] * hd ** -0.5, k_all)
+    s = np.where(vis, s, -np.inf)
+    p = np.exp(s - s.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    return np.einsum("bhqk,bkhd->bqhd", p, v_all).reshape(B, K, C)
+
+
+_GV_GEOM = [(c[1], c[3], c[4], c[5], c[6], c[7], c[8], c[9]) for c in PC.GV_LAYER_CASES]
+
+
+@pytest.mark.parametrize("case", _GV_GEOM, ids=[c[0] for c in PC.GV_LAYER_CASES])
+def test_global_vector_tables_vs_oracle(case):
+    """The slot list + gmask the global-attention kernel walks reproduce the pinned oracle's new global vectors."""
+    dims, heads, size, strat, shift, pad, K, gsa = case
+    hd = 8
+    C = heads * hd
+    rng = np.random.Generator(np.random.PCG64(13))
+    qkv = rng.standard_normal((2, *dims, 3 * C), dtype=np.float32)
+    gqkv = rng.standard_normal((2, K, 3 * C), dtype=np.float32)
+    n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
+    table = (0.3 * rng.standard_normal((n_rel, heads), dtype=np.float32))
+    _, want = O.cuboid_attention_core(torch.from_numpy(qkv), torch.from_numpy(table), heads, size, tuple(strat), shift, pad,
+                                      gqkv=torch.from_numpy(gqkv), global_self_attn=gsa)
+    geo = P.layer_geometry(dims, size, tuple(strat), shift, pad)
+    assert (geo["gmask"] is not None) == (pad == "ignore")
+    got = global_attention_from_tables(qkv, gqkv, heads, geo, gsa)
+    assert maxrel(got, want) < 1e-5
+
+
 @pytest.mark.parametrize("case", GEOM_CASES, ids=[f"{c[0]}-{c[2]}-{c[3]}-{c[4]}-{c[5]}" for c in GEOM_CASES])
 def test_c_abi_tables_equal_python_tables(case):
     """pd_cuboid_tables (host-only C++ builder the UNet plan uses) == prediff_b200.patterns.layer_geometry."""
@@ -190,6 +234,13 @@ def test_c_abi_tables_equal_python_tables(case):
     assert rd == (0 if geo["dst"] is None else 1)
     if geo["dst"] is not None:
         assert np.array_equal(dst, geo["dst"])
+    gm = np.full(n, -7, np.int32)
+    rg = L.lib().pd_cuboid_tables_gmask(*dims, i3(*size), i3(*[0 if s == "l" else 1 for s in strat]), i3(*shift),
+                                        {"zeros": 0, "ignore": 1, "nearest": 2}[pad], gm.ctypes.data_as(ctypes.c_void_p),
+                                        ctypes.c_int64(n))
+    assert rg == (0 if geo["gmask"] is None else 1)
+    if geo["gmask"] is not None:
+        assert np.array_equal(gm, geo["gmask"])
     is_axial = sum(s > 1 for s in geo["size"]) == 1 and geo["size"] == tuple(size) and max(geo["size"]) <= 16 \
         and all(geo["size"][a] in (1, dims[a]) for a in range(3)) and not any(geo["shift"])
     assert (rc > 0) == is_axial
