@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kGaThreads) global_attention_kernel(const floa
             const float sum = warp_sum(p0 + p1);
             s_p[g][lane] = p0;
             s_p[g][lane + 32] = p1;
+            __syncwarp();   // every lane has read s_m[g] before lane 0 replaces it
             if (lane == 0) {
                 s_m[g] = m_new;
                 s_l[g] = s_l[g] * alpha + sum;
