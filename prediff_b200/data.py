@@ -8,9 +8,14 @@ bit-identical values - but the events cross PCIe as uint8 from pinned memory on 
 fp32 batch the reference moves) and are windowed / rescaled / transposed by one kernel (`pd_sevir_windows`, csrc/io.cu),
 double-buffered so the copy of batch i+1 runs under the sampling of batch i.
 
-The HDF5 / catalog layer of the reference (h5py, pandas filters, `_load_event_batch`) is not rebuilt: `events` is any
-uint8 array of shape (num_events, H, W, raw_seq_len) - a numpy array, an `np.load(..., mmap_mode="r")` memory map of an
-exported event file, or an `h5py.Dataset` (`f["vil"]`), which has the same indexing interface.
+`events` is any uint8 array of shape (num_events, H, W, raw_seq_len) - a numpy array, an `np.load(..., mmap_mode="r")`
+memory map of an exported event file, an `h5py.Dataset` (`f["vil"]`), or a `SEVIRCatalogEvents`: the reference's catalog
+layer (sevir_dataloader.py:212-300, 360-390 - catalog CSV, date / datetime / catalog filters, co-located image types,
+duplicate-id removal, optional shuffle, one open file per HDF5 name) restated over pandas, which presents the selected
+events, in the reference's order, behind the same indexing interface. `SEVIRDataLoader.from_catalog(...)` takes the
+reference constructor's catalog arguments. Files are opened with `h5py.File(path, "r")`; h5py is absent from this image, so
+the opener is injectable (`open_file=`: any callable path -> mapping with a "vil" dataset) and a missing h5py without an
+opener is an error at construction, not a fallback.
 """
 import numpy as np
 import torch
@@ -19,6 +24,109 @@ from . import _lib as L
 
 PREPROCESS_SCALE = {"sevir": 1 / 47.54, "01": 1 / 255}      # sevir_dataloader.py:25-44, 'vil' entries
 PREPROCESS_OFFSET = {"sevir": -33.44, "01": 0.0}
+
+
+def _default_open_file(path):
+    try:
+        import h5py
+    except ImportError as e:
+        raise L.PDError("prediff_b200.data.SEVIRCatalogEvents: h5py is not importable - pass open_file= (a callable "
+                        "path -> mapping with a 'vil' dataset of shape (n, H, W, raw_seq_len) uint8)") from e
+    return h5py.File(path, "r")
+
+
+class SEVIRCatalogEvents:
+    """The catalog layer of the reference's SEVIRDataLoader for the 'vil' data type (sevir_dataloader.py:212-300):
+    `catalog` (CSV path or DataFrame) filtered by start_date < time_utc <= end_date (:239-242), `datetime_filter` (:243-244)
+    and `catalog_filter` ('default' = pct_missing == 0, :246-249); `_compute_samples` (:256-271): rows of the requested image
+    types, ids that have every requested type exactly once (repeated ids are dropped entirely, as the reference does),
+    one (file name, file index) per id in the reference's order (ids sorted by `groupby`, or `DataFrame.sample(frac=1,
+    random_state=shuffle_seed)` when shuffled); `_open_files` (:287-299): one handle per distinct file name.
+    Indexing (`events[e0:e1]`, `events[i]`) = `_read_data` (:360-390): `file["vil"][index:index + 1]` per event,
+    concatenated -> uint8 (n, H, W, raw_seq_len)."""
+
+    dtype = np.dtype(np.uint8)
+
+    def __init__(self, sevir_catalog, sevir_data_dir, data_types=("vil",), start_date=None, end_date=None, datetime_filter=None,
+                 catalog_filter="default", shuffle=False, shuffle_seed=1, open_file=None, verbose=False):
+        import pandas as pd
+        if "vil" not in tuple(data_types):
+            raise NotImplementedError("prediff_b200.data.SEVIRCatalogEvents: the PreDiff path reads the 'vil' data type")
+        if "lght" in tuple(data_types):
+            raise NotImplementedError("prediff_b200.data.SEVIRCatalogEvents: lightning ('lght') gridding is not on the path")
+        self.data_types = list(data_types)
+        cat = pd.read_csv(sevir_catalog, parse_dates=["time_utc"], low_memory=False) if isinstance(sevir_catalog, str) \
+            else sevir_catalog
+        if start_date is not None:
+            cat = cat[cat.time_utc > start_date]
+        if end_date is not None:
+            cat = cat[cat.time_utc <= end_date]
+        if datetime_filter:
+            cat = cat[datetime_filter(cat.time_utc)]
+        if catalog_filter is not None:
+            if isinstance(catalog_filter, str) and catalog_filter == "default":
+                catalog_filter = lambda c: c.pct_missing == 0   # noqa: E731
+            cat = cat[catalog_filter(cat)]
+        self.catalog = cat
+        self.sevir_data_dir = sevir_data_dir
+        self.shuffle, self.shuffle_seed = bool(shuffle), int(shuffle_seed)
+        self._compute_samples()
+        self.reset()   # the reference constructor ends with reset(): a shuffled loader starts from the SECOND permutation
+        opener = open_file or _default_open_file
+        self._files = {}
+        for f in np.unique(self._samples["vil_filename"].values):   # _open_files
+            if verbose:
+                print("Opening HDF5 file for reading", f)
+            self._files[f] = opener(f"{self.sevir_data_dir}/{f}")
+        first = self._files[self._samples["vil_filename"].iloc[0]]["vil"] if len(self._samples) else None
+        self._event_shape = tuple(int(v) for v in first.shape[1:]) if first is not None else (0, 0, 0)
+
+    def _compute_samples(self):
+        import pandas as pd
+        imgt = self.data_types
+        cat = self.catalog
+        filt = cat[np.logical_or.reduce([cat.img_type == i for i in imgt])]
+        n_types = filt.groupby("id")["img_type"].nunique()
+        n_rows = filt.groupby("id").size()
+        keep = n_rows.index[(n_types == len(imgt)) & (n_rows == len(imgt))]   # every requested type present, no repeated id
+        filt = filt[filt.id.isin(keep)]
+        rows = filt[filt.img_type == "vil"].sort_values("id", kind="stable")   # groupby('id') yields ids in sorted order
+        self._samples = pd.DataFrame({"id": rows.id.values, "vil_filename": rows.file_name.values,
+                                      "vil_index": rows.file_index.values.astype(np.int64)})
+        if self.shuffle:
+            self.shuffle_samples()
+
+    def shuffle_samples(self):
+        self._samples = self._samples.sample(frac=1, random_state=self.shuffle_seed)
+
+    def reset(self, shuffle=None):
+        """Start of an epoch (sevir_dataloader.py:508-515): reshuffles the CURRENT order with the same seed."""
+        if self.shuffle if shuffle is None else shuffle:
+            self.shuffle_samples()
+
+    def close(self):
+        for f in self._files.values():
+            if hasattr(f, "close"):
+                f.close()
+        self._files = {}
+
+    @property
+    def shape(self):
+        return (len(self._samples),) + self._event_shape
+
+    def __len__(self):
+        return len(self._samples)
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            return self[int(key):int(key) + 1][0]
+        if not isinstance(key, slice):
+            raise TypeError("SEVIRCatalogEvents is indexed by an event number or a slice of event numbers")
+        rows = self._samples.iloc[key]
+        out = np.empty((len(rows),) + self._event_shape, np.uint8)
+        for k, (fname, idx) in enumerate(zip(rows["vil_filename"].values, rows["vil_index"].values)):
+            out[k] = self._files[fname]["vil"][int(idx):int(idx) + 1][0]
+        return out
 
 
 class SEVIRDataLoader:
@@ -50,6 +158,16 @@ class SEVIRDataLoader:
         self.prefetch = max(1, int(prefetch))
         self._copy_stream = None
         self._slots = None
+
+    @classmethod
+    def from_catalog(cls, sevir_catalog, sevir_data_dir, data_types=("vil",), start_date=None, end_date=None,
+                     datetime_filter=None, catalog_filter="default", shuffle=False, shuffle_seed=1, open_file=None,
+                     verbose=False, **loader_kwargs):
+        """The reference constructor's catalog arguments (sevir_dataloader.py:99-122) -> a loader over the selected events."""
+        events = SEVIRCatalogEvents(sevir_catalog, sevir_data_dir, data_types=data_types, start_date=start_date, end_date=end_date,
+                                    datetime_filter=datetime_filter, catalog_filter=catalog_filter, shuffle=shuffle,
+                                    shuffle_seed=shuffle_seed, open_file=open_file, verbose=verbose)
+        return cls(events, data_types=("vil",), **loader_kwargs)
 
     # ---- the reference's bookkeeping (sevir_dataloader.py:310-358, :517-521) ----
     @property

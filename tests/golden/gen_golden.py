@@ -230,6 +230,35 @@ def gen_loader():
     save("loader", **out)
 
 
+def gen_catalog():
+    """The catalog layer of the unmodified reference SEVIRDataLoader (sevir_dataloader.py:212-300, 360-390, 541-576): the
+    constructor run on a synthetic catalog with `h5py.File` replaced by an in-memory mapping (h5py and the dataset are absent
+    from the image) - the pandas filtering, sample order, shuffling, file bookkeeping and reads are the reference's own."""
+    import catalog_cases as CC
+    files = CC.catalog_files()
+    h5 = types.ModuleType("h5py")
+    h5.File = lambda path, mode="r": files[path.split("/data/", 1)[1]]
+    sys.modules["h5py"] = h5
+    from prediff.datasets.sevir.sevir_dataloader import SEVIRDataLoader
+    out = {}
+    for tag, (ckw, lkw) in CC.CASES.items():
+        ckw = dict(ckw)
+        dtypes = ckw.pop("data_types", ["vil"])
+        dl = SEVIRDataLoader(data_types=dtypes, raw_seq_len=CC.T_RAW, sample_mode="sequent", sevir_catalog=CC.catalog_frame(),
+                             sevir_data_dir="/data", preprocess=True, **ckw, **lkw)
+        out[f"{tag}_files"] = np.asarray([str(v) for v in dl._samples["vil_filename"].values])
+        out[f"{tag}_index"] = np.asarray(dl._samples["vil_index"].values, dtype=np.int64)
+        out[f"{tag}_len"] = np.asarray(len(dl))
+        for i in range(len(dl)):
+            out[f"{tag}_b{i}"] = np.asarray(dl[i]["vil"])
+        if ckw.get("shuffle"):   # every reset() reshuffles the current order with the same seed (:508-515, :273-274)
+            dl.reset()
+            out[f"{tag}_files_epoch2"] = np.asarray([str(v) for v in dl._samples["vil_filename"].values])
+            out[f"{tag}_index_epoch2"] = np.asarray(dl._samples["vil_index"].values, dtype=np.int64)
+        print(f"catalog {tag}: {len(dl._samples)} events, {len(dl)} batches")
+    save("catalog", **out)
+
+
 def gen_skill():
     """SEVIRSkillScore of the unmodified reference (datasets/sevir/evaluation.py). `torchmetrics` and `h5py` are absent
     from the image; the metric only uses torchmetrics.Metric as a state container (add_state / reset), so an inert
@@ -739,6 +768,8 @@ if __name__ == "__main__":
         gen_skill()
     if "loader" in todo:
         gen_loader()
+    if "catalog" in todo:
+        gen_catalog()
     if "patterns" in todo:
         gen_patterns()
     if "patterns_nearest" in todo:

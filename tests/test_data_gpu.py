@@ -86,3 +86,22 @@ def test_windows_abi_rejects_out_of_range():
     with pytest.raises(NotImplementedError):
         from prediff_b200.data import SEVIRDataLoader
         SEVIRDataLoader(ev.cpu().numpy(), sample_mode="random")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["default", "dates", "filters", "nofilter", "shuffle", "colocated"])
+def test_loader_from_catalog_matches_reference_loader(tag):
+    """SEVIRDataLoader.from_catalog (catalog filters -> event order -> per-event reads -> pinned staging -> window kernel)
+    against the batches of the unmodified reference SEVIRDataLoader built from the same synthetic catalog
+    (tests/golden/catalog.npz) - bit-exact."""
+    from prediff_b200.data import SEVIRDataLoader
+    from tests.golden import catalog_cases as CC
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "catalog.npz"))
+    files = CC.catalog_files()
+    ckw, lkw = CC.CASES[tag]
+    dl = SEVIRDataLoader.from_catalog(CC.catalog_frame(), "/data", open_file=lambda p: files[p[len("/data/"):]], **ckw, **lkw)
+    assert len(dl) == int(g[f"{tag}_len"])
+    for i in range(len(dl)):
+        assert np.array_equal(dl._idx_sample(i)["vil"].cpu().numpy(), g[f"{tag}_b{i}"])
+    for i, b in enumerate(dl):   # the prefetching iterator reads through the catalog layer too
+        assert np.array_equal(b.cpu().numpy(), g[f"{tag}_b{i}"])
