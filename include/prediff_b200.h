@@ -336,6 +336,10 @@ int pd_op_cuboid_attention_impl(const void* qkv_bf16, const float* bias_table, v
  * pd_op_cuboid_attention_gv: qkv bf16 [B][T][H][W][3C] and the global rows' q|k|v (gqkv_f32 [B][K][3C] and its bf16 copy)
  *   -> out bf16 [B][T][H][W][C] (local + local-to-global attention, :902-913) and gout fp32 [B][K][C] (global-to-local
  *   (+ global-to-global) attention, :928-945), both before their output projections. */
+/* pd_op_axial_attention_gv: pd_op_axial_attention with the sample's <= 16 global vectors as extra keys of every line (k | v
+ *   rows of gqkv_bf16 [B][K][3C]; unmasked, no position bias) - what the UNet runs for axial layers when K <= 16. */
+int pd_op_axial_attention_gv(const void* qkv_bf16, const float* bias_table, const void* gqkv_bf16, void* out_bf16, int B, int T,
+                             int H, int W, int C, int heads, int axis, int n_global, void* stream);
 int pd_cuboid_tables_gmask(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                            int padding_type, int32_t* gmask, int64_t capacity);
 int pd_op_gv_linear(const float* in, const float* ln_gamma, const float* ln_beta, const float* W, const float* bias,

@@ -190,6 +190,14 @@ int pd_op_axial_attention(const void* qkv, const float* bias_table, void* out, i
                            S(stream));
 }
 
+int pd_op_axial_attention_gv(const void* qkv, const float* bias_table, const void* gqkv_bf16, void* out, int B, int T, int H,
+                             int W, int C, int heads, int axis, int n_global, void* stream) {
+    PD_TRY(gemm_init());
+    PD_CHECK(n_global >= 1 && gqkv_bf16, PD_ERR_ARG, "pd_op_axial_attention_gv: needs 1..16 global vectors");
+    return axial_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T, H, W, C, heads, axis,
+                           S(stream), 0, static_cast<const bf16*>(gqkv_bf16), n_global);
+}
+
 int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
                      int padding_type, int32_t meta[12], int32_t* tok, int32_t* lab, int32_t* rel, int64_t capacity) {
     CuboidLayerSpec sp;

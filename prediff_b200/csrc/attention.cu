@@ -46,17 +46,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // in smem with cp.async (rows padded by 16 B so ldmatrix is bank-conflict free); per head the 16x16 score tile and
 // the 16xHD output come from warp-level mma.sync (the sequence is far too short to fill a 128-row tcgen05 tile:
 // this op is 0.25 % of the step's FLOPs), softmax stays in the accumulator registers.
-template <int HD>
+// GV: the sample's global vectors (cuboid_transformer.py:902-913) ride along as up to 16 more keys per line - k|v rows of gkv
+// [B][n_global][3C] staged beside the line, scores without position bias, never masked - one more 16-key tile through the same
+// fragments (the shipped config has no global vectors and runs the GV = false instantiation, unchanged).
+template <int HD, bool GV>
 __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __restrict__ qkv,
                                                               const float* __restrict__ bias_table,
                                                               bf16* __restrict__ out, int T, int H, int W, int C,
-                                                              int heads, int axis) {
+                                                              int heads, int axis, const bf16* __restrict__ gkv, int n_global) {
     grid_dep_launch();
     grid_dep_wait();
     extern __shared__ __align__(16) uint8_t smem_att[];
     bf16* s_qkv = reinterpret_cast<bf16*>(smem_att);  // [16][3C + 8]
     const int C3 = 3 * C;
     const int ld = C3 + 8;
+    bf16* s_g = s_qkv + (size_t)kMaxLine * ld;        // GV: [16][2C + 8] = k | v rows of the global vectors
+    const int ldg = 2 * C + 8;
     int L, stride, base;
     {
         const int line = blockIdx.x;
@@ -82,6 +87,16 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
             if (r < L) cp_async16(dst, qkv + (size_t)(base + r * stride) * C3 + v * 8);
             else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);  // padded tokens: finite (zero) rows
         }
+        if constexpr (GV) {
+            const bf16* grow = gkv + (size_t)(base / (T * H * W)) * n_global * C3 + C;   // the sample's rows, from the k part on
+            const int vpr = 2 * C / 8;
+            for (int i = threadIdx.x; i < kMaxLine * vpr; i += blockDim.x) {
+                const int r = i / vpr, v = i - r * vpr;
+                bf16* dst = s_g + (size_t)r * ldg + v * 8;
+                if (r < n_global) cp_async16(dst, grow + (size_t)r * C3 + v * 8);
+                else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
@@ -89,12 +104,16 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, tq = lane & 3;
     const float scale = rsqrtf((float)HD);
+    constexpr int NK = GV ? 8 : 4;   // scores per thread and row half: 4 local (+ 4 global) keys
     for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
         const bf16* sq = s_qkv + h * HD;
         const bf16* sk = s_qkv + C + h * HD;
         const bf16* sv = s_qkv + 2 * C + h * HD;
-        // ---- S = Q K^T : 16 x 16, two 8-wide key tiles ----
+        const bf16* sgk = s_g + h * HD;
+        const bf16* sgv = s_g + C + h * HD;
+        // ---- S = Q K^T : 16 x 16 (+ 16 global keys), 8-wide key tiles ----
         float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        float s2[4] = {0.f, 0.f, 0.f, 0.f}, s3[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
             uint32_t a[4], b[4];
@@ -102,13 +121,21 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
             ldmatrix_x4(b, sk + (size_t)((lane & 7) + 8 * (lane >> 4)) * ld + kk * 16 + 8 * ((lane >> 3) & 1));
             mma_bf16_16816(s0, a, b[0], b[1]);
             mma_bf16_16816(s1, a, b[2], b[3]);
+            if constexpr (GV) {
+                uint32_t bg[4];
+                ldmatrix_x4(bg, sgk + (size_t)((lane & 7) + 8 * (lane >> 4)) * ldg + kk * 16 + 8 * ((lane >> 3) & 1));
+                mma_bf16_16816(s2, a, bg[0], bg[1]);
+                mma_bf16_16816(s3, a, bg[2], bg[3]);
+            }
         }
-        // thread holds rows g, g+8; keys {2tq, 2tq+1} (s0) and {8+2tq, 9+2tq} (s1)
-        float p[2][4];  // [row half][key slot]
+        // thread holds rows g, g+8; keys {2tq, 2tq+1} (s0), {8+2tq, 9+2tq} (s1) and the same slots of the global tile (s2, s3)
+        float p[2][NK];  // [row half][key slot]
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh) {
             const int i = g + 8 * rh;
-            float v[4] = {s0[2 * rh], s0[2 * rh + 1], s1[2 * rh], s1[2 * rh + 1]};
+            float v[NK];
+            v[0] = s0[2 * rh]; v[1] = s0[2 * rh + 1]; v[2] = s1[2 * rh]; v[3] = s1[2 * rh + 1];
+            if constexpr (GV) { v[4] = s2[2 * rh]; v[5] = s2[2 * rh + 1]; v[6] = s3[2 * rh]; v[7] = s3[2 * rh + 1]; }
             const int j[4] = {2 * tq, 2 * tq + 1, 8 + 2 * tq, 9 + 2 * tq};
             float mx = -INFINITY;
 #pragma unroll
@@ -117,12 +144,19 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
                 else v[k] = -INFINITY;
                 mx = fmaxf(mx, v[k]);
             }
+            if constexpr (GV) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[4 + k] = (j[k] < n_global && i < L) ? v[4 + k] * scale : -INFINITY;
+                    mx = fmaxf(mx, v[4 + k]);
+                }
+            }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             if (mx == -INFINITY) mx = 0.f;  // padded query row
             float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NK; ++k) {
                 v[k] = __expf(v[k] - mx);
                 sum += v[k];
             }
@@ -130,14 +164,20 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             const float inv = sum > 0.f ? 1.f / sum : 0.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) p[rh][k] = v[k] * inv;
+            for (int k = 0; k < NK; ++k) p[rh][k] = v[k] * inv;
         }
         // P (C-fragment layout) is already the A fragment of the next mma: a0=(g, k lo), a1=(g+8, k lo), a2/a3 = k hi
-        uint32_t pa[4];
+        uint32_t pa[4], pg[4] = {0u, 0u, 0u, 0u};
         pa[0] = pack_bf16x2(p[0][0], p[0][1]);
         pa[1] = pack_bf16x2(p[1][0], p[1][1]);
         pa[2] = pack_bf16x2(p[0][2], p[0][3]);
         pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+        if constexpr (GV) {
+            pg[0] = pack_bf16x2(p[0][NK - 4], p[0][NK - 3]);
+            pg[1] = pack_bf16x2(p[1][NK - 4], p[1][NK - 3]);
+            pg[2] = pack_bf16x2(p[0][NK - 2], p[0][NK - 1]);
+            pg[3] = pack_bf16x2(p[1][NK - 2], p[1][NK - 1]);
+        }
         // ---- O = P V : 16 x HD ----
         bf16* o_lo = out + (size_t)(base + g * stride) * C + h * HD + 2 * tq;
         bf16* o_hi = out + (size_t)(base + (g + 8) * stride) * C + h * HD + 2 * tq;
@@ -148,6 +188,12 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
             float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
             mma_bf16_16816(o0, pa, b[0], b[1]);
             mma_bf16_16816(o1, pa, b[2], b[3]);
+            if constexpr (GV) {
+                uint32_t bg[4];
+                ldmatrix_x4_trans(bg, sgv + (size_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * ldg + 8 * (jn + (lane >> 4)));
+                mma_bf16_16816(o0, pg, bg[0], bg[1]);
+                mma_bf16_16816(o1, pg, bg[2], bg[3]);
+            }
             if (g < L) {
                 *reinterpret_cast<uint32_t*>(o_lo + 8 * jn) = pack_bf16x2(o0[0], o0[1]);
                 *reinterpret_cast<uint32_t*>(o_lo + 8 * jn + 8) = pack_bf16x2(o1[0], o1[1]);
@@ -611,7 +657,9 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
 }  // namespace
 
 int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int B, int T, int H, int W, int C, int heads,
-                    int axis, cudaStream_t st, int f32) {
+                    int axis, cudaStream_t st, int f32, const bf16* gkv, int n_global) {
+    PD_CHECK(n_global >= 0 && n_global <= kMaxLine && (n_global == 0 || (gkv && !f32)), PD_ERR_ARG,
+             "axial_attention: %d global vectors (at most %d, bf16 operands)", n_global, kMaxLine);
     PD_CHECK(axis >= 0 && axis <= 2, PD_ERR_ARG, "axial_attention: axis %d", axis);
     const int L = axis == 0 ? T : (axis == 1 ? H : W);
     PD_CHECK(L >= 1 && L <= kMaxLine, PD_ERR_SHAPE,
@@ -655,16 +703,23 @@ int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int
     }
     const bf16* qkv = static_cast<const bf16*>(qkv_v);
     bf16* out = static_cast<bf16*>(out_v);
-    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16);
+    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16) + (n_global ? (size_t)kMaxLine * (2 * C + 8) * sizeof(bf16) : 0);
 #define PD_LAUNCH_AX(HDV)                                                                                            \
     do {                                                                                                             \
         static bool attr_set = false;                                                                                \
         if (!attr_set) {                                                                                             \
-            PD_CUDA(cudaFuncSetAttribute(axial_attention_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+            PD_CUDA(cudaFuncSetAttribute((axial_attention_kernel<HDV, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         160 * 1024));                                                               \
+            PD_CUDA(cudaFuncSetAttribute((axial_attention_kernel<HDV, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          160 * 1024));                                                               \
             attr_set = true;                                                                                         \
         }                                                                                                            \
-        PD_LAUNCH((axial_attention_kernel<HDV>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, axis);    \
+        if (n_global)                                                                                                \
+            PD_LAUNCH((axial_attention_kernel<HDV, true>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, \
+                      axis, gkv, n_global);                                                                          \
+        else                                                                                                         \
+            PD_LAUNCH((axial_attention_kernel<HDV, false>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, \
+                      axis, gkv, n_global);                                                                          \
     } while (0)
     PD_CHECK(smem <= 160 * 1024, PD_ERR_SHAPE, "axial_attention: line of %zu bytes does not fit in smem", smem);
     switch (hd) {

@@ -29,8 +29,10 @@ int patch_merge_ln(const float* x, const float* gamma, const float* beta, void* 
 // `axis` (0=T, 1=H, 2=W) and head, relative-position bias table fp32 [2L-1][heads]; out bf16 [B][T][H][W][C].
 // Reference: cuboid_transformer.py:849-861,949 with cuboids (T,1,1)/(1,H,1)/(1,1,W) (patterns.py:34-36).
 // f32 = 1: qkv and out are fp32 (out tf32-rounded) and the whole core runs in fp32 on the CUDA cores.
+// gkv / n_global (bf16 mode only): q|k|v rows of the sample's global vectors [B][n_global][3C], n_global <= 16 - every
+// query also attends to their keys, unmasked and without position bias (cuboid_transformer.py:902-913).
 int axial_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
-                    int axis, cudaStream_t st, int f32 = 0);
+                    int axis, cudaStream_t st, int f32 = 0, const bf16* gkv = nullptr, int n_global = 0);
 // General cuboid self-attention core (any cuboid size, 'l' / 'd' strategy, shifted windows, end padding with
 // padding_type 'zeros' (0) or 'ignore' (1)): cuboid_transformer.py:812-966 without global vectors.
 struct CuboidLayerSpec {   // constructor arguments of one CuboidSelfAttentionLayer

@@ -373,7 +373,6 @@ int UNet::finalize() {
             PD_CHECK((g.axial_axis >= 0 && n_global == 0) || !precision, PD_ERR_ARG,
                      "unet: PD_PRECISION_TF32 is built for the axial pattern without global vectors (the shipped config); other "
                      "cuboid patterns and global vectors run with bf16 operands");
-            if (n_global > 0) cub_axis[lvl].back() = -1;   // the global keys ride the general kernel, axial layers included
             if (g.axial_axis < 0 || n_global > 0) {
                 cub_dev[lvl].back().reset(new CuboidTablesDev());
                 PD_TRY(cub_dev[lvl].back()->upload(g));
@@ -573,7 +572,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             pl.add([=](cudaStream_t st) {
                 return gv_linear(gv, aw.g_ln_w, aw.g_ln_b, aw.g_qkv_w, nullptr, nullptr, g_qkv, g_qkv_bf16, Mg, C, 3 * C, 0, st);
             }, "gv.qkv");
-        if (cub_axis[lvl][i] >= 0 && !prec && qkv_attn_supported(Tn, H, W, C, heads, cub_axis[lvl][i]) &&
+        if (cub_axis[lvl][i] >= 0 && !prec && Kg == 0 && qkv_attn_supported(Tn, H, W, C, heads, cub_axis[lvl][i]) &&
             getenv("PD_NO_QKV_ATTN_FUSION") == nullptr) {
             // axial layer, bf16 operands: QKV projection + attention core in one kernel (qkv_attn.cu); q|k|v never exist
             const int axis = cub_axis[lvl][i];
@@ -589,16 +588,27 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             PD_TRY(gemm_make(&op, ln, geom(GemmGeom::linear(P, C)), aw.qkv_w, 3 * C, e));
             pl.add_gemm(op, "qkv");
         }
-        if (cub_axis[lvl][i] >= 0) {
+        static const bool gv_no_axial = getenv("PD_GV_NO_AXIAL") != nullptr;   // A/B: global keys through the general kernel
+        const bool axial_line = cub_axis[lvl][i] >= 0 && (Kg == 0 || (Kg <= 16 && !gv_no_axial));
+        if (axial_line) {
+            // axial layer: one block per line (with global vectors: their <= 16 keys as a second key tile of the same kernel)
             const int axis = cub_axis[lvl][i];
-            pl.add([=](cudaStream_t st) { return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st, prec); },
-                   axis == 0 ? "attn_T" : (axis == 1 ? "attn_H" : "attn_W"));
+            pl.add([=](cudaStream_t st) {
+                return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st, prec, Kg ? g_qkv_bf16 : nullptr, Kg);
+            }, axis == 0 ? "attn_T" : (axis == 1 ? "attn_H" : "attn_W"));
         } else {   // any other cuboid (shifted / padded / dilated / multi-axis): gather tables + flash-style kernel
             const CuboidDev cd = cub_dev[lvl][i]->dev;
-            if (Kg > 0) {
+            if (Kg > 0)
                 pl.add([=](cudaStream_t st) {
                     return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st, 1, g_qkv_bf16, Kg);
                 }, "attn_cuboid_gv");
+            else
+                pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
+                       "attn_cuboid");
+        }
+        if (Kg > 0) {
+            {
+                const CuboidDev cd = cub_dev[lvl][i]->dev;
                 // the global vectors' own update (:928-945, 951-952, 1137): attention over every slot (+ themselves), then
                 // global_vectors += global_proj(.)
                 pl.add([=](cudaStream_t st) {
@@ -616,9 +626,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
                         return gv_linear(g_mid, nullptr, nullptr, gw.w2, gw.b2, gv, gv, nullptr, Mg, 4 * C, C, 0, st);
                     }, "gv.ffn2");
                 }
-            } else
-            pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
-                   "attn_cuboid");
+            }
         }
         }
         if (C == 256 && !prec && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {

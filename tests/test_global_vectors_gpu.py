@@ -115,6 +115,39 @@ def test_cuboid_attention_gv_op_vs_oracle(case):
     assert torch.equal(o1, out) and torch.equal(g1, gout)   # deterministic (fixed split order)
 
 
+@pytest.mark.parametrize("axis,T,H,W,C,K", [(0, 13, 16, 16, 256, 8), (1, 13, 16, 16, 256, 16), (2, 13, 8, 8, 512, 8),
+                                            (0, 13, 8, 8, 512, 3), (2, 6, 8, 12, 64, 1)])
+def test_axial_attention_with_global_keys_vs_oracle_and_general_kernel(axis, T, H, W, C, K):
+    """The axial fast-path kernel with the global keys as a second key tile: vs the oracle core and vs the general kernel
+    (same fp32 math, two bf16 roundings)."""
+    heads, B = 4, 2
+    g = torch.Generator().manual_seed(23)
+    qkv = torch.randn(B, T, H, W, 3 * C, generator=g).bfloat16()
+    gqkv = torch.randn(B, K, 3 * C, generator=g).bfloat16()
+    Lx = (T, H, W)[axis]
+    table = 0.5 * torch.randn(2 * Lx - 1, heads, generator=g)
+    size = [1, 1, 1]
+    size[axis] = Lx
+    qd, td, gd = qkv.cuda(), table.cuda(), gqkv.cuda()
+    out = torch.full((B, T, H, W, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib().pd_op_axial_attention_gv(L.ptr(qd), L.ptr(td), L.ptr(gd), L.ptr(out), B, T, H, W, C, heads, axis, K,
+                                             L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref, _ = O.cuboid_attention_core(qkv.float(), table, heads, size, ("l", "l", "l"), (0, 0, 0), "zeros", gqkv=gqkv.float())
+    assert torch.isfinite(out.float()).all()
+    r, m = errs(out.float(), ref)
+    gen = torch.empty_like(out)
+    gout = torch.empty(B, K, C, device="cuda")
+    gd32 = gqkv.float().cuda()
+    L.check(L.lib().pd_op_cuboid_attention_gv(L.ptr(qd), L.ptr(td), L.ptr(gd32), L.ptr(gd), L.ptr(gen), L.ptr(gout), B, T, H, W, C,
+                                              heads, I3(*size), I3(0, 0, 0), I3(0, 0, 0), 0, K, 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    r2, m2 = errs(out.float(), gen.float().cpu())
+    print(f"axial + {K} global keys, axis {axis}: vs oracle rel_rms={r:.2e} max={m:.2e}; vs general kernel {r2:.2e} / {m2:.2e}")
+    assert r < 6e-3 and m < 1e-2, (r, m)
+    assert r2 < 6e-3 and m2 < 1.5e-2, (r2, m2)
+
+
 def make_unet(cfg, max_batch=2):
     m = CuboidTransformerUNet(input_shape=[cfg.t_in, cfg.h, cfg.w, cfg.c], target_shape=[cfg.t_out, cfg.h, cfg.w, cfg.c],
                               base_units=cfg.base_units, depth=list(cfg.depth), num_heads=cfg.num_heads,
@@ -146,8 +179,9 @@ def test_unet_global_vectors_vs_reference_golden(case):
 
 
 @pytest.mark.parametrize("case", [("w_axial", ("axial", "axial"), "zeros", 8, True, False),
+                                  ("w_axial24", ("axial", "axial"), "zeros", 24, False, True),   # > 16: the general kernel
                                   ("w_swin", ("video_swin_2x8", "spatial_lg_4"), "ignore", 8, True, True)],
-                         ids=["axial", "swin2x8_lg"])
+                         ids=["axial", "axial_k24", "swin2x8_lg"])
 def test_unet_shipped_width_global_vectors_vs_oracle(case):
     """Widths 256 / 512 (head dims 64 / 128; the fused projection + FFN kernels keep running beside the global path)."""
     cfg = gv_cfg(case, Wt.UNetConfig(depth=(1, 1)))

@@ -35,12 +35,17 @@ ap.add_argument("--patterns", default="axial,axial",
                 help="block_attn_patterns of the two levels (any registered name, e.g. video_swin_2x8,spatial_lg_4)")
 ap.add_argument("--padding", default="zeros", choices=["zeros", "ignore"])
 ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+ap.add_argument("--global-vectors", type=int, default=0, help="num_global_vectors (with use_global_vector_ffn; 0 = none)")
+ap.add_argument("--global-self-attn", action="store_true")
 args = ap.parse_args()
-cfg = Wt.UNetConfig(patterns=tuple(args.patterns.split(",")), padding_type=args.padding)
+cfg = Wt.UNetConfig(patterns=tuple(args.patterns.split(",")), padding_type=args.padding, num_global_vectors=args.global_vectors,
+                    use_global_self_attn=args.global_self_attn)
 B = args.batch
 unet = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
                              depth=list(cfg.depth), num_heads=cfg.num_heads, block_attn_patterns=list(cfg.patterns),
-                             padding_type=cfg.padding_type, max_batch=B, precision=args.precision)
+                             padding_type=cfg.padding_type, max_batch=B, precision=args.precision,
+                             num_global_vectors=cfg.num_global_vectors, use_global_vector_ffn=cfg.use_global_vector_ffn,
+                             use_global_self_attn=cfg.use_global_self_attn)
 unet.load_state_dict({k: torch.from_numpy(v) for k, v in Wt.seeded_state_dict(Wt.unet_param_spec(cfg), 1001).items()},
                      strict=False)
 rng = np.random.Generator(np.random.PCG64(1))
