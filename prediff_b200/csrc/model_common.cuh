@@ -159,23 +159,65 @@ struct Plan {
         fork_begin = begin; fork_end = end; join_before = join;
         return PD_OK;
     }
+    // Second lane: steps added while `cur_lane` is 1 run on the stream `side` - a chain that only meets the main chain at
+    // explicit points (the global vectors' projections / FFN beside the token grid's, unet.cu). mark() names the step added
+    // last, wait(m) makes the step added next wait for mark m (an event recorded after the marked step on its lane's stream);
+    // the side lane joins the main one at the end of run(). Inside a captured graph these become parallel branches; the
+    // traced / profiled passes run every step on one stream in plan order, which satisfies every dependency.
+    std::vector<uint8_t> lanes;                    // per step
+    std::vector<int> mark_of;                      // per step: mark recorded after it, or -1
+    std::vector<std::vector<int>> waits;           // per step: marks it waits for
+    std::vector<cudaEvent_t> mark_ev;              // per mark
+    std::vector<int> pending_waits;                // for the step added next
+    uint8_t cur_lane = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_side_join = nullptr;
+    void lane(int l) { cur_lane = (uint8_t)l; }
+    int mark() {
+        if (mark_of.back() < 0) {
+            mark_of.back() = (int)mark_ev.size();
+            mark_ev.push_back(nullptr);
+        }
+        return mark_of.back();
+    }
+    void wait(int m) { if (m >= 0) pending_waits.push_back(m); }
+    int enable_lanes() {
+        bool any = false;
+        for (auto l : lanes) any = any || l;
+        if (!any) return PD_OK;
+        PD_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        PD_CUDA(cudaEventCreateWithFlags(&ev_side_join, cudaEventDisableTiming));
+        for (auto& e : mark_ev) PD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return PD_OK;
+    }
     int run(cudaStream_t st) const {
-        if (!aux) {
+        if (!aux && !side) {
             for (const auto& s : steps) PD_TRY(s(st));
             return PD_OK;
         }
+        bool side_used = false;
         for (size_t i = 0; i < steps.size(); ++i) {
-            if (i == fork_begin) {
+            if (aux && i == fork_begin) {
                 PD_CUDA(cudaEventRecord(ev_fork, st));
                 PD_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
             }
-            if (i >= fork_begin && i < fork_end) {
+            if (aux && i >= fork_begin && i < fork_end) {
                 PD_TRY(steps[i](aux));
                 if (i + 1 == fork_end) PD_CUDA(cudaEventRecord(ev_join, aux));
                 continue;
             }
-            if (i == join_before) PD_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-            PD_TRY(steps[i](st));
+            if (aux && i == join_before) PD_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+            cudaStream_t s = (side && lanes[i]) ? side : st;
+            if (side) {
+                for (int m : waits[i]) PD_CUDA(cudaStreamWaitEvent(s, mark_ev[m], 0));
+                side_used = side_used || lanes[i];
+            }
+            PD_TRY(steps[i](s));
+            if (side && mark_of[i] >= 0) PD_CUDA(cudaEventRecord(mark_ev[mark_of[i]], s));
+        }
+        if (side_used) {
+            PD_CUDA(cudaEventRecord(ev_side_join, side));
+            PD_CUDA(cudaStreamWaitEvent(st, ev_side_join, 0));
         }
         return PD_OK;
     }
@@ -184,6 +226,10 @@ struct Plan {
         kinds.push_back(k);
         labels.push_back(scope.empty() ? std::string(label) : scope + "." + label);
         flops.push_back(0.0);
+        lanes.push_back(cur_lane);
+        mark_of.push_back(-1);
+        waits.push_back(std::move(pending_waits));
+        pending_waits.clear();
     }
     void add(Step s, const char* label) { add(std::move(s), STEP_KERNEL, label); }
     // GEMM-family steps in launch order, for the L2 weight prefetch chain (common.cuh): `own` = the step's weight ranges,

@@ -568,10 +568,23 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
         const int Kg = n_global, Mg = B * n_global, gsa = global_self_attn ? 1 : 0;
         float *gv = b.gv[lvl], *g_qkv = b.g_qkv, *g_att = b.g_att, *g_mid = b.g_mid, *g_ws = b.g_ws;
         bf16* g_qkv_bf16 = b.g_qkv_bf16;
-        if (Kg > 0)
+        // The global rows' kernels form a second lane (Plan::lane): beside the token grid's projection + FFN kernel, which
+        // leaves 44 SMs idle, run the global attention, global_proj, the global FFN and the next layer's global_qkv. The two
+        // lanes meet where they exchange data: the cuboid kernel needs the global k | v (m_gqkv), the global attention the
+        // grid's q|k|v (m_qkv); and where a buffer is recycled: `qkv` is rewritten by the next layer's GEMM (after this
+        // layer's global attention, gv_mark_gvattn_), the global k | v by the next gv.qkv (after this layer's cuboid kernel,
+        // gv_mark_attn_). PD_NO_GV_LANES=1 keeps everything on one stream (A/B).
+        static const bool gv_lanes = getenv("PD_NO_GV_LANES") == nullptr;
+        int m_gqkv = -1;
+        if (Kg > 0) {
+            if (gv_lanes) pl.lane(1);
+            pl.wait(gv_mark_attn_);
             pl.add([=](cudaStream_t st) {
                 return gv_linear(gv, aw.g_ln_w, aw.g_ln_b, aw.g_qkv_w, nullptr, nullptr, g_qkv, g_qkv_bf16, Mg, C, 3 * C, 0, st);
             }, "gv.qkv");
+            m_gqkv = pl.mark();
+            pl.lane(0);
+        }
         if (cub_axis[lvl][i] >= 0 && !prec && Kg == 0 && qkv_attn_supported(Tn, H, W, C, heads, cub_axis[lvl][i]) &&
             getenv("PD_NO_QKV_ATTN_FUSION") == nullptr) {
             // axial layer, bf16 operands: QKV projection + attention core in one kernel (qkv_attn.cu); q|k|v never exist
@@ -586,7 +599,33 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             if (prec) e.round_tf32 = 0;   // q|k|v feed the fp32 attention core, not a tensor-core GEMM
             GemmOp op;
             PD_TRY(gemm_make(&op, ln, geom(GemmGeom::linear(P, C)), aw.qkv_w, 3 * C, e));
+            if (Kg > 0) pl.wait(gv_mark_gvattn_);
             pl.add_gemm(op, "qkv");
+        }
+        if (Kg > 0) {   // the global vectors' own update, on the side lane
+            const int m_qkv = pl.mark();
+            const CuboidDev cd = cub_dev[lvl][i]->dev;
+            if (gv_lanes) pl.lane(1);
+            pl.wait(m_qkv);
+            // (:928-945, 951-952, 1137): attention over every slot (+ themselves), then global_vectors += global_proj(.)
+            pl.add([=](cudaStream_t st) {
+                return global_attention(g_qkv, qkv, g_qkv_bf16, g_att, g_ws, B, N_tok, C, heads, Kg, gsa, cd, st);
+            }, "gv.attn");
+            gv_mark_gvattn_ = pl.mark();
+            pl.add([=](cudaStream_t st) {
+                return gv_linear(g_att, nullptr, nullptr, aw.g_proj_w, aw.g_proj_b, gv, gv, nullptr, Mg, C, C, 0, st);
+            }, "gv.proj");
+            if (!s.gf.empty()) {   // global_ffn_l[i] (:1143-1144): pre-norm FFN with GELU on the K rows
+                const GFfnW gw = s.gf[i];
+                pl.add([=](cudaStream_t st) {
+                    return gv_linear(gv, gw.ln_w, gw.ln_b, gw.w1, gw.b1, nullptr, g_mid, nullptr, Mg, C, 4 * C, 1, st);
+                }, "gv.ffn1");
+                pl.add([=](cudaStream_t st) {
+                    return gv_linear(g_mid, nullptr, nullptr, gw.w2, gw.b2, gv, gv, nullptr, Mg, 4 * C, C, 0, st);
+                }, "gv.ffn2");
+            }
+            pl.lane(0);
+            pl.wait(m_gqkv);   // the cuboid kernel below reads the global k | v
         }
         static const bool gv_no_axial = getenv("PD_GV_NO_AXIAL") != nullptr;   // A/B: global keys through the general kernel
         const bool axial_line = cub_axis[lvl][i] >= 0 && (Kg == 0 || (Kg <= 16 && !gv_no_axial));
@@ -606,28 +645,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
                 pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },
                        "attn_cuboid");
         }
-        if (Kg > 0) {
-            {
-                const CuboidDev cd = cub_dev[lvl][i]->dev;
-                // the global vectors' own update (:928-945, 951-952, 1137): attention over every slot (+ themselves), then
-                // global_vectors += global_proj(.)
-                pl.add([=](cudaStream_t st) {
-                    return global_attention(g_qkv, qkv, g_qkv_bf16, g_att, g_ws, B, N_tok, C, heads, Kg, gsa, cd, st);
-                }, "gv.attn");
-                pl.add([=](cudaStream_t st) {
-                    return gv_linear(g_att, nullptr, nullptr, aw.g_proj_w, aw.g_proj_b, gv, gv, nullptr, Mg, C, C, 0, st);
-                }, "gv.proj");
-                if (!s.gf.empty()) {   // global_ffn_l[i] (:1143-1144): pre-norm FFN with GELU on the K rows
-                    const GFfnW gw = s.gf[i];
-                    pl.add([=](cudaStream_t st) {
-                        return gv_linear(gv, gw.ln_w, gw.ln_b, gw.w1, gw.b1, nullptr, g_mid, nullptr, Mg, C, 4 * C, 1, st);
-                    }, "gv.ffn1");
-                    pl.add([=](cudaStream_t st) {
-                        return gv_linear(g_mid, nullptr, nullptr, gw.w2, gw.b2, gv, gv, nullptr, Mg, 4 * C, C, 0, st);
-                    }, "gv.ffn2");
-                }
-            }
-        }
+        if (Kg > 0) gv_mark_attn_ = pl.mark();
         }
         if (C == 256 && !prec && getenv("PD_NO_FFN_FUSION") == nullptr && getenv("PD_NO_PROJ_FUSION") == nullptr) {
             // width 256: projection + residual + pre-norm + FFN (+ the next layer's LayerNorm) in ONE kernel per row
@@ -754,6 +772,9 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         PD_CUDA(cudaMemsetAsync(gn_all, 0, gn_bytes, st));
         return PD_OK;
     }, STEP_NONE, "memset");
+    const int m_start = pl.mark();
+    gv_mark_attn_ = gv_mark_gvattn_ = -1;
+    static const bool gv_lanes = getenv("PD_NO_GV_LANES") == nullptr;
     // ---- time embedding (models/utils.py:68-83, time_embed.py:16-24, :108-114) ----
     {
         const float *w0 = te_w0, *b0 = te_b0, *w2 = te_w2, *b2 = te_b2;
@@ -824,7 +845,10 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             const float* gi = gv_init;
             float* gv0 = b.gv[0];
             const int Kg = n_global;
+            if (gv_lanes) pl.lane(1);   // the side lane starts here (it forks from the head of the plan)
+            pl.wait(m_start);
             pl.add([=](cudaStream_t st) { return gv_broadcast(gi, gv0, B, Kg, c0, st); }, "gv.init");
+            pl.lane(0);
         }
         pl.scope.clear();
     }
@@ -861,8 +885,10 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             const float *w = gv_down_w, *bb = gv_down_b;
             float *g0 = b.gv[0], *g1 = b.gv[1];
             const int Mg = B * n_global, c0 = C0, c1 = C1;
+            if (gv_lanes) pl.lane(1);
             pl.add([=](cudaStream_t st) { return gv_linear(g0, nullptr, nullptr, w, bb, nullptr, g1, nullptr, Mg, c0, c1, 0, st); },
                    "down.gv_proj");
+            pl.lane(0);
         }
     }
     for (int d = 0; d < cfg.depth[1]; ++d) {
@@ -897,8 +923,10 @@ int UNet::build_plan(int B, BatchPlan* bp) {
             const float *w = gv_up_w, *bb = gv_up_b;
             float *g0 = b.gv[0], *g1 = b.gv[1];
             const int Mg = B * n_global, c0 = C0, c1 = C1;
+            if (gv_lanes) pl.lane(1);
             pl.add([=](cudaStream_t st) { return gv_linear(g1, nullptr, nullptr, w, bb, nullptr, g0, nullptr, Mg, c1, c0, 0, st); },
                    "up.gv_proj");
+            pl.lane(0);
         }
     }
     for (int d = 0; d < cfg.depth[0]; ++d) {
@@ -925,6 +953,7 @@ int UNet::build_plan(int B, BatchPlan* bp) {
         pl.add([](cudaStream_t) { return PD_OK; }, STEP_GEMM, "final.proj");  // placeholder: final GEMM, bound per call
         pl.flops.back() = bp->final_op.flops;
     }
+    PD_TRY(pl.enable_lanes());
     if (getenv("PD_NO_L2_PREFETCH") == nullptr) pl.link_prefetch();
     if (getenv("PD_NO_TEMB_FORK") == nullptr) {   // time-embedding MLP beside first_proj; joined at the first conv that adds it
         size_t join = 0;

@@ -110,6 +110,9 @@ private:
     void carve(A& ar, int B, Bufs* b) const;
 
     BatchPlan* building_ = nullptr;   // plan under construction (make_conv attaches stream-K workspaces to it)
+    // plan under construction, global vectors: marks (Plan::mark) of the last cuboid-attention kernel (reader of the global
+    // k | v buffer) and of the last global attention (reader of the grid's q|k|v buffer)
+    int gv_mark_attn_ = -1, gv_mark_gvattn_ = -1;
     std::vector<std::unique_ptr<DevMem>> packed;
     std::vector<std::unique_ptr<CuboidTablesDev>> cub_dev[2];   // per level, per layer (null for axial fast-path layers)
     std::vector<int> cub_axis[2];                               // axial fast-path axis or -1

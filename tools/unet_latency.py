@@ -19,10 +19,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--out", default=None)
+ap.add_argument("--global-vectors", type=int, default=0, help="num_global_vectors (with the global FFN; 0 = the shipped config)")
 args = ap.parse_args()
-cfg, B = Wt.UNetConfig(), args.batch
+cfg, B = Wt.UNetConfig(num_global_vectors=args.global_vectors), args.batch
 unet = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
-                             depth=list(cfg.depth), num_heads=cfg.num_heads, max_batch=B)
+                             depth=list(cfg.depth), num_heads=cfg.num_heads, max_batch=B,
+                             num_global_vectors=cfg.num_global_vectors)
 unet.load_state_dict({k: torch.from_numpy(v) for k, v in Wt.seeded_state_dict(Wt.unet_param_spec(cfg), 1001).items()},
                      strict=False)
 rng = np.random.Generator(np.random.PCG64(1234))
