@@ -12,7 +12,7 @@ timeout 400 ncu --profile-from-start off --metrics $M --clock-control none --csv
     --log-file $OUT/ncu_${TAG}_unet_fwd_b4.csv python tools/profile_unet.py --batch 4 > /dev/null 2>&1
 timeout 100 python tools/trace_unet.py --batch 4 --graph --out $OUT/trace_${TAG}_unet_fwd_b4_graph.txt > /dev/null 2>&1
 head -14 $OUT/trace_${TAG}_unet_fwd_b4_graph.txt
-timeout 400 python -m pytest tests/test_tf32_gpu.py tests/test_sampler_round2_gpu.py tests/test_unet_gpu.py tests/test_sampler_gpu.py -m gpu -q -s 2>&1 | grep -E "rel_rms|passed|failed|ssim" > $OUT/parity_${TAG}.txt; tail -3 $OUT/parity_${TAG}.txt
+timeout 400 python -m pytest tests/test_tf32_gpu.py tests/test_sampler_round2_gpu.py tests/test_unet_gpu.py tests/test_sampler_gpu.py tests/test_global_vectors_gpu.py -m gpu -q -s 2>&1 | grep -E "rel_rms|passed|failed|ssim" > $OUT/parity_${TAG}.txt; tail -3 $OUT/parity_${TAG}.txt
 timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench_${TAG}_b200x1.json 2> $OUT/bench_${TAG}_b200x1.err; tail -2 $OUT/bench_${TAG}_b200x1.err
 python -c "
 import json; d=json.loads(open('$OUT/bench_${TAG}_b200x1.json').read().strip().splitlines()[-1])
