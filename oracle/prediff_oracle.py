@@ -146,7 +146,7 @@ def _from_cuboids(y, size, strategy, padded):
 
 
 def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_type="zeros", gqkv=None,
-                          global_self_attn=False):
+                          global_self_attn=False, sep=None):
     """The attention core of CuboidSelfAttentionLayer.forward (cuboid_transformer.py:812-966; global vectors: below)
     from the per-token q|k|v rows: qkv (B, T, H, W, 3C), taken BEFORE padding (qkv has no bias, so the zero rows the
     reference pads after its LayerNorm map to zero q, k, v) -> (B, T, H, W, C) before the final projection.
@@ -157,7 +157,11 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
     returns (o, new_global (B, K, C) before global_proj). Local queries see the K global keys as extra, never-masked
     columns (:902-913); the global queries attend over ALL num_cuboids * volume slots in cuboid order (+ the global keys
     with global_self_attn), and under 'ignore' padding the slot mask is the padded, rolled validity grid flattened in
-    RASTER order - the reference applies it to the cuboid-ordered keys as it is (:915-945), so does this."""
+    RASTER order - the reference applies it to the cuboid-ordered keys as it is (:915-945), so does this.
+    sep (separate_global_qkv=True, :866-891): (tok (B, T, H, W, 3C) = l2g_q | g2l_k | g2l_v rows of the tokens,
+    grow (B, K, 3C or 6C) = l2g_k | l2g_v | g2l_q [| g2g_q | g2g_k | g2g_v] rows of the global vectors) instead of gqkv: the
+    tokens meet the global keys with their own query net, the global queries meet the tokens' own key / value nets, and the
+    global self-attention has a third q|k|v set."""
     B, T, H, W, C3 = qkv.shape
     C, hd = C3 // 3, C3 // 3 // heads
     dims = (T, H, W)
@@ -182,6 +186,8 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
         view = [1, 1, 1, 1, 1]
         view[1 + a] = padded[a]
         region = region * 3 + lab.view(view)
+    if sep is not None:   # the tokens' extra rows travel through the same padding / roll / reorder
+        qkv = torch.cat([qkv, sep[0]], dim=-1)
     if padding_type == "nearest" and any(pad):   # _generalize_padding (models/utils.py:228-258): resample to the padded size
         y = F.interpolate(qkv.permute(0, 4, 1, 2, 3), size=tuple(padded)).permute(0, 2, 3, 4, 1)
     else:
@@ -197,7 +203,11 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
     if padding_type == "ignore":
         ok = _to_cuboids(real, size, strategy)[0, :, :, 0] > 0
         mask = mask & ok[:, :, None] & ok[:, None, :]
-    q, k, v = y.reshape(B, nc, vol, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)
+    if sep is not None:
+        q, k, v, q_lg, k_gl, v_gl = y.reshape(B, nc, vol, 6, heads, hd).permute(3, 0, 4, 1, 2, 5)
+    else:
+        q, k, v = y.reshape(B, nc, vol, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)
+        q_lg, k_gl, v_gl = q, k, v
     s = (q * hd ** -0.5) @ k.transpose(-1, -2)                # (B, heads, nc, vol, vol)
     bt, bh, bw = size0
     i = torch.arange(vol)
@@ -206,20 +216,28 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
         + (cw[:, None] - cw[None] + bw - 1)
     s = s + table[rel].permute(2, 0, 1)[:, None]
     new_g = None
-    if gqkv is not None:
-        K = gqkv.shape[1]
-        gq, gk, gv = gqkv.reshape(B, 1, K, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)   # (B, heads, 1, K, hd)
-        s = torch.cat([s, (q * hd ** -0.5) @ gk.transpose(-1, -2)], dim=-1)          # (B, heads, nc, vol, vol + K)
+    if gqkv is not None or sep is not None:
+        if sep is not None:
+            grow = sep[1]
+            K = grow.shape[1]
+            parts = grow.reshape(B, 1, K, grow.shape[-1] // C, heads, hd).permute(3, 0, 4, 1, 2, 5)   # (n, B, heads, 1, K, hd)
+            gk, gv, gq = parts[0], parts[1], parts[2]
+            gq_g, gk_g, gv_g = (parts[3], parts[4], parts[5]) if global_self_attn else (None, None, None)
+        else:
+            K = gqkv.shape[1]
+            gq, gk, gv = gqkv.reshape(B, 1, K, 3, heads, hd).permute(3, 0, 4, 1, 2, 5)   # (B, heads, 1, K, hd)
+            gq_g, gk_g, gv_g = gq, gk, gv
+        s = torch.cat([s, (q_lg * hd ** -0.5) @ gk.transpose(-1, -2)], dim=-1)       # (B, heads, nc, vol, vol + K)
         mask = F.pad(mask, (0, K), value=True)
         v_lg = torch.cat([v, gv.expand(B, heads, nc, K, hd)], dim=3)
         # global queries over every slot (:928-945)
-        s2 = (gq.squeeze(2) * hd ** -0.5) @ k.reshape(B, heads, nc * vol, hd).transpose(-1, -2)   # (B, heads, K, nc * vol)
+        s2 = (gq.squeeze(2) * hd ** -0.5) @ k_gl.reshape(B, heads, nc * vol, hd).transpose(-1, -2)   # (B, heads, K, nc * vol)
         m2 = real.reshape(-1) > 0 if padding_type == "ignore" else None            # raster order (see the docstring)
-        v2 = v.reshape(B, heads, nc * vol, hd)
+        v2 = v_gl.reshape(B, heads, nc * vol, hd)
         if global_self_attn:
-            s2 = torch.cat([s2, (gq.squeeze(2) * hd ** -0.5) @ gk.squeeze(2).transpose(-1, -2)], dim=-1)
+            s2 = torch.cat([s2, (gq_g.squeeze(2) * hd ** -0.5) @ gk_g.squeeze(2).transpose(-1, -2)], dim=-1)
             m2 = F.pad(m2, (0, K), value=True) if m2 is not None else None
-            v2 = torch.cat([v2, gv.squeeze(2)], dim=2)
+            v2 = torch.cat([v2, gv_g.squeeze(2)], dim=2)
         if m2 is not None:
             p2 = torch.softmax(s2.masked_fill(~m2, -1e18), dim=-1) * m2
         else:
@@ -237,18 +255,28 @@ def cuboid_attention_core(qkv, table, heads, size0, strategy, shift0, padding_ty
         o = F.interpolate(o.permute(0, 4, 1, 2, 3), size=(T, H, W)).permute(0, 2, 3, 4, 1).contiguous()
     else:
         o = o[:, :T, :H, :W].contiguous()
-    return o if gqkv is None else (o, new_g)
+    return o if new_g is None else (o, new_g)
 
 
-def cuboid_attention_gv(sd, p, x, g, heads, size0, strategy, shift0, padding_type="zeros", global_self_attn=False):
-    """CuboidSelfAttentionLayer.forward with use_global_vector, separate_global_qkv=False (cuboid_transformer.py:812-966):
-    x (B, T, H, W, C), g (B, K, C) -> (x_out, g_out), both BEFORE the residual adds of the stack block."""
+def cuboid_attention_gv(sd, p, x, g, heads, size0, strategy, shift0, padding_type="zeros", global_self_attn=False,
+                        separate=False):
+    """CuboidSelfAttentionLayer.forward with use_global_vector (cuboid_transformer.py:812-966), global_dim_ratio = 1:
+    x (B, T, H, W, C), g (B, K, C) -> (x_out, g_out), both BEFORE the residual adds of the stack block.
+    separate: separate_global_qkv=True - the six extra Linear nets of :770-795 (no bias, like qkv)."""
     C = x.shape[-1]
     y = F.layer_norm(x, (C,), sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5)
     gn = F.layer_norm(g, (C,), sd[f"{p}.global_vec_norm.weight"], sd[f"{p}.global_vec_norm.bias"], 1e-5)
+    if separate:
+        tok = torch.cat([F.linear(y, sd[f"{p}.l2g_q_net.weight"]), F.linear(y, sd[f"{p}.g2l_k_net.weight"]),
+                         F.linear(y, sd[f"{p}.g2l_v_net.weight"])], dim=-1)
+        grow = [F.linear(gn, sd[f"{p}.l2g_global_kv_net.weight"]), F.linear(gn, sd[f"{p}.g2l_global_q_net.weight"])]
+        if global_self_attn:
+            grow.append(F.linear(gn, sd[f"{p}.g2g_global_qkv_net.weight"]))
+        kw = dict(sep=(tok, torch.cat(grow, dim=-1)))
+    else:
+        kw = dict(gqkv=F.linear(gn, sd[f"{p}.global_qkv.weight"]))
     o, ng = cuboid_attention_core(F.linear(y, sd[f"{p}.qkv.weight"]), sd[f"{p}.relative_position_bias_table"], heads,
-                                  size0, strategy, shift0, padding_type, gqkv=F.linear(gn, sd[f"{p}.global_qkv.weight"]),
-                                  global_self_attn=global_self_attn)
+                                  size0, strategy, shift0, padding_type, global_self_attn=global_self_attn, **kw)
     return (F.linear(o, sd[f"{p}.proj.weight"], sd[f"{p}.proj.bias"]),
             F.linear(ng, sd[f"{p}.global_proj.weight"], sd[f"{p}.global_proj.bias"]))
 
@@ -264,14 +292,15 @@ def cuboid_attention(sd, p, x, heads, size0, strategy, shift0, padding_type="zer
     return F.linear(o, sd[f"{p}.proj.weight"], sd[f"{p}.proj.bias"])
 
 
-def stack_block(sd, p, x, heads, layers=None, padding_type="zeros", g=None, global_ffn=True, global_self_attn=False):
+def stack_block(sd, p, x, heads, layers=None, padding_type="zeros", g=None, global_ffn=True, global_self_attn=False,
+                separate=False):
     """StackCuboidSelfAttentionBlock.forward with use_inter_ffn (cuboid_transformer.py:1147-1156). `layers`: list of
     (cuboid_size, strategy, shift_size) (None = the axial pattern of the shipped config). g (B, K, C): global vectors
     (:1130-1145) -> returns (x, g)."""
     if g is not None:
         for i, (size, strategy, shift) in enumerate(layers):
             xo, go = cuboid_attention_gv(sd, f"{p}.attn_l.{i}", x, g, heads, size, strategy, shift, padding_type,
-                                         global_self_attn)
+                                         global_self_attn, separate)
             x, g = x + xo, g + go
             x = ffn(sd, f"{p}.ffn_l.{i}", x)
             if global_ffn:
@@ -336,7 +365,8 @@ def unet_forward(sd, cfg, x, t, cond):
         for d in range(cfg.depth[lvl]):
             x = _res_block3d(sd, f"{name_t}.{lvl}", x.permute(0, 4, 1, 2, 3), t_emb, g, g).permute(0, 2, 3, 4, 1)
             r = stack_block(sd, f"{name_s}.{lvl}.{d}", x, heads, layers[lvl], getattr(cfg, "padding_type", "zeros"),
-                            gvec[0], getattr(cfg, "use_global_vector_ffn", True), getattr(cfg, "use_global_self_attn", False))
+                            gvec[0], getattr(cfg, "use_global_vector_ffn", True), getattr(cfg, "use_global_self_attn", False),
+                            getattr(cfg, "separate_global_qkv", False))
             x, gvec[0] = r if K else (r, None)
         return x
 

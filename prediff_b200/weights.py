@@ -33,6 +33,7 @@ class UNetConfig:
     num_global_vectors: int = 0
     use_global_vector_ffn: bool = True
     use_global_self_attn: bool = False
+    separate_global_qkv: bool = False   # True: the six extra Linear nets of cuboid_transformer.py:770-795 instead of global_qkv
 
     @property
     def T(self):
@@ -115,7 +116,7 @@ def _resblock3d(prefix, cin, cout, temb) -> Spec:
     return s
 
 
-def _stack_block(prefix, dim, heads, cuboids, gv=False, gv_ffn=False) -> Spec:
+def _stack_block(prefix, dim, heads, cuboids, gv=False, gv_ffn=False, gv_sep=False, gv_sa=False) -> Spec:
     """gv: the block carries global vectors (global_qkv / global_proj / global_vec_norm per attention layer,
     cuboid_transformer.py:777-810); gv_ffn: and a PositionwiseFFN for them per layer (global_ffn_l, :1054-1068)."""
     s: Spec = []
@@ -129,7 +130,13 @@ def _stack_block(prefix, dim, heads, cuboids, gv=False, gv_ffn=False) -> Spec:
         p = f"{prefix}.attn_l.{i}"
         s += [(f"{p}.relative_position_bias_table", ((2 * bt - 1) * (2 * bh - 1) * (2 * bw - 1), heads)),
               (f"{p}.qkv.weight", (3 * dim, dim))]
-        if gv:
+        if gv and gv_sep:   # separate_global_qkv (registration order of :770-795)
+            s += [(f"{p}.l2g_q_net.weight", (dim, dim)), (f"{p}.l2g_global_kv_net.weight", (2 * dim, dim)),
+                  (f"{p}.g2l_global_q_net.weight", (dim, dim)), (f"{p}.g2l_k_net.weight", (dim, dim)),
+                  (f"{p}.g2l_v_net.weight", (dim, dim))]
+            if gv_sa:
+                s += [(f"{p}.g2g_global_qkv_net.weight", (3 * dim, dim))]
+        elif gv:
             s += [(f"{p}.global_qkv.weight", (3 * dim, dim))]
         s += [(f"{p}.proj.weight", (dim, dim)), (f"{p}.proj.bias", (dim,))]
         if gv:
@@ -164,7 +171,8 @@ def unet_param_spec(cfg: UNetConfig) -> Spec:
     for name in ("down_self_blocks", "up_self_blocks"):
         for lvl, dim in enumerate((u0, u1)):
             for d in range(cfg.depth[lvl]):
-                s += _stack_block(f"{name}.{lvl}.{d}", dim, cfg.num_heads, cfg.cuboids(lvl), gv, cfg.use_global_vector_ffn)
+                s += _stack_block(f"{name}.{lvl}.{d}", dim, cfg.num_heads, cfg.cuboids(lvl), gv, cfg.use_global_vector_ffn,
+                                  cfg.separate_global_qkv, cfg.use_global_self_attn)
     for name in ("down_time_embed_blocks", "up_time_embed_blocks"):
         for lvl, dim in enumerate((u0, u1)):
             s += _resblock3d(f"{name}.{lvl}", dim, dim, te)

@@ -77,7 +77,8 @@ def ref_unet(cfg):
         depth=list(cfg.depth), block_attn_patterns=pats, num_global_vectors=getattr(cfg, "num_global_vectors", 0),
         use_global_vector_ffn=getattr(cfg, "use_global_vector_ffn", True) if getattr(cfg, "num_global_vectors", 0) else False,
         use_global_self_attn=getattr(cfg, "use_global_self_attn", False) if getattr(cfg, "num_global_vectors", 0) else True,
-        separate_global_qkv=not getattr(cfg, "num_global_vectors", 0), global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
+        separate_global_qkv=getattr(cfg, "separate_global_qkv", False) if getattr(cfg, "num_global_vectors", 0) else True,
+        global_dim_ratio=1, ffn_activation="gelu", gated_ffn=False,
         norm_layer="layer_norm", padding_type=getattr(cfg, "padding_type", "zeros"), checkpoint_level=0,
         pos_embed_type="t+h+w", use_relative_pos=True, self_attn_use_final_proj=True, time_embed_channels_mult=4,
         time_embed_use_scale_shift_norm=False, time_embed_dropout=0.0, unet_res_connect=True, **explicit)
@@ -555,6 +556,43 @@ def gen_global_vectors():
 
 
 @torch.no_grad()
+def gen_global_vectors_sep():
+    """separate_global_qkv=True (cuboid_transformer.py:770-795, 866-891): the unmodified layer and UNet, as gen_global_vectors."""
+    import contextlib
+    import dataclasses
+    import io
+    from prediff.models.cuboid_transformer.cuboid_transformer import CuboidSelfAttentionLayer
+    import pattern_cases as PC
+    out = {}
+    for tag, dims, C, heads, size, strat, shift, pad, K, gsa in PC.GV_SEP_LAYER_CASES:
+        m = CuboidSelfAttentionLayer(dim=C, num_heads=heads, cuboid_size=size, shift_size=shift, strategy=tuple(strat),
+                                     padding_type=pad, qkv_bias=False, attn_drop=0.0, proj_drop=0.0,
+                                     use_final_proj=True, norm_layer="layer_norm", use_global_vector=True,
+                                     use_global_self_attn=gsa, separate_global_qkv=True, global_dim_ratio=1,
+                                     checkpoint_level=0, use_relative_pos=True).eval()
+        spec = PC.gv_sep_layer_spec(C, heads, size, gsa)
+        assert [k for k, _ in spec] == ["a." + k for k in m.state_dict() if k != "relative_position_index"], "registration order"
+        sd = Wt.seeded_state_dict(spec, PC.LAYER_SEED)
+        res = m.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        assert not res.unexpected_keys and res.missing_keys == ["relative_position_index"], res
+        x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+        g = inp(PC.LAYER_SEED + 2, 2, K, C)
+        xo, go = m(x, g)
+        out[f"layer_{tag}_x"], out[f"layer_{tag}_g"] = xo, go
+        print(f"global_vectors_sep layer_{tag}: x std {xo.std():.3f}, g std {go.std():.3f}")
+    for tag, pats, pad, K, gffn, gsa in PC.GV_SEP_UNET_CASES:
+        cfg = dataclasses.replace(Wt.TINY_UNET, patterns=tuple(pats), padding_type=pad, num_global_vectors=K,
+                                  use_global_vector_ffn=gffn, use_global_self_attn=gsa, separate_global_qkv=True)
+        m = ref_unet(cfg)
+        x = inp(1234, 2, cfg.t_out, cfg.h, cfg.w, cfg.c)
+        cond = inp(1235, 2, cfg.t_in, cfg.h, cfg.w, cfg.c)
+        with contextlib.redirect_stdout(io.StringIO()):
+            out[f"unet_{tag}"] = m(x, torch.tensor([500, 37], dtype=torch.long), cond)
+        print(f"global_vectors_sep unet_{tag}: out std {out[f'unet_{tag}'].std():.3f}")
+    save("global_vectors_sep", **out)
+
+
+@torch.no_grad()
 def gen_vae(tag, cfg, N):
     m = ref_vae(cfg)
     x = inp(4321, N, 1, cfg.h, cfg.w, uniform=True)
@@ -776,6 +814,8 @@ if __name__ == "__main__":
         gen_patterns_nearest()
     if "global_vectors" in todo:
         gen_global_vectors()
+    if "global_vectors_sep" in todo:
+        gen_global_vectors_sep()
     if "losses" in todo:
         gen_losses()
     if "ema" in todo:

@@ -61,6 +61,31 @@ GV_UNET_CASES = [
 ]
 
 
+# separate_global_qkv=True (the shipped cfg.yaml's value for the UNet): same tuple layouts, goldens in global_vectors_sep.npz
+GV_SEP_LAYER_CASES = [
+    ("gvs_axial_t", (13, 8, 8), 32, 2, (13, 1, 1), "lll", (0, 0, 0), "zeros", 4, True),
+    ("gvs_swin_i", (13, 8, 8), 32, 2, (4, 4, 4), "lll", (2, 2, 2), "ignore", 4, True),
+    ("gvs_dilated_z", (13, 8, 8), 32, 2, (2, 4, 4), "ddd", (0, 0, 0), "zeros", 8, False),
+    ("gvs_ragged_n", (6, 7, 9), 32, 2, (4, 3, 4), "ldl", (2, 1, 2), "nearest", 3, True),
+    ("gvs_full_hd64", (5, 8, 8), 128, 2, (5, 8, 8), "lll", (0, 0, 0), "ignore", 16, True),
+]
+GV_SEP_UNET_CASES = [
+    ("gvs_axial", ("axial", "axial"), "zeros", 4, False, True),          # the shipped flags: no global FFN, global self-attention
+    ("gvs_swin", ("video_swin_2x8", "spatial_lg_4"), "ignore", 8, True, False),
+]
+
+
+def gv_sep_layer_spec(C, heads, size, self_attn):
+    n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
+    s = [("a.relative_position_bias_table", (n_rel, heads)), ("a.qkv.weight", (3 * C, C)),
+         ("a.l2g_q_net.weight", (C, C)), ("a.l2g_global_kv_net.weight", (2 * C, C)), ("a.g2l_global_q_net.weight", (C, C)),
+         ("a.g2l_k_net.weight", (C, C)), ("a.g2l_v_net.weight", (C, C))]
+    if self_attn:
+        s += [("a.g2g_global_qkv_net.weight", (3 * C, C))]
+    return s + [("a.proj.weight", (C, C)), ("a.proj.bias", (C,)), ("a.global_proj.weight", (C, C)), ("a.global_proj.bias", (C,)),
+                ("a.norm.weight", (C,)), ("a.norm.bias", (C,)), ("a.global_vec_norm.weight", (C,)), ("a.global_vec_norm.bias", (C,))]
+
+
 def gv_layer_spec(C, heads, size):
     n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
     return [("a.relative_position_bias_table", (n_rel, heads)), ("a.qkv.weight", (3 * C, C)),

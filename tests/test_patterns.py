@@ -110,6 +110,30 @@ def test_oracle_unet_global_vectors_vs_reference(case):
     assert maxrel(out, GV[f"unet_{case[0]}"]) < 1e-4
 
 
+GVS = np.load(os.path.join(os.path.dirname(__file__), "golden", "global_vectors_sep.npz"))   # separate_global_qkv=True
+
+
+@pytest.mark.parametrize("case", PC.GV_SEP_LAYER_CASES, ids=[c[0] for c in PC.GV_SEP_LAYER_CASES])
+def test_oracle_layer_separate_global_qkv_vs_reference(case):
+    tag, dims, C, heads, size, strat, shift, pad, K, gsa = case
+    sd = O.to_torch_sd(Wt.seeded_state_dict(PC.gv_sep_layer_spec(C, heads, size, gsa), PC.LAYER_SEED))
+    x = inp(PC.LAYER_SEED + 1, 2, *dims, C)
+    g = inp(PC.LAYER_SEED + 2, 2, K, C)
+    xo, go = O.cuboid_attention_gv(sd, "a", x, g, heads, size, tuple(strat), shift, pad, gsa, separate=True)
+    assert maxrel(xo, GVS[f"layer_{tag}_x"]) < 2e-5
+    assert maxrel(go, GVS[f"layer_{tag}_g"]) < 2e-5
+
+
+@pytest.mark.parametrize("case", PC.GV_SEP_UNET_CASES, ids=[c[0] for c in PC.GV_SEP_UNET_CASES])
+def test_oracle_unet_separate_global_qkv_vs_reference(case):
+    cfg = dataclasses.replace(gv_unet_cfg(case), separate_global_qkv=True)
+    sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED))
+    x = inp(1234, 2, cfg.t_out, cfg.h, cfg.w, cfg.c)
+    cond = inp(1235, 2, cfg.t_in, cfg.h, cfg.w, cfg.c)
+    out = O.unet_forward(sd, cfg, x, torch.tensor([500, 37]), cond)
+    assert maxrel(out, GVS[f"unet_{case[0]}"]) < 1e-4
+
+
 def attention_from_tables(qkv, table, heads, geo):
     """What the CUDA kernel computes, in numpy: gather rows by `tok`, mask by `lab`, bias by `rel`."""
     B, T, H, W, C3 = qkv.shape
