@@ -66,9 +66,14 @@ int pd_unet_create_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern,
  * global_dim_ratio=1): num_global_vectors in 1..32; use_global_vector_ffn / use_global_self_attn as the reference's
  * constructor arguments. pattern may be NULL (axial, 'zeros'). Adds the state_dict keys init_global_vectors,
  * {down,up}_layer_global_proj.0.*, <block>.attn_l.i.{global_qkv,global_proj,global_vec_norm}.* and <block>.global_ffn_l.i.*.
- * bf16 operand precision only. */
+ * bf16 operand precision only. pd_unet_create_gv == pd_unet_create_gv_ex with separate_global_qkv = 0. */
 int pd_unet_create_gv(const pd_unet_config* cfg, const pd_unet_pattern* pattern, int num_global_vectors,
                       int use_global_vector_ffn, int use_global_self_attn, pd_unet** out);
+/* ... with separate_global_qkv (cuboid_transformer.py:770-795, the shipped cfg.yaml's value for the UNet): the keys
+ * <block>.attn_l.i.{l2g_q_net, l2g_global_kv_net, g2l_global_q_net, g2l_k_net, g2l_v_net[, g2g_global_qkv_net]}.weight replace
+ * global_qkv.weight. global_dim_ratio is 1. */
+int pd_unet_create_gv_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern, int num_global_vectors,
+                         int use_global_vector_ffn, int use_global_self_attn, int separate_global_qkv, pd_unet** out);
 void pd_unet_destroy(pd_unet* m);
 /* Number of state_dict entries the model expects; name/shape of entry i (reference key names, e.g.
  * "down_self_blocks.0.1.attn_l.2.qkv.weight"). shape has up to 5 dims; returns ndim. */
@@ -336,6 +341,15 @@ int pd_op_cuboid_attention_impl(const void* qkv_bf16, const float* bias_table, v
  * pd_op_cuboid_attention_gv: qkv bf16 [B][T][H][W][3C] and the global rows' q|k|v (gqkv_f32 [B][K][3C] and its bf16 copy)
  *   -> out bf16 [B][T][H][W][C] (local + local-to-global attention, :902-913) and gout fp32 [B][K][C] (global-to-local
  *   (+ global-to-global) attention, :928-945), both before their output projections. */
+/* pd_op_cuboid_attention_gv2: the same pair of kernels with the operand layouts of both global-vector variants.
+ *   tok2_bf16 == NULL: the shared global_qkv net - grow_* = the global rows' [q | k | v], grow_ld = 3C.
+ *   tok2_bf16 [B][T][H][W][3C] = the tokens' [l2g_q | g2l_k | g2l_v] rows: separate_global_qkv=True (cuboid_transformer.py:
+ *   866-891) - grow_* = [l2g_k | l2g_v | g2l_q] (grow_ld = 3C) or, with self_attn, [... | g2g_q | g2g_k | g2g_v] (6C).
+ *   line_kernel = 1: the token grid's part through the axial line kernel (axial layers, n_global <= 16), as the UNet does. */
+int pd_op_cuboid_attention_gv2(const void* qkv_bf16, const float* bias_table, const void* tok2_bf16, const float* grow_f32,
+                               const void* grow_bf16, int grow_ld, void* out_bf16, float* gout, int B, int T, int H, int W, int C,
+                               int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
+                               int padding_type, int n_global, int self_attn, int line_kernel, void* stream);
 /* pd_op_axial_attention_gv: pd_op_axial_attention with the sample's <= 16 global vectors as extra keys of every line (k | v
  *   rows of gqkv_bf16 [B][K][3C]; unmasked, no position bias) - what the UNet runs for axial layers when K <= 16. */
 int pd_op_axial_attention_gv(const void* qkv_bf16, const float* bias_table, const void* gqkv_bf16, void* out_bf16, int B, int T,

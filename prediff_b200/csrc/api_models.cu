@@ -7,8 +7,8 @@ using namespace pd;
 
 struct pd_unet {
     UNet impl;
-    pd_unet(const pd_unet_config& c, const pd_unet_pattern* p, int n_global = 0, int gffn = 1, int gsa = 0)
-        : impl(c, p, n_global, gffn, gsa) {}
+    pd_unet(const pd_unet_config& c, const pd_unet_pattern* p, int n_global = 0, int gffn = 1, int gsa = 0, int gsep = 0)
+        : impl(c, p, n_global, gffn, gsa, gsep) {}
 };
 struct pd_sampler {
     Sampler impl;
@@ -27,6 +27,10 @@ int pd_unet_create_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern,
 }
 int pd_unet_create_gv(const pd_unet_config* cfg, const pd_unet_pattern* pattern, int num_global_vectors,
                       int use_global_vector_ffn, int use_global_self_attn, pd_unet** out) {
+    return pd_unet_create_gv_ex(cfg, pattern, num_global_vectors, use_global_vector_ffn, use_global_self_attn, 0, out);
+}
+int pd_unet_create_gv_ex(const pd_unet_config* cfg, const pd_unet_pattern* pattern, int num_global_vectors,
+                         int use_global_vector_ffn, int use_global_self_attn, int separate_global_qkv, pd_unet** out) {
     PD_CHECK(cfg && out, PD_ERR_ARG, "pd_unet_create: null argument");
     PD_CHECK(num_global_vectors >= 0 && num_global_vectors <= 32, PD_ERR_ARG,
              "pd_unet_create_gv: num_global_vectors %d (0..32 are built)", num_global_vectors);
@@ -34,7 +38,8 @@ int pd_unet_create_gv(const pd_unet_config* cfg, const pd_unet_pattern* pattern,
         for (int l = 0; l < 2; ++l)
             PD_CHECK(pattern->n_layers[l] >= 1 && pattern->n_layers[l] <= PD_MAX_ATTN_LAYERS, PD_ERR_ARG,
                      "pd_unet_create_ex: level %d has %d attention layers (1..%d)", l, pattern->n_layers[l], PD_MAX_ATTN_LAYERS);
-    pd_unet* m = new (std::nothrow) pd_unet(*cfg, pattern, num_global_vectors, use_global_vector_ffn, use_global_self_attn);
+    pd_unet* m = new (std::nothrow) pd_unet(*cfg, pattern, num_global_vectors, use_global_vector_ffn, use_global_self_attn,
+                                            separate_global_qkv);
     PD_CHECK(m, PD_ERR_CUDA, "pd_unet_create: out of host memory");
     const int rc = m->impl.validate();
     if (rc != PD_OK) {

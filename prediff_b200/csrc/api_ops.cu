@@ -194,8 +194,9 @@ int pd_op_axial_attention_gv(const void* qkv, const float* bias_table, const voi
                              int W, int C, int heads, int axis, int n_global, void* stream) {
     PD_TRY(gemm_init());
     PD_CHECK(n_global >= 1 && gqkv_bf16, PD_ERR_ARG, "pd_op_axial_attention_gv: needs 1..16 global vectors");
+    const GvKeys gk = gv_keys(static_cast<const bf16*>(gqkv_bf16), C, n_global, false, 3 * C, nullptr);
     return axial_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T, H, W, C, heads, axis,
-                           S(stream), 0, static_cast<const bf16*>(gqkv_bf16), n_global);
+                           S(stream), 0, &gk);
 }
 
 int pd_cuboid_tables(int T, int H, int W, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3],
@@ -267,9 +268,20 @@ int pd_op_cuboid_attention_gv(const void* qkv, const float* bias_table, const fl
                               float* gout, int B, int T, int H, int W, int C, int heads, const int32_t size[3],
                               const int32_t strategy[3], const int32_t shift[3], int padding_type, int n_global, int self_attn,
                               void* stream) {
+    return pd_op_cuboid_attention_gv2(qkv, bias_table, nullptr, gqkv_f32, gqkv_bf16, 3 * C, out, gout, B, T, H, W, C, heads, size,
+                                      strategy, shift, padding_type, n_global, self_attn, 0, stream);
+}
+
+int pd_op_cuboid_attention_gv2(const void* qkv, const float* bias_table, const void* tok2_bf16, const float* grow_f32,
+                               const void* grow_bf16, int grow_ld, void* out, float* gout, int B, int T, int H, int W, int C,
+                               int heads, const int32_t size[3], const int32_t strategy[3], const int32_t shift[3], int padding_type,
+                               int n_global, int self_attn, int line_kernel, void* stream) {
     PD_TRY(gemm_init());
-    PD_CHECK(qkv && bias_table && gqkv_f32 && gqkv_bf16 && out && gout, PD_ERR_ARG, "pd_op_cuboid_attention_gv: null pointer");
+    PD_CHECK(qkv && bias_table && grow_f32 && grow_bf16 && out && gout, PD_ERR_ARG, "pd_op_cuboid_attention_gv: null pointer");
     PD_CHECK(C % heads == 0 && heads >= 1, PD_ERR_SHAPE, "pd_op_cuboid_attention_gv: C=%d heads=%d", C, heads);
+    const bool separate = tok2_bf16 != nullptr;
+    PD_CHECK(grow_ld == (separate && self_attn ? 6 * C : 3 * C), PD_ERR_ARG,
+             "pd_op_cuboid_attention_gv2: grow_ld %d (3C for the shared net or separate nets without self-attention, else 6C)", grow_ld);
     CuboidLayerSpec sp;
     for (int a = 0; a < 3; ++a) {
         sp.size[a] = size[a];
@@ -278,6 +290,8 @@ int pd_op_cuboid_attention_gv(const void* qkv, const float* bias_table, const fl
     }
     CuboidTables g;
     PD_TRY(build_cuboid_tables(T, H, W, sp, padding_type, &g));
+    PD_CHECK(!line_kernel || (g.axial_axis >= 0 && n_global <= 16), PD_ERR_ARG,
+             "pd_op_cuboid_attention_gv2: the line kernel takes axial layers with at most 16 global vectors");
     CuboidTablesDev d;
     PD_TRY(d.upload(g));
     cudaStream_t st = S(stream);
@@ -285,11 +299,14 @@ int pd_op_cuboid_attention_gv(const void* qkv, const float* bias_table, const fl
     float* ws = nullptr;
     PD_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws),
                             global_attention_workspace_floats(B, heads, n_global, C / heads, n_keys) * sizeof(float) + 16, st));
-    int rc = cuboid_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T * H * W, C, heads, d.dev,
-                              st, 1, static_cast<const bf16*>(gqkv_bf16), n_global);
-    if (rc == PD_OK)
-        rc = global_attention(gqkv_f32, static_cast<const bf16*>(qkv), static_cast<const bf16*>(gqkv_bf16), gout, ws, B, T * H * W,
-                              C, heads, n_global, self_attn, d.dev, st);
+    const bf16* g16 = static_cast<const bf16*>(grow_bf16);
+    const bf16* tok2 = static_cast<const bf16*>(tok2_bf16);
+    const GvKeys gk = gv_keys(g16, C, n_global, separate, grow_ld, tok2);
+    const GvQuery gq = gv_query(grow_f32, g16, static_cast<const bf16*>(qkv), tok2, C, separate, self_attn != 0, grow_ld);
+    int rc = line_kernel ? axial_attention(qkv, bias_table, out, B, T, H, W, C, heads, g.axial_axis, st, 0, &gk)
+                         : cuboid_attention(static_cast<const bf16*>(qkv), bias_table, static_cast<bf16*>(out), B, T * H * W, C,
+                                            heads, d.dev, st, 1, &gk);
+    if (rc == PD_OK) rc = global_attention(gq, gout, ws, B, T * H * W, C, heads, n_global, d.dev, st);
     cudaFreeAsync(ws, st);
     PD_CUDA(cudaStreamSynchronize(st));   // the tables are freed on return
     return rc;

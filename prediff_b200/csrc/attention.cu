@@ -46,14 +46,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 // in smem with cp.async (rows padded by 16 B so ldmatrix is bank-conflict free); per head the 16x16 score tile and
 // the 16xHD output come from warp-level mma.sync (the sequence is far too short to fill a 128-row tcgen05 tile:
 // this op is 0.25 % of the step's FLOPs), softmax stays in the accumulator registers.
-// GV: the sample's global vectors (cuboid_transformer.py:902-913) ride along as up to 16 more keys per line - k|v rows of gkv
-// [B][n_global][3C] staged beside the line, scores without position bias, never masked - one more 16-key tile through the same
-// fragments (the shipped config has no global vectors and runs the GV = false instantiation, unchanged).
+// GV: the sample's global vectors (cuboid_transformer.py:902-913) ride along as up to 16 more keys per line - their k / v rows
+// (GvKeys, ops.cuh) staged beside the line, scores without position bias, never masked - one more 16-key tile through the
+// same fragments; with separate_global_qkv the line's own rows of a second query tensor (gk.q2) meet those keys. (The
+// shipped config has no global vectors and runs the GV = false instantiation, unchanged.)
 template <int HD, bool GV>
 __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __restrict__ qkv,
                                                               const float* __restrict__ bias_table,
                                                               bf16* __restrict__ out, int T, int H, int W, int C,
-                                                              int heads, int axis, const bf16* __restrict__ gkv, int n_global) {
+                                                              int heads, int axis, const GvKeys gk) {
     grid_dep_launch();
     grid_dep_wait();
     extern __shared__ __align__(16) uint8_t smem_att[];
@@ -62,6 +63,9 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
     const int ld = C3 + 8;
     bf16* s_g = s_qkv + (size_t)kMaxLine * ld;        // GV: [16][2C + 8] = k | v rows of the global vectors
     const int ldg = 2 * C + 8;
+    bf16* s_q2 = s_g + (size_t)kMaxLine * ldg;        // GV, gk.q2: [16][C + 8] = the line's queries for the global keys
+    const int ldq2 = C + 8;
+    const int n_global = gk.n;
     int L, stride, base;
     {
         const int line = blockIdx.x;
@@ -88,13 +92,21 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
             else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);  // padded tokens: finite (zero) rows
         }
         if constexpr (GV) {
-            const bf16* grow = gkv + (size_t)(base / (T * H * W)) * n_global * C3 + C;   // the sample's rows, from the k part on
-            const int vpr = 2 * C / 8;
-            for (int i = threadIdx.x; i < kMaxLine * vpr; i += blockDim.x) {
-                const int r = i / vpr, v = i - r * vpr;
+            const size_t grow = (size_t)(base / (T * H * W)) * n_global * gk.ld;   // the sample's global rows
+            const int vpr = C / 8;
+            for (int i = threadIdx.x; i < kMaxLine * 2 * vpr; i += blockDim.x) {
+                const int r = i / (2 * vpr), v = i - r * 2 * vpr;   // v < vpr: key part, else value part
                 bf16* dst = s_g + (size_t)r * ldg + v * 8;
-                if (r < n_global) cp_async16(dst, grow + (size_t)r * C3 + v * 8);
+                if (r < n_global) cp_async16(dst, (v < vpr ? gk.k + v * 8 : gk.v + (v - vpr) * 8) + grow + (size_t)r * gk.ld);
                 else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (gk.q2) {
+                for (int i = threadIdx.x; i < kMaxLine * vpr; i += blockDim.x) {
+                    const int r = i / vpr, v = i - r * vpr;
+                    bf16* dst = s_q2 + (size_t)r * ldq2 + v * 8;
+                    if (r < L) cp_async16(dst, gk.q2 + (size_t)(base + r * stride) * gk.q2_ld + v * 8);
+                    else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
         }
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
@@ -124,8 +136,15 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const bf16* __rest
             if constexpr (GV) {
                 uint32_t bg[4];
                 ldmatrix_x4(bg, sgk + (size_t)((lane & 7) + 8 * (lane >> 4)) * ldg + kk * 16 + 8 * ((lane >> 3) & 1));
-                mma_bf16_16816(s2, a, bg[0], bg[1]);
-                mma_bf16_16816(s3, a, bg[2], bg[3]);
+                if (gk.q2) {   // separate_global_qkv: the tokens' l2g_q rows instead of q
+                    uint32_t a2[4];
+                    ldmatrix_x4(a2, s_q2 + h * HD + (size_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * ldq2 + kk * 16 + 8 * (lane >> 4));
+                    mma_bf16_16816(s2, a2, bg[0], bg[1]);
+                    mma_bf16_16816(s3, a2, bg[2], bg[3]);
+                } else {
+                    mma_bf16_16816(s2, a, bg[0], bg[1]);
+                    mma_bf16_16816(s3, a, bg[2], bg[3]);
+                }
             }
         }
         // thread holds rows g, g+8; keys {2tq, 2tq+1} (s0), {8+2tq, 9+2tq} (s1) and the same slots of the global tile (s2, s3)
@@ -382,14 +401,16 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
                                                                const int* __restrict__ lab, const int* __restrict__ rel,
                                                                const int* __restrict__ dstp, int N, int C, int heads, int vol,
                                                                int rel_off, int n_rel_smem, int kv_stages,
-                                                               const bf16* __restrict__ gkv, int n_global) {
+                                                               const GvKeys gk) {
     grid_dep_launch();
     grid_dep_wait();
     constexpr int LD = HD + 8;        // row pitch: +16 B keeps ldmatrix bank-conflict free
     constexpr int VPR = HD / 8;       // 16-byte vectors per row
     extern __shared__ __align__(16) uint8_t smem_cub[];
     bf16* sQ = reinterpret_cast<bf16*>(smem_cub);
-    bf16* sKV = sQ + kQTile * LD;                                  // [kv_stages][K | V][64][LD]
+    bf16* sQ2 = sQ + kQTile * LD;                                  // gk.q2 only: the tile's queries for the global keys
+    bf16* sKV = sQ + (gk.q2 ? 2 : 1) * kQTile * LD;                // [kv_stages][K | V][64][LD]
+    const int n_global = gk.n;
     int* s_qtok = reinterpret_cast<int*>(sKV + kv_stages * 2 * kQTile * LD);
     int* s_qlab = s_qtok + kQTile;
     int* s_qrel = s_qlab + kQTile;
@@ -406,8 +427,9 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
     const bf16* base = qkv + (size_t)b * N * C3 + h * HD;
     const bool bias_in_smem = n_rel_smem > 0;
     // global vectors (cuboid_transformer.py:902-913): after the cuboid's own slots every query sees the n_global <= 64 global
-    // keys (q|k|v rows gkv [B][n_global][3C]) as one more key chunk - never masked, no position bias
-    const bf16* gbase = n_global > 0 ? gkv + (size_t)b * n_global * C3 + h * HD : nullptr;
+    // keys (GvKeys: k / v rows [B][n_global][ld]) as one more key chunk - never masked, no position bias
+    const bf16* gkb = n_global > 0 ? gk.k + (size_t)b * n_global * gk.ld + h * HD : nullptr;
+    const bf16* gvb = n_global > 0 ? gk.v + (size_t)b * n_global * gk.ld + h * HD : nullptr;
 
     if (tid < kQTile) {
         const int i = q0 + tid;
@@ -447,8 +469,11 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
             const int t = m[r];
             bf16* dk = sK + r * LD + v * 8;
             bf16* dv = sV + r * LD + v * 8;
-            if (t >= 0) {
-                const bf16* src = (t >= kGlobalRow ? gbase + (size_t)(t - kGlobalRow) * C3 : base + (size_t)t * C3) + v * 8;
+            if (t >= kGlobalRow) {
+                cp_async16(dk, gkb + (size_t)(t - kGlobalRow) * gk.ld + v * 8);
+                cp_async16(dv, gvb + (size_t)(t - kGlobalRow) * gk.ld + v * 8);
+            } else if (t >= 0) {
+                const bf16* src = base + (size_t)t * C3 + v * 8;
                 cp_async16(dk, src + C);
                 cp_async16(dv, src + 2 * C);
             } else {
@@ -467,6 +492,11 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
         const int t = s_qtok[r];
         if (t >= 0) cp_async16(dst, base + (size_t)t * C3 + v * 8);
         else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        if (gk.q2) {   // separate_global_qkv: l2g_q rows of the same tokens
+            bf16* dst2 = sQ2 + r * LD + v * 8;
+            if (t >= 0) cp_async16(dst2, gk.q2 + ((size_t)b * N + t) * gk.q2_ld + h * HD + v * 8);
+            else *reinterpret_cast<uint4*>(dst2) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     load_rows(0);
 
@@ -505,10 +535,11 @@ __global__ void __launch_bounds__(128) cuboid_attention_kernel(const bf16* __res
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const bf16* sQa = (gk.q2 && ch >= n_chunks) ? sQ2 : sQ;   // the global chunk may have its own queries
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
             uint32_t a[4];
-            ldmatrix_x4(a, sQ + (size_t)(warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + kk * 16 + 8 * (lane >> 4));
+            ldmatrix_x4(a, sQa + (size_t)(warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LD + kk * 16 + 8 * (lane >> 4));
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
                 uint32_t bb[4];
@@ -657,8 +688,10 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
 }  // namespace
 
 int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int B, int T, int H, int W, int C, int heads,
-                    int axis, cudaStream_t st, int f32, const bf16* gkv, int n_global) {
-    PD_CHECK(n_global >= 0 && n_global <= kMaxLine && (n_global == 0 || (gkv && !f32)), PD_ERR_ARG,
+                    int axis, cudaStream_t st, int f32, const GvKeys* gkp) {
+    const GvKeys gk = gkp ? *gkp : GvKeys();
+    const int n_global = gk.n;
+    PD_CHECK(n_global >= 0 && n_global <= kMaxLine && (n_global == 0 || (gk.k && gk.v && !f32)), PD_ERR_ARG,
              "axial_attention: %d global vectors (at most %d, bf16 operands)", n_global, kMaxLine);
     PD_CHECK(axis >= 0 && axis <= 2, PD_ERR_ARG, "axial_attention: axis %d", axis);
     const int L = axis == 0 ? T : (axis == 1 ? H : W);
@@ -703,7 +736,8 @@ int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int
     }
     const bf16* qkv = static_cast<const bf16*>(qkv_v);
     bf16* out = static_cast<bf16*>(out_v);
-    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16) + (n_global ? (size_t)kMaxLine * (2 * C + 8) * sizeof(bf16) : 0);
+    const size_t smem = (size_t)kMaxLine * (3 * C + 8) * sizeof(bf16) + (n_global ? (size_t)kMaxLine * (2 * C + 8) * sizeof(bf16) : 0) +
+                        (n_global && gk.q2 ? (size_t)kMaxLine * (C + 8) * sizeof(bf16) : 0);
 #define PD_LAUNCH_AX(HDV)                                                                                            \
     do {                                                                                                             \
         static bool attr_set = false;                                                                                \
@@ -716,10 +750,10 @@ int axial_attention(const void* qkv_v, const float* bias_table, void* out_v, int
         }                                                                                                            \
         if (n_global)                                                                                                \
             PD_LAUNCH((axial_attention_kernel<HDV, true>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, \
-                      axis, gkv, n_global);                                                                          \
+                      axis, gk);                                                                                     \
         else                                                                                                         \
             PD_LAUNCH((axial_attention_kernel<HDV, false>), lines, threads, smem, st, qkv, bias_table, out, T, H, W, C, heads, \
-                      axis, gkv, n_global);                                                                          \
+                      axis, gk);                                                                                     \
     } while (0)
     PD_CHECK(smem <= 160 * 1024, PD_ERR_SHAPE, "axial_attention: line of %zu bytes does not fit in smem", smem);
     switch (hd) {
@@ -844,10 +878,12 @@ int build_cuboid_tables(int T, int H, int W, const CuboidLayerSpec& spec, int pa
 }
 
 int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
-                     const CuboidDev& g, cudaStream_t st, int impl, const bf16* gkv, int n_global) {
+                     const CuboidDev& g, cudaStream_t st, int impl, const GvKeys* gkp) {
     PD_CHECK(C % heads == 0, PD_ERR_SHAPE, "cuboid_attention: C=%d heads=%d", C, heads);
     const int hd = C / heads;
-    PD_CHECK(n_global >= 0 && n_global <= kQTile && (n_global == 0 || (gkv && impl != 2)), PD_ERR_ARG,
+    const GvKeys gk = gkp ? *gkp : GvKeys();
+    const int n_global = gk.n;
+    PD_CHECK(n_global >= 0 && n_global <= kQTile && (n_global == 0 || (gk.k && gk.v && impl != 2)), PD_ERR_ARG,
              "cuboid_attention: %d global vectors (at most %d, on the mma.sync kernel)", n_global, kQTile);
     if (n_global == 0 && (impl == 2 || (impl == 0 && cuboid_attention_tc_eligible(hd, g.volume))))
         return cuboid_attention_tc(qkv, bias_table, out, B, N, C, heads, g, st);
@@ -869,7 +905,7 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
     const int kv_stages = (g.volume > kQTile && !one_stage && !big_table) ? 2 : 1;
 #define PD_LAUNCH_CUB(HDV)                                                                                          \
     do {                                                                                                            \
-        const size_t smem = (size_t)(1 + 2 * kv_stages) * kQTile * (HDV + 8) * sizeof(bf16) +                       \
+        const size_t smem = (size_t)(1 + (gk.q2 ? 1 : 0) + 2 * kv_stages) * kQTile * (HDV + 8) * sizeof(bf16) +     \
                             9 * kQTile * sizeof(int) + (size_t)n_rel_smem * sizeof(float);                          \
         static size_t attr_bytes = 0;                                                                               \
         if (smem > attr_bytes) {                                                                                    \
@@ -878,7 +914,7 @@ int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B,
             attr_bytes = smem;                                                                                      \
         }                                                                                                           \
         PD_LAUNCH((cuboid_attention_kernel<HDV>), grid, 128, smem, st, qkv, bias_table, out, g.tok, g.lab, g.rel, g.dst, N, \
-                  C, heads, g.volume, g.rel_off, n_rel_smem, kv_stages, gkv, n_global);                             \
+                  C, heads, g.volume, g.rel_off, n_rel_smem, kv_stages, gk);                                        \
     } while (0)
     switch (hd) {
         case 16: PD_LAUNCH_CUB(16); break;

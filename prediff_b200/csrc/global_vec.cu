@@ -135,8 +135,7 @@ constexpr int kMaxGlobal = 32;   // K <= 32
 // KMAX: K rounded up to 8 / 16 / 32 - the bound of every per-query loop, so that 8 vectors do not pay the instruction
 // stream of 32 (predicated-off FMAs still issue: the first version ran 30 k warp instructions per block, 41 us).
 template <int HD, int KMAX>
-__global__ void __launch_bounds__(kGaThreads) global_attention_kernel(const float* __restrict__ gqkv, const bf16* __restrict__ qkv,
-                                                                      const bf16* __restrict__ gkv, const int* __restrict__ tok,
+__global__ void __launch_bounds__(kGaThreads) global_attention_kernel(const GvQuery a, const int* __restrict__ tok,
                                                                       const int* __restrict__ gmask, int n_slots, int n_keys,
                                                                       int keys_per_split, int K, int N, int C, int heads,
                                                                       float* __restrict__ part) {
@@ -155,14 +154,18 @@ __global__ void __launch_bounds__(kGaThreads) global_attention_kernel(const floa
     const float scale = rsqrtf((float)HD);
     for (int i = tid; i < KMAX * HD; i += kGaThreads) {
         const int g = i / HD, d = i - g * HD;
-        s_q[g][d] = g < K ? gqkv[((size_t)b * K + g) * C3 + h * HD + d] * scale : 0.f;   // q_global * scale (:899)
+        s_q[g][d] = g < K ? a.q[((size_t)b * K + g) * a.q_ld + h * HD + d] * scale : 0.f;   // q_global * scale (:899)
     }
     if (tid < KMAX) {
         s_m[tid] = -INFINITY;
         s_l[tid] = 0.f;
     }
-    const bf16* base = qkv + (size_t)b * N * C3 + h * HD;
-    const bf16* gbase = gkv + (size_t)b * K * C3 + h * HD;
+    const bf16* base = a.tok_kv + (size_t)b * N * C3 + h * HD;
+    const bf16* skb = a.sk ? a.sk + (size_t)b * K * a.s_ld + h * HD : nullptr;   // self-attention: the global keys / values
+    const bf16* svb = a.sv ? a.sv + (size_t)b * K * a.s_ld + h * HD : nullptr;
+    // separate_global_qkv: the global keys meet another query set (g2g_global_q) than the token keys do; it is read from
+    // global memory by the <= 32 threads that hold a global key (one pass of one block per (sample, head))
+    const float* sqb = (a.sq && a.sq != a.q) ? a.sq + (size_t)b * K * a.sq_ld + h * HD : nullptr;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
@@ -183,22 +186,40 @@ __global__ void __launch_bounds__(kGaThreads) global_attention_kernel(const floa
                         row = t >= 0 ? (long long)t * C3 : -1;
                     }
                 } else {
-                    row = (long long)(j - n_slots) * C3;
+                    row = (long long)(j - n_slots) * a.s_ld;
                     isg = 1;
                 }
             }
-            const bf16* rp = (isg ? gbase : base) + (row >= 0 ? row : 0);
+            const bf16* kp = isg ? skb + row : base + (row >= 0 ? row : 0) + C;
+            const bf16* vp = isg ? svb + row : base + (row >= 0 ? row : 0) + 2 * C;
             if (tid < kGaKeys) {
                 s_row[kt] = row;
                 uint4 u[HD / 8];
                 if (row >= 0) {
 #pragma unroll
-                    for (int i = 0; i < HD / 8; ++i) u[i] = *reinterpret_cast<const uint4*>(rp + C + 8 * i);   // all loads in flight
+                    for (int i = 0; i < HD / 8; ++i) u[i] = *reinterpret_cast<const uint4*>(kp + 8 * i);   // all loads in flight
                 }
                 float sc[KMAX];
 #pragma unroll
                 for (int g = 0; g < KMAX; ++g) sc[g] = 0.f;
-                if (row >= 0) {
+                if (row >= 0 && isg && sqb) {   // a global key under separate_global_qkv: queries from global memory
+#pragma unroll 1
+                    for (int g = 0; g < K; ++g) {
+                        const float* qg2 = sqb + (size_t)g * a.sq_ld;
+                        float acc2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < HD / 8; ++i) {
+                            const float2 f0 = unpack_bf16x2(u[i].x), f1 = unpack_bf16x2(u[i].y), f2 = unpack_bf16x2(u[i].z),
+                                         f3 = unpack_bf16x2(u[i].w);
+                            const float4 qa = __ldg(reinterpret_cast<const float4*>(qg2 + 8 * i));
+                            const float4 qb = __ldg(reinterpret_cast<const float4*>(qg2 + 8 * i + 4));
+                            acc2 = fmaf(qa.x, f0.x, acc2); acc2 = fmaf(qa.y, f0.y, acc2); acc2 = fmaf(qa.z, f1.x, acc2);
+                            acc2 = fmaf(qa.w, f1.y, acc2); acc2 = fmaf(qb.x, f2.x, acc2); acc2 = fmaf(qb.y, f2.y, acc2);
+                            acc2 = fmaf(qb.z, f3.x, acc2); acc2 = fmaf(qb.w, f3.y, acc2);
+                        }
+                        s_p[g][kt] = acc2 * scale;
+                    }
+                } else if (row >= 0) {
 #pragma unroll
                     for (int i = 0; i < HD / 8; ++i) {
                         const float2 f0 = unpack_bf16x2(u[i].x), f1 = unpack_bf16x2(u[i].y), f2 = unpack_bf16x2(u[i].z),
@@ -214,13 +235,15 @@ __global__ void __launch_bounds__(kGaThreads) global_attention_kernel(const floa
                         }
                     }
                 }
+                if (!(row >= 0 && isg && sqb)) {
 #pragma unroll
-                for (int g = 0; g < KMAX; ++g) s_p[g][kt] = row == LLONG_MIN ? -INFINITY : sc[g];
+                    for (int g = 0; g < KMAX; ++g) s_p[g][kt] = row == LLONG_MIN ? -INFINITY : sc[g];
+                }
             } else {
                 uint4* dst = reinterpret_cast<uint4*>(&s_v[kt][0]);
                 if (row >= 0) {
 #pragma unroll
-                    for (int i = 0; i < HD / 8; ++i) dst[i] = *reinterpret_cast<const uint4*>(rp + 2 * C + 8 * i);
+                    for (int i = 0; i < HD / 8; ++i) dst[i] = *reinterpret_cast<const uint4*>(vp + 8 * i);
                 } else {   // masked or a zero-padded slot: v = 0
 #pragma unroll
                     for (int i = 0; i < HD / 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -332,9 +355,13 @@ size_t global_attention_workspace_floats(int B, int heads, int K, int hd, int n_
     return (size_t)B * heads * global_attention_splits(n_keys) * K * (hd + 2);
 }
 
-int global_attention(const float* gqkv, const bf16* qkv, const bf16* gkv, float* out, float* workspace, int B, int N, int C,
-                     int heads, int K, int self_attn, const CuboidDev& g, cudaStream_t st) {
-    PD_CHECK(gqkv && qkv && gkv && out && workspace, PD_ERR_ARG, "global_attention: null pointer");
+int global_attention(const GvQuery& a, float* out, float* workspace, int B, int N, int C, int heads, int K, const CuboidDev& g,
+                     cudaStream_t st) {
+    PD_CHECK(a.q && a.tok_kv && out && workspace, PD_ERR_ARG, "global_attention: null pointer");
+    const int self_attn = a.sq != nullptr;
+    PD_CHECK(!self_attn || (a.sk && a.sv && a.s_ld > 0), PD_ERR_ARG, "global_attention: self-attention needs keys and values");
+    PD_CHECK(a.q_ld % 4 == 0 && (!self_attn || (a.sq_ld % 4 == 0 && a.s_ld % 8 == 0)), PD_ERR_ARG,
+             "global_attention: row strides must keep 16-byte alignment");
     PD_CHECK(K >= 1 && K <= kMaxGlobal, PD_ERR_SHAPE, "global vectors: %d (1..%d are built)", K, kMaxGlobal);
     PD_CHECK(C % heads == 0, PD_ERR_SHAPE, "global_attention: C=%d heads=%d", C, heads);
     const int hd = C / heads;
@@ -344,8 +371,8 @@ int global_attention(const float* gqkv, const bf16* qkv, const bf16* gkv, float*
     const int per = global_attention_keys_per_split(n_keys);
     dim3 grid(splits, heads, B);
 #define PD_GA(HDV, KM)                                                                                                         \
-    PD_LAUNCH((global_attention_kernel<HDV, KM>), grid, kGaThreads, 0, st, gqkv, qkv, gkv, g.tok, g.gmask, n_slots, n_keys, per, K, \
-              N, C, heads, workspace)
+    PD_LAUNCH((global_attention_kernel<HDV, KM>), grid, kGaThreads, 0, st, a, g.tok, g.gmask, n_slots, n_keys, per, K, N, C, \
+              heads, workspace)
 #define PD_GA_K(HDV)                          \
     case HDV:                                 \
         if (K <= 8) PD_GA(HDV, 8);            \

@@ -29,10 +29,20 @@ int patch_merge_ln(const float* x, const float* gamma, const float* beta, void* 
 // `axis` (0=T, 1=H, 2=W) and head, relative-position bias table fp32 [2L-1][heads]; out bf16 [B][T][H][W][C].
 // Reference: cuboid_transformer.py:849-861,949 with cuboids (T,1,1)/(1,H,1)/(1,1,W) (patterns.py:34-36).
 // f32 = 1: qkv and out are fp32 (out tf32-rounded) and the whole core runs in fp32 on the CUDA cores.
-// gkv / n_global (bf16 mode only): q|k|v rows of the sample's global vectors [B][n_global][3C], n_global <= 16 - every
-// query also attends to their keys, unmasked and without position bias (cuboid_transformer.py:902-913).
+// The global vectors as extra keys of the token grid's queries (cuboid_transformer.py:902-913: unmasked, no position bias).
+// Shared global_qkv net: k / v point into the rows of one [B][n][3C] tensor (ld = 3C, offsets C and 2C). separate_global_qkv
+// (:866-891): k / v rows of l2g_global_kv_net and q2 = the tokens' l2g_q_net rows, which meet these keys instead of q.
+struct GvKeys {
+    const bf16* k = nullptr;    // [B][n][ld]: keys (head-major channels)
+    const bf16* v = nullptr;    // [B][n][ld]: values
+    int ld = 0;                 // elements between consecutive global rows
+    int n = 0;                  // number of global vectors (0 = none)
+    const bf16* q2 = nullptr;   // [B][N][q2_ld]: the tokens' queries for the global keys (null: the layer's own q)
+    int q2_ld = 0;
+};
+// gk (bf16 mode only, gk->n <= 16): every query of a line also attends to the sample's global keys.
 int axial_attention(const void* qkv, const float* bias_table, void* out, int B, int T, int H, int W, int C, int heads,
-                    int axis, cudaStream_t st, int f32 = 0, const bf16* gkv = nullptr, int n_global = 0);
+                    int axis, cudaStream_t st, int f32 = 0, const GvKeys* gk = nullptr);
 // General cuboid self-attention core (any cuboid size, 'l' / 'd' strategy, shifted windows, end padding with
 // padding_type 'zeros' (0) or 'ignore' (1)): cuboid_transformer.py:812-966 without global vectors.
 struct CuboidLayerSpec {   // constructor arguments of one CuboidSelfAttentionLayer
@@ -73,10 +83,9 @@ struct CuboidTablesDev {   // owner of the device copies
 };
 // qkv bf16 [B][N][3C] (N = T*H*W tokens per sample, q|k|v head-major), bias_table fp32 [n_rel][heads] -> out bf16 [B][N][C]
 // impl: 0 = choose (tcgen05 tile kernel when eligible, see below), 1 = warp-level mma.sync kernel, 2 = tcgen05 tile kernel
-// gkv / n_global: q|k|v rows of the sample's global vectors, bf16 [B][n_global][3C] (n_global <= 64) - every query also
-// attends to their keys, unmasked and without position bias (cuboid_transformer.py:902-913); mma.sync kernel only
+// gk (gk->n <= 64): every query also attends to the sample's global keys (GvKeys above); mma.sync kernel only
 int cuboid_attention(const bf16* qkv, const float* bias_table, bf16* out, int B, int N, int C, int heads,
-                     const CuboidDev& g, cudaStream_t st, int impl = 0, const bf16* gkv = nullptr, int n_global = 0);
+                     const CuboidDev& g, cudaStream_t st, int impl = 0, const GvKeys* gk = nullptr);
 // The same contract on tcgen05 tensor-core tiles (attention_tc.cu): 128-query tile per (cuboid, head, sample), S and O in
 // TMEM, K / V chunks of 128 keys in a swizzled shared-memory ring. Eligible for head dims 64 / 128 and volumes >= 128
 // (cuboid_attention() dispatches to it; PD_CUBOID_NO_TC=1 keeps the mma.sync kernel for A/B runs).
@@ -96,8 +105,50 @@ int gv_broadcast(const float* init, float* g, int B, int K, int C, cudaStream_t 
 // self_attn the global keys / values gkv bf16 [B][K][3C] appended -> out fp32 [B][K][C] (before global_proj).
 // workspace: global_attention_workspace_floats(...) floats. K <= 32.
 size_t global_attention_workspace_floats(int B, int heads, int K, int hd, int n_keys);
-int global_attention(const float* gqkv, const bf16* qkv, const bf16* gkv, float* out, float* workspace, int B, int N, int C,
-                     int heads, int K, int self_attn, const CuboidDev& g, cudaStream_t st);
+// Operands of the global queries' attention. Shared net: q = sq = the fp32 q|k|v rows (ld 3C), tok_kv = the layer's q|k|v,
+// sk / sv = the bf16 copy at offsets C / 2C. separate_global_qkv: q = g2l_global_q rows, tok_kv = the tokens' l2g_q | g2l_k |
+// g2l_v rows (k at +C, v at +2C like q|k|v), sq / sk / sv = the g2g_global_qkv rows.
+struct GvQuery {
+    const float* q = nullptr;       // [B][K][q_ld] fp32: queries for the token keys (scaled by hd^-0.5 inside)
+    int q_ld = 0;
+    const bf16* tok_kv = nullptr;   // [B][N][3C] bf16: the tokens' rows, keys at +C, values at +2C
+    const float* sq = nullptr;      // [B][K][sq_ld] fp32: queries for the global keys (self-attention; null: none)
+    int sq_ld = 0;
+    const bf16* sk = nullptr;       // [B][K][s_ld] bf16: global keys / values of the self-attention
+    const bf16* sv = nullptr;
+    int s_ld = 0;
+};
+int global_attention(const GvQuery& a, float* out, float* workspace, int B, int N, int C, int heads, int K, const CuboidDev& g,
+                     cudaStream_t st);
+// Row layouts of the global vectors' projections as the models produce them (one gv_linear over stacked weights):
+//   shared net     [q | k | v]                                          ld = 3C
+//   separate nets  [l2g_k | l2g_v | g2l_q | g2g_q | g2g_k | g2g_v]      ld = 3C (no global self-attention) or 6C
+// g32 / g16: the fp32 rows and their bf16 copy; tok_qkv: the layer's q|k|v; tok2: the tokens' l2g_q | g2l_k | g2l_v rows (separate).
+inline GvKeys gv_keys(const bf16* g16, int C, int K, bool separate, int ld, const bf16* tok2) {
+    GvKeys k;
+    k.k = separate ? g16 : g16 + C;
+    k.v = separate ? g16 + C : g16 + 2 * C;
+    k.ld = ld;
+    k.n = K;
+    k.q2 = separate ? tok2 : nullptr;
+    k.q2_ld = 3 * C;
+    return k;
+}
+inline GvQuery gv_query(const float* g32, const bf16* g16, const bf16* tok_qkv, const bf16* tok2, int C, bool separate,
+                        bool self_attn, int ld) {
+    GvQuery q;
+    q.q = separate ? g32 + 2 * C : g32;
+    q.q_ld = ld;
+    q.tok_kv = separate ? tok2 : tok_qkv;
+    if (self_attn) {
+        q.sq = separate ? g32 + 3 * C : g32;
+        q.sq_ld = ld;
+        q.sk = separate ? g16 + 4 * C : g16 + C;
+        q.sv = separate ? g16 + 5 * C : g16 + 2 * C;
+        q.s_ld = ld;
+    }
+    return q;
+}
 // Row softmax for the VAE AttentionBlock: s fp32 [rows][L] -> p bf16 [rows][L], p = softmax(scale * s).
 int softmax_rows(const float* s, bf16* p, int rows, int L, float scale, cudaStream_t st);
 // Batched transpose bf16: in [S][R][ld_in] (first C columns used) -> out [S][C][R].

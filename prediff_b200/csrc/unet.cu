@@ -25,6 +25,7 @@ struct UNet::Bufs {
     // keys / values), the global queries' attention output, the global FFN's hidden rows, split partials of that attention
     float *gv[2] = {nullptr, nullptr}, *g_qkv = nullptr, *g_att = nullptr, *g_mid = nullptr, *g_ws = nullptr;
     bf16* g_qkv_bf16 = nullptr;
+    bf16* qkv2[2] = {nullptr, nullptr};   // separate_global_qkv: the tokens' l2g_q | g2l_k | g2l_v rows
     double* gn_sums;
     int* split_flags;  // split-K tile handshake flags, shared by all convs of the plan (kernels run one at a time)
 };
@@ -63,8 +64,10 @@ struct UNet::BatchPlan {
 
 UNet::~UNet() = default;
 
-UNet::UNet(const pd_unet_config& c, const pd_unet_pattern* pattern, int n_global_, int global_ffn_, int global_self_attn_)
-    : cfg(c), n_global(n_global_), global_ffn(global_ffn_ != 0), global_self_attn(global_self_attn_ != 0) {
+UNet::UNet(const pd_unet_config& c, const pd_unet_pattern* pattern, int n_global_, int global_ffn_, int global_self_attn_,
+           int global_separate_)
+    : cfg(c), n_global(n_global_), global_ffn(global_ffn_ != 0), global_self_attn(global_self_attn_ != 0),
+      global_separate(global_separate_ != 0 && n_global_ > 0) {
     C0 = cfg.base_units;
     C1 = 2 * cfg.base_units;
     T = cfg.t_in + cfg.t_out;
@@ -127,7 +130,16 @@ void UNet::declare_stack(const std::string& p, int dim, int lvl) {
         ws.declare(a + ".relative_position_bias_table",
                    {(2 * std::max(sz[0], 1) - 1) * (2 * std::max(sz[1], 1) - 1) * (2 * std::max(sz[2], 1) - 1), cfg.num_heads});
         ws.declare(a + ".qkv.weight", {3 * dim, dim});
-        if (n_global > 0) ws.declare(a + ".global_qkv.weight", {3 * dim, dim});
+        if (n_global > 0 && global_separate) {   // registration order of cuboid_transformer.py:770-795
+            ws.declare(a + ".l2g_q_net.weight", {dim, dim});
+            ws.declare(a + ".l2g_global_kv_net.weight", {2 * dim, dim});
+            ws.declare(a + ".g2l_global_q_net.weight", {dim, dim});
+            ws.declare(a + ".g2l_k_net.weight", {dim, dim});
+            ws.declare(a + ".g2l_v_net.weight", {dim, dim});
+            if (global_self_attn) ws.declare(a + ".g2g_global_qkv_net.weight", {3 * dim, dim});
+        } else if (n_global > 0) {
+            ws.declare(a + ".global_qkv.weight", {3 * dim, dim});
+        }
         ws.declare(a + ".proj.weight", {dim, dim});
         ws.declare(a + ".proj.bias", {dim});
         if (n_global > 0) {
@@ -281,7 +293,38 @@ int UNet::finalize_stack(const std::string& p, int dim, int lvl, StackW* s) {
         if (n_global > 0) {
             PD_GETW(s->a[i].g_ln_w, a + ".global_vec_norm.weight");
             PD_GETW(s->a[i].g_ln_b, a + ".global_vec_norm.bias");
-            PD_GETW(s->a[i].g_qkv_w, a + ".global_qkv.weight");
+            if (global_separate) {
+                // stacked fp32 weights of the global rows' projection: l2g_global_kv (2 dim) | g2l_global_q | g2g_global_qkv (3 dim)
+                const float *wkv, *wq, *wg = nullptr;
+                PD_GETW(wkv, a + ".l2g_global_kv_net.weight");
+                PD_GETW(wq, a + ".g2l_global_q_net.weight");
+                if (global_self_attn) PD_GETW(wg, a + ".g2g_global_qkv_net.weight");
+                const size_t dd = (size_t)dim * dim;
+                gv_stacked.emplace_back(new DevMem());
+                PD_TRY(gv_stacked.back()->alloc((size_t)g_row_ld(dim) * dim * sizeof(float)));
+                float* st = gv_stacked.back()->as<float>();
+                PD_CUDA(cudaMemcpy(st, wkv, 2 * dd * sizeof(float), cudaMemcpyDeviceToDevice));
+                PD_CUDA(cudaMemcpy(st + 2 * dd, wq, dd * sizeof(float), cudaMemcpyDeviceToDevice));
+                if (wg) PD_CUDA(cudaMemcpy(st + 3 * dd, wg, 3 * dd * sizeof(float), cudaMemcpyDeviceToDevice));
+                s->a[i].g_qkv_w = st;
+                // the tokens' second projection: l2g_q | g2l_k | g2l_v stacked into one [3 dim][dim] GEMM operand
+                const float *w0, *w1, *w2;
+                PD_GETW(w0, a + ".l2g_q_net.weight");
+                PD_GETW(w1, a + ".g2l_k_net.weight");
+                PD_GETW(w2, a + ".g2l_v_net.weight");
+                DevMem tmp;
+                PD_TRY(tmp.alloc(3 * dd * sizeof(float)));
+                PD_CUDA(cudaMemcpy(tmp.as<float>(), w0, dd * sizeof(float), cudaMemcpyDeviceToDevice));
+                PD_CUDA(cudaMemcpy(tmp.as<float>() + dd, w1, dd * sizeof(float), cudaMemcpyDeviceToDevice));
+                PD_CUDA(cudaMemcpy(tmp.as<float>() + 2 * dd, w2, dd * sizeof(float), cudaMemcpyDeviceToDevice));
+                packed.emplace_back(new DevMem());
+                PD_TRY(packed.back()->alloc(3 * dd * op_bytes()));
+                s->a[i].tok2_w = packed.back()->as<bf16>();
+                PD_TRY(pack_linear(tmp.as<float>(), s->a[i].tok2_w, 3 * dim, dim, dim, 0, precision));
+                PD_CUDA(cudaDeviceSynchronize());   // tmp is freed on scope exit
+            } else {
+                PD_GETW(s->a[i].g_qkv_w, a + ".global_qkv.weight");
+            }
             PD_GETW(s->a[i].g_proj_w, a + ".global_proj.weight");
             PD_GETW(s->a[i].g_proj_b, a + ".global_proj.bias");
         }
@@ -308,6 +351,7 @@ int UNet::finalize() {
     PD_TRY(ws.check_complete());
     ++generation;
     packed.clear();
+    gv_stacked.clear();
     plans.clear();
     const int cin = cfg.c + 1;
     // first_proj: GroupNorm over 65 channels = 65 groups (time_embed.py:90); padded to 128 one-channel groups with
@@ -428,8 +472,10 @@ void UNet::carve(A& ar, int B, Bufs* b) const {
     if (n_global > 0) {   // global vectors: B * K rows per level + their q|k|v, attention output, FFN hidden, split partials
         const size_t M = (size_t)B * n_global;
         for (int l = 0; l < 2; ++l) b->gv[l] = ar.template take<float>(M * C[l]);
-        b->g_qkv = ar.template take<float>(M * 3 * C1);
-        b->g_qkv_bf16 = ar.template take<bf16>(M * 3 * C1);
+        b->g_qkv = ar.template take<float>(M * g_row_ld(C1));
+        b->g_qkv_bf16 = ar.template take<bf16>(M * g_row_ld(C1));
+        if (global_separate)
+            for (int l = 0; l < 2; ++l) b->qkv2[l] = ar.template take<bf16>(P[l] * 3 * C[l]);
         b->g_att = ar.template take<float>(M * C1);
         b->g_mid = ar.template take<float>(M * 4 * C1);
         size_t wsf = 0;
@@ -565,7 +611,9 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
         if (!ln_ready) pl.add([=](cudaStream_t st) { return layer_norm(x, aw.ln_w, aw.ln_b, ln, P, C, 1e-5f, st, prec); }, "ln");
         // global vectors (cuboid_transformer.py:819-822, 893-901): q|k|v rows of LayerNorm(global_vectors) through the shared
         // global_qkv net - fp32 for the global queries, a bf16 copy as the extra keys / values of every cuboid
-        const int Kg = n_global, Mg = B * n_global, gsa = global_self_attn ? 1 : 0;
+        const int Kg = n_global, Mg = B * n_global, g_ld = g_row_ld(C);
+        const bool gsep = global_separate, gsa = global_self_attn;
+        bf16* qkv2 = b.qkv2[lvl];
         float *gv = b.gv[lvl], *g_qkv = b.g_qkv, *g_att = b.g_att, *g_mid = b.g_mid, *g_ws = b.g_ws;
         bf16* g_qkv_bf16 = b.g_qkv_bf16;
         // The global rows' kernels form a second lane (Plan::lane): beside the token grid's projection + FFN kernel, which
@@ -580,7 +628,7 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             if (gv_lanes) pl.lane(1);
             pl.wait(gv_mark_attn_);
             pl.add([=](cudaStream_t st) {
-                return gv_linear(gv, aw.g_ln_w, aw.g_ln_b, aw.g_qkv_w, nullptr, nullptr, g_qkv, g_qkv_bf16, Mg, C, 3 * C, 0, st);
+                return gv_linear(gv, aw.g_ln_w, aw.g_ln_b, aw.g_qkv_w, nullptr, nullptr, g_qkv, g_qkv_bf16, Mg, C, g_ld, 0, st);
             }, "gv.qkv");
             m_gqkv = pl.mark();
             pl.lane(0);
@@ -602,14 +650,23 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             if (Kg > 0) pl.wait(gv_mark_gvattn_);
             pl.add_gemm(op, "qkv");
         }
+        if (Kg > 0 && gsep) {   // separate_global_qkv: the tokens' second projection l2g_q | g2l_k | g2l_v (:866-888)
+            GemmEpilogue e;
+            operand_out(e, qkv2);
+            GemmOp op;
+            PD_TRY(gemm_make(&op, ln, geom(GemmGeom::linear(P, C)), aw.tok2_w, 3 * C, e));
+            pl.add_gemm(op, "qkv2");
+        }
+        const GvKeys gkeys = gv_keys(g_qkv_bf16, C, Kg, gsep, g_ld, qkv2);
         if (Kg > 0) {   // the global vectors' own update, on the side lane
             const int m_qkv = pl.mark();
             const CuboidDev cd = cub_dev[lvl][i]->dev;
+            const GvQuery gquery = gv_query(g_qkv, g_qkv_bf16, qkv, qkv2, C, gsep, gsa, g_ld);
             if (gv_lanes) pl.lane(1);
             pl.wait(m_qkv);
             // (:928-945, 951-952, 1137): attention over every slot (+ themselves), then global_vectors += global_proj(.)
             pl.add([=](cudaStream_t st) {
-                return global_attention(g_qkv, qkv, g_qkv_bf16, g_att, g_ws, B, N_tok, C, heads, Kg, gsa, cd, st);
+                return global_attention(gquery, g_att, g_ws, B, N_tok, C, heads, Kg, cd, st);
             }, "gv.attn");
             gv_mark_gvattn_ = pl.mark();
             pl.add([=](cudaStream_t st) {
@@ -633,13 +690,13 @@ int UNet::add_stack(Plan& pl, const Bufs& b, int B, int lvl, const StackW& s, do
             // axial layer: one block per line (with global vectors: their <= 16 keys as a second key tile of the same kernel)
             const int axis = cub_axis[lvl][i];
             pl.add([=](cudaStream_t st) {
-                return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st, prec, Kg ? g_qkv_bf16 : nullptr, Kg);
+                return axial_attention(qkv, aw.table, att, B, Tn, H, W, C, heads, axis, st, prec, Kg ? &gkeys : nullptr);
             }, axis == 0 ? "attn_T" : (axis == 1 ? "attn_H" : "attn_W"));
         } else {   // any other cuboid (shifted / padded / dilated / multi-axis): gather tables + flash-style kernel
             const CuboidDev cd = cub_dev[lvl][i]->dev;
             if (Kg > 0)
                 pl.add([=](cudaStream_t st) {
-                    return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st, 1, g_qkv_bf16, Kg);
+                    return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st, 1, &gkeys);
                 }, "attn_cuboid_gv");
             else
                 pl.add([=](cudaStream_t st) { return cuboid_attention(qkv, aw.table, att, B, N_tok, C, heads, cd, st); },

@@ -14,8 +14,11 @@ struct ResW {   // TimeEmbedResBlock
 struct AttnW {  // CuboidSelfAttentionLayer
     const float *ln_w, *ln_b, *table, *proj_b;
     bf16 *qkv_w, *proj_w;
-    // global vectors (fp32 weights in the reference layout, used as loaded): global_vec_norm, global_qkv, global_proj
+    // global vectors (fp32 weights in the reference layout, used as loaded): global_vec_norm, global_proj and the rows'
+    // projection - global_qkv [3C][C], or with separate_global_qkv the stack l2g_global_kv | g2l_global_q [| g2g_global_qkv]
+    // ([3C or 6C][C], concatenated at finalize) - plus, separate only, the tokens' second projection l2g_q | g2l_k | g2l_v
     const float *g_ln_w = nullptr, *g_ln_b = nullptr, *g_qkv_w = nullptr, *g_proj_w = nullptr, *g_proj_b = nullptr;
+    bf16* tok2_w = nullptr;   // packed [3C][C]
 };
 struct FfnW {   // PositionwiseFFN
     const float *ln_w, *ln_b, *b1, *b2;
@@ -36,7 +39,8 @@ public:
     struct BatchPlan;
 
     // n_global > 0: global vectors (cuboid_transformer_unet.py:55-60 with separate_global_qkv=False, global_dim_ratio=1)
-    UNet(const pd_unet_config& c, const pd_unet_pattern* pattern, int n_global = 0, int global_ffn = 1, int global_self_attn = 0);
+    UNet(const pd_unet_config& c, const pd_unet_pattern* pattern, int n_global = 0, int global_ffn = 1, int global_self_attn = 0,
+         int global_separate = 0);
     ~UNet();
     int validate() const;
     int finalize();
@@ -63,6 +67,8 @@ public:
     int padding_type = 0;   // 0 = 'zeros', 1 = 'ignore', 2 = 'nearest'
     int n_global = 0;       // num_global_vectors
     bool global_ffn = true, global_self_attn = false;
+    bool global_separate = false;   // separate_global_qkv
+    int g_row_ld(int C) const { return (global_separate && global_self_attn ? 6 : 3) * C; }   // width of the global rows' projection
     bool all_axial = true;
     WeightStore ws;
     bool finalized = false;
@@ -114,6 +120,7 @@ private:
     // k | v buffer) and of the last global attention (reader of the grid's q|k|v buffer)
     int gv_mark_attn_ = -1, gv_mark_gvattn_ = -1;
     std::vector<std::unique_ptr<DevMem>> packed;
+    std::vector<std::unique_ptr<DevMem>> gv_stacked;   // concatenated fp32 weights of the separate global nets
     std::vector<std::unique_ptr<CuboidTablesDev>> cub_dev[2];   // per level, per layer (null for axial fast-path layers)
     std::vector<int> cub_axis[2];                               // axial fast-path axis or -1
     std::map<std::pair<int, int>, std::unique_ptr<BatchPlan>> plans;  // (batch, replica)

@@ -3,7 +3,7 @@
 
 Same constructor argument names, `forward(x, t, cond, verbose=False)` contract, `state_dict()` key names and
 shapes. Built: two levels, patch-merge / upsample, GELU FFN, relative position bias, global vectors (num_global_vectors
-<= 32 with the shared global_qkv net: separate_global_qkv=False, global_dim_ratio=1), and every
+<= 32, shared global_qkv net or separate_global_qkv=True, global_dim_ratio=1), and every
 registered `block_attn_patterns` name (axial - the shipped SEVIR-LR config, on its own fast path - full, divided_st,
 video_swin_PxM, spatial_lg_M, axial_space_dilate_K; prediff_b200/patterns.py) with 'zeros', 'ignore' or 'nearest' padding;
 anything else raises NotImplementedError at construction - there is no fallback path.
@@ -37,8 +37,8 @@ class _CUnetPattern(ctypes.Structure):
 
 def _unsupported(what):
     raise NotImplementedError(f"prediff_b200.CuboidTransformerUNet: {what} is not built (only the SEVIR-LR "
-                              "configuration family: registered self-attention patterns, 2 levels, global vectors with the "
-                              "shared q|k|v net)")
+                              "configuration family: registered self-attention patterns, 2 levels, global vectors with "
+                              "global_dim_ratio=1)")
 
 
 class CuboidTransformerUNet(nn.Module):
@@ -99,7 +99,6 @@ class CuboidTransformerUNet(nn.Module):
                   (not hierarchical_pos_embed, "hierarchical_pos_embed"), (pos_embed_type == "t+h+w", "pos_embed_type"),
                   (use_relative_pos, "use_relative_pos=False"), (self_attn_use_final_proj, "self_attn_use_final_proj"),
                   (0 <= int(num_global_vectors or 0) <= 32, "num_global_vectors > 32"),
-                  (not num_global_vectors or not separate_global_qkv, "separate_global_qkv=True"),
                   (not num_global_vectors or global_dim_ratio == 1, "global_dim_ratio != 1"),
                   (not num_global_vectors or precision == "bf16", "global vectors with precision='tf32'"),
                   (time_embed_channels_mult == 4, "time_embed_channels_mult"),
@@ -110,7 +109,8 @@ class CuboidTransformerUNet(nn.Module):
         self.cfg = UNetConfig(t_in=T_in, t_out=T_out, h=H, w=W, c=C, base_units=base_units, depth=tuple(depth),
                               num_heads=num_heads, patterns=tuple(patterns), padding_type=padding_type,
                               explicit_layers=explicit, num_global_vectors=int(num_global_vectors or 0),
-                              use_global_vector_ffn=bool(use_global_vector_ffn), use_global_self_attn=bool(use_global_self_attn))
+                              use_global_vector_ffn=bool(use_global_vector_ffn), use_global_self_attn=bool(use_global_self_attn),
+                              separate_global_qkv=bool(separate_global_qkv) and bool(num_global_vectors))
         self.num_global_vectors = self.cfg.num_global_vectors
         self.use_global_vector = self.num_global_vectors > 0
         for lvl in range(2):
@@ -162,8 +162,9 @@ class CuboidTransformerUNet(nn.Module):
                             pt.cuboid_size[lvl][i][a] = size[a]
                             pt.strategy[lvl][i][a] = 0 if strategy[a] == "l" else 1
                             pt.shift_size[lvl][i][a] = shift[a]
-                L.check(L.lib().pd_unet_create_gv(ctypes.byref(cc), ctypes.byref(pt), c.num_global_vectors,
-                                                  int(c.use_global_vector_ffn), int(c.use_global_self_attn), ctypes.byref(h)))
+                L.check(L.lib().pd_unet_create_gv_ex(ctypes.byref(cc), ctypes.byref(pt), c.num_global_vectors,
+                                                     int(c.use_global_vector_ffn), int(c.use_global_self_attn),
+                                                     int(c.separate_global_qkv), ctypes.byref(h)))
             self._handle = h
             self._dirty = True
         return self._handle

@@ -42,11 +42,16 @@ def test_unet_and_vae_weight_specs_match_reference_keys():
     # global vectors (cuboid_transformer_unet.py:124-126, 167-191; cuboid_transformer.py:777-810, 1054-1068): the extra keys, in
     # the reference's registration order (pinned against the reference's state_dict by tests/golden/gen_golden.py::ref_unet)
     import dataclasses
-    for gffn, pats in ((True, ("axial", "axial")), (False, ("video_swin_2x8", "spatial_lg_4"))):
-        cfg = dataclasses.replace(Wt.TINY_UNET, num_global_vectors=4, use_global_vector_ffn=gffn, patterns=pats)
+    for gffn, pats, sep, gsa in ((True, ("axial", "axial"), False, True), (False, ("video_swin_2x8", "spatial_lg_4"), False, True),
+                                 (False, ("axial", "axial"), True, True), (True, ("axial", "axial"), True, False)):
+        cfg = dataclasses.replace(Wt.TINY_UNET, num_global_vectors=4, use_global_vector_ffn=gffn, patterns=pats,
+                                  separate_global_qkv=sep, use_global_self_attn=gsa)
         m = CuboidTransformerUNet([cfg.t_in, cfg.h, cfg.w, cfg.c], [cfg.t_out, cfg.h, cfg.w, cfg.c], base_units=cfg.base_units,
                                   depth=list(cfg.depth), num_heads=cfg.num_heads, block_attn_patterns=list(pats),
-                                  num_global_vectors=4, use_global_vector_ffn=gffn, use_global_self_attn=True)
+                                  num_global_vectors=4, use_global_vector_ffn=gffn, use_global_self_attn=gsa,
+                                  separate_global_qkv=sep)
+        assert any(".g2g_global_qkv_net." in n for n, _ in Wt.unet_param_spec(cfg)) == (sep and gsa)
+        assert any(".global_qkv." in n for n, _ in Wt.unet_param_spec(cfg)) == (not sep)
         spec = [(n, tuple(s)) for n, s in Wt.unet_param_spec(cfg)]
         assert spec[0] == ("init_global_vectors", (4, 64))
         assert m.weight_spec_from_library() == spec
@@ -111,7 +116,7 @@ def test_unsupported_configs_fail_loudly():
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], block_attn_patterns="video_swin_3x5")  # not registered
     with pytest.raises(NotImplementedError):
         CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], padding_type="reflect")   # not one of the reference's three
-    for kw in (dict(num_global_vectors=8, separate_global_qkv=True), dict(num_global_vectors=8, global_dim_ratio=2),
+    for kw in (dict(num_global_vectors=8, separate_global_qkv=True, global_dim_ratio=2), dict(num_global_vectors=8, global_dim_ratio=2),
                dict(num_global_vectors=33), dict(num_global_vectors=8, precision="tf32")):
         with pytest.raises(NotImplementedError):
             CuboidTransformerUNet([7, 16, 16, 64], [6, 16, 16, 64], **kw)

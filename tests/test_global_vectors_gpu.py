@@ -148,12 +148,83 @@ def test_axial_attention_with_global_keys_vs_oracle_and_general_kernel(axis, T, 
     assert r2 < 6e-3 and m2 < 1.5e-2, (r2, m2)
 
 
+# separate_global_qkv=True: (dims, heads, head_dim, cuboid, strategy, shift, padding, K, self-attention, line kernel)
+SEP_CASES = [
+    ((13, 16, 16), 4, 64, (13, 1, 1), "lll", (0, 0, 0), "zeros", 8, True, True),      # shipped flags on an axial layer
+    ((13, 8, 8), 4, 128, (1, 1, 8), "lll", (0, 0, 0), "zeros", 16, False, True),
+    ((13, 16, 16), 4, 64, (13, 1, 1), "lll", (0, 0, 0), "zeros", 8, True, False),     # the same layer through the general kernel
+    ((13, 16, 16), 4, 64, (4, 4, 4), "lll", (2, 2, 2), "ignore", 4, True, False),
+    ((13, 8, 8), 4, 128, (2, 8, 8), "lll", (1, 4, 4), "ignore", 32, True, False),     # two key chunks + 32 global keys
+    ((6, 7, 9), 2, 16, (4, 3, 4), "ldl", (2, 1, 2), "nearest", 3, False, False),
+    ((13, 8, 8), 4, 32, (2, 4, 4), "ddd", (0, 0, 0), "zeros", 5, True, False),
+]
+
+
+@pytest.mark.parametrize("case", SEP_CASES, ids=[f"{c[0]}-hd{c[2]}-{c[3]}-{c[4]}-{c[5]}-{c[6]}-K{c[7]}-{int(c[8])}-{int(c[9])}" for c in SEP_CASES])
+def test_separate_global_qkv_op_vs_oracle(case):
+    dims, heads, hd, size, strat, shift, pad, K, gsa, line = case
+    C, B = heads * hd, 2
+    g = torch.Generator().manual_seed(29)
+    qkv = torch.randn(B, *dims, 3 * C, generator=g).bfloat16()
+    tok2 = torch.randn(B, *dims, 3 * C, generator=g).bfloat16()                    # l2g_q | g2l_k | g2l_v
+    ld = (6 if gsa else 3) * C
+    grow = torch.randn(B, K, ld, generator=g).bfloat16().float()                   # l2g_k | l2g_v | g2l_q [| g2g_q | g2g_k | g2g_v]
+    n_rel = (2 * size[0] - 1) * (2 * size[1] - 1) * (2 * size[2] - 1)
+    table = 0.5 * torch.randn(n_rel, heads, generator=g)
+    out = torch.full((B, *dims, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gout = torch.full((B, K, C), float("nan"), device="cuda")
+    qd, t2d, td, gd, gd16 = qkv.cuda(), tok2.cuda(), table.cuda(), grow.cuda(), grow.bfloat16().cuda()
+    L.check(L.lib().pd_op_cuboid_attention_gv2(L.ptr(qd), L.ptr(td), L.ptr(t2d), L.ptr(gd), L.ptr(gd16), ld, L.ptr(out), L.ptr(gout),
+                                               B, *dims, C, heads, I3(*size), I3(*[0 if s == "l" else 1 for s in strat]), I3(*shift),
+                                               {"zeros": 0, "ignore": 1, "nearest": 2}[pad], K, int(gsa), int(line), L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref, gref = O.cuboid_attention_core(qkv.float(), table, heads, size, tuple(strat), shift, pad, global_self_attn=gsa,
+                                        sep=(tok2.float(), grow))
+    assert torch.isfinite(out.float()).all() and torch.isfinite(gout).all()
+    r, m = errs(out.float(), ref)
+    rg, mg = errs(gout, gref)
+    print(f"separate global nets {case}: grid rel_rms={r:.2e} max={m:.2e}; global vectors rel_rms={rg:.2e} max={mg:.2e}")
+    assert r < 6e-3 and m < 1e-2, (r, m)
+    assert rg < 2e-5 and mg < 2e-5, (rg, mg)
+
+
+GVS = np.load(os.path.join(os.path.dirname(__file__), "golden", "global_vectors_sep.npz"))
+
+
+@pytest.mark.parametrize("case", PC.GV_SEP_UNET_CASES, ids=[c[0] for c in PC.GV_SEP_UNET_CASES])
+def test_unet_separate_global_qkv_vs_reference_golden(case):
+    cfg = dataclasses.replace(gv_cfg(case), separate_global_qkv=True)
+    m, _ = make_unet(cfg)
+    x = inp(1234, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda()
+    cond = inp(1235, 2, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()
+    out = m(x, torch.tensor([500, 37], device="cuda"), cond)
+    rel_rms, mx = errs(out, GVS[f"unet_{case[0]}"])
+    print(f"unet {case[0]}: rel_rms={rel_rms:.2e} max={mx:.2e}")
+    assert rel_rms < REL_RMS_TOL and mx < MAX_TOL, (rel_rms, mx)
+
+
+def test_unet_shipped_flags_with_global_vectors_vs_oracle():
+    """The shipped cfg.yaml's global-vector flags (separate_global_qkv: true, use_global_self_attn: true,
+    use_global_vector_ffn: false) with num_global_vectors turned on, at the shipped widths."""
+    cfg = dataclasses.replace(Wt.UNetConfig(depth=(1, 1)), num_global_vectors=8, use_global_vector_ffn=False,
+                              use_global_self_attn=True, separate_global_qkv=True)
+    m, sd = make_unet(cfg)
+    x, cond, t = inp(31, 2, cfg.t_out, cfg.h, cfg.w, cfg.c), inp(32, 2, cfg.t_in, cfg.h, cfg.w, cfg.c), torch.tensor([981, 3])
+    out = m(x.cuda(), t.cuda(), cond.cuda())
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, x, t, cond)
+    rel_rms, mx = errs(out, ref)
+    print(f"unet shipped global flags (256 / 512): rel_rms={rel_rms:.2e} max={mx:.2e}")
+    assert rel_rms < REL_RMS_TOL and mx < MAX_TOL, (rel_rms, mx)
+    assert torch.equal(m(x[1:].cuda(), t[1:].cuda(), cond[1:].cuda())[0], out[1])
+
+
 def make_unet(cfg, max_batch=2):
     m = CuboidTransformerUNet(input_shape=[cfg.t_in, cfg.h, cfg.w, cfg.c], target_shape=[cfg.t_out, cfg.h, cfg.w, cfg.c],
                               base_units=cfg.base_units, depth=list(cfg.depth), num_heads=cfg.num_heads,
                               block_attn_patterns=list(cfg.patterns), padding_type=cfg.padding_type, max_batch=max_batch,
                               num_global_vectors=cfg.num_global_vectors, use_global_vector_ffn=cfg.use_global_vector_ffn,
-                              use_global_self_attn=cfg.use_global_self_attn)
+                              use_global_self_attn=cfg.use_global_self_attn, separate_global_qkv=cfg.separate_global_qkv)
     sd = O.to_torch_sd(Wt.seeded_state_dict(Wt.unet_param_spec(cfg), UNET_SEED))
     res = m.load_state_dict(sd, strict=False)
     assert not res.unexpected_keys and all(k.endswith("relative_position_index") for k in res.missing_keys)
