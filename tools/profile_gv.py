@@ -22,9 +22,10 @@ for dims, C, size in (((13, 16, 16), 256, (13, 1, 1)), ((13, 8, 8), 512, (1, 8, 
     table = torch.randn(n_rel, heads, generator=g).cuda()
     out = torch.empty(B, *dims, C, device="cuda", dtype=torch.bfloat16)
     gout = torch.empty(B, K, C, device="cuda")
-    for _ in range(3):
-        L.check(L.lib().pd_op_cuboid_attention_gv(L.ptr(qkv), L.ptr(table), L.ptr(gq), L.ptr(gq16), L.ptr(out), L.ptr(gout), B, *dims,
-                                                  C, heads, I3(*size), I3(0, 0, 0), I3(0, 0, 0), 0, K, 1, L.stream_ptr()))
+    for line in (1, 1, 0):   # the line kernel (what the UNet runs for axial layers with K <= 16), then the general kernel
+        L.check(L.lib().pd_op_cuboid_attention_gv2(L.ptr(qkv), L.ptr(table), None, L.ptr(gq), L.ptr(gq16), 3 * C, L.ptr(out),
+                                                   L.ptr(gout), B, *dims, C, heads, I3(*size), I3(0, 0, 0), I3(0, 0, 0), 0, K, 1, line,
+                                                   L.stream_ptr()))
     # the linears of one layer: global_qkv (LayerNorm fused), global_proj, global FFN
     M = B * K
     x = torch.randn(M, C, generator=g).cuda()
