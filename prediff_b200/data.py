@@ -119,7 +119,10 @@ class SEVIRCatalogEvents:
 
     def __getitem__(self, key):
         if isinstance(key, (int, np.integer)):
-            return self[int(key):int(key) + 1][0]
+            k = int(key) + (len(self) if int(key) < 0 else 0)
+            if not 0 <= k < len(self):
+                raise IndexError(f"event {int(key)} out of range for {len(self)} events")
+            return self[k:k + 1][0]
         if not isinstance(key, slice):
             raise TypeError("SEVIRCatalogEvents is indexed by an event number or a slice of event numbers")
         rows = self._samples.iloc[key]

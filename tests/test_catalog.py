@@ -53,6 +53,9 @@ def test_reads_and_windows_equal_the_reference_batches(tag):
     for k in range(len(ev)):
         f, i = str(G[f"{tag}_files"][k]), int(G[f"{tag}_index"][k])
         assert np.array_equal(ev[k], FILES[f]["vil"][i])
+    assert np.array_equal(ev[-1], ev[len(ev) - 1]) and ev[2:2].shape == (0, CC.H, CC.W, CC.T_RAW)
+    with pytest.raises(IndexError):
+        ev[len(ev)]
     n = int(G[f"{tag}_len"])
     n_seq = 1 + (CC.T_RAW - lkw["seq_len"]) // lkw["stride"]
     assert n == (len(ev) * n_seq) // lkw["batch_size"]
