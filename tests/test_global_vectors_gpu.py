@@ -285,3 +285,38 @@ def test_ddim_loop_with_global_vectors_vs_oracle():
     print(f"ddim 5 steps with global vectors: rel_rms={r:.2e} max={mx:.2e}")
     assert r < 1.2e-2 and mx < 2.5e-2
     assert torch.equal(z0, ldm.ddim_sample_loop(cond=cond.cuda(), shape=tuple(z.shape), x_T=z.cuda(), ddim_steps=5, eta=0.0))
+
+
+def test_side_lane_changes_nothing_and_is_repeatable():
+    """The global rows' kernels run on a second plan lane (Plan::lane / mark / wait). Its result must equal the single-stream
+    plan's bit for bit (computed by a child process with PD_NO_GV_LANES=1: the switch is read once per process) and must not
+    vary between replays (a missing dependency between the lanes would show up as run-to-run differences)."""
+    import subprocess
+    import sys
+    import tempfile
+    cfg = dataclasses.replace(Wt.UNetConfig(depth=(1, 1)), num_global_vectors=8, use_global_vector_ffn=True,
+                              use_global_self_attn=True, separate_global_qkv=True)
+    m, _ = make_unet(cfg)
+    x, cond, t = inp(51, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda(), inp(52, 2, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda(), torch.tensor([700, 11]).cuda()
+    first = m(x, t, cond)
+    for _ in range(30):
+        assert torch.equal(m(x, t, cond), first)
+    ldm = LatentDiffusion(torch_nn_module=m)
+    z0 = ldm.ddim_sample_loop(cond=cond, shape=tuple(x.shape), x_T=x, ddim_steps=5, eta=0.0)   # lanes as graph branches
+    for _ in range(5):
+        assert torch.equal(ldm.ddim_sample_loop(cond=cond, shape=tuple(x.shape), x_T=x, ddim_steps=5, eta=0.0), z0)
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "single_lane.pt")
+        code = (
+            "import dataclasses, torch\n"
+            "from prediff_b200 import weights as Wt\n"
+            "from tests.test_global_vectors_gpu import make_unet, inp\n"
+            "cfg = dataclasses.replace(Wt.UNetConfig(depth=(1, 1)), num_global_vectors=8, use_global_vector_ffn=True,\n"
+            "                          use_global_self_attn=True, separate_global_qkv=True)\n"
+            "m, _ = make_unet(cfg)\n"
+            "x, cond = inp(51, 2, cfg.t_out, cfg.h, cfg.w, cfg.c).cuda(), inp(52, 2, cfg.t_in, cfg.h, cfg.w, cfg.c).cuda()\n"
+            f"torch.save(m(x, torch.tensor([700, 11]).cuda(), cond).cpu(), {out!r})\n")
+        env = dict(os.environ, PD_NO_GV_LANES="1")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=root, timeout=600)
+        assert torch.equal(torch.load(out), first.cpu())
