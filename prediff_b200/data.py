@@ -270,3 +270,36 @@ class SEVIRDataLoader:
             j = i + self.prefetch
             if j < nb:
                 self._issue(slots[j % len(slots)], first + j * self.batch_size)
+
+
+class SEVIRTorchDataset(torch.utils.data.Dataset):
+    """Mirror of the reference's torch Dataset wrapper (src/prediff/datasets/sevir/sevir_torch_wrap.py:73-163) for
+    aug_mode "0" (evaluation): item `index` = sequence `index` of the sequent enumeration as a (T, H, W, 1) fp32 tensor in
+    `layout` - here a device tensor produced by the window kernel (the reference returns a host tensor that the Lightning
+    loop then copies to the GPU). Same constructor argument names; the HDF5 opener is injectable like SEVIRCatalogEvents'."""
+
+    def __init__(self, seq_len=25, raw_seq_len=49, sample_mode="sequent", stride=12, layout="THWC", split_mode="uneven",
+                 sevir_catalog=None, sevir_data_dir=None, start_date=None, end_date=None, datetime_filter=None,
+                 catalog_filter="default", shuffle=False, shuffle_seed=1, output_type=np.float32, preprocess=True,
+                 rescale_method="01", verbose=False, aug_mode="0", ret_contiguous=True, open_file=None, device=None):
+        super().__init__()
+        if aug_mode != "0":
+            raise NotImplementedError("prediff_b200.data.SEVIRTorchDataset: augmentation (aug_mode '1' / '2') is a training feature")
+        if output_type not in (np.float32, torch.float32):
+            raise NotImplementedError("prediff_b200.data.SEVIRTorchDataset: fp32 output only")
+        if sorted(layout) != sorted("THWC"):
+            raise ValueError(f"layout {layout!r} must be a permutation of 'THWC'")
+        self.layout, self.ret_contiguous = layout, ret_contiguous
+        self.sevir_dataloader = SEVIRDataLoader.from_catalog(
+            sevir_catalog, sevir_data_dir, start_date=start_date, end_date=end_date, datetime_filter=datetime_filter,
+            catalog_filter=catalog_filter, shuffle=shuffle, shuffle_seed=shuffle_seed, open_file=open_file, verbose=verbose,
+            seq_len=seq_len, raw_seq_len=raw_seq_len, sample_mode=sample_mode, stride=stride, batch_size=1, layout="NTHWC",
+            num_shard=1, rank=0, split_mode=split_mode, preprocess=preprocess, rescale_method=rescale_method, device=device)
+
+    def __getitem__(self, index):
+        data = self.sevir_dataloader._idx_sample(index=index)["vil"].squeeze(0)        # (T, H, W, 1)
+        data = data.permute(*["THWC".index(a) for a in self.layout])
+        return data.contiguous() if self.ret_contiguous else data
+
+    def __len__(self):
+        return len(self.sevir_dataloader)

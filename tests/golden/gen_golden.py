@@ -10,6 +10,7 @@ reference modules with load_state_dict; inputs come from the same kind of stream
 regenerate them bit-exactly anywhere. Only outputs (and small inputs) are stored.
 """
 import argparse
+import datetime
 import os
 import sys
 import time
@@ -257,6 +258,17 @@ def gen_catalog():
             out[f"{tag}_files_epoch2"] = np.asarray([str(v) for v in dl._samples["vil_filename"].values])
             out[f"{tag}_index_epoch2"] = np.asarray(dl._samples["vil_index"].values, dtype=np.int64)
         print(f"catalog {tag}: {len(dl._samples)} events, {len(dl)} batches")
+    # the torch Dataset wrapper the Lightning datamodule hands to its DataLoaders (sevir_torch_wrap.py:73-163), aug_mode "0"
+    sys.modules["lightning"].LightningDataModule = type("LightningDataModule", (), {})
+    sys.modules["lightning"].seed_everything = lambda *a, **k: None
+    from prediff.datasets.sevir.sevir_torch_wrap import SEVIRTorchDataset
+    for tag, layout in (("thwc", "THWC"), ("cthw", "CTHW")):
+        ds = SEVIRTorchDataset(seq_len=13, raw_seq_len=CC.T_RAW, stride=6, layout=layout, sevir_catalog=CC.catalog_frame(),
+                               sevir_data_dir="/data", rescale_method="01", start_date=datetime.datetime(2019, 2, 1))
+        out[f"ds_{tag}_len"] = np.asarray(len(ds))
+        for i in range(len(ds)):
+            out[f"ds_{tag}_{i}"] = ds[i].numpy()
+        print(f"catalog dataset {layout}: {len(ds)} items of shape {tuple(ds[0].shape)}")
     save("catalog", **out)
 
 

@@ -105,3 +105,24 @@ def test_loader_from_catalog_matches_reference_loader(tag):
         assert np.array_equal(dl._idx_sample(i)["vil"].cpu().numpy(), g[f"{tag}_b{i}"])
     for i, b in enumerate(dl):   # the prefetching iterator reads through the catalog layer too
         assert np.array_equal(b.cpu().numpy(), g[f"{tag}_b{i}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,layout", [("thwc", "THWC"), ("cthw", "CTHW")])
+def test_torch_dataset_wrapper_matches_reference(tag, layout):
+    """SEVIRTorchDataset (sevir_torch_wrap.py:73-163, aug_mode "0") item by item against the unmodified reference class."""
+    import datetime
+    from prediff_b200.data import SEVIRTorchDataset
+    from tests.golden import catalog_cases as CC
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "catalog.npz"))
+    files = CC.catalog_files()
+    ds = SEVIRTorchDataset(seq_len=13, raw_seq_len=CC.T_RAW, stride=6, layout=layout, sevir_catalog=CC.catalog_frame(),
+                           sevir_data_dir="/data", rescale_method="01", start_date=datetime.datetime(2019, 2, 1),
+                           open_file=lambda p: files[p[len("/data/"):]])
+    assert len(ds) == int(g[f"ds_{tag}_len"])
+    for i in range(len(ds)):
+        item = ds[i]
+        assert item.is_cuda and item.is_contiguous()
+        assert np.array_equal(item.cpu().numpy(), g[f"ds_{tag}_{i}"])
+    with pytest.raises(NotImplementedError):
+        SEVIRTorchDataset(sevir_catalog=CC.catalog_frame(), sevir_data_dir="/data", aug_mode="1")
