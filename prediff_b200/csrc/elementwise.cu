@@ -163,44 +163,61 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
     }
 }
 
-// VAE encoder conv_in: single input channel, 3x3, pad 1 - write-bound (4 * Cout bytes per pixel out, 4 bytes in). One
-// thread per (pixel, 4 output channels): the 32 lanes of a warp share a pixel (its 9 taps are broadcast loads) and write
-// 512 contiguous bytes; the weights sit in shared memory as [tap][Cout] so a lane's four channels are one LDS.128 per tap.
-// (Round 1 read its 36 weights per thread through __ldg with a 36-byte stride: 541 us for 28 frames = 5 % of the HBM
-// peak, profiles/ncu_r02_vae_summary.txt.)
+// VAE encoder conv_in: single input channel, 3x3, pad 1 - write-bound (4 * Cout bytes per pixel out, 4 bytes in). A thread
+// owns 4 output channels (fixed for its lifetime: the 36 weights + bias live in registers) and walks segments of 8 pixels
+// along W: the segment's 3 x 10 input window is loaded once (broadcast across the 32 lanes that share the segment), every
+// pixel is 36 FMAs and one 16-byte store, a warp writing 512 contiguous bytes per pixel. (Round 1 read its 36 weights per
+// thread through __ldg with a 36-byte stride: 541 us for 28 frames = 5 % of the HBM peak; the first rewrite - one pixel per
+// thread, weights from shared memory per tap - was bound by its 45 load wavefronts per 512 bytes stored: 193 us, 14 %.)
+constexpr int kC1Seg = 8;
 __global__ void __launch_bounds__(kEwThreads) conv3x3_c1_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, float* __restrict__ y,
                                                                    int F, int H, int W, int Cout) {
-    extern __shared__ float s_w[];   // [9][Cout] + bias [Cout]
-    for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
-        const int tap = i / Cout, c = i - tap * Cout;
-        s_w[i] = w[(size_t)c * 9 + tap];
+    const int c4n = Cout >> 2;                          // blockDim.x and the grid stride are multiples of c4n (host check)
+    const int c = (threadIdx.x % c4n) * 4;
+    float wr[9][4], br[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        br[k] = bias[c + k];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[t][k] = w[(size_t)(c + k) * 9 + t];
     }
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[9 * Cout + i] = bias[i];
     grid_dep_launch();
     grid_dep_wait();
-    __syncthreads();
-    const int c4n = Cout >> 2;
-    const int64_t total = (int64_t)F * H * W * c4n;
+    const int segs = (W + kC1Seg - 1) / kC1Seg;
+    const int64_t total = (int64_t)F * H * segs * c4n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % c4n) * 4;
         int64_t pos = i / c4n;
-        const int px = (int)(pos % W); pos /= W;
+        const int px0 = (int)(pos % segs) * kC1Seg; pos /= segs;
         const int py = (int)(pos % H);
         const int f = (int)(pos / H);
-        float4 acc = *reinterpret_cast<const float4*>(s_w + 9 * Cout + c);
         const float* xf = x + (size_t)f * H * W;
+        float win[3][kC1Seg + 2];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py + ky - 1;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int yy = py + ky - 1, xx = px + kx - 1;
-                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xf + (size_t)yy * W + xx) : 0.f;
-                const float4 ww = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * Cout + c);
-                acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y);
-                acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
+            for (int j = 0; j < kC1Seg + 2; ++j) {
+                const int xx = px0 + j - 1;
+                win[ky][j] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xf + (size_t)yy * W + xx) : 0.f;
             }
-        reinterpret_cast<float4*>(y)[i] = acc;
+        }
+        float4* out = reinterpret_cast<float4*>(y + (((size_t)f * H + py) * W + px0) * Cout + c);
+#pragma unroll
+        for (int p = 0; p < kC1Seg; ++p) {
+            if (px0 + p < W) {
+                float a0 = br[0], a1 = br[1], a2 = br[2], a3 = br[3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {   // same tap order as before: results are bit-identical
+                        const float v = win[ky][p + kx];
+                        a0 = fmaf(v, wr[ky * 3 + kx][0], a0); a1 = fmaf(v, wr[ky * 3 + kx][1], a1);
+                        a2 = fmaf(v, wr[ky * 3 + kx][2], a2); a3 = fmaf(v, wr[ky * 3 + kx][3], a3);
+                    }
+                out[(size_t)p * c4n] = make_float4(a0, a1, a2, a3);
+            }
+        }
     }
 }
 
@@ -354,9 +371,10 @@ int small_linear(const float* in, const float* W, const float* bias, float* out,
 int conv3x3_c1_in(const float* x, const float* w, const float* bias, float* y, int F, int H, int W, int Cout,
                   cudaStream_t st) {
     PD_CHECK(Cout % 4 == 0, PD_ERR_SHAPE, "conv3x3_c1_in: Cout=%d", Cout);
-    const int64_t total = (int64_t)F * H * W * (Cout / 4);
-    PD_CHECK(Cout <= 1024, PD_ERR_SHAPE, "conv3x3_c1_in: Cout=%d", Cout);
-    PD_LAUNCH(conv3x3_c1_in_kernel, ew_blocks(total), kEwThreads, (size_t)10 * Cout * sizeof(float), st, x, w, bias, y, F, H, W, Cout);
+    const int64_t total = (int64_t)F * H * ceil_div(W, kC1Seg) * (Cout / 4);
+    PD_CHECK(Cout <= 1024 && kEwThreads % (Cout / 4) == 0, PD_ERR_SHAPE, "conv3x3_c1_in: Cout=%d (Cout / 4 must divide %d)", Cout,
+             kEwThreads);
+    PD_LAUNCH(conv3x3_c1_in_kernel, ew_blocks(total), kEwThreads, 0, st, x, w, bias, y, F, H, W, Cout);
     PD_LAUNCH_CHECK();
     return PD_OK;
 }
