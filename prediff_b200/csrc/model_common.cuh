@@ -137,6 +137,18 @@ struct PlanProfile {
 int stamp_globaltimer(unsigned long long* slot, cudaStream_t st);
 
 struct Plan {
+    Plan() = default;
+    Plan(const Plan&) = delete;
+    Plan& operator=(const Plan&) = delete;
+    ~Plan() {   // plans are rebuilt by every finalize() (weight refresh): their streams and events must not pile up
+        if (aux) cudaStreamDestroy(aux);
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_side_join) cudaEventDestroy(ev_side_join);
+        for (cudaEvent_t e : mark_ev)
+            if (e) cudaEventDestroy(e);
+    }
     std::vector<Step> steps;
     std::vector<uint8_t> kinds;
     std::vector<std::string> labels;   // one per step: kernel class + site, for the per-launch trace
